@@ -1,0 +1,249 @@
+/* xcltk_b200.h -- C-ABI of the B200-native basefc / baf counting paths.
+ *
+ * The reference (hxj5/xcltk v0.5.2) is pure Python and has NO plugin / FFI boundary
+ * (SURVEY.md section 8b); the seam this library sits behind is the per-worker counting core
+ *   basefc: fc_features()  xcltk/rdr/fc/core.py:69-148  (fc_fet1 :151-178, check_read :46-62)
+ *   baf:    fc_features()  xcltk/baf/fc/core.py:42-139  (fc_fet1 :143-194, plp_snp :198-247)
+ * together with the pysam calls underneath it (AlignmentFile.fetch, AlignedSegment fields;
+ * call sites listed in SURVEY.md section 8c).  Every entry point below names the reference
+ * code it replaces.  INTEGRATION.md shows the ctypes stub a maintainer adds to
+ * xcltk/rdr/fc/main.py:fc_core and xcltk/baf/fc/main.py:afc_core.
+ *
+ * Conventions: plain pointers + sizes, little-endian, no exceptions across the boundary.
+ * Return 0 on success, a negative code on error (mirrors the reference's "errcode -N"
+ * convention, xcltk/rdr/fc/main.py:283-292); xg_last_error() gives the message.
+ * There is NO CPU fallback: device entry points fail with XG_E_CUDA when no B200 is present.
+ * One xg_ctx per GPU; a context is not thread-safe, distinct contexts may be used from
+ * distinct host threads concurrently.
+ */
+#ifndef XCLTK_B200_H
+#define XCLTK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XG_OK 0
+#define XG_E_ARG (-1)     /* bad argument                                            */
+#define XG_E_IO (-2)      /* file cannot be read / is not a BAM                      */
+#define XG_E_FORMAT (-3)  /* corrupt BGZF/BAM, or BAM not coordinate sorted          */
+#define XG_E_NOMEM (-4)
+#define XG_E_CUDA (-5)    /* CUDA error or no device: the product path has no CPU fallback */
+#define XG_E_LIMIT (-6)   /* an internal capacity (32-bit offsets ...) would overflow */
+
+/* ---- string keys -------------------------------------------------------------------
+ * Cell barcodes, UMIs and query names are compared by exact string equality in the
+ * reference (dict / set of Python str: rdr/fc/mcount.py:34-43,119-127, baf/fc/mcount.py:109-127).
+ * The device works on lossless 64-bit keys:
+ *   bit63 = 0: the string itself, bit-packed MSB first, 3 bits per character
+ *              (A=1 C=2 G=3 T=4 N=5 '-'=6, 7 = escape followed by a 4-bit decimal digit),
+ *              zero padded; fits e.g. "ACGTACGTACGTACGT-1" and any [ACGTN]{0,21};
+ *   bit63 = 1: (1<<63) | id, id = index of the string in the keyspace's intern table.
+ * Equal strings <=> equal keys within one keyspace.                                     */
+#define XG_KEY_EMPTY 0ULL                       /* tag present, empty string (falsy in Python) */
+#define XG_KEY_NONE 0xFFFFFFFFFFFFFFFFULL       /* tag absent (has_tag() false)              */
+#define XG_KEY_NOMATCH 0xFFFFFFFFFFFFFFFEULL    /* tag present but not a string: equals no barcode */
+
+typedef struct xg_keyspace xg_keyspace;
+xg_keyspace *xg_keyspace_create(void);
+void xg_keyspace_destroy(xg_keyspace *ks);
+uint64_t xg_key_encode(xg_keyspace *ks, const char *s, int64_t len);
+/* Writes the string of `key` into buf (no NUL); returns its length, or -1 if unknown. */
+int64_t xg_key_decode(xg_keyspace *ks, uint64_t key, char *buf, int64_t cap);
+int64_t xg_keyspace_n_interned(xg_keyspace *ks);
+
+/* ---- read records: flat structure-of-arrays -------------------------------------------
+ * What pysam exposes per AlignedSegment to the two paths, one entry per
+ * BAM record that lies on a contig some feature/SNP refers to, in (BAM-list index, file)
+ * order -- the order fetch() yields them in (baf first-read-wins needs it, B4/B5).      */
+typedef struct {
+    int32_t bam_idx;    /* index in the BAM list (= sample column in sample-ID mode)   */
+    int32_t gid;        /* caller's contig id (see tid_map of xg_decode_bams)          */
+    int64_t rec_beg;    /* records [rec_beg, rec_end) are this BAM's reads on this contig, */
+    int64_t rec_end;    /*   sorted by pos (file order)                                */
+} xg_run;
+
+#define XG_TILE 1024    /* max records per tile; tiles never straddle runs */
+typedef struct {
+    int64_t rec_beg;    /* first record of the tile                                    */
+    int32_t n_rec;      /* 1..XG_TILE records                                          */
+    int32_t run;        /* the run all of them belong to                               */
+    int32_t first_pos;  /* pos of the tile's first record                              */
+    int32_t max_end;    /* max bam_endpos over the tile's records                      */
+} xg_tile;
+
+typedef struct {
+    int64_t n_reads;
+    int64_t n_cigar;        /* words in `cigar`                                         */
+    int64_t n_seq_words;    /* words in `seq` (0 when decoded without sequences)        */
+    int32_t n_runs;
+    int32_t n_tiles;        /* sum over runs of ceil(run length / XG_TILE)              */
+    int32_t max_aln_len;    /* max over reads of sum(M,=,X) -- sizes the include table  */
+    int32_t max_span;       /* max over reads of end - pos                              */
+    int64_t n_records_seen; /* all BAM records scanned, incl. dropped contigs/unmapped  */
+    /* per read */
+    const int32_t *pos_end;   /* [2*n] pos (0-based), end = htslib bam_endpos()          */
+    const uint32_t *fmq;      /* flag | mapq<<16 | ncw<<24, ncw = CIGAR words stored:    */
+                              /*   0 = "simple" read (one M/=/X op of length end-pos,     */
+                              /*   nothing stored), 1..254 ops, 255 = true count is in    */
+                              /*   the word before cig_off                                */
+    const uint32_t *cig_off;  /* first CIGAR word of the read in `cigar`                 */
+    const uint64_t *keys;     /* [2*n] cell key, UMI key (UMI tag, or query name)        */
+    const uint32_t *seq_off;  /* first word of the read's 4-bit sequence (NULL if none)  */
+    /* streams */
+    const uint32_t *cigar;    /* BAM CIGAR words (len<<4|op) of the non-simple reads; a  */
+                              /*   record without CIGAR stores one 0-length P op         */
+    const uint32_t *seq;      /* BAM 4-bit bases, 8 per word, each read word-aligned;    */
+                              /*   byte order as in the BAM record                       */
+    const xg_run *runs;
+    const xg_tile *tiles;
+} xg_reads;
+
+/* BAM header access (replaces pysam.AlignmentFile(fn).references; used by the host side to
+ * resolve feature / SNP contig names the way sam_fetch does, xcltk/utils/sam.py:85-118).  */
+typedef struct xg_bam_header xg_bam_header;
+int xg_bam_header_read(const char *path, xg_bam_header **out);
+int32_t xg_bam_header_n_ref(const xg_bam_header *h);
+const char *xg_bam_header_ref_name(const xg_bam_header *h, int32_t tid);
+int64_t xg_bam_header_ref_len(const xg_bam_header *h, int32_t tid);
+void xg_bam_header_free(xg_bam_header *h);
+
+/* Decode BAMs into one xg_reads (replaces pysam.AlignmentFile + AlignedSegment accessors:
+ * rdr/fc/core.py:73-76,154; utils/sam.py:21-27; BGZF inflate is multi-threaded).
+ *   tid_map[b][tid] = caller's contig id (gid) or -1 to drop the contig's reads;
+ *   cell_tag / umi_tag: 2-char tag or NULL; umi_tag NULL => UMI key = query name
+ *   (rdr/fc/mcount.py:36-41); want_seq: also emit 4-bit sequences (baf).
+ * The result is library-owned (pinned host memory when a CUDA device is present).       */
+int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
+                   const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag,
+                   int32_t want_seq, int32_t n_threads, xg_keyspace *ks, xg_reads **out);
+void xg_reads_free(xg_reads *r);
+const char *xg_host_last_error(void);
+
+/* ---- device side --------------------------------------------------------------------- */
+typedef struct xg_ctx xg_ctx;
+typedef struct xg_dreads xg_dreads;      /* read records resident in HBM */
+
+int xg_create(int32_t device, xg_ctx **out);
+void xg_destroy(xg_ctx *ctx);
+const char *xg_last_error(xg_ctx *ctx);
+
+/* Host -> HBM copy of a decoded batch (the only cross-device traffic of the path).      */
+int xg_upload_reads(xg_ctx *ctx, const xg_reads *host, xg_dreads **out);
+/* HBM -> host copy (tests: run the oracle on device-generated records).                 */
+int xg_download_reads(xg_ctx *ctx, const xg_dreads *d, xg_reads **out);
+void xg_dreads_free(xg_ctx *ctx, xg_dreads *d);
+int64_t xg_dreads_n(const xg_dreads *d);
+
+/* Read filters = check_read(), rdr/fc/core.py:46-62 == baf/fc/core.py:18-34.            */
+typedef struct {
+    int32_t min_mapq;      /* ceil(conf.min_mapq): mapq < x  <=>  mapq < ceil(x)          */
+    int32_t min_len;       /* len(read.positions) >= min_len                              */
+    uint32_t incl_flag;    /* 0 disables                                                  */
+    uint32_t excl_flag;    /* 0 disables                                                  */
+    int32_t no_orphan;     /* drop PAIRED & !PROPER_PAIR                                  */
+    int32_t use_cell_tag;  /* barcode mode: cell key must be present and listed           */
+    int32_t need_umi_tag;  /* conf.umi_tag set: has_tag(umi) required                     */
+    /* include test, rdr/fc/core.py:160-165 (basefc only):
+     * keep iff m >= min_incl_tab[n] (n = aligned length) when the table is given
+     * (fraction mode; built by the caller with the reference's own float expression),
+     * else iff m >= min_incl_len.                                                        */
+    const int32_t *min_incl_tab;
+    int32_t min_incl_tab_len;
+    int32_t min_incl_len;
+} xg_params;
+
+/* Features (basefc) / regions (baf): 0-based half-open [beg, end) on contig gid,
+ * gid < 0 or end <= beg => never fetched (unknown contig, start <= 0: utils/sam.py:105-118). */
+typedef struct {
+    int32_t n;
+    const int32_t *gid;
+    const int32_t *beg;
+    const int32_t *end;
+} xg_features;
+
+/* Cell barcodes (barcode mode): keys of conf.samples in column order; n = 0 => sample-ID
+ * mode, column = xg_run.bam_idx (rdr/fc/core.py:166-170).                                */
+typedef struct {
+    int32_t n;
+    const uint64_t *keys;
+    int32_t n_samples;     /* number of columns (= n in barcode mode, #BAMs otherwise)    */
+} xg_barcodes;
+
+/* Sparse result, sorted by (row, col), 0-based; library-owned host memory.               */
+typedef struct {
+    int64_t nnz;
+    int32_t n_rows, n_cols;
+    const int32_t *row;
+    const int32_t *col;
+    const int32_t *val;
+    const int64_t *row_ptr;   /* CSR offsets, n_rows + 1 */
+} xg_coo;
+void xg_coo_free(xg_coo *m);
+
+/* basefc: replaces the per-feature loop fc_features()/fc_fet1() (rdr/fc/core.py:96-124,151-178)
+ * and MCount/SCount (rdr/fc/mcount.py): out[row f, col c] = number of distinct UMI keys among
+ * the reads of cell c that overlap feature f and pass check_read + the include test.     */
+int xg_basefc(xg_ctx *ctx, const xg_dreads *reads, const xg_features *feats,
+              const xg_barcodes *cells, const xg_params *par, xg_coo **out);
+
+/* baf phase 1: replaces plp_snp() up to mcnt.stat() (baf/fc/core.py:198-237; first-read-wins
+ * per (SNP, cell, UMI): baf/fc/mcount.py:109-127; allele: :39-60 + utils/sam.py:4-40).
+ * totals[5*i .. 5*i+4] = A,C,G,T,N bucket counts of SNP i over all listed cells.          */
+typedef struct {
+    int32_t n;
+    const int32_t *gid;
+    const int32_t *pos;        /* 0-based */
+} xg_snps;
+typedef struct xg_baf_state xg_baf_state;
+int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *reads, const xg_snps *snps,
+                  const xg_barcodes *cells, const xg_params *par,
+                  int64_t *totals, xg_baf_state **state);
+/* baf phase 2: replaces fc_fet1() aggregation + emit (baf/fc/core.py:143-194, 84-113).
+ *   hap_of[8*i + code] for SNP i and base code (0..4 = A,C,G,T,N; 5 = other / IUPAC) is the
+ *   region haplotype index 0 / 1, or 2 for "other allele", as SNP.get_region_allele_index
+ *   gives (baf/fc/gfeature.py:38-39); keep[i] = 0 drops the SNP (plp_snp filter :238-246,
+ *   evaluated by the caller in Python for float exactness);
+ *   region r's SNPs are reg_snp[reg_ptr[r] .. reg_ptr[r+1]).
+ * Outputs AD / DP / OTH as in fc_features' emit loop (rows = regions, cols = cells).      */
+int xg_baf_count(xg_ctx *ctx, xg_baf_state *state, int32_t n_regions, const int64_t *reg_ptr,
+                 const int32_t *reg_snp, const uint8_t *hap_of, const uint8_t *keep,
+                 int32_t no_dup_hap, xg_coo **ad, xg_coo **dp, xg_coo **oth);
+void xg_baf_state_free(xg_ctx *ctx, xg_baf_state *state);
+
+/* Synthetic 10x-style records generated directly in HBM (bench / tests; no reference
+ * counterpart -- SURVEY.md 8(d) C3 allows device-side generation for kernel-only runs).  */
+typedef struct {
+    int64_t n_reads;
+    int32_t n_cells;          /* listed barcodes; 5% of molecules carry an unlisted one   */
+    int32_t read_len;
+    int32_t want_seq;
+    uint64_t seed;
+    /* reads are spread uniformly over the union of these spans (sorted, disjoint), per contig */
+    int32_t n_spans;
+    const int32_t *span_gid;
+    const int32_t *span_beg;
+    const int32_t *span_end;
+    /* optional SNP table so that bases at SNPs are haplotype consistent */
+    int32_t n_snps;
+    const int32_t *snp_gid;
+    const int32_t *snp_pos;
+    const uint8_t *snp_ref;   /* base codes 0..3 */
+    const uint8_t *snp_alt;
+    const uint8_t *snp_ref_hap;
+} xg_synth_params;
+int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *p, xg_dreads **out, uint64_t *barcode_keys);
+
+/* Timing of the last xg_basefc / xg_baf_* call, measured with CUDA events on the
+ * library's stream: [0] all kernels of the call (ms), [1] dominant counting kernel (ms),
+ * [2] number of kernel launches, [3] H2D ms, [4] D2H ms.                                  */
+void xg_last_timing(xg_ctx *ctx, double out[8]);
+
+const char *xg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by running the UNMODIFIED reference on the pysam shim.
+
+ORACLE / TEST INFRASTRUCTURE ONLY.  Runs in the build container only (needs
+/root/reference); the GPU box sees just the committed fixtures.  Usage:
+
+    python oracle/make_golden.py [case ...]
+
+Each case directory holds its inputs (small BAMs written by xcltk_b200.synth, barcode /
+feature / SNP files), `case.json` (the runs: wrapper kwargs) and
+`expected/<run>/` = the reference's output files, byte for byte
+(rdr: features.tsv barcodes.tsv matrix.mtx -- xcltk/rdr/fc/main.py:378-383;
+ baf: xcltk.region.tsv xcltk.samples.tsv xcltk.{AD,DP,OTH}.mtx -- xcltk/baf/fc/main.py:373-379).
+"""
+
+import json
+import os
+import random
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from xcltk_b200 import synth  # noqa: E402
+
+
+def _reference_modules():
+    for p in (os.path.join(HERE, "shim"), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import logging
+    logging.disable(logging.CRITICAL)
+    from xcltk.rdr.fc.main import fc_wrapper
+    from xcltk.baf.fc.main import afc_wrapper
+    return fc_wrapper, afc_wrapper
+
+
+def resolve_run(case_dir, case, run):
+    """Merge case-level defaults with per-run overrides; make paths absolute."""
+    g = dict(case.get("defaults", {}))
+    g.update({k: v for k, v in run.items() if k in ("sam", "barcodes", "features", "snps", "kind")})
+    kw = {}
+    for k, v in run.get("kwargs", {}).items():
+        if isinstance(v, str) and v.startswith("@"):
+            v = os.path.join(case_dir, v[1:])
+        kw[k] = v
+    ab = lambda x: os.path.join(case_dir, x) if x else None
+    return dict(kind=g["kind"], sam=[ab(x) for x in g["sam"]], barcodes=ab(g.get("barcodes")),
+                features=ab(g["features"]), snps=ab(g.get("snps")), kwargs=kw)
+
+
+def run_reference(case_dir, case, run, out_dir):
+    """Run one `run` entry of case.json with the reference; returns its return code."""
+    fc_wrapper, afc_wrapper = _reference_modules()
+    r = resolve_run(case_dir, case, run)
+    devnull = open(os.devnull, "w")
+    old = sys.stderr
+    sys.stderr = devnull
+    try:
+        if r["kind"] == "basefc":
+            ret = fc_wrapper(",".join(r["sam"]), r["barcodes"], r["features"], out_dir, **r["kwargs"])
+        else:
+            ret = afc_wrapper(",".join(r["sam"]), r["barcodes"], r["features"], r["snps"], out_dir,
+                              **r["kwargs"])
+    finally:
+        sys.stderr = old
+        devnull.close()
+    return ret
+
+
+def finish_case(case_dir, case):
+    with open(os.path.join(case_dir, "case.json"), "w") as fp:
+        json.dump(case, fp, indent=1, sort_keys=True)
+        fp.write("\n")
+    exp = os.path.join(case_dir, "expected")
+    shutil.rmtree(exp, ignore_errors=True)
+    os.makedirs(exp)
+    for run in case["runs"]:
+        out = os.path.join(exp, run["name"])
+        ret = run_reference(case_dir, case, run, out)
+        with open(os.path.join(out, "RETCODE"), "w") as fp:
+            fp.write("%d\n" % ret)
+        left = sorted(f for f in os.listdir(out) if "pickle" in f or f[-1].isdigit())
+        assert not left, left
+        print("  %-28s ret=%d  %s" % (run["name"], ret, summarize(out)))
+
+
+def summarize(out):
+    s = []
+    for f in sorted(os.listdir(out)):
+        if f.endswith(".mtx"):
+            with open(os.path.join(out, f)) as fp:
+                lines = fp.read().splitlines()
+            s.append("%s[%s]" % (f.replace("xcltk.", ""), lines[2].replace("\t", ",")))
+    return " ".join(s)
+
+
+def fresh(name):
+    d = os.path.join(GOLD, name)
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    return d
+
+
+def seq_with(L, overrides):
+    s = ["A"] * L
+    for i, b in overrides.items():
+        s[i] = b
+    return "".join(s)
+
+
+# ------------------------------------------------------------------ mini cases
+def case_d1():
+    d = fresh("d1_basefc_mini")
+    M, N, S = 0, 3, 4
+
+    def r(name, pos, flag, mapq, cigar, cb, ub, L=40):
+        tags = []
+        if cb is not None:
+            tags.append(("CB", "Z", cb))
+        if ub is not None:
+            tags.append(("UB", "Z", ub))
+        return (name, flag, 0, pos, mapq, cigar, "A" * L, tags)
+
+    recs = [
+        r("r1", 100, 0, 255, [(M, 40)], "BBB", "U1"),
+        r("r2", 100, 0, 255, [(M, 40)], "BBB", "U1"),
+        r("r3", 105, 0, 255, [(M, 40)], "AAA", "U1"),
+        r("r6", 120, 0, 10, [(M, 40)], "AAA", "U4"),
+        r("r7", 120, 256, 255, [(M, 40)], "AAA", "U5"),
+        r("r8", 120, 0, 255, [(M, 40)], "ZZZ", "U6"),
+        r("r9", 120, 0, 255, [(M, 40)], "AAA", None),
+        r("r10", 120, 0, 255, [(S, 15), (M, 25)], "AAA", "U7"),
+        r("r11", 120, 1, 255, [(M, 40)], "AAA", "U8"),
+        r("r12", 120, 2048, 255, [(M, 40)], "AAA", "U9"),
+        r("r13", 120, 0, 255, [(M, 40)], "AAA", ""),
+        r("r4", 170, 0, 255, [(M, 40)], "AAA", "U2"),
+        r("r5", 180, 0, 255, [(M, 20), (N, 500), (M, 20)], "AAA", "U3"),
+    ]
+    recs.sort(key=lambda x: x[3])
+    synth.write_bam(os.path.join(d, "a.bam"), [("chr1", 100000)], recs)
+    synth.write_lines(os.path.join(d, "barcodes.tsv"), ["BBB", "AAA"])
+    with open(os.path.join(d, "features.tsv"), "w") as fp:
+        fp.write("chr1\t175\t400\tg2\n1\t101\t200\tg1\nchr1\t600\t800\tg3\n"
+                 "chr1\t0\t50\tg0\nchrQ\t1\t100\tgq\n")
+    case = {"defaults": {"kind": "basefc", "sam": ["a.bam"], "barcodes": "barcodes.tsv",
+                         "features": "features.tsv"}, "runs": [
+                {"name": "defaults", "kwargs": {}},
+                {"name": "min_include_20", "kwargs": {"min_include": 20}},
+                {"name": "umi_none", "kwargs": {"umi_tag": "None"}},
+                {"name": "min_include_0", "kwargs": {"min_include": 0}},
+                {"name": "min_include_1.0", "kwargs": {"min_include": 1.0}},
+                {"name": "frac_0.5_mapq0_len1", "kwargs": {"min_include": 0.5, "min_mapq": 0, "min_len": 1}},
+                {"name": "no_all_reg", "kwargs": {"output_all_reg": False}},
+                {"name": "incl_flag_16", "kwargs": {"incl_flag": 16}},
+                {"name": "count_orphan", "kwargs": {"no_orphan": False}},
+                {"name": "ncores3", "kwargs": {"ncores": 3}},
+                {"name": "mapq_float", "kwargs": {"min_mapq": 9.5}},
+            ]}
+    finish_case(d, case)
+
+
+def case_d2():
+    d = fresh("d2_baf_mini")
+    M, N = 0, 3
+
+    def r(name, pos, cigar, cb, ub, ov, L=40):
+        L = sum(l for op, l in cigar if op in (0, 1, 4, 7, 8))
+        return (name, 0, 0, pos, 255, cigar, seq_with(L, ov), [("CB", "Z", cb), ("UB", "Z", ub)])
+
+    recs = [
+        r("a1", 100, [(M, 10), (N, 30), (M, 30)], "AAA", "U1", {}),
+        r("a2", 105, [(M, 40)], "AAA", "U1", {14: "T"}),
+        r("b1", 110, [(M, 40)], "AAA", "U2", {9: "C", 39: "G"}),
+        r("c1", 112, [(M, 40)], "AAA", "U3", {7: "T"}),
+        r("d1", 115, [(M, 40)], "BBB", "U4", {4: "G", 34: "C"}),
+        r("e1", 118, [(M, 30)], "BBB", "U5", {1: "N"}),
+        r("f1", 145, [(M, 40)], "BBB", "U6", {4: "G"}),
+    ]
+    synth.write_bam(os.path.join(d, "a.bam"), [("1", 100000)], recs)
+    synth.write_lines(os.path.join(d, "barcodes.tsv"), ["AAA", "BBB"])
+    with open(os.path.join(d, "features.tsv"), "w") as fp:
+        fp.write("1\t101\t400\tg1\n1\t500\t600\tg_nosnp\n1\t130\t160\tg_nested\n")
+    with open(os.path.join(d, "snps.tsv"), "w") as fp:
+        fp.write("chrom\tpos\tref\talt\tref_hap\talt_hap\n"
+                 "1\t120\tC\tT\t0\t1\n1\t150\tG\tA\t1\t0\n1\t550\tA\tC\t0\t1\n")
+    with open(os.path.join(d, "snps.vcf"), "w") as fp:
+        fp.write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\n"
+                 "chr1\t120\t.\tc\tT\t.\tPASS\t.\tGT:AD\t0|1:3\n"
+                 "1\t150\t.\tG\tA\t.\tPASS\t.\tAD:GT\t3:1/0\n"
+                 "1\t550\t.\tA\tC\t.\tPASS\t.\tGT\t0|1\n"
+                 "1\t151\t.\tA\tCT\t.\tPASS\t.\tGT\t0|1\n"
+                 "1\t152\t.\tA\tC\t.\tPASS\t.\tGT\t1|1\n"
+                 "1\t153\t.\tA\tC\t.\tPASS\t.\tDP\t4\n")
+    case = {"defaults": {"kind": "baf", "sam": ["a.bam"], "barcodes": "barcodes.tsv",
+                         "features": "features.tsv", "snps": "snps.tsv"}, "runs": [
+                {"name": "defaults", "kwargs": {}},
+                {"name": "dup_hap_all_reg", "kwargs": {"no_dup_hap": False, "output_all_reg": True}},
+                {"name": "min_count_6", "kwargs": {"min_count": 6}},
+                {"name": "min_count_5", "kwargs": {"min_count": 5, "output_all_reg": True}},
+                {"name": "min_maf_0.3", "kwargs": {"min_maf": 0.3, "output_all_reg": True}},
+                {"name": "vcf", "snps": "snps.vcf", "kwargs": {"output_all_reg": True}},
+                {"name": "umi_none", "kwargs": {"umi_tag": "None", "output_all_reg": True}},
+                {"name": "ncores2", "kwargs": {"ncores": 2, "output_all_reg": True}},
+            ]}
+    finish_case(d, case)
+
+
+def case_d3():
+    d = fresh("d3_sample_mode")
+    M = 0
+
+    def r(name, pos, flag, ov, tags=()):
+        return (name, flag, 0, pos, 255, [(M, 40)], seq_with(40, ov), list(tags))
+
+    w1 = [r("q1", 100, 99, {19: "C"}), r("q2", 100, 355, {}), r("q1", 110, 147, {9: "T"})]
+    w2 = [r("q1", 100, 83, {19: "T"}), r("q9", 100, 1123, {})]
+    tg = [("CB", "Z", "AAA"), ("UB", "Z", "U1")]
+    p1 = [r("x1", 105, 0, {14: "T"}, tg)]
+    p2 = [r("x2", 100, 0, {19: "C"}, tg)]
+    for nm, recs in (("w1", w1), ("w2", w2), ("p1", p1), ("p2", p2)):
+        synth.write_bam(os.path.join(d, nm + ".bam"), [("1", 100000)], recs)
+    synth.write_lines(os.path.join(d, "barcodes.tsv"), ["AAA"])
+    synth.write_lines(os.path.join(d, "sample_ids.tsv"), ["cellB", "cellA"])
+    with open(os.path.join(d, "features.tsv"), "w") as fp:
+        fp.write("1\t101\t200\tg1\n")
+    with open(os.path.join(d, "snps.tsv"), "w") as fp:
+        fp.write("chrom\tpos\tref\talt\tref_hap\talt_hap\n1\t120\tC\tT\t0\t1\n")
+    nb = {"cell_tag": None, "umi_tag": None}
+    case = {"defaults": {"sam": ["w1.bam", "w2.bam"], "barcodes": None, "features": "features.tsv",
+                         "snps": "snps.tsv"}, "runs": [
+        {"name": "rdr_ids", "kind": "basefc", "kwargs": dict(nb, sample_ids="cellB,cellA")},
+        {"name": "rdr_default_ids", "kind": "basefc", "kwargs": dict(nb)},
+        {"name": "rdr_ids_file", "kind": "basefc", "kwargs": dict(nb, sample_id_fn="@sample_ids.tsv")},
+        {"name": "rdr_pooled_p1p2", "kind": "basefc", "sam": ["p1.bam", "p2.bam"],
+         "barcodes": "barcodes.tsv", "kwargs": {}},
+        {"name": "baf_ids", "kind": "baf", "kwargs": dict(nb, sample_ids="cellB,cellA")},
+        {"name": "baf_p1p2", "kind": "baf", "sam": ["p1.bam", "p2.bam"], "barcodes": "barcodes.tsv",
+         "kwargs": {}},
+        {"name": "baf_p2p1", "kind": "baf", "sam": ["p2.bam", "p1.bam"], "barcodes": "barcodes.tsv",
+         "kwargs": {}},
+    ]}
+    finish_case(d, case)
+
+
+# ------------------------------------------------------------------ synthetic 10x cases
+def case_chr22(name="c1_chr22_10x", n_reads=40000, n_bc=60, seed=7):
+    d = fresh(name)
+    rng = random.Random(seed)
+    feats_all = synth.load_features(os.path.join(
+        REF, "data/anno/annotate_genes_hg38_update_20230126.txt"))
+    f22 = [f for f in feats_all if f[0] == "22"]
+    # features on other contigs exercise the "unknown contig -> empty row" path (R4)
+    keep = f22 + [f for f in feats_all if f[0] in ("21", "X")][:200]
+    rng.shuffle(keep)
+    keep = keep[:700]
+    bcs = synth.make_barcodes(rng, n_bc)
+    snps = synth.gen_snps(seed + 1, [f for f in keep if f[0] == "22"], 3000)
+    refs, recs = synth.gen_10x_records(seed, [("22", 50818468)], keep, n_reads, bcs,
+                                       chr_prefix="chr", snps=snps)
+    synth.write_bam(os.path.join(d, "a.bam"), refs, recs)
+    shuffled = list(bcs)
+    rng.shuffle(shuffled)
+    synth.write_lines(os.path.join(d, "barcodes.tsv"), shuffled)
+    with open(os.path.join(d, "features.tsv"), "w") as fp:
+        for i, (c, s, e, n) in enumerate(keep):
+            fp.write("%s%s\t%d\t%d\t%s\n" % ("chr" if i % 3 == 0 else "", c, s, e, n))
+    synth.write_snp_tsv(os.path.join(d, "snps.tsv"), snps, chr_prefix="")
+    case = {"defaults": {"sam": ["a.bam"], "barcodes": "barcodes.tsv", "features": "features.tsv",
+                         "snps": "snps.tsv"}, "runs": [
+        {"name": "rdr_defaults", "kind": "basefc", "kwargs": {"ncores": 4}},
+        {"name": "rdr_frac_0.5", "kind": "basefc", "kwargs": {"min_include": 0.5, "ncores": 4}},
+        {"name": "rdr_len_30_mapq0", "kind": "basefc",
+         "kwargs": {"min_include": 30, "min_mapq": 0, "ncores": 4}},
+        {"name": "rdr_umi_none", "kind": "basefc", "kwargs": {"umi_tag": "None", "ncores": 4}},
+        {"name": "baf_defaults", "kind": "baf", "kwargs": {"ncores": 4}},
+        {"name": "baf_all_reg_dup", "kind": "baf",
+         "kwargs": {"output_all_reg": True, "no_dup_hap": False, "ncores": 4}},
+        {"name": "baf_count3_maf0.1", "kind": "baf",
+         "kwargs": {"min_count": 3, "min_maf": 0.1, "ncores": 4, "output_all_reg": True}},
+        {"name": "baf_umi_none", "kind": "baf", "kwargs": {"umi_tag": "None", "ncores": 4}},
+    ]}
+    finish_case(d, case)
+
+
+CASES = {"d1": case_d1, "d2": case_d2, "d3": case_d3, "chr22": case_chr22}
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        sys.exit("needs /root/reference (build container only)")
+    todo = sys.argv[1:] or list(CASES)
+    for c in todo:
+        print("case", c)
+        CASES[c]()

@@ -1,0 +1,164 @@
+// common.cuh -- shared device helpers and the context object (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/xcltk_b200.h"
+
+#define XG_CUDA(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            return ctx->fail(XG_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+        }                                                                              \
+    } while (0)
+
+// Device-resident read batch: same arrays as xg_reads (include/xcltk_b200.h).
+struct xg_dreads {
+    int64_t n_reads = 0, n_cigar = 0, n_seq_words = 0;
+    int32_t n_runs = 0, n_tiles = 0, max_aln_len = 0, max_span = 0;
+    int2 *pos_end = nullptr;
+    uint32_t *fmq = nullptr;
+    uint32_t *cig_off = nullptr;
+    ulonglong2 *keys = nullptr;
+    uint32_t *seq_off = nullptr;
+    uint32_t *cigar = nullptr;
+    uint32_t *seq = nullptr;
+    xg_run *runs = nullptr;      // device
+    xg_tile *tiles = nullptr;    // device
+    std::vector<xg_run> h_runs;  // host copies for the planners
+    std::vector<xg_tile> h_tiles;
+    double h2d_ms = 0;
+    int64_t bytes = 0;
+};
+
+struct xg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    double timing[8] = {};
+    // growable named scratch buffers (avoid cudaMalloc/cudaFree on every call)
+    struct Buf {
+        void *p = nullptr;
+        size_t cap = 0;
+    };
+    std::map<std::string, Buf> scratch;
+
+    int fail(int code, const std::string &msg) {
+        err = msg;
+        return code;
+    }
+    // Returns nullptr on failure (err set).
+    void *get(const char *name, size_t bytes) {
+        Buf &b = scratch[name];
+        if (b.cap >= bytes && b.p) return b.p;
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&b.p, bytes ? bytes : 256);
+            want = bytes ? bytes : 256;
+        }
+        if (e != cudaSuccess) {
+            err = std::string("cudaMalloc(") + name + ", " + std::to_string(bytes) + " B): " +
+                  cudaGetErrorString(e);
+            b.p = nullptr;
+            return nullptr;
+        }
+        b.cap = want;
+        return b.p;
+    }
+};
+
+#define XG_GET(ptr, type, name, count)                                      \
+    type *ptr = (type *)ctx->get(name, sizeof(type) * (size_t)(count));     \
+    if (!ptr) return XG_E_CUDA;
+
+// ---- device helpers -----------------------------------------------------------------
+struct __align__(16) xg_e128 {
+    unsigned long long a, b;
+};
+
+__device__ __forceinline__ xg_e128 ld128_relaxed(const xg_e128 *addr) {
+    xg_e128 v;
+    asm volatile(
+        "{\n\t.reg .b128 t;\n\tld.relaxed.gpu.global.b128 t, [%2];\n\tmov.b128 {%0, %1}, t;\n\t}"
+        : "=l"(v.a), "=l"(v.b)
+        : "l"(addr)
+        : "memory");
+    return v;
+}
+
+__device__ __forceinline__ xg_e128 cas128(xg_e128 *addr, xg_e128 cmp, xg_e128 val) {
+    xg_e128 old;
+    asm volatile(
+        "{\n\t.reg .b128 c, v, o;\n\t"
+        "mov.b128 c, {%2, %3};\n\t"
+        "mov.b128 v, {%4, %5};\n\t"
+        "atom.relaxed.gpu.global.cas.b128 o, [%6], c, v;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old.a), "=l"(old.b)
+        : "l"(cmp.a), "l"(cmp.b), "l"(val.a), "l"(val.b), "l"(addr)
+        : "memory");
+    return old;
+}
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+// slot in [0, cap) from a 64-bit hash without a division
+__host__ __device__ __forceinline__ uint32_t hash_to_range(uint64_t h, uint32_t cap) {
+    return (uint32_t)(((h >> 32) * (uint64_t)cap) >> 32);
+}
+
+__device__ __forceinline__ bool cig_aligned(uint32_t op) { return op == 0 || op == 7 || op == 8; }
+__device__ __forceinline__ bool cig_skips_ref(uint32_t op) { return op == 2 || op == 3; }
+
+// Cell-barcode lookup table (open addressing, linear probing; empty = XG_KEY_NONE).
+struct BarcodeTable {
+    const uint64_t *keys;
+    const int32_t *cols;
+    uint32_t mask;
+};
+__device__ __forceinline__ int32_t barcode_lookup(const BarcodeTable &t, uint64_t key) {
+    uint32_t s = (uint32_t)mix64(key) & t.mask;
+    while (true) {
+        uint64_t k = __ldg(&t.keys[s]);
+        if (k == key) return __ldg(&t.cols[s]);
+        if (k == XG_KEY_NONE) return -1;
+        s = (s + 1) & t.mask;
+    }
+}
+
+// check_read(): xcltk/rdr/fc/core.py:46-62 (mapq, flags, orphan, tag presence); the
+// min_len test needs the aligned length and is done by the caller.
+struct FilterParams {
+    int32_t min_mapq, min_len;
+    uint32_t incl_flag, excl_flag;
+    int32_t no_orphan, use_cell_tag, need_umi_tag;
+};
+__device__ __forceinline__ bool read_passes_flags(const FilterParams &f, uint32_t fmq) {
+    uint32_t flag = fmq & 0xffffu, mapq = (fmq >> 16) & 0xffu;
+    if ((int32_t)mapq < f.min_mapq) return false;
+    if (f.excl_flag && (flag & f.excl_flag)) return false;
+    if (f.incl_flag && !(flag & f.incl_flag)) return false;
+    if (f.no_orphan && (flag & 1u) && !(flag & 2u)) return false;
+    return true;
+}
+
+int xg_build_barcode_table(xg_ctx *ctx, const xg_barcodes *cells, BarcodeTable *out);

@@ -1,0 +1,223 @@
+// ctx.cu -- context, host<->HBM transfers of read batches, small shared host helpers.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "owner.hpp"
+
+extern "C" void xg_set_host_alloc(void *(*a)(size_t), void (*f)(void *));
+
+namespace {
+void *pinned_alloc(size_t n) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, n ? n : 256, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void pinned_free(void *p) { cudaFreeHost(p); }
+}  // namespace
+
+extern "C" {
+
+const char *xg_version(void) { return "xcltk_b200 0.1 (reference semantics: xcltk 0.5.2)"; }
+
+int xg_create(int32_t device, xg_ctx **out) {
+    if (!out) return XG_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    xg_ctx *ctx = new xg_ctx();
+    *out = ctx;   // returned even on failure so that xg_last_error() works
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return ctx->fail(XG_E_CUDA, std::string("no CUDA device: ") +
+                                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                        " (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return ctx->fail(XG_E_ARG, "device index out of range");
+    ctx->device = device;
+    XG_CUDA(cudaSetDevice(device));
+    XG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto &ev : ctx->ev) XG_CUDA(cudaEventCreate(&ev));
+    xg_set_host_alloc(pinned_alloc, pinned_free);   // decoded batches become pinned
+    return XG_OK;
+}
+
+void xg_destroy(xg_ctx *ctx) {
+    if (!ctx) return;
+    if (ctx->stream) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &kv : ctx->scratch)
+            if (kv.second.p) cudaFree(kv.second.p);
+        for (auto &ev : ctx->ev)
+            if (ev) cudaEventDestroy(ev);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+const char *xg_last_error(xg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void xg_last_timing(xg_ctx *ctx, double out[8]) {
+    for (int i = 0; i < 8; i++) out[i] = ctx->timing[i];
+}
+
+int64_t xg_dreads_n(const xg_dreads *d) { return d ? d->n_reads : 0; }
+
+void xg_dreads_free(xg_ctx *ctx, xg_dreads *d) {
+    if (!d) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    void *ps[] = {d->pos_end, d->fmq, d->cig_off, d->keys, d->seq_off, d->cigar, d->seq, d->runs, d->tiles};
+    for (void *p : ps)
+        if (p) cudaFree(p);
+    delete d;
+}
+
+int xg_upload_reads(xg_ctx *ctx, const xg_reads *h, xg_dreads **out) {
+    if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
+    if (!h || !out) return ctx->fail(XG_E_ARG, "xg_upload_reads: null argument");
+    XG_CUDA(cudaSetDevice(ctx->device));
+    xg_dreads *d = new xg_dreads();
+    d->n_reads = h->n_reads;
+    d->n_cigar = h->n_cigar;
+    d->n_seq_words = h->n_seq_words;
+    d->n_runs = h->n_runs;
+    d->n_tiles = h->n_tiles;
+    d->max_aln_len = h->max_aln_len;
+    d->max_span = h->max_span;
+    d->h_runs.assign(h->runs, h->runs + h->n_runs);
+    d->h_tiles.assign(h->tiles, h->tiles + h->n_tiles);
+    size_t n = (size_t)h->n_reads;
+    bool seq = h->seq_off != nullptr && h->seq != nullptr;
+    struct Cp {
+        void **dst;
+        const void *src;
+        size_t bytes;
+    } cps[] = {
+        {(void **)&d->pos_end, h->pos_end, n * 8},
+        {(void **)&d->fmq, h->fmq, n * 4},
+        {(void **)&d->cig_off, h->cig_off, n * 4},
+        {(void **)&d->keys, h->keys, n * 16},
+        {(void **)&d->seq_off, seq ? h->seq_off : nullptr, seq ? n * 4 : 0},
+        {(void **)&d->cigar, h->cigar, (size_t)h->n_cigar * 4},
+        {(void **)&d->seq, seq ? h->seq : nullptr, seq ? (size_t)h->n_seq_words * 4 : 0},
+        {(void **)&d->runs, h->runs, (size_t)h->n_runs * sizeof(xg_run)},
+        {(void **)&d->tiles, h->tiles, (size_t)h->n_tiles * sizeof(xg_tile)},
+    };
+    for (auto &c : cps) {
+        if (!c.src) continue;
+        cudaError_t e = cudaMalloc(c.dst, c.bytes ? c.bytes : 16);
+        if (e != cudaSuccess) {
+            xg_dreads_free(ctx, d);
+            return ctx->fail(XG_E_CUDA, std::string("cudaMalloc reads: ") + cudaGetErrorString(e));
+        }
+    }
+    cudaEventRecord(ctx->ev[6], ctx->stream);
+    for (auto &c : cps) {
+        if (!c.src || !c.bytes) continue;
+        cudaError_t e = cudaMemcpyAsync(*c.dst, c.src, c.bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            xg_dreads_free(ctx, d);
+            return ctx->fail(XG_E_CUDA, std::string("H2D reads: ") + cudaGetErrorString(e));
+        }
+        d->bytes += (int64_t)c.bytes;
+    }
+    cudaEventRecord(ctx->ev[7], ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        xg_dreads_free(ctx, d);
+        return ctx->fail(XG_E_CUDA, std::string("H2D reads: ") + cudaGetErrorString(e));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+    d->h2d_ms = ms;
+    ctx->timing[3] = ms;
+    *out = d;
+    return XG_OK;
+}
+
+int xg_download_reads(xg_ctx *ctx, const xg_dreads *d, xg_reads **out) {
+    if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
+    XG_CUDA(cudaSetDevice(ctx->device));
+    xg_reads_owner *o = new xg_reads_owner();   // released by xg_reads_free()
+    memset(&o->r, 0, sizeof(o->r));
+    o->free_fn = pinned_free;
+    size_t n = (size_t)d->n_reads;
+    auto dl = [&](const void *src, size_t bytes) -> void * {
+        void *p = pinned_alloc(bytes);
+        if (!p) return nullptr;
+        o->bufs.push_back(p);
+        if (bytes) cudaMemcpyAsync(p, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        return p;
+    };
+    o->r.n_reads = d->n_reads;
+    o->r.n_cigar = d->n_cigar;
+    o->r.n_seq_words = d->n_seq_words;
+    o->r.n_runs = d->n_runs;
+    o->r.n_tiles = d->n_tiles;
+    o->r.max_aln_len = d->max_aln_len;
+    o->r.max_span = d->max_span;
+    o->r.n_records_seen = d->n_reads;
+    o->r.pos_end = (const int32_t *)dl(d->pos_end, n * 8);
+    o->r.fmq = (const uint32_t *)dl(d->fmq, n * 4);
+    o->r.cig_off = (const uint32_t *)dl(d->cig_off, n * 4);
+    o->r.keys = (const uint64_t *)dl(d->keys, n * 16);
+    o->r.cigar = (const uint32_t *)dl(d->cigar, (size_t)d->n_cigar * 4);
+    if (d->seq_off && d->seq) {
+        o->r.seq_off = (const uint32_t *)dl(d->seq_off, n * 4);
+        o->r.seq = (const uint32_t *)dl(d->seq, (size_t)d->n_seq_words * 4);
+    }
+    xg_run *runs = (xg_run *)pinned_alloc(sizeof(xg_run) * (d->h_runs.size() + 1));
+    xg_tile *tiles = (xg_tile *)pinned_alloc(sizeof(xg_tile) * (d->h_tiles.size() + 1));
+    o->bufs.push_back(runs);
+    o->bufs.push_back(tiles);
+    memcpy(runs, d->h_runs.data(), sizeof(xg_run) * d->h_runs.size());
+    memcpy(tiles, d->h_tiles.data(), sizeof(xg_tile) * d->h_tiles.size());
+    o->r.runs = runs;
+    o->r.tiles = tiles;
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = &o->r;
+    return XG_OK;
+}
+
+void xg_coo_free(xg_coo *m) {
+    if (!m) return;
+    xg_coo_owner *o = reinterpret_cast<xg_coo_owner *>(m);
+    for (void *p : o->bufs) cudaFreeHost(p);
+    delete o;
+}
+
+}  // extern "C"
+
+// Build the open-addressing cell-barcode table on the host and upload it.
+// Replaces the dict lookup `smp in self.cell_cnt` (rdr/fc/mcount.py:119-127).
+int xg_build_barcode_table(xg_ctx *ctx, const xg_barcodes *cells, BarcodeTable *out) {
+    uint32_t cap = 16;
+    while (cap < (uint32_t)cells->n * 2u + 2u) cap <<= 1;
+    std::vector<uint64_t> k(cap, XG_KEY_NONE);
+    std::vector<int32_t> v(cap, -1);
+    for (int32_t i = 0; i < cells->n; i++) {
+        uint64_t key = cells->keys[i];
+        if (key == XG_KEY_NONE || key == XG_KEY_NOMATCH)
+            return ctx->fail(XG_E_ARG, "invalid barcode key");
+        uint32_t s = (uint32_t)mix64(key) & (cap - 1);
+        while (k[s] != XG_KEY_NONE) {
+            if (k[s] == key) return ctx->fail(XG_E_ARG, "duplicate barcode key");
+            s = (s + 1) & (cap - 1);
+        }
+        k[s] = key;
+        v[s] = i;
+    }
+    XG_GET(dk, uint64_t, "bc_keys", cap);
+    XG_GET(dv, int32_t, "bc_cols", cap);
+    XG_CUDA(cudaMemcpyAsync(dk, k.data(), cap * 8, cudaMemcpyHostToDevice, ctx->stream));
+    XG_CUDA(cudaMemcpyAsync(dv, v.data(), cap * 4, cudaMemcpyHostToDevice, ctx->stream));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));   // k, v go out of scope
+    out->keys = dk;
+    out->cols = dv;
+    out->mask = cap - 1;
+    return XG_OK;
+}

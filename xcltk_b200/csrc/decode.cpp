@@ -1,0 +1,620 @@
+// decode.cpp -- host side: BGZF inflate + BAM record parse -> flat structure-of-arrays.
+//
+// Replaces what the reference gets from pysam/htslib on its two counting paths
+// (pysam.AlignmentFile / AlignedSegment; call sites in SURVEY.md section 8c):
+//   pos, bam_endpos (fetch overlap rule), flag, mapq, CIGAR words, 4-bit sequence, the
+//   cell / UMI tag strings (or the query name when no UMI tag is used).
+// Semantics restated from the SAM/BAM specification (SAMv1 section 4.2) and SURVEY.md A.3.
+// Inflate and field extraction are multi-threaded; nothing here touches the GPU except the
+// (optional) pinned allocator installed by the CUDA translation unit.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "keys.hpp"
+#include "owner.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+void *default_alloc(size_t n) {
+    void *p = nullptr;
+    if (posix_memalign(&p, 256, n ? n : 256) != 0) return nullptr;
+    return p;
+}
+void default_free(void *p) { free(p); }
+void *(*g_alloc)(size_t) = default_alloc;
+void (*g_free)(void *) = default_free;
+
+inline uint32_t rd32(const uint8_t *p) {
+    uint32_t v;
+    memcpy(&v, p, 4);
+    return v;
+}
+inline uint16_t rd16(const uint8_t *p) {
+    uint16_t v;
+    memcpy(&v, p, 2);
+    return v;
+}
+
+template <class F>
+void parallel_for(int64_t n, int n_threads, F f) {
+    // f(thread_index, begin, end) over a static partition of [0, n)
+    if (n_threads < 1) n_threads = 1;
+    if (n < 4096) n_threads = 1;
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) {
+        int64_t b = n * t / n_threads, e = n * (t + 1) / n_threads;
+        if (t == n_threads - 1) {
+            f(t, b, e);
+        } else {
+            th.emplace_back([=] { f(t, b, e); });
+        }
+    }
+    for (auto &x : th) x.join();
+}
+
+struct BgzfBlock {
+    uint64_t coff;    // offset of the deflate payload in the file
+    uint32_t clen;    // deflate payload length
+    uint32_t isize;   // uncompressed length
+    uint64_t uoff;    // offset in the uncompressed stream
+};
+
+int read_file(const char *path, std::vector<uint8_t> &buf) {
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail(XG_E_IO, std::string("cannot open '") + path + "'");
+    fseek(fp, 0, SEEK_END);
+    long n = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    buf.resize((size_t)n);
+    size_t got = n ? fread(buf.data(), 1, (size_t)n, fp) : 0;
+    fclose(fp);
+    if ((long)got != n) return fail(XG_E_IO, std::string("short read on '") + path + "'");
+    return XG_OK;
+}
+
+// Walk the BGZF block headers (RFC 1952 member with a 'BC' extra subfield, SAMv1 4.1).
+int scan_bgzf(const std::vector<uint8_t> &f, std::vector<BgzfBlock> &blocks, const char *path,
+              int64_t max_blocks = -1) {
+    uint64_t off = 0, uoff = 0, n = f.size();
+    while (off < n) {
+        if (off + 18 > n || f[off] != 31 || f[off + 1] != 139 || f[off + 2] != 8 || !(f[off + 3] & 4))
+            return fail(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (bad block header)");
+        uint32_t xlen = rd16(&f[off + 10]);
+        uint64_t x = off + 12, xend = x + xlen;
+        if (xend > n) return fail(XG_E_FORMAT, "truncated BGZF extra field");
+        int64_t bsize = -1;
+        while (x + 4 <= xend) {
+            uint32_t slen = rd16(&f[x + 2]);
+            if (f[x] == 66 && f[x + 1] == 67 && slen == 2) bsize = rd16(&f[x + 4]);
+            x += 4 + slen;
+        }
+        if (bsize < 0) return fail(XG_E_FORMAT, "BGZF block without BC subfield");
+        uint64_t total = (uint64_t)bsize + 1;
+        if (off + total > n || total < 12 + xlen + 8)
+            return fail(XG_E_FORMAT, std::string("truncated BGZF block in '") + path + "'");
+        BgzfBlock b;
+        b.coff = off + 12 + xlen;
+        b.clen = (uint32_t)(total - 12 - xlen - 8);
+        b.isize = rd32(&f[off + total - 4]);
+        b.uoff = uoff;
+        if (b.isize > 65536) return fail(XG_E_FORMAT, "BGZF block larger than 64 KiB");
+        uoff += b.isize;
+        blocks.push_back(b);
+        off += total;
+        if (max_blocks > 0 && (int64_t)blocks.size() >= max_blocks) break;
+    }
+    return XG_OK;
+}
+
+int inflate_blocks(const std::vector<uint8_t> &f, const std::vector<BgzfBlock> &blocks,
+                   std::vector<uint8_t> &out, int n_threads) {
+    uint64_t total = blocks.empty() ? 0 : blocks.back().uoff + blocks.back().isize;
+    out.resize(total);
+    std::atomic<int> bad(0);
+    parallel_for((int64_t)blocks.size(), n_threads, [&](int, int64_t b, int64_t e) {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) {
+            bad = 1;
+            return;
+        }
+        for (int64_t i = b; i < e; i++) {
+            const BgzfBlock &bk = blocks[i];
+            if (bk.isize == 0) continue;
+            inflateReset(&zs);
+            zs.next_in = const_cast<Bytef *>(&f[bk.coff]);
+            zs.avail_in = bk.clen;
+            zs.next_out = &out[bk.uoff];
+            zs.avail_out = bk.isize;
+            int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0) {
+                bad = 1;
+                break;
+            }
+        }
+        inflateEnd(&zs);
+    });
+    if (bad) return fail(XG_E_FORMAT, "BGZF inflate failed (corrupt block)");
+    return XG_OK;
+}
+
+struct Header {
+    std::vector<std::string> names;
+    std::vector<int64_t> lens;
+    uint64_t end_off = 0;   // first record
+};
+
+int parse_header(const std::vector<uint8_t> &u, Header &h, const char *path) {
+    uint64_t n = u.size();
+    if (n < 12 || memcmp(u.data(), "BAM\1", 4) != 0)
+        return fail(XG_E_IO, std::string("'") + path + "' is not a BAM file (bad magic)");
+    uint64_t off = 8 + (uint64_t)(int32_t)rd32(&u[4]);
+    if (off + 4 > n) return fail(XG_E_FORMAT, "truncated BAM header");
+    int32_t n_ref = (int32_t)rd32(&u[off]);
+    off += 4;
+    for (int32_t i = 0; i < n_ref; i++) {
+        if (off + 4 > n) return fail(XG_E_FORMAT, "truncated BAM header");
+        uint32_t l = rd32(&u[off]);
+        off += 4;
+        if (off + l + 4 > n || l == 0) return fail(XG_E_FORMAT, "truncated BAM header");
+        h.names.emplace_back((const char *)&u[off], l - 1);
+        off += l;
+        h.lens.push_back((int64_t)(int32_t)rd32(&u[off]));
+        off += 4;
+    }
+    h.end_off = off;
+    return XG_OK;
+}
+
+// One BAM, inflated, with the offsets of the records we keep.
+struct Bam {
+    std::vector<uint8_t> u;
+    Header h;
+    std::vector<uint64_t> rec;      // offset of block_size of each kept record
+    struct Run {
+        int32_t gid;
+        int64_t beg, end;           // into rec
+    };
+    std::vector<Run> runs;
+    int64_t n_seen = 0;
+};
+
+inline bool op_aligned(uint32_t op) { return op == 0 || op == 7 || op == 8; }
+inline bool op_ref(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
+
+struct RecInfo {
+    int32_t pos, end;
+    uint32_t fmq;
+    uint32_t n_words;      // cigar words stored (incl. overflow count word)
+    uint32_t seq_words;
+    int32_t aln_len;
+};
+
+inline RecInfo rec_info(const uint8_t *r, bool want_seq) {
+    RecInfo o;
+    int32_t pos = (int32_t)rd32(r + 8);
+    uint32_t l_name = r[12], mapq = r[13];
+    uint32_t n_cig = rd16(r + 16), flag = rd16(r + 18), l_seq = rd32(r + 20);
+    const uint8_t *cig = r + 36 + l_name;
+    int64_t rlen = 0, aln = 0;
+    for (uint32_t i = 0; i < n_cig; i++) {
+        uint32_t w = rd32(cig + 4 * i), op = w & 15, l = w >> 4;
+        if (op_ref(op)) rlen += l;
+        if (op_aligned(op)) aln += l;
+    }
+    if (flag & 4) rlen = 0;          // htslib bam_endpos(): FUNMAP => rlen 0 => 1
+    if (rlen == 0) rlen = 1;
+    o.pos = pos;
+    o.end = (int32_t)(pos + rlen);
+    o.aln_len = (int32_t)aln;
+    bool simple = n_cig == 1 && op_aligned(rd32(cig) & 15) && aln == rlen && !(flag & 4);
+    uint32_t ncw;
+    if (simple) {
+        ncw = 0;
+        o.n_words = 0;
+    } else if (n_cig == 0) {
+        ncw = 1;
+        o.n_words = 1;
+    } else if (n_cig < 255) {
+        ncw = n_cig;
+        o.n_words = n_cig;
+    } else {
+        ncw = 255;
+        o.n_words = n_cig + 1;
+    }
+    o.fmq = flag | (mapq << 16) | (ncw << 24);
+    o.seq_words = want_seq ? (((l_seq + 1) / 2 + 3) / 4) : 0;
+    return o;
+}
+
+// Locate an aux tag; returns pointer to its type byte or nullptr. First match wins (bam_aux_get).
+const uint8_t *find_tag(const uint8_t *aux, const uint8_t *end, const char *tag) {
+    const uint8_t *p = aux;
+    while (p + 3 <= end) {
+        bool hit = p[0] == (uint8_t)tag[0] && p[1] == (uint8_t)tag[1];
+        uint8_t t = p[2];
+        const uint8_t *v = p + 3;
+        if (hit) return p + 2;
+        size_t sz;
+        switch (t) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'Z': case 'H': {
+                const uint8_t *q = (const uint8_t *)memchr(v, 0, (size_t)(end - v));
+                if (!q) return nullptr;
+                sz = (size_t)(q - v) + 1;
+                break;
+            }
+            case 'B': {
+                if (v + 5 > end) return nullptr;
+                uint8_t st = v[0];
+                uint32_t cnt = rd32(v + 1);
+                size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                sz = 5 + es * cnt;
+                break;
+            }
+            default: return nullptr;
+        }
+        p = v + sz;
+    }
+    return nullptr;
+}
+
+// Key of a tag value as Python would see it through pysam get_tag():
+// Z/H/A -> str; integer / float types are not strings: they never equal a barcode
+// (cell) and are interned under a type-tagged spelling (UMI; falsy 0 -> EMPTY).
+uint64_t tag_key(const uint8_t *t, const uint8_t *end, xg_keyspace *ks, bool is_cell) {
+    uint8_t typ = t[0];
+    const uint8_t *v = t + 1;
+    if (typ == 'Z' || typ == 'H') {
+        const uint8_t *q = (const uint8_t *)memchr(v, 0, (size_t)(end - v));
+        int64_t n = q ? (int64_t)(q - v) : (int64_t)(end - v);
+        return ks->encode((const char *)v, n);
+    }
+    if (typ == 'A') return ks->encode((const char *)v, 1);
+    if (is_cell) return XG_KEY_NOMATCH;
+    char buf[48];
+    long long iv = 0;
+    switch (typ) {
+        case 'c': iv = (int8_t)v[0]; break;
+        case 'C': iv = v[0]; break;
+        case 's': iv = (int16_t)rd16(v); break;
+        case 'S': iv = rd16(v); break;
+        case 'i': iv = (int32_t)rd32(v); break;
+        case 'I': iv = rd32(v); break;
+        case 'f': {
+            float fv;
+            memcpy(&fv, v, 4);
+            if (fv == 0.0f) return XG_KEY_EMPTY;
+            int n = snprintf(buf, sizeof buf, "\x02%a", (double)fv);
+            return ks->intern(buf, n);
+        }
+        default: return XG_KEY_NOMATCH;
+    }
+    if (iv == 0) return XG_KEY_EMPTY;
+    int n = snprintf(buf, sizeof buf, "\x01%lld", iv);
+    return ks->intern(buf, n);
+}
+
+}  // namespace
+
+struct xg_bam_header {
+    Header h;
+};
+
+extern "C" {
+
+void xg_set_host_alloc(void *(*a)(size_t), void (*f)(void *)) {
+    g_alloc = a ? a : default_alloc;
+    g_free = f ? f : default_free;
+}
+
+const char *xg_host_last_error(void) { return g_err.c_str(); }
+
+xg_keyspace *xg_keyspace_create(void) { return new (std::nothrow) xg_keyspace(); }
+void xg_keyspace_destroy(xg_keyspace *ks) { delete ks; }
+uint64_t xg_key_encode(xg_keyspace *ks, const char *s, int64_t len) { return ks->encode(s, len); }
+int64_t xg_key_decode(xg_keyspace *ks, uint64_t key, char *buf, int64_t cap) {
+    return ks->decode(key, buf, cap);
+}
+int64_t xg_keyspace_n_interned(xg_keyspace *ks) { return ks->n_interned(); }
+
+int xg_bam_header_read(const char *path, xg_bam_header **out) {
+    std::vector<uint8_t> f;
+    int rc = read_file(path, f);
+    if (rc) return rc;
+    // The header may span several blocks: inflate blocks until it parses.
+    std::vector<BgzfBlock> blocks;
+    rc = scan_bgzf(f, blocks, path);
+    if (rc) return rc;
+    size_t nb = 1;
+    while (true) {
+        std::vector<BgzfBlock> part(blocks.begin(), blocks.begin() + std::min(nb, blocks.size()));
+        std::vector<uint8_t> u;
+        rc = inflate_blocks(f, part, u, 1);
+        if (rc) return rc;
+        Header h;
+        rc = parse_header(u, h, path);
+        if (rc == XG_OK) {
+            xg_bam_header *bh = new xg_bam_header();
+            bh->h = std::move(h);
+            *out = bh;
+            return XG_OK;
+        }
+        if (rc == XG_E_IO || nb >= blocks.size()) return rc;
+        nb *= 2;
+    }
+}
+int32_t xg_bam_header_n_ref(const xg_bam_header *h) { return (int32_t)h->h.names.size(); }
+const char *xg_bam_header_ref_name(const xg_bam_header *h, int32_t tid) {
+    return (tid >= 0 && tid < (int32_t)h->h.names.size()) ? h->h.names[tid].c_str() : nullptr;
+}
+int64_t xg_bam_header_ref_len(const xg_bam_header *h, int32_t tid) {
+    return (tid >= 0 && tid < (int32_t)h->h.lens.size()) ? h->h.lens[tid] : -1;
+}
+void xg_bam_header_free(xg_bam_header *h) { delete h; }
+
+void xg_reads_free(xg_reads *r) {
+    if (!r) return;
+    xg_reads_owner *o = reinterpret_cast<xg_reads_owner *>(r);
+    for (void *p : o->bufs) (o->free_fn ? o->free_fn : default_free)(p);
+    delete o;
+}
+
+int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
+                   const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag,
+                   int32_t want_seq, int32_t n_threads, xg_keyspace *ks, xg_reads **out) {
+    if (n_bams < 0 || !out || !ks) return fail(XG_E_ARG, "xg_decode_bams: bad argument");
+    if (cell_tag && strlen(cell_tag) != 2) return fail(XG_E_ARG, "cell tag must have 2 characters");
+    if (umi_tag && strlen(umi_tag) != 2) return fail(XG_E_ARG, "UMI tag must have 2 characters");
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads <= 0) n_threads = 1;
+
+    std::vector<Bam> bams((size_t)n_bams);
+    int64_t n_total = 0, n_seen = 0;
+    for (int32_t b = 0; b < n_bams; b++) {
+        Bam &bm = bams[b];
+        {
+            std::vector<uint8_t> f;
+            int rc = read_file(paths[b], f);
+            if (rc) return rc;
+            std::vector<BgzfBlock> blocks;
+            rc = scan_bgzf(f, blocks, paths[b]);
+            if (rc) return rc;
+            rc = inflate_blocks(f, blocks, bm.u, n_threads);
+            if (rc) return rc;
+        }
+        int rc = parse_header(bm.u, bm.h, paths[b]);
+        if (rc) return rc;
+        int32_t n_ref = (int32_t)bm.h.names.size();
+        if (tid_map_len[b] < n_ref) return fail(XG_E_ARG, "tid_map shorter than the BAM's contig list");
+        const int32_t *map = tid_map[b];
+        // sequential walk over record boundaries; sortedness check (the reference needs a
+        // coordinate-sorted, indexed BAM for fetch()).
+        uint64_t off = bm.h.end_off, n = bm.u.size();
+        int32_t last_tid = -2, last_pos = -1, run_tid = -2;
+        bool seen_unplaced = false;
+        while (off + 4 <= n) {
+            uint32_t bs = rd32(&bm.u[off]);
+            if (bs < 32 || off + 4 + bs > n)
+                return fail(XG_E_FORMAT, std::string("corrupt BAM record in '") + paths[b] + "'");
+            int32_t tid = (int32_t)rd32(&bm.u[off + 4]);
+            int32_t pos = (int32_t)rd32(&bm.u[off + 8]);
+            bm.n_seen++;
+            if (tid >= n_ref) return fail(XG_E_FORMAT, "record refers to an unknown contig");
+            if (tid < 0) {
+                seen_unplaced = true;
+            } else {
+                if (seen_unplaced || tid < last_tid || (tid == last_tid && pos < last_pos))
+                    return fail(XG_E_FORMAT,
+                                std::string("'") + paths[b] + "' is not coordinate sorted");
+                if (map[tid] >= 0) {
+                    if (tid != run_tid) {
+                        bm.runs.push_back({map[tid], (int64_t)bm.rec.size(), (int64_t)bm.rec.size()});
+                        run_tid = tid;
+                    }
+                    bm.rec.push_back(off);
+                    bm.runs.back().end = (int64_t)bm.rec.size();
+                }
+                last_tid = tid;
+                last_pos = pos;
+            }
+            off += 4 + bs;
+        }
+        if (off != n) return fail(XG_E_FORMAT, std::string("trailing bytes in '") + paths[b] + "'");
+        n_total += (int64_t)bm.rec.size();
+        n_seen += bm.n_seen;
+    }
+
+    // pass A: sizes of the streams (per thread partial sums over a global record numbering)
+    struct Part {
+        int64_t cig = 0, seq = 0;
+        int32_t max_aln = 0, max_span = 0;
+    };
+    std::vector<int64_t> bam_base((size_t)n_bams + 1, 0);
+    for (int32_t b = 0; b < n_bams; b++) bam_base[b + 1] = bam_base[b] + (int64_t)bams[b].rec.size();
+    std::vector<std::vector<Part>> parts((size_t)n_bams);
+    int64_t cig_total = 0, seq_total = 0;
+    int32_t max_aln = 0, max_span = 0;
+    std::vector<std::vector<int64_t>> cig_base((size_t)n_bams), seq_base((size_t)n_bams);
+    for (int32_t b = 0; b < n_bams; b++) {
+        Bam &bm = bams[b];
+        parts[b].assign((size_t)n_threads, Part());
+        parallel_for((int64_t)bm.rec.size(), n_threads, [&](int t, int64_t lo, int64_t hi) {
+            Part p;
+            for (int64_t i = lo; i < hi; i++) {
+                RecInfo ri = rec_info(&bm.u[bm.rec[i]], want_seq != 0);
+                p.cig += ri.n_words;
+                p.seq += ri.seq_words;
+                p.max_aln = std::max(p.max_aln, ri.aln_len);
+                p.max_span = std::max(p.max_span, ri.end - ri.pos);
+            }
+            parts[b][t] = p;
+        });
+        cig_base[b].assign((size_t)n_threads, 0);
+        seq_base[b].assign((size_t)n_threads, 0);
+        for (int t = 0; t < n_threads; t++) {
+            cig_base[b][t] = cig_total;
+            seq_base[b][t] = seq_total;
+            cig_total += parts[b][t].cig;
+            seq_total += parts[b][t].seq;
+            max_aln = std::max(max_aln, parts[b][t].max_aln);
+            max_span = std::max(max_span, parts[b][t].max_span);
+        }
+    }
+    if (cig_total >= (1LL << 32) || seq_total >= (1LL << 32))
+        return fail(XG_E_LIMIT, "batch too large for 32-bit stream offsets; decode fewer reads per batch");
+
+    xg_reads_owner *own = new xg_reads_owner();
+    memset(&own->r, 0, sizeof(own->r));
+    own->free_fn = g_free;
+    auto alloc = [&](size_t bytes) -> void * {
+        void *p = g_alloc(bytes);
+        if (p) own->bufs.push_back(p);
+        return p;
+    };
+    int32_t n_runs = 0;
+    for (auto &bm : bams) n_runs += (int32_t)bm.runs.size();
+    int64_t n_tiles = 0;
+    for (auto &bm : bams)
+        for (auto &r : bm.runs) n_tiles += (r.end - r.beg + XG_TILE - 1) / XG_TILE;
+    int32_t *pos_end = (int32_t *)alloc(sizeof(int32_t) * 2 * (size_t)n_total);
+    uint32_t *fmq = (uint32_t *)alloc(sizeof(uint32_t) * (size_t)n_total);
+    uint32_t *cig_off = (uint32_t *)alloc(sizeof(uint32_t) * (size_t)n_total);
+    uint64_t *keys = (uint64_t *)alloc(sizeof(uint64_t) * 2 * (size_t)n_total);
+    uint32_t *seq_off = want_seq ? (uint32_t *)alloc(sizeof(uint32_t) * (size_t)n_total) : nullptr;
+    uint32_t *cigar = (uint32_t *)alloc(sizeof(uint32_t) * (size_t)cig_total);
+    uint32_t *seq = want_seq ? (uint32_t *)alloc(sizeof(uint32_t) * (size_t)seq_total) : nullptr;
+    xg_run *runs = (xg_run *)alloc(sizeof(xg_run) * (size_t)n_runs);
+    xg_tile *tiles = (xg_tile *)alloc(sizeof(xg_tile) * (size_t)n_tiles);
+    if (!pos_end || !fmq || !cig_off || !keys || !cigar || !runs || !tiles ||
+        (want_seq && (!seq_off || !seq))) {
+        xg_reads_free(&own->r);
+        return fail(XG_E_NOMEM, "out of host memory");
+    }
+
+    // pass B: fill
+    for (int32_t b = 0; b < n_bams; b++) {
+        Bam &bm = bams[b];
+        int64_t base = bam_base[b];
+        parallel_for((int64_t)bm.rec.size(), n_threads, [&](int t, int64_t lo, int64_t hi) {
+            int64_t co = cig_base[b][t], so = seq_base[b][t];
+            for (int64_t i = lo; i < hi; i++) {
+                const uint8_t *r = &bm.u[bm.rec[i]];
+                RecInfo ri = rec_info(r, want_seq != 0);
+                int64_t g = base + i;
+                pos_end[2 * g] = ri.pos;
+                pos_end[2 * g + 1] = ri.end;
+                fmq[g] = ri.fmq;
+                uint32_t l_name = r[12], n_cig = rd16(r + 16), l_seq = rd32(r + 20);
+                uint32_t bs = rd32(r);
+                const uint8_t *cig = r + 36 + l_name;
+                uint32_t ncw = ri.fmq >> 24;
+                if (ncw == 0) {
+                    cig_off[g] = (uint32_t)co;
+                } else if (n_cig == 0) {
+                    cig_off[g] = (uint32_t)co;
+                    cigar[co++] = 6;    // 0-length P op: consumes nothing
+                } else {
+                    if (ncw == 255) cigar[co++] = n_cig;
+                    cig_off[g] = (uint32_t)co;
+                    memcpy(&cigar[co], cig, 4 * (size_t)n_cig);
+                    co += n_cig;
+                }
+                const uint8_t *sq = cig + 4 * (size_t)n_cig;
+                if (want_seq) {
+                    // a record without sequence (l_seq == 0: query_sequence is None) is marked
+                    seq_off[g] = ri.seq_words ? (uint32_t)so : 0xFFFFFFFFu;
+                    if (ri.seq_words) {
+                        seq[so + ri.seq_words - 1] = 0;
+                        memcpy(&seq[so], sq, (l_seq + 1) / 2);
+                        so += ri.seq_words;
+                    }
+                }
+                const uint8_t *aux = sq + (l_seq + 1) / 2 + l_seq;
+                const uint8_t *end = r + 4 + bs;
+                uint64_t ck = XG_KEY_NONE, uk = XG_KEY_NONE;
+                if (cell_tag) {
+                    const uint8_t *t = find_tag(aux, end, cell_tag);
+                    if (t) ck = tag_key(t, end, ks, true);
+                }
+                if (umi_tag) {
+                    const uint8_t *t = find_tag(aux, end, umi_tag);
+                    if (t) uk = tag_key(t, end, ks, false);
+                } else {
+                    uk = ks->encode((const char *)(r + 36), l_name ? (int64_t)l_name - 1 : 0);
+                }
+                keys[2 * g] = ck;
+                keys[2 * g + 1] = uk;
+            }
+        });
+    }
+
+    // runs + tile index
+    int32_t ri = 0;
+    int64_t ti = 0;
+    for (int32_t b = 0; b < n_bams; b++) {
+        for (auto &r : bams[b].runs) {
+            runs[ri].bam_idx = b;
+            runs[ri].gid = r.gid;
+            runs[ri].rec_beg = bam_base[b] + r.beg;
+            runs[ri].rec_end = bam_base[b] + r.end;
+            for (int64_t s = runs[ri].rec_beg; s < runs[ri].rec_end; s += XG_TILE) {
+                int64_t e = std::min<int64_t>(s + XG_TILE, runs[ri].rec_end);
+                xg_tile &tl = tiles[ti++];
+                tl.rec_beg = s;
+                tl.n_rec = (int32_t)(e - s);
+                tl.run = ri;
+                tl.first_pos = pos_end[2 * s];
+                tl.max_end = 0;
+            }
+            ri++;
+        }
+    }
+    parallel_for(n_tiles, n_threads, [&](int, int64_t lo, int64_t hi) {
+        for (int64_t t = lo; t < hi; t++) {
+            int32_t m = INT32_MIN;
+            for (int64_t i = tiles[t].rec_beg; i < tiles[t].rec_beg + tiles[t].n_rec; i++)
+                m = std::max(m, pos_end[2 * i + 1]);
+            tiles[t].max_end = m;
+        }
+    });
+
+    xg_reads &o = own->r;
+    o.n_reads = n_total;
+    o.n_cigar = cig_total;
+    o.n_seq_words = seq_total;
+    o.n_runs = n_runs;
+    o.n_tiles = (int32_t)n_tiles;
+    o.max_aln_len = max_aln;
+    o.max_span = max_span;
+    o.n_records_seen = n_seen;
+    o.pos_end = pos_end;
+    o.fmq = fmq;
+    o.cig_off = cig_off;
+    o.keys = keys;
+    o.seq_off = seq_off;
+    o.cigar = cigar;
+    o.seq = seq;
+    o.runs = runs;
+    o.tiles = tiles;
+    *out = &own->r;
+    return XG_OK;
+}
+
+}  // extern "C"

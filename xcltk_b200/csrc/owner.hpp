@@ -1,0 +1,16 @@
+// owner.hpp -- library-owned host results: the public struct first, then what frees it.
+#pragma once
+#include <vector>
+
+#include "../../include/xcltk_b200.h"
+
+struct xg_reads_owner {
+    xg_reads r;
+    std::vector<void *> bufs;
+    void (*free_fn)(void *) = nullptr;
+};
+
+struct xg_coo_owner {
+    xg_coo m;
+    std::vector<void *> bufs;   // pinned (cudaFreeHost)
+};

@@ -1,0 +1,433 @@
+"""ctypes binding of include/xcltk_b200.h (the C-ABI boundary).
+
+The product path has no CPU fallback: if the library cannot be built/loaded or no CUDA
+device is present, the device entry points raise `XgError`.
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+XG_KEY_EMPTY = 0
+XG_KEY_NONE = 0xFFFFFFFFFFFFFFFF
+XG_KEY_NOMATCH = 0xFFFFFFFFFFFFFFFE
+XG_TILE = 1024
+
+c_i32p = C.POINTER(C.c_int32)
+c_u32p = C.POINTER(C.c_uint32)
+c_i64p = C.POINTER(C.c_int64)
+c_u64p = C.POINTER(C.c_uint64)
+c_u8p = C.POINTER(C.c_uint8)
+
+
+class XgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("xcltk_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Run(C.Structure):
+    _fields_ = [("bam_idx", C.c_int32), ("gid", C.c_int32), ("rec_beg", C.c_int64), ("rec_end", C.c_int64)]
+
+
+class Tile(C.Structure):
+    _fields_ = [("rec_beg", C.c_int64), ("n_rec", C.c_int32), ("run", C.c_int32),
+                ("first_pos", C.c_int32), ("max_end", C.c_int32)]
+
+
+class Reads(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_cigar", C.c_int64), ("n_seq_words", C.c_int64),
+                ("n_runs", C.c_int32), ("n_tiles", C.c_int32), ("max_aln_len", C.c_int32),
+                ("max_span", C.c_int32), ("n_records_seen", C.c_int64),
+                ("pos_end", c_i32p), ("fmq", c_u32p), ("cig_off", c_u32p), ("keys", c_u64p),
+                ("seq_off", c_u32p), ("cigar", c_u32p), ("seq", c_u32p),
+                ("runs", C.POINTER(Run)), ("tiles", C.POINTER(Tile))]
+
+
+class Params(C.Structure):
+    _fields_ = [("min_mapq", C.c_int32), ("min_len", C.c_int32), ("incl_flag", C.c_uint32),
+                ("excl_flag", C.c_uint32), ("no_orphan", C.c_int32), ("use_cell_tag", C.c_int32),
+                ("need_umi_tag", C.c_int32), ("min_incl_tab", c_i32p), ("min_incl_tab_len", C.c_int32),
+                ("min_incl_len", C.c_int32)]
+
+
+class Features(C.Structure):
+    _fields_ = [("n", C.c_int32), ("gid", c_i32p), ("beg", c_i32p), ("end", c_i32p)]
+
+
+class Barcodes(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys", c_u64p), ("n_samples", C.c_int32)]
+
+
+class Coo(C.Structure):
+    _fields_ = [("nnz", C.c_int64), ("n_rows", C.c_int32), ("n_cols", C.c_int32),
+                ("row", c_i32p), ("col", c_i32p), ("val", c_i32p), ("row_ptr", c_i64p)]
+
+
+class Snps(C.Structure):
+    _fields_ = [("n", C.c_int32), ("gid", c_i32p), ("pos", c_i32p)]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("n_reads", C.c_int64), ("n_cells", C.c_int32), ("read_len", C.c_int32),
+                ("want_seq", C.c_int32), ("seed", C.c_uint64),
+                ("n_spans", C.c_int32), ("span_gid", c_i32p), ("span_beg", c_i32p), ("span_end", c_i32p),
+                ("n_snps", C.c_int32), ("snp_gid", c_i32p), ("snp_pos", c_i32p),
+                ("snp_ref", c_u8p), ("snp_alt", c_u8p), ("snp_ref_hap", c_u8p)]
+
+
+# every symbol include/xcltk_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "xg_keyspace_create": (_P, []),
+    "xg_keyspace_destroy": (None, [_P]),
+    "xg_key_encode": (C.c_uint64, [_P, C.c_char_p, C.c_int64]),
+    "xg_key_decode": (C.c_int64, [_P, C.c_uint64, C.c_char_p, C.c_int64]),
+    "xg_keyspace_n_interned": (C.c_int64, [_P]),
+    "xg_bam_header_read": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "xg_bam_header_n_ref": (C.c_int32, [_P]),
+    "xg_bam_header_ref_name": (C.c_char_p, [_P, C.c_int32]),
+    "xg_bam_header_ref_len": (C.c_int64, [_P, C.c_int32]),
+    "xg_bam_header_free": (None, [_P]),
+    "xg_decode_bams": (C.c_int, [C.c_int32, C.POINTER(C.c_char_p), C.POINTER(c_i32p), c_i32p,
+                                 C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, _P,
+                                 C.POINTER(C.POINTER(Reads))]),
+    "xg_reads_free": (None, [C.POINTER(Reads)]),
+    "xg_host_last_error": (C.c_char_p, []),
+    "xg_create": (C.c_int, [C.c_int32, C.POINTER(_P)]),
+    "xg_destroy": (None, [_P]),
+    "xg_last_error": (C.c_char_p, [_P]),
+    "xg_upload_reads": (C.c_int, [_P, C.POINTER(Reads), C.POINTER(_P)]),
+    "xg_download_reads": (C.c_int, [_P, _P, C.POINTER(C.POINTER(Reads))]),
+    "xg_dreads_free": (None, [_P, _P]),
+    "xg_dreads_n": (C.c_int64, [_P]),
+    "xg_coo_free": (None, [C.POINTER(Coo)]),
+    "xg_basefc": (C.c_int, [_P, _P, C.POINTER(Features), C.POINTER(Barcodes), C.POINTER(Params),
+                            C.POINTER(C.POINTER(Coo))]),
+    "xg_baf_pileup": (C.c_int, [_P, _P, C.POINTER(Snps), C.POINTER(Barcodes), C.POINTER(Params),
+                                c_i64p, C.POINTER(_P)]),
+    "xg_baf_count": (C.c_int, [_P, _P, C.c_int32, c_i64p, c_i32p, c_u8p, c_u8p, C.c_int32,
+                               C.POINTER(C.POINTER(Coo)), C.POINTER(C.POINTER(Coo)),
+                               C.POINTER(C.POINTER(Coo))]),
+    "xg_baf_state_free": (None, [_P, _P]),
+    "xg_synth_reads": (C.c_int, [_P, C.POINTER(SynthParams), C.POINTER(_P), c_u64p]),
+    "xg_last_timing": (None, [_P, C.POINTER(C.c_double)]),
+    "xg_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(rebuild=True):
+    """Load (building first if sources are newer) and type every exported symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if rebuild:
+        try:
+            path = _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)           # AttributeError = missing export: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def as_ptr(arr, ptype):
+    return arr.ctypes.data_as(ptype)
+
+
+def np_view(ptr, n, dtype):
+    """Zero-copy numpy view of library-owned memory (valid until the owner is freed)."""
+    if n <= 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    t = np.dtype(dtype)
+    buf = (C.c_char * (n * t.itemsize)).from_address(C.addressof(ptr.contents))
+    return np.frombuffer(buf, dtype=t, count=n)
+
+
+class KeySpace(object):
+    def __init__(self):
+        self.lib = load()
+        self.h = self.lib.xg_keyspace_create()
+
+    def encode(self, s):
+        b = s.encode("utf8") if isinstance(s, str) else bytes(s)
+        return int(self.lib.xg_key_encode(self.h, b, len(b)))
+
+    def decode(self, key):
+        buf = C.create_string_buffer(4096)
+        n = self.lib.xg_key_decode(self.h, C.c_uint64(key), buf, 4096)
+        if n < 0:
+            return None
+        return buf.raw[:n].decode("utf8", "replace")
+
+    def n_interned(self):
+        return int(self.lib.xg_keyspace_n_interned(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.xg_keyspace_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def bam_references(path):
+    """[(name, length)] of a BAM header (pysam: AlignmentFile.references / .lengths)."""
+    lib = load()
+    h = _P()
+    rc = lib.xg_bam_header_read(path.encode(), C.byref(h))
+    if rc != 0:
+        raise XgError(rc, lib.xg_host_last_error().decode())
+    try:
+        n = lib.xg_bam_header_n_ref(h)
+        return [(lib.xg_bam_header_ref_name(h, i).decode(), int(lib.xg_bam_header_ref_len(h, i)))
+                for i in range(n)]
+    finally:
+        lib.xg_bam_header_free(h)
+
+
+class HostReads(object):
+    """A decoded batch (library-owned host memory) with numpy views."""
+
+    def __init__(self, ptr):
+        self.lib = load()
+        self.ptr = ptr
+        r = ptr.contents
+        self.n = int(r.n_reads)
+        self.n_records_seen = int(r.n_records_seen)
+        self.max_aln_len = int(r.max_aln_len)
+        self.max_span = int(r.max_span)
+        self.pos_end = np_view(r.pos_end, 2 * self.n, np.int32).reshape(-1, 2)
+        self.fmq = np_view(r.fmq, self.n, np.uint32)
+        self.cig_off = np_view(r.cig_off, self.n, np.uint32)
+        self.keys = np_view(r.keys, 2 * self.n, np.uint64).reshape(-1, 2)
+        self.cigar = np_view(r.cigar, int(r.n_cigar), np.uint32)
+        self.has_seq = bool(r.seq_off) and bool(r.seq)
+        self.seq_off = np_view(r.seq_off, self.n, np.uint32) if self.has_seq else None
+        self.seq = np_view(r.seq, int(r.n_seq_words), np.uint32) if self.has_seq else None
+        self.runs = [(x.bam_idx, x.gid, x.rec_beg, x.rec_end) for x in
+                     (r.runs[i] for i in range(r.n_runs))]
+        self.n_tiles = int(r.n_tiles)
+
+    def tiles(self):
+        r = self.ptr.contents
+        return [(t.rec_beg, t.n_rec, t.run, t.first_pos, t.max_end) for t in
+                (r.tiles[i] for i in range(r.n_tiles))]
+
+    def nbytes(self):
+        r = self.ptr.contents
+        b = self.n * (8 + 4 + 4 + 16) + int(r.n_cigar) * 4
+        if self.has_seq:
+            b += self.n * 4 + int(r.n_seq_words) * 4
+        return b
+
+    def close(self):
+        if self.ptr is not None:
+            for a in ("pos_end", "fmq", "cig_off", "keys", "cigar", "seq_off", "seq"):
+                setattr(self, a, None)
+            self.lib.xg_reads_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def decode_bams(paths, tid_maps, cell_tag, umi_tag, want_seq, keyspace, n_threads=0):
+    lib = load()
+    n = len(paths)
+    cpaths = (C.c_char_p * n)(*[p.encode() for p in paths])
+    maps = [np.ascontiguousarray(m, dtype=np.int32) for m in tid_maps]
+    cmaps = (c_i32p * n)(*[as_ptr(m, c_i32p) for m in maps])
+    lens = np.array([len(m) for m in maps], dtype=np.int32)
+    out = C.POINTER(Reads)()
+    rc = lib.xg_decode_bams(n, cpaths, cmaps, as_ptr(lens, c_i32p),
+                            cell_tag.encode() if cell_tag else None,
+                            umi_tag.encode() if umi_tag else None,
+                            1 if want_seq else 0, n_threads, keyspace.h, C.byref(out))
+    if rc != 0:
+        raise XgError(rc, lib.xg_host_last_error().decode())
+    return HostReads(out)
+
+
+def coo_to_numpy(lib, pcoo, free=True):
+    m = pcoo.contents
+    nnz = int(m.nnz)
+    row = np_view(m.row, nnz, np.int32).copy()
+    col = np_view(m.col, nnz, np.int32).copy()
+    val = np_view(m.val, nnz, np.int32).copy()
+    shape = (int(m.n_rows), int(m.n_cols))
+    if free:
+        lib.xg_coo_free(pcoo)
+    return row, col, val, shape
+
+
+class Context(object):
+    """One per GPU (include/xcltk_b200.h: xg_ctx)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self.h = _P()
+        rc = self.lib.xg_create(device, C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.xg_last_error(self.h).decode() if self.h else "xg_create failed"
+            if self.h:
+                self.lib.xg_destroy(self.h)
+                self.h = None
+            raise XgError(rc, msg)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise XgError(rc, self.lib.xg_last_error(self.h).decode())
+
+    def upload(self, host_reads):
+        d = _P()
+        self._check(self.lib.xg_upload_reads(self.h, host_reads.ptr, C.byref(d)))
+        return DeviceReads(self, d)
+
+    def timing(self):
+        t = (C.c_double * 8)()
+        self.lib.xg_last_timing(self.h, t)
+        return list(t)
+
+    def basefc(self, dreads, gid, beg, end, cell_keys, n_samples, params):
+        gid = np.ascontiguousarray(gid, dtype=np.int32)
+        beg = np.ascontiguousarray(beg, dtype=np.int32)
+        end = np.ascontiguousarray(end, dtype=np.int32)
+        keys = np.ascontiguousarray(cell_keys if cell_keys is not None else [], dtype=np.uint64)
+        f = Features(len(gid), as_ptr(gid, c_i32p), as_ptr(beg, c_i32p), as_ptr(end, c_i32p))
+        b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
+        out = C.POINTER(Coo)()
+        self._check(self.lib.xg_basefc(self.h, dreads.h, C.byref(f), C.byref(b), C.byref(params.c),
+                                       C.byref(out)))
+        return coo_to_numpy(self.lib, out)
+
+    def baf_pileup(self, dreads, gid, pos, cell_keys, n_samples, params):
+        gid = np.ascontiguousarray(gid, dtype=np.int32)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        keys = np.ascontiguousarray(cell_keys if cell_keys is not None else [], dtype=np.uint64)
+        s = Snps(len(gid), as_ptr(gid, c_i32p), as_ptr(pos, c_i32p))
+        b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
+        totals = np.zeros((len(gid), 5), dtype=np.int64)
+        st = _P()
+        self._check(self.lib.xg_baf_pileup(self.h, dreads.h, C.byref(s), C.byref(b), C.byref(params.c),
+                                           as_ptr(totals, c_i64p), C.byref(st)))
+        return totals, BafState(self, st)
+
+    def baf_count(self, state, reg_ptr, reg_snp, hap_of, keep, no_dup_hap):
+        reg_ptr = np.ascontiguousarray(reg_ptr, dtype=np.int64)
+        reg_snp = np.ascontiguousarray(reg_snp, dtype=np.int32)
+        hap_of = np.ascontiguousarray(hap_of, dtype=np.uint8)
+        keep = np.ascontiguousarray(keep, dtype=np.uint8)
+        ad, dp, oth = C.POINTER(Coo)(), C.POINTER(Coo)(), C.POINTER(Coo)()
+        self._check(self.lib.xg_baf_count(self.h, state.h, len(reg_ptr) - 1, as_ptr(reg_ptr, c_i64p),
+                                          as_ptr(reg_snp, c_i32p), as_ptr(hap_of, c_u8p),
+                                          as_ptr(keep, c_u8p), 1 if no_dup_hap else 0,
+                                          C.byref(ad), C.byref(dp), C.byref(oth)))
+        return tuple(coo_to_numpy(self.lib, m) for m in (ad, dp, oth))
+
+    def synth_reads(self, n_reads, n_cells, span_gid, span_beg, span_end, seed=7, read_len=91,
+                    want_seq=False, snps=None):
+        sg = np.ascontiguousarray(span_gid, dtype=np.int32)
+        sb = np.ascontiguousarray(span_beg, dtype=np.int32)
+        se = np.ascontiguousarray(span_end, dtype=np.int32)
+        p = SynthParams()
+        p.n_reads, p.n_cells, p.read_len, p.want_seq, p.seed = n_reads, n_cells, read_len, int(want_seq), seed
+        p.n_spans, p.span_gid, p.span_beg, p.span_end = len(sg), as_ptr(sg, c_i32p), as_ptr(sb, c_i32p), as_ptr(se, c_i32p)
+        keep = [sg, sb, se]
+        if snps is not None:
+            arrs = [np.ascontiguousarray(snps[0], dtype=np.int32), np.ascontiguousarray(snps[1], dtype=np.int32)] + \
+                   [np.ascontiguousarray(a, dtype=np.uint8) for a in snps[2:5]]
+            keep += arrs
+            p.n_snps = len(arrs[0])
+            p.snp_gid, p.snp_pos = as_ptr(arrs[0], c_i32p), as_ptr(arrs[1], c_i32p)
+            p.snp_ref, p.snp_alt, p.snp_ref_hap = (as_ptr(a, c_u8p) for a in arrs[2:5])
+        bk = np.zeros(n_cells, dtype=np.uint64)
+        d = _P()
+        self._check(self.lib.xg_synth_reads(self.h, C.byref(p), C.byref(d), as_ptr(bk, c_u64p)))
+        return DeviceReads(self, d), bk
+
+    def close(self):
+        if self.h:
+            self.lib.xg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceReads(object):
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    @property
+    def n(self):
+        return int(self.ctx.lib.xg_dreads_n(self.h))
+
+    def download(self):
+        out = C.POINTER(Reads)()
+        self.ctx._check(self.ctx.lib.xg_download_reads(self.ctx.h, self.h, C.byref(out)))
+        return HostReads(out)
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.xg_dreads_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BafState(object):
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def close(self):
+        if self.h and self.ctx.h:
+            self.ctx.lib.xg_baf_state_free(self.ctx.h, self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ParamsBox(object):
+    """xg_params plus the numpy array that backs min_incl_tab."""
+
+    def __init__(self, min_mapq, min_len, incl_flag, excl_flag, no_orphan, use_cell_tag,
+                 need_umi_tag, incl_tab=None, incl_len=0):
+        self.tab = None if incl_tab is None else np.ascontiguousarray(incl_tab, dtype=np.int32)
+        self.c = Params(int(min_mapq), int(min_len), int(incl_flag), int(excl_flag), int(bool(no_orphan)),
+                        int(bool(use_cell_tag)), int(bool(need_umi_tag)),
+                        as_ptr(self.tab, c_i32p) if self.tab is not None else None,
+                        len(self.tab) if self.tab is not None else 0, int(incl_len))
