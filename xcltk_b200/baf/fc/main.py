@@ -1,0 +1,296 @@
+"""baf feature-level allele counting on B200 (AD / DP / OTH matrices at phased het SNPs).
+
+Same entry points, arguments, return codes and output files as the reference
+(xcltk/baf/fc/main.py: afc_wrapper :32, afc_core :81, afc_run :262, prepare_config :298);
+the per-SNP pysam pileup of fc_features / fc_fet1 / plp_snp (xcltk/baf/fc/core.py:42-247) is
+replaced by: decode BAMs (with sequences) -> HBM -> xg_baf_pileup -> SNP filter (host, exact
+float compare) -> xg_baf_count -> MTX / TSV text.
+"""
+
+import os
+import sys
+import time
+from logging import debug, error, info
+from logging import warning as warn
+
+import numpy as np
+
+from ... import engine
+from ...utils.zfile import zopen
+from .config import Config
+from .utils import load_region_from_txt, load_snp_from_tsv, load_snp_from_vcf
+
+BASES = "ACGTN"
+BASE_IDX = {"A": 0, "C": 1, "G": 2, "T": 3, "N": 4}      # MCount.base_idx, baf/fc/mcount.py:178
+
+
+def afc_wrapper(sam_fn, barcode_fn, region_fn, phased_snp_fn, out_dir, sam_list_fn=None,
+                sample_ids=None, sample_id_fn=None, debug_level=0, ncores=1, cellsnp_dir=None,
+                ref_cell_fn=None, cell_tag="CB", umi_tag="UB", min_count=1, min_maf=0,
+                output_all_reg=False, no_dup_hap=True, min_mapq=20, min_len=30, incl_flag=0,
+                excl_flag=None, no_orphan=True):
+    """Python API, signature of baf/fc/main.py:32-47."""
+    conf = Config()
+    conf.sam_fn, conf.sam_list_fn = sam_fn, sam_list_fn
+    conf.barcode_fn, conf.region_fn, conf.snp_fn = barcode_fn, region_fn, phased_snp_fn
+    conf.sample_id_str, conf.sample_id_fn = sample_ids, sample_id_fn
+    conf.out_dir, conf.debug = out_dir, debug_level
+    conf.cellsnp_dir, conf.ref_cell_fn = cellsnp_dir, ref_cell_fn
+    conf.cell_tag, conf.umi_tag = cell_tag, umi_tag
+    conf.nproc = ncores
+    conf.min_count, conf.min_maf = min_count, min_maf
+    conf.output_all_reg, conf.no_dup_hap = output_all_reg, no_dup_hap
+    conf.min_mapq, conf.min_len = min_mapq, min_len
+    conf.incl_flag = incl_flag
+    conf.excl_flag = -1 if excl_flag is None else excl_flag
+    conf.no_orphan = no_orphan
+    return afc_run(conf)
+
+
+def prepare_config(conf):
+    """Validate options, load regions / SNPs; 0 if ok, -1 otherwise (baf/fc/main.py:298-495)."""
+    if conf.sam_fn:
+        if conf.sam_list_fn:
+            error("should not specify 'sam_fn' and 'sam_list_fn' together.")
+            return -1
+        conf.sam_fn_list = conf.sam_fn.split(",")
+    else:
+        if not conf.sam_list_fn:
+            error("one of 'sam_fn' and 'sam_list_fn' should be specified.")
+            return -1
+        with open(conf.sam_list_fn, "r") as fp:
+            conf.sam_fn_list = [x.rstrip() for x in fp.readlines()]
+    for fn in conf.sam_fn_list:
+        if not os.path.isfile(fn):
+            error("sam file '%s' does not exist." % fn)
+            return -1
+
+    if conf.barcode_fn:
+        conf.sample_ids = None
+        if conf.sample_id_str or conf.sample_id_fn:
+            error("should not specify barcodes and sample IDs together.")
+            return -1
+        if not os.path.isfile(conf.barcode_fn):
+            error("barcode file '%s' does not exist." % conf.barcode_fn)
+            return -1
+        with zopen(conf.barcode_fn, "rt") as fp:
+            conf.barcodes = sorted(x.strip() for x in fp)
+        if len(set(conf.barcodes)) != len(conf.barcodes):
+            error("duplicate barcodes!")
+            return -1
+    else:
+        conf.barcodes = None
+        if conf.sample_id_str and conf.sample_id_fn:
+            error("should not specify 'sample_id_str' and 'sample_fn' together.")
+            return -1
+        elif conf.sample_id_str:
+            conf.sample_ids = conf.sample_id_str.split(",")
+        elif conf.sample_id_fn:
+            with zopen(conf.sample_id_fn, "rt") as fp:
+                conf.sample_ids = [x.strip() for x in fp]
+        else:
+            warn("use default sample IDs ...")
+            conf.sample_ids = ["Sample%d" % i for i in range(len(conf.sam_fn_list))]
+        if len(conf.sample_ids) != len(conf.sam_fn_list):
+            error("numbers of sam files and sample IDs are different.")
+            return -1
+    conf.samples = conf.barcodes if conf.barcodes else conf.sample_ids
+
+    if not conf.out_dir:
+        error("out dir needed!")
+        return -1
+    if not os.path.isdir(conf.out_dir):
+        os.mkdir(conf.out_dir)
+    pre = os.path.join(conf.out_dir, conf.out_prefix)
+    conf.out_region_fn, conf.out_sample_fn = pre + "region.tsv", pre + "samples.tsv"
+    conf.out_ad_fn, conf.out_dp_fn, conf.out_oth_fn = pre + "AD.mtx", pre + "DP.mtx", pre + "OTH.mtx"
+
+    if not conf.region_fn:
+        error("region file needed!")
+        return -1
+    if not os.path.isfile(conf.region_fn):
+        error("region file '%s' does not exist." % conf.region_fn)
+        return -1
+    conf.reg_list = load_region_from_txt(conf.region_fn, verbose=True)
+    if not conf.reg_list:
+        error("failed to load region file.")
+        return -1
+    info("count %d regions in %d single cells." % (len(conf.reg_list), len(conf.samples)))
+
+    if not conf.snp_fn:
+        error("SNP file needed!")
+        return -1
+    if not os.path.isfile(conf.snp_fn):
+        error("snp file '%s' does not exist." % conf.snp_fn)
+        return -1
+    if conf.snp_fn.endswith((".vcf", ".vcf.gz", ".vcf.bgz")):
+        conf.snp_set = load_snp_from_vcf(conf.snp_fn, verbose=True)
+    else:
+        conf.snp_set = load_snp_from_tsv(conf.snp_fn, verbose=True)
+    if not conf.snp_set or conf.snp_set.get_n() <= 0:
+        error("failed to load snp file.")
+        return -1
+    info("%d SNPs loaded." % conf.snp_set.get_n())
+
+    if conf.cellsnp_dir is not None or conf.ref_cell_fn is not None:
+        # Local phasing (baf/fc/main.py:112-149, phasing.py, localphase.py) is a host-side
+        # numpy EM that needs the cellsnp-lite AnnData; it is outside this build's scope
+        # (SURVEY.md 8f N4).  Refuse loudly instead of silently skipping it.
+        error("local phasing (cellsnp_dir / ref_cell_fn) is not available in xcltk_b200.")
+        return -1
+
+    if conf.cell_tag and conf.cell_tag.upper() == "NONE":
+        conf.cell_tag = None
+    if (not conf.cell_tag) != (not conf.barcodes):
+        error("should not specify cell_tag or barcodes alone.")
+        return -1
+    if conf.umi_tag:
+        if conf.umi_tag.upper() == "AUTO":
+            conf.umi_tag = None if conf.barcodes is None else conf.defaults.UMI_TAG_BC
+        elif conf.umi_tag.upper() == "NONE":
+            conf.umi_tag = None
+
+    with open(conf.out_sample_fn, "w") as fp:
+        fp.write("".join(smp + "\n" for smp in conf.samples))
+    if conf.excl_flag < 0:
+        conf.excl_flag = conf.defaults.EXCL_FLAG_UMI if conf.use_umi() else conf.defaults.EXCL_FLAG_XUMI
+    return 0
+
+
+def snp_filter(conf, snps, totals):
+    """plp_snp's SNP filter (baf/fc/core.py:238-246) from the five bucket totals, evaluated
+    with the reference's own expressions (int < int|float; int < int * float)."""
+    keep = np.zeros(len(snps), dtype=np.uint8)
+    for i, snp in enumerate(snps):
+        t = totals[i]
+        snp_cnt = int(t[0]) + int(t[1]) + int(t[2]) + int(t[3]) + int(t[4])
+        if snp_cnt < conf.min_count:
+            continue
+        minor = min(int(t[BASE_IDX[snp.ref]]), int(t[BASE_IDX[snp.alt]]))
+        if minor < snp_cnt * conf.min_maf:
+            continue
+        keep[i] = 1
+    return keep
+
+
+def hap_table(snps):
+    """hap_of[8*i + code]: region haplotype (0 / 1) of base code at SNP i, 2 = other allele
+    (SNP.get_region_allele_index, gfeature.py:38-39; codes 0..4 = A,C,G,T,N, 5 = any other)."""
+    hap = np.full((len(snps), 8), 2, dtype=np.uint8)
+    for i, snp in enumerate(snps):
+        for code, base in enumerate(BASES):
+            h = snp.get_region_allele_index(base)
+            if h in (0, 1):
+                hap[i, code] = h
+    return hap
+
+
+def count_regions(conf, regs, batch=None):
+    """Device counting; returns three (row, col, val) triples (AD, DP, OTH), rows index `regs`."""
+    snps = conf.snp_set.snps
+    own = batch is None
+    if own:
+        chroms = list(dict.fromkeys([s.chrom for s in snps]))
+        batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True,
+                                  engine.n_decode_threads(conf.nproc))
+    try:
+        gid = np.array([batch.gid_of.get(s.chrom, -1) for s in snps], dtype=np.int32)
+        pos0 = np.array([s.pos - 1 for s in snps], dtype=np.int64)      # fetch(chrom, pos-1, pos)
+        bad = (pos0 < 0) | (pos0 >= 2147483647)
+        gid[bad] = -1
+        pos0[bad] = 0
+        cell_keys = None
+        if conf.use_barcodes():
+            cell_keys = np.array([batch.keyspace.encode(b) for b in conf.barcodes], dtype=np.uint64)
+        params = engine.make_params(conf, batch.stats["max_aln_len"], with_include=False)
+        totals, state = batch.ctx.baf_pileup(batch.dreads, gid, pos0.astype(np.int32), cell_keys,
+                                             len(conf.samples), params)
+        t1 = batch.ctx.timing()
+        keep = snp_filter(conf, snps, totals)
+        reg_ptr = np.zeros(len(regs) + 1, dtype=np.int64)
+        reg_snp = []
+        for r, reg in enumerate(regs):
+            if reg.snp_list:
+                reg_snp.extend(s.index for s in reg.snp_list)
+            reg_ptr[r + 1] = len(reg_snp)
+        out = batch.ctx.baf_count(state, reg_ptr, np.array(reg_snp, dtype=np.int32), hap_table(snps),
+                                  keep, conf.no_dup_hap)
+        t2 = batch.ctx.timing()
+        state.close()
+        conf.last_timing = [t1, t2]
+        conf.last_stats = dict(batch.stats)
+    finally:
+        if own:
+            batch.close()
+    return out
+
+
+def afc_core(conf):
+    if prepare_config(conf) < 0:
+        raise ValueError("errcode -2")
+    info("program configuration:")
+    conf.show(fp=sys.stderr, prefix="\t")
+
+    # SNPs of each region: start <= pos < end, sorted by pos (baf/fc/main.py:88-104)
+    with_snps = []
+    for reg in conf.reg_list:
+        snp_list = conf.snp_set.fetch(reg.chrom, reg.start, reg.end)
+        if snp_list:
+            reg.snp_list = snp_list
+            with_snps.append(reg)
+        elif conf.debug > 2:
+            debug("region '%s': no SNP fetched." % reg.name)
+    info("#regions: total=%d; with_snps=%d." % (len(conf.reg_list), len(with_snps)))
+    if not conf.output_all_reg:
+        conf.reg_list = with_snps
+    info("#regions: total=%d; local_phasing=%d; local_phasing_failed=%d." % (len(conf.reg_list), 0, 0))
+    info("#SNPs: local_phasing=%d; local_phasing_flipped=%d." % (0, 0))
+
+    regs = conf.reg_list
+    if len(regs) == 0:
+        # the reference divides by the worker count min(nproc, 0) here (main.py:152-158)
+        raise ZeroDivisionError("integer division or modulo by zero")
+
+    (ad, dp, oth) = count_regions(conf, regs)
+
+    # emit (baf/fc/core.py:70-122): a region with SNPs gets a row iff it has a DP or OTH
+    # entry, or output_all_reg; SNP-less regions only with output_all_reg.
+    n_reg = len(regs)
+    has = np.zeros(n_reg, dtype=bool)
+    has[dp[0]] = True
+    has[oth[0]] = True
+    emitted = np.ones(n_reg, dtype=bool) if conf.output_all_reg else has
+    new_row = np.cumsum(emitted)
+    with open(conf.out_region_fn, "w") as fp:
+        fp.write("".join("%s\t%d\t%d\t%s\n" % (r.chrom, r.start, r.end - 1, r.name)
+                         for r, e in zip(regs, emitted) if e))
+    n_out = int(emitted.sum())
+    for fn, (row, col, val, _shape) in ((conf.out_ad_fn, ad), (conf.out_dp_fn, dp), (conf.out_oth_fn, oth)):
+        engine.write_mtx(fn, n_out, len(conf.samples), new_row[row], col + 1, val)
+
+
+def afc_run(conf):
+    ret = -1
+    cmdline = None
+    start_time = time.time()
+    info("start time: %s." % time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(start_time)))
+    if conf.argv is not None:
+        cmdline = " ".join(conf.argv)
+        info("CMD: %s" % cmdline)
+    try:
+        ret = afc_core(conf)
+    except ValueError as e:
+        error(str(e))
+        error("Running program failed.")
+        error("Quiting ...")
+        ret = -1
+    else:
+        info("All Done!")
+        ret = 0
+    finally:
+        if conf.argv is not None:
+            info("CMD: %s" % cmdline)
+        end_time = time.time()
+        info("end time: %s" % time.strftime("%Y-%m-%d %H:%M:%S", time.localtime(end_time)))
+        info("time spent: %.2fs" % (end_time - start_time, ))
+    return ret

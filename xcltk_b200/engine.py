@@ -1,0 +1,113 @@
+"""Host-side plumbing shared by basefc and baf: BAM decode -> HBM, parameter packing, output.
+
+Replaces the process pool of the reference (`multiprocessing.Pool` over feature chunks,
+xcltk/rdr/fc/main.py:191-235, xcltk/baf/fc/main.py:156-211): one context per GPU, the decoded
+read batch is uploaded once and every feature / SNP is evaluated against it on the device.
+"""
+
+import math
+import os
+
+import numpy as np
+
+from . import lib
+from .utils.sam import build_tid_maps
+
+INT32_MAX = 2147483647
+
+
+def min_mapq_int(min_mapq):
+    """`read.mapq < conf.min_mapq` with a possibly float threshold (rdr/fc/main.py:126,
+    core.py:47): for integer mapq, mapq < x  <=>  mapq < ceil(x)."""
+    return int(math.ceil(min_mapq))
+
+
+def include_threshold(min_include, max_aln_len):
+    """Integer form of the include test (rdr/fc/core.py:160-165).
+
+    Fraction mode iff 0 < min_include < 1: keep iff not (m / float(n) < min_include); the
+    table gives, for every aligned length n, the smallest m that is kept, found with the
+    reference's own float expression (m / float(n) is monotone in m, so bisection is exact).
+    Otherwise length mode: keep iff not (m < min_include)  <=>  m >= ceil(min_include).
+    Returns (table or None, min_len)."""
+    if 0 < min_include < 1:
+        tab = np.empty(max(1, max_aln_len) + 1, dtype=np.int32)
+        tab[0] = INT32_MAX            # n == 0: the reference's frac is None (never reached with min_len >= 1)
+        for n in range(1, len(tab)):
+            lo, hi = 0, n + 1         # smallest m in [0, n+1) with not (m/float(n) < f); n+1 = none
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if mid / float(n) < min_include:
+                    lo = mid + 1
+                else:
+                    hi = mid
+            tab[n] = lo if lo <= n else INT32_MAX
+        return tab, 0
+    return None, int(math.ceil(min_include))
+
+
+class ReadBatch(object):
+    """Decoded reads of all BAMs resident on one GPU + what is needed to address them."""
+
+    def __init__(self, ctx, dreads, keyspace, gid_of, stats):
+        self.ctx, self.dreads, self.keyspace, self.gid_of, self.stats = ctx, dreads, keyspace, gid_of, stats
+
+    def close(self):
+        if self.dreads is not None:
+            self.dreads.close()
+            self.dreads = None
+
+
+_contexts = {}
+
+
+def get_context(device=0):
+    """One xg_ctx per device, created on first use.  Raises XgError without a GPU: the
+    counting paths have no CPU fallback."""
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = lib.Context(device)
+        _contexts[device] = ctx
+    return ctx
+
+
+def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, device=0):
+    """Decode every BAM (host, multi-threaded) and upload the batch to `device`.
+
+    chroms: distinct (already 'chr'-stripped) contig names the features / SNPs use; reads on
+    other contigs can never be fetched by the reference and are dropped at decode time."""
+    ctx = get_context(device)
+    ks = lib.KeySpace()
+    bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
+    gid_of, tid_maps = build_tid_maps(bam_refs, list(chroms))
+    host = lib.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, ks, n_threads)
+    stats = {"n_reads": host.n, "n_records_seen": host.n_records_seen, "max_aln_len": host.max_aln_len,
+             "max_span": host.max_span, "bytes": host.nbytes()}
+    dreads = ctx.upload(host)
+    host.close()
+    return ReadBatch(ctx, dreads, ks, gid_of, stats)
+
+
+def make_params(conf, max_aln_len, with_include):
+    tab, incl_len = (None, 0)
+    if with_include:
+        tab, incl_len = include_threshold(conf.min_include, max_aln_len)
+    return lib.ParamsBox(min_mapq_int(conf.min_mapq), conf.min_len, conf.incl_flag, conf.excl_flag,
+                         conf.no_orphan, conf.use_barcodes(), conf.use_umi(), tab, incl_len)
+
+
+def write_mtx(path, n_rows, n_cols, row1, col1, val):
+    """MatrixMarket text exactly as merge_mtx writes it (rdr/fc/utils.py:65-67,80-86):
+    header, `%%`, `nrow\\tncol\\tnnz`, then 1-based `row\\tcol\\tval` lines."""
+    with open(path, "w") as fp:
+        fp.write("%%MatrixMarket matrix coordinate integer general\n%%\n")
+        fp.write("%d\t%d\t%d\n" % (n_rows, n_cols, len(val)))
+        step = 1 << 20
+        for s in range(0, len(val), step):
+            blk = np.stack([row1[s:s + step], col1[s:s + step], val[s:s + step]], axis=1)
+            fp.write("".join("%d\t%d\t%d\n" % (a, b, c) for a, b, c in blk.tolist()))
+
+
+def n_decode_threads(nproc):
+    n = int(nproc) if nproc else 1
+    return max(1, min(n, os.cpu_count() or 1))
