@@ -89,7 +89,8 @@ typedef struct {
                               /*   0 = "simple" read (one M/=/X op of length end-pos,     */
                               /*   nothing stored), 1..254 ops, 255 = true count is in    */
                               /*   the word before cig_off                                */
-    const uint32_t *cig_off;  /* first CIGAR word of the read in `cigar`                 */
+    const uint32_t *cig_off;  /* [n+1] first CIGAR word of the read in `cigar`; non-       */
+                              /*   decreasing; cig_off[n] = n_cigar                         */
     const uint64_t *keys;     /* [2*n] cell key, UMI key (UMI tag, or query name)        */
     const uint32_t *seq_off;  /* first word of the read's 4-bit sequence (NULL if none)  */
     /* streams */

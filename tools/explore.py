@@ -14,8 +14,8 @@ for it in range(3):
     row, col, val, shape = ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, n_cells, w.params)
     dt = time.time() - t
     tm = ctx.timing()
-    print("basefc n=%d cells=%d feats=%d nnz=%d sum=%d wall=%.1fms kern=%.2fms count=%.2fms zero=%.2fms launches=%d tbl=%.1fMB d2h=%.2fms" % (
-        n_reads, n_cells, n_feat, len(val), int(val.sum()), dt * 1e3, tm[0], tm[1], tm[5], tm[2], tm[6] / 1e6, tm[4]))
+    print("basefc n=%d cells=%d feats=%d nnz=%d sum=%d wall=%.1fms kern=%.2fms count=%.2fms epochs=%d launches=%d pool=%.1fMB staging=%.1fM d2h=%.2fms" % (
+        n_reads, n_cells, n_feat, len(val), int(val.sum()), dt * 1e3, tm[0], tm[1], tm[5], tm[2], tm[6] / 1e6, tm[7] / 1e6, tm[4]))
 
 if len(sys.argv) > 4:
     nb = int(float(sys.argv[4]))

@@ -11,13 +11,16 @@
 // streamed ONCE in file order (coalesced, one CTA per tile of <= 1024 records); each read finds
 // the features it overlaps through a per-contig interval index (sorted boundaries + per-segment
 // stabbing lists + start-sorted features), evaluates the include test arithmetically on its CIGAR
-// and inserts (cell, UMI) into the feature's open-addressing set in HBM with a 128-bit CAS.
-// A new element bumps the dense (feature, cell) counter; the counters are then compacted into
-// (row, col)-sorted COO.  Features are counted independently (a read overlapping k features is
-// evaluated k times), exactly as the reference does.
+// and inserts (cell, UMI) into the feature's open-addressing set with a 128-bit CAS.  When the
+// last read that can touch a feature has been streamed, one CTA scans the feature's set into a
+// shared-memory histogram over cells and writes the row's non-zeros in column order.  Features
+// are counted independently (a read overlapping k features is evaluated k times), exactly as
+// the reference does.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
-#include <numeric>
+#include <iterator>
+#include <map>
 
 #include "compact.cuh"
 
@@ -27,6 +30,7 @@ struct FeatIndexHost {
     int32_t n_gid = 0;
     std::vector<int32_t> sf_goff, sf_beg, sf_end, sf_row;
     std::vector<int32_t> bnd_goff, bnd, stab_off, stab;
+    std::vector<int32_t> fb;   // per boundary: first sorted feature with beg >= bnd[k] (+ terminator)
 };
 
 // Interval index over the valid features of every contig.
@@ -100,15 +104,30 @@ int build_feat_index(xg_ctx *ctx, const xg_features *f, int32_t n_gid, FeatIndex
         ix.bnd_goff[(size_t)g + 1] = (int32_t)ix.bnd.size();
     }
     ix.stab_off.push_back((int32_t)ix.stab.size());
+    // features beginning exactly at boundary k are the sorted features [fb[k], fb[k+1])
+    ix.fb.resize(ix.bnd.size() + 1);
+    for (int32_t g = 0; g < n_gid; g++) {
+        int32_t j = ix.sf_goff[g];
+        for (int32_t k = ix.bnd_goff[g]; k < ix.bnd_goff[(size_t)g + 1]; k++) {
+            while (j < ix.sf_goff[(size_t)g + 1] && ix.sf_beg[(size_t)j] < ix.bnd[(size_t)k]) j++;
+            ix.fb[(size_t)k] = j;
+        }
+    }
+    ix.fb[ix.bnd.size()] = (int32_t)m;
     return XG_OK;
 }
 
-// Upper bound on the reads that can overlap each (sorted) feature, from the tile index:
-// tiles of the feature's contig with prefix-max(end) > beg and first_pos < end.
-void feature_windows(const xg_dreads *rd, const FeatIndexHost &ix, std::vector<int64_t> &cand) {
+// Per (feature, run): the tiles that can hold an overlapping read -- tiles of the feature's
+// contig with prefix-max(end) > beg and first_pos < end.  Their union over the runs of the
+// contig is the feature's lifetime [tlo, thi) in global tile numbering.
+struct Window {
+    int32_t j, lo_tile, hi_tile;   // sorted feature, tiles [lo_tile, hi_tile)
+};
+void feature_windows(const xg_dreads *rd, const FeatIndexHost &ix, std::vector<Window> &wins,
+                     std::vector<int32_t> &tlo, std::vector<int32_t> &thi) {
     size_t m = ix.sf_beg.size();
-    cand.assign(m, 0);
-    // tiles are laid out run by run
+    tlo.assign(m, INT32_MAX);
+    thi.assign(m, -1);
     size_t nt = rd->h_tiles.size();
     std::vector<int32_t> pmax(nt);
     std::vector<size_t> run_t0((size_t)rd->n_runs + 1, nt);
@@ -125,26 +144,163 @@ void feature_windows(const xg_dreads *rd, const FeatIndexHost &ix, std::vector<i
         size_t t1 = t0 + (size_t)((run.rec_end - run.rec_beg + XG_TILE - 1) / XG_TILE);
         for (int32_t j = ix.sf_goff[run.gid]; j < ix.sf_goff[run.gid + 1]; j++) {
             int32_t beg = ix.sf_beg[(size_t)j], end = ix.sf_end[(size_t)j];
-            // lo: first tile with pmax > beg ; hi: first tile with first_pos >= end
-            size_t lo = t0, hi = t1, a = t0, b = t1;
-            while (a < b) {
+            size_t a = t0, b = t1;
+            while (a < b) {            // lo: first tile with pmax > beg
                 size_t mid = (a + b) / 2;
                 if (pmax[mid] > beg) b = mid; else a = mid + 1;
             }
-            lo = a;
+            size_t lo = a;
             a = t0, b = t1;
-            while (a < b) {
+            while (a < b) {            // hi: first tile with first_pos >= end
                 size_t mid = (a + b) / 2;
                 if (rd->h_tiles[mid].first_pos >= end) b = mid; else a = mid + 1;
             }
-            hi = a;
+            size_t hi = a;
             if (hi > lo) {
-                int64_t e = (hi == t1) ? run.rec_end : rd->h_tiles[hi].rec_beg;
-                cand[(size_t)j] += e - rd->h_tiles[lo].rec_beg;
+                wins.push_back(Window{j, (int32_t)lo, (int32_t)hi});
+                tlo[(size_t)j] = std::min(tlo[(size_t)j], (int32_t)lo);
+                thi[(size_t)j] = std::max(thi[(size_t)j], (int32_t)hi);
             }
         }
     }
 }
+
+// Tighten a window to records: from the first record of tile lo whose end > beg to the first
+// record of tile hi-1 whose pos >= end.  One warp per window; adds the count to cand[j].
+__global__ void __launch_bounds__(256) k_window_cand(const Window *wins, int32_t n_win, const xg_tile *tiles,
+                                                     const int2 *pos_end, const int32_t *sf_beg,
+                                                     const int32_t *sf_end, unsigned long long *cand) {
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= n_win) return;
+    const Window win = wins[w];
+    const int32_t beg = sf_beg[win.j], end = sf_end[win.j];
+    const xg_tile L = tiles[win.lo_tile], H = tiles[win.hi_tile - 1];
+    int64_t first = L.rec_beg + L.n_rec, last = H.rec_beg + H.n_rec;
+    for (int base = 0; base < L.n_rec; base += 32) {
+        int k = base + lane;
+        unsigned msk = __ballot_sync(0xffffffffu, k < L.n_rec && pos_end[L.rec_beg + k].y > beg);
+        if (msk) {
+            first = L.rec_beg + base + (__ffs(msk) - 1);
+            break;
+        }
+    }
+    for (int base = 0; base < H.n_rec; base += 32) {
+        int k = base + lane;
+        unsigned msk = __ballot_sync(0xffffffffu, k < H.n_rec && pos_end[H.rec_beg + k].x >= end);
+        if (msk) {
+            last = H.rec_beg + base + (__ffs(msk) - 1);
+            break;
+        }
+    }
+    if (lane == 0 && last > first) atomicAdd(&cand[win.j], (unsigned long long)(last - first));
+}
+
+// ---- epoch plan ------------------------------------------------------------------------
+// The read stream is cut into epochs of `epoch_tiles` tiles.  A feature owns a block of the
+// pool (its (cell, UMI) set) from the first epoch that can hold one of its reads to the last;
+// the block is zeroed just before the first, reduced to the row's non-zeros just after the
+// last, and then reused by later features.  The pool therefore stays about as large as the
+// state of the features under the current genomic window, so that it can live in the 126 MB
+// L2 instead of streaming through HBM.
+struct EpochPlan {
+    int32_t n_epochs = 0, epoch_tiles = 0;
+    std::vector<uint64_t> blk_off;      // per sorted feature: byte offset of its set
+    std::vector<uint32_t> tbl_cap;      // slots of its set (0 = feature never active)
+    uint64_t pool_bytes = 0;
+    std::vector<int32_t> zero_ptr, fin_ptr;           // per epoch ranges
+    std::vector<uint64_t> zseg_off, zseg_pre;
+    std::vector<int32_t> fin_feat;
+    int64_t staging_cap = 0;
+};
+
+int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const std::vector<int32_t> &tlo,
+              const std::vector<int32_t> &thi, int32_t n_tiles, int32_t n_cols, int32_t epoch_tiles,
+              EpochPlan &pl) {
+    size_t m = cand.size();
+    pl.epoch_tiles = epoch_tiles;
+    pl.n_epochs = std::max(1, (n_tiles + epoch_tiles - 1) / epoch_tiles);
+    pl.blk_off.assign(m, 0);
+    pl.tbl_cap.assign(m, 0);
+    std::vector<std::vector<int32_t>> starts((size_t)pl.n_epochs), ends((size_t)pl.n_epochs);
+    for (size_t j = 0; j < m; j++) {
+        if (cand[j] == 0) continue;
+        unsigned long long cap = cand[j] + cand[j] / 4 + 8;
+        if (cap >= (1ull << 32)) return ctx->fail(XG_E_LIMIT, "feature window exceeds 2^32 reads");
+        pl.tbl_cap[j] = (uint32_t)cap;
+        pl.staging_cap += (int64_t)std::min<unsigned long long>(cand[j], (unsigned long long)n_cols);
+        starts[(size_t)(tlo[j] / epoch_tiles)].push_back((int32_t)j);
+        ends[(size_t)((thi[j] - 1) / epoch_tiles)].push_back((int32_t)j);
+    }
+    std::map<uint64_t, uint64_t> free_blocks;   // first-fit free list keyed by offset
+    auto release = [&](uint64_t off, uint64_t len) {
+        auto it = free_blocks.emplace(off, len).first;
+        auto nx = std::next(it);
+        if (nx != free_blocks.end() && it->first + it->second == nx->first) {
+            it->second += nx->second;
+            free_blocks.erase(nx);
+        }
+        if (it != free_blocks.begin()) {
+            auto pv = std::prev(it);
+            if (pv->first + pv->second == it->first) {
+                pv->second += it->second;
+                free_blocks.erase(it);
+            }
+        }
+    };
+    pl.zero_ptr.assign((size_t)pl.n_epochs + 1, 0);
+    pl.fin_ptr.assign((size_t)pl.n_epochs + 1, 0);
+    for (int32_t e = 0; e < pl.n_epochs; e++) {
+        // a block is reused two epochs after its feature ended, so that zeroing the blocks of
+        // epoch e never races with the (overlapped) counting of epoch e-1
+        if (e > 1)
+            for (int32_t j : ends[(size_t)e - 2])
+                release(pl.blk_off[(size_t)j], (uint64_t)pl.tbl_cap[(size_t)j] * 16);
+        uint64_t pre = 0;
+        for (int32_t j : starts[(size_t)e]) {
+            uint64_t need = (uint64_t)pl.tbl_cap[(size_t)j] * 16, off = UINT64_MAX;
+            for (auto it = free_blocks.begin(); it != free_blocks.end(); ++it)
+                if (it->second >= need) {
+                    off = it->first;
+                    uint64_t rest = it->second - need;
+                    free_blocks.erase(it);
+                    if (rest) free_blocks.emplace(off + need, rest);
+                    break;
+                }
+            if (off == UINT64_MAX) {
+                off = pl.pool_bytes;
+                if (!free_blocks.empty()) {      // extend a free block that touches the pool end
+                    auto last = std::prev(free_blocks.end());
+                    if (last->first + last->second == pl.pool_bytes) {
+                        off = last->first;
+                        free_blocks.erase(last);
+                    }
+                }
+                pl.pool_bytes = off + need;
+            }
+            pl.blk_off[(size_t)j] = off;
+            pl.zseg_off.push_back(off);
+            pl.zseg_pre.push_back(pre);
+            pre += need;
+        }
+        pl.zseg_pre.push_back(pre);      // terminator of the epoch: total bytes
+        pl.zseg_off.push_back(0);
+        pl.zero_ptr[(size_t)e + 1] = (int32_t)pl.zseg_off.size();
+        for (int32_t j : ends[(size_t)e]) pl.fin_feat.push_back(j);
+        pl.fin_ptr[(size_t)e + 1] = (int32_t)pl.fin_feat.size();
+    }
+    return XG_OK;
+}
+
+#define SB_MAX 512       // boundaries staged in shared memory per tile
+#define PAIR_CAP 1536    // (feature, cell, UMI) triples staged per tile
+#define RPT 4            // records per thread (XG_TILE / 256)
+#define PB 2             // staged pairs a thread keeps in flight in the insert phase
+
+// per sorted feature: where its set lives
+struct __align__(16) FeatDesc {
+    unsigned long long blk_off;
+    uint32_t cap, pad;
+};
 
 struct BasefcDev {
     const int2 *pos_end;
@@ -152,39 +308,79 @@ struct BasefcDev {
     const ulonglong2 *keys;
     const xg_run *runs;
     const xg_tile *tiles;
-    const int32_t *sf_goff, *sf_beg, *sf_end, *sf_row, *bnd_goff, *bnd, *stab_off, *stab;
+    const int2 *tile_bnd;         // per tile: boundaries [x, y) under its window
+    const int32_t *sf_goff, *sf_end, *bnd_goff, *bnd, *stab_off, *fb;
+    const int4 *stab4;            // stabbing lists: {sorted feature, beg, end, 0}
     int32_t n_gid;
-    xg_e128 *tbl;
-    const uint64_t *tbl_base;
-    const uint32_t *tbl_cap;
-    uint32_t *counts;
-    int32_t n_cols;
+    uint8_t *pool;
+    const FeatDesc *fdesc;
+    int32_t tile0;                // first tile of this launch (epoch)
+    int32_t ablate;               // profiling only: 1 skip inserts, 2 stop after cell lookup, 3 after loads
     BarcodeTable bc;
     FilterParams fp;
     const int32_t *incl_tab;
     int32_t incl_tab_len, incl_len;
 };
 
-// (cell, UMI) -> the feature's set; returns true when the element is new.
-__device__ __forceinline__ bool set_insert(xg_e128 *tbl, uint32_t cap, uint64_t umi, uint32_t col) {
-    xg_e128 want;
-    want.a = umi;
-    want.b = (unsigned long long)col + 1ull;       // b == 0 marks an empty slot
-    uint32_t s = hash_to_range(mix64(umi ^ ((uint64_t)col * 0x9E3779B97F4A7C15ULL)), cap);
+// per tile: the range of boundaries that its window [first_pos, max_end) can touch
+__global__ void k_tile_bounds(const xg_tile *tiles, const xg_run *runs, int32_t n_tiles, int32_t n_gid,
+                              const int32_t *bnd_goff, const int32_t *bnd, int2 *out) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const xg_tile tl = tiles[t];
+    const int32_t gid = runs[tl.run].gid;
+    if (gid < 0 || gid >= n_gid) {
+        out[t] = make_int2(0, 0);
+        return;
+    }
+    const int32_t b0 = bnd_goff[gid], b1 = bnd_goff[gid + 1];
+    int32_t lo = b0, hi = b1;
+    while (lo < hi) {              // upper_bound(first_pos)
+        int32_t mid = (lo + hi) >> 1;
+        if (bnd[mid] <= tl.first_pos) lo = mid + 1; else hi = mid;
+    }
+    int32_t x = max(b0, lo - 1);
+    hi = b1;
+    while (lo < hi) {              // lower_bound(max_end)
+        int32_t mid = (lo + hi) >> 1;
+        if (bnd[mid] < tl.max_end) lo = mid + 1; else hi = mid;
+    }
+    out[t] = make_int2(x, max(x, lo));
+}
+
+__device__ __forceinline__ uint32_t set_home(uint64_t umi, uint32_t col, uint32_t cap) {
+    return hash_to_range(mix64(umi ^ ((uint64_t)col * 0x9E3779B97F4A7C15ULL)), cap);
+}
+
+// (cell, UMI) -> the feature's set, starting at slot s whose content `cur` was already loaded.
+// Empty slot: b == 0.
+__device__ __forceinline__ void set_insert_from(xg_e128 *tbl, uint32_t cap, uint32_t s, xg_e128 cur,
+                                                xg_e128 want) {
     for (uint32_t probe = 0; probe < cap; probe++) {
-        xg_e128 cur = ld128_relaxed(&tbl[s]);
         if (cur.b == 0) {
             xg_e128 empty;
             empty.a = 0;
             empty.b = 0;
             cur = cas128(&tbl[s], empty, want);
-            if (cur.b == 0) return true;
+            if (cur.b == 0) return;
         }
-        if (cur.a == want.a && cur.b == want.b) return false;
+        if (cur.a == want.a && cur.b == want.b) return;
         s = (s + 1 == cap) ? 0 : s + 1;
+        cur = ld128_relaxed(&tbl[s]);
     }
-    return false;   // table full: cannot happen, cap > number of candidate reads
 }
+
+#define CIG_CAP 2048     // CIGAR words of the tile staged in shared memory
+#define STAB_CAP 512     // stabbing-list entries of the tile's boundaries staged in shared memory
+
+struct PairStage {
+    unsigned long long umi[PAIR_CAP];
+    uint32_t j[PAIR_CAP], col[PAIR_CAP];
+    int4 stab4[STAB_CAP];
+    uint32_t cigar[CIG_CAP];
+    int32_t bnd[SB_MAX], stab_off[SB_MAX + 1];
+    int n_pairs;
+};
 
 // m = number of aligned (M/=/X) reference positions p of the read with s0 <= p < e0
 // (== len([x for x in read.positions if s <= x <= e]), rdr/fc/core.py:40-43)
@@ -192,7 +388,7 @@ __device__ __forceinline__ int32_t included_len(const uint32_t *cig, uint32_t n_
                                                  int32_t s0, int32_t e0) {
     int32_t m = 0, p = pos;
     for (uint32_t k = 0; k < n_ops; k++) {
-        uint32_t w = __ldg(&cig[k]), op = w & 15u;
+        uint32_t w = cig[k], op = w & 15u;
         int32_t l = (int32_t)(w >> 4);
         if (cig_aligned(op)) {
             int32_t a = max(p, s0), b = min(p + l, e0);
@@ -205,10 +401,10 @@ __device__ __forceinline__ int32_t included_len(const uint32_t *cig, uint32_t n_
     return m;
 }
 
-__device__ __forceinline__ void count_pair(const BasefcDev &P, int32_t j, int32_t pos, int32_t end,
-                                           const uint32_t *cig, uint32_t n_ops, int32_t need,
-                                           uint64_t umi, uint32_t col) {
-    int32_t s0 = __ldg(&P.sf_beg[j]), e0 = __ldg(&P.sf_end[j]);
+// include test of one (read, feature) pair; a passing pair is staged for the insert phase
+__device__ __forceinline__ void emit_pair(const BasefcDev &P, PairStage &S, int32_t j, int32_t s0, int32_t e0,
+                                          int32_t pos, int32_t end, const uint32_t *cig, uint32_t n_ops,
+                                          int32_t need, uint64_t umi, uint32_t col) {
     int32_t m;
     if (n_ops == 0) {
         int32_t a = max(pos, s0), b = min(end, e0);
@@ -217,92 +413,389 @@ __device__ __forceinline__ void count_pair(const BasefcDev &P, int32_t j, int32_
         m = included_len(cig, n_ops, pos, s0, e0);
     }
     if (m < need) return;
-    uint32_t cap = __ldg(&P.tbl_cap[j]);
-    if (cap == 0) return;
-    if (set_insert(P.tbl + __ldg(&P.tbl_base[j]), cap, umi, col)) {
-        int32_t row = __ldg(&P.sf_row[j]);
-        atomicAdd(&P.counts[(size_t)row * (size_t)P.n_cols + col], 1u);
+    int slot = atomicAdd(&S.n_pairs, 1);
+    if (slot < PAIR_CAP) {
+        S.umi[slot] = umi;
+        S.j[slot] = (uint32_t)j;
+        S.col[slot] = col;
+    } else {                       // stage full (very deep feature overlap): insert right away
+        const FeatDesc fd = P.fdesc[j];
+        if (fd.cap) {
+            xg_e128 want;
+            want.a = umi;
+            want.b = (unsigned long long)col + 1ull;
+            xg_e128 *tbl = (xg_e128 *)(P.pool + fd.blk_off);
+            uint32_t s = set_home(umi, col, fd.cap);
+            set_insert_from(tbl, fd.cap, s, ld128_relaxed(&tbl[s]), want);
+        }
     }
 }
 
-__global__ void __launch_bounds__(256) k_basefc_count(const __grid_constant__ BasefcDev P) {
-    const xg_tile tile = P.tiles[blockIdx.x];
+// Insert phase: all lanes insert staged pairs; descriptor and home-slot loads of a batch are
+// issued together before any of them is consumed.  Ends with the stage empty.
+__device__ __forceinline__ void flush_pairs(const BasefcDev &P, PairStage &S) {
+    const int np = P.ablate == 1 ? 0 : min(S.n_pairs, PAIR_CAP);
+    for (int p0 = 0; p0 < np; p0 += 256 * PB) {
+        xg_e128 *tbl[PB];
+        uint32_t cap[PB], home[PB];
+        xg_e128 cur[PB];
+#pragma unroll
+        for (int r = 0; r < PB; r++) {
+            const int p = p0 + r * 256 + threadIdx.x;
+            cap[r] = 0;
+            if (p < np) {
+                const FeatDesc fd = P.fdesc[S.j[p]];
+                cap[r] = fd.cap;
+                tbl[r] = (xg_e128 *)(P.pool + fd.blk_off);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < PB; r++) {
+            const int p = p0 + r * 256 + threadIdx.x;
+            if (cap[r]) {
+                home[r] = set_home(S.umi[p], S.col[p], cap[r]);
+                cur[r] = ld128_relaxed(tbl[r] + home[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < PB; r++) {
+            const int p = p0 + r * 256 + threadIdx.x;
+            if (cap[r]) {
+                xg_e128 want;
+                want.a = S.umi[p];
+                want.b = (unsigned long long)S.col[p] + 1ull;
+                set_insert_from(tbl[r], cap[r], home[r], cur[r], want);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) S.n_pairs = 0;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 4) k_basefc_count(const __grid_constant__ BasefcDev P) {
+    __shared__ PairStage S;
+    const int t = P.tile0 + blockIdx.x;
+    const xg_tile tile = P.tiles[t];
     const xg_run run = P.runs[tile.run];
     const int32_t gid = run.gid;
     if (gid < 0 || gid >= P.n_gid) return;
-    const int32_t f0 = P.sf_goff[gid], f1 = P.sf_goff[gid + 1];
-    if (f0 == f1) return;
+    if (P.sf_goff[gid] == P.sf_goff[gid + 1]) return;
     const int32_t b0 = P.bnd_goff[gid], b1 = P.bnd_goff[gid + 1];
+    const int2 tb = P.tile_bnd[t];
+    const int32_t nb = tb.y - tb.x;
 
-    for (int32_t k = threadIdx.x; k < tile.n_rec; k += blockDim.x) {
-        const int64_t i = tile.rec_beg + k;
-        const int2 pe = P.pos_end[i];
-        const uint32_t fmq = P.fmq[i];
-        if (!read_passes_flags(P.fp, fmq)) continue;
-        const ulonglong2 ky = P.keys[i];
-        const uint64_t umi = ky.y;
-        if (umi == XG_KEY_NONE || umi == XG_KEY_EMPTY) continue;   // has_tag / `if umi:`
-        uint32_t col;
-        if (P.fp.use_cell_tag) {
-            if (ky.x == XG_KEY_NONE) continue;
-            int32_t c = barcode_lookup(P.bc, ky.x);
-            if (c < 0) continue;
-            col = (uint32_t)c;
-        } else {
-            col = (uint32_t)run.bam_idx;
+    // ---- the thread's records: independent, coalesced loads issued up front
+    int2 pe[RPT];
+    uint32_t fq[RPT], co[RPT];
+    ulonglong2 ky[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+        const int32_t k = threadIdx.x + r * 256;
+        const bool live = k < tile.n_rec;
+        const int64_t i = tile.rec_beg + (live ? k : 0);
+        pe[r] = P.pos_end[i];
+        fq[r] = P.fmq[i];
+        co[r] = P.cig_off[i];
+        ky[r] = P.keys[i];
+        if (!live) ky[r].y = XG_KEY_NONE;          // an absent UMI drops the record
+    }
+    // ---- stage the slice of the interval index under the tile window and the tile's CIGAR words
+    const uint32_t c_first = __ldg(&P.cig_off[tile.rec_beg]);
+    const uint32_t c_lo = c_first ? c_first - 1 : 0;      // one word back: a >=255-op count word
+    const uint32_t c_hi = __ldg(&P.cig_off[tile.rec_beg + tile.n_rec]);
+    const bool cig_staged = c_hi - c_lo <= CIG_CAP;
+    const bool staged = nb <= SB_MAX;
+    int32_t st_lo = 0, st_n = 0;
+    if (staged) {
+        st_lo = __ldg(&P.stab_off[tb.x]);
+        st_n = __ldg(&P.stab_off[tb.y]) - st_lo;
+        for (int k = threadIdx.x; k < nb; k += blockDim.x) S.bnd[k] = __ldg(&P.bnd[tb.x + k]);
+        for (int k = threadIdx.x; k <= nb; k += blockDim.x) S.stab_off[k] = __ldg(&P.stab_off[tb.x + k]);
+        if (st_n <= STAB_CAP)
+            for (int k = threadIdx.x; k < st_n; k += blockDim.x) S.stab4[k] = __ldg(&P.stab4[st_lo + k]);
+    }
+    const bool stab_staged = staged && st_n <= STAB_CAP;
+    if (cig_staged)
+        for (uint32_t k = threadIdx.x; k < c_hi - c_lo; k += blockDim.x) S.cigar[k] = __ldg(&P.cigar[c_lo + k]);
+    if (threadIdx.x == 0) S.n_pairs = 0;
+
+    // ---- cell lookup: the home slots of the records are probed together
+    int32_t colv[RPT];
+    if (P.fp.use_cell_tag) {
+        ulonglong2 slot[RPT];
+        uint32_t hs[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+            hs[r] = (uint32_t)mix64(ky[r].x) & P.bc.mask;
+            slot[r] = __ldg(&P.bc.slots[hs[r]]);
         }
-        // aligned length = len(read.positions)
-        uint32_t n_ops = fmq >> 24;
+#pragma unroll
+        for (int r = 0; r < RPT; r++) {
+            int32_t c = -1;
+            if (ky[r].x != XG_KEY_NONE) {
+                ulonglong2 e = slot[r];
+                uint32_t s = hs[r];
+                while (true) {
+                    if (e.x == ky[r].x) {
+                        c = (int32_t)e.y;
+                        break;
+                    }
+                    if (e.x == XG_KEY_NONE) break;
+                    s = (s + 1) & P.bc.mask;
+                    e = __ldg(&P.bc.slots[s]);
+                }
+            }
+            colv[r] = c;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < RPT; r++) colv[r] = run.bam_idx;
+    }
+    __syncthreads();
+
+    // ---- phase 1: filters, overlapping features, include test; passing pairs are staged
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+        do {
+        const uint32_t fmq = fq[r];
+        const uint64_t umi = ky[r].y;
+        if (P.ablate == 3) {
+            if (umi == 12345 && fmq == 77 && pe[r].x == 3) S.n_pairs = 1;
+            break;
+        }
+        if (umi == XG_KEY_NONE || umi == XG_KEY_EMPTY) break;   // has_tag / `if umi:`
+        if (!read_passes_flags(P.fp, fmq)) break;
+        if (colv[r] < 0) break;                                   // cell tag absent or not listed
+        const uint32_t col = (uint32_t)colv[r];
+        if (P.ablate == 2) {
+            if (col == 0x7fffffff) S.n_pairs = 1;
+            break;
+        }
+        const int32_t pos = pe[r].x, end = pe[r].y;
+        uint32_t n_ops = fmq >> 24;               // aligned length = len(read.positions)
         const uint32_t *cig = nullptr;
         int32_t aln;
         if (n_ops == 0) {
-            aln = pe.y - pe.x;
+            aln = end - pos;
         } else {
-            cig = P.cigar + P.cig_off[i];
-            if (n_ops == 255) n_ops = __ldg(cig - 1);
+            cig = cig_staged ? &S.cigar[co[r] - c_lo] : P.cigar + co[r];
+            if (n_ops == 255) n_ops = cig[-1];
             aln = 0;
             for (uint32_t q = 0; q < n_ops; q++) {
-                uint32_t w = __ldg(&cig[q]);
+                uint32_t w = cig[q];
                 if (cig_aligned(w & 15u)) aln += (int32_t)(w >> 4);
             }
         }
-        if (aln < P.fp.min_len) continue;
+        if (aln < P.fp.min_len) break;
         const int32_t need = P.incl_tab ? __ldg(&P.incl_tab[min(aln, P.incl_tab_len - 1)]) : P.incl_len;
 
-        // (1) features covering `pos`: stabbing list of the segment that contains it
-        {
-            int32_t lo = b0, hi = b1;          // upper_bound(bnd, pos)
+        // first boundary > pos (global index)
+        int32_t ub;
+        if (staged) {
+            int32_t lo = 0, hi = nb;
             while (lo < hi) {
                 int32_t mid = (lo + hi) >> 1;
-                if (__ldg(&P.bnd[mid]) <= pe.x) lo = mid + 1; else hi = mid;
+                if (S.bnd[mid] <= pos) lo = mid + 1; else hi = mid;
             }
-            int32_t seg = lo - 1;
-            if (seg >= b0) {
-                int32_t s1 = __ldg(&P.stab_off[seg + 1]);
-                for (int32_t s = __ldg(&P.stab_off[seg]); s < s1; s++)
-                    count_pair(P, __ldg(&P.stab[s]), pe.x, pe.y, cig, n_ops, need, umi, col);
+            ub = tb.x + lo;
+        } else {
+            int32_t lo = b0, hi = b1;
+            while (lo < hi) {
+                int32_t mid = (lo + hi) >> 1;
+                if (__ldg(&P.bnd[mid]) <= pos) lo = mid + 1; else hi = mid;
+            }
+            ub = lo;
+        }
+        // (1) features covering `pos`: stabbing list of the segment [bnd[ub-1], bnd[ub])
+        if (ub > b0) {
+            int32_t s0i, s1i;
+            if (staged && ub > tb.x) {
+                s0i = S.stab_off[ub - 1 - tb.x];
+                s1i = S.stab_off[ub - tb.x];
+            } else {
+                s0i = __ldg(&P.stab_off[ub - 1]);
+                s1i = __ldg(&P.stab_off[ub]);
+            }
+            for (int32_t s = s0i; s < s1i; s++) {
+                const int4 f = (stab_staged && s >= st_lo) ? S.stab4[s - st_lo] : __ldg(&P.stab4[s]);
+                emit_pair(P, S, f.x, f.y, f.z, pos, end, cig, n_ops, need, umi, col);
             }
         }
-        // (2) features starting inside (pos, end)
-        {
-            int32_t lo = f0, hi = f1;          // upper_bound(sf_beg, pos)
-            while (lo < hi) {
-                int32_t mid = (lo + hi) >> 1;
-                if (__ldg(&P.sf_beg[mid]) <= pe.x) lo = mid + 1; else hi = mid;
+        // (2) features beginning at a boundary inside (pos, end); every boundary from tb.y on is
+        // >= the tile's max end, so a staged tile never looks past its staged range
+        const int32_t kb_end = staged ? tb.y : b1;
+        for (int32_t kb = ub; kb < kb_end; kb++) {
+            const int32_t bv = staged ? S.bnd[kb - tb.x] : __ldg(&P.bnd[kb]);
+            if (bv >= end) break;
+            const int32_t j1 = __ldg(&P.fb[kb + 1]);
+            for (int32_t j = __ldg(&P.fb[kb]); j < j1; j++)
+                emit_pair(P, S, j, bv, __ldg(&P.sf_end[j]), pos, end, cig, n_ops, need, umi, col);
+        }
+        } while (false);
+        // deep feature overlap: drain the stage between rounds so that the next 256 records
+        // find room (the direct-insert path of emit_pair stays the last resort)
+        if (r + 1 < RPT) {
+            __syncthreads();
+            if (S.n_pairs > PAIR_CAP / 2) flush_pairs(P, S);
+        }
+    }
+    __syncthreads();
+
+    flush_pairs(P, S);
+}
+
+// Zero the sets of the features that become active in this epoch.  The segments are laid
+// end to end in a virtual byte space (pre[] = exclusive prefix, pre[n_seg] = total).
+#define ZERO_CHUNK 16384
+__global__ void __launch_bounds__(256) k_zero_segments(uint8_t *pool, const uint64_t *off,
+                                                       const uint64_t *pre, int32_t n_seg) {
+    const uint64_t total = pre[n_seg];
+    const uint64_t c0 = (uint64_t)blockIdx.x * ZERO_CHUNK;
+    int32_t lo = 0, hi = n_seg;          // last segment with pre <= c0
+    while (hi - lo > 1) {
+        int32_t mid = (lo + hi) >> 1;
+        if (pre[mid] <= c0) lo = mid; else hi = mid;
+    }
+    int32_t s = lo;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (uint64_t p = c0 + (uint64_t)threadIdx.x * 16; p < c0 + ZERO_CHUNK && p < total;
+         p += (uint64_t)blockDim.x * 16) {
+        while (p >= pre[s + 1]) s++;
+        *(uint4 *)(pool + off[s] + (p - pre[s])) = z;
+    }
+}
+
+// Reduce the set of a feature whose last epoch just finished to its row of the matrix:
+// histogram of the cells of its (cell, UMI) elements in shared memory plus a bitmap of the
+// touched cells; the set bits enumerated in order give the non-zeros in column order (the
+// reference's emit loop, rdr/fc/core.py:109-117).  The row goes to a staging area at an
+// atomically reserved offset; k_gather_rows puts the rows in input order.  Persistent CTAs:
+// histogram and bitmap are cleared while they are read, so the next feature starts clean.
+// When the cells do not fit the histogram (n_cols > hist_cols) the set is scanned once per
+// column range, first to count, then to write.
+__global__ void __launch_bounds__(256) k_basefc_finalize(const uint8_t *pool, const FeatDesc *fdesc,
+                                                         const int32_t *sf_row, const int32_t *fin_feat,
+                                                         int32_t n_fin, int32_t n_cols, int32_t hist_cols,
+                                                         unsigned long long *cursor, int64_t *seg_base,
+                                                         int32_t *seg_nnz, int32_t *st_col, int32_t *st_val) {
+    extern __shared__ uint32_t smem[];
+    uint32_t *hist = smem;                          // hist_cols
+    uint32_t *bitmap = smem + hist_cols;            // (hist_cols + 31) / 32
+    __shared__ int warp_tot[8];
+    __shared__ long long base_s;
+    const int n_words_max = (hist_cols + 31) >> 5;
+    for (int c = threadIdx.x; c < hist_cols; c += blockDim.x) hist[c] = 0;
+    for (int c = threadIdx.x; c < n_words_max; c += blockDim.x) bitmap[c] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n_pass = (n_cols + hist_cols - 1) / hist_cols;
+
+    for (int f = blockIdx.x; f < n_fin; f += gridDim.x) {
+        const int32_t j = fin_feat[f];
+        const FeatDesc fd = fdesc[j];
+        const xg_e128 *tbl = (const xg_e128 *)(pool + fd.blk_off);
+        long long base = 0;
+        // stage 0 (only when n_pass > 1): count; stage 1: write
+        for (int stage = (n_pass > 1 ? 0 : 1); stage < 2; stage++) {
+            int total_nz = 0;
+            for (int pass = 0; pass < n_pass; pass++) {
+                const uint32_t c_lo = (uint32_t)pass * (uint32_t)hist_cols;
+                const int nc = min(hist_cols, n_cols - (int)c_lo);
+                const int nw = (nc + 31) >> 5;
+                for (uint32_t s = threadIdx.x; s < fd.cap; s += blockDim.x) {
+                    const xg_e128 e = tbl[s];
+                    if (e.b != 0) {
+                        const uint32_t col = (uint32_t)(e.b - 1ull) - c_lo;
+                        if (col < (uint32_t)nc && atomicAdd(&hist[col], 1u) == 0)
+                            atomicOr(&bitmap[col >> 5], 1u << (col & 31));
+                    }
+                }
+                __syncthreads();
+                const bool writing = (stage == 1);
+                if (!writing || n_pass == 1) {            // non-zero cells of this range
+                    int nz = 0;
+                    for (int k = threadIdx.x; k < nw; k += blockDim.x) nz += __popc(bitmap[k]);
+                    for (int d = 16; d > 0; d >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, d);
+                    if (lane == 0) warp_tot[w] = nz;
+                    __syncthreads();
+                    for (int k = 0; k < 8; k++) total_nz += warp_tot[k];
+                    __syncthreads();
+                }
+                if (writing && n_pass == 1) {             // single range: reserve now
+                    if (threadIdx.x == 0) {
+                        const int32_t row = sf_row[j];
+                        long long b = total_nz ? (long long)atomicAdd(cursor, (unsigned long long)total_nz) : 0;
+                        seg_base[row] = b;
+                        seg_nnz[row] = total_nz;
+                        base_s = b;
+                    }
+                    __syncthreads();
+                    base = base_s;
+                }
+                // ordered walk over the bitmap words; clears histogram and bitmap as it goes
+                for (int k0 = 0; k0 < nw; k0 += blockDim.x) {
+                    const int k = k0 + threadIdx.x;
+                    uint32_t bits = k < nw ? bitmap[k] : 0u;
+                    int cnt = __popc(bits), incl = cnt;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        int y = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += y;
+                    }
+                    if (lane == 31) warp_tot[w] = incl;
+                    __syncthreads();
+                    int before = 0, tot = 0;
+                    for (int q = 0; q < 8; q++) {
+                        const int x = warp_tot[q];
+                        if (q < w) before += x;
+                        tot += x;
+                    }
+                    long long o = base + before + (incl - cnt);
+                    while (bits) {
+                        const int bpos = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const int c = (k << 5) + bpos;
+                        if (writing) {
+                            st_col[o] = (int32_t)(c_lo + (uint32_t)c);
+                            st_val[o] = (int32_t)hist[c];
+                            o++;
+                        }
+                        hist[c] = 0;
+                    }
+                    if (k < nw) bitmap[k] = 0;
+                    base += tot;
+                    __syncthreads();
+                }
             }
-            for (int32_t j = lo; j < f1 && __ldg(&P.sf_beg[j]) < pe.y; j++)
-                count_pair(P, j, pe.x, pe.y, cig, n_ops, need, umi, col);
+            if (stage == 0) {                             // multi-range: reserve after counting
+                if (threadIdx.x == 0) {
+                    const int32_t row = sf_row[j];
+                    long long b = total_nz ? (long long)atomicAdd(cursor, (unsigned long long)total_nz) : 0;
+                    seg_base[row] = b;
+                    seg_nnz[row] = total_nz;
+                    base_s = b;
+                }
+                __syncthreads();
+                base = base_s;
+            }
         }
     }
 }
 
-struct DenseCounts {
-    const uint32_t *counts;
-    int32_t n_cols;
-    __device__ int operator()(int row, int col) const {
-        return (int)counts[(size_t)row * (size_t)n_cols + col];
+__global__ void __launch_bounds__(256) k_gather_rows(int32_t n_rows, const int64_t *seg_base,
+                                                     const int32_t *seg_nnz, const int64_t *row_ptr,
+                                                     const int32_t *st_col, const int32_t *st_val,
+                                                     int32_t *o_row, int32_t *o_col, int32_t *o_val) {
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const int n = seg_nnz[row];
+        const int64_t src = seg_base[row], dst = row_ptr[row];
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            o_row[dst + k] = row;
+            o_col[dst + k] = st_col[src + k];
+            o_val[dst + k] = st_val[src + k];
+        }
     }
-};
+}
 
 }  // namespace
 
@@ -334,22 +827,14 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
         for (auto &r : rd->h_runs)
             if (r.bam_idx >= n_cols) return ctx->fail(XG_E_ARG, "more BAMs than sample columns");
 
+    // ---- interval index and per-feature tile windows (host), exact candidate counts (device)
     FeatIndexHost ix;
     int rc = build_feat_index(ctx, feats, n_gid, ix);
     if (rc) return rc;
-    std::vector<int64_t> cand;
-    feature_windows(rd, ix, cand);
-    size_t m = ix.sf_beg.size();
-    std::vector<uint64_t> tbl_base(m + 1, 0);
-    std::vector<uint32_t> tbl_cap(m, 0);
-    for (size_t j = 0; j < m; j++) {
-        int64_t c = cand[j];
-        int64_t cap = c > 0 ? c + c / 4 + 8 : 0;
-        if (cap >= (1LL << 32)) return ctx->fail(XG_E_LIMIT, "feature window exceeds 2^32 reads");
-        tbl_cap[j] = (uint32_t)cap;
-        tbl_base[j + 1] = tbl_base[j] + (uint64_t)cap;
-    }
-    const uint64_t tbl_total = tbl_base[m];
+    const size_t m = ix.sf_beg.size();
+    std::vector<Window> wins;
+    std::vector<int32_t> tlo, thi;
+    feature_windows(rd, ix, wins, tlo, thi);
 
     BasefcDev P;
     memset(&P, 0, sizeof(P));
@@ -361,17 +846,57 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     P.runs = rd->runs;
     P.tiles = rd->tiles;
     P.n_gid = n_gid;
-    P.n_cols = n_cols;
+    const int32_t *d_sf_row = nullptr;
+    const Window *d_wins = nullptr;
+    const int32_t *d_sf_beg = nullptr;
+    std::vector<int4> stab4(ix.stab.size());
+    for (size_t k = 0; k < ix.stab.size(); k++) {
+        const int32_t j = ix.stab[k];
+        stab4[k] = make_int4(j, ix.sf_beg[(size_t)j], ix.sf_end[(size_t)j], 0);
+    }
     if ((rc = upload_vec(ctx, ix.sf_goff, "fx_sf_goff", &P.sf_goff))) return rc;
-    if ((rc = upload_vec(ctx, ix.sf_beg, "fx_sf_beg", &P.sf_beg))) return rc;
+    if ((rc = upload_vec(ctx, ix.sf_beg, "fx_sf_beg", &d_sf_beg))) return rc;
     if ((rc = upload_vec(ctx, ix.sf_end, "fx_sf_end", &P.sf_end))) return rc;
-    if ((rc = upload_vec(ctx, ix.sf_row, "fx_sf_row", &P.sf_row))) return rc;
+    if ((rc = upload_vec(ctx, ix.sf_row, "fx_sf_row", &d_sf_row))) return rc;
     if ((rc = upload_vec(ctx, ix.bnd_goff, "fx_bnd_goff", &P.bnd_goff))) return rc;
     if ((rc = upload_vec(ctx, ix.bnd, "fx_bnd", &P.bnd))) return rc;
     if ((rc = upload_vec(ctx, ix.stab_off, "fx_stab_off", &P.stab_off))) return rc;
-    if ((rc = upload_vec(ctx, ix.stab, "fx_stab", &P.stab))) return rc;
-    if ((rc = upload_vec(ctx, tbl_base, "fx_tbl_base", &P.tbl_base))) return rc;
-    if ((rc = upload_vec(ctx, tbl_cap, "fx_tbl_cap", &P.tbl_cap))) return rc;
+    if ((rc = upload_vec(ctx, stab4, "fx_stab4", &P.stab4))) return rc;
+    if ((rc = upload_vec(ctx, ix.fb, "fx_fb", &P.fb))) return rc;
+    if ((rc = upload_vec(ctx, wins, "fx_wins", &d_wins))) return rc;
+    XG_GET(d_cand, unsigned long long, "fx_cand", m + 1);
+    XG_GET(d_tile_bnd, int2, "fx_tile_bnd", rd->n_tiles + 1);
+    P.tile_bnd = d_tile_bnd;
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    XG_CUDA(cudaMemsetAsync(d_cand, 0, sizeof(unsigned long long) * (m + 1), ctx->stream));
+    std::vector<unsigned long long> cand(m, 0);
+    if (!wins.empty()) {
+        k_window_cand<<<(unsigned)((wins.size() + 7) / 8), 256, 0, ctx->stream>>>(
+            d_wins, (int32_t)wins.size(), rd->tiles, rd->pos_end, d_sf_beg, P.sf_end, d_cand);
+        launches++;
+    }
+    if (rd->n_tiles > 0) {
+        k_tile_bounds<<<(rd->n_tiles + 255) / 256, 256, 0, ctx->stream>>>(rd->tiles, rd->runs, rd->n_tiles, n_gid,
+                                                                       P.bnd_goff, P.bnd, d_tile_bnd);
+        launches++;
+    }
+    if (m) XG_CUDA(cudaMemcpyAsync(cand.data(), d_cand, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    // ---- pool layout over epochs
+    int32_t epoch_tiles = 8192;
+    if (const char *e = getenv("XG_EPOCH_TILES")) epoch_tiles = std::max(1, atoi(e));
+    EpochPlan pl;
+    if ((rc = make_plan(ctx, cand, tlo, thi, rd->n_tiles, n_cols, epoch_tiles, pl))) return rc;
+    const int32_t *d_fin_feat = nullptr;
+    const uint64_t *d_zoff = nullptr, *d_zpre = nullptr;
+    std::vector<FeatDesc> fdesc(m);
+    for (size_t j = 0; j < m; j++) fdesc[j] = FeatDesc{pl.blk_off[j], pl.tbl_cap[j], 0};
+    if ((rc = upload_vec(ctx, fdesc, "fx_fdesc", &P.fdesc))) return rc;
+    if ((rc = upload_vec(ctx, pl.fin_feat, "fx_fin_feat", &d_fin_feat))) return rc;
+    if ((rc = upload_vec(ctx, pl.zseg_off, "fx_zseg_off", &d_zoff))) return rc;
+    if ((rc = upload_vec(ctx, pl.zseg_pre, "fx_zseg_pre", &d_zpre))) return rc;
     if (par->min_incl_tab) {
         if (par->min_incl_tab_len <= rd->max_aln_len)
             return ctx->fail(XG_E_ARG, "min_incl_tab shorter than max aligned length + 1");
@@ -381,6 +906,7 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
         XG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     P.incl_len = par->min_incl_len;
+    if (const char *e = getenv("XG_ABLATE")) P.ablate = atoi(e);
     P.fp.min_mapq = par->min_mapq;
     P.fp.min_len = par->min_len;
     P.fp.incl_flag = par->incl_flag;
@@ -391,36 +917,162 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     if (par->use_cell_tag) {
         if ((rc = xg_build_barcode_table(ctx, cells, &P.bc))) return rc;
     }
-    XG_GET(tbl, xg_e128, "fx_tbl", tbl_total + 1);
-    XG_GET(counts, uint32_t, "fx_counts", (size_t)n_rows * (size_t)n_cols + 1);
-    P.tbl = tbl;
-    P.counts = counts;
+    XG_GET(pool, uint8_t, "fx_pool", pl.pool_bytes + 16);
+    XG_GET(seg_base, int64_t, "fx_seg_base", n_rows + 1);
+    XG_GET(seg_nnz, int32_t, "fx_seg_nnz", n_rows + 1);
+    XG_GET(row_ptr, int64_t, "fx_row_ptr", n_rows + 2);
+    XG_GET(st_col, int32_t, "fx_st_col", pl.staging_cap + 1);
+    XG_GET(st_val, int32_t, "fx_st_val", pl.staging_cap + 1);
+    XG_GET(cursor, unsigned long long, "fx_cursor", 2);
+    P.pool = pool;
     XG_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors above are about to die
 
-    cudaEventRecord(ctx->ev[0], ctx->stream);
-    XG_CUDA(cudaMemsetAsync(tbl, 0, sizeof(xg_e128) * (size_t)tbl_total, ctx->stream));
-    XG_CUDA(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)n_rows * (size_t)n_cols, ctx->stream));
-    launches += 2;
-    cudaEventRecord(ctx->ev[1], ctx->stream);
-    if (rd->n_tiles > 0 && m > 0) {
-        k_basefc_count<<<rd->n_tiles, 256, 0, ctx->stream>>>(P);
-        launches++;
-        XG_CUDA(cudaGetLastError());
+    // shared-memory histogram (+ bitmap) of the finalize kernel: all cells if they fit
+    const int32_t hist_cols = std::min(n_cols, 40 * 1024);
+    const size_t hist_bytes = (size_t)hist_cols * 4 + (size_t)((hist_cols + 31) / 32) * 4;
+    XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+    const int fin_ctas_per_sm = std::max(1, std::min(8, (int)(200 * 1024 / (hist_bytes + 1024))));
+
+    // ---- device: epochs.  zero(e) -> count(e) -> finalize(e) per epoch; with overlap the three
+    // kinds run on their own streams and count(e+1) fills the SMs while count(e) drains:
+    //   zero(e)     waits finalize(e-2)           (its blocks were released by then)
+    //   count(e)    waits zero(e)                 (alternating between two streams)
+    //   finalize(e) waits count(e), count(e-1)
+    bool overlap = pl.n_epochs > 1;
+    if (const char *e = getenv("XG_OVERLAP")) overlap = overlap && atoi(e) != 0;
+    if (overlap && !ctx->aux[0])
+        for (auto &st : ctx->aux) XG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    while ((int32_t)ctx->ev_pool.size() < 4 * pl.n_epochs + 1) {
+        cudaEvent_t ev;
+        XG_CUDA(cudaEventCreate(&ev));
+        ctx->ev_pool.push_back(ev);
     }
-    cudaEventRecord(ctx->ev[2], ctx->stream);
-    DenseCounts dc{counts, n_cols};
-    rc = xg_dense_to_coo(ctx, dc, n_rows, n_cols, "fx", out, &launches);
-    if (rc) return rc;
-    cudaEventRecord(ctx->ev[3], ctx->stream);
+    auto EV = [&](int kind, int32_t e) { return ctx->ev_pool[(size_t)4 * e + kind]; };   // 0 Z, 1 S, 2 C, 3 F
+    cudaEvent_t ev_init = ctx->ev_pool[(size_t)4 * pl.n_epochs];
+    XG_CUDA(cudaMemsetAsync(seg_nnz, 0, sizeof(int32_t) * (size_t)(n_rows + 1), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(seg_base, 0, sizeof(int64_t) * (size_t)(n_rows + 1), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
+    launches += 4;
+    cudaEventRecord(ev_init, ctx->stream);
+    cudaStream_t st_z = overlap ? ctx->aux[0] : ctx->stream, st_f = overlap ? ctx->aux[1] : ctx->stream;
+    if (overlap) {
+        cudaStreamWaitEvent(st_z, ev_init, 0);
+        cudaStreamWaitEvent(st_f, ev_init, 0);
+        cudaStreamWaitEvent(ctx->aux[2], ev_init, 0);
+    }
+    for (int32_t e = 0; e < pl.n_epochs; e++) {
+        cudaStream_t st_c = overlap ? ((e & 1) ? ctx->aux[2] : ctx->stream) : ctx->stream;
+        const int32_t z0 = pl.zero_ptr[(size_t)e], z1 = pl.zero_ptr[(size_t)e + 1];
+        const int32_t n_seg = z1 - z0 - 1;
+        if (overlap && e >= 2) cudaStreamWaitEvent(st_z, EV(3, e - 2), 0);
+        if (n_seg > 0) {
+            const uint64_t total = pl.zseg_pre[(size_t)z1 - 1];
+            k_zero_segments<<<(unsigned)((total + ZERO_CHUNK - 1) / ZERO_CHUNK), 256, 0, st_z>>>(
+                pool, d_zoff + z0, d_zpre + z0, n_seg);
+            launches++;
+        }
+        cudaEventRecord(EV(0, e), st_z);
+        if (overlap) cudaStreamWaitEvent(st_c, EV(0, e), 0);
+        const int32_t t0 = e * pl.epoch_tiles, t1 = std::min(rd->n_tiles, t0 + pl.epoch_tiles);
+        cudaEventRecord(EV(1, e), st_c);
+        if (t1 > t0 && m > 0) {
+            P.tile0 = t0;
+            k_basefc_count<<<t1 - t0, 256, 0, st_c>>>(P);
+            launches++;
+        }
+        cudaEventRecord(EV(2, e), st_c);
+        const int32_t n_fin = pl.fin_ptr[(size_t)e + 1] - pl.fin_ptr[(size_t)e];
+        if (overlap) {
+            cudaStreamWaitEvent(st_f, EV(2, e), 0);
+            if (e > 0) cudaStreamWaitEvent(st_f, EV(2, e - 1), 0);
+        }
+        if (n_fin > 0) {
+            const int grid = std::min(n_fin, 148 * fin_ctas_per_sm);
+            k_basefc_finalize<<<grid, 256, hist_bytes, st_f>>>(
+                pool, P.fdesc, d_sf_row, d_fin_feat + pl.fin_ptr[(size_t)e], n_fin, n_cols, hist_cols, cursor,
+                seg_base, seg_nnz, st_col, st_val);
+            launches++;
+        }
+        cudaEventRecord(EV(3, e), st_f);
+    }
+    if (overlap) {
+        cudaStreamWaitEvent(ctx->stream, EV(3, pl.n_epochs - 1), 0);
+        cudaStreamWaitEvent(ctx->stream, EV(2, pl.n_epochs - 1), 0);
+        if (pl.n_epochs > 1) cudaStreamWaitEvent(ctx->stream, EV(2, pl.n_epochs - 2), 0);
+    }
+    XG_CUDA(cudaGetLastError());
+    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(seg_nnz, row_ptr, n_rows);
+    launches++;
+    int64_t nnz = 0;
+    XG_CUDA(cudaMemcpyAsync(&nnz, row_ptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
-    float t_all = 0, t_cnt = 0, t_zero = 0;
+    XG_GET(d_row, int32_t, "fx_coo_row", nnz + 1);
+    XG_GET(d_col, int32_t, "fx_coo_col", nnz + 1);
+    XG_GET(d_val, int32_t, "fx_coo_val", nnz + 1);
+    if (nnz > 0) {
+        k_gather_rows<<<std::min(n_rows, 148 * 32), 256, 0, ctx->stream>>>(n_rows, seg_base, seg_nnz, row_ptr,
+                                                                          st_col, st_val, d_row, d_col, d_val);
+        launches++;
+    }
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    XG_CUDA(cudaGetLastError());
+
+    // ---- result -> pinned host memory
+    xg_coo_owner *o = new xg_coo_owner();
+    memset(&o->m, 0, sizeof(o->m));
+    void *hp[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t hs[4] = {(size_t)(nnz + 1) * 4, (size_t)(nnz + 1) * 4, (size_t)(nnz + 1) * 4, (size_t)(n_rows + 1) * 8};
+    for (int k = 0; k < 4; k++)
+        if (cudaHostAlloc(&hp[k], hs[k], 0) != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < k; q++) cudaFreeHost(hp[q]);
+            delete o;
+            return ctx->fail(XG_E_NOMEM, "out of pinned host memory for the result");
+        }
+    o->bufs = {hp[0], hp[1], hp[2], hp[3]};
+    cudaEventRecord(ctx->ev[4], ctx->stream);
+    if (nnz > 0) {
+        cudaMemcpyAsync(hp[0], d_row, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(hp[1], d_col, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(hp[2], d_val, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaMemcpyAsync(hp[3], row_ptr, (size_t)(n_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaEventRecord(ctx->ev[5], ctx->stream);
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) {
+        for (void *p : o->bufs) cudaFreeHost(p);
+        delete o;
+        return ctx->fail(XG_E_CUDA, std::string("xg_basefc: ") + cudaGetErrorString(ce));
+    }
+    o->m.nnz = nnz;
+    o->m.n_rows = n_rows;
+    o->m.n_cols = n_cols;
+    o->m.row = (const int32_t *)hp[0];
+    o->m.col = (const int32_t *)hp[1];
+    o->m.val = (const int32_t *)hp[2];
+    o->m.row_ptr = (const int64_t *)hp[3];
+    *out = &o->m;
+
+    float t_all = 0, t_d2h = 0;
+    double t_cnt = 0;
     cudaEventElapsedTime(&t_all, ctx->ev[0], ctx->ev[3]);
-    cudaEventElapsedTime(&t_cnt, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&t_zero, ctx->ev[0], ctx->ev[1]);
-    ctx->timing[0] = t_all - ctx->timing[4];   // kernels (incl. zeroing + compaction), excl. result D2H
-    ctx->timing[1] = t_cnt;
+    cudaEventElapsedTime(&t_d2h, ctx->ev[4], ctx->ev[5]);
+    int n_cnt = 0;
+    for (int32_t e = 0; e < pl.n_epochs; e++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, EV(1, e), EV(2, e));     // per-launch duration on its own stream
+        t_cnt += t;
+        n_cnt++;
+    }
+    float t_span = 0;
+    cudaEventElapsedTime(&t_span, ev_init, ctx->ev[3]);
+    ctx->timing[0] = t_all;      // device time of the call: planning kernels, zero, count, finalize, gather
+    ctx->timing[1] = t_cnt;      // sum over epochs of the counting kernel
     ctx->timing[2] = launches;
-    ctx->timing[5] = t_zero;
-    ctx->timing[6] = (double)tbl_total * sizeof(xg_e128);
+    ctx->timing[3] = t_span;     // epochs + scan + gather (no host planning in between)
+    ctx->timing[4] = t_d2h;
+    ctx->timing[5] = pl.n_epochs;
+    ctx->timing[6] = (double)pl.pool_bytes;
+    ctx->timing[7] = (double)pl.staging_cap;
     return XG_OK;
 }

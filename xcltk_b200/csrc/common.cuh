@@ -40,7 +40,9 @@ struct xg_dreads {
 struct xg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux[3] = {};              // overlapped epochs: zero, finalize, second count stream
     cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> ev_pool;     // per-epoch timing events
     std::string err;
     double timing[8] = {};
     // growable named scratch buffers (avoid cudaMalloc/cudaFree on every call)
@@ -130,17 +132,17 @@ __device__ __forceinline__ bool cig_aligned(uint32_t op) { return op == 0 || op 
 __device__ __forceinline__ bool cig_skips_ref(uint32_t op) { return op == 2 || op == 3; }
 
 // Cell-barcode lookup table (open addressing, linear probing; empty = XG_KEY_NONE).
+// One 16-byte entry {key, column} per slot: a probe is a single 128-bit load.
 struct BarcodeTable {
-    const uint64_t *keys;
-    const int32_t *cols;
+    const ulonglong2 *slots;
     uint32_t mask;
 };
 __device__ __forceinline__ int32_t barcode_lookup(const BarcodeTable &t, uint64_t key) {
     uint32_t s = (uint32_t)mix64(key) & t.mask;
     while (true) {
-        uint64_t k = __ldg(&t.keys[s]);
-        if (k == key) return __ldg(&t.cols[s]);
-        if (k == XG_KEY_NONE) return -1;
+        const ulonglong2 e = __ldg(&t.slots[s]);
+        if (e.x == key) return (int32_t)e.y;
+        if (e.x == XG_KEY_NONE) return -1;
         s = (s + 1) & t.mask;
     }
 }

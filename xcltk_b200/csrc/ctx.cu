@@ -54,6 +54,9 @@ void xg_destroy(xg_ctx *ctx) {
             if (kv.second.p) cudaFree(kv.second.p);
         for (auto &ev : ctx->ev)
             if (ev) cudaEventDestroy(ev);
+        for (auto &ev : ctx->ev_pool) cudaEventDestroy(ev);
+        for (auto &st : ctx->aux)
+            if (st) cudaStreamDestroy(st);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -99,7 +102,7 @@ int xg_upload_reads(xg_ctx *ctx, const xg_reads *h, xg_dreads **out) {
     } cps[] = {
         {(void **)&d->pos_end, h->pos_end, n * 8},
         {(void **)&d->fmq, h->fmq, n * 4},
-        {(void **)&d->cig_off, h->cig_off, n * 4},
+        {(void **)&d->cig_off, h->cig_off, (n + 1) * 4},
         {(void **)&d->keys, h->keys, n * 16},
         {(void **)&d->seq_off, seq ? h->seq_off : nullptr, seq ? n * 4 : 0},
         {(void **)&d->cigar, h->cigar, (size_t)h->n_cigar * 4},
@@ -163,7 +166,7 @@ int xg_download_reads(xg_ctx *ctx, const xg_dreads *d, xg_reads **out) {
     o->r.n_records_seen = d->n_reads;
     o->r.pos_end = (const int32_t *)dl(d->pos_end, n * 8);
     o->r.fmq = (const uint32_t *)dl(d->fmq, n * 4);
-    o->r.cig_off = (const uint32_t *)dl(d->cig_off, n * 4);
+    o->r.cig_off = (const uint32_t *)dl(d->cig_off, (n + 1) * 4);
     o->r.keys = (const uint64_t *)dl(d->keys, n * 16);
     o->r.cigar = (const uint32_t *)dl(d->cigar, (size_t)d->n_cigar * 4);
     if (d->seq_off && d->seq) {
@@ -197,27 +200,22 @@ void xg_coo_free(xg_coo *m) {
 int xg_build_barcode_table(xg_ctx *ctx, const xg_barcodes *cells, BarcodeTable *out) {
     uint32_t cap = 16;
     while (cap < (uint32_t)cells->n * 2u + 2u) cap <<= 1;
-    std::vector<uint64_t> k(cap, XG_KEY_NONE);
-    std::vector<int32_t> v(cap, -1);
+    std::vector<ulonglong2> tab(cap, make_ulonglong2(XG_KEY_NONE, 0));
     for (int32_t i = 0; i < cells->n; i++) {
         uint64_t key = cells->keys[i];
         if (key == XG_KEY_NONE || key == XG_KEY_NOMATCH)
             return ctx->fail(XG_E_ARG, "invalid barcode key");
         uint32_t s = (uint32_t)mix64(key) & (cap - 1);
-        while (k[s] != XG_KEY_NONE) {
-            if (k[s] == key) return ctx->fail(XG_E_ARG, "duplicate barcode key");
+        while (tab[s].x != XG_KEY_NONE) {
+            if (tab[s].x == key) return ctx->fail(XG_E_ARG, "duplicate barcode key");
             s = (s + 1) & (cap - 1);
         }
-        k[s] = key;
-        v[s] = i;
+        tab[s] = make_ulonglong2(key, (unsigned long long)i);
     }
-    XG_GET(dk, uint64_t, "bc_keys", cap);
-    XG_GET(dv, int32_t, "bc_cols", cap);
-    XG_CUDA(cudaMemcpyAsync(dk, k.data(), cap * 8, cudaMemcpyHostToDevice, ctx->stream));
-    XG_CUDA(cudaMemcpyAsync(dv, v.data(), cap * 4, cudaMemcpyHostToDevice, ctx->stream));
-    XG_CUDA(cudaStreamSynchronize(ctx->stream));   // k, v go out of scope
-    out->keys = dk;
-    out->cols = dv;
+    XG_GET(dt, ulonglong2, "bc_slots", cap);
+    XG_CUDA(cudaMemcpyAsync(dt, tab.data(), (size_t)cap * 16, cudaMemcpyHostToDevice, ctx->stream));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));   // tab goes out of scope
+    out->slots = dt;
     out->mask = cap - 1;
     return XG_OK;
 }

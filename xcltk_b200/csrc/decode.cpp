@@ -495,7 +495,7 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
         for (auto &r : bm.runs) n_tiles += (r.end - r.beg + XG_TILE - 1) / XG_TILE;
     int32_t *pos_end = (int32_t *)alloc(sizeof(int32_t) * 2 * (size_t)n_total);
     uint32_t *fmq = (uint32_t *)alloc(sizeof(uint32_t) * (size_t)n_total);
-    uint32_t *cig_off = (uint32_t *)alloc(sizeof(uint32_t) * (size_t)n_total);
+    uint32_t *cig_off = (uint32_t *)alloc(sizeof(uint32_t) * ((size_t)n_total + 1));
     uint64_t *keys = (uint64_t *)alloc(sizeof(uint64_t) * 2 * (size_t)n_total);
     uint32_t *seq_off = want_seq ? (uint32_t *)alloc(sizeof(uint32_t) * (size_t)n_total) : nullptr;
     uint32_t *cigar = (uint32_t *)alloc(sizeof(uint32_t) * (size_t)cig_total);
@@ -564,6 +564,8 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
             }
         });
     }
+
+    cig_off[n_total] = (uint32_t)cig_total;    // sentinel: end of the last read's words
 
     // runs + tile index
     int32_t ri = 0;

@@ -369,7 +369,7 @@ extern "C" int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *sp, xg_dreads 
     }
     SYN_MALLOC(d->pos_end, (size_t)N * 8);
     SYN_MALLOC(d->fmq, (size_t)N * 4);
-    SYN_MALLOC(d->cig_off, (size_t)N * 4);
+    SYN_MALLOC(d->cig_off, ((size_t)N + 1) * 4);
     SYN_MALLOC(d->keys, (size_t)N * 16);
     if (sp->want_seq) {
         SYN_MALLOC(d->seq_off, (size_t)N * 4);
@@ -418,6 +418,11 @@ extern "C" int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *sp, xg_dreads 
     SYN_MALLOC(d->cigar, (size_t)n_cig * 4);
     d->n_cigar = n_cig;
 
+    {
+        uint32_t sentinel = (uint32_t)n_cig;
+        cudaMemcpyAsync(d->cig_off + N, &sentinel, 4, cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+    }
     SynthDev P;
     memset(&P, 0, sizeof(P));
     P.n_reads = N;
