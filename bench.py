@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- reads/sec counted (basefc + baf fc) on synthetic 10x-style batches.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A step = one pass of both hot paths over one batch per GPU:
+  basefc on config C3 (10k cells, 300M reads, ~60k features: hg38 genes + seeded nested intervals)
+  baf fc  on config C2 (5k cells, 50M reads chr1-22, 200k phased het SNPs)
+`value` = reads counted / step time with the records already resident in HBM; `e2e` = the
+same through the C-ABI with HOST (pinned) record buffers, H2D upload and D2H result copy
+inside the timed region.  Multi-GPU: one batch (library) per GPU, no collective ("weak").
+The reference arm times the CPU oracle (a C port of the reference's algorithm; the
+reference itself is Python on pysam and cannot run on the box) on a bounded sample.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+C_BAR = 1.43                      # mean CIGAR ops per read of the synthetic mix
+BASEFC_BYTES_PER_READ = 28 + 4 * C_BAR
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as fp:
+                return float(json.load(fp)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def barrier_sync(dist, local):
+    import torch
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(local)
+
+
+def max_over_ranks(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+class Batch(object):
+    """One GPU's workload: device-resident records + the pinned host copy used by e2e."""
+
+    def __init__(self, ctx, args, rank):
+        from xcltk_b200 import workload
+        self.ctx = ctx
+        seed = 7 + 1000 * rank
+        self.fc = workload.make_basefc_workload(ctx, args.reads, args.cells, args.features, seed=seed)
+        self.baf = workload.make_baf_workload(ctx, args.baf_reads, args.baf_cells, args.snps, seed=seed + 1)
+        self.n_reads = args.reads + args.baf_reads
+        self.keep = None
+
+    def step_device(self):
+        ctx, fc, bf = self.ctx, self.fc, self.baf
+        launches = 0
+        row, col, val, _ = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params)
+        t_fc = ctx.timing()
+        launches += int(t_fc[2])
+        totals, st = ctx.baf_pileup(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
+        t_p = ctx.timing()
+        launches += int(t_p[2])
+        keep = (totals.sum(axis=1) >= 1).astype(np.uint8)        # min_count=1, min_maf=0 (pipeline values)
+        ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, keep, True)
+        t_c = ctx.timing()
+        launches += int(t_c[2])
+        st.close()
+        return dict(nnz=len(val), checksum=int(val.sum()) + int(dp[2].sum()) + int(ad[2].sum()),
+                    launches=launches, t_fc=t_fc, t_pileup=t_p, t_count=t_c,
+                    out_bytes=12 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])))
+
+    def make_host(self):
+        self.h_fc = self.fc.dreads.download()         # pinned host record arrays
+        self.h_baf = self.baf.dreads.download()
+
+    def step_e2e(self):
+        ctx, fc, bf = self.ctx, self.fc, self.baf
+        d_fc = ctx.upload(self.h_fc)
+        row, col, val, _ = ctx.basefc(d_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params)
+        d_fc.close()
+        d_bf = ctx.upload(self.h_baf)
+        totals, st = ctx.baf_pileup(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
+        keep = (totals.sum(axis=1) >= 1).astype(np.uint8)
+        ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, keep, True)
+        st.close()
+        d_bf.close()
+        return dict(h2d=self.h_fc.nbytes() + self.h_baf.nbytes(),
+                    d2h=12 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])) + totals.nbytes)
+
+
+def cpu_sample(ctx, args, n_sample, n_threads):
+    """A bounded sample of the basefc workload (same generator, fewer reads) for the CPU legs."""
+    from xcltk_b200 import workload
+    from oracle import oracle
+    w = workload.make_basefc_workload(ctx, n_sample, args.cells, args.features, seed=99)
+    host = w.dreads.download()
+    conf = workload.Conf()
+    par = oracle.params(conf)
+
+    def run():
+        t = time.perf_counter()
+        oracle.basefc(host, w.gid, w.beg, w.end, w.cell_keys, args.cells, par, n_threads)
+        return time.perf_counter() - t
+    return run, host
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=float, default=300e6, help="basefc reads per GPU (C3: 300M)")
+    ap.add_argument("--cells", type=int, default=10000)
+    ap.add_argument("--features", type=int, default=60000)
+    ap.add_argument("--baf-reads", type=float, default=50e6, help="baf reads per GPU (C2)")
+    ap.add_argument("--baf-cells", type=int, default=5000)
+    ap.add_argument("--snps", type=int, default=200000)
+    ap.add_argument("--cpu-sample", type=float, default=4e6, help="reads of the CPU baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.reads, args.baf_reads, args.cpu_sample = int(args.reads), int(args.baf_reads), int(args.cpu_sample)
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    from xcltk_b200 import engine
+    workload_name = ("basefc C3 (%d cells, %.0fM reads, %d features: hg38 genes + nested) + baf fc C2 "
+                     "(%d cells, %.0fM reads chr1-22, %d phased het SNPs), per GPU" % (
+                         args.cells, args.reads / 1e6, args.features, args.baf_cells, args.baf_reads / 1e6,
+                         args.snps))
+    config = {"workload": workload_name, "reads_per_gpu": args.reads + args.baf_reads,
+              "partition": "one batch (library) per GPU, no collective",
+              "l2_policy": "inputs (%.1f GB of records per step) are larger than L2" % (
+                  (args.reads * BASEFC_BYTES_PER_READ + args.baf_reads * 8) / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ctx = engine.get_context(local)
+        n_thr = os.cpu_count() or 1
+        run, host = cpu_sample(ctx, args, args.cpu_sample, n_thr)
+        for _ in range(args.warmup):
+            run()
+        ts = [run() for _ in range(args.steps)]
+        v = args.cpu_sample / (sum(ts) / len(ts))
+        line = {"impl": "reference", "metric": "reads/sec counted (basefc + baf fc)", "value": v, "unit": "reads/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64 keys / i32 counts", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": n_thr, "kind": "port",
+                                 "sample": "basefc on %d reads of the C3 generator (oracle/xg_oracle.c, OpenMP "
+                                           "over features like the reference's process pool)" % args.cpu_sample},
+                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    ctx = engine.get_context(local)
+    batch = Batch(ctx, args, rank)
+    for _ in range(args.warmup):
+        info = batch.step_device()
+    sampler = ClockSampler(local)
+    barrier_sync(dist, local)
+    sampler.start()
+    t0 = time.perf_counter()
+    infos = [batch.step_device() for _ in range(args.steps)]
+    barrier_sync(dist, local)
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dt = max_over_ranks(dist, local, dt)
+    total_reads = sum_over_ranks(dist, local, float(batch.n_reads))
+    value = total_reads * args.steps / dt
+    info = infos[-1]
+
+    # roofline of the dominant kernel (k_basefc_count): algorithmic bytes / its summed launch time
+    peak, peak_src = peaks()
+    t_cnt_ms = float(np.mean([i["t_fc"][1] for i in infos]))
+    n_epochs = int(info["t_fc"][5])
+    alg_bytes = args.reads * BASEFC_BYTES_PER_READ + 12.0 * info["nnz"]
+    achieved = alg_bytes / (t_cnt_ms * 1e-3) / 1e9
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tj):
+        try:
+            with open(tj) as fp:
+                traffic = json.load(fp).get("k_basefc_count_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_basefc_count", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                "launches_per_step": n_epochs, "avg_launch_ms": t_cnt_ms / max(1, n_epochs),
+                "algorithmic_bytes_per_launch": alg_bytes / max(1, n_epochs),
+                "note": "launch durations from CUDA events on the launching streams; epochs overlap, so the "
+                        "sum over-counts (conservative)"}
+
+    e2e = None
+    if not args.no_e2e:
+        try:
+            batch.make_host()
+            for _ in range(2):
+                batch.step_e2e()
+            barrier_sync(dist, local)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                io = batch.step_e2e()
+            barrier_sync(dist, local)
+            de = max_over_ranks(dist, local, time.perf_counter() - t0)
+            e2e = {"value": total_reads * args.steps / de, "unit": "reads/s", "h2d_bytes_per_step": io["h2d"],
+                   "d2h_bytes_per_step": io["d2h"], "ms_per_step": 1e3 * de / args.steps}
+        except Exception as ex:            # e.g. not enough pinned host memory on the box
+            e2e = {"value": None, "unit": "reads/s", "error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle  # noqa: F401
+        run, host = cpu_sample(ctx, args, args.cpu_sample, os.cpu_count() or 1)
+        run()
+        t = run()
+        cpu = {"value": args.cpu_sample / t, "unit": "reads/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": "basefc on %d reads of the C3 generator with the C oracle, %.1f s" % (args.cpu_sample, t)}
+
+    if rank == 0:
+        line = {"metric": "reads/sec counted (basefc + baf fc)", "value": value, "unit": "reads/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64 keys / i32 counts", "data": "synthetic", "config": config,
+                "e2e": e2e, "gpu_launches": int(sum(i["launches"] for i in infos)), "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu,
+                "detail": {"basefc_device_ms": float(np.mean([i["t_fc"][0] for i in infos])),
+                           "basefc_epoch_span_ms": float(np.mean([i["t_fc"][3] for i in infos])),
+                           "basefc_count_kernel_ms": t_cnt_ms,
+                           "baf_pileup_ms": float(np.mean([i["t_pileup"][0] for i in infos])),
+                           "baf_scan_kernel_ms": float(np.mean([i["t_pileup"][1] for i in infos])),
+                           "baf_count_ms": float(np.mean([i["t_count"][0] for i in infos])),
+                           "basefc_nnz": info["nnz"], "checksum": info["checksum"],
+                           "basefc_reads_per_s_kernels_only": args.reads / (
+                               float(np.mean([i["t_fc"][3] for i in infos])) * 1e-3)}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

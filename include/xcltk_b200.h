@@ -173,7 +173,8 @@ typedef struct {
     int32_t n_samples;     /* number of columns (= n in barcode mode, #BAMs otherwise)    */
 } xg_barcodes;
 
-/* Sparse result, sorted by (row, col), 0-based; library-owned host memory.               */
+/* Sparse result, sorted by (row, col), 0-based; library-owned pinned host memory, valid until
+ * xg_coo_free() (which must be called before the context is destroyed).               */
 typedef struct {
     int64_t nnz;
     int32_t n_rows, n_cols;
@@ -237,10 +238,12 @@ typedef struct {
 } xg_synth_params;
 int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *p, xg_dreads **out, uint64_t *barcode_keys);
 
-/* Timing of the last xg_basefc / xg_baf_* call, measured with CUDA events on the
- * library's stream: [0] all kernels of the call (ms), [1] dominant counting kernel (ms),
- * [2] number of kernel launches, [3] H2D ms, [4] D2H ms.                                  */
-void xg_last_timing(xg_ctx *ctx, double out[8]);
+/* Timing of the last xg_basefc / xg_baf_* call (CUDA events on the library's streams, ms):
+ * [0] device span of the call  [1] sum of the dominant counting kernel's launches
+ * [2] kernel launches          [3] span of the epoch loop + gather (basefc)
+ * [4] result D2H               [5] epochs (basefc)   [6] pool bytes / pairs   [7] staging entries
+ * [8..11] host phases of xg_basefc (ms): index build, windows, plan, uploads; [12] whole call. */
+void xg_last_timing(xg_ctx *ctx, double out[16]);
 
 const char *xg_version(void);
 

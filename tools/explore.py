@@ -16,6 +16,7 @@ for it in range(3):
     tm = ctx.timing()
     print("basefc n=%d cells=%d feats=%d nnz=%d sum=%d wall=%.1fms kern=%.2fms count=%.2fms epochs=%d launches=%d pool=%.1fMB staging=%.1fM d2h=%.2fms" % (
         n_reads, n_cells, n_feat, len(val), int(val.sum()), dt * 1e3, tm[0], tm[1], tm[5], tm[2], tm[6] / 1e6, tm[7] / 1e6, tm[4]))
+    print("   host ms: index=%.1f windows=%.1f plan=%.1f upload=%.1f call=%.1f span=%.2f" % (tm[8], tm[9], tm[10], tm[11], tm[12], tm[3]))
 
 if len(sys.argv) > 4:
     nb = int(float(sys.argv[4]))

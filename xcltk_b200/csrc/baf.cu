@@ -311,12 +311,12 @@ struct CooAccum {
         void *p[4] = {nullptr, nullptr, nullptr, nullptr};
         size_t sz[4] = {(nnz + 1) * 4, (nnz + 1) * 4, (nnz + 1) * 4, row_ptr.size() * 8};
         for (int k = 0; k < 4; k++)
-            if (cudaHostAlloc(&p[k], sz[k], 0) != cudaSuccess) {
-                cudaGetLastError();
-                for (int q = 0; q < k; q++) cudaFreeHost(p[q]);
+            if (!(p[k] = ctx->pinned_get(sz[k]))) {
+                for (int q = 0; q < k; q++) ctx->pinned_put(p[q]);
                 delete o;
                 return ctx->fail(XG_E_NOMEM, "out of pinned host memory");
             }
+        o->ctx = ctx;
         if (nnz) {
             memcpy(p[0], row.data(), nnz * 4);
             memcpy(p[1], col.data(), nnz * 4);

@@ -17,6 +17,7 @@
 // are counted independently (a read overlapping k features is evaluated k times), exactly as
 // the reference does.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <iterator>
@@ -828,13 +829,22 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
             if (r.bam_idx >= n_cols) return ctx->fail(XG_E_ARG, "more BAMs than sample columns");
 
     // ---- interval index and per-feature tile windows (host), exact candidate counts (device)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+    };
+    const auto t_call = now();
+    auto t_ph = now();
     FeatIndexHost ix;
     int rc = build_feat_index(ctx, feats, n_gid, ix);
     if (rc) return rc;
     const size_t m = ix.sf_beg.size();
+    const double ms_index = ms_since(t_ph);
+    t_ph = now();
     std::vector<Window> wins;
     std::vector<int32_t> tlo, thi;
     feature_windows(rd, ix, wins, tlo, thi);
+    const double ms_windows = ms_since(t_ph);
 
     BasefcDev P;
     memset(&P, 0, sizeof(P));
@@ -888,7 +898,10 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     int32_t epoch_tiles = 8192;
     if (const char *e = getenv("XG_EPOCH_TILES")) epoch_tiles = std::max(1, atoi(e));
     EpochPlan pl;
+    t_ph = now();
     if ((rc = make_plan(ctx, cand, tlo, thi, rd->n_tiles, n_cols, epoch_tiles, pl))) return rc;
+    const double ms_plan = ms_since(t_ph);
+    t_ph = now();
     const int32_t *d_fin_feat = nullptr;
     const uint64_t *d_zoff = nullptr, *d_zpre = nullptr;
     std::vector<FeatDesc> fdesc(m);
@@ -926,6 +939,7 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     XG_GET(cursor, unsigned long long, "fx_cursor", 2);
     P.pool = pool;
     XG_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors above are about to die
+    const double ms_upload = ms_since(t_ph);
 
     // shared-memory histogram (+ bitmap) of the finalize kernel: all cells if they fit
     const int32_t hist_cols = std::min(n_cols, 40 * 1024);
@@ -1023,13 +1037,13 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     void *hp[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t hs[4] = {(size_t)(nnz + 1) * 4, (size_t)(nnz + 1) * 4, (size_t)(nnz + 1) * 4, (size_t)(n_rows + 1) * 8};
     for (int k = 0; k < 4; k++)
-        if (cudaHostAlloc(&hp[k], hs[k], 0) != cudaSuccess) {
-            cudaGetLastError();
-            for (int q = 0; q < k; q++) cudaFreeHost(hp[q]);
+        if (!(hp[k] = ctx->pinned_get(hs[k]))) {
+            for (int q = 0; q < k; q++) ctx->pinned_put(hp[q]);
             delete o;
             return ctx->fail(XG_E_NOMEM, "out of pinned host memory for the result");
         }
     o->bufs = {hp[0], hp[1], hp[2], hp[3]};
+    o->ctx = ctx;
     cudaEventRecord(ctx->ev[4], ctx->stream);
     if (nnz > 0) {
         cudaMemcpyAsync(hp[0], d_row, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1040,7 +1054,7 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     cudaEventRecord(ctx->ev[5], ctx->stream);
     cudaError_t ce = cudaStreamSynchronize(ctx->stream);
     if (ce != cudaSuccess) {
-        for (void *p : o->bufs) cudaFreeHost(p);
+        for (void *p : o->bufs) ctx->pinned_put(p);
         delete o;
         return ctx->fail(XG_E_CUDA, std::string("xg_basefc: ") + cudaGetErrorString(ce));
     }
@@ -1074,5 +1088,10 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     ctx->timing[5] = pl.n_epochs;
     ctx->timing[6] = (double)pl.pool_bytes;
     ctx->timing[7] = (double)pl.staging_cap;
+    ctx->timing[8] = ms_index;
+    ctx->timing[9] = ms_windows;
+    ctx->timing[10] = ms_plan;
+    ctx->timing[11] = ms_upload;
+    ctx->timing[12] = ms_since(t_call);
     return XG_OK;
 }

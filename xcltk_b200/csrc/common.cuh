@@ -44,13 +44,58 @@ struct xg_ctx {
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> ev_pool;     // per-epoch timing events
     std::string err;
-    double timing[8] = {};
+    double timing[16] = {};
     // growable named scratch buffers (avoid cudaMalloc/cudaFree on every call)
     struct Buf {
         void *p = nullptr;
         size_t cap = 0;
     };
     std::map<std::string, Buf> scratch;
+
+    // pinned host buffers of results are recycled (cudaHostAlloc of GBs costs ~100 ms/GB)
+    struct Pinned {
+        void *p;
+        size_t cap;
+        bool used;
+    };
+    std::vector<Pinned> pinned;
+    void *pinned_get(size_t bytes) {
+        size_t best = pinned.size();
+        for (size_t k = 0; k < pinned.size(); k++)
+            if (!pinned[k].used && pinned[k].cap >= bytes && (best == pinned.size() || pinned[k].cap < pinned[best].cap))
+                best = k;
+        if (best < pinned.size()) {
+            pinned[best].used = true;
+            return pinned[best].p;
+        }
+        void *p = nullptr;
+        size_t want = bytes + bytes / 8 + 4096;
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            for (auto it = pinned.begin(); it != pinned.end();)      // drop idle buffers and retry
+                if (!it->used) {
+                    cudaFreeHost(it->p);
+                    it = pinned.erase(it);
+                } else {
+                    ++it;
+                }
+            want = bytes ? bytes : 4096;
+            if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        pinned.push_back(Pinned{p, want, true});
+        return p;
+    }
+    void pinned_put(void *p) {
+        for (auto &b : pinned)
+            if (b.p == p) {
+                b.used = false;
+                return;
+            }
+        cudaFreeHost(p);
+    }
 
     int fail(int code, const std::string &msg) {
         err = msg;

@@ -115,16 +115,18 @@ int xg_dense_to_coo(xg_ctx *ctx, V v, int32_t n_rows, int32_t n_cols, const char
     memset(&o->m, 0, sizeof(o->m));
     void *h_row = nullptr, *h_col = nullptr, *h_val = nullptr, *h_ptr = nullptr;
     size_t nb = (size_t)(nnz > 0 ? nnz : 1) * 4;
-    if (cudaHostAlloc(&h_row, nb, 0) != cudaSuccess || cudaHostAlloc(&h_col, nb, 0) != cudaSuccess ||
-        cudaHostAlloc(&h_val, nb, 0) != cudaSuccess ||
-        cudaHostAlloc(&h_ptr, (size_t)(n_rows + 1) * 8, 0) != cudaSuccess) {
-        cudaGetLastError();
+    h_row = ctx->pinned_get(nb);
+    h_col = ctx->pinned_get(nb);
+    h_val = ctx->pinned_get(nb);
+    h_ptr = ctx->pinned_get((size_t)(n_rows + 1) * 8);
+    if (!h_row || !h_col || !h_val || !h_ptr) {
         for (void *p : {h_row, h_col, h_val, h_ptr})
-            if (p) cudaFreeHost(p);
+            if (p) ctx->pinned_put(p);
         delete o;
         return ctx->fail(XG_E_NOMEM, "out of pinned host memory for the result");
     }
     o->bufs = {h_row, h_col, h_val, h_ptr};
+    o->ctx = ctx;
     cudaEventRecord(ctx->ev[4], ctx->stream);
     if (nnz > 0) {
         cudaMemcpyAsync(h_row, d_row, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -135,7 +137,7 @@ int xg_dense_to_coo(xg_ctx *ctx, V v, int32_t n_rows, int32_t n_cols, const char
     cudaEventRecord(ctx->ev[5], ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
-        for (void *p : o->bufs) cudaFreeHost(p);
+        for (void *p : o->bufs) ctx->pinned_put(p);
         delete o;
         return ctx->fail(XG_E_CUDA, std::string("result D2H: ") + cudaGetErrorString(e));
     }

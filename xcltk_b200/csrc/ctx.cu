@@ -57,6 +57,7 @@ void xg_destroy(xg_ctx *ctx) {
         for (auto &ev : ctx->ev_pool) cudaEventDestroy(ev);
         for (auto &st : ctx->aux)
             if (st) cudaStreamDestroy(st);
+        for (auto &b : ctx->pinned) cudaFreeHost(b.p);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -64,8 +65,8 @@ void xg_destroy(xg_ctx *ctx) {
 
 const char *xg_last_error(xg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-void xg_last_timing(xg_ctx *ctx, double out[8]) {
-    for (int i = 0; i < 8; i++) out[i] = ctx->timing[i];
+void xg_last_timing(xg_ctx *ctx, double out[16]) {
+    for (int i = 0; i < 16; i++) out[i] = ctx->timing[i];
 }
 
 int64_t xg_dreads_n(const xg_dreads *d) { return d ? d->n_reads : 0; }
@@ -189,7 +190,9 @@ int xg_download_reads(xg_ctx *ctx, const xg_dreads *d, xg_reads **out) {
 void xg_coo_free(xg_coo *m) {
     if (!m) return;
     xg_coo_owner *o = reinterpret_cast<xg_coo_owner *>(m);
-    for (void *p : o->bufs) cudaFreeHost(p);
+    for (void *p : o->bufs) {
+        if (o->ctx) o->ctx->pinned_put(p); else cudaFreeHost(p);
+    }
     delete o;
 }
 

@@ -10,7 +10,9 @@ struct xg_reads_owner {
     void (*free_fn)(void *) = nullptr;
 };
 
+struct xg_ctx;
 struct xg_coo_owner {
     xg_coo m;
-    std::vector<void *> bufs;   // pinned (cudaFreeHost)
+    std::vector<void *> bufs;   // pinned; returned to ctx's pool (or cudaFreeHost when ctx is null)
+    xg_ctx *ctx = nullptr;
 };

@@ -271,16 +271,45 @@ def decode_bams(paths, tid_maps, cell_tag, umi_tag, want_seq, keyspace, n_thread
     return HostReads(out)
 
 
-def coo_to_numpy(lib, pcoo, free=True):
+class _CooOwner(object):
+    """Keeps a library-owned xg_coo alive while numpy views of it exist."""
+
+    def __init__(self, lib, pcoo, ctx_obj=None):
+        self.lib, self.pcoo, self.ctx_obj = lib, pcoo, ctx_obj   # ctx_obj: the Context must outlive us
+
+    def __del__(self):
+        try:
+            self.lib.xg_coo_free(self.pcoo)
+        except Exception:
+            pass
+
+
+class _View(np.ndarray):
+    """ndarray view that carries a reference to the owner of its memory."""
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
+def coo_to_numpy(lib, pcoo, copy_below=1 << 16, ctx_obj=None):
+    """(row, col, val, shape).  Large results are zero-copy views of the library's pinned
+    buffers (released when the last view dies); small ones are copied and freed at once."""
     m = pcoo.contents
     nnz = int(m.nnz)
-    row = np_view(m.row, nnz, np.int32).copy()
-    col = np_view(m.col, nnz, np.int32).copy()
-    val = np_view(m.val, nnz, np.int32).copy()
     shape = (int(m.n_rows), int(m.n_cols))
-    if free:
+    views = [np_view(p, nnz, np.int32) for p in (m.row, m.col, m.val)]
+    if nnz <= copy_below:
+        out = [v.copy() for v in views]
         lib.xg_coo_free(pcoo)
-    return row, col, val, shape
+        return out[0], out[1], out[2], shape
+    owner = _CooOwner(lib, pcoo, ctx_obj)
+    out = []
+    for v in views:
+        w = v.view(_View)
+        w._owner = owner
+        out.append(w)
+    return out[0], out[1], out[2], shape
 
 
 class Context(object):
@@ -307,7 +336,7 @@ class Context(object):
         return DeviceReads(self, d)
 
     def timing(self):
-        t = (C.c_double * 8)()
+        t = (C.c_double * 16)()
         self.lib.xg_last_timing(self.h, t)
         return list(t)
 
@@ -321,7 +350,7 @@ class Context(object):
         out = C.POINTER(Coo)()
         self._check(self.lib.xg_basefc(self.h, dreads.h, C.byref(f), C.byref(b), C.byref(params.c),
                                        C.byref(out)))
-        return coo_to_numpy(self.lib, out)
+        return coo_to_numpy(self.lib, out, ctx_obj=self)
 
     def baf_pileup(self, dreads, gid, pos, cell_keys, n_samples, params):
         gid = np.ascontiguousarray(gid, dtype=np.int32)
@@ -345,7 +374,7 @@ class Context(object):
                                           as_ptr(reg_snp, c_i32p), as_ptr(hap_of, c_u8p),
                                           as_ptr(keep, c_u8p), 1 if no_dup_hap else 0,
                                           C.byref(ad), C.byref(dp), C.byref(oth)))
-        return tuple(coo_to_numpy(self.lib, m) for m in (ad, dp, oth))
+        return tuple(coo_to_numpy(self.lib, m, ctx_obj=self) for m in (ad, dp, oth))
 
     def synth_reads(self, n_reads, n_cells, span_gid, span_beg, span_end, seed=7, read_len=91,
                     want_seq=False, snps=None):
