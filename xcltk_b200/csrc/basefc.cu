@@ -203,10 +203,15 @@ __global__ void __launch_bounds__(256) k_window_cand(const Window *wins, int32_t
 // last, and then reused by later features.  The pool therefore stays about as large as the
 // state of the features under the current genomic window, so that it can live in the 126 MB
 // L2 instead of streaming through HBM.
+static inline uint64_t plan_blk_bytes(uint32_t cap, uint32_t log_cap) {
+    return (uint64_t)cap * 16 + 16 + ((((uint64_t)log_cap * 4) + 15) & ~15ull);
+}
+
 struct EpochPlan {
     int32_t n_epochs = 0, epoch_tiles = 0;
     std::vector<uint64_t> blk_off;      // per sorted feature: byte offset of its set
     std::vector<uint32_t> tbl_cap;      // slots of its set (0 = feature never active)
+    std::vector<uint32_t> log_cap;      // entries of its new-element log (= candidate reads)
     uint64_t pool_bytes = 0;
     std::vector<int32_t> zero_ptr, fin_ptr;           // per epoch ranges
     std::vector<uint64_t> zseg_off, zseg_pre;
@@ -222,12 +227,14 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
     pl.n_epochs = std::max(1, (n_tiles + epoch_tiles - 1) / epoch_tiles);
     pl.blk_off.assign(m, 0);
     pl.tbl_cap.assign(m, 0);
+    pl.log_cap.assign(m, 0);
     std::vector<std::vector<int32_t>> starts((size_t)pl.n_epochs), ends((size_t)pl.n_epochs);
     for (size_t j = 0; j < m; j++) {
         if (cand[j] == 0) continue;
         unsigned long long cap = cand[j] + cand[j] / 4 + 8;
         if (cap >= (1ull << 32)) return ctx->fail(XG_E_LIMIT, "feature window exceeds 2^32 reads");
         pl.tbl_cap[j] = (uint32_t)cap;
+        pl.log_cap[j] = (uint32_t)cand[j];
         pl.staging_cap += (int64_t)std::min<unsigned long long>(cand[j], (unsigned long long)n_cols);
         starts[(size_t)(tlo[j] / epoch_tiles)].push_back((int32_t)j);
         ends[(size_t)((thi[j] - 1) / epoch_tiles)].push_back((int32_t)j);
@@ -255,10 +262,11 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
         // epoch e never races with the (overlapped) counting of epoch e-1
         if (e > 1)
             for (int32_t j : ends[(size_t)e - 2])
-                release(pl.blk_off[(size_t)j], (uint64_t)pl.tbl_cap[(size_t)j] * 16);
+                release(pl.blk_off[(size_t)j], plan_blk_bytes(pl.tbl_cap[(size_t)j], pl.log_cap[(size_t)j]));
         uint64_t pre = 0;
         for (int32_t j : starts[(size_t)e]) {
-            uint64_t need = (uint64_t)pl.tbl_cap[(size_t)j] * 16, off = UINT64_MAX;
+            uint64_t need = plan_blk_bytes(pl.tbl_cap[(size_t)j], pl.log_cap[(size_t)j]), off = UINT64_MAX;
+            const uint64_t zero_len = (uint64_t)pl.tbl_cap[(size_t)j] * 16 + 16;   // set + cursor
             for (auto it = free_blocks.begin(); it != free_blocks.end(); ++it)
                 if (it->second >= need) {
                     off = it->first;
@@ -281,7 +289,7 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
             pl.blk_off[(size_t)j] = off;
             pl.zseg_off.push_back(off);
             pl.zseg_pre.push_back(pre);
-            pre += need;
+            pre += zero_len;
         }
         pl.zseg_pre.push_back(pre);      // terminator of the epoch: total bytes
         pl.zseg_off.push_back(0);
@@ -297,11 +305,18 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
 #define RPT 4            // records per thread (XG_TILE / 256)
 #define PB 2             // staged pairs a thread keeps in flight in the insert phase
 
-// per sorted feature: where its set lives
+// per sorted feature: where its block lives.  Block layout:
+//   [ set: cap x 16 B ][ cursor: 16 B ][ log: log_cap x 4 B ]
+// The log receives the cell of every NEW (cell, UMI) element, so that the row can be reduced
+// from n_new x 4 B instead of a scan of the whole (mostly empty or duplicate-free) set.
 struct __align__(16) FeatDesc {
     unsigned long long blk_off;
-    uint32_t cap, pad;
+    uint32_t cap, log_cap;
 };
+__host__ __device__ __forceinline__ uint64_t blk_zero_bytes(uint32_t cap) { return (uint64_t)cap * 16 + 16; }
+__host__ __device__ __forceinline__ uint64_t blk_bytes(uint32_t cap, uint32_t log_cap) {
+    return blk_zero_bytes(cap) + ((((uint64_t)log_cap * 4) + 15) & ~15ull);
+}
 
 struct BasefcDev {
     const int2 *pos_end;
@@ -355,7 +370,8 @@ __device__ __forceinline__ uint32_t set_home(uint64_t umi, uint32_t col, uint32_
 
 // (cell, UMI) -> the feature's set, starting at slot s whose content `cur` was already loaded.
 // Empty slot: b == 0.
-__device__ __forceinline__ void set_insert_from(xg_e128 *tbl, uint32_t cap, uint32_t s, xg_e128 cur,
+// Returns true when the element is new.
+__device__ __forceinline__ bool set_insert_from(xg_e128 *tbl, uint32_t cap, uint32_t s, xg_e128 cur,
                                                 xg_e128 want) {
     for (uint32_t probe = 0; probe < cap; probe++) {
         if (cur.b == 0) {
@@ -363,12 +379,28 @@ __device__ __forceinline__ void set_insert_from(xg_e128 *tbl, uint32_t cap, uint
             empty.a = 0;
             empty.b = 0;
             cur = cas128(&tbl[s], empty, want);
-            if (cur.b == 0) return;
+            if (cur.b == 0) return true;
         }
-        if (cur.a == want.a && cur.b == want.b) return;
+        if (cur.a == want.a && cur.b == want.b) return false;
         s = (s + 1 == cap) ? 0 : s + 1;
         cur = ld128_relaxed(&tbl[s]);
     }
+    return false;
+}
+
+// Append the cell of a new element to the feature's log.  Lanes of the warp that append to
+// the same feature are grouped with match_any: one cursor atomic per group.
+__device__ __forceinline__ void log_append(xg_e128 *tbl, uint32_t cap, bool is_new, uint32_t col) {
+    const unsigned active = __ballot_sync(0xffffffffu, is_new);
+    if (!is_new) return;
+    const unsigned peers = __match_any_sync(active, (unsigned long long)tbl);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    uint32_t *cursor = (uint32_t *)(tbl + cap);
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    uint32_t *log = cursor + 4;
+    log[base + __popc(peers & ((1u << lane) - 1u))] = col;
 }
 
 #define CIG_CAP 2048     // CIGAR words of the tile staged in shared memory
@@ -427,7 +459,10 @@ __device__ __forceinline__ void emit_pair(const BasefcDev &P, PairStage &S, int3
             want.b = (unsigned long long)col + 1ull;
             xg_e128 *tbl = (xg_e128 *)(P.pool + fd.blk_off);
             uint32_t s = set_home(umi, col, fd.cap);
-            set_insert_from(tbl, fd.cap, s, ld128_relaxed(&tbl[s]), want);
+            if (set_insert_from(tbl, fd.cap, s, ld128_relaxed(&tbl[s]), want)) {
+                uint32_t *cursor = (uint32_t *)(tbl + fd.cap);
+                cursor[4 + atomicAdd(cursor, 1u)] = col;
+            }
         }
     }
 }
@@ -461,12 +496,16 @@ __device__ __forceinline__ void flush_pairs(const BasefcDev &P, PairStage &S) {
 #pragma unroll
         for (int r = 0; r < PB; r++) {
             const int p = p0 + r * 256 + threadIdx.x;
+            bool is_new = false;
+            uint32_t col = 0;
             if (cap[r]) {
                 xg_e128 want;
+                col = S.col[p];
                 want.a = S.umi[p];
-                want.b = (unsigned long long)S.col[p] + 1ull;
-                set_insert_from(tbl[r], cap[r], home[r], cur[r], want);
+                want.b = (unsigned long long)col + 1ull;
+                is_new = set_insert_from(tbl[r], cap[r], home[r], cur[r], want);
             }
+            log_append(tbl[r], cap[r], is_new, col);     // whole warp: uses match_any
         }
     }
     __syncthreads();
@@ -667,35 +706,43 @@ __global__ void __launch_bounds__(256) k_zero_segments(uint8_t *pool, const uint
     }
 }
 
-// Reduce the set of a feature whose last epoch just finished to its row of the matrix:
-// histogram of the cells of its (cell, UMI) elements in shared memory plus a bitmap of the
-// touched cells; the set bits enumerated in order give the non-zeros in column order (the
+// Reduce a feature whose last epoch just finished to its row of the matrix: histogram of its
+// new-element log (one cell index per distinct (cell, UMI)) in shared memory plus a bitmap of
+// the touched cells; the set bits enumerated in order give the non-zeros in column order (the
 // reference's emit loop, rdr/fc/core.py:109-117).  The row goes to a staging area at an
-// atomically reserved offset; k_gather_rows puts the rows in input order.  Persistent CTAs:
-// histogram and bitmap are cleared while they are read, so the next feature starts clean.
-// When the cells do not fit the histogram (n_cols > hist_cols) the set is scanned once per
-// column range, first to count, then to write.
+// atomically reserved offset; k_gather_rows puts the rows in input order.  Persistent CTAs
+// take features from a work counter; histogram and bitmap are cleared while they are read, so
+// the next feature starts clean.  When the cells do not fit the histogram (n_cols > hist_cols)
+// the log is read once per column range, first to count, then to write.
 __global__ void __launch_bounds__(256) k_basefc_finalize(const uint8_t *pool, const FeatDesc *fdesc,
                                                          const int32_t *sf_row, const int32_t *fin_feat,
                                                          int32_t n_fin, int32_t n_cols, int32_t hist_cols,
-                                                         unsigned long long *cursor, int64_t *seg_base,
-                                                         int32_t *seg_nnz, int32_t *st_col, int32_t *st_val) {
+                                                         unsigned int *work, unsigned long long *cursor,
+                                                         int64_t *seg_base, int32_t *seg_nnz, int32_t *st_col,
+                                                         int32_t *st_val) {
     extern __shared__ uint32_t smem[];
     uint32_t *hist = smem;                          // hist_cols
     uint32_t *bitmap = smem + hist_cols;            // (hist_cols + 31) / 32
     __shared__ int warp_tot[8];
     __shared__ long long base_s;
+    __shared__ int f_s;
     const int n_words_max = (hist_cols + 31) >> 5;
     for (int c = threadIdx.x; c < hist_cols; c += blockDim.x) hist[c] = 0;
     for (int c = threadIdx.x; c < n_words_max; c += blockDim.x) bitmap[c] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n_pass = (n_cols + hist_cols - 1) / hist_cols;
 
-    for (int f = blockIdx.x; f < n_fin; f += gridDim.x) {
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) f_s = (int)atomicAdd(work, 1u);
+        __syncthreads();
+        const int f = f_s;
+        if (f >= n_fin) break;
         const int32_t j = fin_feat[f];
         const FeatDesc fd = fdesc[j];
-        const xg_e128 *tbl = (const xg_e128 *)(pool + fd.blk_off);
+        const uint32_t *cur_p = (const uint32_t *)(pool + fd.blk_off + (size_t)fd.cap * 16);
+        const uint32_t n_new = cur_p[0];
+        const uint32_t *log = cur_p + 4;
         long long base = 0;
         // stage 0 (only when n_pass > 1): count; stage 1: write
         for (int stage = (n_pass > 1 ? 0 : 1); stage < 2; stage++) {
@@ -704,13 +751,10 @@ __global__ void __launch_bounds__(256) k_basefc_finalize(const uint8_t *pool, co
                 const uint32_t c_lo = (uint32_t)pass * (uint32_t)hist_cols;
                 const int nc = min(hist_cols, n_cols - (int)c_lo);
                 const int nw = (nc + 31) >> 5;
-                for (uint32_t s = threadIdx.x; s < fd.cap; s += blockDim.x) {
-                    const xg_e128 e = tbl[s];
-                    if (e.b != 0) {
-                        const uint32_t col = (uint32_t)(e.b - 1ull) - c_lo;
-                        if (col < (uint32_t)nc && atomicAdd(&hist[col], 1u) == 0)
-                            atomicOr(&bitmap[col >> 5], 1u << (col & 31));
-                    }
+                for (uint32_t s = threadIdx.x; s < n_new; s += blockDim.x) {
+                    const uint32_t col = log[s] - c_lo;
+                    if (col < (uint32_t)nc && atomicAdd(&hist[col], 1u) == 0)
+                        atomicOr(&bitmap[col >> 5], 1u << (col & 31));
                 }
                 __syncthreads();
                 const bool writing = (stage == 1);
@@ -905,7 +949,7 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     const int32_t *d_fin_feat = nullptr;
     const uint64_t *d_zoff = nullptr, *d_zpre = nullptr;
     std::vector<FeatDesc> fdesc(m);
-    for (size_t j = 0; j < m; j++) fdesc[j] = FeatDesc{pl.blk_off[j], pl.tbl_cap[j], 0};
+    for (size_t j = 0; j < m; j++) fdesc[j] = FeatDesc{pl.blk_off[j], pl.tbl_cap[j], pl.log_cap[j]};
     if ((rc = upload_vec(ctx, fdesc, "fx_fdesc", &P.fdesc))) return rc;
     if ((rc = upload_vec(ctx, pl.fin_feat, "fx_fin_feat", &d_fin_feat))) return rc;
     if ((rc = upload_vec(ctx, pl.zseg_off, "fx_zseg_off", &d_zoff))) return rc;
@@ -937,6 +981,7 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     XG_GET(st_col, int32_t, "fx_st_col", pl.staging_cap + 1);
     XG_GET(st_val, int32_t, "fx_st_val", pl.staging_cap + 1);
     XG_GET(cursor, unsigned long long, "fx_cursor", 2);
+    XG_GET(fin_work, unsigned int, "fx_fin_work", pl.n_epochs + 1);
     P.pool = pool;
     XG_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors above are about to die
     const double ms_upload = ms_since(t_ph);
@@ -966,7 +1011,8 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     XG_CUDA(cudaMemsetAsync(seg_nnz, 0, sizeof(int32_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(seg_base, 0, sizeof(int64_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
-    launches += 4;
+    XG_CUDA(cudaMemsetAsync(fin_work, 0, sizeof(unsigned int) * (size_t)(pl.n_epochs + 1), ctx->stream));
+    launches += 5;
     cudaEventRecord(ev_init, ctx->stream);
     cudaStream_t st_z = overlap ? ctx->aux[0] : ctx->stream, st_f = overlap ? ctx->aux[1] : ctx->stream;
     if (overlap) {
@@ -1003,8 +1049,8 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
         if (n_fin > 0) {
             const int grid = std::min(n_fin, 148 * fin_ctas_per_sm);
             k_basefc_finalize<<<grid, 256, hist_bytes, st_f>>>(
-                pool, P.fdesc, d_sf_row, d_fin_feat + pl.fin_ptr[(size_t)e], n_fin, n_cols, hist_cols, cursor,
-                seg_base, seg_nnz, st_col, st_val);
+                pool, P.fdesc, d_sf_row, d_fin_feat + pl.fin_ptr[(size_t)e], n_fin, n_cols, hist_cols,
+                fin_work + e, cursor, seg_base, seg_nnz, st_col, st_val);
             launches++;
         }
         cudaEventRecord(EV(3, e), st_f);
