@@ -1,0 +1,160 @@
+"""GPU parity on device-generated 10x-style batches: CUDA path (through the C-ABI) vs the CPU
+oracle on the same records, bit-exact; plus size-independent properties at larger sizes."""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+class Conf(object):
+    min_mapq, min_len, min_include = 20, 30, 0.9
+    incl_flag, excl_flag, no_orphan = 0, 772, True
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    def use_barcodes(self):
+        return True
+
+    def use_umi(self):
+        return True
+
+
+def gpu_params(conf, with_include=True):
+    from xcltk_b200 import engine
+    return engine.make_params(conf, 91, with_include)
+
+
+@pytest.fixture(scope="module")
+def fc_batch(gpu_ctx):
+    from xcltk_b200 import workload
+    w = workload.make_basefc_workload(gpu_ctx, 1500000, 2000, 33472, seed=21)
+    w.host = w.dreads.download()
+    return w
+
+
+@pytest.mark.parametrize("kw", [
+    {}, {"min_include": 0.5}, {"min_include": 30, "min_mapq": 0}, {"min_include": 0, "excl_flag": 0, "min_len": 1},
+    {"min_include": 1.0, "incl_flag": 16}, {"min_include": 0.95, "min_mapq": 2.5, "no_orphan": False},
+])
+def test_basefc_matches_oracle(gpu_ctx, fc_batch, kw):
+    from oracle import oracle
+    conf, w = Conf(**kw), fc_batch
+    row, col, val, shape = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, gpu_params(conf))
+    o_row, o_col, o_val = oracle.basefc(w.host, w.gid, w.beg, w.end, w.cell_keys, 2000, oracle.params(conf), 4)
+    assert shape == (len(w.gid), 2000) and len(val) > 1000
+    assert np.array_equal(row, o_row) and np.array_equal(col, o_col) and np.array_equal(val, o_val)
+    assert np.all(np.diff(row.astype(np.int64) * 2000 + col) > 0)          # sorted by (row, col), unique
+
+
+def test_basefc_epoch_size_and_overlap_invariance(gpu_ctx, fc_batch, monkeypatch):
+    w, conf = fc_batch, Conf()
+    ref = None
+    for tiles, ov in (("100000", "1"), ("64", "1"), ("64", "0"), ("7", "1"), ("1", "1")):
+        monkeypatch.setenv("XG_EPOCH_TILES", tiles)
+        monkeypatch.setenv("XG_OVERLAP", ov)
+        out = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, gpu_params(conf))[:3]
+        out = [np.array(x) for x in out]
+        if ref is None:
+            ref = out
+        assert all(np.array_equal(a, b) for a, b in zip(ref, out)), (tiles, ov)
+
+
+def test_basefc_feature_rows_are_independent(gpu_ctx, fc_batch):
+    """Duplicated / permuted features give duplicated / permuted rows (R9: features are counted
+    independently, output rows follow input order)."""
+    w, conf = fc_batch, Conf()
+    rng = np.random.RandomState(3)
+    perm = rng.permutation(len(w.gid))[:5000]
+    idx = np.concatenate([perm, perm[:100]])                  # first 100 appear twice
+    row, col, val, _ = gpu_ctx.basefc(w.dreads, w.gid[idx], w.beg[idx], w.end[idx], w.cell_keys, 2000,
+                                      gpu_params(conf))
+    r0, c0, v0, _ = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, gpu_params(conf))
+    full = {}
+    for r, c, v in zip(r0.tolist(), c0.tolist(), v0.tolist()):
+        full.setdefault(r, []).append((c, v))
+    got = {}
+    for r, c, v in zip(row.tolist(), col.tolist(), val.tolist()):
+        got.setdefault(r, []).append((c, v))
+    for k, orig in enumerate(idx.tolist()):
+        assert got.get(k, []) == full.get(orig, [])
+
+
+def test_basefc_many_cells_multi_pass_histogram(gpu_ctx):
+    """More cells than the shared-memory histogram holds (> 40 960): column-range passes."""
+    from oracle import oracle
+    from xcltk_b200 import workload
+    w = workload.make_basefc_workload(gpu_ctx, 300000, 100000, 2000, seed=4, chroms={"20", "21", "22"})
+    conf = Conf()
+    row, col, val, _ = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 100000, gpu_params(conf))
+    host = w.dreads.download()
+    o = oracle.basefc(host, w.gid, w.beg, w.end, w.cell_keys, 100000, oracle.params(conf), 4)
+    assert col.max() > 40960
+    assert np.array_equal(row, o[0]) and np.array_equal(col, o[1]) and np.array_equal(val, o[2])
+
+
+def test_basefc_bins_large_windows(gpu_ctx):
+    """1 Mb bins (config 5 shape): few features, very large per-feature sets."""
+    from oracle import oracle
+    from xcltk_b200 import workload
+    w = workload.make_basefc_workload(gpu_ctx, 2000000, 500, 0, seed=9, chroms={"21", "22"}, bins_kb=1000)
+    conf = Conf(min_include=0.5)
+    row, col, val, _ = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 500, gpu_params(conf))
+    host = w.dreads.download()
+    o = oracle.basefc(host, w.gid, w.beg, w.end, w.cell_keys, 500, oracle.params(conf), 4)
+    assert np.array_equal(row, o[0]) and np.array_equal(col, o[1]) and np.array_equal(val, o[2])
+
+
+@pytest.fixture(scope="module")
+def baf_batch(gpu_ctx):
+    from xcltk_b200 import workload
+    b = workload.make_baf_workload(gpu_ctx, 1000000, 1000, 40000, seed=31, chroms={"19", "20", "21", "22"})
+    b.host = b.dreads.download()
+    return b
+
+
+@pytest.mark.parametrize("min_count,min_maf,no_dup", [(1, 0, True), (1, 0, False), (3, 0.1, True), (2, 0.34, False)])
+def test_baf_matches_oracle(gpu_ctx, baf_batch, min_count, min_maf, no_dup):
+    from oracle import oracle
+    b = baf_batch
+    conf = Conf(min_include=0)
+    totals, st = gpu_ctx.baf_pileup(b.dreads, b.snp_gid, b.snp_pos, b.cell_keys, 1000, gpu_params(conf, False))
+    tot = totals.sum(axis=1)
+    idx = np.arange(len(tot))
+    minor = np.minimum(totals[idx, b.snp_ref], totals[idx, b.snp_alt])
+    keep = ((tot >= min_count) & ~(minor < tot * min_maf)).astype(np.uint8)
+    ad, dp, oth = gpu_ctx.baf_count(st, b.reg_ptr, b.reg_snp, b.hap_of, keep, no_dup)
+    st.close()
+    letters = "ACGT"
+    o = oracle.baf(b.host, b.snp_gid, b.snp_pos, "".join(letters[x] for x in b.snp_ref),
+                   "".join(letters[x] for x in b.snp_alt), b.snp_ref_hap, 1 - b.snp_ref_hap, b.reg_ptr,
+                   b.reg_snp, b.cell_keys, 1000, oracle.params(conf), min_count, min_maf, no_dup, 4)
+    assert len(dp[2]) > 100
+    for got, exp in zip((ad, dp, oth), o):
+        assert all(np.array_equal(g, e) for g, e in zip(got[:3], exp))
+
+
+def test_basefc_full_size_properties(gpu_ctx):
+    """Bench-scale batch (config 3 shape, 50M reads): idempotence and per-contig additivity --
+    counting each contig's features separately and concatenating equals the whole run."""
+    from xcltk_b200 import workload
+    n = int(float(os.environ.get("XG_TEST_BIG_READS", "5e7")))
+    w = workload.make_basefc_workload(gpu_ctx, n, 10000, 60000, seed=13)
+    p = gpu_params(Conf())
+    a = [np.array(x) for x in gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 10000, p)[:3]]
+    b = [np.array(x) for x in gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 10000, p)[:3]]
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert int(a[2].sum()) <= int(n * 1.5) and len(a[2]) > n // 10
+    rows, cols, vals = [], [], []
+    for g in np.unique(w.gid):
+        sel = np.nonzero(w.gid == g)[0]
+        r, c, v, _ = gpu_ctx.basefc(w.dreads, w.gid[sel], w.beg[sel], w.end[sel], w.cell_keys, 10000, p)
+        rows.append(sel[r])
+        cols.append(np.array(c))
+        vals.append(np.array(v))
+    rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    order = np.lexsort((cols, rows))
+    assert np.array_equal(rows[order], a[0]) and np.array_equal(cols[order], a[1]) and np.array_equal(vals[order], a[2])
