@@ -49,7 +49,7 @@ def resolve_run(case_dir, case, run):
         if isinstance(v, str) and v.startswith("@"):
             v = os.path.join(case_dir, v[1:])
         kw[k] = v
-    ab = lambda x: os.path.join(case_dir, x) if x else None
+    ab = lambda x: (x if os.path.isabs(x) else os.path.join(case_dir, x)) if x else None
     return dict(kind=g["kind"], sam=[ab(x) for x in g["sam"]], barcodes=ab(g.get("barcodes")),
                 features=ab(g["features"]), snps=ab(g.get("snps")), kwargs=kw)
 
@@ -289,6 +289,92 @@ def case_chr22(name="c1_chr22_10x", n_reads=40000, n_bc=60, seed=7):
 
 
 CASES = {"d1": case_d1, "d2": case_d2, "d3": case_d3, "chr22": case_chr22}
+
+
+
+# ------------------------------------------------------------------ the reference's only real fixture
+def case_bch869():
+    """BCH869 SMART-seq BAM (preprocess/deprecated/merge_smartseq, 32 764 reads, RG = cell).
+    The BAM itself stays in /root/reference; the fixture holds the decoded record arrays
+    (xcltk_b200 decoder, cross-checked against oracle/shim in tests/test_decode.py) + the
+    reference's outputs on the real BAM."""
+    import gzip
+    import numpy as np
+    from xcltk_b200 import lib
+    d = fresh("bch869_smartseq")
+    src = os.path.join(REF, "preprocess/deprecated/merge_smartseq")
+    bam = os.path.join(src, "BCH869.output.bam")
+    # inputs the reference reads
+    with open(os.path.join(src, "BCH869.output.492.RG.barcodes.tsv")) as fp:
+        barcodes = [x.strip() for x in fp if x.strip()]
+    synth.write_lines(os.path.join(d, "barcodes.tsv"), barcodes)
+    with open(os.path.join(REF, "data/anno/annotate_genes_hg19_update_20230126.txt")) as fp, \
+            gzip.GzipFile(os.path.join(d, "features.tsv.gz"), "wb", mtime=0) as out:
+        for line in fp:
+            out.write(("\t".join(line.rstrip("\n").split("\t")[:4]) + "\n").encode())
+    # decoded records (identity contig map: gid = tid)
+    ks = lib.KeySpace()
+    refs = lib.bam_references(bam)
+    hr = lib.decode_bams([bam], [np.arange(len(refs), dtype=np.int32)], "RG", None, True, ks, 4)
+    cells, umis = {}, {}
+    cell_idx = np.full(hr.n, -1, dtype=np.int32)
+    umi_idx = np.zeros(hr.n, dtype=np.int32)
+    for i in range(hr.n):
+        ck, uk = int(hr.keys[i, 0]), int(hr.keys[i, 1])
+        if ck != lib.XG_KEY_NONE:
+            cell_idx[i] = cells.setdefault(ks.decode(ck), len(cells))
+        umi_idx[i] = umis.setdefault(ks.decode(uk), len(umis))
+    # SNPs at covered positions (REF = an observed base) so that the pileup has something to count
+    rng = random.Random(869)
+    nt16 = "=ACMGRSVTWYHKDBN"
+    snp_rows, seen = [], set()
+    while len(snp_rows) < 2547:
+        i = rng.randrange(hr.n)
+        f = int(hr.fmq[i])
+        if (f >> 24) != 0:
+            continue                      # simple reads only: query index = ref offset
+        pos, end = (int(x) for x in hr.pos_end[i])
+        q = rng.randrange(end - pos)
+        tid = [r for r in hr.runs if r[2] <= i < r[3]][0][1]
+        if (tid, pos + q) in seen:
+            continue
+        raw = hr.seq[int(hr.seq_off[i]):int(hr.seq_off[i]) + 16].tobytes()
+        b = raw[q >> 1]
+        base = nt16[(b & 15) if (q & 1) else (b >> 4)]
+        if base not in "ACGT":
+            continue
+        seen.add((tid, pos + q))
+        alt = rng.choice([x for x in "ACGT" if x != base])
+        a1 = rng.randrange(2)
+        snp_rows.append((refs[tid][0], pos + q + 1, base, alt, a1, 1 - a1))
+    with open(os.path.join(d, "snps.tsv"), "w") as fp:
+        fp.write("chrom\tpos\tref\talt\tref_hap\talt_hap\n")
+        for r in snp_rows:
+            fp.write("%s\t%d\t%s\t%s\t%d\t%d\n" % r)
+    np.savez_compressed(
+        os.path.join(d, "reads.npz"), pos_end=hr.pos_end, fmq=hr.fmq, cig_off=np.append(hr.cig_off, len(hr.cigar)),
+        cigar=hr.cigar, seq_off=hr.seq_off, seq=hr.seq, runs=np.array(hr.runs, dtype=np.int64),
+        cell_idx=cell_idx, umi_idx=umi_idx, cell_names=np.array(list(cells)), umi_names=np.array(list(umis)),
+        ref_names=np.array([r[0] for r in refs]), max_aln_len=hr.max_aln_len, max_span=hr.max_span)
+    hr.close()
+    # `sam` holds the real BAM for the reference run; the tests feed reads.npz instead
+    case = {"defaults": {"sam": [bam], "barcodes": "barcodes.tsv", "features": "features.tsv.gz",
+                         "snps": "snps.tsv", "reads_npz": "reads.npz"}, "runs": [
+        {"name": "rdr_rg_barcodes", "kind": "basefc", "kwargs": {"cell_tag": "RG", "umi_tag": "None", "ncores": 8}},
+        {"name": "rdr_rg_frac0.5_len20", "kind": "basefc",
+         "kwargs": {"cell_tag": "RG", "umi_tag": "None", "ncores": 8, "min_include": 0.5, "min_len": 20, "min_mapq": 0}},
+        {"name": "rdr_sample_id", "kind": "basefc", "barcodes": None,
+         "kwargs": {"cell_tag": None, "umi_tag": None, "sample_ids": "BCH869", "ncores": 8}},
+        {"name": "baf_rg_all_reg", "kind": "baf",
+         "kwargs": {"cell_tag": "RG", "umi_tag": None, "ncores": 8, "output_all_reg": True}},
+        {"name": "baf_rg_count2", "kind": "baf",
+         "kwargs": {"cell_tag": "RG", "umi_tag": None, "ncores": 8, "min_count": 2, "no_dup_hap": False}},
+    ]}
+    finish_case(d, case)
+
+
+CASES["bch869"] = case_bch869
+
 
 if __name__ == "__main__":
     if not os.path.isdir(REF):

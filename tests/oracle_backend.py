@@ -10,6 +10,9 @@ from xcltk_b200.utils.sam import build_tid_maps
 
 
 def decode_host(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=2):
+    if sam_fn_list[0].endswith(".npz"):
+        from npz_reads import load_npz_reads
+        return load_npz_reads(sam_fn_list[0], list(chroms))
     ks = lib.KeySpace()
     bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
     gid_of, tid_maps = build_tid_maps(bam_refs, list(chroms))

@@ -197,3 +197,20 @@ def test_packed_key_examples():
     assert ks.n_interned() == 0
     assert ks.encode("A" * 22) >> 63 == 1 and ks.encode("read/1") >> 63 == 1
     assert ks.n_interned() == 2
+
+
+BCH869 = "/root/reference/preprocess/deprecated/merge_smartseq/BCH869.output.bam"
+
+
+@pytest.mark.skipif(not os.path.exists(BCH869), reason="reference fixture only exists in the build container")
+def test_real_smartseq_bam_and_committed_arrays():
+    """The reference's only real BAM: decoder vs the Python reader, and the committed
+    tests/golden/bch869_smartseq/reads.npz is exactly what the decoder produces."""
+    hr, ks = decode([BCH869], cell_tag="RG", umi_tag=None, threads=4)
+    assert check_against_shim(BCH869, hr, ks, 0, "RG", None) == 32764
+    z = np.load(os.path.join(GOLD, "bch869_smartseq", "reads.npz"))
+    assert np.array_equal(z["pos_end"], hr.pos_end) and np.array_equal(z["fmq"], hr.fmq)
+    assert np.array_equal(z["cigar"], hr.cigar) and np.array_equal(z["seq"], hr.seq)
+    names = [ks.decode(int(k)) for k in hr.keys[:, 1]]
+    umi_names, umi_idx = z["umi_names"], z["umi_idx"]
+    assert [str(x) for x in umi_names[umi_idx]] == names

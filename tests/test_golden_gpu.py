@@ -12,10 +12,27 @@ pytestmark = pytest.mark.gpu
 logging.disable(logging.CRITICAL)
 
 
+def use_npz_reads(monkeypatch, r):
+    """Cases whose BAM cannot travel feed the decoded record arrays to the same upload path."""
+    if not r["reads_npz"]:
+        return
+    from npz_reads import load_npz_reads
+    from xcltk_b200 import engine
+
+    def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, device=0):
+        ctx = engine.get_context(device)
+        host, ks, gid_of = load_npz_reads(sam_fn_list[0], list(chroms))
+        stats = {"n_reads": host.n, "n_records_seen": host.n, "max_aln_len": host.max_aln_len,
+                 "max_span": host.max_span, "bytes": host.nbytes()}
+        return engine.ReadBatch(ctx, ctx.upload(host), ks, gid_of, stats)
+    monkeypatch.setattr(engine, "load_reads", load_reads)
+
+
 @pytest.mark.parametrize("case,run", golden_runs("basefc"))
-def test_basefc_matches_reference(case, run, tmp_path, gpu_ctx):
+def test_basefc_matches_reference(case, run, tmp_path, gpu_ctx, monkeypatch):
     from xcltk_b200.rdr.fc.main import fc_wrapper
     r = resolve(case, run)
+    use_npz_reads(monkeypatch, r)
     out = str(tmp_path / "out")
     ret = fc_wrapper(",".join(r["sam"]), r["barcodes"], r["features"], out, **r["kwargs"])
     assert ret == int(read(r["expected"] + "/RETCODE"))
@@ -23,9 +40,10 @@ def test_basefc_matches_reference(case, run, tmp_path, gpu_ctx):
 
 
 @pytest.mark.parametrize("case,run", golden_runs("baf"))
-def test_baf_matches_reference(case, run, tmp_path, gpu_ctx):
+def test_baf_matches_reference(case, run, tmp_path, gpu_ctx, monkeypatch):
     from xcltk_b200.baf.fc.main import afc_wrapper
     r = resolve(case, run)
+    use_npz_reads(monkeypatch, r)
     out = str(tmp_path / "out")
     ret = afc_wrapper(",".join(r["sam"]), r["barcodes"], r["features"], r["snps"], out, **r["kwargs"])
     assert ret == int(read(r["expected"] + "/RETCODE"))

@@ -41,8 +41,10 @@ def resolve(case, run_name):
 
     def ab(x):
         return os.path.join(case_dir, x) if x else None
-    return dict(kind=g["kind"], sam=[ab(x) for x in g["sam"]], barcodes=ab(g.get("barcodes")),
-                features=ab(g["features"]), snps=ab(g.get("snps")), kwargs=kw,
+    npz = ab(spec.get("defaults", {}).get("reads_npz"))
+    sam = [npz] if npz else [ab(x) for x in g["sam"]]      # the BAM of an npz case cannot travel
+    return dict(kind=g["kind"], sam=sam, barcodes=ab(g.get("barcodes")),
+                features=ab(g["features"]), snps=ab(g.get("snps")), kwargs=kw, reads_npz=npz,
                 expected=os.path.join(case_dir, "expected", run_name))
 
 

@@ -460,3 +460,57 @@ class ParamsBox(object):
                         int(bool(use_cell_tag)), int(bool(need_umi_tag)),
                         as_ptr(self.tab, c_i32p) if self.tab is not None else None,
                         len(self.tab) if self.tab is not None else 0, int(incl_len))
+
+
+class ArrayReads(object):
+    """xg_reads assembled from caller-owned numpy arrays (same duck type as HostReads: `.ptr`
+    for xg_upload_reads).  Used for record batches that do not come from xg_decode_bams."""
+
+    def __init__(self, pos_end, fmq, cig_off, keys, cigar, runs, seq_off=None, seq=None,
+                 max_aln_len=0, max_span=0):
+        n = len(fmq)
+        self.n = n
+        a = self._arrays = {
+            "pos_end": np.ascontiguousarray(pos_end, dtype=np.int32).reshape(-1),
+            "fmq": np.ascontiguousarray(fmq, dtype=np.uint32),
+            "cig_off": np.ascontiguousarray(cig_off, dtype=np.uint32),
+            "keys": np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1),
+            "cigar": np.ascontiguousarray(cigar if len(cigar) else [0], dtype=np.uint32),
+        }
+        assert len(a["cig_off"]) == n + 1 and len(a["pos_end"]) == 2 * n and len(a["keys"]) == 2 * n
+        self.has_seq = seq_off is not None and seq is not None
+        if self.has_seq:
+            a["seq_off"] = np.ascontiguousarray(seq_off, dtype=np.uint32)
+            a["seq"] = np.ascontiguousarray(seq if len(seq) else [0], dtype=np.uint32)
+        run_arr = (Run * max(1, len(runs)))()
+        tiles = []
+        pe = a["pos_end"].reshape(-1, 2)
+        for k, (bam_idx, gid, rb, re_) in enumerate(runs):
+            run_arr[k] = Run(int(bam_idx), int(gid), int(rb), int(re_))
+            for s in range(int(rb), int(re_), XG_TILE):
+                e = min(s + XG_TILE, int(re_))
+                tiles.append(Tile(s, e - s, k, int(pe[s, 0]), int(pe[s:e, 1].max())))
+        tile_arr = (Tile * max(1, len(tiles)))(*tiles)
+        self._keep = (run_arr, tile_arr)
+        self.runs = [tuple(int(x) for x in r) for r in runs]
+        self.pos_end, self.fmq, self.keys = pe, a["fmq"], a["keys"].reshape(-1, 2)
+        self.max_aln_len, self.max_span = int(max_aln_len), int(max_span)
+        r = Reads()
+        r.n_reads, r.n_cigar = n, len(cigar)
+        r.n_seq_words = len(seq) if self.has_seq else 0
+        r.n_runs, r.n_tiles = len(runs), len(tiles)
+        r.max_aln_len, r.max_span, r.n_records_seen = int(max_aln_len), int(max_span), n
+        r.pos_end, r.fmq = as_ptr(a["pos_end"], c_i32p), as_ptr(a["fmq"], c_u32p)
+        r.cig_off, r.keys = as_ptr(a["cig_off"], c_u32p), as_ptr(a["keys"], c_u64p)
+        r.cigar = as_ptr(a["cigar"], c_u32p)
+        if self.has_seq:
+            r.seq_off, r.seq = as_ptr(a["seq_off"], c_u32p), as_ptr(a["seq"], c_u32p)
+        r.runs, r.tiles = C.cast(run_arr, C.POINTER(Run)), C.cast(tile_arr, C.POINTER(Tile))
+        self._struct = r
+        self.ptr = C.pointer(r)
+
+    def nbytes(self):
+        return sum(v.nbytes for v in self._arrays.values())
+
+    def close(self):
+        pass
