@@ -140,21 +140,27 @@ class Batch(object):
         self.n_reads = args.reads + args.baf_reads
         self.keep = None
 
-    def step_device(self):
+    def step_device(self, checksum=False):
         ctx, fc, bf = self.ctx, self.fc, self.baf
         launches = 0
+        w0 = time.perf_counter()
         row, col, val, _ = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params)
+        w1 = time.perf_counter()
         t_fc = ctx.timing()
         launches += int(t_fc[2])
         totals, st = ctx.baf_pileup(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
+        w2 = time.perf_counter()
         t_p = ctx.timing()
         launches += int(t_p[2])
         keep = (totals.sum(axis=1) >= 1).astype(np.uint8)        # min_count=1, min_maf=0 (pipeline values)
         ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, keep, True)
+        w3 = time.perf_counter()
         t_c = ctx.timing()
         launches += int(t_c[2])
         st.close()
-        return dict(nnz=len(val), checksum=int(val.sum()) + int(dp[2].sum()) + int(ad[2].sum()),
+        chk = (int(val.sum(dtype=np.int64)) + int(dp[2].sum()) + int(ad[2].sum())) if checksum else None
+        w4 = time.perf_counter()
+        return dict(nnz=len(val), checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w3 - w2), 1e3 * (w4 - w3)],
                     launches=launches, t_fc=t_fc, t_pileup=t_p, t_count=t_c,
                     out_bytes=12 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])))
 
@@ -247,7 +253,8 @@ def main():
     ctx = engine.get_context(local)
     batch = Batch(ctx, args, rank)
     for _ in range(args.warmup):
-        info = batch.step_device()
+        info = batch.step_device(checksum=True)
+    checksum = info["checksum"]
     sampler = ClockSampler(local)
     barrier_sync(dist, local)
     sampler.start()
@@ -321,7 +328,10 @@ def main():
                            "baf_pileup_ms": float(np.mean([i["t_pileup"][0] for i in infos])),
                            "baf_scan_kernel_ms": float(np.mean([i["t_pileup"][1] for i in infos])),
                            "baf_count_ms": float(np.mean([i["t_count"][0] for i in infos])),
-                           "basefc_nnz": info["nnz"], "checksum": info["checksum"],
+                           "basefc_nnz": info["nnz"], "checksum": checksum,
+                           "wall_ms_basefc_pileup_count_checksum": [float(x) for x in np.mean(
+                               [i["wall_ms"] for i in infos], axis=0)],
+                           "basefc_host_ms_index_windows_plan_upload_call": [float(x) for x in info["t_fc"][8:13]],
                            "basefc_reads_per_s_kernels_only": args.reads / (
                                float(np.mean([i["t_fc"][3] for i in infos])) * 1e-3)}}
         print(json.dumps(line))

@@ -350,9 +350,10 @@ int upload_arr(xg_ctx *ctx, const T *src, size_t n, const char *name, const T **
 extern "C" void xg_baf_state_free(xg_ctx *ctx, xg_baf_state *st) {
     if (!st) return;
     if (ctx) cudaSetDevice(ctx->device);
-    if (st->pr_snp) cudaFree(st->pr_snp);
-    if (st->pr_colal) cudaFree(st->pr_colal);
-    if (st->pr_umi) cudaFree(st->pr_umi);
+    for (void *p : {(void *)st->pr_snp, (void *)st->pr_colal, (void *)st->pr_umi})
+        if (p) {
+            if (ctx) ctx->dev_put(p); else cudaFree(p);
+        }
     delete st;
 }
 
@@ -474,12 +475,12 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
         launches += 4;
         XG_CUDA(cudaGetLastError());
         // the state keeps its own copy of the pairs (scratch buffers are reused by later calls)
-        if (cudaMalloc((void **)&st->pr_snp, n_pairs * 4) != cudaSuccess ||
-            cudaMalloc((void **)&st->pr_colal, n_pairs * 4) != cudaSuccess ||
-            cudaMalloc((void **)&st->pr_umi, n_pairs * 8) != cudaSuccess) {
-            cudaGetLastError();
+        st->pr_snp = (uint32_t *)ctx->dev_get(n_pairs * 4);
+        st->pr_colal = (uint32_t *)ctx->dev_get(n_pairs * 4);
+        st->pr_umi = (uint64_t *)ctx->dev_get(n_pairs * 8);
+        if (!st->pr_snp || !st->pr_colal || !st->pr_umi) {
             xg_baf_state_free(ctx, st);
-            return ctx->fail(XG_E_CUDA, "cudaMalloc failed for the pileup state");
+            return ctx->fail(XG_E_CUDA, "out of device memory for the pileup state");
         }
         cudaMemcpyAsync(st->pr_snp, P.pr_snp, n_pairs * 4, cudaMemcpyDeviceToDevice, ctx->stream);
         cudaMemcpyAsync(st->pr_colal, P.pr_colal, n_pairs * 4, cudaMemcpyDeviceToDevice, ctx->stream);

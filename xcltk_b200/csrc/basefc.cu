@@ -124,6 +124,12 @@ int build_feat_index(xg_ctx *ctx, const xg_features *f, int32_t n_gid, FeatIndex
 struct Window {
     int32_t j, lo_tile, hi_tile;   // sorted feature, tiles [lo_tile, hi_tile)
 };
+
+struct FeatCache {
+    bool valid = false;
+    uint64_t hash = 0;
+    FeatIndexHost ix;
+};
 void feature_windows(const xg_dreads *rd, const FeatIndexHost &ix, std::vector<Window> &wins,
                      std::vector<int32_t> &tlo, std::vector<int32_t> &thi) {
     size_t m = ix.sf_beg.size();
@@ -879,9 +885,33 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     };
     const auto t_call = now();
     auto t_ph = now();
-    FeatIndexHost ix;
-    int rc = build_feat_index(ctx, feats, n_gid, ix);
-    if (rc) return rc;
+    // the interval index depends on the features only: reuse it (host copy and the uploaded
+    // device arrays, which live in named scratch buffers) while the caller passes the same set
+    uint64_t fh = 1469598103934665603ull;
+    auto mixh = [&](const void *p, size_t n) {
+        const uint8_t *b = (const uint8_t *)p;
+        for (size_t k = 0; k < n; k++) fh = (fh ^ b[k]) * 1099511628211ull;
+    };
+    mixh(&n_gid, sizeof n_gid);
+    mixh(&feats->n, sizeof feats->n);
+    mixh(feats->gid, sizeof(int32_t) * (size_t)feats->n);
+    mixh(feats->beg, sizeof(int32_t) * (size_t)feats->n);
+    mixh(feats->end, sizeof(int32_t) * (size_t)feats->n);
+    FeatCache *fc = (FeatCache *)ctx->fx_cache;
+    if (!fc) {
+        fc = new FeatCache();
+        ctx->fx_cache = fc;
+        ctx->fx_cache_free = [](void *p) { delete (FeatCache *)p; };
+    }
+    const bool index_cached = fc->valid && fc->hash == fh;
+    int rc = XG_OK;
+    if (!index_cached) {
+        fc->valid = false;
+        fc->ix = FeatIndexHost();
+        if ((rc = build_feat_index(ctx, feats, n_gid, fc->ix))) return rc;
+        fc->hash = fh;
+    }
+    const FeatIndexHost &ix = fc->ix;
     const size_t m = ix.sf_beg.size();
     const double ms_index = ms_since(t_ph);
     t_ph = now();
@@ -903,20 +933,36 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     const int32_t *d_sf_row = nullptr;
     const Window *d_wins = nullptr;
     const int32_t *d_sf_beg = nullptr;
-    std::vector<int4> stab4(ix.stab.size());
-    for (size_t k = 0; k < ix.stab.size(); k++) {
-        const int32_t j = ix.stab[k];
-        stab4[k] = make_int4(j, ix.sf_beg[(size_t)j], ix.sf_end[(size_t)j], 0);
+    if (!index_cached) {
+        std::vector<int4> stab4(ix.stab.size());
+        for (size_t k = 0; k < ix.stab.size(); k++) {
+            const int32_t j = ix.stab[k];
+            stab4[k] = make_int4(j, ix.sf_beg[(size_t)j], ix.sf_end[(size_t)j], 0);
+        }
+        const int4 *d_stab4 = nullptr;
+        const int32_t *d = nullptr;
+        if ((rc = upload_vec(ctx, ix.sf_goff, "fx_sf_goff", &d))) return rc;
+        if ((rc = upload_vec(ctx, ix.sf_beg, "fx_sf_beg", &d))) return rc;
+        if ((rc = upload_vec(ctx, ix.sf_end, "fx_sf_end", &d))) return rc;
+        if ((rc = upload_vec(ctx, ix.sf_row, "fx_sf_row", &d))) return rc;
+        if ((rc = upload_vec(ctx, ix.bnd_goff, "fx_bnd_goff", &d))) return rc;
+        if ((rc = upload_vec(ctx, ix.bnd, "fx_bnd", &d))) return rc;
+        if ((rc = upload_vec(ctx, ix.stab_off, "fx_stab_off", &d))) return rc;
+        if ((rc = upload_vec(ctx, stab4, "fx_stab4", &d_stab4))) return rc;
+        if ((rc = upload_vec(ctx, ix.fb, "fx_fb", &d))) return rc;
+        XG_CUDA(cudaStreamSynchronize(ctx->stream));
+        fc->valid = true;
     }
-    if ((rc = upload_vec(ctx, ix.sf_goff, "fx_sf_goff", &P.sf_goff))) return rc;
-    if ((rc = upload_vec(ctx, ix.sf_beg, "fx_sf_beg", &d_sf_beg))) return rc;
-    if ((rc = upload_vec(ctx, ix.sf_end, "fx_sf_end", &P.sf_end))) return rc;
-    if ((rc = upload_vec(ctx, ix.sf_row, "fx_sf_row", &d_sf_row))) return rc;
-    if ((rc = upload_vec(ctx, ix.bnd_goff, "fx_bnd_goff", &P.bnd_goff))) return rc;
-    if ((rc = upload_vec(ctx, ix.bnd, "fx_bnd", &P.bnd))) return rc;
-    if ((rc = upload_vec(ctx, ix.stab_off, "fx_stab_off", &P.stab_off))) return rc;
-    if ((rc = upload_vec(ctx, stab4, "fx_stab4", &P.stab4))) return rc;
-    if ((rc = upload_vec(ctx, ix.fb, "fx_fb", &P.fb))) return rc;
+    // the named scratch buffers keep their addresses between calls
+    P.sf_goff = (const int32_t *)ctx->scratch["fx_sf_goff"].p;
+    d_sf_beg = (const int32_t *)ctx->scratch["fx_sf_beg"].p;
+    P.sf_end = (const int32_t *)ctx->scratch["fx_sf_end"].p;
+    d_sf_row = (const int32_t *)ctx->scratch["fx_sf_row"].p;
+    P.bnd_goff = (const int32_t *)ctx->scratch["fx_bnd_goff"].p;
+    P.bnd = (const int32_t *)ctx->scratch["fx_bnd"].p;
+    P.stab_off = (const int32_t *)ctx->scratch["fx_stab_off"].p;
+    P.stab4 = (const int4 *)ctx->scratch["fx_stab4"].p;
+    P.fb = (const int32_t *)ctx->scratch["fx_fb"].p;
     if ((rc = upload_vec(ctx, wins, "fx_wins", &d_wins))) return rc;
     XG_GET(d_cand, unsigned long long, "fx_cand", m + 1);
     XG_GET(d_tile_bnd, int2, "fx_tile_bnd", rd->n_tiles + 1);

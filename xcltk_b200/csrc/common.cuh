@@ -35,6 +35,7 @@ struct xg_dreads {
     std::vector<xg_tile> h_tiles;
     double h2d_ms = 0;
     int64_t bytes = 0;
+    bool pooled = false;         // buffers came from xg_ctx::dev_get
 };
 
 struct xg_ctx {
@@ -96,6 +97,51 @@ struct xg_ctx {
             }
         cudaFreeHost(p);
     }
+
+    // device buffers with caller-visible lifetime (uploaded read batches, baf state) are
+    // recycled the same way: cudaMalloc / cudaFree of GBs per call is slow and synchronises
+    std::vector<Pinned> devbufs;
+    void *dev_get(size_t bytes) {
+        size_t best = devbufs.size();
+        for (size_t k = 0; k < devbufs.size(); k++)
+            if (!devbufs[k].used && devbufs[k].cap >= bytes && devbufs[k].cap <= bytes + bytes / 2 + (1 << 20) &&
+                (best == devbufs.size() || devbufs[k].cap < devbufs[best].cap))
+                best = k;
+        if (best < devbufs.size()) {
+            devbufs[best].used = true;
+            return devbufs[best].p;
+        }
+        void *p = nullptr;
+        size_t want = bytes ? bytes : 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            for (auto it = devbufs.begin(); it != devbufs.end();)     // drop idle buffers and retry
+                if (!it->used) {
+                    cudaFree(it->p);
+                    it = devbufs.erase(it);
+                } else {
+                    ++it;
+                }
+            if (cudaMalloc(&p, want) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        devbufs.push_back(Pinned{p, want, true});
+        return p;
+    }
+    void dev_put(void *p) {
+        if (!p) return;
+        for (auto &b : devbufs)
+            if (b.p == p) {
+                b.used = false;
+                return;
+            }
+        cudaFree(p);
+    }
+    // cache of the last interval index built by xg_basefc (owned by basefc.cu)
+    void *fx_cache = nullptr;
+    void (*fx_cache_free)(void *) = nullptr;
 
     int fail(int code, const std::string &msg) {
         err = msg;

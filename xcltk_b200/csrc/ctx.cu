@@ -58,6 +58,8 @@ void xg_destroy(xg_ctx *ctx) {
         for (auto &st : ctx->aux)
             if (st) cudaStreamDestroy(st);
         for (auto &b : ctx->pinned) cudaFreeHost(b.p);
+        for (auto &b : ctx->devbufs) cudaFree(b.p);
+        if (ctx->fx_cache && ctx->fx_cache_free) ctx->fx_cache_free(ctx->fx_cache);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -76,7 +78,9 @@ void xg_dreads_free(xg_ctx *ctx, xg_dreads *d) {
     if (ctx) cudaSetDevice(ctx->device);
     void *ps[] = {d->pos_end, d->fmq, d->cig_off, d->keys, d->seq_off, d->cigar, d->seq, d->runs, d->tiles};
     for (void *p : ps)
-        if (p) cudaFree(p);
+        if (p) {
+            if (d->pooled && ctx) ctx->dev_put(p); else cudaFree(p);
+        }
     delete d;
 }
 
@@ -111,12 +115,13 @@ int xg_upload_reads(xg_ctx *ctx, const xg_reads *h, xg_dreads **out) {
         {(void **)&d->runs, h->runs, (size_t)h->n_runs * sizeof(xg_run)},
         {(void **)&d->tiles, h->tiles, (size_t)h->n_tiles * sizeof(xg_tile)},
     };
+    d->pooled = true;
     for (auto &c : cps) {
         if (!c.src) continue;
-        cudaError_t e = cudaMalloc(c.dst, c.bytes ? c.bytes : 16);
-        if (e != cudaSuccess) {
+        *c.dst = ctx->dev_get(c.bytes ? c.bytes : 16);
+        if (!*c.dst) {
             xg_dreads_free(ctx, d);
-            return ctx->fail(XG_E_CUDA, std::string("cudaMalloc reads: ") + cudaGetErrorString(e));
+            return ctx->fail(XG_E_CUDA, "out of device memory for the read batch");
         }
     }
     cudaEventRecord(ctx->ev[6], ctx->stream);
