@@ -307,7 +307,7 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
 }
 
 #define SB_MAX 512       // boundaries staged in shared memory per tile
-#define PAIR_CAP 1536    // (feature, cell, UMI) triples staged per tile
+#define PAIR_CAP 1024    // (feature, cell, UMI) triples staged per tile
 #define RPT 4            // records per thread (XG_TILE / 256)
 #define PB 2             // staged pairs a thread keeps in flight in the insert phase
 
@@ -409,8 +409,8 @@ __device__ __forceinline__ void log_append(xg_e128 *tbl, uint32_t cap, bool is_n
     log[base + __popc(peers & ((1u << lane) - 1u))] = col;
 }
 
-#define CIG_CAP 2048     // CIGAR words of the tile staged in shared memory
-#define STAB_CAP 512     // stabbing-list entries of the tile's boundaries staged in shared memory
+#define CIG_CAP 1024     // CIGAR words of the tile staged in shared memory
+#define STAB_CAP 256     // stabbing-list entries of the tile's boundaries staged in shared memory
 
 struct PairStage {
     unsigned long long umi[PAIR_CAP];
@@ -475,6 +475,10 @@ __device__ __forceinline__ void emit_pair(const BasefcDev &P, PairStage &S, int3
 
 // Insert phase: all lanes insert staged pairs; descriptor and home-slot loads of a batch are
 // issued together before any of them is consumed.  Ends with the stage empty.
+// Insert phase: all lanes insert the staged (feature, cell, UMI) triples into the features'
+// sets; the descriptor and home-slot loads of a batch are issued together before any of them
+// is consumed.  Ends with the stage empty.  (A tile-local dedup table in shared memory and a
+// CAS-first probe were tried and measured slower: the phase is issue-bound, not L2-bound.)
 __device__ __forceinline__ void flush_pairs(const BasefcDev &P, PairStage &S) {
     const int np = P.ablate == 1 ? 0 : min(S.n_pairs, PAIR_CAP);
     for (int p0 = 0; p0 < np; p0 += 256 * PB) {
@@ -540,10 +544,10 @@ __global__ void __launch_bounds__(256, 4) k_basefc_count(const __grid_constant__
         const int32_t k = threadIdx.x + r * 256;
         const bool live = k < tile.n_rec;
         const int64_t i = tile.rec_beg + (live ? k : 0);
-        pe[r] = P.pos_end[i];
-        fq[r] = P.fmq[i];
-        co[r] = P.cig_off[i];
-        ky[r] = P.keys[i];
+        pe[r] = __ldcs(&P.pos_end[i]);         // streamed once: evict-first, keep L2 for the pool
+        fq[r] = __ldcs(&P.fmq[i]);
+        co[r] = __ldcs(&P.cig_off[i]);
+        ky[r] = __ldcs(&P.keys[i]);
         if (!live) ky[r].y = XG_KEY_NONE;          // an absent UMI drops the record
     }
     // ---- stage the slice of the interval index under the tile window and the tile's CIGAR words
@@ -985,7 +989,7 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
 
     // ---- pool layout over epochs
-    int32_t epoch_tiles = 8192;
+    int32_t epoch_tiles = 65536;
     if (const char *e = getenv("XG_EPOCH_TILES")) epoch_tiles = std::max(1, atoi(e));
     EpochPlan pl;
     t_ph = now();
