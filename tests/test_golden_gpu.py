@@ -48,3 +48,36 @@ def test_baf_matches_reference(case, run, tmp_path, gpu_ctx, monkeypatch):
     ret = afc_wrapper(",".join(r["sam"]), r["barcodes"], r["features"], r["snps"], out, **r["kwargs"])
     assert ret == int(read(r["expected"] + "/RETCODE"))
     compare_dirs(r["expected"], out, BAF_FILES)
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("case,run", [("c1_chr22_10x", "rdr_defaults"), ("c1_chr22_10x", "rdr_umi_none"),
+                                      ("d1_basefc_mini", "defaults"), ("d3_sample_mode", "rdr_ids"),
+                                      ("c1_chr22_10x", "baf_all_reg_dup"), ("c1_chr22_10x", "baf_defaults"),
+                                      ("d2_baf_mini", "defaults"), ("d3_sample_mode", "baf_p2p1")])
+def test_region_sharded_over_gpus_matches_reference(case, run, tmp_path, monkeypatch):
+    """Product path sharded by genomic chunks over all GPUs of the box (>= 2), rows merged on
+    the host: still byte-identical to the reference."""
+    n = _n_gpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("XCLTK_B200_GPUS", str(min(n, 4)))
+    r = resolve(case, run)
+    out = str(tmp_path / "out")
+    if r["kind"] == "basefc":
+        from xcltk_b200.rdr.fc.main import fc_wrapper
+        ret = fc_wrapper(",".join(r["sam"]), r["barcodes"], r["features"], out, **r["kwargs"])
+        files = RDR_FILES
+    else:
+        from xcltk_b200.baf.fc.main import afc_wrapper
+        ret = afc_wrapper(",".join(r["sam"]), r["barcodes"], r["features"], r["snps"], out, **r["kwargs"])
+        files = BAF_FILES
+    assert ret == int(read(r["expected"] + "/RETCODE"))
+    compare_dirs(r["expected"], out, files)

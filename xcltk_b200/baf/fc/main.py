@@ -185,39 +185,74 @@ def hap_table(snps):
     return hap
 
 
+def _count_shard(conf, ctx, dreads, keyspace, gid_of, max_aln_len, regs, snps):
+    """Pileup + count of `regs` (whose snp_list entries index `snps`) on one device."""
+    local = {}                                   # SNPs of this shard, renumbered
+    reg_ptr = np.zeros(len(regs) + 1, dtype=np.int64)
+    reg_snp = []
+    for r, reg in enumerate(regs):
+        for s in (reg.snp_list or ()):
+            reg_snp.append(local.setdefault(s.index, len(local)))
+        reg_ptr[r + 1] = len(reg_snp)
+    sub = [None] * len(local)
+    for gi, li in local.items():
+        sub[li] = snps[gi]
+    gid = np.array([gid_of.get(s.chrom, -1) for s in sub], dtype=np.int32)
+    pos0 = np.array([s.pos - 1 for s in sub], dtype=np.int64)          # fetch(chrom, pos-1, pos)
+    bad = (pos0 < 0) | (pos0 >= 2147483647)
+    gid[bad] = -1
+    pos0[bad] = 0
+    cell_keys = None
+    if conf.use_barcodes():
+        cell_keys = np.array([keyspace.encode(b) for b in conf.barcodes], dtype=np.uint64)
+    params = engine.make_params(conf, max_aln_len, with_include=False)
+    totals, state = ctx.baf_pileup(dreads, gid, pos0.astype(np.int32), cell_keys, len(conf.samples), params)
+    t1 = ctx.timing()
+    keep = snp_filter(conf, sub, totals)
+    out = ctx.baf_count(state, reg_ptr, np.array(reg_snp, dtype=np.int32), hap_table(sub), keep, conf.no_dup_hap)
+    t2 = ctx.timing()
+    state.close()
+    return out, [t1, t2]
+
+
 def count_regions(conf, regs, batch=None):
-    """Device counting; returns three (row, col, val) triples (AD, DP, OTH), rows index `regs`."""
+    """Device counting; returns three (row, col, val, shape) tuples (AD, DP, OTH), rows index
+    `regs`.  With several GPUs the regions are cut into contiguous genomic chunks (their SNPs
+    follow them; a SNP shared by regions of two chunks is piled up on both), no collective."""
+    from ... import parallel
     snps = conf.snp_set.snps
+    n_dev = parallel.n_devices(getattr(conf, "n_gpus", None))
     own = batch is None
     if own:
         chroms = list(dict.fromkeys([s.chrom for s in snps]))
-        batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True,
-                                  engine.n_decode_threads(conf.nproc))
+        threads = engine.n_decode_threads(conf.nproc)
+        if n_dev > 1:
+            batch = engine.load_reads_multi(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True,
+                                            threads, devices=tuple(range(n_dev)))
+        else:
+            batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True, threads)
     try:
-        gid = np.array([batch.gid_of.get(s.chrom, -1) for s in snps], dtype=np.int32)
-        pos0 = np.array([s.pos - 1 for s in snps], dtype=np.int64)      # fetch(chrom, pos-1, pos)
-        bad = (pos0 < 0) | (pos0 >= 2147483647)
-        gid[bad] = -1
-        pos0[bad] = 0
-        cell_keys = None
-        if conf.use_barcodes():
-            cell_keys = np.array([batch.keyspace.encode(b) for b in conf.barcodes], dtype=np.uint64)
-        params = engine.make_params(conf, batch.stats["max_aln_len"], with_include=False)
-        totals, state = batch.ctx.baf_pileup(batch.dreads, gid, pos0.astype(np.int32), cell_keys,
-                                             len(conf.samples), params)
-        t1 = batch.ctx.timing()
-        keep = snp_filter(conf, snps, totals)
-        reg_ptr = np.zeros(len(regs) + 1, dtype=np.int64)
-        reg_snp = []
-        for r, reg in enumerate(regs):
-            if reg.snp_list:
-                reg_snp.extend(s.index for s in reg.snp_list)
-            reg_ptr[r + 1] = len(reg_snp)
-        out = batch.ctx.baf_count(state, reg_ptr, np.array(reg_snp, dtype=np.int32), hap_table(snps),
-                                  keep, conf.no_dup_hap)
-        t2 = batch.ctx.timing()
-        state.close()
-        conf.last_timing = [t1, t2]
+        shape = (len(regs), len(conf.samples))
+        if isinstance(batch, engine.MultiBatch):
+            gid = np.array([batch.gid_of.get(r.chrom, -1) if r.snp_list else -1 for r in regs], dtype=np.int32)
+            beg = np.array([r.start - 1 for r in regs], dtype=np.int64)
+            load, total = parallel.reads_before(gid, beg, batch.runs, batch.pos_of_run)
+            shards = parallel.partition(gid, beg, load, total, len(batch.batches))
+
+            def one(k):
+                b = batch.batches[k]
+                return _count_shard(conf, b.ctx, b.dreads, b.keyspace, b.gid_of, b.stats["max_aln_len"],
+                                    [regs[i] for i in shards[k]], snps)
+            parts = parallel.run_on_devices(len(shards), one)
+            out = []
+            for w in range(3):
+                r, c, v = parallel.merge_coo([[np.array(x) for x in p[0][w][:3]] for p in parts], shards, len(regs))
+                out.append((r, c, v, shape))
+            out = tuple(out)
+            conf.last_timing = parts[0][1]
+        else:
+            out, conf.last_timing = _count_shard(conf, batch.ctx, batch.dreads, batch.keyspace, batch.gid_of,
+                                                 batch.stats["max_aln_len"], regs, snps)
         conf.last_stats = dict(batch.stats)
     finally:
         if own:

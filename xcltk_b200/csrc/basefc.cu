@@ -346,13 +346,14 @@ struct BasefcDev {
 
 // per tile: the range of boundaries that its window [first_pos, max_end) can touch
 __global__ void k_tile_bounds(const xg_tile *tiles, const xg_run *runs, int32_t n_tiles, int32_t n_gid,
-                              const int32_t *bnd_goff, const int32_t *bnd, int2 *out) {
+                              const int32_t *bnd_goff, const int32_t *bnd, const int32_t *stab_off,
+                              const int32_t *fb, int2 *out) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     const xg_tile tl = tiles[t];
     const int32_t gid = runs[tl.run].gid;
-    if (gid < 0 || gid >= n_gid) {
-        out[t] = make_int2(0, 0);
+    if (gid < 0 || gid >= n_gid || bnd_goff[gid] == bnd_goff[gid + 1]) {
+        out[t] = make_int2(-1, -1);
         return;
     }
     const int32_t b0 = bnd_goff[gid], b1 = bnd_goff[gid + 1];
@@ -367,7 +368,12 @@ __global__ void k_tile_bounds(const xg_tile *tiles, const xg_run *runs, int32_t 
         int32_t mid = (lo + hi) >> 1;
         if (bnd[mid] < tl.max_end) lo = mid + 1; else hi = mid;
     }
-    out[t] = make_int2(x, max(x, lo));
+    const int32_t y = max(x, lo);
+    // features that a record of this tile can overlap: those stabbing a segment in [x, y] or
+    // beginning at a boundary in (x, y).  None (e.g. another GPU's genomic chunk): skip the tile.
+    const int32_t y_seg = min(y + 1, b1);
+    const bool any = stab_off[y_seg] > stab_off[x] || fb[y] > fb[min(x + 1, y)];
+    out[t] = any ? make_int2(x, y) : make_int2(-1, -1);
 }
 
 __device__ __forceinline__ uint32_t set_home(uint64_t umi, uint32_t col, uint32_t cap) {
@@ -533,6 +539,7 @@ __global__ void __launch_bounds__(256, 4) k_basefc_count(const __grid_constant__
     if (P.sf_goff[gid] == P.sf_goff[gid + 1]) return;
     const int32_t b0 = P.bnd_goff[gid], b1 = P.bnd_goff[gid + 1];
     const int2 tb = P.tile_bnd[t];
+    if (tb.x < 0) return;          // no feature under this tile's window: its records are never read
     const int32_t nb = tb.y - tb.x;
 
     // ---- the thread's records: independent, coalesced loads issued up front
@@ -981,7 +988,8 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     }
     if (rd->n_tiles > 0) {
         k_tile_bounds<<<(rd->n_tiles + 255) / 256, 256, 0, ctx->stream>>>(rd->tiles, rd->runs, rd->n_tiles, n_gid,
-                                                                       P.bnd_goff, P.bnd, d_tile_bnd);
+                                                                       P.bnd_goff, P.bnd, P.stab_off, P.fb,
+                                                                       d_tile_bnd);
         launches++;
     }
     if (m) XG_CUDA(cudaMemcpyAsync(cand.data(), d_cand, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost,

@@ -88,6 +88,46 @@ def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, de
     return ReadBatch(ctx, dreads, ks, gid_of, stats)
 
 
+class MultiBatch(object):
+    """The decoded batch resident on several GPUs (one full copy each; the genomic sharding
+    happens on the feature side, see parallel.py) + the tile starts used to balance shards."""
+
+    def __init__(self, batches, runs, tile_pos):
+        self.batches, self.runs, self._tile_pos = batches, runs, tile_pos
+        b0 = batches[0]
+        self.keyspace, self.gid_of, self.stats = b0.keyspace, b0.gid_of, b0.stats
+
+    def pos_of_run(self, r):
+        """(sorted start positions sampled once per tile, reads per sample) of run r."""
+        return self._tile_pos[r], float(lib.XG_TILE)
+
+    def close(self):
+        for b in self.batches:
+            b.close()
+
+
+def load_reads_multi(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, devices=(0,)):
+    """Decode once on the host, upload to every device in `devices` (one host thread each)."""
+    from . import parallel
+    ctxs = [get_context(d) for d in devices]
+    ks = lib.KeySpace()
+    bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
+    gid_of, tid_maps = build_tid_maps(bam_refs, list(chroms))
+    host = lib.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, ks, n_threads)
+    stats = {"n_reads": host.n, "n_records_seen": host.n_records_seen, "max_aln_len": host.max_aln_len,
+             "max_span": host.max_span, "bytes": host.nbytes()}
+    runs = list(host.runs)
+    tile_pos = {}
+    for rec_beg, n_rec, run, first_pos, max_end in host.tiles():
+        tile_pos.setdefault(run, []).append(first_pos)
+    tile_pos = {r: np.asarray(v, dtype=np.int64) for r, v in tile_pos.items()}
+    for r in range(len(runs)):
+        tile_pos.setdefault(r, np.zeros(0, dtype=np.int64))
+    dreads = parallel.run_on_devices(len(ctxs), lambda k: ctxs[k].upload(host))
+    host.close()
+    return MultiBatch([ReadBatch(c, d, ks, gid_of, stats) for c, d in zip(ctxs, dreads)], runs, tile_pos)
+
+
 def make_params(conf, max_aln_len, with_include):
     tab, incl_len = (None, 0)
     if with_include:

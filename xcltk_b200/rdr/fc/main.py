@@ -241,30 +241,59 @@ def prepare_config(conf):
     return 0
 
 
+def feature_arrays(regs, gid_of):
+    """0-based half-open [start-1, end) of every Region; gid -1 where fetch() would raise or
+    be empty (unknown contig, start <= 0; utils/sam.py:105-118)."""
+    gid = np.array([gid_of.get(r.chrom, -1) for r in regs], dtype=np.int32)
+    beg = np.array([r.start - 1 for r in regs], dtype=np.int64)       # fetch(chrom, start-1, end)
+    end = np.array([r.end - 1 for r in regs], dtype=np.int64)
+    bad = (beg < 0) | (end <= beg) | (end > 2147483647)
+    gid[bad] = -1
+    beg[bad] = 0
+    end[bad] = 0
+    return gid, beg.astype(np.int32), end.astype(np.int32)
+
+
 def count_features(conf, batch=None):
     """Device counting for conf.reg_list; returns (row, col, val) 0-based, sorted by (row, col).
-    Replaces the pool of fc_features workers (rdr/fc/main.py:213-235, rdr/fc/core.py:69-148)."""
+    Replaces the pool of fc_features workers (rdr/fc/main.py:213-235, rdr/fc/core.py:69-148).
+    With several GPUs (conf.n_gpus / $XCLTK_B200_GPUS) the features are cut into contiguous
+    genomic chunks balanced by reads, one per GPU; rows are merged on the host (no collective)."""
+    from ... import parallel
     regs = conf.reg_list
+    n_dev = parallel.n_devices(getattr(conf, "n_gpus", None))
     own = batch is None
     if own:
         chroms = list(dict.fromkeys(r.chrom for r in regs))
-        batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False,
-                                  engine.n_decode_threads(conf.nproc))
+        threads = engine.n_decode_threads(conf.nproc)
+        if n_dev > 1:
+            batch = engine.load_reads_multi(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False,
+                                            threads, devices=tuple(range(n_dev)))
+        else:
+            batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False, threads)
     try:
-        gid = np.array([batch.gid_of.get(r.chrom, -1) for r in regs], dtype=np.int32)
-        beg = np.array([r.start - 1 for r in regs], dtype=np.int64)       # fetch(chrom, start-1, end)
-        end = np.array([r.end - 1 for r in regs], dtype=np.int64)
-        bad = (beg < 0) | (end <= beg) | (end > 2147483647)               # fetch raises / is empty
-        gid[bad] = -1
-        beg[bad] = 0
-        end[bad] = 0
+        gid, beg, end = feature_arrays(regs, batch.gid_of)
         cell_keys = None
         if conf.use_barcodes():
             cell_keys = np.array([batch.keyspace.encode(b) for b in conf.barcodes], dtype=np.uint64)
-        params = engine.make_params(conf, batch.stats["max_aln_len"], with_include=True)
-        row, col, val, _shape = batch.ctx.basefc(batch.dreads, gid, beg.astype(np.int32),
-                                                 end.astype(np.int32), cell_keys, len(conf.samples), params)
-        conf.last_timing = batch.ctx.timing()
+        if isinstance(batch, engine.MultiBatch):
+            load, total = parallel.reads_before(gid, beg, batch.runs, batch.pos_of_run)
+            shards = parallel.partition(gid, beg, load, total, len(batch.batches))
+
+            def one(k):
+                b, sh = batch.batches[k], shards[k]
+                params = engine.make_params(conf, b.stats["max_aln_len"], with_include=True)
+                r, c, v, _ = b.ctx.basefc(b.dreads, gid[sh], beg[sh], end[sh], cell_keys, len(conf.samples), params)
+                return np.array(r), np.array(c), np.array(v), b.ctx.timing()
+            parts = parallel.run_on_devices(len(shards), one)
+            row, col, val = parallel.merge_coo([p[:3] for p in parts], shards, len(regs))
+            conf.last_timing = parts[0][3]
+            conf.shard_sizes = [len(s) for s in shards]
+        else:
+            params = engine.make_params(conf, batch.stats["max_aln_len"], with_include=True)
+            row, col, val, _shape = batch.ctx.basefc(batch.dreads, gid, beg, end, cell_keys,
+                                                     len(conf.samples), params)
+            conf.last_timing = batch.ctx.timing()
         conf.last_stats = dict(batch.stats)
     finally:
         if own:
