@@ -173,13 +173,14 @@ class Batch(object):
         d_fc = ctx.upload(self.h_fc)
         row, col, val, _ = ctx.basefc(d_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params)
         d_fc.close()
-        d_bf = ctx.upload(self.h_baf)
+        d_bf = ctx.map_reads(self.h_baf)          # zero-copy: 8 B/read over PCIe, rest on demand
         totals, st = ctx.baf_pileup(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
+        ctx.timing_pairs = ctx.timing()[6]            # (read, SNP) pairs: records fetched on demand
         keep = (totals.sum(axis=1) >= 1).astype(np.uint8)
         ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, keep, True)
         st.close()
         d_bf.close()
-        return dict(h2d=self.h_fc.nbytes() + self.h_baf.nbytes(),
+        return dict(h2d=self.h_fc.nbytes() + 8 * self.h_baf.n + 72 * int(self.ctx.timing_pairs),
                     d2h=12 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])) + totals.nbytes)
 
 

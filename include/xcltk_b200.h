@@ -133,6 +133,11 @@ const char *xg_last_error(xg_ctx *ctx);
 
 /* Host -> HBM copy of a decoded batch (the only cross-device traffic of the path).      */
 int xg_upload_reads(xg_ctx *ctx, const xg_reads *host, xg_dreads **out);
+/* Zero-copy variant for the baf pileup: pos/end are copied to HBM, every other array is read
+ * by the kernels from the (pinned) host arrays of `host`, which must outlive the result.
+ * The pileup touches flag / keys / CIGAR / sequence of the reads that cover a SNP only, so
+ * ~8 B per read cross PCIe instead of ~84 B.  XG_E_ARG if the arrays are not pinned.           */
+int xg_map_reads(xg_ctx *ctx, const xg_reads *host, xg_dreads **out);
 /* HBM -> host copy (tests: run the oracle on device-generated records).                 */
 int xg_download_reads(xg_ctx *ctx, const xg_dreads *d, xg_reads **out);
 void xg_dreads_free(xg_ctx *ctx, xg_dreads *d);
@@ -185,7 +190,7 @@ typedef struct {
 } xg_coo;
 void xg_coo_free(xg_coo *m);
 
-/* basefc: replaces the per-feature loop fc_features()/fc_fet1() (rdr/fc/core.py:96-124,151-178)
+/* basefc (needs a batch from xg_upload_reads, not xg_map_reads): replaces the per-feature loop fc_features()/fc_fet1() (rdr/fc/core.py:96-124,151-178)
  * and MCount/SCount (rdr/fc/mcount.py): out[row f, col c] = number of distinct UMI keys among
  * the reads of cell c that overlap feature f and pass check_read + the include test.     */
 int xg_basefc(xg_ctx *ctx, const xg_dreads *reads, const xg_features *feats,

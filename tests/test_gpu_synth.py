@@ -137,6 +137,28 @@ def test_baf_matches_oracle(gpu_ctx, baf_batch, min_count, min_maf, no_dup):
         assert all(np.array_equal(g, e) for g, e in zip(got[:3], exp))
 
 
+def test_baf_zero_copy_batch_equals_uploaded(gpu_ctx, baf_batch):
+    """xg_map_reads (records read from pinned host memory) gives the same pileup as the
+    HBM-resident batch; basefc refuses a mapped batch."""
+    from xcltk_b200 import lib
+    b = baf_batch
+    p = gpu_params(Conf(min_include=0), False)
+    t0, st0 = gpu_ctx.baf_pileup(b.dreads, b.snp_gid, b.snp_pos, b.cell_keys, 1000, p)
+    mapped = gpu_ctx.map_reads(b.host)
+    t1, st1 = gpu_ctx.baf_pileup(mapped, b.snp_gid, b.snp_pos, b.cell_keys, 1000, p)
+    assert np.array_equal(t0, t1) and t0.sum() > 1000
+    keep = (t0.sum(axis=1) >= 1).astype(np.uint8)
+    a = gpu_ctx.baf_count(st0, b.reg_ptr, b.reg_snp, b.hap_of, keep, True)
+    c = gpu_ctx.baf_count(st1, b.reg_ptr, b.reg_snp, b.hap_of, keep, True)
+    for x, y in zip(a, c):
+        assert all(np.array_equal(u, v) for u, v in zip(x[:3], y[:3]))
+    with pytest.raises(lib.XgError):
+        gpu_ctx.basefc(mapped, b.gid, b.beg, b.end, b.cell_keys, 1000, gpu_params(Conf()))
+    st0.close()
+    st1.close()
+    mapped.close()
+
+
 def test_basefc_full_size_properties(gpu_ctx):
     """Bench-scale batch (config 3 shape, 50M reads): idempotence and per-contig additivity --
     counting each contig's features separately and concatenating equals the whole run."""

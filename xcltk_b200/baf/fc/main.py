@@ -230,7 +230,8 @@ def count_regions(conf, regs, batch=None):
             batch = engine.load_reads_multi(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True,
                                             threads, devices=tuple(range(n_dev)))
         else:
-            batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True, threads)
+            batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True, threads,
+                                      mapped=True)
     try:
         shape = (len(regs), len(conf.samples))
         if isinstance(batch, engine.MultiBatch):

@@ -878,6 +878,7 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     if (feats->n < 0 || cells->n_samples <= 0) return ctx->fail(XG_E_ARG, "xg_basefc: empty sample list");
     if (par->use_cell_tag && cells->n != cells->n_samples)
         return ctx->fail(XG_E_ARG, "xg_basefc: barcode mode needs one key per column");
+    if (rd->mapped) return ctx->fail(XG_E_ARG, "xg_basefc: needs an uploaded batch (xg_upload_reads), not xg_map_reads");
     XG_CUDA(cudaSetDevice(ctx->device));
     for (double &t : ctx->timing) t = 0;
     int launches = 0;

@@ -36,6 +36,7 @@ struct xg_dreads {
     double h2d_ms = 0;
     int64_t bytes = 0;
     bool pooled = false;         // buffers came from xg_ctx::dev_get
+    bool mapped = false;         // xg_map_reads: only pos_end / runs / tiles are device copies
 };
 
 struct xg_ctx {

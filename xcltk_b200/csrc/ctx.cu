@@ -76,7 +76,10 @@ int64_t xg_dreads_n(const xg_dreads *d) { return d ? d->n_reads : 0; }
 void xg_dreads_free(xg_ctx *ctx, xg_dreads *d) {
     if (!d) return;
     if (ctx) cudaSetDevice(ctx->device);
-    void *ps[] = {d->pos_end, d->fmq, d->cig_off, d->keys, d->seq_off, d->cigar, d->seq, d->runs, d->tiles};
+    void *ps_all[] = {d->pos_end, d->fmq, d->cig_off, d->keys, d->seq_off, d->cigar, d->seq, d->runs, d->tiles};
+    void *ps_map[] = {d->pos_end, d->runs, d->tiles};      // mapped batch: the rest is the caller's host memory
+    std::vector<void *> ps(d->mapped ? std::begin(ps_map) : std::begin(ps_all),
+                           d->mapped ? std::end(ps_map) : std::end(ps_all));
     for (void *p : ps)
         if (p) {
             if (d->pooled && ctx) ctx->dev_put(p); else cudaFree(p);
@@ -144,6 +147,76 @@ int xg_upload_reads(xg_ctx *ctx, const xg_reads *h, xg_dreads **out) {
     cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
     d->h2d_ms = ms;
     ctx->timing[3] = ms;
+    *out = d;
+    return XG_OK;
+}
+
+// Records stay in pinned host memory; only pos/end (+ runs, tiles) are copied to HBM and the
+// other arrays are read by the kernels through the mapped host pointers (zero-copy).  For the
+// baf pileup, which needs flag / keys / CIGAR / sequence of the few reads that cover a SNP
+// only: 8 B per read cross PCIe instead of ~84 B.
+int xg_map_reads(xg_ctx *ctx, const xg_reads *h, xg_dreads **out) {
+    if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
+    if (!h || !out) return ctx->fail(XG_E_ARG, "xg_map_reads: null argument");
+    XG_CUDA(cudaSetDevice(ctx->device));
+    const void *must_be_pinned[] = {h->fmq, h->cig_off, h->keys, h->cigar, h->seq_off, h->seq};
+    for (const void *p : must_be_pinned) {
+        if (!p) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            return ctx->fail(XG_E_ARG, "xg_map_reads: record arrays must be pinned host memory "
+                                       "(xg_decode_bams output after xg_create, or cudaHostRegister)");
+        }
+    }
+    xg_dreads *d = new xg_dreads();
+    d->n_reads = h->n_reads;
+    d->n_cigar = h->n_cigar;
+    d->n_seq_words = h->n_seq_words;
+    d->n_runs = h->n_runs;
+    d->n_tiles = h->n_tiles;
+    d->max_aln_len = h->max_aln_len;
+    d->max_span = h->max_span;
+    d->h_runs.assign(h->runs, h->runs + h->n_runs);
+    d->h_tiles.assign(h->tiles, h->tiles + h->n_tiles);
+    d->pooled = true;
+    d->mapped = true;
+    size_t n = (size_t)h->n_reads;
+    d->pos_end = (int2 *)ctx->dev_get(n * 8 + 16);
+    d->runs = (xg_run *)ctx->dev_get((size_t)h->n_runs * sizeof(xg_run) + 16);
+    d->tiles = (xg_tile *)ctx->dev_get((size_t)h->n_tiles * sizeof(xg_tile) + 16);
+    if (!d->pos_end || !d->runs || !d->tiles) {
+        xg_dreads_free(ctx, d);
+        return ctx->fail(XG_E_CUDA, "out of device memory for the read batch");
+    }
+    auto devptr = [](const void *p) -> void * {
+        void *q = nullptr;
+        if (!p || cudaHostGetDevicePointer(&q, const_cast<void *>(p), 0) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return q;
+    };
+    d->fmq = (uint32_t *)devptr(h->fmq);
+    d->cig_off = (uint32_t *)devptr(h->cig_off);
+    d->keys = (ulonglong2 *)devptr(h->keys);
+    d->cigar = (uint32_t *)devptr(h->cigar);
+    d->seq_off = (uint32_t *)devptr(h->seq_off);
+    d->seq = (uint32_t *)devptr(h->seq);
+    cudaEventRecord(ctx->ev[6], ctx->stream);
+    cudaMemcpyAsync(d->pos_end, h->pos_end, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d->runs, h->runs, (size_t)h->n_runs * sizeof(xg_run), cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d->tiles, h->tiles, (size_t)h->n_tiles * sizeof(xg_tile), cudaMemcpyHostToDevice, ctx->stream);
+    cudaEventRecord(ctx->ev[7], ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        xg_dreads_free(ctx, d);
+        return ctx->fail(XG_E_CUDA, std::string("xg_map_reads: ") + cudaGetErrorString(e));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
+    d->h2d_ms = ms;
+    d->bytes = (int64_t)(n * 8);
     *out = d;
     return XG_OK;
 }

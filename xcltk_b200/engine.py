@@ -56,6 +56,10 @@ class ReadBatch(object):
         if self.dreads is not None:
             self.dreads.close()
             self.dreads = None
+        host = getattr(self, "host", None)
+        if host is not None:             # zero-copy batch: the pinned records were still in use
+            host.close()
+            self.host = None
 
 
 _contexts = {}
@@ -71,11 +75,12 @@ def get_context(device=0):
     return ctx
 
 
-def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, device=0):
+def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, device=0, mapped=False):
     """Decode every BAM (host, multi-threaded) and upload the batch to `device`.
 
     chroms: distinct (already 'chr'-stripped) contig names the features / SNPs use; reads on
-    other contigs can never be fetched by the reference and are dropped at decode time."""
+    other contigs can never be fetched by the reference and are dropped at decode time.
+    mapped: keep the records in pinned host memory and copy only pos/end (baf pileup)."""
     ctx = get_context(device)
     ks = lib.KeySpace()
     bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
@@ -83,6 +88,10 @@ def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, de
     host = lib.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, ks, n_threads)
     stats = {"n_reads": host.n, "n_records_seen": host.n_records_seen, "max_aln_len": host.max_aln_len,
              "max_span": host.max_span, "bytes": host.nbytes()}
+    if mapped:
+        batch = ReadBatch(ctx, ctx.map_reads(host), ks, gid_of, stats)
+        batch.host = host
+        return batch
     dreads = ctx.upload(host)
     host.close()
     return ReadBatch(ctx, dreads, ks, gid_of, stats)

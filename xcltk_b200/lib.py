@@ -101,6 +101,7 @@ SYMBOLS = {
     "xg_destroy": (None, [_P]),
     "xg_last_error": (C.c_char_p, [_P]),
     "xg_upload_reads": (C.c_int, [_P, C.POINTER(Reads), C.POINTER(_P)]),
+    "xg_map_reads": (C.c_int, [_P, C.POINTER(Reads), C.POINTER(_P)]),
     "xg_download_reads": (C.c_int, [_P, _P, C.POINTER(C.POINTER(Reads))]),
     "xg_dreads_free": (None, [_P, _P]),
     "xg_dreads_n": (C.c_int64, [_P]),
@@ -334,6 +335,14 @@ class Context(object):
         d = _P()
         self._check(self.lib.xg_upload_reads(self.h, host_reads.ptr, C.byref(d)))
         return DeviceReads(self, d)
+
+    def map_reads(self, host_reads):
+        """Zero-copy batch for baf: only pos/end go to HBM; `host_reads` must stay alive."""
+        d = _P()
+        self._check(self.lib.xg_map_reads(self.h, host_reads.ptr, C.byref(d)))
+        dr = DeviceReads(self, d)
+        dr._host = host_reads
+        return dr
 
     def timing(self):
         t = (C.c_double * 16)()
