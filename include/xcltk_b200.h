@@ -196,6 +196,12 @@ void xg_coo_free(xg_coo *m);
 int xg_basefc(xg_ctx *ctx, const xg_dreads *reads, const xg_features *feats,
               const xg_barcodes *cells, const xg_params *par, xg_coo **out);
 
+/* Same from a pinned host batch (xg_decode_bams output): the records are copied to HBM epoch
+ * by epoch on a copy stream while the previous epochs are being counted, so that the call
+ * costs about max(H2D, kernels) instead of their sum.  This is the end-to-end entry point. */
+int xg_basefc_host(xg_ctx *ctx, const xg_reads *host, const xg_features *feats,
+                   const xg_barcodes *cells, const xg_params *par, xg_coo **out);
+
 /* baf phase 1: replaces plp_snp() up to mcnt.stat() (baf/fc/core.py:198-237; first-read-wins
  * per (SNP, cell, UMI): baf/fc/mcount.py:109-127; allele: :39-60 + utils/sam.py:4-40).
  * totals[5*i .. 5*i+4] = A,C,G,T,N bucket counts of SNP i over all listed cells.          */

@@ -19,7 +19,8 @@ def use_npz_reads(monkeypatch, r):
     from npz_reads import load_npz_reads
     from xcltk_b200 import engine
 
-    def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, device=0, mapped=False):
+    def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, device=0, mapped=False,
+                   host_only=False):
         ctx = engine.get_context(device)
         host, ks, gid_of = load_npz_reads(sam_fn_list[0], list(chroms))
         stats = {"n_reads": host.n, "n_records_seen": host.n, "max_aln_len": host.max_aln_len,

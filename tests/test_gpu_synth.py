@@ -137,6 +137,16 @@ def test_baf_matches_oracle(gpu_ctx, baf_batch, min_count, min_maf, no_dup):
         assert all(np.array_equal(g, e) for g, e in zip(got[:3], exp))
 
 
+def test_basefc_streamed_from_host_equals_resident(gpu_ctx, fc_batch, monkeypatch):
+    """xg_basefc_host (records copied epoch by epoch under the kernels) == xg_basefc."""
+    w, p = fc_batch, gpu_params(Conf())
+    ref = [np.array(x) for x in gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, p)[:3]]
+    for tiles in ("8192", "100", "3"):
+        monkeypatch.setenv("XG_EPOCH_TILES_HOST", tiles)
+        out = [np.array(x) for x in gpu_ctx.basefc_host(w.host, w.gid, w.beg, w.end, w.cell_keys, 2000, p)[:3]]
+        assert all(np.array_equal(a, b) for a, b in zip(ref, out)), tiles
+
+
 def test_baf_zero_copy_batch_equals_uploaded(gpu_ctx, baf_batch):
     """xg_map_reads (records read from pinned host memory) gives the same pileup as the
     HBM-resident batch; basefc refuses a mapped batch."""

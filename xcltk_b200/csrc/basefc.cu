@@ -871,8 +871,11 @@ static int upload_vec(xg_ctx *ctx, const std::vector<T> &v, const char *name, co
     return XG_OK;
 }
 
-extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *feats,
-                         const xg_barcodes *cells, const xg_params *par, xg_coo **out) {
+// `src` != nullptr: the records of `rd` are not in HBM yet -- its device arrays are allocated
+// but empty, and every epoch's slice is copied from the pinned host batch `src` on a copy
+// stream just ahead of the epoch that counts it (H2D overlaps the kernels).
+static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, const xg_features *feats,
+                      const xg_barcodes *cells, const xg_params *par, xg_coo **out) {
     if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
     if (!rd || !feats || !cells || !par || !out) return ctx->fail(XG_E_ARG, "xg_basefc: null argument");
     if (feats->n < 0 || cells->n_samples <= 0) return ctx->fail(XG_E_ARG, "xg_basefc: empty sample list");
@@ -982,7 +985,7 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     cudaEventRecord(ctx->ev[0], ctx->stream);
     XG_CUDA(cudaMemsetAsync(d_cand, 0, sizeof(unsigned long long) * (m + 1), ctx->stream));
     std::vector<unsigned long long> cand(m, 0);
-    if (!wins.empty()) {
+    if (!wins.empty() && !src) {
         k_window_cand<<<(unsigned)((wins.size() + 7) / 8), 256, 0, ctx->stream>>>(
             d_wins, (int32_t)wins.size(), rd->tiles, rd->pos_end, d_sf_beg, P.sf_end, d_cand);
         launches++;
@@ -993,13 +996,19 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
                                                                        d_tile_bnd);
         launches++;
     }
-    if (m) XG_CUDA(cudaMemcpyAsync(cand.data(), d_cand, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost,
-                                   ctx->stream));
+    if (m && !src)
+        XG_CUDA(cudaMemcpyAsync(cand.data(), d_cand, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost,
+                                ctx->stream));
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (src)      // streaming: the records are not on the device yet; whole tiles bound the windows
+        for (const Window &w : wins) {
+            const xg_tile &L = rd->h_tiles[(size_t)w.lo_tile], &H = rd->h_tiles[(size_t)w.hi_tile - 1];
+            cand[(size_t)w.j] += (unsigned long long)(H.rec_beg + H.n_rec - L.rec_beg);
+        }
 
     // ---- pool layout over epochs
-    int32_t epoch_tiles = 65536;
-    if (const char *e = getenv("XG_EPOCH_TILES")) epoch_tiles = std::max(1, atoi(e));
+    int32_t epoch_tiles = src ? 8192 : 65536;     // streaming: finer epochs = finer H2D / kernel overlap
+    if (const char *e = getenv(src ? "XG_EPOCH_TILES_HOST" : "XG_EPOCH_TILES")) epoch_tiles = std::max(1, atoi(e));
     EpochPlan pl;
     t_ph = now();
     if ((rc = make_plan(ctx, cand, tlo, thi, rd->n_tiles, n_cols, epoch_tiles, pl))) return rc;
@@ -1058,15 +1067,16 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     //   finalize(e) waits count(e), count(e-1)
     bool overlap = pl.n_epochs > 1;
     if (const char *e = getenv("XG_OVERLAP")) overlap = overlap && atoi(e) != 0;
-    if (overlap && !ctx->aux[0])
+    if ((overlap || src) && !ctx->aux[0])
         for (auto &st : ctx->aux) XG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    while ((int32_t)ctx->ev_pool.size() < 4 * pl.n_epochs + 1) {
+    if (src && !ctx->copy_stream) XG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    while ((int32_t)ctx->ev_pool.size() < 5 * pl.n_epochs + 1) {
         cudaEvent_t ev;
         XG_CUDA(cudaEventCreate(&ev));
         ctx->ev_pool.push_back(ev);
     }
-    auto EV = [&](int kind, int32_t e) { return ctx->ev_pool[(size_t)4 * e + kind]; };   // 0 Z, 1 S, 2 C, 3 F
-    cudaEvent_t ev_init = ctx->ev_pool[(size_t)4 * pl.n_epochs];
+    auto EV = [&](int kind, int32_t e) { return ctx->ev_pool[(size_t)5 * e + kind]; };   // 0 Z, 1 S, 2 C, 3 F, 4 H2D
+    cudaEvent_t ev_init = ctx->ev_pool[(size_t)5 * pl.n_epochs];
     XG_CUDA(cudaMemsetAsync(seg_nnz, 0, sizeof(int32_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(seg_base, 0, sizeof(int64_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
@@ -1079,8 +1089,30 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
         cudaStreamWaitEvent(st_f, ev_init, 0);
         cudaStreamWaitEvent(ctx->aux[2], ev_init, 0);
     }
+    if (src) cudaStreamWaitEvent(ctx->copy_stream, ev_init, 0);
+    int64_t h2d_bytes = 0;
     for (int32_t e = 0; e < pl.n_epochs; e++) {
         cudaStream_t st_c = overlap ? ((e & 1) ? ctx->aux[2] : ctx->stream) : ctx->stream;
+        if (src) {      // this epoch's records: host -> HBM on the copy stream
+            const int32_t ta = e * pl.epoch_tiles, tb_ = std::min(rd->n_tiles, ta + pl.epoch_tiles);
+            if (tb_ > ta) {
+                const int64_t ra = rd->h_tiles[(size_t)ta].rec_beg;
+                const int64_t rb = rd->h_tiles[(size_t)tb_ - 1].rec_beg + rd->h_tiles[(size_t)tb_ - 1].n_rec;
+                const size_t nr = (size_t)(rb - ra);
+                const uint32_t ca = src->cig_off[ra], cb = src->cig_off[rb];
+                cudaStream_t cs = ctx->copy_stream;
+                cudaMemcpyAsync(rd->pos_end + ra, src->pos_end + 2 * ra, nr * 8, cudaMemcpyHostToDevice, cs);
+                cudaMemcpyAsync(rd->fmq + ra, src->fmq + ra, nr * 4, cudaMemcpyHostToDevice, cs);
+                cudaMemcpyAsync(rd->cig_off + ra, src->cig_off + ra, (nr + 1) * 4, cudaMemcpyHostToDevice, cs);
+                cudaMemcpyAsync(rd->keys + ra, src->keys + 2 * ra, nr * 16, cudaMemcpyHostToDevice, cs);
+                const uint32_t ca1 = ca ? ca - 1 : 0;      // one word back: a >=255-op count word
+                if (cb > ca1)
+                    cudaMemcpyAsync(rd->cigar + ca1, src->cigar + ca1, (size_t)(cb - ca1) * 4, cudaMemcpyHostToDevice, cs);
+                h2d_bytes += (int64_t)(nr * 32 + 4 + (size_t)(cb - ca1) * 4);
+            }
+            cudaEventRecord(EV(4, e), ctx->copy_stream);
+            cudaStreamWaitEvent(st_c, EV(4, e), 0);
+        }
         const int32_t z0 = pl.zero_ptr[(size_t)e], z1 = pl.zero_ptr[(size_t)e + 1];
         const int32_t n_seg = z1 - z0 - 1;
         if (overlap && e >= 2) cudaStreamWaitEvent(st_z, EV(3, e - 2), 0);
@@ -1198,5 +1230,52 @@ extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *fe
     ctx->timing[10] = ms_plan;
     ctx->timing[11] = ms_upload;
     ctx->timing[12] = ms_since(t_call);
+    ctx->timing[13] = (double)h2d_bytes;
     return XG_OK;
+}
+
+extern "C" int xg_basefc(xg_ctx *ctx, const xg_dreads *rd, const xg_features *feats,
+                         const xg_barcodes *cells, const xg_params *par, xg_coo **out) {
+    return basefc_run(ctx, rd, nullptr, feats, cells, par, out);
+}
+
+extern "C" int xg_basefc_host(xg_ctx *ctx, const xg_reads *h, const xg_features *feats,
+                              const xg_barcodes *cells, const xg_params *par, xg_coo **out) {
+    if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
+    if (!h) return ctx->fail(XG_E_ARG, "xg_basefc_host: null argument");
+    XG_CUDA(cudaSetDevice(ctx->device));
+    cudaPointerAttributes at;
+    if (h->n_reads > 0 && (cudaPointerGetAttributes(&at, h->pos_end) != cudaSuccess || at.type != cudaMemoryTypeHost)) {
+        cudaGetLastError();
+        return ctx->fail(XG_E_ARG, "xg_basefc_host: record arrays must be pinned host memory");
+    }
+    xg_dreads *d = new xg_dreads();
+    d->n_reads = h->n_reads;
+    d->n_cigar = h->n_cigar;
+    d->n_runs = h->n_runs;
+    d->n_tiles = h->n_tiles;
+    d->max_aln_len = h->max_aln_len;
+    d->max_span = h->max_span;
+    d->h_runs.assign(h->runs, h->runs + h->n_runs);
+    d->h_tiles.assign(h->tiles, h->tiles + h->n_tiles);
+    d->pooled = true;
+    const size_t n = (size_t)h->n_reads;
+    d->pos_end = (int2 *)ctx->dev_get(n * 8 + 16);
+    d->fmq = (uint32_t *)ctx->dev_get(n * 4 + 16);
+    d->cig_off = (uint32_t *)ctx->dev_get((n + 1) * 4 + 16);
+    d->keys = (ulonglong2 *)ctx->dev_get(n * 16 + 16);
+    d->cigar = (uint32_t *)ctx->dev_get((size_t)h->n_cigar * 4 + 16);
+    d->runs = (xg_run *)ctx->dev_get((size_t)h->n_runs * sizeof(xg_run) + 16);
+    d->tiles = (xg_tile *)ctx->dev_get((size_t)h->n_tiles * sizeof(xg_tile) + 16);
+    int rc = XG_OK;
+    if (!d->pos_end || !d->fmq || !d->cig_off || !d->keys || !d->cigar || !d->runs || !d->tiles) {
+        rc = ctx->fail(XG_E_CUDA, "out of device memory for the read batch");
+    } else {
+        cudaMemcpyAsync(d->runs, h->runs, (size_t)h->n_runs * sizeof(xg_run), cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d->tiles, h->tiles, (size_t)h->n_tiles * sizeof(xg_tile), cudaMemcpyHostToDevice, ctx->stream);
+        rc = basefc_run(ctx, d, h, feats, cells, par, out);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    xg_dreads_free(ctx, d);
+    return rc;
 }

@@ -42,6 +42,7 @@ struct xg_dreads {
 struct xg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;    // xg_basefc_host: H2D of the next epoch
     cudaStream_t aux[3] = {};              // overlapped epochs: zero, finalize, second count stream
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> ev_pool;     // per-epoch timing events

@@ -57,6 +57,7 @@ void xg_destroy(xg_ctx *ctx) {
         for (auto &ev : ctx->ev_pool) cudaEventDestroy(ev);
         for (auto &st : ctx->aux)
             if (st) cudaStreamDestroy(st);
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         for (auto &b : ctx->pinned) cudaFreeHost(b.p);
         for (auto &b : ctx->devbufs) cudaFree(b.p);
         if (ctx->fx_cache && ctx->fx_cache_free) ctx->fx_cache_free(ctx->fx_cache);

@@ -75,12 +75,14 @@ def get_context(device=0):
     return ctx
 
 
-def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, device=0, mapped=False):
+def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, device=0, mapped=False,
+               host_only=False):
     """Decode every BAM (host, multi-threaded) and upload the batch to `device`.
 
     chroms: distinct (already 'chr'-stripped) contig names the features / SNPs use; reads on
     other contigs can never be fetched by the reference and are dropped at decode time.
-    mapped: keep the records in pinned host memory and copy only pos/end (baf pileup)."""
+    mapped: keep the records in pinned host memory and copy only pos/end (baf pileup).
+    host_only: no upload at all -- the caller streams the batch with Context.basefc_host."""
     ctx = get_context(device)
     ks = lib.KeySpace()
     bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
@@ -88,8 +90,8 @@ def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, de
     host = lib.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, ks, n_threads)
     stats = {"n_reads": host.n, "n_records_seen": host.n_records_seen, "max_aln_len": host.max_aln_len,
              "max_span": host.max_span, "bytes": host.nbytes()}
-    if mapped:
-        batch = ReadBatch(ctx, ctx.map_reads(host), ks, gid_of, stats)
+    if mapped or host_only:
+        batch = ReadBatch(ctx, None if host_only else ctx.map_reads(host), ks, gid_of, stats)
         batch.host = host
         return batch
     dreads = ctx.upload(host)

@@ -108,6 +108,8 @@ SYMBOLS = {
     "xg_coo_free": (None, [C.POINTER(Coo)]),
     "xg_basefc": (C.c_int, [_P, _P, C.POINTER(Features), C.POINTER(Barcodes), C.POINTER(Params),
                             C.POINTER(C.POINTER(Coo))]),
+    "xg_basefc_host": (C.c_int, [_P, C.POINTER(Reads), C.POINTER(Features), C.POINTER(Barcodes), C.POINTER(Params),
+                                 C.POINTER(C.POINTER(Coo))]),
     "xg_baf_pileup": (C.c_int, [_P, _P, C.POINTER(Snps), C.POINTER(Barcodes), C.POINTER(Params),
                                 c_i64p, C.POINTER(_P)]),
     "xg_baf_count": (C.c_int, [_P, _P, C.c_int32, c_i64p, c_i32p, c_u8p, c_u8p, C.c_int32,
@@ -359,6 +361,19 @@ class Context(object):
         out = C.POINTER(Coo)()
         self._check(self.lib.xg_basefc(self.h, dreads.h, C.byref(f), C.byref(b), C.byref(params.c),
                                        C.byref(out)))
+        return coo_to_numpy(self.lib, out, ctx_obj=self)
+
+    def basefc_host(self, host_reads, gid, beg, end, cell_keys, n_samples, params):
+        """basefc straight from a pinned host batch: H2D streamed under the counting kernels."""
+        gid = np.ascontiguousarray(gid, dtype=np.int32)
+        beg = np.ascontiguousarray(beg, dtype=np.int32)
+        end = np.ascontiguousarray(end, dtype=np.int32)
+        keys = np.ascontiguousarray(cell_keys if cell_keys is not None else [], dtype=np.uint64)
+        f = Features(len(gid), as_ptr(gid, c_i32p), as_ptr(beg, c_i32p), as_ptr(end, c_i32p))
+        b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
+        out = C.POINTER(Coo)()
+        self._check(self.lib.xg_basefc_host(self.h, host_reads.ptr, C.byref(f), C.byref(b), C.byref(params.c),
+                                            C.byref(out)))
         return coo_to_numpy(self.lib, out, ctx_obj=self)
 
     def baf_pileup(self, dreads, gid, pos, cell_keys, n_samples, params):

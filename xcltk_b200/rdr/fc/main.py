@@ -270,7 +270,8 @@ def count_features(conf, batch=None):
             batch = engine.load_reads_multi(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False,
                                             threads, devices=tuple(range(n_dev)))
         else:
-            batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False, threads)
+            batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False, threads,
+                                      host_only=True)
     try:
         gid, beg, end = feature_arrays(regs, batch.gid_of)
         cell_keys = None
@@ -291,8 +292,12 @@ def count_features(conf, batch=None):
             conf.shard_sizes = [len(s) for s in shards]
         else:
             params = engine.make_params(conf, batch.stats["max_aln_len"], with_include=True)
-            row, col, val, _shape = batch.ctx.basefc(batch.dreads, gid, beg, end, cell_keys,
-                                                     len(conf.samples), params)
+            if batch.dreads is None:       # pinned host batch: H2D streamed under the kernels
+                row, col, val, _shape = batch.ctx.basefc_host(batch.host, gid, beg, end, cell_keys,
+                                                              len(conf.samples), params)
+            else:
+                row, col, val, _shape = batch.ctx.basefc(batch.dreads, gid, beg, end, cell_keys,
+                                                         len(conf.samples), params)
             conf.last_timing = batch.ctx.timing()
         conf.last_stats = dict(batch.stats)
     finally:
