@@ -1,0 +1,141 @@
+"""Host-side logic that must reproduce the reference exactly: the integer forms of the float
+comparisons, contig-name resolution, configuration errors, the SNP loaders and the join."""
+
+import logging
+import math
+import os
+
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from util import GOLD
+
+from xcltk_b200 import engine
+from xcltk_b200.utils.sam import build_tid_maps, resolve_tid
+
+logging.disable(logging.CRITICAL)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.floats(min_value=1e-6, max_value=0.999999), st.integers(min_value=1, max_value=400))
+def test_include_table_is_the_reference_expression(f, n):
+    """keep iff not (m / float(n) < min_include)  (rdr/fc/core.py:160-162)."""
+    tab, _ = engine.include_threshold(f, 400)
+    for m in range(0, n + 1):
+        assert (m >= tab[n]) == (not (m / float(n) < f))
+
+
+def test_include_length_mode_and_mapq():
+    for v, exp in ((0, 0), (1, 1), (1.0, 1), (20, 20), (2.5, 3), (-3, -3)):
+        tab, ln = engine.include_threshold(v, 100)
+        assert tab is None and ln == exp
+        for m in range(0, 30):
+            assert (m >= ln) == (not (m < v))
+    for x in (20, 20.0, 19.5, 0, 0.1, 255):
+        for mapq in range(0, 256):
+            assert (mapq < x) == (mapq < engine.min_mapq_int(x))
+    assert engine.include_threshold(0.9, 91)[0][91] == 82          # 81/91 < 0.9 <= 82/91
+    assert engine.include_threshold(0.9, 40)[0][40] == 36          # 36/40 passes
+
+
+def test_contig_resolution_follows_sam_fetch():
+    idx = {"chr1": 0, "2": 1, "chrM": 2, "MT": 3}
+    assert resolve_tid(idx, "1") == 0 and resolve_tid(idx, "2") == 1          # 'chr' toggled on / exact
+    assert resolve_tid(idx, "chr2") == 1 and resolve_tid(idx, "M") == 2
+    assert resolve_tid(idx, "3") == -1 and resolve_tid(idx, "MT") == 3
+    gid_of, maps = build_tid_maps([[("chr1", 10), ("2", 10)], [("1", 10), ("chr2", 10), ("X", 5)]], ["2", "1", "Q"])
+    assert gid_of == {"2": 0, "1": 1, "Q": 2}
+    assert maps == [[1, 0], [1, 0, -1]]
+    with pytest.raises(ValueError):
+        build_tid_maps([[("chr1", 10)]], ["1", "chr1"])
+
+
+def _conf(tmp_path, **kw):
+    from xcltk_b200.rdr.fc.config import Config
+    d = os.path.join(GOLD, "d1_basefc_mini")
+    c = Config()
+    c.sam_fn, c.barcode_fn = os.path.join(d, "a.bam"), os.path.join(d, "barcodes.tsv")
+    c.region_fn, c.out_dir = os.path.join(d, "features.tsv"), str(tmp_path / "o")
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+@pytest.mark.parametrize("kw", [
+    {"sam_list_fn": "x"}, {"sam_fn": None}, {"sam_fn": "/nonexistent.bam"}, {"sample_id_str": "a"},
+    {"barcode_fn": "/nonexistent.tsv"}, {"out_dir": None}, {"region_fn": None}, {"region_fn": "/nonexistent"},
+    {"cell_tag": "None"}, {"barcode_fn": None, "sample_id_str": "a,b"}, {"barcode_fn": None, "sample_id_str": "a"},
+])
+def test_basefc_configuration_errors_return_minus_one(tmp_path, kw):
+    from xcltk_b200.rdr.fc.main import fc_run, prepare_config
+    assert prepare_config(_conf(tmp_path, **kw)) == -1
+    assert fc_run(_conf(tmp_path, **kw)) == -1                     # ValueError("errcode -2") -> -1
+
+
+def test_basefc_prepare_config_derives_like_the_reference(tmp_path):
+    from xcltk_b200.rdr.fc.main import prepare_config
+    c = _conf(tmp_path, umi_tag="Auto")
+    assert prepare_config(c) == 0
+    assert c.samples == ["AAA", "BBB"] and c.umi_tag == "UB" and c.excl_flag == 772
+    assert open(c.out_sample_fn).read() == "AAA\nBBB\n"
+    assert [(r.chrom, r.start, r.end, r.get_id()) for r in c.reg_list][:2] == [("1", 175, 401, "g2"), ("1", 101, 201, "g1")]
+    c = _conf(tmp_path, umi_tag="none")
+    assert prepare_config(c) == 0 and c.umi_tag is None and c.excl_flag == 1796
+    c = _conf(tmp_path, excl_flag=4)
+    assert prepare_config(c) == 0 and c.excl_flag == 4              # CLI --exclFLAG is honoured
+
+
+def test_basefc_cli_options(tmp_path, monkeypatch):
+    """Option parsing of fc_main (long options case-insensitive, minINCLUDE int vs float)."""
+    from xcltk_b200.rdr.fc import main as m
+    seen = {}
+    monkeypatch.setattr(m, "fc_run", lambda conf: seen.setdefault("conf", conf) and 0)
+    monkeypatch.setattr(m, "init_logging", lambda **k: None)
+    m.fc_main(["xcltk", "basefc", "-s", "a.bam", "-b", "b.tsv", "-R", "r.tsv", "-O", "o", "-p", "4", "--cellTAG", "RG",
+               "--UMItag", "None", "--minMAPQ", "9.5", "--minINCLUDE", "20", "--countORPHAN", "--exclFLAG", "0"])
+    c = seen["conf"]
+    assert (c.sam_fn, c.nproc, c.cell_tag, c.umi_tag, c.min_mapq, c.min_include, c.no_orphan, c.excl_flag) == \
+        ("a.bam", 4, "RG", "None", 9.5, 20, False, 0) and isinstance(c.min_include, int)
+    seen.clear()
+    m.fc_main(["xcltk", "basefc", "-s", "a.bam", "--minINCLUDE", "0.5", "--minLEN", "10", "--inclFLAG", "2"])
+    assert seen["conf"].min_include == 0.5 and seen["conf"].min_len == 10 and seen["conf"].incl_flag == 2
+    with pytest.raises(SystemExit):
+        m.fc_main(["xcltk", "basefc"])
+
+
+def test_snp_loaders_and_region_join():
+    from xcltk_b200.baf.fc.utils import load_region_from_txt, load_snp_from_tsv, load_snp_from_vcf
+    d = os.path.join(GOLD, "d2_baf_mini")
+    tsv = load_snp_from_tsv(os.path.join(d, "snps.tsv"))
+    assert [(s.chrom, s.pos, s.ref, s.alt, s.ref_idx, s.alt_idx) for s in tsv.snps] == \
+        [("1", 120, "C", "T", 0, 1), ("1", 150, "G", "A", 1, 0), ("1", 550, "A", "C", 0, 1)]
+    vcf = load_snp_from_vcf(os.path.join(d, "snps.vcf"))          # lower-case REF, '/' GT, multi-base ALT, 1|1, no GT
+    assert [(s.chrom, s.pos, s.ref, s.alt, s.ref_idx) for s in vcf.snps] == \
+        [("1", 120, "C", "T", 0), ("1", 150, "G", "A", 1), ("1", 550, "A", "C", 0)]
+    regs = load_region_from_txt(os.path.join(d, "features.tsv"))
+    got = [[s.pos for s in tsv.fetch(r.chrom, r.start, r.end)] for r in regs]
+    assert got == [[120, 150], [550], [150]]
+    assert tsv.fetch("chr1", 150, 151)[0].pos == 150 and tsv.fetch("2", 1, 1000) == [] and tsv.fetch("1", 151, 151) == []
+    snp = tsv.snps[1]
+    assert [snp.get_region_allele_index(b) for b in "GACTN"] == [1, 0, -1, -1, -1]
+
+
+def test_baf_refuses_local_phasing_and_empty_region_list(tmp_path):
+    from xcltk_b200.baf.fc.main import afc_wrapper
+    d = os.path.join(GOLD, "d2_baf_mini")
+    args = (os.path.join(d, "a.bam"), os.path.join(d, "barcodes.tsv"), os.path.join(d, "features.tsv"),
+            os.path.join(d, "snps.tsv"), str(tmp_path / "o"))
+    assert afc_wrapper(*args, cellsnp_dir="/some/dir") == -1
+    far = str(tmp_path / "far.tsv")                               # no SNP in any region, output_all_reg=False:
+    with open(far, "w") as fp:                                    # the reference divides by zero workers
+        fp.write("9\t1\t100\tg\n")
+    with pytest.raises(ZeroDivisionError):
+        afc_wrapper(args[0], args[1], far, args[3], args[4])
+
+
+def test_write_mtx_format(tmp_path):
+    p = str(tmp_path / "m.mtx")
+    engine.write_mtx(p, 5, 2, np.array([1, 2, 2]), np.array([1, 1, 2]), np.array([1, 2, 1]))
+    assert open(p).read() == "%%MatrixMarket matrix coordinate integer general\n%%\n5\t2\t3\n1\t1\t1\n2\t1\t2\n2\t2\t1\n"
