@@ -227,19 +227,39 @@ struct BafRegDev {
     uint32_t *mask;
 };
 
-__global__ void k_baf_count_combos(BafRegDev P, unsigned long long *total) {
+// upper bound of the (region, cell, UMI) elements of every region: one per (winner, region)
+__global__ void k_baf_count_combos(BafRegDev P, int32_t *reg_cnt) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long c = 0;
-    if (p < P.n_pairs) {
-        uint32_t ca = P.pr_colal[p], snp = P.pr_snp[p];
-        if ((ca & 0x80000000u) && ((ca >> 24) & 7u) != CODE_NONE && P.keep[snp])
-            c = (unsigned long long)(P.snp_reg_ptr[snp + 1] - P.snp_reg_ptr[snp]);
-    }
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+    if (p >= P.n_pairs) return;
+    uint32_t ca = P.pr_colal[p], snp = P.pr_snp[p];
+    if (!(ca & 0x80000000u) || ((ca >> 24) & 7u) == CODE_NONE || !P.keep[snp]) return;
+    for (int64_t k = P.snp_reg_ptr[snp]; k < P.snp_reg_ptr[snp + 1]; k++) atomicAdd(&reg_cnt[P.snp_reg[k]], 1);
 }
 
-__global__ void k_baf_region_masks(BafRegDev P) {
+// find-or-insert of a 128-bit key; returns the slot and whether it was created by this call
+__device__ __forceinline__ uint32_t table_slot_new(xg_e128 *tbl, uint32_t cap, xg_e128 want, bool *is_new) {
+    uint32_t s = hash_to_range(mix64(want.a ^ (want.b * 0x9E3779B97F4A7C15ULL)), cap);
+    *is_new = false;
+    while (true) {
+        xg_e128 cur = ld128_relaxed(&tbl[s]);
+        if (cur.b == 0) {
+            xg_e128 empty;
+            empty.a = 0;
+            empty.b = 0;
+            cur = cas128(&tbl[s], empty, want);
+            if (cur.b == 0) {
+                *is_new = true;
+                return s;
+            }
+        }
+        if (cur.a == want.a && cur.b == want.b) return s;
+        s = (s + 1 == cap) ? 0 : s + 1;
+    }
+}
+
+// winners of kept SNPs OR their haplotype bit into (region, cell, UMI); a new element is
+// appended to its region's log so that the region can be reduced from its own elements only
+__global__ void k_baf_region_masks(BafRegDev P, const int64_t *reg_log_off, int32_t *reg_cur, uint32_t *reg_log) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.n_pairs) return;
     uint32_t ca = P.pr_colal[p], snp = P.pr_snp[p];
@@ -249,92 +269,170 @@ __global__ void k_baf_region_masks(BafRegDev P) {
     uint32_t col = ca & 0xFFFFFFu;
     uint64_t umi = P.pr_umi[p];
     for (int64_t k = P.snp_reg_ptr[snp]; k < P.snp_reg_ptr[snp + 1]; k++) {
+        const int32_t r = P.snp_reg[k];
         xg_e128 want;
         want.a = umi;
-        want.b = ((unsigned long long)col << 32) | ((unsigned long long)P.snp_reg[k] + 1ull);
-        uint32_t s = table_slot(P.tbl, P.cap, want);
+        want.b = ((unsigned long long)col << 32) | ((unsigned long long)r + 1ull);
+        bool is_new;
+        uint32_t s = table_slot_new(P.tbl, P.cap, want, &is_new);
         atomicOr(&P.mask[s], bit);
+        if (is_new) reg_log[reg_log_off[r] + atomicAdd(&reg_cur[r], 1)] = s;
     }
 }
 
-// masks of (region, cell, UMI) -> ref / alt / share / oth counters of (region, cell), rows [r0, r1)
-__global__ void k_baf_accumulate(const xg_e128 *tbl, const uint32_t *mask, uint32_t cap, int32_t r0,
-                                 int32_t r1, int32_t n_cols, uint32_t *cnt /* [4][rows][cols] */) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= cap) return;
-    xg_e128 e = tbl[s];
-    if (e.b == 0) return;
-    int32_t r = (int32_t)((e.b & 0xFFFFFFFFull) - 1ull);
-    if (r < r0 || r >= r1) return;
-    uint32_t col = (uint32_t)(e.b >> 32), m = mask[s];
-    size_t plane = (size_t)(r1 - r0) * (size_t)n_cols, o = (size_t)(r - r0) * (size_t)n_cols + col;
-    if (m & 1u) atomicAdd(&cnt[o], 1u);
-    if (m & 2u) atomicAdd(&cnt[plane + o], 1u);
-    if ((m & 3u) == 3u) atomicAdd(&cnt[2 * plane + o], 1u);
-    if ((m & 3u) == 0u && (m & 4u)) atomicAdd(&cnt[3 * plane + o], 1u);
-}
-
-struct BafVal {
-    const uint32_t *cnt;
-    size_t plane;
-    int32_t n_cols, which, no_dup;
-    __device__ int operator()(int row, int col) const {
-        size_t o = (size_t)row * (size_t)n_cols + col;
-        int ref = (int)cnt[o], alt = (int)cnt[plane + o], share = (int)cnt[2 * plane + o];
-        if (which == 2) return (int)cnt[3 * plane + o];
-        if (no_dup) {
-            ref -= share;
-            alt -= share;
-        }
-        return which == 0 ? alt : ref + alt;
-    }
-};
-
-// host-side concatenation of per-chunk results (rows offset by the chunk start)
-struct CooAccum {
-    std::vector<int32_t> row, col, val;
-    std::vector<int64_t> row_ptr{0};
-    void append(const xg_coo *m, int32_t r0) {
-        for (int64_t k = 0; k < m->nnz; k++) {
-            row.push_back(m->row[k] + r0);
-            col.push_back(m->col[k]);
-            val.push_back(m->val[k]);
-        }
-        int64_t base = row_ptr.back();
-        for (int32_t r = 0; r < m->n_rows; r++) row_ptr.push_back(base + m->row_ptr[r + 1]);
-    }
-    int finish(xg_ctx *ctx, int32_t n_rows, int32_t n_cols, xg_coo **out) {
-        while ((int32_t)row_ptr.size() < n_rows + 1) row_ptr.push_back(row_ptr.back());
-        xg_coo_owner *o = new xg_coo_owner();
-        memset(&o->m, 0, sizeof(o->m));
-        size_t nnz = row.size();
-        void *p[4] = {nullptr, nullptr, nullptr, nullptr};
-        size_t sz[4] = {(nnz + 1) * 4, (nnz + 1) * 4, (nnz + 1) * 4, row_ptr.size() * 8};
-        for (int k = 0; k < 4; k++)
-            if (!(p[k] = ctx->pinned_get(sz[k]))) {
-                for (int q = 0; q < k; q++) ctx->pinned_put(p[q]);
-                delete o;
-                return ctx->fail(XG_E_NOMEM, "out of pinned host memory");
+// Reduce one region to its rows of AD / DP / OTH (baf/fc/core.py:156-192 + emit :84-101):
+// per UMI mask m (bit0 ref-hap, bit1 alt-hap, bit2 other):
+//   no_dup_hap:  AD += alt - both,  DP += ref + alt - 2*both      (both = ref & alt)
+//   otherwise:   AD += alt,         DP += ref + alt
+//   OTH += other & !(ref | alt)
+// Histograms over cells + a bitmap of touched cells in shared memory; the set bits walked in
+// order give the rows in column order.  Persistent CTAs, work counter, staging + cursors per
+// matrix; column-range passes when 3 histograms of all cells do not fit.
+__global__ void __launch_bounds__(256) k_baf_finalize(const xg_e128 *tbl, const uint32_t *mask,
+                                                      const int64_t *reg_log_off, const int32_t *reg_cur,
+                                                      const uint32_t *reg_log, int32_t n_regions, int32_t n_cols,
+                                                      int32_t hist_cols, int32_t no_dup, unsigned int *work,
+                                                      unsigned long long *cursor /* [3] */,
+                                                      int64_t *seg_base /* [3][n_regions] */,
+                                                      int32_t *seg_nnz /* [3][n_regions] */,
+                                                      int32_t *st_col /* [3][cap] */, int32_t *st_val, int64_t st_cap) {
+    extern __shared__ uint32_t smem[];
+    uint32_t *hist = smem;                                   // [3][hist_cols]
+    uint32_t *bitmap = smem + 3 * (size_t)hist_cols;         // (hist_cols + 31) / 32
+    __shared__ int warp_tot[8];
+    __shared__ long long base_s;
+    __shared__ int r_s;
+    const int nwm = (hist_cols + 31) >> 5;
+    for (int c = threadIdx.x; c < 3 * hist_cols; c += blockDim.x) hist[c] = 0;
+    for (int c = threadIdx.x; c < nwm; c += blockDim.x) bitmap[c] = 0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n_pass = (n_cols + hist_cols - 1) / hist_cols;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) r_s = (int)atomicAdd(work, 1u);
+        __syncthreads();
+        const int r = r_s;
+        if (r >= n_regions) break;
+        const int n_el = reg_cur[r];
+        if (n_el == 0) continue;
+        const uint32_t *log = reg_log + reg_log_off[r];
+        long long base[3] = {0, 0, 0};
+        // stage 0 (only when n_pass > 1): count; stage 1: write
+        for (int stage = (n_pass > 1 ? 0 : 1); stage < 2; stage++) {
+            int total_nz[3] = {0, 0, 0};
+            for (int pass = 0; pass < n_pass; pass++) {
+                const uint32_t c_lo = (uint32_t)pass * (uint32_t)hist_cols;
+                const int nc = min(hist_cols, n_cols - (int)c_lo);
+                const int nw = (nc + 31) >> 5;
+                for (int k = threadIdx.x; k < n_el; k += blockDim.x) {
+                    const uint32_t s = log[k];
+                    const uint32_t col = (uint32_t)(tbl[s].b >> 32) - c_lo;
+                    if (col >= (uint32_t)nc) continue;
+                    const uint32_t m = mask[s];
+                    const int ref = m & 1, alt = (m >> 1) & 1, both = ref & alt;
+                    const int ad_c = no_dup ? alt - both : alt;
+                    const int dp_c = no_dup ? ref + alt - 2 * both : ref + alt;
+                    const int ot_c = ((m & 4u) && !(m & 3u)) ? 1 : 0;
+                    if (ad_c) atomicAdd(&hist[col], (uint32_t)ad_c);
+                    if (dp_c) atomicAdd(&hist[hist_cols + col], (uint32_t)dp_c);
+                    if (ot_c) atomicAdd(&hist[2 * hist_cols + col], 1u);
+                    if (ad_c | dp_c | ot_c) atomicOr(&bitmap[col >> 5], 1u << (col & 31));
+                }
+                __syncthreads();
+                const bool writing = (stage == 1);
+                for (int wh = 0; wh < 3; wh++) {
+                    const uint32_t *hw = hist + (size_t)wh * hist_cols;
+                    if (!writing || n_pass == 1) {            // non-zero cells of this range
+                        int nz = 0;
+                        for (int k = threadIdx.x; k < nw; k += blockDim.x) {
+                            uint32_t bits = bitmap[k];
+                            while (bits) {
+                                const int bpos = __ffs(bits) - 1;
+                                bits &= bits - 1;
+                                nz += hw[(k << 5) + bpos] != 0;
+                            }
+                        }
+                        for (int d = 16; d > 0; d >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, d);
+                        if (lane == 0) warp_tot[w] = nz;
+                        __syncthreads();
+                        for (int k = 0; k < 8; k++) total_nz[wh] += warp_tot[k];
+                        __syncthreads();
+                    }
+                    if (writing && n_pass == 1) {             // single range: reserve now
+                        if (threadIdx.x == 0) {
+                            long long b = total_nz[wh] ? (long long)atomicAdd(&cursor[wh], (unsigned long long)total_nz[wh]) : 0;
+                            seg_base[(size_t)wh * n_regions + r] = b;
+                            seg_nnz[(size_t)wh * n_regions + r] = total_nz[wh];
+                            base_s = b;
+                        }
+                        __syncthreads();
+                        base[wh] = base_s;
+                    }
+                    if (!writing) continue;
+                    for (int k0 = 0; k0 < nw; k0 += blockDim.x) {     // ordered walk over the bitmap
+                        const int k = k0 + threadIdx.x;
+                        uint32_t bits = k < nw ? bitmap[k] : 0u;
+                        int cnt = 0;
+                        for (uint32_t bb = bits; bb; bb &= bb - 1) cnt += hw[(k << 5) + __ffs(bb) - 1] != 0;
+                        int incl = cnt;
+                        for (int d = 1; d < 32; d <<= 1) {
+                            int y = __shfl_up_sync(0xffffffffu, incl, d);
+                            if (lane >= d) incl += y;
+                        }
+                        if (lane == 31) warp_tot[w] = incl;
+                        __syncthreads();
+                        int before = 0, tot = 0;
+                        for (int q = 0; q < 8; q++) {
+                            const int x = warp_tot[q];
+                            if (q < w) before += x;
+                            tot += x;
+                        }
+                        long long o = base[wh] + before + (incl - cnt);
+                        while (bits) {
+                            const int bpos = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const int c = (k << 5) + bpos;
+                            const uint32_t v = hw[c];
+                            if (v) {
+                                st_col[(size_t)wh * st_cap + o] = (int32_t)(c_lo + (uint32_t)c);
+                                st_val[(size_t)wh * st_cap + o] = (int32_t)v;
+                                o++;
+                            }
+                        }
+                        base[wh] += tot;
+                        __syncthreads();
+                    }
+                }
+                // clear what this range touched
+                for (int k = threadIdx.x; k < nw; k += blockDim.x) {
+                    uint32_t bits = bitmap[k];
+                    while (bits) {
+                        const int c = (k << 5) + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        hist[c] = 0;
+                        hist[hist_cols + c] = 0;
+                        hist[2 * hist_cols + c] = 0;
+                    }
+                    bitmap[k] = 0;
+                }
+                __syncthreads();
             }
-        o->ctx = ctx;
-        if (nnz) {
-            memcpy(p[0], row.data(), nnz * 4);
-            memcpy(p[1], col.data(), nnz * 4);
-            memcpy(p[2], val.data(), nnz * 4);
+            if (stage == 0) {                                 // multi-range: reserve after counting
+                for (int wh = 0; wh < 3; wh++) {
+                    if (threadIdx.x == 0) {
+                        long long b = total_nz[wh] ? (long long)atomicAdd(&cursor[wh], (unsigned long long)total_nz[wh]) : 0;
+                        seg_base[(size_t)wh * n_regions + r] = b;
+                        seg_nnz[(size_t)wh * n_regions + r] = total_nz[wh];
+                        base_s = b;
+                    }
+                    __syncthreads();
+                    base[wh] = base_s;
+                    __syncthreads();
+                }
+            }
         }
-        memcpy(p[3], row_ptr.data(), row_ptr.size() * 8);
-        o->bufs = {p[0], p[1], p[2], p[3]};
-        o->m.nnz = (int64_t)nnz;
-        o->m.n_rows = n_rows;
-        o->m.n_cols = n_cols;
-        o->m.row = (const int32_t *)p[0];
-        o->m.col = (const int32_t *)p[1];
-        o->m.val = (const int32_t *)p[2];
-        o->m.row_ptr = (const int64_t *)p[3];
-        *out = &o->m;
-        return XG_OK;
     }
-};
+}
 
 template <class T>
 int upload_arr(xg_ctx *ctx, const T *src, size_t n, const char *name, const T **out) {
@@ -377,22 +475,54 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
     if (!par->use_cell_tag)
         for (auto &r : rd->h_runs)
             if (r.bam_idx >= cells->n_samples) return ctx->fail(XG_E_ARG, "more BAMs than sample columns");
-    // SNPs sorted by (gid, pos); pos < 0 (1-based pos <= 0) can never be fetched
-    std::vector<int32_t> ord;
-    for (int32_t i = 0; i < snps->n; i++)
-        if (snps->gid[i] >= 0 && snps->gid[i] < n_gid && snps->pos[i] >= 0) ord.push_back(i);
-    std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {
-        if (snps->gid[a] != snps->gid[b]) return snps->gid[a] < snps->gid[b];
-        if (snps->pos[a] != snps->pos[b]) return snps->pos[a] < snps->pos[b];
-        return a < b;
-    });
-    std::vector<int32_t> goff((size_t)n_gid + 1, 0), spos(ord.size()), sidx(ord.size());
-    for (size_t k = 0; k < ord.size(); k++) {
-        goff[(size_t)snps->gid[ord[k]] + 1]++;
-        spos[k] = snps->pos[ord[k]];
-        sidx[k] = ord[k];
+    // SNPs sorted by (gid, pos); pos < 0 (1-based pos <= 0) can never be fetched.  The sorted
+    // table depends on the SNP list only: it is kept on the device while the caller passes
+    // the same list (hash of the arrays).
+    uint64_t sh = 1469598103934665603ull;
+    auto mixh = [&](const void *p, size_t n) {
+        const uint8_t *q = (const uint8_t *)p;
+        size_t k = 0;
+        for (; k + 8 <= n; k += 8) {               // word-wise FNV-style mix
+            uint64_t wv;
+            memcpy(&wv, q + k, 8);
+            sh = (sh ^ wv) * 1099511628211ull;
+            sh ^= sh >> 29;
+        }
+        for (; k < n; k++) sh = (sh ^ q[k]) * 1099511628211ull;
+    };
+    mixh(&n_gid, sizeof n_gid);
+    mixh(&snps->n, sizeof snps->n);
+    mixh(snps->gid, sizeof(int32_t) * (size_t)snps->n);
+    mixh(snps->pos, sizeof(int32_t) * (size_t)snps->n);
+    const bool snp_cached = ctx->bf_snp_valid && ctx->bf_snp_hash == sh;
+    if (!snp_cached) {
+        ctx->bf_snp_valid = false;
+        std::vector<int32_t> ord;
+        for (int32_t i = 0; i < snps->n; i++)
+            if (snps->gid[i] >= 0 && snps->gid[i] < n_gid && snps->pos[i] >= 0) ord.push_back(i);
+        std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {
+            if (snps->gid[a] != snps->gid[b]) return snps->gid[a] < snps->gid[b];
+            if (snps->pos[a] != snps->pos[b]) return snps->pos[a] < snps->pos[b];
+            return a < b;
+        });
+        std::vector<int32_t> goff((size_t)n_gid + 1, 0), spos(ord.size()), sidx(ord.size());
+        for (size_t k = 0; k < ord.size(); k++) {
+            goff[(size_t)snps->gid[ord[k]] + 1]++;
+            spos[k] = snps->pos[ord[k]];
+            sidx[k] = ord[k];
+        }
+        for (int32_t g = 0; g < n_gid; g++) goff[(size_t)g + 1] += goff[(size_t)g];
+        const int32_t *dummy = nullptr;
+        int rc0;
+        if ((rc0 = upload_arr(ctx, goff.data(), goff.size(), "bf_goff", &dummy))) return rc0;
+        if ((rc0 = upload_arr(ctx, spos.data(), spos.size(), "bf_spos", &dummy))) return rc0;
+        if ((rc0 = upload_arr(ctx, sidx.data(), sidx.size(), "bf_sidx", &dummy))) return rc0;
+        XG_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->bf_snp_hash = sh;
+        ctx->bf_snp_sorted = (int64_t)ord.size();
+        ctx->bf_snp_valid = true;
     }
-    for (int32_t g = 0; g < n_gid; g++) goff[(size_t)g + 1] += goff[(size_t)g];
+    const bool any_snp = ctx->bf_snp_sorted > 0;
 
     BafScanDev P;
     memset(&P, 0, sizeof(P));
@@ -407,9 +537,9 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
     P.tiles = rd->tiles;
     P.n_gid = n_gid;
     int rc;
-    if ((rc = upload_arr(ctx, goff.data(), goff.size(), "bf_goff", &P.snp_goff))) return rc;
-    if ((rc = upload_arr(ctx, spos.data(), spos.size(), "bf_spos", &P.snp_pos))) return rc;
-    if ((rc = upload_arr(ctx, sidx.data(), sidx.size(), "bf_sidx", &P.snp_idx))) return rc;
+    P.snp_goff = (const int32_t *)ctx->scratch["bf_goff"].p;
+    P.snp_pos = (const int32_t *)ctx->scratch["bf_spos"].p;
+    P.snp_idx = (const int32_t *)ctx->scratch["bf_sidx"].p;
     P.fp.min_mapq = par->min_mapq;
     P.fp.min_len = par->min_len;
     P.fp.incl_flag = par->incl_flag;
@@ -440,7 +570,7 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
         P.cap_pairs = cap_pairs;
         XG_CUDA(cudaMemsetAsync(d_npairs, 0, 16, ctx->stream));
         cudaEventRecord(ctx->ev[1], ctx->stream);
-        if (rd->n_tiles > 0 && !ord.empty()) {
+        if (rd->n_tiles > 0 && any_snp) {
             k_baf_scan<<<rd->n_tiles, 256, 0, ctx->stream>>>(P);
             launches++;
             XG_CUDA(cudaGetLastError());
@@ -487,17 +617,23 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
         cudaMemcpyAsync(st->pr_umi, P.pr_umi, n_pairs * 8, cudaMemcpyDeviceToDevice, ctx->stream);
     }
     cudaEventRecord(ctx->ev[3], ctx->stream);
-    std::vector<unsigned long long> h_tot((size_t)snps->n * 5 + 1);
+    unsigned long long *h_tot = (unsigned long long *)ctx->pinned_get(sizeof(unsigned long long) * ((size_t)snps->n * 5 + 1));
+    if (!h_tot) {
+        xg_baf_state_free(ctx, st);
+        return ctx->fail(XG_E_NOMEM, "out of pinned host memory");
+    }
     cudaEventRecord(ctx->ev[4], ctx->stream);
-    cudaMemcpyAsync(h_tot.data(), d_totals, sizeof(unsigned long long) * (size_t)snps->n * 5,
+    cudaMemcpyAsync(h_tot, d_totals, sizeof(unsigned long long) * (size_t)snps->n * 5,
                     cudaMemcpyDeviceToHost, ctx->stream);
     cudaEventRecord(ctx->ev[5], ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
+        ctx->pinned_put(h_tot);
         xg_baf_state_free(ctx, st);
         return ctx->fail(XG_E_CUDA, std::string("baf pileup: ") + cudaGetErrorString(e));
     }
     for (size_t k = 0; k < (size_t)snps->n * 5; k++) totals[k] = (int64_t)h_tot[k];
+    ctx->pinned_put(h_tot);
     float t_all = 0, t_d2h = 0;
     cudaEventElapsedTime(&t_all, ctx->ev[0], ctx->ev[3]);
     cudaEventElapsedTime(&t_d2h, ctx->ev[4], ctx->ev[5]);
@@ -548,64 +684,70 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
     if ((rc = upload_arr(ctx, sr.data(), sr.size(), "bf_sr", &R.snp_reg))) return rc;
     if ((rc = upload_arr(ctx, hap_of, (size_t)n_snps * 8, "bf_hap_of", &R.hap_of))) return rc;
     if ((rc = upload_arr(ctx, keep, (size_t)n_snps, "bf_keep", &R.keep))) return rc;
-    XG_GET(d_total, unsigned long long, "bf_combo_total", 2);
+    XG_GET(reg_cnt, int32_t, "bf_reg_cnt", n_regions + 1);
+    XG_GET(reg_cur, int32_t, "bf_reg_cur", n_regions + 1);
+    XG_GET(reg_log_off, int64_t, "bf_reg_log_off", n_regions + 2);
+    XG_GET(cursor, unsigned long long, "bf_cursor", 4);
+    XG_GET(work, unsigned int, "bf_work", 4);
+    XG_GET(seg_base, int64_t, "bf_seg_base", 3 * (size_t)n_regions + 1);
+    XG_GET(seg_nnz, int32_t, "bf_seg_nnz", 3 * (size_t)n_regions + 1);
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
-    unsigned long long combos = 0;
     unsigned grid = (unsigned)((st->n_pairs + 255) / 256);
-    XG_CUDA(cudaMemsetAsync(d_total, 0, 16, ctx->stream));
+    XG_CUDA(cudaMemsetAsync(reg_cnt, 0, sizeof(int32_t) * (size_t)(n_regions + 1), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(reg_cur, 0, sizeof(int32_t) * (size_t)(n_regions + 1), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(cursor, 0, 32, ctx->stream));
+    XG_CUDA(cudaMemsetAsync(work, 0, 16, ctx->stream));
+    XG_CUDA(cudaMemsetAsync(seg_base, 0, sizeof(int64_t) * (3 * (size_t)n_regions + 1), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(seg_nnz, 0, sizeof(int32_t) * (3 * (size_t)n_regions + 1), ctx->stream));
     if (st->n_pairs > 0) {
-        k_baf_count_combos<<<grid, 256, 0, ctx->stream>>>(R, d_total);
+        k_baf_count_combos<<<grid, 256, 0, ctx->stream>>>(R, reg_cnt);
         launches++;
     }
-    XG_CUDA(cudaMemcpyAsync(&combos, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(reg_cnt, reg_log_off, n_regions);
+    launches++;
+    long long combos = 0;
+    XG_CUDA(cudaMemcpyAsync(&combos, reg_log_off + n_regions, 8, cudaMemcpyDeviceToHost, ctx->stream));
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (combos >= (1ull << 31)) return ctx->fail(XG_E_LIMIT, "more than 2^31 (region, cell, UMI) candidates");
+    if (combos >= (1ll << 31)) return ctx->fail(XG_E_LIMIT, "more than 2^31 (region, cell, UMI) candidates");
     const uint32_t cap = (uint32_t)(2 * combos + 16);
     XG_GET(tbl, xg_e128, "bf_tbl2", cap);
     XG_GET(mask, uint32_t, "bf_mask", cap);
+    XG_GET(reg_log, uint32_t, "bf_reg_log", combos + 1);
+    XG_GET(st_col, int32_t, "bf_st_col", 3 * (size_t)combos + 1);
+    XG_GET(st_val, int32_t, "bf_st_val", 3 * (size_t)combos + 1);
     XG_CUDA(cudaMemsetAsync(tbl, 0, sizeof(xg_e128) * cap, ctx->stream));
     XG_CUDA(cudaMemsetAsync(mask, 0, sizeof(uint32_t) * cap, ctx->stream));
     R.tbl = tbl;
     R.cap = cap;
     R.mask = mask;
     if (combos > 0) {
-        k_baf_region_masks<<<grid, 256, 0, ctx->stream>>>(R);
+        k_baf_region_masks<<<grid, 256, 0, ctx->stream>>>(R, reg_log_off, reg_cur, reg_log);
+        launches++;
+        // three histograms over the cells (+ bitmap) in shared memory; column ranges if too many
+        const int32_t hist_cols = std::min(n_cols, 14 * 1024);
+        const size_t smem = (size_t)hist_cols * 12 + (size_t)((hist_cols + 31) / 32) * 4;
+        XG_CUDA(cudaFuncSetAttribute(k_baf_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = std::max(1, std::min(8, (int)(200 * 1024 / (smem + 1024))));
+        k_baf_finalize<<<std::min(n_regions, 148 * per_sm), 256, smem, ctx->stream>>>(
+            tbl, mask, reg_log_off, reg_cur, reg_log, n_regions, n_cols, hist_cols, no_dup_hap, work, cursor,
+            seg_base, seg_nnz, st_col, st_val, (int64_t)combos);
         launches++;
         XG_CUDA(cudaGetLastError());
     }
-    // dense (region, cell) counters in row chunks of bounded size
-    const size_t budget = (size_t)1 << 31;    // bytes for the 4 counter planes
-    int32_t rows_per_chunk = (int32_t)std::max<size_t>(1, budget / ((size_t)n_cols * 16));
-    rows_per_chunk = std::min(rows_per_chunk, std::max(n_regions, 1));
-    XG_GET(cnt, uint32_t, "bf_cnt", (size_t)rows_per_chunk * (size_t)n_cols * 4);
-    CooAccum acc[3];
-    for (int32_t r0 = 0; r0 < n_regions; r0 += rows_per_chunk) {
-        int32_t r1 = std::min(n_regions, r0 + rows_per_chunk), nr = r1 - r0;
-        size_t plane = (size_t)nr * (size_t)n_cols;
-        XG_CUDA(cudaMemsetAsync(cnt, 0, plane * 16, ctx->stream));
-        if (combos > 0) {
-            k_baf_accumulate<<<(cap + 255) / 256, 256, 0, ctx->stream>>>(tbl, mask, cap, r0, r1, n_cols, cnt);
-            launches++;
-        }
-        for (int which = 0; which < 3; which++) {
-            BafVal v{cnt, plane, n_cols, which, no_dup_hap};
-            xg_coo *part = nullptr;
-            rc = xg_dense_to_coo(ctx, v, nr, n_cols, "bf", &part, &launches);
-            if (rc) return rc;
-            acc[which].append(part, r0);
-            xg_coo_free(part);
-        }
-    }
-    cudaEventRecord(ctx->ev[3], ctx->stream);
+    xg_coo **outs[3] = {ad, dp, oth};
+    const char *tags[3] = {"bfad", "bfdp", "bfot"};
+    for (int wh = 0; wh < 3; wh++)
+        if ((rc = xg_staging_to_coo(ctx, tags[wh], n_regions, n_cols, seg_base + (size_t)wh * n_regions,
+                                    seg_nnz + (size_t)wh * n_regions, st_col + (size_t)wh * combos,
+                                    st_val + (size_t)wh * combos, outs[wh], &launches)))
+            return rc;
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
     float t_all = 0;
     cudaEventElapsedTime(&t_all, ctx->ev[0], ctx->ev[3]);
-    ctx->timing[0] = t_all - ctx->timing[4];
+    ctx->timing[0] = t_all;
     ctx->timing[2] = launches;
-    xg_coo **outs[3] = {ad, dp, oth};
-    for (int which = 0; which < 3; which++)
-        if ((rc = acc[which].finish(ctx, n_regions, n_cols, outs[which]))) return rc;
+    ctx->timing[6] = (double)combos;
     return XG_OK;
 }

@@ -529,7 +529,7 @@ __device__ __forceinline__ void flush_pairs(const BasefcDev &P, PairStage &S) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 4) k_basefc_count(const __grid_constant__ BasefcDev P) {
+__global__ void __launch_bounds__(256, 6) k_basefc_count(const __grid_constant__ BasefcDev P) {
     __shared__ PairStage S;
     const int t = P.tile0 + blockIdx.x;
     const xg_tile tile = P.tiles[t];
@@ -844,21 +844,6 @@ __global__ void __launch_bounds__(256) k_basefc_finalize(const uint8_t *pool, co
     }
 }
 
-__global__ void __launch_bounds__(256) k_gather_rows(int32_t n_rows, const int64_t *seg_base,
-                                                     const int32_t *seg_nnz, const int64_t *row_ptr,
-                                                     const int32_t *st_col, const int32_t *st_val,
-                                                     int32_t *o_row, int32_t *o_col, int32_t *o_val) {
-    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
-        const int n = seg_nnz[row];
-        const int64_t src = seg_base[row], dst = row_ptr[row];
-        for (int k = threadIdx.x; k < n; k += blockDim.x) {
-            o_row[dst + k] = row;
-            o_col[dst + k] = st_col[src + k];
-            o_val[dst + k] = st_val[src + k];
-        }
-    }
-}
-
 }  // namespace
 
 template <class T>
@@ -905,7 +890,14 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     uint64_t fh = 1469598103934665603ull;
     auto mixh = [&](const void *p, size_t n) {
         const uint8_t *b = (const uint8_t *)p;
-        for (size_t k = 0; k < n; k++) fh = (fh ^ b[k]) * 1099511628211ull;
+        size_t k = 0;
+        for (; k + 8 <= n; k += 8) {               // word-wise FNV-style mix
+            uint64_t wv;
+            memcpy(&wv, b + k, 8);
+            fh = (fh ^ wv) * 1099511628211ull;
+            fh ^= fh >> 29;
+        }
+        for (; k < n; k++) fh = (fh ^ b[k]) * 1099511628211ull;
     };
     mixh(&n_gid, sizeof n_gid);
     mixh(&feats->n, sizeof feats->n);
@@ -1045,7 +1037,6 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_GET(pool, uint8_t, "fx_pool", pl.pool_bytes + 16);
     XG_GET(seg_base, int64_t, "fx_seg_base", n_rows + 1);
     XG_GET(seg_nnz, int32_t, "fx_seg_nnz", n_rows + 1);
-    XG_GET(row_ptr, int64_t, "fx_row_ptr", n_rows + 2);
     XG_GET(st_col, int32_t, "fx_st_col", pl.staging_cap + 1);
     XG_GET(st_val, int32_t, "fx_st_val", pl.staging_cap + 1);
     XG_GET(cursor, unsigned long long, "fx_cursor", 2);
@@ -1152,62 +1143,13 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         if (pl.n_epochs > 1) cudaStreamWaitEvent(ctx->stream, EV(2, pl.n_epochs - 2), 0);
     }
     XG_CUDA(cudaGetLastError());
-    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(seg_nnz, row_ptr, n_rows);
-    launches++;
-    int64_t nnz = 0;
-    XG_CUDA(cudaMemcpyAsync(&nnz, row_ptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    XG_CUDA(cudaStreamSynchronize(ctx->stream));
-    XG_GET(d_row, int32_t, "fx_coo_row", nnz + 1);
-    XG_GET(d_col, int32_t, "fx_coo_col", nnz + 1);
-    XG_GET(d_val, int32_t, "fx_coo_val", nnz + 1);
-    if (nnz > 0) {
-        k_gather_rows<<<std::min(n_rows, 148 * 32), 256, 0, ctx->stream>>>(n_rows, seg_base, seg_nnz, row_ptr,
-                                                                          st_col, st_val, d_row, d_col, d_val);
-        launches++;
-    }
-    cudaEventRecord(ctx->ev[3], ctx->stream);
-    XG_CUDA(cudaGetLastError());
+    if ((rc = xg_staging_to_coo(ctx, "fx", n_rows, n_cols, seg_base, seg_nnz, st_col, st_val, out, &launches)))
+        return rc;
 
-    // ---- result -> pinned host memory
-    xg_coo_owner *o = new xg_coo_owner();
-    memset(&o->m, 0, sizeof(o->m));
-    void *hp[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t hs[4] = {(size_t)(nnz + 1) * 4, (size_t)(nnz + 1) * 4, (size_t)(nnz + 1) * 4, (size_t)(n_rows + 1) * 8};
-    for (int k = 0; k < 4; k++)
-        if (!(hp[k] = ctx->pinned_get(hs[k]))) {
-            for (int q = 0; q < k; q++) ctx->pinned_put(hp[q]);
-            delete o;
-            return ctx->fail(XG_E_NOMEM, "out of pinned host memory for the result");
-        }
-    o->bufs = {hp[0], hp[1], hp[2], hp[3]};
-    o->ctx = ctx;
-    cudaEventRecord(ctx->ev[4], ctx->stream);
-    if (nnz > 0) {
-        cudaMemcpyAsync(hp[0], d_row, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(hp[1], d_col, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(hp[2], d_val, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
-    }
-    cudaMemcpyAsync(hp[3], row_ptr, (size_t)(n_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaEventRecord(ctx->ev[5], ctx->stream);
-    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
-    if (ce != cudaSuccess) {
-        for (void *p : o->bufs) ctx->pinned_put(p);
-        delete o;
-        return ctx->fail(XG_E_CUDA, std::string("xg_basefc: ") + cudaGetErrorString(ce));
-    }
-    o->m.nnz = nnz;
-    o->m.n_rows = n_rows;
-    o->m.n_cols = n_cols;
-    o->m.row = (const int32_t *)hp[0];
-    o->m.col = (const int32_t *)hp[1];
-    o->m.val = (const int32_t *)hp[2];
-    o->m.row_ptr = (const int64_t *)hp[3];
-    *out = &o->m;
-
-    float t_all = 0, t_d2h = 0;
+    float t_all = 0;
+    const double t_d2h = ctx->timing[4];
     double t_cnt = 0;
     cudaEventElapsedTime(&t_all, ctx->ev[0], ctx->ev[3]);
-    cudaEventElapsedTime(&t_d2h, ctx->ev[4], ctx->ev[5]);
     int n_cnt = 0;
     for (int32_t e = 0; e < pl.n_epochs; e++) {
         float t = 0;

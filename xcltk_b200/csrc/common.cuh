@@ -141,6 +141,10 @@ struct xg_ctx {
             }
         cudaFree(p);
     }
+    // cache of the last sorted SNP table of xg_baf_pileup (device arrays in scratch "bf_*")
+    bool bf_snp_valid = false;
+    uint64_t bf_snp_hash = 0;
+    int64_t bf_snp_sorted = 0;
     // cache of the last interval index built by xg_basefc (owned by basefc.cu)
     void *fx_cache = nullptr;
     void (*fx_cache_free)(void *) = nullptr;

@@ -154,3 +154,82 @@ int xg_dense_to_coo(xg_ctx *ctx, V v, int32_t n_rows, int32_t n_cols, const char
     *out = &o->m;
     return XG_OK;
 }
+
+// Rows were written to a staging area in completion order (seg_base / seg_nnz per row);
+// copy them to their place in row order.
+static __global__ void __launch_bounds__(256) k_gather_rows(int32_t n_rows, const int64_t *seg_base,
+                                                            const int32_t *seg_nnz, const int64_t *row_ptr,
+                                                            const int32_t *st_col, const int32_t *st_val,
+                                                            int32_t *o_row, int32_t *o_col, int32_t *o_val) {
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const int n = seg_nnz[row];
+        const int64_t src = seg_base[row], dst = row_ptr[row];
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            o_row[dst + k] = row;
+            o_col[dst + k] = st_col[src + k];
+            o_val[dst + k] = st_val[src + k];
+        }
+    }
+}
+
+// seg_nnz -> row_ptr (scan), staging -> (row, col)-sorted device COO (gather), -> pinned host.
+// One host synchronisation for nnz.  `tag` names the scratch buffers.
+static int xg_staging_to_coo(xg_ctx *ctx, const char *tag, int32_t n_rows, int32_t n_cols,
+                             const int64_t *seg_base, const int32_t *seg_nnz, const int32_t *st_col,
+                             const int32_t *st_val, xg_coo **out, int *n_launches) {
+    std::string t(tag);
+    XG_GET(row_ptr, int64_t, (t + "_row_ptr").c_str(), n_rows + 2);
+    k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(seg_nnz, row_ptr, n_rows);
+    int64_t nnz = 0;
+    XG_CUDA(cudaMemcpyAsync(&nnz, row_ptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    XG_GET(d_row, int32_t, (t + "_coo_row").c_str(), nnz + 1);
+    XG_GET(d_col, int32_t, (t + "_coo_col").c_str(), nnz + 1);
+    XG_GET(d_val, int32_t, (t + "_coo_val").c_str(), nnz + 1);
+    *n_launches += 1;
+    if (nnz > 0) {
+        k_gather_rows<<<n_rows < 148 * 32 ? n_rows : 148 * 32, 256, 0, ctx->stream>>>(
+            n_rows, seg_base, seg_nnz, row_ptr, st_col, st_val, d_row, d_col, d_val);
+        *n_launches += 1;
+    }
+    cudaEventRecord(ctx->ev[3], ctx->stream);
+    XG_CUDA(cudaGetLastError());
+    xg_coo_owner *o = new xg_coo_owner();
+    memset(&o->m, 0, sizeof(o->m));
+    void *hp[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t hs[4] = {(size_t)(nnz + 1) * 4, (size_t)(nnz + 1) * 4, (size_t)(nnz + 1) * 4, (size_t)(n_rows + 1) * 8};
+    for (int k = 0; k < 4; k++)
+        if (!(hp[k] = ctx->pinned_get(hs[k]))) {
+            for (int q = 0; q < k; q++) ctx->pinned_put(hp[q]);
+            delete o;
+            return ctx->fail(XG_E_NOMEM, "out of pinned host memory for the result");
+        }
+    o->bufs = {hp[0], hp[1], hp[2], hp[3]};
+    o->ctx = ctx;
+    cudaEventRecord(ctx->ev[4], ctx->stream);
+    if (nnz > 0) {
+        cudaMemcpyAsync(hp[0], d_row, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(hp[1], d_col, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(hp[2], d_val, (size_t)nnz * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    cudaMemcpyAsync(hp[3], row_ptr, (size_t)(n_rows + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaEventRecord(ctx->ev[5], ctx->stream);
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) {
+        for (void *q : o->bufs) ctx->pinned_put(q);
+        delete o;
+        return ctx->fail(XG_E_CUDA, std::string("result D2H: ") + cudaGetErrorString(ce));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+    ctx->timing[4] += ms;
+    o->m.nnz = nnz;
+    o->m.n_rows = n_rows;
+    o->m.n_cols = n_cols;
+    o->m.row = (const int32_t *)hp[0];
+    o->m.col = (const int32_t *)hp[1];
+    o->m.val = (const int32_t *)hp[2];
+    o->m.row_ptr = (const int64_t *)hp[3];
+    *out = &o->m;
+    return XG_OK;
+}
