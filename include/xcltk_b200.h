@@ -130,6 +130,9 @@ typedef struct xg_dreads xg_dreads;      /* read records resident in HBM */
 int xg_create(int32_t device, xg_ctx **out);
 void xg_destroy(xg_ctx *ctx);
 const char *xg_last_error(xg_ctx *ctx);
+/* Options: "coo_rows" (default 1): 0 = results are CSR only (row == NULL; row_ptr, col, val),
+ * which saves a third of the device->host result copy.                                   */
+int xg_set_option(xg_ctx *ctx, const char *name, int64_t value);
 
 /* Host -> HBM copy of a decoded batch (the only cross-device traffic of the path).      */
 int xg_upload_reads(xg_ctx *ctx, const xg_reads *host, xg_dreads **out);
@@ -183,7 +186,7 @@ typedef struct {
 typedef struct {
     int64_t nnz;
     int32_t n_rows, n_cols;
-    const int32_t *row;
+    const int32_t *row;       /* NULL when the context option "coo_rows" is 0 (CSR only) */
     const int32_t *col;
     const int32_t *val;
     const int64_t *row_ptr;   /* CSR offsets, n_rows + 1 */

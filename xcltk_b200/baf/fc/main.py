@@ -293,8 +293,8 @@ def afc_core(conf):
     # entry, or output_all_reg; SNP-less regions only with output_all_reg.
     n_reg = len(regs)
     has = np.zeros(n_reg, dtype=bool)
-    has[dp[0]] = True
-    has[oth[0]] = True
+    has[np.asarray(dp[0])] = True
+    has[np.asarray(oth[0])] = True
     emitted = np.ones(n_reg, dtype=bool) if conf.output_all_reg else has
     new_row = np.cumsum(emitted)
     with open(conf.out_region_fn, "w") as fp:
@@ -302,7 +302,7 @@ def afc_core(conf):
                          for r, e in zip(regs, emitted) if e))
     n_out = int(emitted.sum())
     for fn, (row, col, val, _shape) in ((conf.out_ad_fn, ad), (conf.out_dp_fn, dp), (conf.out_oth_fn, oth)):
-        engine.write_mtx(fn, n_out, len(conf.samples), new_row[row], col + 1, val)
+        engine.write_mtx(fn, n_out, len(conf.samples), new_row[np.asarray(row)], col + 1, val)
 
 
 def afc_run(conf):

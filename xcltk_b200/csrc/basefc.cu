@@ -650,10 +650,15 @@ __global__ void __launch_bounds__(256, 6) k_basefc_count(const __grid_constant__
         // first boundary > pos (global index)
         int32_t ub;
         if (staged) {
-            int32_t lo = 0, hi = nb;
-            while (lo < hi) {
-                int32_t mid = (lo + hi) >> 1;
-                if (S.bnd[mid] <= pos) lo = mid + 1; else hi = mid;
+            int32_t lo = 0;
+            if (nb <= 8) {                     // few boundaries under the tile: branch-free count
+                for (int k = 0; k < nb; k++) lo += S.bnd[k] <= pos;
+            } else {
+                int32_t hi = nb;
+                while (lo < hi) {
+                    int32_t mid = (lo + hi) >> 1;
+                    if (S.bnd[mid] <= pos) lo = mid + 1; else hi = mid;
+                }
             }
             ub = tb.x + lo;
         } else {
@@ -700,334 +705,6 @@ __global__ void __launch_bounds__(256, 6) k_basefc_count(const __grid_constant__
     __syncthreads();
 
     flush_pairs(P, S);
-}
-
-// ---- counting kernel, version 2: dense lanes -------------------------------------------
-// Same work as k_basefc_count, organised as a pipeline of shared-memory queues that WARPS drain
-// 32 (or 64) entries at a time, so that after every filtering step the surviving work is dense
-// again instead of leaving lanes idle for the rest of the record's processing:
-//   records (512 per CTA = half a tile, 2 per thread, loaded up front)
-//     -> flags / UMI / cell filters -> survivor queue (simple reads from the front, reads with
-//        a stored CIGAR from the back; pushes are ballot-aggregated: one atomic per warp)
-//     -> [simple] boundary search + stabbing list + arithmetic include test   -> pair stage
-//     -> [CIGAR]  aligned length from the staged CIGAR + per-block include    -> pair stage
-//     -> insert into the features' sets + new-element log (match_any aggregated)
-#define V2_REC 512
-#define V2_PAIRS 768
-
-struct StageV2 {
-    unsigned long long q_umi[V2_REC];
-    int32_t q_pos[V2_REC], q_end[V2_REC];
-    uint32_t q_co[V2_REC], q_colops[V2_REC];     // col | n_ops << 24
-    unsigned long long p_umi[V2_PAIRS];
-    uint32_t p_j[V2_PAIRS], p_col[V2_PAIRS];
-    int4 stab4[STAB_CAP];
-    uint32_t cigar[CIG_CAP];
-    int32_t bnd[SB_MAX], stab_off[SB_MAX + 1];
-    int n_simple, n_complex, head_simple, head_complex, n_pairs, head_pairs;
-};
-
-struct TileCtxV2 {
-    int32_t b0, b1, nb, tbx, tby, st_lo;
-    uint32_t c_lo;
-    bool staged, stab_staged, cig_staged;
-};
-
-__device__ __forceinline__ void emit_pair_v2(const BasefcDev &P, StageV2 &S, int32_t j, int32_t m, int32_t need,
-                                             uint64_t umi, uint32_t col) {
-    if (m < need) return;
-    int slot = atomicAdd(&S.n_pairs, 1);
-    if (slot < V2_PAIRS) {
-        S.p_umi[slot] = umi;
-        S.p_j[slot] = (uint32_t)j;
-        S.p_col[slot] = col;
-    } else {                       // stage full (very deep feature overlap): insert right away
-        const FeatDesc fd = P.fdesc[j];
-        if (fd.cap) {
-            xg_e128 want;
-            want.a = umi;
-            want.b = (unsigned long long)col + 1ull;
-            xg_e128 *tbl = (xg_e128 *)(P.pool + fd.blk_off);
-            uint32_t s = set_home(umi, col, fd.cap);
-            if (set_insert_from(tbl, fd.cap, s, ld128_relaxed(&tbl[s]), want)) {
-                uint32_t *cursor = (uint32_t *)(tbl + fd.cap);
-                cursor[4 + atomicAdd(cursor, 1u)] = col;
-            }
-        }
-    }
-}
-
-// features overlapping [pos, end) -> include test -> pair stage.  cig == nullptr: simple read.
-__device__ __forceinline__ void lookup_and_emit_v2(const BasefcDev &P, StageV2 &S, const TileCtxV2 &T,
-                                                   int32_t pos, int32_t end, const uint32_t *cig, uint32_t n_ops,
-                                                   int32_t need, uint64_t umi, uint32_t col) {
-    // first boundary > pos (global index)
-    int32_t ub;
-    if (T.staged) {
-        int32_t lo = 0;
-        if (T.nb <= 8) {                       // few boundaries under the tile: branch-free count
-            for (int k = 0; k < T.nb; k++) lo += S.bnd[k] <= pos;
-        } else {
-            int32_t hi = T.nb;
-            while (lo < hi) {
-                int32_t mid = (lo + hi) >> 1;
-                if (S.bnd[mid] <= pos) lo = mid + 1; else hi = mid;
-            }
-        }
-        ub = T.tbx + lo;
-    } else {
-        int32_t lo = T.b0, hi = T.b1;
-        while (lo < hi) {
-            int32_t mid = (lo + hi) >> 1;
-            if (__ldg(&P.bnd[mid]) <= pos) lo = mid + 1; else hi = mid;
-        }
-        ub = lo;
-    }
-    // (1) features covering `pos`: stabbing list of the segment [bnd[ub-1], bnd[ub])
-    if (ub > T.b0) {
-        int32_t s0i, s1i;
-        if (T.staged && ub > T.tbx) {
-            s0i = S.stab_off[ub - 1 - T.tbx];
-            s1i = S.stab_off[ub - T.tbx];
-        } else {
-            s0i = __ldg(&P.stab_off[ub - 1]);
-            s1i = __ldg(&P.stab_off[ub]);
-        }
-        for (int32_t s = s0i; s < s1i; s++) {
-            const int4 f = (T.stab_staged && s >= T.st_lo) ? S.stab4[s - T.st_lo] : __ldg(&P.stab4[s]);
-            int32_t m;
-            if (!cig) {
-                const int32_t a = max(pos, f.y), b = min(end, f.z);
-                m = b > a ? b - a : 0;
-            } else {
-                m = included_len(cig, n_ops, pos, f.y, f.z);
-            }
-            emit_pair_v2(P, S, f.x, m, need, umi, col);
-        }
-    }
-    // (2) features beginning at a boundary inside (pos, end)
-    const int32_t kb_end = T.staged ? T.tby : T.b1;
-    for (int32_t kb = ub; kb < kb_end; kb++) {
-        const int32_t bv = T.staged ? S.bnd[kb - T.tbx] : __ldg(&P.bnd[kb]);
-        if (bv >= end) break;
-        const int32_t j1 = __ldg(&P.fb[kb + 1]);
-        for (int32_t j = __ldg(&P.fb[kb]); j < j1; j++) {
-            const int32_t e0 = __ldg(&P.sf_end[j]);
-            int32_t m;
-            if (!cig) {
-                const int32_t a = max(pos, bv), b = min(end, e0);
-                m = b > a ? b - a : 0;
-            } else {
-                m = included_len(cig, n_ops, pos, bv, e0);
-            }
-            emit_pair_v2(P, S, j, m, need, umi, col);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(256, 6) k_basefc_count_v2(const __grid_constant__ BasefcDev P) {
-    __shared__ StageV2 S;
-    const int t = P.tile0 + (int)(blockIdx.x >> 1);
-    const int half = blockIdx.x & 1;
-    const xg_tile tile = P.tiles[t];
-    const int32_t nrec = min(V2_REC, tile.n_rec - half * V2_REC);
-    if (nrec <= 0) return;
-    const int64_t rec0 = tile.rec_beg + (int64_t)half * V2_REC;
-    const xg_run run = P.runs[tile.run];
-    const int32_t gid = run.gid;
-    if (gid < 0 || gid >= P.n_gid) return;
-    if (P.sf_goff[gid] == P.sf_goff[gid + 1]) return;
-    const int2 tb = P.tile_bnd[t];
-    if (tb.x < 0) return;          // no feature under this tile's window: its records are never read
-    TileCtxV2 T;
-    T.b0 = P.bnd_goff[gid];
-    T.b1 = P.bnd_goff[gid + 1];
-    T.tbx = tb.x;
-    T.tby = tb.y;
-    T.nb = tb.y - tb.x;
-    T.staged = T.nb <= SB_MAX;
-    const int lane = threadIdx.x & 31;
-
-    // ---- the thread's records: independent, coalesced loads issued up front
-    int2 pe[2];
-    uint32_t fq[2], co[2];
-    ulonglong2 ky[2];
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        const int32_t k = threadIdx.x + r * 256;
-        const bool live = k < nrec;
-        const int64_t i = rec0 + (live ? k : 0);
-        pe[r] = __ldcs(&P.pos_end[i]);
-        fq[r] = __ldcs(&P.fmq[i]);
-        co[r] = __ldcs(&P.cig_off[i]);
-        ky[r] = __ldcs(&P.keys[i]);
-        if (!live) ky[r].y = XG_KEY_NONE;
-    }
-    // ---- stage the index slice under the tile window and this half's CIGAR words
-    const uint32_t c_first = __ldg(&P.cig_off[rec0]);
-    T.c_lo = c_first ? c_first - 1 : 0;
-    const uint32_t c_hi = __ldg(&P.cig_off[rec0 + nrec]);
-    T.cig_staged = c_hi - T.c_lo <= CIG_CAP;
-    T.st_lo = 0;
-    int32_t st_n = 0;
-    if (T.staged) {
-        T.st_lo = __ldg(&P.stab_off[tb.x]);
-        st_n = __ldg(&P.stab_off[tb.y]) - T.st_lo;
-        for (int k = threadIdx.x; k < T.nb; k += blockDim.x) S.bnd[k] = __ldg(&P.bnd[tb.x + k]);
-        for (int k = threadIdx.x; k <= T.nb; k += blockDim.x) S.stab_off[k] = __ldg(&P.stab_off[tb.x + k]);
-        if (st_n <= STAB_CAP)
-            for (int k = threadIdx.x; k < st_n; k += blockDim.x) S.stab4[k] = __ldg(&P.stab4[T.st_lo + k]);
-    }
-    T.stab_staged = T.staged && st_n <= STAB_CAP;
-    if (T.cig_staged)
-        for (uint32_t k = threadIdx.x; k < c_hi - T.c_lo; k += blockDim.x) S.cigar[k] = __ldg(&P.cigar[T.c_lo + k]);
-    if (threadIdx.x == 0) {
-        S.n_simple = S.n_complex = S.head_simple = S.head_complex = S.n_pairs = S.head_pairs = 0;
-    }
-    // ---- cell lookup: the home slots of both records are probed together
-    int32_t colv[2];
-    if (P.fp.use_cell_tag) {
-        ulonglong2 slot[2];
-        uint32_t hs[2];
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            hs[r] = (uint32_t)mix64(ky[r].x) & P.bc.mask;
-            slot[r] = __ldg(&P.bc.slots[hs[r]]);
-        }
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            int32_t c = -1;
-            if (ky[r].x != XG_KEY_NONE) {
-                ulonglong2 e = slot[r];
-                uint32_t s = hs[r];
-                while (true) {
-                    if (e.x == ky[r].x) {
-                        c = (int32_t)e.y;
-                        break;
-                    }
-                    if (e.x == XG_KEY_NONE) break;
-                    s = (s + 1) & P.bc.mask;
-                    e = __ldg(&P.bc.slots[s]);
-                }
-            }
-            colv[r] = c;
-        }
-    } else {
-        colv[0] = colv[1] = run.bam_idx;
-    }
-    __syncthreads();
-
-    // ---- stage 1: filters -> survivor queue (ballot-aggregated pushes)
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-        const uint64_t umi = ky[r].y;
-        const uint32_t ncw = fq[r] >> 24;
-        bool ok = umi != XG_KEY_NONE && umi != XG_KEY_EMPTY && read_passes_flags(P.fp, fq[r]) && colv[r] >= 0;
-        if (ok && ncw == 0 && pe[r].y - pe[r].x < P.fp.min_len) ok = false;      // simple: aligned length known
-        const bool simple = ok && ncw == 0, cplx = ok && ncw != 0;
-        const unsigned ms = __ballot_sync(0xffffffffu, simple), mc = __ballot_sync(0xffffffffu, cplx);
-        int bs = 0, bc = 0;
-        if (lane == 0) {
-            if (ms) bs = atomicAdd(&S.n_simple, __popc(ms));
-            if (mc) bc = atomicAdd(&S.n_complex, __popc(mc));
-        }
-        bs = __shfl_sync(0xffffffffu, bs, 0);
-        bc = __shfl_sync(0xffffffffu, bc, 0);
-        if (ok) {
-            const unsigned below = (1u << lane) - 1u;
-            const int q = simple ? bs + __popc(ms & below) : V2_REC - 1 - (bc + __popc(mc & below));
-            S.q_pos[q] = pe[r].x;
-            S.q_end[q] = pe[r].y;
-            S.q_co[q] = co[r];
-            S.q_colops[q] = (uint32_t)colv[r] | (ncw << 24);
-            S.q_umi[q] = umi;
-        }
-    }
-    __syncthreads();
-
-    // ---- stage 2: simple reads, one warp-load of 32 survivors at a time
-    const int n_simple = S.n_simple, n_complex = S.n_complex;
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&S.head_simple, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_simple) break;
-        const int q = base + lane;
-        if (q < n_simple) {
-            const int32_t pos = S.q_pos[q], end = S.q_end[q], aln = end - pos;
-            const int32_t need = P.incl_tab ? __ldg(&P.incl_tab[min(aln, P.incl_tab_len - 1)]) : P.incl_len;
-            lookup_and_emit_v2(P, S, T, pos, end, nullptr, 0, need, S.q_umi[q], S.q_colops[q] & 0xFFFFFFu);
-        }
-    }
-    // ---- stage 3: reads with a stored CIGAR
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&S.head_complex, 32);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_complex) break;
-        const int qi = base + lane;
-        if (qi < n_complex) {
-            const int q = V2_REC - 1 - qi;
-            const int32_t pos = S.q_pos[q], end = S.q_end[q];
-            uint32_t n_ops = S.q_colops[q] >> 24;
-            const uint32_t *cig = T.cig_staged ? &S.cigar[S.q_co[q] - T.c_lo] : P.cigar + S.q_co[q];
-            if (n_ops == 255) n_ops = cig[-1];
-            int32_t aln = 0;
-            for (uint32_t k = 0; k < n_ops; k++) {
-                const uint32_t w = cig[k];
-                if (cig_aligned(w & 15u)) aln += (int32_t)(w >> 4);
-            }
-            if (aln >= P.fp.min_len) {
-                const int32_t need = P.incl_tab ? __ldg(&P.incl_tab[min(aln, P.incl_tab_len - 1)]) : P.incl_len;
-                lookup_and_emit_v2(P, S, T, pos, end, cig, n_ops, need, S.q_umi[q], S.q_colops[q] & 0xFFFFFFu);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- stage 4: insert the staged pairs, 64 per warp-load (two in flight per lane)
-    const int np = P.ablate == 1 ? 0 : min(S.n_pairs, V2_PAIRS);
-    while (true) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&S.head_pairs, 64);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= np) break;
-        xg_e128 *tbl[2];
-        uint32_t cap[2], home[2];
-        xg_e128 cur[2];
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const int p = base + r * 32 + lane;
-            cap[r] = 0;
-            if (p < np) {
-                const FeatDesc fd = P.fdesc[S.p_j[p]];
-                cap[r] = fd.cap;
-                tbl[r] = (xg_e128 *)(P.pool + fd.blk_off);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const int p = base + r * 32 + lane;
-            if (cap[r]) {
-                home[r] = set_home(S.p_umi[p], S.p_col[p], cap[r]);
-                cur[r] = ld128_relaxed(tbl[r] + home[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const int p = base + r * 32 + lane;
-            bool is_new = false;
-            uint32_t col = 0;
-            if (cap[r]) {
-                xg_e128 want;
-                col = S.p_col[p];
-                want.a = S.p_umi[p];
-                want.b = (unsigned long long)col + 1ull;
-                is_new = set_insert_from(tbl[r], cap[r], home[r], cur[r], want);
-            }
-            log_append(tbl[r], cap[r], is_new, col);     // whole warp: uses match_any
-        }
-    }
 }
 
 // Zero the sets of the features that become active in this epoch.  The segments are laid
@@ -1386,9 +1063,6 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     //   finalize(e) waits count(e), count(e-1)
     bool overlap = pl.n_epochs > 1;
     if (const char *e = getenv("XG_OVERLAP")) overlap = overlap && atoi(e) != 0;
-    int count_version = 2;
-    if (const char *e = getenv("XG_COUNT_V")) count_version = atoi(e);
-    if (n_cols >= (1 << 24)) count_version = 1;      // v2 packs the column into 24 bits of a queue word
     if ((overlap || src) && !ctx->aux[0])
         for (auto &st : ctx->aux) XG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (src && !ctx->copy_stream) XG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -1450,10 +1124,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         cudaEventRecord(EV(1, e), st_c);
         if (t1 > t0 && m > 0) {
             P.tile0 = t0;
-            if (count_version == 2)
-                k_basefc_count_v2<<<2 * (t1 - t0), 256, 0, st_c>>>(P);
-            else
-                k_basefc_count<<<t1 - t0, 256, 0, st_c>>>(P);
+            k_basefc_count<<<t1 - t0, 256, 0, st_c>>>(P);
             launches++;
         }
         cudaEventRecord(EV(2, e), st_c);

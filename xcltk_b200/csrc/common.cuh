@@ -48,6 +48,7 @@ struct xg_ctx {
     std::vector<cudaEvent_t> ev_pool;     // per-epoch timing events
     std::string err;
     double timing[16] = {};
+    bool coo_rows = true;                  // results carry the row array (else CSR: row_ptr only)
     // growable named scratch buffers (avoid cudaMalloc/cudaFree on every call)
     struct Buf {
         void *p = nullptr;

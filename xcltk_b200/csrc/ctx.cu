@@ -66,6 +66,15 @@ void xg_destroy(xg_ctx *ctx) {
     delete ctx;
 }
 
+int xg_set_option(xg_ctx *ctx, const char *name, int64_t value) {
+    if (!ctx || !name) return XG_E_ARG;
+    if (std::string(name) == "coo_rows") {
+        ctx->coo_rows = value != 0;
+        return XG_OK;
+    }
+    return ctx->fail(XG_E_ARG, std::string("unknown option '") + name + "'");
+}
+
 const char *xg_last_error(xg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 void xg_last_timing(xg_ctx *ctx, double out[16]) {

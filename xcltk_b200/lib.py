@@ -100,6 +100,7 @@ SYMBOLS = {
     "xg_create": (C.c_int, [C.c_int32, C.POINTER(_P)]),
     "xg_destroy": (None, [_P]),
     "xg_last_error": (C.c_char_p, [_P]),
+    "xg_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "xg_upload_reads": (C.c_int, [_P, C.POINTER(Reads), C.POINTER(_P)]),
     "xg_map_reads": (C.c_int, [_P, C.POINTER(Reads), C.POINTER(_P)]),
     "xg_download_reads": (C.c_int, [_P, _P, C.POINTER(C.POINTER(Reads))]),
@@ -295,24 +296,54 @@ class _View(np.ndarray):
         self._owner = getattr(obj, "_owner", None)
 
 
+class LazyRows(object):
+    """Row indices of a CSR result, expanded from row_ptr on first use (np.asarray(rows),
+    rows[...], len(rows)); the library then ships col / val / row_ptr only."""
+
+    def __init__(self, row_ptr, nnz):
+        self._ptr, self._n, self._rows = row_ptr, nnz, None
+
+    def __len__(self):
+        return self._n
+
+    def __array__(self, dtype=None, copy=None):
+        if self._rows is None:
+            counts = np.diff(self._ptr)
+            self._rows = np.repeat(np.arange(len(counts), dtype=np.int32), counts)
+        return self._rows if dtype is None else self._rows.astype(dtype)
+
+    def __getitem__(self, k):
+        return np.asarray(self)[k]
+
+    def tolist(self):
+        return np.asarray(self).tolist()
+
+    def astype(self, dtype):
+        return np.asarray(self).astype(dtype)
+
+
 def coo_to_numpy(lib, pcoo, copy_below=1 << 16, ctx_obj=None):
     """(row, col, val, shape).  Large results are zero-copy views of the library's pinned
-    buffers (released when the last view dies); small ones are copied and freed at once."""
+    buffers (released when the last view dies); small ones are copied and freed at once.
+    With the context option coo_rows = 0 `row` is a LazyRows (expanded from row_ptr on use)."""
     m = pcoo.contents
     nnz = int(m.nnz)
     shape = (int(m.n_rows), int(m.n_cols))
-    views = [np_view(p, nnz, np.int32) for p in (m.row, m.col, m.val)]
+    has_rows = bool(m.row)
+    row_ptr = np_view(m.row_ptr, shape[0] + 1, np.int64).copy()
+    views = [np_view(p, nnz, np.int32) for p in ((m.row if has_rows else m.col), m.col, m.val)]
     if nnz <= copy_below:
         out = [v.copy() for v in views]
         lib.xg_coo_free(pcoo)
-        return out[0], out[1], out[2], shape
-    owner = _CooOwner(lib, pcoo, ctx_obj)
-    out = []
-    for v in views:
-        w = v.view(_View)
-        w._owner = owner
-        out.append(w)
-    return out[0], out[1], out[2], shape
+    else:
+        owner = _CooOwner(lib, pcoo, ctx_obj)
+        out = []
+        for v in views:
+            w = v.view(_View)
+            w._owner = owner
+            out.append(w)
+    row = out[0] if has_rows else LazyRows(row_ptr, nnz)
+    return row, out[1], out[2], shape
 
 
 class Context(object):
@@ -328,6 +359,7 @@ class Context(object):
                 self.lib.xg_destroy(self.h)
                 self.h = None
             raise XgError(rc, msg)
+        self.lib.xg_set_option(self.h, b"coo_rows", 0)      # CSR over PCIe; rows expanded lazily on the host
 
     def _check(self, rc):
         if rc != 0:

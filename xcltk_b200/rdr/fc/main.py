@@ -314,6 +314,7 @@ def fc_core(conf):
 
     regs = conf.reg_list
     row, col, val = count_features(conf)
+    row = np.asarray(row)            # CSR result: rows are expanded on the host
 
     # emit (rdr/fc/core.py:96-124): a feature gets an output row iff it has a non-zero
     # count or output_all_reg; rows are numbered over the emitted features, input order.
