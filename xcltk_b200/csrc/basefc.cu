@@ -118,89 +118,78 @@ int build_feat_index(xg_ctx *ctx, const xg_features *f, int32_t n_gid, FeatIndex
     return XG_OK;
 }
 
-// Per (feature, run): the tiles that can hold an overlapping read -- tiles of the feature's
-// contig with prefix-max(end) > beg and first_pos < end.  Their union over the runs of the
-// contig is the feature's lifetime [tlo, thi) in global tile numbering.
-struct Window {
-    int32_t j, lo_tile, hi_tile;   // sorted feature, tiles [lo_tile, hi_tile)
+// Per (feature, run of its contig): the tiles that can hold an overlapping read -- tiles with
+// prefix-max(end) > beg and first_pos < end (two binary searches over the tile index) --
+// tightened to records: from the first record of the first tile whose end > beg to the first
+// record of the last tile whose pos >= end.  One warp per (feature, run).  Outputs per feature:
+// candidate-read count (capacity of its set), first / last tile (its lifetime).
+struct WinJob {
+    int32_t j0, j1;          // sorted features [j0, j1) of the run's contig
+    int32_t t0, t1;          // tiles [t0, t1) of the run
+    int64_t warp0;           // first warp of the job (prefix of j1 - j0)
 };
+__global__ void __launch_bounds__(256) k_feature_windows(const WinJob *jobs, int32_t n_jobs, int64_t n_warps,
+                                                         const xg_tile *tiles, const int32_t *pmax,
+                                                         const int2 *pos_end, int32_t refine,
+                                                         const int32_t *sf_beg, const int32_t *sf_end,
+                                                         unsigned long long *cand, int32_t *tlo, int32_t *thi) {
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= n_warps) return;
+    int a = 0, b = n_jobs;                  // last job with warp0 <= w
+    while (b - a > 1) {
+        int mid = (a + b) >> 1;
+        if (jobs[mid].warp0 <= w) a = mid; else b = mid;
+    }
+    const WinJob job = jobs[a];
+    const int32_t j = job.j0 + (int32_t)(w - job.warp0);
+    const int32_t beg = sf_beg[j], end = sf_end[j];
+    int32_t lo = job.t0, hi = job.t1;
+    while (lo < hi) {                       // first tile with pmax > beg
+        int32_t mid = (lo + hi) >> 1;
+        if (pmax[mid] > beg) hi = mid; else lo = mid + 1;
+    }
+    const int32_t t_lo = lo;
+    hi = job.t1;
+    while (lo < hi) {                       // first tile with first_pos >= end
+        int32_t mid = (lo + hi) >> 1;
+        if (tiles[mid].first_pos >= end) hi = mid; else lo = mid + 1;
+    }
+    const int32_t t_hi = lo;
+    if (t_hi <= t_lo) return;
+    const xg_tile L = tiles[t_lo], H = tiles[t_hi - 1];
+    int64_t first = L.rec_beg, last = H.rec_beg + H.n_rec;
+    if (refine) {
+        first = L.rec_beg + L.n_rec;
+        for (int base = 0; base < L.n_rec; base += 32) {
+            int k = base + lane;
+            unsigned msk = __ballot_sync(0xffffffffu, k < L.n_rec && pos_end[L.rec_beg + k].y > beg);
+            if (msk) {
+                first = L.rec_beg + base + (__ffs(msk) - 1);
+                break;
+            }
+        }
+        for (int base = 0; base < H.n_rec; base += 32) {
+            int k = base + lane;
+            unsigned msk = __ballot_sync(0xffffffffu, k < H.n_rec && pos_end[H.rec_beg + k].x >= end);
+            if (msk) {
+                last = H.rec_beg + base + (__ffs(msk) - 1);
+                break;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (last > first) atomicAdd(&cand[j], (unsigned long long)(last - first));
+        atomicMin(&tlo[j], t_lo);
+        atomicMax(&thi[j], t_hi);
+    }
+}
 
 struct FeatCache {
     bool valid = false;
     uint64_t hash = 0;
     FeatIndexHost ix;
 };
-void feature_windows(const xg_dreads *rd, const FeatIndexHost &ix, std::vector<Window> &wins,
-                     std::vector<int32_t> &tlo, std::vector<int32_t> &thi) {
-    size_t m = ix.sf_beg.size();
-    tlo.assign(m, INT32_MAX);
-    thi.assign(m, -1);
-    size_t nt = rd->h_tiles.size();
-    std::vector<int32_t> pmax(nt);
-    std::vector<size_t> run_t0((size_t)rd->n_runs + 1, nt);
-    for (size_t t = 0; t < nt; t++) {
-        int32_t r = rd->h_tiles[t].run;
-        bool first = (t == 0) || rd->h_tiles[t - 1].run != r;
-        if (first) run_t0[(size_t)r] = t;
-        pmax[t] = first ? rd->h_tiles[t].max_end : std::max(pmax[t - 1], rd->h_tiles[t].max_end);
-    }
-    for (int32_t r = 0; r < rd->n_runs; r++) {
-        const xg_run &run = rd->h_runs[(size_t)r];
-        if (run.gid < 0 || run.gid >= ix.n_gid || run.rec_end == run.rec_beg) continue;
-        size_t t0 = run_t0[(size_t)r];
-        size_t t1 = t0 + (size_t)((run.rec_end - run.rec_beg + XG_TILE - 1) / XG_TILE);
-        for (int32_t j = ix.sf_goff[run.gid]; j < ix.sf_goff[run.gid + 1]; j++) {
-            int32_t beg = ix.sf_beg[(size_t)j], end = ix.sf_end[(size_t)j];
-            size_t a = t0, b = t1;
-            while (a < b) {            // lo: first tile with pmax > beg
-                size_t mid = (a + b) / 2;
-                if (pmax[mid] > beg) b = mid; else a = mid + 1;
-            }
-            size_t lo = a;
-            a = t0, b = t1;
-            while (a < b) {            // hi: first tile with first_pos >= end
-                size_t mid = (a + b) / 2;
-                if (rd->h_tiles[mid].first_pos >= end) b = mid; else a = mid + 1;
-            }
-            size_t hi = a;
-            if (hi > lo) {
-                wins.push_back(Window{j, (int32_t)lo, (int32_t)hi});
-                tlo[(size_t)j] = std::min(tlo[(size_t)j], (int32_t)lo);
-                thi[(size_t)j] = std::max(thi[(size_t)j], (int32_t)hi);
-            }
-        }
-    }
-}
-
-// Tighten a window to records: from the first record of tile lo whose end > beg to the first
-// record of tile hi-1 whose pos >= end.  One warp per window; adds the count to cand[j].
-__global__ void __launch_bounds__(256) k_window_cand(const Window *wins, int32_t n_win, const xg_tile *tiles,
-                                                     const int2 *pos_end, const int32_t *sf_beg,
-                                                     const int32_t *sf_end, unsigned long long *cand) {
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (w >= n_win) return;
-    const Window win = wins[w];
-    const int32_t beg = sf_beg[win.j], end = sf_end[win.j];
-    const xg_tile L = tiles[win.lo_tile], H = tiles[win.hi_tile - 1];
-    int64_t first = L.rec_beg + L.n_rec, last = H.rec_beg + H.n_rec;
-    for (int base = 0; base < L.n_rec; base += 32) {
-        int k = base + lane;
-        unsigned msk = __ballot_sync(0xffffffffu, k < L.n_rec && pos_end[L.rec_beg + k].y > beg);
-        if (msk) {
-            first = L.rec_beg + base + (__ffs(msk) - 1);
-            break;
-        }
-    }
-    for (int base = 0; base < H.n_rec; base += 32) {
-        int k = base + lane;
-        unsigned msk = __ballot_sync(0xffffffffu, k < H.n_rec && pos_end[H.rec_beg + k].x >= end);
-        if (msk) {
-            last = H.rec_beg + base + (__ffs(msk) - 1);
-            break;
-        }
-    }
-    if (lane == 0 && last > first) atomicAdd(&cand[win.j], (unsigned long long)(last - first));
-}
 
 // ---- epoch plan ------------------------------------------------------------------------
 // The read stream is cut into epochs of `epoch_tiles` tiles.  A feature owns a block of the
@@ -927,11 +916,6 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     const size_t m = ix.sf_beg.size();
     const double ms_index = ms_since(t_ph);
     t_ph = now();
-    std::vector<Window> wins;
-    std::vector<int32_t> tlo, thi;
-    feature_windows(rd, ix, wins, tlo, thi);
-    const double ms_windows = ms_since(t_ph);
-
     BasefcDev P;
     memset(&P, 0, sizeof(P));
     P.pos_end = rd->pos_end;
@@ -943,7 +927,6 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     P.tiles = rd->tiles;
     P.n_gid = n_gid;
     const int32_t *d_sf_row = nullptr;
-    const Window *d_wins = nullptr;
     const int32_t *d_sf_beg = nullptr;
     if (!index_cached) {
         std::vector<int4> stab4(ix.stab.size());
@@ -975,16 +958,41 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     P.stab_off = (const int32_t *)ctx->scratch["fx_stab_off"].p;
     P.stab4 = (const int4 *)ctx->scratch["fx_stab4"].p;
     P.fb = (const int32_t *)ctx->scratch["fx_fb"].p;
-    if ((rc = upload_vec(ctx, wins, "fx_wins", &d_wins))) return rc;
+    // feature windows on the device: one job per run whose contig has features
+    std::vector<WinJob> jobs;
+    int64_t n_warps = 0;
+    {
+        size_t t = 0;
+        const size_t nt = rd->h_tiles.size();
+        while (t < nt) {
+            const int32_t r = rd->h_tiles[t].run;
+            size_t e = t;
+            while (e < nt && rd->h_tiles[e].run == r) e++;
+            const int32_t g = rd->h_runs[(size_t)r].gid;
+            if (g >= 0 && g < n_gid && ix.sf_goff[(size_t)g + 1] > ix.sf_goff[(size_t)g]) {
+                jobs.push_back(WinJob{ix.sf_goff[(size_t)g], ix.sf_goff[(size_t)g + 1], (int32_t)t, (int32_t)e, n_warps});
+                n_warps += ix.sf_goff[(size_t)g + 1] - ix.sf_goff[(size_t)g];
+            }
+            t = e;
+        }
+    }
+    const WinJob *d_jobs = nullptr;
+    if ((rc = upload_vec(ctx, jobs, "fx_jobs", &d_jobs))) return rc;
     XG_GET(d_cand, unsigned long long, "fx_cand", m + 1);
+    XG_GET(d_tlo, int32_t, "fx_tlo", m + 1);
+    XG_GET(d_thi, int32_t, "fx_thi", m + 1);
     XG_GET(d_tile_bnd, int2, "fx_tile_bnd", rd->n_tiles + 1);
     P.tile_bnd = d_tile_bnd;
     cudaEventRecord(ctx->ev[0], ctx->stream);
     XG_CUDA(cudaMemsetAsync(d_cand, 0, sizeof(unsigned long long) * (m + 1), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(d_tlo, 0x7f, sizeof(int32_t) * (m + 1), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(d_thi, 0xff, sizeof(int32_t) * (m + 1), ctx->stream));
     std::vector<unsigned long long> cand(m, 0);
-    if (!wins.empty() && !src) {
-        k_window_cand<<<(unsigned)((wins.size() + 7) / 8), 256, 0, ctx->stream>>>(
-            d_wins, (int32_t)wins.size(), rd->tiles, rd->pos_end, d_sf_beg, P.sf_end, d_cand);
+    std::vector<int32_t> tlo(m, INT32_MAX), thi(m, -1);
+    if (n_warps > 0) {
+        k_feature_windows<<<(unsigned)((n_warps + 7) / 8), 256, 0, ctx->stream>>>(
+            d_jobs, (int32_t)jobs.size(), n_warps, rd->tiles, rd->tile_pmax, rd->pos_end, src ? 0 : 1, d_sf_beg,
+            P.sf_end, d_cand, d_tlo, d_thi);
         launches++;
     }
     if (rd->n_tiles > 0) {
@@ -993,15 +1001,13 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
                                                                        d_tile_bnd);
         launches++;
     }
-    if (m && !src)
-        XG_CUDA(cudaMemcpyAsync(cand.data(), d_cand, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost,
-                                ctx->stream));
+    if (m) {
+        XG_CUDA(cudaMemcpyAsync(cand.data(), d_cand, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        XG_CUDA(cudaMemcpyAsync(tlo.data(), d_tlo, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        XG_CUDA(cudaMemcpyAsync(thi.data(), d_thi, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (src)      // streaming: the records are not on the device yet; whole tiles bound the windows
-        for (const Window &w : wins) {
-            const xg_tile &L = rd->h_tiles[(size_t)w.lo_tile], &H = rd->h_tiles[(size_t)w.hi_tile - 1];
-            cand[(size_t)w.j] += (unsigned long long)(H.rec_beg + H.n_rec - L.rec_beg);
-        }
+    const double ms_windows = ms_since(t_ph);
 
     // ---- pool layout over epochs
     int32_t epoch_tiles = src ? 8192 : 65536;     // streaming: finer epochs = finer H2D / kernel overlap
@@ -1220,7 +1226,8 @@ extern "C" int xg_basefc_host(xg_ctx *ctx, const xg_reads *h, const xg_features 
     } else {
         cudaMemcpyAsync(d->runs, h->runs, (size_t)h->n_runs * sizeof(xg_run), cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(d->tiles, h->tiles, (size_t)h->n_tiles * sizeof(xg_tile), cudaMemcpyHostToDevice, ctx->stream);
-        rc = basefc_run(ctx, d, h, feats, cells, par, out);
+        rc = xg_make_tile_pmax(ctx, d);
+        if (!rc) rc = basefc_run(ctx, d, h, feats, cells, par, out);
     }
     cudaStreamSynchronize(ctx->stream);
     xg_dreads_free(ctx, d);

@@ -31,6 +31,7 @@ struct xg_dreads {
     uint32_t *seq = nullptr;
     xg_run *runs = nullptr;      // device
     xg_tile *tiles = nullptr;    // device
+    int32_t *tile_pmax = nullptr;   // device: per run, prefix max of tile.max_end (window planning)
     std::vector<xg_run> h_runs;  // host copies for the planners
     std::vector<xg_tile> h_tiles;
     double h2d_ms = 0;
@@ -262,3 +263,4 @@ __device__ __forceinline__ bool read_passes_flags(const FilterParams &f, uint32_
 }
 
 int xg_build_barcode_table(xg_ctx *ctx, const xg_barcodes *cells, BarcodeTable *out);
+int xg_make_tile_pmax(xg_ctx *ctx, xg_dreads *d);

@@ -1,4 +1,5 @@
 // ctx.cu -- context, host<->HBM transfers of read batches, small shared host helpers.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -94,6 +95,9 @@ void xg_dreads_free(xg_ctx *ctx, xg_dreads *d) {
         if (p) {
             if (d->pooled && ctx) ctx->dev_put(p); else cudaFree(p);
         }
+    if (d->tile_pmax) {
+        if (ctx) ctx->dev_put(d->tile_pmax); else cudaFree(d->tile_pmax);
+    }
     delete d;
 }
 
@@ -157,6 +161,11 @@ int xg_upload_reads(xg_ctx *ctx, const xg_reads *h, xg_dreads **out) {
     cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
     d->h2d_ms = ms;
     ctx->timing[3] = ms;
+    int rc = xg_make_tile_pmax(ctx, d);
+    if (rc) {
+        xg_dreads_free(ctx, d);
+        return rc;
+    }
     *out = d;
     return XG_OK;
 }
@@ -285,6 +294,22 @@ void xg_coo_free(xg_coo *m) {
 }
 
 }  // extern "C"
+
+// Prefix max (restarting at every run) of the tiles' max_end: with it "first tile whose records
+// can still reach position x" is a binary search.  Built once per batch from the host tile index.
+int xg_make_tile_pmax(xg_ctx *ctx, xg_dreads *d) {
+    size_t nt = d->h_tiles.size();
+    std::vector<int32_t> pm(nt);
+    for (size_t t = 0; t < nt; t++) {
+        bool first = (t == 0) || d->h_tiles[t - 1].run != d->h_tiles[t].run;
+        pm[t] = first ? d->h_tiles[t].max_end : std::max(pm[t - 1], d->h_tiles[t].max_end);
+    }
+    if (d->tile_pmax) ctx->dev_put(d->tile_pmax);
+    d->tile_pmax = (int32_t *)ctx->dev_get(nt * 4 + 16);
+    if (!d->tile_pmax) return ctx->fail(XG_E_CUDA, "out of device memory for the tile index");
+    if (nt) XG_CUDA(cudaMemcpy(d->tile_pmax, pm.data(), nt * 4, cudaMemcpyHostToDevice));
+    return XG_OK;
+}
 
 // Build the open-addressing cell-barcode table on the host and upload it.
 // Replaces the dict lookup `smp in self.cell_cnt` (rdr/fc/mcount.py:119-127).

@@ -462,6 +462,13 @@ extern "C" int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *sp, xg_dreads 
     if (e != cudaSuccess) return fail_free(XG_E_CUDA, std::string("synth fill: ") + cudaGetErrorString(e));
     d->max_aln_len = h_max[0];
     d->max_span = h_max[1];
+    {
+        int rc = xg_make_tile_pmax(ctx, d);
+        if (rc) {
+            xg_dreads_free(ctx, d);
+            return rc;
+        }
+    }
     d->bytes = N * 32 + n_cig * 4 + d->n_seq_words * 4 + (sp->want_seq ? N * 4 : 0);
 
     // barcode keys in column order = sorted barcode strings (rdr/fc/main.py:346)
