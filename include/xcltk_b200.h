@@ -123,6 +123,15 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
 void xg_reads_free(xg_reads *r);
 const char *xg_host_last_error(void);
 
+/* Matrix-Market text of a CSR result, byte-identical to merge_mtx (rdr/fc/utils.py:54-94):
+ * header, "%%", "nrow\tncol\tnnz", then 1-based "row\tcol\tval" lines.  row_ptr spans all
+ * n_rows_in input rows; out_row[r] = 1-based output row of input row r, 0 = not emitted (the
+ * row must then be empty) -- the renumbering over emitted features of fc_features' emit loop
+ * (rdr/fc/core.py:109-124).  Multi-threaded formatting, ordered write.                     */
+int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *row_ptr, const int32_t *out_row,
+                 int32_t n_rows_out, int32_t n_cols, const int32_t *col, const int32_t *val,
+                 int32_t n_threads);
+
 /* ---- device side --------------------------------------------------------------------- */
 typedef struct xg_ctx xg_ctx;
 typedef struct xg_dreads xg_dreads;      /* read records resident in HBM */

@@ -137,5 +137,16 @@ def test_baf_refuses_local_phasing_and_empty_region_list(tmp_path):
 
 def test_write_mtx_format(tmp_path):
     p = str(tmp_path / "m.mtx")
-    engine.write_mtx(p, 5, 2, np.array([1, 2, 2]), np.array([1, 1, 2]), np.array([1, 2, 1]))
-    assert open(p).read() == "%%MatrixMarket matrix coordinate integer general\n%%\n5\t2\t3\n1\t1\t1\n2\t1\t2\n2\t2\t1\n"
+    emitted = np.array([True, True, False, True, True])           # input row 2 is not emitted
+    engine.write_mtx(p, 5, np.array([0, 1, 1, 4]), np.array([0, 0, 1, 6]), np.array([1, 2, 1, 123456]), emitted, 7, 3)
+    assert open(p).read() == ("%%MatrixMarket matrix coordinate integer general\n%%\n4\t7\t4\n"
+                              "1\t1\t1\n2\t1\t2\n2\t2\t1\n4\t7\t123456\n")
+    engine.write_mtx(p, 3, np.zeros(0, int), np.zeros(0, int), np.zeros(0, int), np.array([True, False, True]), 2)
+    assert open(p).read() == "%%MatrixMarket matrix coordinate integer general\n%%\n2\t2\t0\n"
+    rng = np.random.RandomState(1)                                # many slabs / threads == python formatting
+    n, rows = 3000000, 5000
+    row = np.sort(rng.randint(0, rows, size=n))
+    col, val = rng.randint(0, 99999, size=n), rng.randint(1, 2 ** 31 - 1, size=n)
+    engine.write_mtx(p, rows, row, col, val, np.ones(rows, dtype=bool), 99999, 5)
+    body = open(p).read().split("\n", 3)[3]
+    assert body == "".join("%d\t%d\t%d\n" % t for t in zip((row + 1).tolist(), (col + 1).tolist(), val.tolist()))

@@ -296,13 +296,11 @@ def afc_core(conf):
     has[np.asarray(dp[0])] = True
     has[np.asarray(oth[0])] = True
     emitted = np.ones(n_reg, dtype=bool) if conf.output_all_reg else has
-    new_row = np.cumsum(emitted)
     with open(conf.out_region_fn, "w") as fp:
         fp.write("".join("%s\t%d\t%d\t%s\n" % (r.chrom, r.start, r.end - 1, r.name)
                          for r, e in zip(regs, emitted) if e))
-    n_out = int(emitted.sum())
     for fn, (row, col, val, _shape) in ((conf.out_ad_fn, ad), (conf.out_dp_fn, dp), (conf.out_oth_fn, oth)):
-        engine.write_mtx(fn, n_out, len(conf.samples), new_row[np.asarray(row)], col + 1, val)
+        engine.write_mtx(fn, n_reg, row, col, val, emitted, len(conf.samples), engine.n_decode_threads(conf.nproc))
 
 
 def afc_run(conf):

@@ -265,7 +265,7 @@ __global__ void k_baf_region_masks(BafRegDev P, const int64_t *reg_log_off, int3
     uint32_t ca = P.pr_colal[p], snp = P.pr_snp[p];
     uint32_t code = (ca >> 24) & 7u;
     if (!(ca & 0x80000000u) || code == CODE_NONE || !P.keep[snp]) return;
-    uint32_t bit = 1u << P.hap_of[(size_t)snp * 8 + code];     // 1 ref-hap, 2 alt-hap, 4 other
+    uint32_t bit = 1u << min((uint32_t)P.hap_of[(size_t)snp * 8 + code], 2u);     // 1 ref-hap, 2 alt-hap, 4 other
     uint32_t col = ca & 0xFFFFFFu;
     uint64_t umi = P.pr_umi[p];
     for (int64_t k = P.snp_reg_ptr[snp]; k < P.snp_reg_ptr[snp + 1]; k++) {
@@ -656,22 +656,48 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
     for (double &t : ctx->timing) t = 0;
     int launches = 0;
     const int32_t n_cols = st->n_cols, n_snps = st->n_snps;
-    // invert region -> SNP lists
-    std::vector<int64_t> sr_ptr((size_t)n_snps + 1, 0);
-    int64_t n_mem = reg_ptr[n_regions];
-    for (int64_t k = 0; k < n_mem; k++) {
-        if (reg_snp[k] < 0 || reg_snp[k] >= n_snps) return ctx->fail(XG_E_ARG, "reg_snp out of range");
-        sr_ptr[(size_t)reg_snp[k] + 1]++;
+    // invert region -> SNP lists (cached on the device while the caller passes the same lists)
+    const int64_t n_mem = reg_ptr[n_regions];
+    uint64_t sh = 1469598103934665603ull;
+    auto mixh = [&](const void *p, size_t n) {
+        const uint8_t *q = (const uint8_t *)p;
+        size_t k = 0;
+        for (; k + 8 <= n; k += 8) {
+            uint64_t wv;
+            memcpy(&wv, q + k, 8);
+            sh = (sh ^ wv) * 1099511628211ull;
+            sh ^= sh >> 29;
+        }
+        for (; k < n; k++) sh = (sh ^ q[k]) * 1099511628211ull;
+    };
+    mixh(&n_snps, sizeof n_snps);
+    mixh(&n_regions, sizeof n_regions);
+    mixh(reg_ptr, sizeof(int64_t) * ((size_t)n_regions + 1));
+    mixh(reg_snp, sizeof(int32_t) * (size_t)n_mem);
+    const bool sr_cached = ctx->bf_sr_valid && ctx->bf_sr_hash == sh;
+    if (!sr_cached) {
+        ctx->bf_sr_valid = false;
+        std::vector<int64_t> sr_ptr((size_t)n_snps + 1, 0);
+        for (int64_t k = 0; k < n_mem; k++) {
+            if (reg_snp[k] < 0 || reg_snp[k] >= n_snps) return ctx->fail(XG_E_ARG, "reg_snp out of range");
+            sr_ptr[(size_t)reg_snp[k] + 1]++;
+        }
+        for (int32_t s2 = 0; s2 < n_snps; s2++) sr_ptr[(size_t)s2 + 1] += sr_ptr[(size_t)s2];
+        std::vector<int32_t> sr((size_t)n_mem);
+        {
+            std::vector<int64_t> cur(sr_ptr.begin(), sr_ptr.end() - 1);
+            for (int32_t r = 0; r < n_regions; r++)
+                for (int64_t k = reg_ptr[r]; k < reg_ptr[r + 1]; k++) sr[(size_t)cur[(size_t)reg_snp[k]]++] = r;
+        }
+        const int64_t *d64 = nullptr;
+        const int32_t *d32 = nullptr;
+        int rc0;
+        if ((rc0 = upload_arr(ctx, sr_ptr.data(), sr_ptr.size(), "bf_sr_ptr", &d64))) return rc0;
+        if ((rc0 = upload_arr(ctx, sr.data(), sr.size(), "bf_sr", &d32))) return rc0;
+        XG_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->bf_sr_hash = sh;
+        ctx->bf_sr_valid = true;
     }
-    for (int32_t s = 0; s < n_snps; s++) sr_ptr[(size_t)s + 1] += sr_ptr[(size_t)s];
-    std::vector<int32_t> sr((size_t)n_mem);
-    {
-        std::vector<int64_t> cur(sr_ptr.begin(), sr_ptr.end() - 1);
-        for (int32_t r = 0; r < n_regions; r++)
-            for (int64_t k = reg_ptr[r]; k < reg_ptr[r + 1]; k++) sr[(size_t)cur[(size_t)reg_snp[k]]++] = r;
-    }
-    for (size_t k = 0; k < (size_t)n_snps * 8; k++)
-        if (hap_of[k] > 2) return ctx->fail(XG_E_ARG, "hap_of entries must be 0, 1 or 2");
 
     BafRegDev R;
     memset(&R, 0, sizeof(R));
@@ -680,8 +706,8 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
     R.pr_colal = st->pr_colal;
     R.pr_umi = st->pr_umi;
     int rc;
-    if ((rc = upload_arr(ctx, sr_ptr.data(), sr_ptr.size(), "bf_sr_ptr", &R.snp_reg_ptr))) return rc;
-    if ((rc = upload_arr(ctx, sr.data(), sr.size(), "bf_sr", &R.snp_reg))) return rc;
+    R.snp_reg_ptr = (const int64_t *)ctx->scratch["bf_sr_ptr"].p;
+    R.snp_reg = (const int32_t *)ctx->scratch["bf_sr"].p;
     if ((rc = upload_arr(ctx, hap_of, (size_t)n_snps * 8, "bf_hap_of", &R.hap_of))) return rc;
     if ((rc = upload_arr(ctx, keep, (size_t)n_snps, "bf_keep", &R.keep))) return rc;
     XG_GET(reg_cnt, int32_t, "bf_reg_cnt", n_regions + 1);

@@ -147,6 +147,8 @@ struct xg_ctx {
     bool bf_snp_valid = false;
     uint64_t bf_snp_hash = 0;
     int64_t bf_snp_sorted = 0;
+    bool bf_sr_valid = false;              // ... and of the inverted region -> SNP lists of xg_baf_count
+    uint64_t bf_sr_hash = 0;
     // cache of the last interval index built by xg_basefc (owned by basefc.cu)
     void *fx_cache = nullptr;
     void (*fx_cache_free)(void *) = nullptr;

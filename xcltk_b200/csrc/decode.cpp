@@ -620,3 +620,85 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
 }
 
 }  // extern "C"
+
+// ---- Matrix-Market writer ---------------------------------------------------------------
+// Text exactly as merge_mtx produces it (xcltk/rdr/fc/utils.py:54-94 == baf/fc/utils.py:204-245):
+//   "%%MatrixMarket matrix coordinate integer general\n%%\n<nrow>\t<ncol>\t<nnz>\n" then one
+//   "<row>\t<col>\t<val>\n" per non-zero, 1-based, rows renumbered over the EMITTED features.
+// Input is the CSR result of the counting call over all input rows; out_row[r] is the 1-based
+// output row of input row r (0 = row not emitted; such a row must be empty).  Rows are
+// formatted by a pool of threads in slabs and written in order.
+namespace {
+inline char *put_int(char *p, uint32_t v) {
+    char tmp[12];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+}  // namespace
+
+extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *row_ptr, const int32_t *out_row,
+                            int32_t n_rows_out, int32_t n_cols, const int32_t *col, const int32_t *val,
+                            int32_t n_threads) {
+    if (!path || !row_ptr || !out_row || n_rows_in < 0) return fail(XG_E_ARG, "xg_write_mtx: bad argument");
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads <= 0) n_threads = 1;
+    int64_t nnz = 0;
+    for (int32_t r = 0; r < n_rows_in; r++) {
+        int64_t c = row_ptr[r + 1] - row_ptr[r];
+        if (c && out_row[r] <= 0) return fail(XG_E_ARG, "xg_write_mtx: non-empty row without an output row");
+        nnz += c;
+    }
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return fail(XG_E_IO, std::string("cannot write '") + path + "'");
+    fprintf(fp, "%%%%MatrixMarket matrix coordinate integer general\n%%%%\n%d\t%d\t%lld\n", n_rows_out, n_cols,
+            (long long)nnz);
+    // slabs of consecutive rows holding about `slab` non-zeros each
+    const int64_t slab = 1 << 21;
+    std::vector<int32_t> cut{0};
+    {
+        int64_t acc = 0;
+        for (int32_t r = 0; r < n_rows_in; r++) {
+            acc += row_ptr[r + 1] - row_ptr[r];
+            if (acc >= slab) {
+                cut.push_back(r + 1);
+                acc = 0;
+            }
+        }
+        if (cut.back() != n_rows_in) cut.push_back(n_rows_in);
+    }
+    const size_t n_slabs = cut.size() - 1;
+    bool ok = true;
+    for (size_t s0 = 0; s0 < n_slabs && ok; s0 += (size_t)n_threads) {
+        const size_t s1 = std::min(n_slabs, s0 + (size_t)n_threads);
+        std::vector<std::vector<char>> bufs(s1 - s0);
+        std::vector<std::thread> th;
+        for (size_t s = s0; s < s1; s++)
+            th.emplace_back([&, s] {
+                const int32_t r0 = cut[s], r1 = cut[s + 1];
+                std::vector<char> &b = bufs[s - s0];
+                b.resize((size_t)(row_ptr[r1] - row_ptr[r0]) * 36 + 16);
+                char *p = b.data();
+                for (int32_t r = r0; r < r1; r++)
+                    for (int64_t k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+                        p = put_int(p, (uint32_t)out_row[r]);
+                        *p++ = '\t';
+                        p = put_int(p, (uint32_t)col[k] + 1u);
+                        *p++ = '\t';
+                        p = put_int(p, (uint32_t)val[k]);
+                        *p++ = '\n';
+                    }
+                b.resize((size_t)(p - b.data()));
+            });
+        for (auto &t : th) t.join();
+        for (auto &b : bufs)
+            if (!b.empty() && fwrite(b.data(), 1, b.size(), fp) != b.size()) ok = false;
+    }
+    if (fclose(fp) != 0) ok = false;
+    if (!ok) return fail(XG_E_IO, std::string("short write on '") + path + "'");
+    return XG_OK;
+}

@@ -147,16 +147,16 @@ def make_params(conf, max_aln_len, with_include):
                          conf.no_orphan, conf.use_barcodes(), conf.use_umi(), tab, incl_len)
 
 
-def write_mtx(path, n_rows, n_cols, row1, col1, val):
-    """MatrixMarket text exactly as merge_mtx writes it (rdr/fc/utils.py:65-67,80-86):
-    header, `%%`, `nrow\\tncol\\tnnz`, then 1-based `row\\tcol\\tval` lines."""
-    with open(path, "w") as fp:
-        fp.write("%%MatrixMarket matrix coordinate integer general\n%%\n")
-        fp.write("%d\t%d\t%d\n" % (n_rows, n_cols, len(val)))
-        step = 1 << 20
-        for s in range(0, len(val), step):
-            blk = np.stack([row1[s:s + step], col1[s:s + step], val[s:s + step]], axis=1)
-            fp.write("".join("%d\t%d\t%d\n" % (a, b, c) for a, b, c in blk.tolist()))
+def write_mtx(path, n_rows_in, row, col, val, emitted, n_cols, n_threads=0):
+    """MatrixMarket text exactly as merge_mtx writes it (rdr/fc/utils.py:65-67,80-86): header,
+    `%%`, `nrow\tncol\tnnz`, then 1-based `row\tcol\tval` lines with the rows renumbered over
+    the emitted features.  (row, col, val): 0-based, sorted by (row, col); emitted: bool per
+    input row.  Formatting is done by the library's multi-threaded writer."""
+    row = np.asarray(row)
+    counts = np.bincount(row, minlength=n_rows_in) if len(row) else np.zeros(n_rows_in, dtype=np.int64)
+    row_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
+    lib.write_mtx(path, row_ptr, out_row, int(np.count_nonzero(emitted)), n_cols, col, val, n_threads)
 
 
 def n_decode_threads(nproc):

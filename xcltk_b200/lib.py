@@ -97,6 +97,8 @@ SYMBOLS = {
                                  C.POINTER(C.POINTER(Reads))]),
     "xg_reads_free": (None, [C.POINTER(Reads)]),
     "xg_host_last_error": (C.c_char_p, []),
+    "xg_write_mtx": (C.c_int, [C.c_char_p, C.c_int32, c_i64p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p,
+                               C.c_int32]),
     "xg_create": (C.c_int, [C.c_int32, C.POINTER(_P)]),
     "xg_destroy": (None, [_P]),
     "xg_last_error": (C.c_char_p, [_P]),
@@ -273,6 +275,22 @@ def decode_bams(paths, tid_maps, cell_tag, umi_tag, want_seq, keyspace, n_thread
     if rc != 0:
         raise XgError(rc, lib.xg_host_last_error().decode())
     return HostReads(out)
+
+
+def write_mtx(path, row_ptr, out_row, n_rows_out, n_cols, col, val, n_threads=0):
+    """CSR (all input rows) -> MatrixMarket text; out_row[r] = 1-based output row or 0."""
+    lib = load()
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    out_row = np.ascontiguousarray(out_row, dtype=np.int32)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.int32)
+    if len(col) == 0:
+        col = np.zeros(1, dtype=np.int32)
+        val = np.zeros(1, dtype=np.int32)
+    rc = lib.xg_write_mtx(path.encode(), len(row_ptr) - 1, as_ptr(row_ptr, c_i64p), as_ptr(out_row, c_i32p),
+                          int(n_rows_out), int(n_cols), as_ptr(col, c_i32p), as_ptr(val, c_i32p), n_threads)
+    if rc != 0:
+        raise XgError(rc, lib.xg_host_last_error().decode())
 
 
 class _CooOwner(object):

@@ -322,12 +322,11 @@ def fc_core(conf):
     has = np.zeros(n_reg, dtype=bool)
     has[row] = True
     emitted = np.ones(n_reg, dtype=bool) if conf.output_all_reg else has
-    new_row = np.cumsum(emitted)            # 1-based output row of each emitted feature
     with open(conf.out_region_fn, "w") as fp:
         fp.write("".join("%s\t%d\t%d\t%s\n" % (r.chrom, r.start, r.end - 1, r.get_id())
                          for r, e in zip(regs, emitted) if e))
-    engine.write_mtx(conf.out_mtx_fn, int(emitted.sum()), len(conf.samples),
-                     new_row[row], col + 1, val)
+    engine.write_mtx(conf.out_mtx_fn, n_reg, row, col, val, emitted, len(conf.samples),
+                     engine.n_decode_threads(conf.nproc))
     info("[GPU] %d reads counted in %.2f ms of kernels." % (
         conf.last_stats["n_reads"], conf.last_timing[0]))
 
