@@ -162,7 +162,7 @@ class Batch(object):
         w4 = time.perf_counter()
         return dict(nnz=len(val), checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w3 - w2), 1e3 * (w4 - w3)],
                     launches=launches, t_fc=t_fc, t_pileup=t_p, t_count=t_c,
-                    out_bytes=12 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])))
+                    out_bytes=8 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])))
 
     def make_host(self):
         self.h_fc = self.fc.dreads.download()         # pinned host record arrays
@@ -180,7 +180,8 @@ class Batch(object):
         st.close()
         d_bf.close()
         return dict(h2d=h2d_fc + 8 * self.h_baf.n + 72 * int(self.ctx.timing_pairs),
-                    d2h=12 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])) + totals.nbytes)
+                    d2h=8 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])) + totals.nbytes +
+                    8 * (len(fc.gid) + 3 * (len(bf.reg_ptr) - 1) + 4))       # CSR: col + val + row_ptr
 
 
 def cpu_sample(ctx, args, n_sample, n_threads):
