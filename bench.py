@@ -316,13 +316,36 @@ def main():
         cpu = {"value": args.cpu_sample / t, "unit": "reads/s", "cores": os.cpu_count() or 1, "kind": "port",
                "sample": "basefc on %d reads of the C3 generator with the C oracle, %.1f s" % (args.cpu_sample, t)}
 
+    decode = None
+    if rank == 0 and not args.no_cpu:
+        # host BGZF/BAM decode throughput (the stage before the path) on a bounded sample
+        try:
+            import tempfile
+            from xcltk_b200 import lib, synth
+            n_dec = 2000000
+            with tempfile.TemporaryDirectory() as td:
+                bam = os.path.join(td, "s.bam")
+                synth.write_fast_bam(bam, n_dec, [("chr%d" % c, 100000000) for c in range(1, 6)], 1000, seed=5,
+                                     threads=os.cpu_count() or 1)
+                ks = lib.KeySpace()
+                t = time.perf_counter()
+                hr = lib.decode_bams([bam], [np.arange(5, dtype=np.int32)], "CB", "UB", False, ks, os.cpu_count() or 1)
+                dt_dec = time.perf_counter() - t
+                decode = {"reads_per_s": hr.n / dt_dec, "threads": os.cpu_count() or 1, "sample_reads": hr.n,
+                          "bam_bytes": os.path.getsize(bam),
+                          "note": "xg_decode_bams on a %d-read synthetic BAM; at this rate decoding the C3 batch "
+                                  "takes %.0f s -- file-to-matrix time is decode-bound" % (hr.n, args.reads / (hr.n / dt_dec))}
+                hr.close()
+        except Exception as ex:
+            decode = {"error": str(ex)[:200]}
+
     if rank == 0:
         line = {"metric": "reads/sec counted (basefc + baf fc)", "value": value, "unit": "reads/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64 keys / i32 counts", "data": "synthetic", "config": config,
                 "e2e": e2e, "gpu_launches": int(sum(i["launches"] for i in infos)), "clocks": clocks,
-                "roofline": roofline, "cpu_baseline": cpu,
+                "roofline": roofline, "cpu_baseline": cpu, "host_decode": decode,
                 "detail": {"basefc_device_ms": float(np.mean([i["t_fc"][0] for i in infos])),
                            "basefc_epoch_span_ms": float(np.mean([i["t_fc"][3] for i in infos])),
                            "basefc_count_kernel_ms": t_cnt_ms,

@@ -11,9 +11,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -73,7 +75,22 @@ struct BgzfBlock {
     uint64_t uoff;    // offset in the uncompressed stream
 };
 
-int read_file(const char *path, std::vector<uint8_t> &buf) {
+// Byte buffer without the value-initialisation of std::vector::resize (GBs of memset).
+struct Bytes {
+    std::unique_ptr<uint8_t[]> p;
+    size_t n = 0;
+    void resize(size_t m) {
+        p.reset(new uint8_t[m ? m : 1]);
+        n = m;
+    }
+    size_t size() const { return n; }
+    uint8_t *data() { return p.get(); }
+    const uint8_t *data() const { return p.get(); }
+    uint8_t &operator[](size_t i) { return p[i]; }
+    const uint8_t &operator[](size_t i) const { return p[i]; }
+};
+
+int read_file(const char *path, Bytes &buf) {
     FILE *fp = fopen(path, "rb");
     if (!fp) return fail(XG_E_IO, std::string("cannot open '") + path + "'");
     fseek(fp, 0, SEEK_END);
@@ -87,7 +104,7 @@ int read_file(const char *path, std::vector<uint8_t> &buf) {
 }
 
 // Walk the BGZF block headers (RFC 1952 member with a 'BC' extra subfield, SAMv1 4.1).
-int scan_bgzf(const std::vector<uint8_t> &f, std::vector<BgzfBlock> &blocks, const char *path,
+int scan_bgzf(const Bytes &f, std::vector<BgzfBlock> &blocks, const char *path,
               int64_t max_blocks = -1) {
     uint64_t off = 0, uoff = 0, n = f.size();
     while (off < n) {
@@ -120,8 +137,7 @@ int scan_bgzf(const std::vector<uint8_t> &f, std::vector<BgzfBlock> &blocks, con
     return XG_OK;
 }
 
-int inflate_blocks(const std::vector<uint8_t> &f, const std::vector<BgzfBlock> &blocks,
-                   std::vector<uint8_t> &out, int n_threads) {
+int inflate_blocks(const Bytes &f, const std::vector<BgzfBlock> &blocks, Bytes &out, int n_threads) {
     uint64_t total = blocks.empty() ? 0 : blocks.back().uoff + blocks.back().isize;
     out.resize(total);
     std::atomic<int> bad(0);
@@ -158,7 +174,7 @@ struct Header {
     uint64_t end_off = 0;   // first record
 };
 
-int parse_header(const std::vector<uint8_t> &u, Header &h, const char *path) {
+int parse_header(const Bytes &u, Header &h, const char *path) {
     uint64_t n = u.size();
     if (n < 12 || memcmp(u.data(), "BAM\1", 4) != 0)
         return fail(XG_E_IO, std::string("'") + path + "' is not a BAM file (bad magic)");
@@ -182,7 +198,7 @@ int parse_header(const std::vector<uint8_t> &u, Header &h, const char *path) {
 
 // One BAM, inflated, with the offsets of the records we keep.
 struct Bam {
-    std::vector<uint8_t> u;
+    Bytes u;
     Header h;
     std::vector<uint64_t> rec;      // offset of block_size of each kept record
     struct Run {
@@ -335,7 +351,7 @@ int64_t xg_key_decode(xg_keyspace *ks, uint64_t key, char *buf, int64_t cap) {
 int64_t xg_keyspace_n_interned(xg_keyspace *ks) { return ks->n_interned(); }
 
 int xg_bam_header_read(const char *path, xg_bam_header **out) {
-    std::vector<uint8_t> f;
+    Bytes f;
     int rc = read_file(path, f);
     if (rc) return rc;
     // The header may span several blocks: inflate blocks until it parses.
@@ -345,7 +361,7 @@ int xg_bam_header_read(const char *path, xg_bam_header **out) {
     size_t nb = 1;
     while (true) {
         std::vector<BgzfBlock> part(blocks.begin(), blocks.begin() + std::min(nb, blocks.size()));
-        std::vector<uint8_t> u;
+        Bytes u;
         rc = inflate_blocks(f, part, u, 1);
         if (rc) return rc;
         Header h;
@@ -385,19 +401,31 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
     if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
     if (n_threads <= 0) n_threads = 1;
 
+    const bool timing = getenv("XG_DECODE_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tprev = tnow();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        auto t = tnow();
+        fprintf(stderr, "[decode] %-10s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - tprev).count());
+        tprev = t;
+    };
     std::vector<Bam> bams((size_t)n_bams);
     int64_t n_total = 0, n_seen = 0;
     for (int32_t b = 0; b < n_bams; b++) {
         Bam &bm = bams[b];
         {
-            std::vector<uint8_t> f;
+            Bytes f;
             int rc = read_file(paths[b], f);
             if (rc) return rc;
+            lap("read");
             std::vector<BgzfBlock> blocks;
             rc = scan_bgzf(f, blocks, paths[b]);
             if (rc) return rc;
+            lap("scan");
             rc = inflate_blocks(f, blocks, bm.u, n_threads);
             if (rc) return rc;
+            lap("inflate");
         }
         int rc = parse_header(bm.u, bm.h, paths[b]);
         if (rc) return rc;
@@ -437,6 +465,7 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
             off += 4 + bs;
         }
         if (off != n) return fail(XG_E_FORMAT, std::string("trailing bytes in '") + paths[b] + "'");
+        lap("walk");
         n_total += (int64_t)bm.rec.size();
         n_seen += bm.n_seen;
     }
@@ -477,6 +506,7 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
             max_span = std::max(max_span, parts[b][t].max_span);
         }
     }
+    lap("passA");
     if (cig_total >= (1LL << 32) || seq_total >= (1LL << 32))
         return fail(XG_E_LIMIT, "batch too large for 32-bit stream offsets; decode fewer reads per batch");
 
@@ -508,6 +538,7 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
         return fail(XG_E_NOMEM, "out of host memory");
     }
 
+    lap("alloc");
     // pass B: fill
     for (int32_t b = 0; b < n_bams; b++) {
         Bam &bm = bams[b];
@@ -566,6 +597,7 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
     }
 
     cig_off[n_total] = (uint32_t)cig_total;    // sentinel: end of the last read's words
+    lap("passB");
 
     // runs + tile index
     int32_t ri = 0;
@@ -597,6 +629,7 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
         }
     });
 
+    lap("tiles");
     xg_reads &o = own->r;
     o.n_reads = n_total;
     o.n_cigar = cig_total;
