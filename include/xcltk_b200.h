@@ -32,6 +32,7 @@ extern "C" {
 #define XG_E_NOMEM (-4)
 #define XG_E_CUDA (-5)    /* CUDA error or no device: the product path has no CPU fallback */
 #define XG_E_LIMIT (-6)   /* an internal capacity (32-bit offsets ...) would overflow */
+#define XG_E_UNSUPPORTED (-7) /* xg_decode_bams_device: file layout / keys need the host decoder */
 
 /* ---- string keys -------------------------------------------------------------------
  * Cell barcodes, UMIs and query names are compared by exact string equality in the
@@ -150,10 +151,27 @@ int xg_upload_reads(xg_ctx *ctx, const xg_reads *host, xg_dreads **out);
  * The pileup touches flag / keys / CIGAR / sequence of the reads that cover a SNP only, so
  * ~8 B per read cross PCIe instead of ~84 B.  XG_E_ARG if the arrays are not pinned.           */
 int xg_map_reads(xg_ctx *ctx, const xg_reads *host, xg_dreads **out);
+/* Device decoder: BGZF inflate + BAM record parse on the GPU; the compressed files cross PCIe
+ * once and the batch is left in HBM, array for array what xg_decode_bams + xg_upload_reads
+ * produce.  Replaces pysam.AlignmentFile + fetch() (xcltk/rdr/fc/core.py:75,100;
+ * xcltk/baf/fc/core.py:60,99).  Arguments as xg_decode_bams.  Returns XG_E_UNSUPPORTED -- and
+ * the caller falls back to xg_decode_bams + xg_upload_reads -- when a BAM's records cross BGZF
+ * block boundaries (htslib-written files never do, unless a record exceeds 64 KiB), when a
+ * cell / UMI value needs the host intern table (query-name keys, non-ACGTN-/digit strings,
+ * numeric tags), or when the inflated file does not fit the device.  n_records_seen may be NULL. */
+int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
+                          const int32_t *const *tid_map, const int32_t *tid_map_len,
+                          const char *cell_tag, const char *umi_tag, int32_t want_seq,
+                          xg_dreads **out, int64_t *n_records_seen);
+/* Validation entry: inflate a whole BGZF file on the device into out[0, cap).  With out == NULL
+ * (or cap too small) only *n_out, the inflated size, is set.                               */
+int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t cap, int64_t *n_out);
 /* HBM -> host copy (tests: run the oracle on device-generated records).                 */
 int xg_download_reads(xg_ctx *ctx, const xg_dreads *d, xg_reads **out);
 void xg_dreads_free(xg_ctx *ctx, xg_dreads *d);
 int64_t xg_dreads_n(const xg_dreads *d);
+/* out[0..7] = n_reads, n_cigar, n_seq_words, n_runs, n_tiles, max_aln_len, max_span, bytes in HBM */
+void xg_dreads_info(const xg_dreads *d, int64_t out[8]);
 
 /* Read filters = check_read(), rdr/fc/core.py:46-62 == baf/fc/core.py:18-34.            */
 typedef struct {

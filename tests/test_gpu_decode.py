@@ -1,0 +1,218 @@
+"""Device decoder (xcltk_b200/csrc/gpu_decode.cu: BGZF inflate + BAM parse on the GPU) against
+the host decoder (decode.cpp, itself checked record by record against an independent Python BAM
+reader in test_decode.py): every array of the batch must be identical.  The inflate kernel is
+checked byte for byte against zlib."""
+
+import gzip
+import os
+import random
+
+import numpy as np
+import pytest
+
+from util import GOLD
+
+pytestmark = pytest.mark.gpu
+
+
+def host_decode(paths, maps, cell_tag, umi_tag, want_seq):
+    from xcltk_b200 import lib
+    ks = lib.KeySpace()
+    return lib.decode_bams(paths, maps, cell_tag, umi_tag, want_seq, ks, 4)
+
+
+def full_maps(paths):
+    from xcltk_b200 import lib
+    return [np.arange(len(lib.bam_references(p)), dtype=np.int32) for p in paths]
+
+
+def assert_same_batch(dev, seen, host):
+    got = dev.download()
+    info = dev.info()
+    assert info["n_reads"] == host.n == got.n
+    assert seen == host.n_records_seen
+    assert (info["max_aln_len"], info["max_span"]) == (host.max_aln_len, host.max_span)
+    for name in ("pos_end", "fmq", "cig_off", "keys", "cigar"):
+        assert np.array_equal(getattr(got, name), getattr(host, name)), name
+    assert got.has_seq == host.has_seq
+    if host.has_seq:
+        assert np.array_equal(got.seq_off, host.seq_off)
+        assert np.array_equal(got.seq, host.seq)
+    assert got.runs == host.runs
+    assert got.tiles() == host.tiles()
+    got.close()
+
+
+def tenx_bam(tmp_path, n_reads, seed, name="t.bam", level=6, align=True, mix=None):
+    from xcltk_b200 import synth
+    rng = random.Random(seed)
+    contigs = [("chr1", 2000000), ("chr2", 1200000), ("chrX", 600000), ("chrM", 16000)]
+    feats = synth.synth_features(rng, [(c, l - 20000) for c, l in contigs[:3]], 60)    # reads stay on the contig
+    barcodes = synth.make_barcodes(rng, 50)
+    kw = {} if mix is None else {"cigar_mix": mix}
+    refs, recs = synth.gen_10x_records(seed, contigs, feats, n_reads, barcodes, **kw)
+    p = str(tmp_path / name)
+    synth.write_bam(p, refs, recs, level=level, align=align)
+    return p
+
+
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_inflate_kernel_matches_zlib(gpu_ctx, tmp_path, level):
+    """stored (level 0), fixed-Huffman-heavy (tiny blocks) and dynamic blocks"""
+    p = tenx_bam(tmp_path, 6000, 3 + level, level=level)
+    with gzip.open(p, "rb") as fp:
+        exp = fp.read()
+    got = gpu_ctx.bgzf_inflate(p)
+    assert got.tobytes() == exp
+
+
+def test_inflate_kernel_tiny_and_incompressible_blocks(gpu_ctx, tmp_path):
+    from xcltk_b200 import synth
+    rng = random.Random(5)
+    payloads = [b"", b"A", b"ACGT" * 3, bytes(rng.getrandbits(8) for _ in range(40000)), b"\0" * 65280,
+                bytes(rng.choice(b"ACGT") for _ in range(65280)), (b"x" * 258 + b"y") * 200]
+    p = str(tmp_path / "blocks.bgzf")
+    with open(p, "wb") as fp:
+        for k, pl in enumerate(payloads):
+            fp.write(synth._bgzf_block(pl, level=(1, 6, 9)[k % 3]))
+        fp.write(synth.BGZF_EOF)
+    assert gpu_ctx.bgzf_inflate(p).tobytes() == b"".join(payloads)
+
+
+@pytest.mark.parametrize("want_seq,cell_tag,umi_tag", [(True, "CB", "UB"), (False, "CB", "UB"), (True, "CB", "CB"),
+                                                       (False, None, "UB")])
+def test_device_decode_equals_host_decode(gpu_ctx, tmp_path, want_seq, cell_tag, umi_tag):
+    p = tenx_bam(tmp_path, 30000, 11)
+    maps = full_maps([p])
+    host = host_decode([p], maps, cell_tag, umi_tag, want_seq)
+    dev, seen = gpu_ctx.decode_bams([p], maps, cell_tag, umi_tag, want_seq)
+    assert_same_batch(dev, seen, host)
+    dev.close()
+
+
+def test_device_decode_drops_contigs_and_joins_bams(gpu_ctx, tmp_path):
+    """tid_map drops chr2 / chrM; two BAMs are concatenated in list order (fetch order, B4)"""
+    p1 = tenx_bam(tmp_path, 20000, 12, "a.bam")
+    p2 = tenx_bam(tmp_path, 9000, 13, "b.bam", level=1)
+    maps = [np.array([0, -1, 1, -1], dtype=np.int32), np.array([0, -1, 1, -1], dtype=np.int32)]
+    host = host_decode([p1, p2], maps, "CB", "UB", True)
+    dev, seen = gpu_ctx.decode_bams([p1, p2], maps, "CB", "UB", True)
+    assert host.n < host.n_records_seen
+    assert [r[0] for r in host.runs] == [0, 0, 1, 1]
+    assert_same_batch(dev, seen, host)
+    dev.close()
+
+
+def test_device_decode_handbuilt_cigars(gpu_ctx, tmp_path):
+    from xcltk_b200 import synth
+    M, I, D, N, S, H, P, EQ, X = range(9)
+    recs = [
+        ("a", 4, 0, 10, 0, [(M, 20)], "A" * 20, [("CB", "Z", "ACGT-1"), ("UB", "Z", "AC")]),
+        ("b", 0, 0, 20, 30, [], "", [("UB", "Z", "")]),
+        ("c", 0, 0, 30, 30, [(S, 3), (EQ, 5), (X, 2), (I, 4), (D, 6), (N, 100), (M, 7), (H, 9)],
+         "ACGTNACGTNACGTNACGTNA", [("XX", "B", ("S", [1, 2, 3])), ("CB", "Z", "ACGT-1"), ("UB", "A", "T")]),
+        ("d", 0, 0, 40, 30, [(M, 1), (I, 1)] * 150, "AC" * 150, [("CB", "i", 5), ("UB", "Z", "01234567")]),
+        ("e", 0, 1, 5, 30, [(M, 10)], "ACGTACGTAC", [("CB", "Z", ""), ("xf", "i", 25), ("UB", "Z", "NNN-")]),
+        ("f", 0, -1, -1, 0, [], "ACGT", []),
+    ]
+    p = str(tmp_path / "h.bam")
+    synth.write_bam(p, [("chr1", 100000), ("chr2", 50000)], recs)
+    maps = full_maps([p])
+    host = host_decode([p], maps, "CB", "UB", True)
+    dev, seen = gpu_ctx.decode_bams([p], maps, "CB", "UB", True)
+    assert host.n == 5 and seen == 6
+    assert_same_batch(dev, seen, host)
+    dev.close()
+
+
+def test_device_decode_refuses_what_needs_the_host(gpu_ctx, tmp_path):
+    from xcltk_b200 import lib
+    p = tenx_bam(tmp_path, 5000, 14, "u.bam", align=False)         # records straddle blocks
+    maps = full_maps([p])
+    assert gpu_ctx.decode_bams([p], maps, "CB", "UB", True) is None
+    assert "block boundaries" in gpu_ctx.decode_fallback_reason
+    q = tenx_bam(tmp_path, 5000, 14, "q.bam")
+    assert gpu_ctx.decode_bams([q], maps, "CB", None, True) is None   # query-name keys are interned
+    assert "intern" in gpu_ctx.decode_fallback_reason
+    # ... and the host decoder reads both
+    assert host_decode([p], maps, "CB", "UB", True).n == host_decode([q], maps, "CB", None, True).n
+    with pytest.raises(lib.XgError):
+        gpu_ctx.decode_bams([str(tmp_path / "missing.bam")], maps, "CB", "UB", True)
+
+
+def test_device_decode_rejects_unsorted_and_corrupt(gpu_ctx, tmp_path):
+    from xcltk_b200 import lib, synth
+    recs = [("r%d" % i, 0, 0, pos, 30, [(0, 50)], "A" * 50, [("CB", "Z", "ACGT"), ("UB", "Z", "AC")])
+            for i, pos in enumerate([100, 300, 200])]
+    p = str(tmp_path / "unsorted.bam")
+    synth.write_bam(p, [("chr1", 100000)], recs)
+    with pytest.raises(lib.XgError) as ei:
+        gpu_ctx.decode_bams([p], full_maps([p]), "CB", "UB", True)
+    assert ei.value.code == -3 and "sorted" in str(ei.value)
+    good = tenx_bam(tmp_path, 3000, 15, "good.bam")
+    raw = bytearray(open(good, "rb").read())
+    raw[len(raw) // 2] ^= 0x5a                                     # flip bits inside a deflate stream
+    bad = str(tmp_path / "bad.bam")
+    open(bad, "wb").write(bytes(raw))
+    # neither decoder checks the gzip CRC; a flipped bit shows as a bad stream, a bad record or
+    # an order violation -- or (device only) as a layout the host decoder is asked to judge
+    try:
+        res = gpu_ctx.decode_bams([bad], full_maps([good]), "CB", "UB", True)
+        assert res is None
+        with pytest.raises(lib.XgError):
+            host_decode([bad], full_maps([good]), "CB", "UB", True)
+    except lib.XgError as e:
+        assert e.code == -3
+
+
+def golden_bams():
+    out = []
+    for case in sorted(os.listdir(GOLD)):
+        d = os.path.join(GOLD, case)
+        out += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".bam")]
+    return out
+
+
+@pytest.mark.parametrize("path", golden_bams())
+def test_device_decode_golden_bams(gpu_ctx, tmp_path, path):
+    """The golden BAMs were cut into blocks without regard to records (no htslib writer does
+    that): refused as they are, identical to the host decode once laid out as htslib would."""
+    from xcltk_b200 import synth
+    maps = full_maps([path])
+    host = host_decode([path], maps, "CB", "UB", True)
+    if host.n > 400:
+        assert gpu_ctx.decode_bams([path], maps, "CB", "UB", True) is None
+    p = str(tmp_path / "reblocked.bam")
+    synth.reblock_bam(path, p)
+    with gzip.open(path, "rb") as f1, gzip.open(p, "rb") as f2:
+        assert f1.read() == f2.read()
+    res = gpu_ctx.decode_bams([p], maps, "CB", "UB", True)
+    if res is None:                                    # sample-mode BAMs may carry free-text tags
+        assert "intern" in gpu_ctx.decode_fallback_reason
+        return
+    assert_same_batch(res[0], res[1], host)
+    res[0].close()
+
+
+def test_device_decode_small_staging_chunks(gpu_ctx, tmp_path, monkeypatch):
+    """file -> HBM in many chunks: blocks cut by chunk boundaries are carried over"""
+    monkeypatch.setenv("XG_STAGE_BYTES", str(132 << 10))
+    p = tenx_bam(tmp_path, 40000, 16, level=1)
+    assert os.path.getsize(p) > 8 * (132 << 10)
+    maps = full_maps([p])
+    host = host_decode([p], maps, "CB", "UB", True)
+    dev, seen = gpu_ctx.decode_bams([p], maps, "CB", "UB", True)
+    assert_same_batch(dev, seen, host)
+    dev.close()
+
+
+def test_device_decode_large_uniform_bam(gpu_ctx, tmp_path):
+    from xcltk_b200 import synth
+    p = str(tmp_path / "big.bam")
+    contigs = [("chr%d" % (i + 1), 3000000) for i in range(6)]
+    synth.write_fast_bam(p, 1500000, contigs, n_cells=300, seed=3)
+    maps = full_maps([p])
+    host = host_decode([p], maps, "CB", "UB", True)
+    dev, seen = gpu_ctx.decode_bams([p], maps, "CB", "UB", True)
+    assert_same_batch(dev, seen, host)
+    dev.close()

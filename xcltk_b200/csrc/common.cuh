@@ -134,6 +134,23 @@ struct xg_ctx {
         devbufs.push_back(Pinned{p, want, true});
         return p;
     }
+    size_t dev_idle_bytes() const {
+        size_t n = 0;
+        for (auto &b : devbufs)
+            if (!b.used) n += b.cap;
+        return n;
+    }
+    // free idle buffers (largest first) until at most `keep` bytes stay pooled
+    void dev_trim(size_t keep) {
+        while (dev_idle_bytes() > keep) {
+            size_t big = devbufs.size();
+            for (size_t k = 0; k < devbufs.size(); k++)
+                if (!devbufs[k].used && (big == devbufs.size() || devbufs[k].cap > devbufs[big].cap)) big = k;
+            if (big == devbufs.size()) break;
+            cudaFree(devbufs[big].p);
+            devbufs.erase(devbufs.begin() + (long)big);
+        }
+    }
     void dev_put(void *p) {
         if (!p) return;
         for (auto &b : devbufs)
@@ -168,6 +185,7 @@ struct xg_ctx {
         cudaError_t e = cudaMalloc(&b.p, want);
         if (e != cudaSuccess) {
             cudaGetLastError();
+            dev_trim(0);                     // idle pooled buffers give way to scratch
             e = cudaMalloc(&b.p, bytes ? bytes : 256);
             want = bytes ? bytes : 256;
         }

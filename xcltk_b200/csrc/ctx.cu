@@ -84,6 +84,12 @@ void xg_last_timing(xg_ctx *ctx, double out[16]) {
 
 int64_t xg_dreads_n(const xg_dreads *d) { return d ? d->n_reads : 0; }
 
+void xg_dreads_info(const xg_dreads *d, int64_t out[8]) {
+    const int64_t v[8] = {d->n_reads, d->n_cigar,     d->n_seq_words, d->n_runs,
+                          d->n_tiles, d->max_aln_len, d->max_span,    d->bytes};
+    for (int i = 0; i < 8; i++) out[i] = v[i];
+}
+
 void xg_dreads_free(xg_ctx *ctx, xg_dreads *d) {
     if (!d) return;
     if (ctx) cudaSetDevice(ctx->device);

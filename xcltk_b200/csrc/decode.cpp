@@ -20,16 +20,23 @@
 #include <thread>
 #include <vector>
 
+#include "bamfile.hpp"
 #include "keys.hpp"
 #include "owner.hpp"
 
 namespace {
-
 thread_local std::string g_err;
+}
+
+namespace xg_dec {
 int fail(int code, const std::string &msg) {
     g_err = msg;
     return code;
 }
+}  // namespace xg_dec
+
+namespace {
+using namespace xg_dec;
 
 void *default_alloc(size_t n) {
     void *p = nullptr;
@@ -68,34 +75,17 @@ void parallel_for(int64_t n, int n_threads, F f) {
     for (auto &x : th) x.join();
 }
 
-struct BgzfBlock {
-    uint64_t coff;    // offset of the deflate payload in the file
-    uint32_t clen;    // deflate payload length
-    uint32_t isize;   // uncompressed length
-    uint64_t uoff;    // offset in the uncompressed stream
-};
+}  // namespace
 
-// Byte buffer without the value-initialisation of std::vector::resize (GBs of memset).
-struct Bytes {
-    std::unique_ptr<uint8_t[]> p;
-    size_t n = 0;
-    void resize(size_t m) {
-        p.reset(new uint8_t[m ? m : 1]);
-        n = m;
-    }
-    size_t size() const { return n; }
-    uint8_t *data() { return p.get(); }
-    const uint8_t *data() const { return p.get(); }
-    uint8_t &operator[](size_t i) { return p[i]; }
-    const uint8_t &operator[](size_t i) const { return p[i]; }
-};
+namespace xg_dec {
 
-int read_file(const char *path, Bytes &buf) {
+int read_file(const char *path, Bytes &buf, int64_t max_bytes) {
     FILE *fp = fopen(path, "rb");
     if (!fp) return fail(XG_E_IO, std::string("cannot open '") + path + "'");
     fseek(fp, 0, SEEK_END);
     long n = ftell(fp);
     fseek(fp, 0, SEEK_SET);
+    if (max_bytes >= 0 && n > max_bytes) n = (long)max_bytes;
     buf.resize((size_t)n);
     size_t got = n ? fread(buf.data(), 1, (size_t)n, fp) : 0;
     fclose(fp);
@@ -103,45 +93,62 @@ int read_file(const char *path, Bytes &buf) {
     return XG_OK;
 }
 
-// Walk the BGZF block headers (RFC 1952 member with a 'BC' extra subfield, SAMv1 4.1).
-int scan_bgzf(const Bytes &f, std::vector<BgzfBlock> &blocks, const char *path,
-              int64_t max_blocks = -1) {
+// One BGZF block header at p (RFC 1952 member with a 'BC' extra subfield, SAMv1 4.1).
+// Returns 0 and the block's total / header sizes, 1 when fewer than the needed bytes are
+// available (the caller supplies more), or a negative XG_E_* code.
+int bgzf_block_header(const uint8_t *p, uint64_t avail, uint32_t *total, uint32_t *hdr_len) {
+    if (avail < 18) return 1;
+    if (p[0] != 31 || p[1] != 139 || p[2] != 8 || !(p[3] & 4)) return XG_E_FORMAT;
+    const uint32_t xlen = rd16(p + 10);
+    if (avail < 12ull + xlen) return 1;
+    int64_t bsize = -1;
+    uint64_t x = 12, xend = 12ull + xlen;
+    while (x + 4 <= xend) {
+        const uint32_t slen = rd16(p + x + 2);
+        if (p[x] == 66 && p[x + 1] == 67 && slen == 2 && x + 6 <= xend) bsize = rd16(p + x + 4);
+        x += 4 + slen;
+    }
+    if (bsize < 0) return XG_E_FORMAT;
+    *total = (uint32_t)bsize + 1;
+    *hdr_len = 12 + xlen;
+    if (*total < *hdr_len + 8) return XG_E_FORMAT;
+    return 0;
+}
+
+// Walk the BGZF blocks of a buffer.  allow_partial_tail: the buffer is a prefix of the file;
+// stop quietly at the first block that is cut off.
+int scan_bgzf(const Bytes &f, std::vector<BgzfBlock> &blocks, const char *path, bool allow_partial_tail) {
     uint64_t off = 0, uoff = 0, n = f.size();
     while (off < n) {
-        if (off + 18 > n || f[off] != 31 || f[off + 1] != 139 || f[off + 2] != 8 || !(f[off + 3] & 4))
-            return fail(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (bad block header)");
-        uint32_t xlen = rd16(&f[off + 10]);
-        uint64_t x = off + 12, xend = x + xlen;
-        if (xend > n) return fail(XG_E_FORMAT, "truncated BGZF extra field");
-        int64_t bsize = -1;
-        while (x + 4 <= xend) {
-            uint32_t slen = rd16(&f[x + 2]);
-            if (f[x] == 66 && f[x + 1] == 67 && slen == 2) bsize = rd16(&f[x + 4]);
-            x += 4 + slen;
-        }
-        if (bsize < 0) return fail(XG_E_FORMAT, "BGZF block without BC subfield");
-        uint64_t total = (uint64_t)bsize + 1;
-        if (off + total > n || total < 12 + xlen + 8)
+        uint32_t total = 0, hdr = 0;
+        int rc = bgzf_block_header(&f[off], n - off, &total, &hdr);
+        if (rc == 0 && off + total > n) rc = 1;
+        if (rc == 1) {
+            if (allow_partial_tail) break;
             return fail(XG_E_FORMAT, std::string("truncated BGZF block in '") + path + "'");
+        }
+        if (rc < 0) return fail(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (bad block header)");
         BgzfBlock b;
-        b.coff = off + 12 + xlen;
-        b.clen = (uint32_t)(total - 12 - xlen - 8);
+        b.coff = off + hdr;
+        b.clen = total - hdr - 8;
         b.isize = rd32(&f[off + total - 4]);
         b.uoff = uoff;
         if (b.isize > 65536) return fail(XG_E_FORMAT, "BGZF block larger than 64 KiB");
         uoff += b.isize;
         blocks.push_back(b);
         off += total;
-        if (max_blocks > 0 && (int64_t)blocks.size() >= max_blocks) break;
     }
     return XG_OK;
 }
 
-int inflate_blocks(const Bytes &f, const std::vector<BgzfBlock> &blocks, Bytes &out, int n_threads) {
-    uint64_t total = blocks.empty() ? 0 : blocks.back().uoff + blocks.back().isize;
+// f_base: file offset of f[0] (block descriptors hold file offsets)
+int inflate_blocks(const uint8_t *f, uint64_t f_base, const BgzfBlock *blocks, size_t n_blocks, Bytes &out,
+                   int n_threads) {
+    uint64_t base = n_blocks ? blocks[0].uoff : 0;
+    uint64_t total = n_blocks ? blocks[n_blocks - 1].uoff + blocks[n_blocks - 1].isize - base : 0;
     out.resize(total);
     std::atomic<int> bad(0);
-    parallel_for((int64_t)blocks.size(), n_threads, [&](int, int64_t b, int64_t e) {
+    parallel_for((int64_t)n_blocks, n_threads, [&](int, int64_t b, int64_t e) {
         z_stream zs;
         memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, -15) != Z_OK) {
@@ -152,9 +159,9 @@ int inflate_blocks(const Bytes &f, const std::vector<BgzfBlock> &blocks, Bytes &
             const BgzfBlock &bk = blocks[i];
             if (bk.isize == 0) continue;
             inflateReset(&zs);
-            zs.next_in = const_cast<Bytef *>(&f[bk.coff]);
+            zs.next_in = const_cast<Bytef *>(f + (bk.coff - f_base));
             zs.avail_in = bk.clen;
-            zs.next_out = &out[bk.uoff];
+            zs.next_out = &out[bk.uoff - base];
             zs.avail_out = bk.isize;
             int rc = inflate(&zs, Z_FINISH);
             if (rc != Z_STREAM_END || zs.avail_out != 0) {
@@ -168,25 +175,24 @@ int inflate_blocks(const Bytes &f, const std::vector<BgzfBlock> &blocks, Bytes &
     return XG_OK;
 }
 
-struct Header {
-    std::vector<std::string> names;
-    std::vector<int64_t> lens;
-    uint64_t end_off = 0;   // first record
-};
-
+// XG_E_LIMIT: the buffer ends inside the header (the caller inflates more blocks and retries)
 int parse_header(const Bytes &u, Header &h, const char *path) {
     uint64_t n = u.size();
-    if (n < 12 || memcmp(u.data(), "BAM\1", 4) != 0)
+    if (n >= 4 && memcmp(u.data(), "BAM\1", 4) != 0)
         return fail(XG_E_IO, std::string("'") + path + "' is not a BAM file (bad magic)");
+    if (n < 12) return fail(XG_E_LIMIT, "truncated BAM header");
     uint64_t off = 8 + (uint64_t)(int32_t)rd32(&u[4]);
-    if (off + 4 > n) return fail(XG_E_FORMAT, "truncated BAM header");
+    if (off + 4 > n) return fail(XG_E_LIMIT, "truncated BAM header");
     int32_t n_ref = (int32_t)rd32(&u[off]);
     off += 4;
+    h.names.clear();
+    h.lens.clear();
     for (int32_t i = 0; i < n_ref; i++) {
-        if (off + 4 > n) return fail(XG_E_FORMAT, "truncated BAM header");
+        if (off + 4 > n) return fail(XG_E_LIMIT, "truncated BAM header");
         uint32_t l = rd32(&u[off]);
         off += 4;
-        if (off + l + 4 > n || l == 0) return fail(XG_E_FORMAT, "truncated BAM header");
+        if (l == 0) return fail(XG_E_FORMAT, "corrupt BAM header (empty contig name)");
+        if (off + l + 4 > n) return fail(XG_E_LIMIT, "truncated BAM header");
         h.names.emplace_back((const char *)&u[off], l - 1);
         off += l;
         h.lens.push_back((int64_t)(int32_t)rd32(&u[off]));
@@ -196,7 +202,37 @@ int parse_header(const Bytes &u, Header &h, const char *path) {
     return XG_OK;
 }
 
-// One BAM, inflated, with the offsets of the records we keep.
+// Read (a prefix of) the file, index its blocks and parse the header, inflating only as many
+// leading blocks as the header spans.  header_only reads a growing prefix instead of the file.
+int open_bam(const char *path, BamFile &bf, bool header_only) {
+    int64_t prefix = header_only ? (1 << 20) : -1;
+    while (true) {
+        bf.blocks.clear();
+        int rc = read_file(path, bf.f, prefix);
+        if (rc) return rc;
+        bool partial = prefix >= 0 && (int64_t)bf.f.size() >= prefix;
+        rc = scan_bgzf(bf.f, bf.blocks, path, partial);
+        if (rc) return rc;
+        size_t nb = 1;
+        while (true) {
+            size_t take = std::min(nb, bf.blocks.size());
+            Bytes u;
+            rc = inflate_blocks(bf.f.data(), 0, bf.blocks.data(), take, u, 1);
+            if (rc) return rc;
+            rc = parse_header(u, bf.h, path);
+            if (rc != XG_E_LIMIT) return rc;
+            if (take >= bf.blocks.size()) break;
+            nb *= 2;
+        }
+        if (!partial) return fail(XG_E_FORMAT, std::string("truncated BAM header in '") + path + "'");
+        prefix *= 8;          // header longer than the prefix: read more of the file
+    }
+}
+
+}  // namespace xg_dec
+
+namespace {
+
 struct Bam {
     Bytes u;
     Header h;
@@ -351,30 +387,13 @@ int64_t xg_key_decode(xg_keyspace *ks, uint64_t key, char *buf, int64_t cap) {
 int64_t xg_keyspace_n_interned(xg_keyspace *ks) { return ks->n_interned(); }
 
 int xg_bam_header_read(const char *path, xg_bam_header **out) {
-    Bytes f;
-    int rc = read_file(path, f);
+    BamFile bf;
+    int rc = open_bam(path, bf, true);
     if (rc) return rc;
-    // The header may span several blocks: inflate blocks until it parses.
-    std::vector<BgzfBlock> blocks;
-    rc = scan_bgzf(f, blocks, path);
-    if (rc) return rc;
-    size_t nb = 1;
-    while (true) {
-        std::vector<BgzfBlock> part(blocks.begin(), blocks.begin() + std::min(nb, blocks.size()));
-        Bytes u;
-        rc = inflate_blocks(f, part, u, 1);
-        if (rc) return rc;
-        Header h;
-        rc = parse_header(u, h, path);
-        if (rc == XG_OK) {
-            xg_bam_header *bh = new xg_bam_header();
-            bh->h = std::move(h);
-            *out = bh;
-            return XG_OK;
-        }
-        if (rc == XG_E_IO || nb >= blocks.size()) return rc;
-        nb *= 2;
-    }
+    xg_bam_header *bh = new xg_bam_header();
+    bh->h = std::move(bf.h);
+    *out = bh;
+    return XG_OK;
 }
 int32_t xg_bam_header_n_ref(const xg_bam_header *h) { return (int32_t)h->h.names.size(); }
 const char *xg_bam_header_ref_name(const xg_bam_header *h, int32_t tid) {
@@ -423,12 +442,12 @@ int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *cons
             rc = scan_bgzf(f, blocks, paths[b]);
             if (rc) return rc;
             lap("scan");
-            rc = inflate_blocks(f, blocks, bm.u, n_threads);
+            rc = inflate_blocks(f.data(), 0, blocks.data(), blocks.size(), bm.u, n_threads);
             if (rc) return rc;
             lap("inflate");
         }
         int rc = parse_header(bm.u, bm.h, paths[b]);
-        if (rc) return rc;
+        if (rc) return rc == XG_E_LIMIT ? XG_E_FORMAT : rc;
         int32_t n_ref = (int32_t)bm.h.names.size();
         if (tid_map_len[b] < n_ref) return fail(XG_E_ARG, "tid_map shorter than the BAM's contig list");
         const int32_t *map = tid_map[b];

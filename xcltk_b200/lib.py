@@ -23,6 +23,9 @@ c_u64p = C.POINTER(C.c_uint64)
 c_u8p = C.POINTER(C.c_uint8)
 
 
+XG_E_UNSUPPORTED = -7
+
+
 class XgError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("xcltk_b200 error %d: %s" % (code, msg))
@@ -108,6 +111,10 @@ SYMBOLS = {
     "xg_download_reads": (C.c_int, [_P, _P, C.POINTER(C.POINTER(Reads))]),
     "xg_dreads_free": (None, [_P, _P]),
     "xg_dreads_n": (C.c_int64, [_P]),
+    "xg_dreads_info": (None, [_P, c_i64p]),
+    "xg_decode_bams_device": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(c_i32p), c_i32p,
+                                        C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(_P), c_i64p]),
+    "xg_bgzf_inflate_device": (C.c_int, [_P, C.c_char_p, c_u8p, C.c_int64, c_i64p]),
     "xg_coo_free": (None, [C.POINTER(Coo)]),
     "xg_basefc": (C.c_int, [_P, _P, C.POINTER(Features), C.POINTER(Barcodes), C.POINTER(Params),
                             C.POINTER(C.POINTER(Coo))]),
@@ -388,6 +395,34 @@ class Context(object):
         self._check(self.lib.xg_upload_reads(self.h, host_reads.ptr, C.byref(d)))
         return DeviceReads(self, d)
 
+    def decode_bams(self, paths, tid_maps, cell_tag, umi_tag, want_seq):
+        """BGZF inflate + BAM parse on the device (xg_decode_bams_device).  Returns
+        (DeviceReads, n_records_seen), or None when the files need the host decoder."""
+        n = len(paths)
+        cpaths = (C.c_char_p * n)(*[p.encode() for p in paths])
+        maps = [np.ascontiguousarray(m, dtype=np.int32) for m in tid_maps]
+        cmaps = (c_i32p * n)(*[as_ptr(m, c_i32p) for m in maps])
+        lens = np.array([len(m) for m in maps], dtype=np.int32)
+        d = _P()
+        seen = C.c_int64(0)
+        rc = self.lib.xg_decode_bams_device(self.h, n, cpaths, cmaps, as_ptr(lens, c_i32p),
+                                            cell_tag.encode() if cell_tag else None,
+                                            umi_tag.encode() if umi_tag else None,
+                                            1 if want_seq else 0, C.byref(d), C.byref(seen))
+        if rc == XG_E_UNSUPPORTED:
+            self.decode_fallback_reason = self.lib.xg_last_error(self.h).decode()
+            return None
+        self._check(rc)
+        return DeviceReads(self, d), int(seen.value)
+
+    def bgzf_inflate(self, path):
+        """Inflate a BGZF file on the device; returns the bytes (validation of the inflate kernel)."""
+        n = C.c_int64(0)
+        self._check(self.lib.xg_bgzf_inflate_device(self.h, path.encode(), None, 0, C.byref(n)))
+        out = np.empty(max(1, n.value), dtype=np.uint8)
+        self._check(self.lib.xg_bgzf_inflate_device(self.h, path.encode(), as_ptr(out, c_u8p), n.value, C.byref(n)))
+        return out[:n.value]
+
     def map_reads(self, host_reads):
         """Zero-copy batch for baf: only pos/end go to HBM; `host_reads` must stay alive."""
         d = _P()
@@ -490,6 +525,12 @@ class DeviceReads(object):
     @property
     def n(self):
         return int(self.ctx.lib.xg_dreads_n(self.h))
+
+    def info(self):
+        v = (C.c_int64 * 8)()
+        self.ctx.lib.xg_dreads_info(self.h, v)
+        return dict(zip(("n_reads", "n_cigar", "n_seq_words", "n_runs", "n_tiles", "max_aln_len", "max_span",
+                         "bytes"), [int(x) for x in v]))
 
     def download(self):
         out = C.POINTER(Reads)()

@@ -95,8 +95,16 @@ def pack_record(rec):
     return struct.pack("<i", len(body)) + body
 
 
-def write_bam(path, refs, records, header_text=None, block=60000, level=6):
-    """Write a coordinate-sorted BAM (no index; the decoders scan)."""
+BGZF_MAX_PAYLOAD = 0xff00      # htslib's BGZF_BLOCK_SIZE
+
+
+def write_bam(path, refs, records, header_text=None, block=60000, level=6, align=True):
+    """Write a coordinate-sorted BAM (no index; the decoders scan).
+
+    align=True lays the blocks out as htslib does (bam_hdr_write ends with a flush; bam_write1
+    flushes before a record that would not fit, so a record crosses a block boundary only when it
+    is larger than a block).  align=False cuts the stream every `block` bytes regardless of the
+    records -- legal BGZF/BAM that no htslib writer produces; the device decoder must refuse it."""
     if header_text is None:
         header_text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(
             "@SQ\tSN:%s\tLN:%d\n" % (n, l) for n, l in refs)
@@ -106,6 +114,20 @@ def write_bam(path, refs, records, header_text=None, block=60000, level=6):
         bn = n.encode("ascii") + b"\0"
         buf += struct.pack("<i", len(bn)) + bn + struct.pack("<i", l)
     with open(path, "wb") as fp:
+        if align:
+            def flush():
+                while buf:
+                    fp.write(_bgzf_block(bytes(buf[:BGZF_MAX_PAYLOAD]), level))
+                    del buf[:BGZF_MAX_PAYLOAD]
+            flush()
+            for rec in records:
+                r = pack_record(rec)
+                if len(buf) + len(r) > BGZF_MAX_PAYLOAD:
+                    flush()
+                buf += r
+            flush()
+            fp.write(BGZF_EOF)
+            return
         for rec in records:
             buf += pack_record(rec)
             while len(buf) >= block:
@@ -113,6 +135,32 @@ def write_bam(path, refs, records, header_text=None, block=60000, level=6):
                 del buf[:block]
         if buf:
             fp.write(_bgzf_block(bytes(buf), level))
+        fp.write(BGZF_EOF)
+
+
+def reblock_bam(src, dst, level=6):
+    """Rewrite a BAM with htslib's block layout (header flushed, whole records per block);
+    the uncompressed stream is unchanged."""
+    import gzip
+    with gzip.open(src, "rb") as fp:
+        u = fp.read()
+    o = 8 + struct.unpack_from("<i", u, 4)[0]
+    n_ref = struct.unpack_from("<i", u, o)[0]
+    o += 4
+    for _ in range(n_ref):
+        o += 8 + struct.unpack_from("<i", u, o)[0]
+    with open(dst, "wb") as fp:
+        for i in range(0, o, BGZF_MAX_PAYLOAD):
+            fp.write(_bgzf_block(u[i:min(o, i + BGZF_MAX_PAYLOAD)], level))
+        beg = q = o
+        while q < len(u):
+            nxt = q + 4 + struct.unpack_from("<i", u, q)[0]
+            if nxt - beg > BGZF_MAX_PAYLOAD and q > beg:
+                fp.write(_bgzf_block(u[beg:q], level))
+                beg = q
+            q = nxt
+        for i in range(beg, len(u), BGZF_MAX_PAYLOAD):       # an oversized record is cut, as htslib does
+            fp.write(_bgzf_block(u[i:min(len(u), i + BGZF_MAX_PAYLOAD)], level))
         fp.write(BGZF_EOF)
 
 
@@ -327,7 +375,7 @@ def write_fast_bam(path, n_reads, contigs, n_cells=500, seed=7, read_len=91, lev
     for nm, ln in contigs:
         b = nm.encode() + b"\0"
         head += struct.pack("<i", len(b)) + b + struct.pack("<i", ln)
-    chunks = [bytes(head)]
+    chunks = []
     serial = 0
     for tid, ((nm, ln), n) in enumerate(zip(contigs, per)):
         if n <= 0:
@@ -372,7 +420,8 @@ def write_fast_bam(path, n_reads, contigs, n_cells=500, seed=7, read_len=91, lev
         put(o + 3, acgt[rng.randint(0, 4, size=(n, 12))])
         chunks.append(rec.tobytes())
     raw = b"".join(chunks)
-    blocks = [raw[i:i + 60000] for i in range(0, len(raw), 60000)]
+    step = (BGZF_MAX_PAYLOAD // rec_len) * rec_len          # whole records per block, as htslib writes
+    blocks = [bytes(head)] + [raw[i:i + step] for i in range(0, len(raw), step)]
     with ThreadPoolExecutor(max_workers=threads) as ex, open(path, "wb") as fp:
         for blk in ex.map(lambda b: _bgzf_block(b, level), blocks):
             fp.write(blk)
