@@ -1,6 +1,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include <zlib.h>
 #define __device__
@@ -10,10 +11,13 @@
 struct TI { unsigned x; } threadIdx = {0};
 static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 32; i++) if (v & (1u << i)) r |= 1u << (31 - i); return r; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
-template <class T> T __shfl_sync(unsigned, T v, int, int) { return v; }
+template <class T> T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
 template <class T> T __shfl_up_sync(unsigned, T v, int, int) { return v; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline void __syncwarp(unsigned) {}
+static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return v; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+using std::min;
 #include "../xcltk_b200/csrc/inflate.cuh"
 int main(int argc, char **argv) {
     FILE *fp = fopen(argv[1], "rb");

@@ -25,8 +25,8 @@ for want_seq in (False, True):
         dev, seen = ctx.decode_bams([path], maps, "CB", "UB", want_seq)
         dt = time.time() - t0
         t = ctx.timing()
-        print("device want_seq=%d: %.3f s  %.1f Mreads/s | read %.0f ms, h2d %.0f ms, inflate %.1f ms, walk %.1f ms, "
-              "extract %.1f ms, alloc %.0f ms, trim %.0f ms, call %.0f ms" % (want_seq, dt, seen / dt / 1e6, t[8], t[4], t[1], t[2], t[3], t[9], t[10], t[12]),
+        print("device want_seq=%d: %.3f s  %.1f Mreads/s | pread %.0f ms, read+h2d+inflate %.1f ms, walk %.1f ms, "
+              "extract %.1f ms, alloc %.0f ms, trim %.0f ms, call %.0f ms" % (want_seq, dt, seen / dt / 1e6, t[8], t[4], t[2], t[3], t[9], t[10], t[12]),
               flush=True)
         dev.close()
     t0 = time.time()

@@ -57,7 +57,7 @@ struct BlkInfo {
 constexpr int INFLATE_THREADS = 128;
 template <int S>
 __global__ void __launch_bounds__(INFLATE_THREADS) k_inflate(const uint8_t *comp, const BgzfBlockDev *blocks,
-                                                             int32_t n_blocks, uint8_t *ubuf, int *n_bad) {
+                                                             int32_t n_blocks, int *n_bad) {
     extern __shared__ __align__(16) unsigned char inflate_smem[];
     xg_inflate::GroupSmem *gs = reinterpret_cast<xg_inflate::GroupSmem *>(inflate_smem);
     const int grp = threadIdx.x / S;
@@ -65,23 +65,32 @@ __global__ void __launch_bounds__(INFLATE_THREADS) k_inflate(const uint8_t *comp
     if (b >= n_blocks) return;
     const BgzfBlockDev bk = blocks[b];
     if (bk.isize == 0) return;
-    const int n = xg_inflate::inflate_group<S>(gs[grp], comp + bk.coff, bk.clen, ubuf + bk.uoff, bk.isize);
+    const int n = xg_inflate::inflate_group<S>(gs[grp], comp + bk.coff, bk.clen, bk.uptr, bk.isize);
     if ((threadIdx.x & (S - 1)) == 0 && n != (int)bk.isize) atomicAdd(n_bad, 1);
 }
 
-constexpr int INFLATE_S = 32;
-inline void launch_inflate(cudaStream_t st, const uint8_t *comp, const BgzfBlockDev *blocks, int32_t n_blocks,
-                           uint8_t *ubuf, int *n_bad) {
-    if (n_blocks <= 0) return;
-    constexpr int per_cta = INFLATE_THREADS / INFLATE_S;
+template <int S>
+void launch_inflate_s(cudaStream_t st, const uint8_t *comp, const BgzfBlockDev *blocks, int32_t n_blocks, int *n_bad) {
+    constexpr int per_cta = INFLATE_THREADS / S;
     const size_t smem = per_cta * sizeof(xg_inflate::GroupSmem);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_inflate<INFLATE_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_inflate<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_set = true;
     }
-    k_inflate<INFLATE_S><<<(unsigned)((n_blocks + per_cta - 1) / per_cta), INFLATE_THREADS, smem, st>>>(
-        comp, blocks, n_blocks, ubuf, n_bad);
+    k_inflate<S><<<(unsigned)((n_blocks + per_cta - 1) / per_cta), INFLATE_THREADS, smem, st>>>(comp, blocks, n_blocks,
+                                                                                              n_bad);
+}
+
+inline void launch_inflate(cudaStream_t st, const uint8_t *comp, const BgzfBlockDev *blocks, int32_t n_blocks,
+                           int *n_bad) {
+    if (n_blocks <= 0) return;
+    static const int S = [] {
+        const char *e = getenv("XG_INFLATE_S");
+        return e ? atoi(e) : 32;
+    }();
+    if (S == 16) launch_inflate_s<16>(st, comp, blocks, n_blocks, n_bad);     // experiments only: slower
+    else launch_inflate_s<32>(st, comp, blocks, n_blocks, n_bad);
 }
 
 __device__ __forceinline__ unsigned long long sort_key(int32_t tid, int32_t pos) {
@@ -143,7 +152,7 @@ __device__ __forceinline__ RecGeom rec_geom(const uint8_t *r, uint32_t bs, bool 
 
 // One thread per BGZF block: check that the block holds whole records in coordinate order and
 // size what the kept ones will store.
-__global__ void k_walk(const uint8_t *ubuf, const BgzfBlockDev *blocks, int32_t n_blocks, unsigned long long hdr_end,
+__global__ void k_walk(const BgzfBlockDev *blocks, int32_t n_blocks, unsigned long long hdr_end,
                        const int32_t *tid_map, int32_t n_ref, int want_seq, BlkInfo *info, int *maxes) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
@@ -154,25 +163,25 @@ __global__ void k_walk(const uint8_t *ubuf, const BgzfBlockDev *blocks, int32_t 
     bi.last_key = 0;
     bi.status = 0;
     bi.n_starts = 0;
-    unsigned long long off = bk.uoff, end = bk.uoff + bk.isize;
-    if (end <= hdr_end) {
+    if (bk.uoff + bk.isize <= hdr_end) {
         info[b] = bi;
         return;
     }
-    if (off < hdr_end) off = hdr_end;
+    uint32_t off = bk.uoff < hdr_end ? (uint32_t)(hdr_end - bk.uoff) : 0u;      // offsets within the block
+    const uint32_t end = bk.isize;
     int32_t max_aln = 0, max_span = 0, prev_kept_tid = -2;
     while (off < end) {
         if (off + 4 > end) {
             bi.status = 1;
             break;
         }
-        const uint8_t *r = ubuf + off;
+        const uint8_t *r = bk.uptr + off;
         const uint32_t bs = ld32u(r);
         if (bs < 32) {
             bi.status = 2;
             break;
         }
-        if (off + 4 + bs > end) {
+        if ((unsigned long long)off + 4ull + bs > end) {
             bi.status = 1;
             break;
         }
@@ -200,7 +209,7 @@ __global__ void k_walk(const uint8_t *ubuf, const BgzfBlockDev *blocks, int32_t 
             if (tid != prev_kept_tid) bi.n_starts++;
             prev_kept_tid = tid;
         }
-        off += 4ull + bs;
+        off += 4u + bs;
     }
     info[b] = bi;
     if (max_aln > 0) atomicMax(&maxes[0], max_aln);
@@ -259,7 +268,6 @@ struct RunStart {
 };
 
 struct ExtractArgs {
-    const uint8_t *ubuf;
     const BgzfBlockDev *blocks;
     const BlkInfo *info;
     const unsigned long long *rec_base;   // per block: global index of its first kept record
@@ -284,16 +292,16 @@ __global__ void k_extract(const ExtractArgs a) {
     const BlkInfo bi = a.info[b];
     if (bi.n_kept == 0) return;
     const BgzfBlockDev bk = a.blocks[b];
-    unsigned long long off = bk.uoff, end = bk.uoff + bk.isize;
-    if (off < a.hdr_end) off = a.hdr_end;
+    uint32_t off = bk.uoff < a.hdr_end ? (uint32_t)(a.hdr_end - bk.uoff) : 0u;
+    const uint32_t end = bk.isize;
     unsigned long long g = a.rec_base[b], co = a.cig_base[b], so = a.seq_base[b];
     int32_t prev_tid = -2;
     int need_host = 0;
     while (off < end) {
-        const uint8_t *r = a.ubuf + off;
+        const uint8_t *r = bk.uptr + off;
         const uint32_t bs = ld32u(r);
         const int32_t tid = (int32_t)ld32u(r + 4);
-        off += 4ull + bs;
+        off += 4u + bs;
         if (tid < 0 || a.tid_map[tid] < 0) continue;
         const RecGeom q = rec_geom(r, bs, a.want_seq != 0);
         a.pos_end[g] = make_int2(q.pos, q.end);
@@ -388,7 +396,7 @@ __global__ void k_tile_index2(const int2 *pos_end, xg_tile *tiles, int32_t n_til
 }
 
 struct DevBam {
-    uint8_t *ubuf = nullptr;
+    std::vector<uint8_t *> slabs;           // inflated bytes; a block lies within one slab
     BgzfBlockDev *blocks = nullptr;
     BlkInfo *info = nullptr;
     int32_t *tid_map = nullptr;
@@ -400,12 +408,12 @@ struct DevBam {
     int32_t max_aln = 0, max_span = 0;
     xg_ctx *ctx = nullptr;
     void release() {          // buffers go back to the context's device pool (reused by the next call)
-        ctx->dev_put(ubuf);
+        for (uint8_t *p : slabs) ctx->dev_put(p);
+        slabs.clear();
         ctx->dev_put(blocks);
         ctx->dev_put(info);
         ctx->dev_put(tid_map);
         ctx->dev_put(bases);
-        ubuf = nullptr;
         blocks = nullptr;
         info = nullptr;
         tid_map = nullptr;
@@ -413,16 +421,28 @@ struct DevBam {
     }
 };
 
+double now_ms();
+bool g_lap_on = false;          // XG_DECODE_TIMING: host-side phase times on stderr
+double g_lap_t = 0;
+void lap(const char *what) {
+    if (!g_lap_on) return;
+    const double t = now_ms();
+    fprintf(stderr, "[device decode] %-14s %8.2f ms\n", what, t - g_lap_t);
+    g_lap_t = t;
+}
+
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// ---- file -> HBM ---------------------------------------------------------------------------
+// ---- file -> HBM -> inflated, pipelined -------------------------------------------------------
 // The compressed file is read straight into two pinned staging buffers (several pread threads
-// per chunk) and copied to the device chunk by chunk, so the read of chunk k+1 overlaps the
-// copy of chunk k and the file is never held in host memory.  The BGZF block index is built
-// from each chunk while it is staged; the unscanned tail of a chunk (a block cut by the chunk
-// boundary, < 64 KiB + header) is carried in front of the next one.
+// per chunk) and copied to the device chunk by chunk on the copy stream; the file is never held
+// in host memory.  The BGZF block index is built from each chunk while it is staged (the
+// unscanned tail of a chunk -- a block cut by the chunk boundary, < 64 KiB + header -- is carried
+// in front of the next one), and the blocks that are complete are inflated on the compute
+// stream as soon as their chunk has landed: disk read, PCIe copy and inflate overlap.
+// Inflated bytes go to slabs sized from the first chunk's compression ratio.
 constexpr size_t STAGE_HEAD = 128u << 10;
 size_t stage_bytes() {          // XG_STAGE_BYTES: tests use small chunks to exercise the carry
     const char *e = getenv("XG_STAGE_BYTES");
@@ -454,19 +474,15 @@ bool pread_parallel(int fd, uint8_t *dst, size_t len, uint64_t off, int n_thread
     return ok;
 }
 
-struct StreamedBam {
-    std::vector<xg_dec::BgzfBlock> blocks;
-    xg_dec::Header h;
-    uint64_t csize = 0, usize = 0;
-};
-
-// comp: device buffer of csize + 16 bytes.  The copies are queued on ctx->stream.
-int stream_bam(xg_ctx *ctx, const char *path, int fd, uint8_t *comp, StreamedBam &sb, double *t_read) {
+// comp: device buffer of csize + 16 bytes.  On success every block's inflate kernel has been
+// queued on ctx->stream; db.{blocks, slabs, n_blocks, usize, hdr_end, n_ref} are set.
+int stream_and_inflate(xg_ctx *ctx, const char *path, int fd, uint64_t csize, uint8_t *comp, size_t cap_blocks,
+                       int *d_bad, DevBam &db, double *t_read) {
     const size_t STAGE_BYTES = stage_bytes();
     uint8_t *stage[2] = {(uint8_t *)ctx->pinned_get(STAGE_HEAD + STAGE_BYTES), (uint8_t *)ctx->pinned_get(STAGE_HEAD + STAGE_BYTES)};
     cudaEvent_t done[2] = {nullptr, nullptr};
     auto finish = [&](int code, const std::string &msg) {
-        cudaStreamSynchronize(ctx->stream);       // staging buffers may still be in flight
+        cudaStreamSynchronize(ctx->copy_stream);       // staging buffers may still be in flight
         for (int k = 0; k < 2; k++) {
             if (stage[k]) ctx->pinned_put(stage[k]);
             if (done[k]) cudaEventDestroy(done[k]);
@@ -479,9 +495,13 @@ int stream_bam(xg_ctx *ctx, const char *path, int fd, uint8_t *comp, StreamedBam
     const int n_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
     uint64_t next_off = 0, uoff = 0;
     const uint8_t *prev_data = nullptr;
-    size_t prev_len = 0;
+    size_t prev_len = 0, n_blocks = 0;
     bool header_done = false;
-    const uint64_t csize = sb.csize;
+    xg_dec::Header hdr;
+    std::vector<xg_dec::BgzfBlock> hb;            // the blocks of the current chunk (host descriptors)
+    std::vector<BgzfBlockDev> dv;
+    uint8_t *slab = nullptr;
+    size_t slab_cap = 0, slab_used = 0;
     if (csize == 0) return finish(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (empty file)");
     uint64_t k = 0;
     for (uint64_t c0 = 0; c0 < csize; c0 += STAGE_BYTES, k++) {
@@ -494,13 +514,13 @@ int stream_bam(xg_ctx *ctx, const char *path, int fd, uint8_t *comp, StreamedBam
         const double t0 = now_ms();
         if (!pread_parallel(fd, data, len, c0, n_threads)) return finish(XG_E_IO, std::string("short read on '") + path + "'");
         *t_read += now_ms() - t0;
-        cudaMemcpyAsync(comp + c0, data, len, cudaMemcpyHostToDevice, ctx->stream);
-        cudaEventRecord(done[si], ctx->stream);
+        cudaMemcpyAsync(comp + c0, data, len, cudaMemcpyHostToDevice, ctx->copy_stream);
         const uint64_t view_end = c0 + len;
+        hb.clear();
         while (next_off < view_end) {
             const uint8_t *p = data - (c0 - next_off);      // next_off >= c0 - carry
-            uint32_t total = 0, hdr = 0;
-            int rc = xg_dec::bgzf_block_header(p, view_end - next_off, &total, &hdr);
+            uint32_t total = 0, hl = 0;
+            int rc = xg_dec::bgzf_block_header(p, view_end - next_off, &total, &hl);
             if (rc == 0 && next_off + total > view_end) rc = 1;
             if (rc == 1) {
                 if (view_end == csize) return finish(XG_E_FORMAT, std::string("truncated BGZF block in '") + path + "'");
@@ -508,13 +528,13 @@ int stream_bam(xg_ctx *ctx, const char *path, int fd, uint8_t *comp, StreamedBam
             }
             if (rc < 0) return finish(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (bad block header)");
             xg_dec::BgzfBlock b;
-            b.coff = next_off + hdr;
-            b.clen = total - hdr - 8;
+            b.coff = next_off + hl;
+            b.clen = total - hl - 8;
             memcpy(&b.isize, p + total - 4, 4);
             b.uoff = uoff;
             if (b.isize > 65536) return finish(XG_E_FORMAT, "BGZF block larger than 64 KiB");
             uoff += b.isize;
-            sb.blocks.push_back(b);
+            hb.push_back(b);
             next_off += total;
         }
         if (view_end - next_off > STAGE_HEAD) return finish(XG_E_FORMAT, "BGZF block larger than 64 KiB");
@@ -522,98 +542,126 @@ int stream_bam(xg_ctx *ctx, const char *path, int fd, uint8_t *comp, StreamedBam
             // the BAM header: inflate leading blocks on the host until it parses
             size_t nb = 1;
             while (true) {
-                const size_t take = std::min(nb, sb.blocks.size());
+                const size_t take = std::min(nb, hb.size());
                 xg_dec::Bytes u;
-                int rc = xg_dec::inflate_blocks(data, c0, sb.blocks.data(), take, u, 1);
+                int rc = xg_dec::inflate_blocks(data, c0, hb.data(), take, u, 1);
                 if (rc) return finish(rc, xg_host_last_error());
-                rc = xg_dec::parse_header(u, sb.h, path);
+                rc = xg_dec::parse_header(u, hdr, path);
                 if (rc == XG_OK) break;
                 if (rc != XG_E_LIMIT) return finish(rc, xg_host_last_error());
-                if (take >= sb.blocks.size())
+                if (take >= hb.size())
                     return finish(view_end == csize ? XG_E_FORMAT : XG_E_UNSUPPORTED,
                                   std::string("BAM header of '") + path + "' does not end within the first staged chunk");
                 nb *= 2;
             }
             header_done = true;
         }
+        if (n_blocks + hb.size() > cap_blocks)
+            return finish(XG_E_UNSUPPORTED, std::string("'") + path + "' has unusually small BGZF blocks");
+        // place the chunk's blocks in the slabs, hand their descriptors to the device, inflate
+        dv.resize(hb.size());
+        for (size_t i = 0; i < hb.size(); i++) {
+            if (!slab || slab_used + hb[i].isize + 16 > slab_cap) {
+                // what is left of the file at the ratio seen so far (+10%), at least 64 MiB
+                const double ratio = next_off ? (double)uoff / (double)next_off : 4.0;
+                size_t want = (size_t)((double)(csize - std::min<uint64_t>(csize, hb[i].coff)) * ratio * 1.1) + (64u << 20);
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                if (want + (2ull << 30) > free_b + ctx->dev_idle_bytes())
+                    return finish(XG_E_UNSUPPORTED, "BAM too large to inflate on this device in one piece");
+                const double ta = now_ms();
+                slab = (uint8_t *)ctx->dev_get(want);
+                ctx->timing[9] += now_ms() - ta;
+                if (!slab) return finish(XG_E_CUDA, "out of device memory for the inflated BAM");
+                db.slabs.push_back(slab);
+                slab_cap = want;
+                slab_used = 0;
+            }
+            dv[i].coff = hb[i].coff;
+            dv[i].clen = hb[i].clen;
+            dv[i].isize = hb[i].isize;
+            dv[i].uoff = hb[i].uoff;
+            dv[i].uptr = slab + slab_used;
+            slab_used += hb[i].isize;
+        }
+        if (!dv.empty())
+            cudaMemcpyAsync(db.blocks + n_blocks, dv.data(), dv.size() * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice,
+                            ctx->copy_stream);
+        cudaEventRecord(done[si], ctx->copy_stream);
+        cudaStreamWaitEvent(ctx->stream, done[si], 0);
+        launch_inflate(ctx->stream, comp, db.blocks + n_blocks, (int32_t)dv.size(), d_bad);
+        n_blocks += hb.size();
         prev_data = data;
         prev_len = len;
     }
-    sb.usize = uoff;
+    db.n_blocks = (int32_t)n_blocks;
+    db.usize = uoff;
+    db.hdr_end = hdr.end_off;
+    db.n_ref = (int32_t)hdr.names.size();
     return finish(XG_OK, "");
 }
 
 // Stream one BAM's compressed bytes to the device, inflate them and walk the records.  On
 // success db holds the inflated stream and the per-block sizing.
 int inflate_and_walk(xg_ctx *ctx, const char *path, const int32_t *tid_map, int32_t tid_map_len, int want_seq,
-                     int *d_counters, DevBam &db, double *t_read, double *t_h2d, double *t_inflate, double *t_walk) {
+                     int *d_counters, DevBam &db, double *t_read, double *t_h2d, double *t_walk) {
     const int fd = open(path, O_RDONLY);
     struct stat stt;
     if (fd < 0 || fstat(fd, &stt) != 0) {
         if (fd >= 0) close(fd);
         return ctx->fail(XG_E_IO, std::string("cannot open '") + path + "'");
     }
-    StreamedBam bf;
-    bf.csize = (uint64_t)stt.st_size;
-    const size_t csize = (size_t)bf.csize;
+    const size_t csize = (size_t)stt.st_size;
     db.ctx = ctx;
+    if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        close(fd);
+        return ctx->fail(XG_E_CUDA, "cannot create the copy stream");
+    }
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
     if (csize + (2ull << 30) > free_b + ctx->dev_idle_bytes()) {
         close(fd);
         return ctx->fail(XG_E_UNSUPPORTED, "BAM too large to inflate on this device in one piece");
     }
+    // htslib fills blocks to ~64 KiB of payload; a file whose blocks average under 1 KiB
+    // compressed is not worth a device pass
+    const size_t cap_blocks = csize / 1024 + 4096;
     double t_a0 = now_ms();
     uint8_t *comp = (uint8_t *)ctx->dev_get(csize + 16);
+    db.blocks = (BgzfBlockDev *)ctx->dev_get((cap_blocks + 1) * sizeof(BgzfBlockDev));
+    db.info = (BlkInfo *)ctx->dev_get((cap_blocks + 1) * sizeof(BlkInfo));
+    db.bases = (unsigned long long *)ctx->dev_get((3 * cap_blocks + 1) * 8);
     ctx->timing[9] += now_ms() - t_a0;
-    if (!comp) {
-        close(fd);
-        return ctx->fail(XG_E_CUDA, "out of device memory for the compressed BAM");
-    }
-    cudaStream_t st = ctx->stream;
-    cudaEventRecord(ctx->ev[6], st);
-    int rc = stream_bam(ctx, path, fd, comp, bf, t_read);
-    close(fd);
-    cudaEventRecord(ctx->ev[7], st);
-    if (rc) {
-        ctx->dev_put(comp);
-        return rc;
-    }
     auto bail = [&](int code, const std::string &msg) {
+        cudaStreamSynchronize(ctx->stream);
         ctx->dev_put(comp);
         db.release();
         return ctx->fail(code, msg);
     };
-    db.n_ref = (int32_t)bf.h.names.size();
-    if (tid_map_len < db.n_ref) return bail(XG_E_ARG, "tid_map shorter than the BAM's contig list");
-    if (bf.blocks.size() > (size_t)INT32_MAX) return bail(XG_E_LIMIT, "too many BGZF blocks");
-    db.n_blocks = (int32_t)bf.blocks.size();
-    db.hdr_end = bf.h.end_off;
-    db.usize = bf.usize;
-    const size_t nb = (size_t)db.n_blocks;
-    cudaMemGetInfo(&free_b, &total_b);
-    if (db.usize + nb * (sizeof(BgzfBlockDev) + sizeof(BlkInfo) + 24) + (1ull << 30) > free_b + ctx->dev_idle_bytes())
-        return bail(XG_E_UNSUPPORTED, "BAM too large to inflate on this device in one piece");
-    t_a0 = now_ms();
-    db.ubuf = (uint8_t *)ctx->dev_get(db.usize + 16);
-    db.blocks = (BgzfBlockDev *)ctx->dev_get((nb + 1) * sizeof(BgzfBlockDev));
-    db.info = (BlkInfo *)ctx->dev_get((nb + 1) * sizeof(BlkInfo));
-    db.tid_map = (int32_t *)ctx->dev_get(((size_t)db.n_ref + 1) * 4);
-    db.bases = (unsigned long long *)ctx->dev_get((3 * nb + 1) * 8);
-    if (!comp || !db.ubuf || !db.blocks || !db.info || !db.tid_map || !db.bases)
-        return bail(XG_E_CUDA, "out of device memory for the inflated BAM");
-    ctx->timing[9] += now_ms() - t_a0;
-    static_assert(sizeof(BgzfBlockDev) == sizeof(xg_dec::BgzfBlock), "block descriptors must match");
-    cudaMemcpyAsync(db.blocks, bf.blocks.data(), nb * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(db.tid_map, tid_map, (size_t)db.n_ref * 4, cudaMemcpyHostToDevice, st);
-    cudaMemsetAsync(db.ubuf + (db.usize & ~(uint64_t)7), 0, 16 + (db.usize & 7) - 8, st);   // padding read by ld32u
+    if (!comp || !db.blocks || !db.info || !db.bases) {
+        close(fd);
+        return bail(XG_E_CUDA, "out of device memory for the compressed BAM");
+    }
+    cudaStream_t st = ctx->stream;
     cudaMemsetAsync(d_counters, 0, 8 * sizeof(int), st);
-    cudaEventRecord(ctx->ev[0], st);
-    launch_inflate(st, comp, db.blocks, db.n_blocks, db.ubuf, d_counters + 0);
-    cudaEventRecord(ctx->ev[1], st);
+    cudaEventRecord(ctx->ev[6], st);
+    cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[6], 0);      // comp may be a recycled buffer still in use
+    int rc = stream_and_inflate(ctx, path, fd, csize, comp, cap_blocks, d_counters + 0, db, t_read);
+    close(fd);
+    cudaEventRecord(ctx->ev[7], st);                            // all inflate kernels queued before this
+    if (rc) {
+        const std::string msg = ctx->err;
+        return bail(rc, msg);
+    }
+    lap("stream");
+    if (tid_map_len < db.n_ref) return bail(XG_E_ARG, "tid_map shorter than the BAM's contig list");
+    const size_t nb = (size_t)db.n_blocks;
+    db.tid_map = (int32_t *)ctx->dev_get(((size_t)db.n_ref + 1) * 4);
+    if (!db.tid_map) return bail(XG_E_CUDA, "out of device memory");
+    cudaMemcpyAsync(db.tid_map, tid_map, (size_t)db.n_ref * 4, cudaMemcpyHostToDevice, st);
     if (nb) {
-        k_walk<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(db.ubuf, db.blocks, db.n_blocks, db.hdr_end, db.tid_map, db.n_ref,
-                                                          want_seq, db.info, d_counters + 2);
+        k_walk<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(db.blocks, db.n_blocks, db.hdr_end, db.tid_map, db.n_ref, want_seq,
+                                                          db.info, d_counters + 2);
     }
     cudaEventRecord(ctx->ev[4], st);
     db.h_info.resize(nb);
@@ -622,12 +670,11 @@ int inflate_and_walk(xg_ctx *ctx, const char *path, const int32_t *tid_map, int3
     if (nb) cudaMemcpyAsync(db.h_info.data(), db.info, nb * sizeof(BlkInfo), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return bail(XG_E_CUDA, std::string("device inflate: ") + cudaGetErrorString(e));
+    lap("inflate sync");
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
-    *t_h2d += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-    *t_inflate += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[4]);
+    *t_h2d += ms;                                               // read + copy + inflate, overlapped
+    cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[4]);
     *t_walk += ms;
     ctx->dev_put(comp);
     comp = nullptr;
@@ -663,6 +710,7 @@ int inflate_and_walk(xg_ctx *ctx, const char *path, const int32_t *tid_map, int3
     }
     db.max_aln = h_cnt[2];
     db.max_span = h_cnt[3];
+    lap("block sizes");
     return XG_OK;
 }
 
@@ -701,10 +749,18 @@ int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t 
     }
     cudaStream_t st = ctx->stream;
     cudaMemcpyAsync(comp, f.data(), f.size(), cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(dblk, blocks.data(), blocks.size() * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice, st);
+    std::vector<BgzfBlockDev> dv(blocks.size());
+    for (size_t i = 0; i < blocks.size(); i++) {
+        dv[i].coff = blocks[i].coff;
+        dv[i].clen = blocks[i].clen;
+        dv[i].isize = blocks[i].isize;
+        dv[i].uoff = blocks[i].uoff;
+        dv[i].uptr = ubuf + blocks[i].uoff;
+    }
+    cudaMemcpyAsync(dblk, dv.data(), dv.size() * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(cnt, 0, 8 * sizeof(int), st);
     cudaEventRecord(ctx->ev[0], st);
-    launch_inflate(st, comp, dblk, (int32_t)blocks.size(), ubuf, cnt);
+    launch_inflate(st, comp, dblk, (int32_t)blocks.size(), cnt);
     cudaEventRecord(ctx->ev[1], st);
     int bad = 0;
     cudaMemcpyAsync(&bad, cnt, 4, cudaMemcpyDeviceToHost, st);
@@ -731,19 +787,20 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     XG_CUDA(cudaSetDevice(ctx->device));
     const double t_begin = now_ms();
     for (double &t : ctx->timing) t = 0;
+    g_lap_on = getenv("XG_DECODE_TIMING") != nullptr;
+    g_lap_t = t_begin;
     XG_GET(cnt, int, "gd_counters", 8);
     std::vector<DevBam> bams((size_t)n_bams);
     auto release_all = [&] {
         for (auto &b : bams)
             if (b.ctx) b.release();
     };
-    double t_read = 0, t_h2d = 0, t_inflate = 0, t_walk = 0;
+    double t_read = 0, t_h2d = 0, t_walk = 0;
     int64_t n_total = 0, n_seen = 0, cig_total = 0, seq_total = 0, n_starts = 0;
     int32_t max_aln = 0, max_span = 0;
     cudaEventRecord(ctx->ev[2], ctx->stream);
     for (int32_t b = 0; b < n_bams; b++) {
-        int rc = inflate_and_walk(ctx, paths[b], tid_map[b], tid_map_len[b], want_seq, cnt, bams[b], &t_read, &t_h2d, &t_inflate,
-                                  &t_walk);
+        int rc = inflate_and_walk(ctx, paths[b], tid_map[b], tid_map_len[b], want_seq, cnt, bams[b], &t_read, &t_h2d, &t_walk);
         if (rc) {
             release_all();
             return rc;
@@ -756,6 +813,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
         max_aln = std::max(max_aln, bams[b].max_aln);
         max_span = std::max(max_span, bams[b].max_span);
     }
+    lap("inflate+walk");
     if (cig_total >= (1LL << 32) || seq_total >= (1LL << 32)) {
         release_all();
         return ctx->fail(XG_E_LIMIT, "batch too large for 32-bit stream offsets; decode fewer reads per batch");
@@ -788,6 +846,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
         cudaGetLastError();
         return fail_free(XG_E_CUDA, "out of device memory for the read batch");
     }
+    lap("alloc");
     cudaStream_t st = ctx->stream;
     cudaMemsetAsync(cnt, 0, 8 * sizeof(int), st);
     cudaEventRecord(ctx->ev[0], st);
@@ -800,7 +859,6 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
             if (cig0) k_add_base<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(db.bases + nb, nb, (unsigned long long)cig0);
             if (seq0) k_add_base<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(db.bases + 2 * nb, nb, (unsigned long long)seq0);
             ExtractArgs a;
-            a.ubuf = db.ubuf;
             a.blocks = db.blocks;
             a.info = db.info;
             a.rec_base = db.bases;
@@ -837,6 +895,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     int h_cnt[8];
     cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
+    lap("extract");
     release_all();
     if (e != cudaSuccess) {
         cudaFree(d_starts);
@@ -855,6 +914,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     std::vector<RunStart> starts((size_t)h_cnt[4]);
     if (!starts.empty()) cudaMemcpy(starts.data(), d_starts, starts.size() * sizeof(RunStart), cudaMemcpyDeviceToHost);
     cudaFree(d_starts);
+    lap("release");
     std::sort(starts.begin(), starts.end(), [](const RunStart &x, const RunStart &y) { return x.rec < y.rec; });
     // runs: maximal stretches of kept records of one contig of one BAM (decode.cpp's run_tid)
     int64_t bam_end = 0;
@@ -899,18 +959,19 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     cudaEventRecord(ctx->ev[3], st);
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail_free(XG_E_CUDA, std::string("device decode: ") + cudaGetErrorString(e));
+    lap("runs+tiles");
     int rc = xg_make_tile_pmax(ctx, d);
     if (rc) {
         xg_dreads_free(ctx, d);
         return rc;
     }
+    lap("pmax");
     d->bytes = (int64_t)(n * 32 + (size_t)cig_total * 4 + (size_t)seq_total * 4 + (want_seq ? n * 4 : 0));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
     ctx->timing[0] = ms;                    // device span incl. H2D of the compressed files
-    ctx->timing[1] = t_inflate;             // inflate kernels
     ctx->timing[2] = t_walk;                // walk kernels
-    ctx->timing[4] = t_h2d;                 // H2D of the compressed bytes
+    ctx->timing[4] = t_h2d;                 // file read + H2D of the compressed bytes + inflate, pipelined
     ctx->timing[8] = t_read;                // file read + block scan on the host
     {
         const double t_f0 = now_ms();

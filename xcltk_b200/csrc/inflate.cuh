@@ -21,6 +21,7 @@ struct BgzfBlockDev {
     unsigned int clen;         // payload bytes
     unsigned int isize;        // uncompressed bytes
     unsigned long long uoff;   // offset in the uncompressed stream
+    unsigned char *uptr;       // where the block is inflated to (slabs: blocks are contiguous within one)
 };
 
 namespace xg_inflate {
@@ -340,8 +341,38 @@ __device__ int inflate_group(GroupSmem &g, const uint8_t *in, uint32_t n_in, uin
             }
             const uint32_t myoff = o + incl - mylen;
             const uint32_t total = __shfl_sync(gmask, incl, S - 1, S);
-            if ((int)lane < n && !is_match) out[myoff] = (uint8_t)q;
-            uint32_t mm = (__ballot_sync(gmask, is_match) >> gbase) & (S == 32 ? 0xffffffffu : ((1u << S) - 1u));
+            uint32_t mm;
+            if constexpr (S == 32) {
+                // Every output byte of the batch is produced by the lane at its position: 32 bytes per
+                // round, the owning symbol found from a bitmap of the symbols' start offsets.  A match
+                // that reads bytes of this very batch (distance shorter than its offset into the batch)
+                // is left to the ordered loop below; BAM matches mostly reach back whole records.
+                const bool valid = (int)lane < n;
+                const uint32_t d_i = q & 0xffffu;
+                const bool dep_i = valid && is_match && (myoff - d_i + min(mylen, d_i) > o);
+                const uint32_t offv = valid ? myoff : 0xffffffffu;
+                const uint32_t end = o + total;
+                for (uint32_t base = o; base < end; base += 32) {
+                    const uint32_t sym_before = __popc(__ballot_sync(0xffffffffu, offv < base));
+                    const uint32_t rel = offv - base;
+                    const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+                    const uint32_t p = base + lane;
+                    const int idx = (int)(sym_before + __popc(starts & (0xffffffffu >> (31 - lane)))) - 1;
+                    const uint32_t sq = __shfl_sync(0xffffffffu, q, idx), soff = __shfl_sync(0xffffffffu, myoff, idx);
+                    if (p < end) {
+                        if (sq >> 31) {
+                            const uint32_t d = sq & 0xffffu, len = (sq >> 16) & 0x1ffu;
+                            if (soff - d + min(len, d) <= o) out[p] = out[d >= len ? p - d : soff - d + ((p - soff) % d)];
+                        } else {
+                            out[p] = (uint8_t)sq;
+                        }
+                    }
+                }
+                mm = __ballot_sync(0xffffffffu, dep_i);
+            } else {
+                if ((int)lane < n && !is_match) out[myoff] = (uint8_t)q;
+                mm = (__ballot_sync(gmask, is_match) >> gbase) & ((1u << S) - 1u);
+            }
             if (mm) {
                 __syncwarp(gmask);
                 while (mm) {
