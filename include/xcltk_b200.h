@@ -172,6 +172,8 @@ void xg_dreads_free(xg_ctx *ctx, xg_dreads *d);
 int64_t xg_dreads_n(const xg_dreads *d);
 /* out[0..7] = n_reads, n_cigar, n_seq_words, n_runs, n_tiles, max_aln_len, max_span, bytes in HBM */
 void xg_dreads_info(const xg_dreads *d, int64_t out[8]);
+/* Host copies of the batch's run and tile index (n_runs / n_tiles entries; either may be NULL). */
+void xg_dreads_index(const xg_dreads *d, xg_run *runs_out, xg_tile *tiles_out);
 
 /* Read filters = check_read(), rdr/fc/core.py:46-62 == baf/fc/core.py:18-34.            */
 typedef struct {

@@ -90,6 +90,11 @@ void xg_dreads_info(const xg_dreads *d, int64_t out[8]) {
     for (int i = 0; i < 8; i++) out[i] = v[i];
 }
 
+void xg_dreads_index(const xg_dreads *d, xg_run *runs_out, xg_tile *tiles_out) {
+    if (runs_out && !d->h_runs.empty()) memcpy(runs_out, d->h_runs.data(), d->h_runs.size() * sizeof(xg_run));
+    if (tiles_out && !d->h_tiles.empty()) memcpy(tiles_out, d->h_tiles.data(), d->h_tiles.size() * sizeof(xg_tile));
+}
+
 void xg_dreads_free(xg_ctx *ctx, xg_dreads *d) {
     if (!d) return;
     if (ctx) cudaSetDevice(ctx->device);

@@ -75,18 +75,44 @@ def get_context(device=0):
     return ctx
 
 
+def device_decode_enabled():
+    """The device decoder (BGZF inflate + BAM parse on the GPU) is tried first unless
+    $XCLTK_B200_DEVICE_DECODE is 0; files it declines go through the host decoder."""
+    return os.environ.get("XCLTK_B200_DEVICE_DECODE", "1") not in ("0", "", "no", "false")
+
+
+def _device_decode(ctx, sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq):
+    """(dreads, stats) or None."""
+    if not device_decode_enabled():
+        return None
+    res = ctx.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq)
+    if res is None:
+        return None
+    dreads, seen = res
+    i = dreads.info()
+    return dreads, {"n_reads": i["n_reads"], "n_records_seen": seen, "max_aln_len": i["max_aln_len"],
+                    "max_span": i["max_span"], "bytes": i["bytes"], "decoder": "device"}
+
+
 def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, device=0, mapped=False,
                host_only=False):
-    """Decode every BAM (host, multi-threaded) and upload the batch to `device`.
+    """Bring every BAM's reads to `device` as one batch.
 
+    The device decoder is tried first (the compressed files cross PCIe, the batch is built in
+    HBM); when it declines -- records crossing BGZF blocks, keys that need the intern table --
+    the BAMs are decoded on the host (multi-threaded) and uploaded.
     chroms: distinct (already 'chr'-stripped) contig names the features / SNPs use; reads on
     other contigs can never be fetched by the reference and are dropped at decode time.
-    mapped: keep the records in pinned host memory and copy only pos/end (baf pileup).
-    host_only: no upload at all -- the caller streams the batch with Context.basefc_host."""
+    Host decoder only -- mapped: keep the records in pinned host memory and copy only pos/end
+    (baf pileup); host_only: no upload at all, the caller streams the batch with
+    Context.basefc_host."""
     ctx = get_context(device)
     ks = lib.KeySpace()
     bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
     gid_of, tid_maps = build_tid_maps(bam_refs, list(chroms))
+    dev = _device_decode(ctx, sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq)
+    if dev is not None:
+        return ReadBatch(ctx, dev[0], ks, gid_of, dev[1])
     host = lib.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, ks, n_threads)
     stats = {"n_reads": host.n, "n_records_seen": host.n_records_seen, "max_aln_len": host.max_aln_len,
              "max_span": host.max_span, "bytes": host.nbytes()}
@@ -117,23 +143,37 @@ class MultiBatch(object):
             b.close()
 
 
+def _tile_pos(runs, tiles):
+    tile_pos = {}
+    for rec_beg, n_rec, run, first_pos, max_end in tiles:
+        tile_pos.setdefault(run, []).append(first_pos)
+    tile_pos = {r: np.asarray(v, dtype=np.int64) for r, v in tile_pos.items()}
+    for r in range(len(runs)):
+        tile_pos.setdefault(r, np.zeros(0, dtype=np.int64))
+    return tile_pos
+
+
 def load_reads_multi(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, devices=(0,)):
-    """Decode once on the host, upload to every device in `devices` (one host thread each)."""
+    """The batch on every device in `devices`: each GPU decodes the files itself (device
+    decoder, one host thread per GPU), else they are decoded once on the host and uploaded."""
     from . import parallel
     ctxs = [get_context(d) for d in devices]
     ks = lib.KeySpace()
     bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
     gid_of, tid_maps = build_tid_maps(bam_refs, list(chroms))
+    devs = parallel.run_on_devices(len(ctxs), lambda k: _device_decode(ctxs[k], sam_fn_list, tid_maps, cell_tag,
+                                                                       umi_tag, want_seq))
+    if all(d is not None for d in devs):
+        runs, tiles = devs[0][0].index()
+        return MultiBatch([ReadBatch(c, d[0], ks, gid_of, d[1]) for c, d in zip(ctxs, devs)], runs, _tile_pos(runs, tiles))
+    for d in devs:
+        if d is not None:
+            d[0].close()
     host = lib.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, ks, n_threads)
     stats = {"n_reads": host.n, "n_records_seen": host.n_records_seen, "max_aln_len": host.max_aln_len,
              "max_span": host.max_span, "bytes": host.nbytes()}
     runs = list(host.runs)
-    tile_pos = {}
-    for rec_beg, n_rec, run, first_pos, max_end in host.tiles():
-        tile_pos.setdefault(run, []).append(first_pos)
-    tile_pos = {r: np.asarray(v, dtype=np.int64) for r, v in tile_pos.items()}
-    for r in range(len(runs)):
-        tile_pos.setdefault(r, np.zeros(0, dtype=np.int64))
+    tile_pos = _tile_pos(runs, host.tiles())
     dreads = parallel.run_on_devices(len(ctxs), lambda k: ctxs[k].upload(host))
     host.close()
     return MultiBatch([ReadBatch(c, d, ks, gid_of, stats) for c, d in zip(ctxs, dreads)], runs, tile_pos)

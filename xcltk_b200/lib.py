@@ -112,6 +112,7 @@ SYMBOLS = {
     "xg_dreads_free": (None, [_P, _P]),
     "xg_dreads_n": (C.c_int64, [_P]),
     "xg_dreads_info": (None, [_P, c_i64p]),
+    "xg_dreads_index": (None, [_P, C.POINTER(Run), C.POINTER(Tile)]),
     "xg_decode_bams_device": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(c_i32p), c_i32p,
                                         C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(_P), c_i64p]),
     "xg_bgzf_inflate_device": (C.c_int, [_P, C.c_char_p, c_u8p, C.c_int64, c_i64p]),
@@ -531,6 +532,16 @@ class DeviceReads(object):
         self.ctx.lib.xg_dreads_info(self.h, v)
         return dict(zip(("n_reads", "n_cigar", "n_seq_words", "n_runs", "n_tiles", "max_aln_len", "max_span",
                          "bytes"), [int(x) for x in v]))
+
+    def index(self):
+        """(runs, tiles) as the host decoder reports them: [(bam_idx, gid, rec_beg, rec_end)],
+        [(rec_beg, n_rec, run, first_pos, max_end)]."""
+        i = self.info()
+        runs = (Run * max(1, i["n_runs"]))()
+        tiles = (Tile * max(1, i["n_tiles"]))()
+        self.ctx.lib.xg_dreads_index(self.h, runs, tiles)
+        return ([(x.bam_idx, x.gid, x.rec_beg, x.rec_end) for x in runs[:i["n_runs"]]],
+                [(t.rec_beg, t.n_rec, t.run, t.first_pos, t.max_end) for t in tiles[:i["n_tiles"]]])
 
     def download(self):
         out = C.POINTER(Reads)()
