@@ -15,6 +15,10 @@ template <class T> T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
 template <class T> T __shfl_up_sync(unsigned, T v, int, int) { return v; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
 static inline void __syncwarp(unsigned) {}
+static inline bool __any_sync(unsigned, bool p) { return p; }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+    return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31));
+}
 static inline unsigned __reduce_or_sync(unsigned, unsigned v) { return v; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 using std::min;

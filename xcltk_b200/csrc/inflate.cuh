@@ -104,10 +104,10 @@ __device__ int build_table(GroupSmem &g, const uint8_t *lens, int n, uint32_t *l
 }
 
 // code longer than the table: walk the lengths on the peeked bits
-__device__ __noinline__ int slow_decode(unsigned long long buf, const uint16_t *count, const uint16_t *symarr, int *len) {
+__device__ __noinline__ int slow_decode(uint32_t buf, const uint16_t *count, const uint16_t *symarr, int *len) {
     int code = 0, first = 0, index = 0;
     for (int l = 1; l < 16; l++) {
-        code |= (int)((buf >> (l - 1)) & 1ull);
+        code |= (int)((buf >> (l - 1)) & 1u);
         const int c = count[l];
         if (code - c < first) {
             *len = l;
@@ -120,32 +120,37 @@ __device__ __noinline__ int slow_decode(unsigned long long buf, const uint16_t *
     return -1;
 }
 
+// Bit window over the compressed stream: two consecutive little-endian words and the bit
+// offset into the first; peek() is one funnel shift, skip() refills at most once (n <= 32).
+// The words are read aligned, so up to 3 bytes before the stream and 11 after it are touched
+// (both inside the compressed buffer: neighbouring blocks / its padding).
 struct BitReader {
-    const uint32_t *wp;
-    unsigned long long buf;
-    int cnt;
+    const uint32_t *wp;     // next word to load
+    uint32_t w0, w1, pos;   // pos in [0, 32)
     __device__ __forceinline__ void init(const uint8_t *p) {
-        buf = 0;
-        cnt = 0;
-        while ((uintptr_t)p & 3) {
-            buf |= (unsigned long long)(*p++) << cnt;
-            cnt += 8;
-        }
-        wp = (const uint32_t *)p;
+        const uintptr_t a = (uintptr_t)p;
+        wp = (const uint32_t *)(a & ~(uintptr_t)3);
+        pos = (uint32_t)(a & 3) * 8;
+        w0 = wp[0];
+        w1 = wp[1];
+        wp += 2;
     }
-    __device__ __forceinline__ void refill() {       // afterwards cnt >= 33
-        if (cnt <= 32) {
-            buf |= (unsigned long long)(*wp++) << cnt;
-            cnt += 32;
+    __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(w0, w1, pos); }
+    __device__ __forceinline__ void skip(uint32_t n) {
+        pos += n;
+        if (pos >= 32) {
+            w0 = w1;
+            w1 = *wp++;
+            pos -= 32;
         }
     }
-    __device__ __forceinline__ uint32_t take(int n) {   // n <= 16, bits must be present
-        const uint32_t v = (uint32_t)buf & ((1u << n) - 1u);
-        buf >>= n;
-        cnt -= n;
+    __device__ __forceinline__ uint32_t take(uint32_t n) {   // n <= 16
+        const uint32_t v = peek() & ((1u << n) - 1u);
+        skip(n);
         return v;
     }
-    __device__ __forceinline__ const uint8_t *byte_pos() const { return (const uint8_t *)wp - (cnt >> 3); }
+    __device__ __forceinline__ void align_byte() { skip((8 - (pos & 7)) & 7); }
+    __device__ __forceinline__ const uint8_t *byte_pos() const { return (const uint8_t *)(wp - 2) + (pos >> 3); }
 };
 
 __device__ __constant__ const unsigned char CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
@@ -168,13 +173,11 @@ __device__ int inflate_group(GroupSmem &g, const uint8_t *in, uint32_t n_in, uin
         const uint8_t *stored_src = nullptr;
         int hlit = 0, hdist = 0;
         if (lane == 0) {
-            br.refill();
             last = (int)br.take(1);
             type = (int)br.take(2);
-            if ((const uint8_t *)br.wp > in_end + 8) err = -20;
+            if ((const uint8_t *)br.wp > in_end + 16) err = -20;
             if (type == 0) {
-                br.take(br.cnt & 7);
-                br.refill();
+                br.align_byte();
                 const uint32_t len = br.take(16), nlen = br.take(16);
                 if ((len ^ 0xffffu) != nlen) err = -2;
                 stored_len = len;
@@ -195,22 +198,18 @@ __device__ int inflate_group(GroupSmem &g, const uint8_t *in, uint32_t n_in, uin
                 const int hclen = (int)br.take(4) + 4;
                 if (hlit > 286 || hdist > 30) err = -5;
                 for (int k = 0; k < 19; k++) g.cl_lens[k] = 0;
-                for (int k = 0; k < hclen; k++) {
-                    br.refill();
-                    g.cl_lens[CL_ORDER[k]] = (uint8_t)br.take(3);
-                }
+                for (int k = 0; k < hclen; k++) g.cl_lens[CL_ORDER[k]] = (uint8_t)br.take(3);
                 for (int k = 0; k < 128; k++) g.cllut[k] = 0;
                 if (!err && build_table(g, g.cl_lens, 19, g.cllut, 7, nullptr, g.lcount, 2) != 0) err = -6;
                 int idx = 0;
                 while (!err && idx < hlit + hdist) {
-                    br.refill();
-                    const uint32_t e = g.cllut[(uint32_t)br.buf & 127u];
-                    const int l = (int)(e & 15u);
+                    const uint32_t e = g.cllut[br.peek() & 127u];
+                    const uint32_t l = e & 15u;
                     if (!l) {
                         err = -7;
                         break;
                     }
-                    br.take(l);
+                    br.skip(l);
                     const int sym = (int)(e >> 8);
                     if (sym < 16) {
                         g.lens[idx++] = (uint8_t)sym;
@@ -271,59 +270,58 @@ __device__ int inflate_group(GroupSmem &g, const uint8_t *in, uint32_t n_in, uin
         while (!eob) {
             int n = 0;
             if (lane == 0) {
-                uint32_t oo = o;
+                // queue entries: a literal keeps its table entry (byte in bits 8..15, bit 31 clear),
+                // a match is 1<<31 | length << 16 | distance; offsets are validated by the group
+                uint32_t bad = 0;
                 while (n < S) {
-                    br.refill();
-                    uint32_t e = g.lut[(uint32_t)br.buf & ((1u << LB) - 1u)];
+                    const uint32_t bits = br.peek();
+                    uint32_t e = g.lut[bits & ((1u << LB) - 1u)];
                     if ((e & 15u) == 0) {
                         int l = 0;
-                        const int sym = slow_decode(br.buf, g.lcount, g.lsym, &l);
+                        const int sym = slow_decode(bits, g.lcount, g.lsym, &l);
                         if (sym < 0) {
                             err = -13;
                             break;
                         }
                         e = lit_entry(sym, l);
                     }
-                    br.take((int)(e & 15u));
-                    const uint32_t kind = e >> 28;
-                    if (kind == KIND_LIT) {
-                        g.queue[n++] = (e >> 8) & 0xffu;
-                        oo++;
-                    } else if (kind == KIND_LEN) {
-                        const uint32_t len = ((e >> 8) & 0xffffu) + br.take((int)((e >> 4) & 15u));
-                        br.refill();
-                        uint32_t de = g.dlut[(uint32_t)br.buf & ((1u << DB) - 1u)];
-                        if ((de & 15u) == 0) {
-                            int l = 0;
-                            const int sym = slow_decode(br.buf, g.dcount, g.dsym, &l);
-                            if (sym < 0) {
-                                err = -15;
-                                break;
-                            }
-                            de = dist_entry(sym, l);
+                    const uint32_t l = e & 15u;
+                    if (e < (1u << 28)) {                 // literal
+                        br.skip(l);
+                        g.queue[n++] = e;
+                        continue;
+                    }
+                    if ((e >> 28) != KIND_LEN) {
+                        if ((e >> 28) == KIND_EOB) {
+                            br.skip(l);
+                            eob = 1;
+                        } else {
+                            err = -14;
                         }
-                        if ((de >> 28) != 0) {
+                        break;
+                    }
+                    const uint32_t ex = (e >> 4) & 15u;
+                    const uint32_t len = ((e >> 8) & 0xffffu) + ((bits >> l) & ~(0xffffffffu << ex));
+                    br.skip(l + ex);
+                    const uint32_t dbits = br.peek();
+                    uint32_t de = g.dlut[dbits & ((1u << DB) - 1u)];
+                    if ((de & 15u) == 0) {
+                        int dl = 0;
+                        const int sym = slow_decode(dbits, g.dcount, g.dsym, &dl);
+                        if (sym < 0) {
                             err = -15;
                             break;
                         }
-                        br.take((int)(de & 15u));
-                        const uint32_t d = ((de >> 8) & 0xffffu) + br.take((int)((de >> 4) & 15u));
-                        if (d > oo) {
-                            err = -16;
-                            break;
-                        }
-                        g.queue[n++] = 0x80000000u | (len << 16) | d;
-                        oo += len;
-                    } else if (kind == KIND_EOB) {
-                        eob = 1;
-                        break;
-                    } else {
-                        err = -14;
-                        break;
+                        de = dist_entry(sym, dl);
                     }
+                    bad |= de >> 28;
+                    const uint32_t dl = de & 15u, dx = (de >> 4) & 15u;
+                    const uint32_t d = ((de >> 8) & 0xffffu) + ((dbits >> dl) & ~(0xffffffffu << dx));
+                    br.skip(dl + dx);
+                    g.queue[n++] = 0x80000000u | (len << 16) | d;
                 }
-                if (oo > cap) err = -3;
-                if ((const uint8_t *)br.wp > in_end + 8) err = -20;
+                if (bad) err = -15;
+                if ((const uint8_t *)br.wp > in_end + 16) err = -20;
             }
             __syncwarp(gmask);
             err = __shfl_sync(gmask, err, 0, S);
@@ -341,6 +339,8 @@ __device__ int inflate_group(GroupSmem &g, const uint8_t *in, uint32_t n_in, uin
             }
             const uint32_t myoff = o + incl - mylen;
             const uint32_t total = __shfl_sync(gmask, incl, S - 1, S);
+            // a distance reaching before the start of the output, or output past the block's size
+            if (__any_sync(gmask, (is_match && (q & 0xffffu) > myoff) || o + total > cap)) return -16;
             uint32_t mm;
             if constexpr (S == 32) {
                 // Every output byte of the batch is produced by the lane at its position: 32 bytes per
@@ -364,13 +364,13 @@ __device__ int inflate_group(GroupSmem &g, const uint8_t *in, uint32_t n_in, uin
                             const uint32_t d = sq & 0xffffu, len = (sq >> 16) & 0x1ffu;
                             if (soff - d + min(len, d) <= o) out[p] = out[d >= len ? p - d : soff - d + ((p - soff) % d)];
                         } else {
-                            out[p] = (uint8_t)sq;
+                            out[p] = (uint8_t)(sq >> 8);
                         }
                     }
                 }
                 mm = __ballot_sync(0xffffffffu, dep_i);
             } else {
-                if ((int)lane < n && !is_match) out[myoff] = (uint8_t)q;
+                if ((int)lane < n && !is_match) out[myoff] = (uint8_t)(q >> 8);
                 mm = (__ballot_sync(gmask, is_match) >> gbase) & ((1u << S) - 1u);
             }
             if (mm) {
