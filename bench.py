@@ -144,7 +144,9 @@ class Batch(object):
         ctx, fc, bf = self.ctx, self.fc, self.baf
         launches = 0
         w0 = time.perf_counter()
-        row, col, val, _ = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params)
+        # rows in completion order (what the Matrix-Market writer consumes): copied out under the kernels
+        seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments=True)
+        val = seg.val
         w1 = time.perf_counter()
         t_fc = ctx.timing()
         launches += int(t_fc[2])
@@ -170,7 +172,8 @@ class Batch(object):
 
     def step_e2e(self):
         ctx, fc, bf = self.ctx, self.fc, self.baf
-        row, col, val, _ = ctx.basefc_host(self.h_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params)
+        seg = ctx.basefc_host(self.h_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments=True)
+        val = seg.val
         h2d_fc = int(ctx.timing()[13])
         d_bf = ctx.map_reads(self.h_baf)          # zero-copy: 8 B/read over PCIe, rest on demand
         totals, st = ctx.baf_pileup(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
@@ -181,7 +184,7 @@ class Batch(object):
         d_bf.close()
         return dict(h2d=h2d_fc + 8 * self.h_baf.n + 72 * int(self.ctx.timing_pairs),
                     d2h=8 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])) + totals.nbytes +
-                    8 * (len(fc.gid) + 3 * (len(bf.reg_ptr) - 1) + 4))       # CSR: col + val + row_ptr
+                    12 * len(fc.gid) + 8 * (3 * (len(bf.reg_ptr) - 1) + 3))  # col + val + row_beg/row_cnt | row_ptr
 
 
 def cpu_sample(ctx, args, n_sample, n_threads):

@@ -132,6 +132,10 @@ const char *xg_host_last_error(void);
 int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *row_ptr, const int32_t *out_row,
                  int32_t n_rows_out, int32_t n_cols, const int32_t *col, const int32_t *val,
                  int32_t n_threads);
+/* Same text from rows located by (row_beg, row_cnt) -- the "row_order" 0 layout of xg_coo.   */
+int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
+                      const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const int32_t *col,
+                      const int32_t *val, int32_t n_threads);
 
 /* ---- device side --------------------------------------------------------------------- */
 typedef struct xg_ctx xg_ctx;
@@ -141,7 +145,9 @@ int xg_create(int32_t device, xg_ctx **out);
 void xg_destroy(xg_ctx *ctx);
 const char *xg_last_error(xg_ctx *ctx);
 /* Options: "coo_rows" (default 1): 0 = results are CSR only (row == NULL; row_ptr, col, val),
- * which saves a third of the device->host result copy.                                   */
+ * which saves a third of the device->host result copy.  "row_order" (default 1): 0 = basefc
+ * results keep the device's completion order of the rows (see xg_coo), which lets the result
+ * copy overlap the counting.                                                                */
 int xg_set_option(xg_ctx *ctx, const char *name, int64_t value);
 
 /* Host -> HBM copy of a decoded batch (the only cross-device traffic of the path).      */
@@ -210,15 +216,21 @@ typedef struct {
     int32_t n_samples;     /* number of columns (= n in barcode mode, #BAMs otherwise)    */
 } xg_barcodes;
 
-/* Sparse result, sorted by (row, col), 0-based; library-owned pinned host memory, valid until
- * xg_coo_free() (which must be called before the context is destroyed).               */
+/* Sparse result, 0-based; library-owned pinned host memory, valid until xg_coo_free() (which
+ * must be called before the context is destroyed).  Default layout: sorted by (row, col) with
+ * CSR offsets.  With the context option "row_order" = 0 (xg_basefc / xg_basefc_host only) the
+ * rows are stored in the order the device completed them -- each row still contiguous and
+ * sorted by col -- and located by row_beg / row_cnt; this layout is copied to the host while
+ * the later reads are still being counted, and xg_write_mtx_rows writes it directly.        */
 typedef struct {
     int64_t nnz;
     int32_t n_rows, n_cols;
-    const int32_t *row;       /* NULL when the context option "coo_rows" is 0 (CSR only) */
+    const int32_t *row;       /* NULL when the context option "coo_rows" is 0, or "row_order" is 0 */
     const int32_t *col;
     const int32_t *val;
-    const int64_t *row_ptr;   /* CSR offsets, n_rows + 1 */
+    const int64_t *row_ptr;   /* CSR offsets, n_rows + 1; NULL when "row_order" is 0 */
+    const int64_t *row_beg;   /* "row_order" 0: first entry of every row, n_rows; else NULL */
+    const int32_t *row_cnt;   /* "row_order" 0: entries of every row, n_rows; else NULL */
 } xg_coo;
 void xg_coo_free(xg_coo *m);
 

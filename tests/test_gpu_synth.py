@@ -190,3 +190,35 @@ def test_basefc_full_size_properties(gpu_ctx):
     rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
     order = np.lexsort((cols, rows))
     assert np.array_equal(rows[order], a[0]) and np.array_equal(cols[order], a[1]) and np.array_equal(vals[order], a[2])
+
+
+def test_basefc_row_segments_equal_sorted_result(gpu_ctx, fc_batch, tmp_path):
+    """context option row_order = 0: rows in completion order, copied out under the kernels --
+    the same matrix as the sorted result, from HBM and streamed from the host, on the first call
+    (no size hint: one copy at the end) and on repeated ones (per-epoch copies); and the
+    Matrix-Market text written from it is the one written from the sorted CSR."""
+    from xcltk_b200 import engine, lib
+    w, p = fc_batch, gpu_params(Conf())
+    ref = [np.array(x) for x in gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, p)[:3]]
+    for k in range(3):
+        seg = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, p, segments=True)
+        assert isinstance(seg, lib.RowSegments) and seg.nnz == len(ref[2])
+        for a, b in zip(seg.to_sorted(), ref):
+            assert np.array_equal(a, b)
+    seg_h = gpu_ctx.basefc_host(w.host, w.gid, w.beg, w.end, w.cell_keys, 2000, p, segments=True)
+    for a, b in zip(seg_h.to_sorted(), ref):
+        assert np.array_equal(a, b)
+    # a smaller and a larger problem after the hint was set
+    for sel in (slice(0, len(w.gid) // 3), slice(None)):
+        seg = gpu_ctx.basefc(w.dreads, w.gid[sel], w.beg[sel], w.end[sel], w.cell_keys, 2000, p, segments=True)
+        r = [np.array(x) for x in gpu_ctx.basefc(w.dreads, w.gid[sel], w.beg[sel], w.end[sel], w.cell_keys, 2000, p)[:3]]
+        for a, b in zip(seg.to_sorted(), r):
+            assert np.array_equal(a, b)
+    n = len(w.gid)
+    emitted = np.zeros(n, dtype=bool)
+    emitted[ref[0]] = True
+    emitted[::7] = True
+    engine.write_mtx(str(tmp_path / "a.mtx"), n, ref[0], ref[1], ref[2], emitted, 2000)
+    out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
+    lib.write_mtx_rows(str(tmp_path / "b.mtx"), seg, out_row, int(emitted.sum()))
+    assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "b.mtx"), "rb").read()

@@ -150,3 +150,38 @@ def test_write_mtx_format(tmp_path):
     engine.write_mtx(p, rows, row, col, val, np.ones(rows, dtype=bool), 99999, 5)
     body = open(p).read().split("\n", 3)[3]
     assert body == "".join("%d\t%d\t%d\n" % t for t in zip((row + 1).tolist(), (col + 1).tolist(), val.tolist()))
+
+
+def test_write_mtx_rows_equals_csr_writer(tmp_path):
+    """rows stored out of order and located by (row_beg, row_cnt) -- the layout basefc returns
+    with row_order = 0 -- give the text of the sorted CSR"""
+    import numpy as np
+    from xcltk_b200 import engine, lib
+    rng = np.random.RandomState(4)
+    n_rows, n_cols = 300, 50
+    cnt = rng.randint(0, 12, size=n_rows).astype(np.int32)
+    cnt[rng.rand(n_rows) < 0.3] = 0
+    row = np.repeat(np.arange(n_rows, dtype=np.int32), cnt)
+    col = np.concatenate([np.sort(rng.choice(n_cols, c, replace=False)) for c in cnt] + [np.zeros(0, int)]).astype(np.int32)
+    val = rng.randint(1, 1000000, size=len(row)).astype(np.int32)
+    emitted = cnt > 0
+    emitted[::5] = True
+    engine.write_mtx(str(tmp_path / "a.mtx"), n_rows, row, col, val, emitted, n_cols, 3)
+    # scatter the rows in a random order, with gaps
+    order = rng.permutation(n_rows)
+    beg = np.zeros(n_rows, dtype=np.int64)
+    pos = 0
+    for r in order:
+        beg[r] = pos
+        pos += cnt[r]
+    ptr = np.concatenate([[0], np.cumsum(cnt)])
+    c2, v2 = np.zeros(pos, dtype=np.int32), np.zeros(pos, dtype=np.int32)
+    for r in range(n_rows):
+        c2[beg[r]:beg[r] + cnt[r]] = col[ptr[r]:ptr[r + 1]]
+        v2[beg[r]:beg[r] + cnt[r]] = val[ptr[r]:ptr[r + 1]]
+    seg = lib.RowSegments(beg, cnt, c2, v2, (n_rows, n_cols))
+    out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
+    lib.write_mtx_rows(str(tmp_path / "b.mtx"), seg, out_row, int(emitted.sum()), 2)
+    assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "b.mtx"), "rb").read()
+    for a, b in zip(seg.to_sorted(), (row, col, val)):
+        assert np.array_equal(a, b)

@@ -1092,6 +1092,16 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         cudaStreamWaitEvent(ctx->aux[2], ev_init, 0);
     }
     if (src) cudaStreamWaitEvent(ctx->copy_stream, ev_init, 0);
+    // "row_order" 0: the rows stay in the order they were completed; after every epoch the
+    // staging cursor is snapshotted so that the host can copy that epoch's rows out while the
+    // later epochs are still being counted
+    const bool staged_out = !ctx->row_order;
+    unsigned long long *h_cur = nullptr;
+    if (staged_out) {
+        if (!ctx->d2h_stream) XG_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        h_cur = (unsigned long long *)ctx->pinned_get(sizeof(unsigned long long) * (size_t)(pl.n_epochs + 1));
+        if (!h_cur) return ctx->fail(XG_E_NOMEM, "out of pinned host memory");
+    }
     int64_t h2d_bytes = 0;
     for (int32_t e = 0; e < pl.n_epochs; e++) {
         cudaStream_t st_c = overlap ? ((e & 1) ? ctx->aux[2] : ctx->stream) : ctx->stream;
@@ -1146,6 +1156,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
                 fin_work + e, cursor, seg_base, seg_nnz, st_col, st_val);
             launches++;
         }
+        if (h_cur) cudaMemcpyAsync(h_cur + e, cursor, 8, cudaMemcpyDeviceToHost, st_f);
         cudaEventRecord(EV(3, e), st_f);
     }
     if (overlap) {
@@ -1154,8 +1165,91 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         if (pl.n_epochs > 1) cudaStreamWaitEvent(ctx->stream, EV(2, pl.n_epochs - 2), 0);
     }
     XG_CUDA(cudaGetLastError());
-    if ((rc = xg_staging_to_coo(ctx, "fx", n_rows, n_cols, seg_base, seg_nnz, st_col, st_val, out, &launches)))
+    if (staged_out) {
+        const auto t_tail = std::chrono::steady_clock::now();
+        xg_coo_owner *o = new xg_coo_owner();
+        memset(&o->m, 0, sizeof(o->m));
+        o->ctx = ctx;
+        auto give_up = [&](int code, const std::string &msg) {
+            cudaStreamSynchronize(ctx->d2h_stream);
+            cudaStreamSynchronize(ctx->stream);
+            for (void *q : o->bufs) ctx->pinned_put(q);
+            ctx->pinned_put(h_cur);
+            delete o;
+            return ctx->fail(code, msg);
+        };
+        int64_t cap = ctx->fx_nnz_hint > 0 ? ctx->fx_nnz_hint + ctx->fx_nnz_hint / 8 + 1024 : 0;
+        cap = std::min<int64_t>(cap, pl.staging_cap + 1);
+        int32_t *h_col = nullptr, *h_val = nullptr;
+        if (cap > 0) {
+            h_col = (int32_t *)ctx->pinned_get((size_t)cap * 4);
+            h_val = (int32_t *)ctx->pinned_get((size_t)cap * 4);
+            if (h_col) o->bufs.push_back(h_col);
+            if (h_val) o->bufs.push_back(h_val);
+            if (!h_col || !h_val) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
+        }
+        int64_t done = 0;            // entries already queued for the host
+        bool fits = cap > 0;
+        for (int32_t e = 0; e < pl.n_epochs && fits; e++) {
+            cudaError_t ce = cudaEventSynchronize(EV(3, e));
+            if (ce != cudaSuccess) return give_up(XG_E_CUDA, std::string("basefc: ") + cudaGetErrorString(ce));
+            const int64_t cur = (int64_t)h_cur[e];
+            if (cur > cap) {
+                fits = false;        // more rows than the last call: finish with one copy at the end
+                break;
+            }
+            if (cur > done) {
+                cudaMemcpyAsync(h_col + done, st_col + done, (size_t)(cur - done) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+                cudaMemcpyAsync(h_val + done, st_val + done, (size_t)(cur - done) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+                done = cur;
+            }
+        }
+        cudaError_t ce = cudaStreamSynchronize(ctx->stream);      // every epoch has finished
+        if (ce != cudaSuccess) return give_up(XG_E_CUDA, std::string("basefc: ") + cudaGetErrorString(ce));
+        unsigned long long nnz_u = 0;
+        XG_CUDA(cudaMemcpy(&nnz_u, cursor, 8, cudaMemcpyDeviceToHost));
+        const int64_t nnz = (int64_t)nnz_u;
+        if (!fits || nnz > cap) {
+            cudaStreamSynchronize(ctx->d2h_stream);
+            for (void *q : o->bufs) ctx->pinned_put(q);
+            o->bufs.clear();
+            cap = nnz + nnz / 8 + 1024;
+            h_col = (int32_t *)ctx->pinned_get((size_t)cap * 4);
+            h_val = (int32_t *)ctx->pinned_get((size_t)cap * 4);
+            if (h_col) o->bufs.push_back(h_col);
+            if (h_val) o->bufs.push_back(h_val);
+            if (!h_col || !h_val) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
+            done = 0;
+        }
+        if (nnz > done) {
+            cudaMemcpyAsync(h_col + done, st_col + done, (size_t)(nnz - done) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+            cudaMemcpyAsync(h_val + done, st_val + done, (size_t)(nnz - done) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+        }
+        int64_t *h_beg = (int64_t *)ctx->pinned_get((size_t)(n_rows + 1) * 8);
+        int32_t *h_cnt = (int32_t *)ctx->pinned_get((size_t)(n_rows + 1) * 4);
+        if (h_beg) o->bufs.push_back(h_beg);
+        if (h_cnt) o->bufs.push_back(h_cnt);
+        if (!h_beg || !h_cnt) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
+        cudaMemcpyAsync(h_beg, seg_base, (size_t)n_rows * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+        cudaMemcpyAsync(h_cnt, seg_nnz, (size_t)n_rows * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+        cudaEventRecord(ctx->ev[3], ctx->stream);
+        ce = cudaStreamSynchronize(ctx->d2h_stream);
+        if (ce != cudaSuccess) return give_up(XG_E_CUDA, std::string("result D2H: ") + cudaGetErrorString(ce));
+        cudaEventSynchronize(ctx->ev[3]);
+        ctx->pinned_put(h_cur);
+        ctx->fx_nnz_hint = nnz;
+        ctx->timing[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_tail).count();
+        o->m.nnz = nnz;
+        o->m.n_rows = n_rows;
+        o->m.n_cols = n_cols;
+        o->m.col = h_col;
+        o->m.val = h_val;
+        o->m.row_beg = h_beg;
+        o->m.row_cnt = h_cnt;
+        *out = &o->m;
+    } else if ((rc = xg_staging_to_coo(ctx, "fx", n_rows, n_cols, seg_base, seg_nnz, st_col, st_val, out, &launches))) {
         return rc;
+    }
 
     float t_all = 0;
     const double t_d2h = ctx->timing[4];

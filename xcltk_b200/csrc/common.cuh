@@ -44,12 +44,15 @@ struct xg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;    // xg_basefc_host: H2D of the next epoch
+    cudaStream_t d2h_stream = nullptr;     // "row_order" 0: result rows copied out while later epochs run
+    int64_t fx_nnz_hint = 0;               // nnz of the last basefc call (sizes the pinned result up front)
     cudaStream_t aux[3] = {};              // overlapped epochs: zero, finalize, second count stream
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> ev_pool;     // per-epoch timing events
     std::string err;
     double timing[16] = {};
     bool coo_rows = true;                  // results carry the row array (else CSR: row_ptr only)
+    bool row_order = true;                 // basefc results sorted by row (else rows as completed + row_beg/row_cnt)
     // growable named scratch buffers (avoid cudaMalloc/cudaFree on every call)
     struct Buf {
         void *p = nullptr;

@@ -59,6 +59,7 @@ void xg_destroy(xg_ctx *ctx) {
         for (auto &st : ctx->aux)
             if (st) cudaStreamDestroy(st);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+        if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
         for (auto &b : ctx->pinned) cudaFreeHost(b.p);
         for (auto &b : ctx->devbufs) cudaFree(b.p);
         if (ctx->fx_cache && ctx->fx_cache_free) ctx->fx_cache_free(ctx->fx_cache);
@@ -71,6 +72,10 @@ int xg_set_option(xg_ctx *ctx, const char *name, int64_t value) {
     if (!ctx || !name) return XG_E_ARG;
     if (std::string(name) == "coo_rows") {
         ctx->coo_rows = value != 0;
+        return XG_OK;
+    }
+    if (std::string(name) == "row_order") {
+        ctx->row_order = value != 0;
         return XG_OK;
     }
     return ctx->fail(XG_E_ARG, std::string("unknown option '") + name + "'");

@@ -693,15 +693,16 @@ inline char *put_int(char *p, uint32_t v) {
 }
 }  // namespace
 
-extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *row_ptr, const int32_t *out_row,
-                            int32_t n_rows_out, int32_t n_cols, const int32_t *col, const int32_t *val,
-                            int32_t n_threads) {
-    if (!path || !row_ptr || !out_row || n_rows_in < 0) return fail(XG_E_ARG, "xg_write_mtx: bad argument");
+extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
+                                 const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const int32_t *col,
+                                 const int32_t *val, int32_t n_threads) {
+    if (!path || !row_beg || !row_cnt || !out_row || n_rows_in < 0)
+        return fail(XG_E_ARG, "xg_write_mtx: bad argument");
     if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
     if (n_threads <= 0) n_threads = 1;
     int64_t nnz = 0;
     for (int32_t r = 0; r < n_rows_in; r++) {
-        int64_t c = row_ptr[r + 1] - row_ptr[r];
+        int64_t c = row_cnt[r];
         if (c && out_row[r] <= 0) return fail(XG_E_ARG, "xg_write_mtx: non-empty row without an output row");
         nnz += c;
     }
@@ -715,7 +716,7 @@ extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *
     {
         int64_t acc = 0;
         for (int32_t r = 0; r < n_rows_in; r++) {
-            acc += row_ptr[r + 1] - row_ptr[r];
+            acc += row_cnt[r];
             if (acc >= slab) {
                 cut.push_back(r + 1);
                 acc = 0;
@@ -733,10 +734,12 @@ extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *
             th.emplace_back([&, s] {
                 const int32_t r0 = cut[s], r1 = cut[s + 1];
                 std::vector<char> &b = bufs[s - s0];
-                b.resize((size_t)(row_ptr[r1] - row_ptr[r0]) * 36 + 16);
+                int64_t n_ent = 0;
+                for (int32_t r = r0; r < r1; r++) n_ent += row_cnt[r];
+                b.resize((size_t)n_ent * 36 + 16);
                 char *p = b.data();
                 for (int32_t r = r0; r < r1; r++)
-                    for (int64_t k = row_ptr[r]; k < row_ptr[r + 1]; k++) {
+                    for (int64_t k = row_beg[r]; k < row_beg[r] + row_cnt[r]; k++) {
                         p = put_int(p, (uint32_t)out_row[r]);
                         *p++ = '\t';
                         p = put_int(p, (uint32_t)col[k] + 1u);
@@ -753,4 +756,13 @@ extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *
     if (fclose(fp) != 0) ok = false;
     if (!ok) return fail(XG_E_IO, std::string("short write on '") + path + "'");
     return XG_OK;
+}
+
+extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *row_ptr, const int32_t *out_row,
+                            int32_t n_rows_out, int32_t n_cols, const int32_t *col, const int32_t *val,
+                            int32_t n_threads) {
+    if (!path || !row_ptr || !out_row || n_rows_in < 0) return fail(XG_E_ARG, "xg_write_mtx: bad argument");
+    std::vector<int32_t> cnt((size_t)n_rows_in);
+    for (int32_t r = 0; r < n_rows_in; r++) cnt[(size_t)r] = (int32_t)(row_ptr[r + 1] - row_ptr[r]);
+    return xg_write_mtx_rows(path, n_rows_in, row_ptr, cnt.data(), out_row, n_rows_out, n_cols, col, val, n_threads);
 }

@@ -67,7 +67,8 @@ class Barcodes(C.Structure):
 
 class Coo(C.Structure):
     _fields_ = [("nnz", C.c_int64), ("n_rows", C.c_int32), ("n_cols", C.c_int32),
-                ("row", c_i32p), ("col", c_i32p), ("val", c_i32p), ("row_ptr", c_i64p)]
+                ("row", c_i32p), ("col", c_i32p), ("val", c_i32p), ("row_ptr", c_i64p),
+                ("row_beg", c_i64p), ("row_cnt", c_i32p)]
 
 
 class Snps(C.Structure):
@@ -100,6 +101,8 @@ SYMBOLS = {
                                  C.POINTER(C.POINTER(Reads))]),
     "xg_reads_free": (None, [C.POINTER(Reads)]),
     "xg_host_last_error": (C.c_char_p, []),
+    "xg_write_mtx_rows": (C.c_int, [C.c_char_p, C.c_int32, c_i64p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p,
+                                    c_i32p, C.c_int32]),
     "xg_write_mtx": (C.c_int, [C.c_char_p, C.c_int32, c_i64p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p,
                                C.c_int32]),
     "xg_create": (C.c_int, [C.c_int32, C.POINTER(_P)]),
@@ -348,6 +351,39 @@ class LazyRows(object):
         return np.asarray(self).astype(dtype)
 
 
+class RowSegments(object):
+    """basefc result with the rows in the order the device completed them (context option
+    row_order = 0): row r is col/val[row_beg[r] : row_beg[r] + row_cnt[r]], sorted by col.  This
+    is what the Matrix-Market writer consumes (write_mtx_rows); to_sorted() gives (row, col, val)
+    sorted by (row, col) for everything else."""
+
+    def __init__(self, row_beg, row_cnt, col, val, shape):
+        self.row_beg, self.row_cnt, self.col, self.val, self.shape = row_beg, row_cnt, col, val, shape
+        self.nnz = len(val)
+
+    def to_sorted(self):
+        cnt = self.row_cnt.astype(np.int64)
+        row = np.repeat(np.arange(len(cnt), dtype=np.int32), cnt)
+        ptr = np.concatenate([[0], np.cumsum(cnt)])
+        src = np.repeat(self.row_beg - ptr[:-1], cnt) + np.arange(int(ptr[-1]), dtype=np.int64)
+        return row, np.asarray(self.col)[src], np.asarray(self.val)[src]
+
+
+def write_mtx_rows(path, seg, out_row, n_rows_out, n_threads=0):
+    """RowSegments -> MatrixMarket text (xg_write_mtx_rows)."""
+    lib = load()
+    out_row = np.ascontiguousarray(out_row, dtype=np.int32)
+    col, val = seg.col, seg.val
+    if seg.nnz == 0:
+        col = np.zeros(1, dtype=np.int32)
+        val = np.zeros(1, dtype=np.int32)
+    rc = lib.xg_write_mtx_rows(path.encode(), len(seg.row_cnt), as_ptr(seg.row_beg, c_i64p),
+                               as_ptr(seg.row_cnt, c_i32p), as_ptr(out_row, c_i32p), int(n_rows_out),
+                               int(seg.shape[1]), as_ptr(col, c_i32p), as_ptr(val, c_i32p), n_threads)
+    if rc != 0:
+        raise XgError(rc, lib.xg_host_last_error().decode())
+
+
 def coo_to_numpy(lib, pcoo, copy_below=1 << 16, ctx_obj=None):
     """(row, col, val, shape).  Large results are zero-copy views of the library's pinned
     buffers (released when the last view dies); small ones are copied and freed at once.
@@ -355,6 +391,21 @@ def coo_to_numpy(lib, pcoo, copy_below=1 << 16, ctx_obj=None):
     m = pcoo.contents
     nnz = int(m.nnz)
     shape = (int(m.n_rows), int(m.n_cols))
+    if bool(m.row_beg):                       # rows in completion order
+        row_beg = np_view(m.row_beg, shape[0], np.int64).copy()
+        row_cnt = np_view(m.row_cnt, shape[0], np.int32).copy()
+        views = [np_view(p, nnz, np.int32) for p in (m.col, m.val)]
+        if nnz <= copy_below:
+            cv = [v.copy() for v in views]
+            lib.xg_coo_free(pcoo)
+        else:
+            owner = _CooOwner(lib, pcoo, ctx_obj)
+            cv = []
+            for v in views:
+                w = v.view(_View)
+                w._owner = owner
+                cv.append(w)
+        return RowSegments(row_beg, row_cnt, cv[0], cv[1], shape)
     has_rows = bool(m.row)
     row_ptr = np_view(m.row_ptr, shape[0] + 1, np.int64).copy()
     views = [np_view(p, nnz, np.int32) for p in ((m.row if has_rows else m.col), m.col, m.val)]
@@ -437,7 +488,9 @@ class Context(object):
         self.lib.xg_last_timing(self.h, t)
         return list(t)
 
-    def basefc(self, dreads, gid, beg, end, cell_keys, n_samples, params):
+    def basefc(self, dreads, gid, beg, end, cell_keys, n_samples, params, segments=False):
+        """(row, col, val, shape) sorted by (row, col); segments=True: a RowSegments (rows in
+        completion order, copied out while the counting is still running)."""
         gid = np.ascontiguousarray(gid, dtype=np.int32)
         beg = np.ascontiguousarray(beg, dtype=np.int32)
         end = np.ascontiguousarray(end, dtype=np.int32)
@@ -445,11 +498,15 @@ class Context(object):
         f = Features(len(gid), as_ptr(gid, c_i32p), as_ptr(beg, c_i32p), as_ptr(end, c_i32p))
         b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
         out = C.POINTER(Coo)()
-        self._check(self.lib.xg_basefc(self.h, dreads.h, C.byref(f), C.byref(b), C.byref(params.c),
-                                       C.byref(out)))
+        self.lib.xg_set_option(self.h, b"row_order", 0 if segments else 1)
+        try:
+            self._check(self.lib.xg_basefc(self.h, dreads.h, C.byref(f), C.byref(b), C.byref(params.c),
+                                           C.byref(out)))
+        finally:
+            self.lib.xg_set_option(self.h, b"row_order", 1)
         return coo_to_numpy(self.lib, out, ctx_obj=self)
 
-    def basefc_host(self, host_reads, gid, beg, end, cell_keys, n_samples, params):
+    def basefc_host(self, host_reads, gid, beg, end, cell_keys, n_samples, params, segments=False):
         """basefc straight from a pinned host batch: H2D streamed under the counting kernels."""
         gid = np.ascontiguousarray(gid, dtype=np.int32)
         beg = np.ascontiguousarray(beg, dtype=np.int32)
@@ -458,8 +515,12 @@ class Context(object):
         f = Features(len(gid), as_ptr(gid, c_i32p), as_ptr(beg, c_i32p), as_ptr(end, c_i32p))
         b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
         out = C.POINTER(Coo)()
-        self._check(self.lib.xg_basefc_host(self.h, host_reads.ptr, C.byref(f), C.byref(b), C.byref(params.c),
-                                            C.byref(out)))
+        self.lib.xg_set_option(self.h, b"row_order", 0 if segments else 1)
+        try:
+            self._check(self.lib.xg_basefc_host(self.h, host_reads.ptr, C.byref(f), C.byref(b), C.byref(params.c),
+                                                C.byref(out)))
+        finally:
+            self.lib.xg_set_option(self.h, b"row_order", 1)
         return coo_to_numpy(self.lib, out, ctx_obj=self)
 
     def baf_pileup(self, dreads, gid, pos, cell_keys, n_samples, params):

@@ -15,7 +15,7 @@ from logging import warning as warn
 
 import numpy as np
 
-from ... import engine
+from ... import engine, lib
 from ...config import APP, VERSION
 from ...utils.grange import Region
 from ...utils.xlog import init_logging
@@ -292,13 +292,18 @@ def count_features(conf, batch=None):
             conf.shard_sizes = [len(s) for s in shards]
         else:
             params = engine.make_params(conf, batch.stats["max_aln_len"], with_include=True)
+            seg = bool(getattr(conf, "row_segments", False))     # fc_core: rows as completed, for the MTX writer
             if batch.dreads is None:       # pinned host batch: H2D streamed under the kernels
-                row, col, val, _shape = batch.ctx.basefc_host(batch.host, gid, beg, end, cell_keys,
-                                                              len(conf.samples), params)
+                res = batch.ctx.basefc_host(batch.host, gid, beg, end, cell_keys, len(conf.samples), params,
+                                            segments=seg)
             else:
-                row, col, val, _shape = batch.ctx.basefc(batch.dreads, gid, beg, end, cell_keys,
-                                                         len(conf.samples), params)
+                res = batch.ctx.basefc(batch.dreads, gid, beg, end, cell_keys, len(conf.samples), params,
+                                       segments=seg)
             conf.last_timing = batch.ctx.timing()
+            if seg:
+                conf.last_stats = dict(batch.stats)
+                return res
+            row, col, val, _shape = res
         conf.last_stats = dict(batch.stats)
     finally:
         if own:
@@ -313,20 +318,30 @@ def fc_core(conf):
     conf.show(fp=sys.stderr, prefix="\t")
 
     regs = conf.reg_list
-    row, col, val = count_features(conf)
-    row = np.asarray(row)            # CSR result: rows are expanded on the host
+    conf.row_segments = True         # one GPU: rows in completion order, copied out under the kernels
+    res = count_features(conf)
 
     # emit (rdr/fc/core.py:96-124): a feature gets an output row iff it has a non-zero
     # count or output_all_reg; rows are numbered over the emitted features, input order.
     n_reg = len(regs)
-    has = np.zeros(n_reg, dtype=bool)
-    has[row] = True
+    if isinstance(res, lib.RowSegments):
+        has = res.row_cnt > 0
+    else:
+        row, col, val = res
+        row = np.asarray(row)        # CSR result: rows are expanded on the host
+        has = np.zeros(n_reg, dtype=bool)
+        has[row] = True
     emitted = np.ones(n_reg, dtype=bool) if conf.output_all_reg else has
     with open(conf.out_region_fn, "w") as fp:
         fp.write("".join("%s\t%d\t%d\t%s\n" % (r.chrom, r.start, r.end - 1, r.get_id())
                          for r, e in zip(regs, emitted) if e))
-    engine.write_mtx(conf.out_mtx_fn, n_reg, row, col, val, emitted, len(conf.samples),
-                     engine.n_decode_threads(conf.nproc))
+    if isinstance(res, lib.RowSegments):
+        out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
+        lib.write_mtx_rows(conf.out_mtx_fn, res, out_row, int(np.count_nonzero(emitted)),
+                           engine.n_decode_threads(conf.nproc))
+    else:
+        engine.write_mtx(conf.out_mtx_fn, n_reg, row, col, val, emitted, len(conf.samples),
+                         engine.n_decode_threads(conf.nproc))
     info("[GPU] %d reads counted in %.2f ms of kernels." % (
         conf.last_stats["n_reads"], conf.last_timing[0]))
 
