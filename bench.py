@@ -323,6 +323,7 @@ def main():
 
     decode = None
     device_decode = None
+    file_to_matrix = None
     if rank == 0 and not args.no_cpu:
         # host BGZF/BAM decode throughput (the stage before the path) on a bounded sample
         try:
@@ -331,16 +332,16 @@ def main():
             n_dec = 6000000
             with tempfile.TemporaryDirectory() as td:
                 bam = os.path.join(td, "s.bam")
-                synth.write_fast_bam(bam, n_dec, [("chr%d" % c, 100000000) for c in range(1, 6)], 1000, seed=5,
-                                     threads=os.cpu_count() or 1)
+                barcodes = synth.write_fast_bam(bam, n_dec, [("chr%d" % c, 100000000) for c in range(1, 6)], 1000,
+                                                seed=5, threads=os.cpu_count() or 1)
                 ks = lib.KeySpace()
                 t = time.perf_counter()
                 hr = lib.decode_bams([bam], [np.arange(5, dtype=np.int32)], "CB", "UB", False, ks, os.cpu_count() or 1)
                 dt_dec = time.perf_counter() - t
                 decode = {"reads_per_s": hr.n / dt_dec, "threads": os.cpu_count() or 1, "sample_reads": hr.n,
                           "bam_bytes": os.path.getsize(bam),
-                          "note": "xg_decode_bams on a %d-read synthetic BAM; at this rate decoding the C3 batch "
-                                  "takes %.0f s -- file-to-matrix time is decode-bound" % (hr.n, args.reads / (hr.n / dt_dec))}
+                          "note": "xg_decode_bams (host decoder, used for files the device decoder declines) on a "
+                                  "%d-read synthetic BAM; at this rate decoding the C3 batch takes %.0f s" % (hr.n, args.reads / (hr.n / dt_dec))}
                 hr.close()
                 # the same file through the device decoder (BGZF inflate + BAM parse on the GPU,
                 # batch left in HBM); first call warms the staging / slab pools
@@ -362,6 +363,29 @@ def main():
                                              "the C3 batch at this rate takes %.1f s" % (args.reads / (n_dev / best))}
                 else:
                     device_decode = {"declined": getattr(ctx, "decode_fallback_reason", "")}
+                # the user's call, file to file: fc_wrapper(BAM, barcodes, features, out_dir) ->
+                # features.tsv / barcodes.tsv / matrix.mtx on disk (device decode + basefc + MTX writer)
+                from xcltk_b200.rdr.fc.main import fc_wrapper
+                bc_fn, ft_fn = os.path.join(td, "barcodes.tsv"), os.path.join(td, "features.tsv")
+                with open(bc_fn, "w") as fp:
+                    fp.write("".join(b + "\n" for b in barcodes))
+                with open(ft_fn, "w") as fp:
+                    for c in range(1, 6):
+                        for k in range(2000):          # 50 kb windows, every other one overlapping its neighbour
+                            fp.write("chr%d\t%d\t%d\tw%d_%d\n" % (c, k * 50000 + 1, k * 50000 + (75000 if k & 1 else 50000), c, k))
+                best_f = None
+                for k in range(2):
+                    out_dir = os.path.join(td, "out%d" % k)
+                    t = time.perf_counter()
+                    ret = fc_wrapper(bam, bc_fn, ft_fn, out_dir, ncores=os.cpu_count() or 1)
+                    dt_f = time.perf_counter() - t
+                    if ret != 0:
+                        raise RuntimeError("fc_wrapper returned %d" % ret)
+                    best_f = dt_f if best_f is None else min(best_f, dt_f)
+                file_to_matrix = {"reads_per_s": n_dec / best_f, "sample_reads": n_dec, "call_ms": 1e3 * best_f,
+                                  "mtx_bytes": os.path.getsize(os.path.join(out_dir, "matrix.mtx")),
+                                  "note": "fc_wrapper(): BAM file -> features.tsv, barcodes.tsv, matrix.mtx on disk "
+                                          "(10000 windows x %d cells), best of 2" % len(barcodes)}
         except Exception as ex:
             decode = {"error": str(ex)[:200]}
 
@@ -371,7 +395,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u64 keys / i32 counts", "data": "synthetic", "config": config,
                 "e2e": e2e, "gpu_launches": int(sum(i["launches"] for i in infos)), "clocks": clocks,
-                "roofline": roofline, "cpu_baseline": cpu, "host_decode": decode, "device_decode": device_decode,
+                "roofline": roofline, "cpu_baseline": cpu, "host_decode": decode, "device_decode": device_decode, "file_to_matrix": file_to_matrix,
                 "detail": {"basefc_device_ms": float(np.mean([i["t_fc"][0] for i in infos])),
                            "basefc_epoch_span_ms": float(np.mean([i["t_fc"][3] for i in infos])),
                            "basefc_count_kernel_ms": t_cnt_ms,

@@ -216,3 +216,94 @@ def test_device_decode_large_uniform_bam(gpu_ctx, tmp_path):
     dev, seen = gpu_ctx.decode_bams([p], maps, "CB", "UB", True)
     assert_same_batch(dev, seen, host)
     dev.close()
+
+
+def _random_records(seed, n):
+    """records with every aux type around the cell / UMI tags, CIGARs from none to > 255 ops,
+    odd sequence lengths, missing tags, unplaced reads at the end"""
+    rng = random.Random(seed)
+    alpha = "ACGTN-0123456789"
+    recs = []
+    pos = {0: 0, 1: 0}
+    for i in range(n):
+        tid = 0 if i < n * 0.6 else 1
+        pos[tid] += rng.randrange(0, 40)
+        kind = rng.random()
+        if kind < 0.05:
+            cigar, l_seq = [], rng.choice([0, 5])
+        elif kind < 0.10:
+            cigar = [(0, 1), (1, 1)] * rng.randrange(130, 200)          # > 255 ops
+            l_seq = sum(l for op, l in cigar if op in (0, 1, 4, 7, 8))
+        else:
+            ops = []
+            for _ in range(rng.randrange(1, 7)):
+                ops.append((rng.choice([0, 0, 0, 1, 2, 3, 4, 7, 8, 5, 6]), rng.randrange(1, 60)))
+            cigar = ops
+            l_seq = sum(l for op, l in cigar if op in (0, 1, 4, 7, 8))
+        seq = "".join(rng.choice("ACGTN=MRY") for _ in range(l_seq))
+        tags = []
+
+        def noise():
+            for _ in range(rng.randrange(0, 4)):
+                t = rng.choice(["NH", "HI", "AS", "nM", "xf", "RG", "GX", "ZZ", "fl", "ba"])
+                typ = rng.choice("AcCsSiIfZHB")
+                if typ == "A":
+                    v = rng.choice("ACGTXYZ!")
+                elif typ in "cCsSiI":
+                    lo, hi = {"c": (-128, 127), "C": (0, 255), "s": (-32768, 32767), "S": (0, 65535),
+                              "i": (-2 ** 31, 2 ** 31 - 1), "I": (0, 2 ** 32 - 1)}[typ]
+                    v = rng.randint(lo, hi)
+                elif typ == "f":
+                    v = rng.random() * 100
+                elif typ == "Z":
+                    v = "".join(rng.choice("abc:/ ACGT0123") for _ in range(rng.randrange(0, 30)))
+                elif typ == "H":
+                    v = "".join(rng.choice("0123456789ABCDEF") for _ in range(2 * rng.randrange(0, 8)))
+                else:
+                    sub = rng.choice("cCsSiIf")
+                    cnt = rng.randrange(0, 9)
+                    if sub == "f":
+                        v = (sub, [rng.random() for _ in range(cnt)])
+                    else:
+                        lo, hi = {"c": (-128, 127), "C": (0, 255), "s": (-32768, 32767), "S": (0, 65535),
+                                  "i": (-2 ** 31, 2 ** 31 - 1), "I": (0, 2 ** 32 - 1)}[sub]
+                        v = (sub, [rng.randint(lo, hi) for _ in range(cnt)])
+                tags.append((t, typ, v))
+        noise()
+        r = rng.random()
+        if r < 0.85:
+            tags.append(("CB", "Z", "".join(rng.choice(alpha[:6]) for _ in range(rng.randrange(0, 17))) +
+                         rng.choice(["", "-1", "-2"])))
+        elif r < 0.90:
+            tags.append(("CB", "A", rng.choice("ACGTN-7")))
+        elif r < 0.93:
+            tags.append(("CB", "i", rng.randrange(0, 100)))               # not a string: never a listed barcode
+        noise()
+        r = rng.random()
+        if r < 0.9:
+            tags.append(("UB", "Z", "".join(rng.choice(alpha) for _ in range(rng.randrange(0, 9)))))
+        elif r < 0.95:
+            tags.append(("UB", "A", rng.choice("ACGT5")))
+        if rng.random() < 0.1:
+            tags.append(("CB", "Z", "TTTT"))                              # a second CB: the first one wins
+        noise()
+        flag = rng.choice([0, 16, 4, 99, 147, 256, 1024, 2048])
+        name = "q%d" % i + "x" * rng.randrange(0, 20)
+        recs.append((name, flag, tid, pos[tid], rng.choice([0, 3, 20, 255]), cigar, seq, tags))
+    for i in range(5):
+        recs.append(("u%d" % i, 4, -1, -1, 0, [], "ACGT", [("CB", "Z", "ACGT")]))
+    return recs
+
+
+@pytest.mark.parametrize("seed,want_seq", [(1, True), (2, False), (3, True)])
+def test_device_decode_random_records_all_aux_types(gpu_ctx, tmp_path, seed, want_seq):
+    from xcltk_b200 import synth
+    recs = _random_records(seed, 6000)
+    p = str(tmp_path / "r.bam")
+    synth.write_bam(p, [("chr1", 10000000), ("chr2", 10000000)], recs, level=(1, 6, 9)[seed % 3])
+    maps = full_maps([p])
+    host = host_decode([p], maps, "CB", "UB", want_seq)
+    res = gpu_ctx.decode_bams([p], maps, "CB", "UB", want_seq)
+    assert res is not None, gpu_ctx.decode_fallback_reason
+    assert_same_batch(res[0], res[1], host)
+    res[0].close()
