@@ -438,11 +438,13 @@ __device__ __forceinline__ int32_t included_len(const uint32_t *cig, uint32_t n_
 // include test of one (read, feature) pair; a passing pair is staged for the insert phase
 __device__ __forceinline__ void emit_pair(const BasefcDev &P, PairStage &S, int32_t j, int32_t s0, int32_t e0,
                                           int32_t pos, int32_t end, const uint32_t *cig, uint32_t n_ops,
-                                          int32_t need, uint64_t umi, uint32_t col) {
+                                          int32_t aln, int32_t need, uint64_t umi, uint32_t col) {
     int32_t m;
     if (n_ops == 0) {
         int32_t a = max(pos, s0), b = min(end, e0);
         m = b > a ? b - a : 0;
+    } else if (s0 <= pos && end <= e0) {
+        m = aln;                  // the read lies inside the feature: every aligned position counts
     } else {
         m = included_len(cig, n_ops, pos, s0, e0);
     }
@@ -670,7 +672,7 @@ __global__ void __launch_bounds__(256, 6) k_basefc_count(const __grid_constant__
             }
             for (int32_t s = s0i; s < s1i; s++) {
                 const int4 f = (stab_staged && s >= st_lo) ? S.stab4[s - st_lo] : __ldg(&P.stab4[s]);
-                emit_pair(P, S, f.x, f.y, f.z, pos, end, cig, n_ops, need, umi, col);
+                emit_pair(P, S, f.x, f.y, f.z, pos, end, cig, n_ops, aln, need, umi, col);
             }
         }
         // (2) features beginning at a boundary inside (pos, end); every boundary from tb.y on is
@@ -681,7 +683,7 @@ __global__ void __launch_bounds__(256, 6) k_basefc_count(const __grid_constant__
             if (bv >= end) break;
             const int32_t j1 = __ldg(&P.fb[kb + 1]);
             for (int32_t j = __ldg(&P.fb[kb]); j < j1; j++)
-                emit_pair(P, S, j, bv, __ldg(&P.sf_end[j]), pos, end, cig, n_ops, need, umi, col);
+                emit_pair(P, S, j, bv, __ldg(&P.sf_end[j]), pos, end, cig, n_ops, aln, need, umi, col);
         }
         } while (false);
         // deep feature overlap: drain the stage between rounds so that the next 256 records
