@@ -307,3 +307,28 @@ def test_device_decode_random_records_all_aux_types(gpu_ctx, tmp_path, seed, wan
     assert res is not None, gpu_ctx.decode_fallback_reason
     assert_same_batch(res[0], res[1], host)
     res[0].close()
+
+
+def test_device_decode_empty_and_header_heavy_bams(gpu_ctx, tmp_path):
+    """no records at all; only unplaced records; a header of 6000 contigs spanning several blocks
+    with the records on the last contigs"""
+    from xcltk_b200 import synth
+    tag = [("CB", "Z", "ACGT-1"), ("UB", "Z", "ACGTAC")]
+    cases = {
+        "empty": ([("chr1", 1000)], []),
+        "unplaced": ([("chr1", 1000)], [("u%d" % i, 4, -1, -1, 0, [], "ACGT", tag) for i in range(10)]),
+        "bighdr": ([("contig_with_a_long_name_%06d" % i, 100000 + i) for i in range(6000)],
+                   [("r%d" % i, 0, 5990 + i // 100, 10 * (i % 100), 30, [(0, 40)], "ACGT" * 10, tag) for i in range(900)]),
+    }
+    for name, (refs, recs) in cases.items():
+        p = str(tmp_path / (name + ".bam"))
+        synth.write_bam(p, refs, recs)
+        maps = full_maps([p])
+        if name == "bighdr":
+            maps[0][5995] = -1                       # one contig in the middle of the data is not wanted
+            assert os.path.getsize(p) > 0 and len(refs) * 40 > synth.BGZF_MAX_PAYLOAD
+        host = host_decode([p], maps, "CB", "UB", True)
+        res = gpu_ctx.decode_bams([p], maps, "CB", "UB", True)
+        assert res is not None, (name, gpu_ctx.decode_fallback_reason)
+        assert_same_batch(res[0], res[1], host)
+        res[0].close()

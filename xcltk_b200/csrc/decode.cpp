@@ -710,8 +710,9 @@ extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int6
     if (!fp) return fail(XG_E_IO, std::string("cannot write '") + path + "'");
     fprintf(fp, "%%%%MatrixMarket matrix coordinate integer general\n%%%%\n%d\t%d\t%lld\n", n_rows_out, n_cols,
             (long long)nnz);
-    // slabs of consecutive rows holding about `slab` non-zeros each
-    const int64_t slab = 1 << 21;
+    // slabs of consecutive rows holding about `slab` non-zeros each: a few per thread, so that
+    // small matrices still use every thread and large ones keep the buffers modest
+    const int64_t slab = std::max<int64_t>(1 << 15, std::min<int64_t>(1 << 21, nnz / (4 * (int64_t)n_threads) + 1));
     std::vector<int32_t> cut{0};
     {
         int64_t acc = 0;
@@ -725,19 +726,24 @@ extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int6
         if (cut.back() != n_rows_in) cut.push_back(n_rows_in);
     }
     const size_t n_slabs = cut.size() - 1;
-    bool ok = true;
+    std::atomic<bool> ok(true);
+    struct Text {
+        std::unique_ptr<char[]> p;      // not value-initialised: 36 bytes per entry are reserved
+        size_t n = 0;
+    };
+    std::thread writer;                 // writes group g while group g + 1 is being formatted
     for (size_t s0 = 0; s0 < n_slabs && ok; s0 += (size_t)n_threads) {
         const size_t s1 = std::min(n_slabs, s0 + (size_t)n_threads);
-        std::vector<std::vector<char>> bufs(s1 - s0);
+        auto bufs = std::make_shared<std::vector<Text>>(s1 - s0);
         std::vector<std::thread> th;
         for (size_t s = s0; s < s1; s++)
             th.emplace_back([&, s] {
                 const int32_t r0 = cut[s], r1 = cut[s + 1];
-                std::vector<char> &b = bufs[s - s0];
+                Text &b = (*bufs)[s - s0];
                 int64_t n_ent = 0;
                 for (int32_t r = r0; r < r1; r++) n_ent += row_cnt[r];
-                b.resize((size_t)n_ent * 36 + 16);
-                char *p = b.data();
+                b.p.reset(new char[(size_t)n_ent * 36 + 16]);
+                char *p = b.p.get();
                 for (int32_t r = r0; r < r1; r++)
                     for (int64_t k = row_beg[r]; k < row_beg[r] + row_cnt[r]; k++) {
                         p = put_int(p, (uint32_t)out_row[r]);
@@ -747,12 +753,16 @@ extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int6
                         p = put_int(p, (uint32_t)val[k]);
                         *p++ = '\n';
                     }
-                b.resize((size_t)(p - b.data()));
+                b.n = (size_t)(p - b.p.get());
             });
         for (auto &t : th) t.join();
-        for (auto &b : bufs)
-            if (!b.empty() && fwrite(b.data(), 1, b.size(), fp) != b.size()) ok = false;
+        if (writer.joinable()) writer.join();
+        writer = std::thread([fp, bufs, &ok] {
+            for (auto &b : *bufs)
+                if (b.n && fwrite(b.p.get(), 1, b.n, fp) != b.n) ok = false;
+        });
     }
+    if (writer.joinable()) writer.join();
     if (fclose(fp) != 0) ok = false;
     if (!ok) return fail(XG_E_IO, std::string("short write on '") + path + "'");
     return XG_OK;
