@@ -205,7 +205,29 @@ def cpu_sample(ctx, args, n_sample, n_threads):
     return run, host
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: keep a private handle on it and point fd 1 at stderr,
+    so that nothing a library prints (NCCL's version banner, for one) can get in front of it."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -253,7 +275,7 @@ def main():
                                  "sample": "basefc on %d reads of the C3 generator (oracle/xg_oracle.c, OpenMP "
                                            "over features like the reference's process pool)" % args.cpu_sample},
                 "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     ctx = engine.get_context(local)
@@ -408,7 +430,7 @@ def main():
                            "basefc_host_ms_index_windows_plan_upload_call": [float(x) for x in info["t_fc"][8:13]],
                            "basefc_reads_per_s_kernels_only": args.reads / (
                                float(np.mean([i["t_fc"][3] for i in infos])) * 1e-3)}}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -64,14 +64,24 @@ def _n_gpus():
                                       ("d1_basefc_mini", "defaults"), ("d3_sample_mode", "rdr_ids"),
                                       ("c1_chr22_10x", "baf_all_reg_dup"), ("c1_chr22_10x", "baf_defaults"),
                                       ("d2_baf_mini", "defaults"), ("d3_sample_mode", "baf_p2p1")])
-def test_region_sharded_over_gpus_matches_reference(case, run, tmp_path, monkeypatch):
+@pytest.mark.parametrize("reblock", [False, True])
+def test_region_sharded_over_gpus_matches_reference(case, run, reblock, tmp_path, monkeypatch):
     """Product path sharded by genomic chunks over all GPUs of the box (>= 2), rows merged on
-    the host: still byte-identical to the reference."""
+    the host: still byte-identical to the reference.  reblock: the BAMs in htslib's block layout,
+    so that every GPU decodes them itself with the device decoder."""
     n = _n_gpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     monkeypatch.setenv("XCLTK_B200_GPUS", str(min(n, 4)))
     r = resolve(case, run)
+    if reblock:
+        from xcltk_b200 import synth
+        sams = []
+        for k, p in enumerate(r["sam"]):
+            q = str(tmp_path / ("%d_%s" % (k, os.path.basename(p))))
+            synth.reblock_bam(p, q)
+            sams.append(q)
+        r["sam"] = sams
     out = str(tmp_path / "out")
     if r["kind"] == "basefc":
         from xcltk_b200.rdr.fc.main import fc_wrapper
