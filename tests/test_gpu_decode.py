@@ -194,14 +194,23 @@ def test_device_decode_golden_bams(gpu_ctx, tmp_path, path):
     res[0].close()
 
 
-def test_device_decode_small_staging_chunks(gpu_ctx, tmp_path, monkeypatch):
-    """file -> HBM in many chunks: blocks cut by chunk boundaries are carried over"""
+@pytest.mark.parametrize("window", [None, 300000, 140000])
+def test_device_decode_small_staging_chunks_and_windows(gpu_ctx, tmp_path, monkeypatch, window):
+    """file -> HBM in many chunks: blocks cut by chunk boundaries are carried over; with a small
+    XG_DECODE_WINDOW the file goes through many windows (bounded device memory): the batch grows
+    window by window, runs and sort order are stitched across them; two BAMs share the buffers"""
     monkeypatch.setenv("XG_STAGE_BYTES", str(132 << 10))
+    if window:
+        monkeypatch.setenv("XG_DECODE_WINDOW", str(window))
     p = tenx_bam(tmp_path, 40000, 16, level=1)
+    q = tenx_bam(tmp_path, 15000, 17, "q.bam", level=6)
     assert os.path.getsize(p) > 8 * (132 << 10)
-    maps = full_maps([p])
-    host = host_decode([p], maps, "CB", "UB", True)
-    dev, seen = gpu_ctx.decode_bams([p], maps, "CB", "UB", True)
+    maps = full_maps([p, q])
+    maps[1][1] = -1
+    host = host_decode([p, q], maps, "CB", "UB", True)
+    dev, seen = gpu_ctx.decode_bams([p, q], maps, "CB", "UB", True)
+    if window:
+        assert gpu_ctx.timing()[5] >= 6          # windows
     assert_same_batch(dev, seen, host)
     dev.close()
 

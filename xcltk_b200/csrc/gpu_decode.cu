@@ -395,32 +395,6 @@ __global__ void k_tile_index2(const int2 *pos_end, xg_tile *tiles, int32_t n_til
     }
 }
 
-struct DevBam {
-    std::vector<uint8_t *> slabs;           // inflated bytes; a block lies within one slab
-    BgzfBlockDev *blocks = nullptr;
-    BlkInfo *info = nullptr;
-    int32_t *tid_map = nullptr;
-    unsigned long long *bases = nullptr;    // 3 x n_blocks
-    int32_t n_blocks = 0, n_ref = 0;
-    uint64_t hdr_end = 0, usize = 0;
-    std::vector<BlkInfo> h_info;
-    int64_t n_kept = 0, n_all = 0, cig = 0, seq = 0, n_starts = 0;
-    int32_t max_aln = 0, max_span = 0;
-    xg_ctx *ctx = nullptr;
-    void release() {          // buffers go back to the context's device pool (reused by the next call)
-        for (uint8_t *p : slabs) ctx->dev_put(p);
-        slabs.clear();
-        ctx->dev_put(blocks);
-        ctx->dev_put(info);
-        ctx->dev_put(tid_map);
-        ctx->dev_put(bases);
-        blocks = nullptr;
-        info = nullptr;
-        tid_map = nullptr;
-        bases = nullptr;
-    }
-};
-
 double now_ms();
 bool g_lap_on = false;          // XG_DECODE_TIMING: host-side phase times on stderr
 double g_lap_t = 0;
@@ -435,19 +409,24 @@ double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// ---- file -> HBM -> inflated, pipelined -------------------------------------------------------
+// ---- file -> HBM -> inflated -> records, in windows -----------------------------------------------
 // The compressed file is read straight into two pinned staging buffers (several pread threads
 // per chunk) and copied to the device chunk by chunk on the copy stream; the file is never held
 // in host memory.  The BGZF block index is built from each chunk while it is staged (the
 // unscanned tail of a chunk -- a block cut by the chunk boundary, < 64 KiB + header -- is carried
 // in front of the next one), and the blocks that are complete are inflated on the compute
 // stream as soon as their chunk has landed: disk read, PCIe copy and inflate overlap.
-// Inflated bytes go to slabs sized from the first chunk's compression ratio.
+// A window is a run of chunks whose compressed and inflated bytes fit the window buffers (sized
+// from the free device memory); at the end of a window its blocks are walked and their records are
+// appended to the batch, and the buffers are reused.  Device memory is therefore bounded by the
+// window plus the batch itself, whatever the size of the BAM.
 constexpr size_t STAGE_HEAD = 128u << 10;
-size_t stage_bytes() {          // XG_STAGE_BYTES: tests use small chunks to exercise the carry
-    const char *e = getenv("XG_STAGE_BYTES");
-    const size_t v = e ? (size_t)atoll(e) : (64u << 20);
-    return std::max<size_t>(v, STAGE_HEAD) & ~(size_t)4095;
+size_t env_bytes(const char *name, size_t dflt) {
+    const char *e = getenv(name);
+    return e ? (size_t)atoll(e) : dflt;
+}
+size_t stage_bytes() {          // XG_STAGE_BYTES / XG_DECODE_WINDOW: tests use small values to exercise the carry / windows
+    return std::max<size_t>(env_bytes("XG_STAGE_BYTES", 64u << 20), STAGE_HEAD) & ~(size_t)4095;
 }
 
 bool pread_all(int fd, uint8_t *dst, size_t len, uint64_t off) {
@@ -474,35 +453,249 @@ bool pread_parallel(int fd, uint8_t *dst, size_t len, uint64_t off, int n_thread
     return ok;
 }
 
-// comp: device buffer of csize + 16 bytes.  On success every block's inflate kernel has been
-// queued on ctx->stream; db.{blocks, slabs, n_blocks, usize, hdr_end, n_ref} are set.
-int stream_and_inflate(xg_ctx *ctx, const char *path, int fd, uint64_t csize, uint8_t *comp, size_t cap_blocks,
-                       int *d_bad, DevBam &db, double *t_read) {
+struct Decoder {
+    xg_ctx *ctx = nullptr;
+    int want_seq = 0;
+    const char *cell_tag = nullptr, *umi_tag = nullptr;
+    int *cnt = nullptr;                       // device counters: [0] bad blocks, [2] max aln, [3] max span, [4] starts, [5] keys for the host
+    // window buffers, shared by all BAMs of the call
+    uint8_t *comp = nullptr, *slab = nullptr;
+    size_t comp_cap = 0, slab_cap = 0, blk_cap = 0, tid_cap = 0;
+    BgzfBlockDev *blocks = nullptr;
+    BlkInfo *info = nullptr;
+    unsigned long long *bases = nullptr;      // 3 x blk_cap
+    int32_t *d_tid_map = nullptr;
+    cudaEvent_t ev_win = nullptr;             // the window buffers are free again
+    // the batch under construction (capacities in elements)
+    int2 *pos_end = nullptr;
+    uint32_t *fmq = nullptr, *cig_off = nullptr, *seq_off = nullptr, *cigar = nullptr, *seq = nullptr;
+    ulonglong2 *keys = nullptr;
+    size_t cap_n = 0, cap_cig = 0, cap_seq = 0;
+    int64_t n_total = 0, cig_total = 0, seq_total = 0, n_seen = 0;
+    int32_t max_aln = 0, max_span = 0;
+    std::vector<RunStart> starts;
+    uint64_t comp_all = 0, comp_done = 0;     // compressed bytes of all BAMs / consumed so far (sizes the batch)
+    double t_read = 0, t_stream = 0, t_walk = 0, t_extract = 0, t_alloc = 0;
+    int n_windows = 0;
+
+    template <class T>
+    bool regrow(T *&p, size_t used, size_t want) {      // new buffer of `want` elements holding the first `used`
+        T *q = (T *)ctx->dev_get(want * sizeof(T) + 16);
+        if (!q) return false;
+        if (p && used) cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (p) {
+            cudaStreamSynchronize(ctx->stream);          // the old buffer goes back to the pool
+            ctx->dev_put(p);
+        }
+        p = q;
+        return true;
+    }
+    // room for the records of the window that is about to be extracted
+    bool reserve(int64_t n_need, int64_t cig_need, int64_t seq_need) {
+        const double t0 = now_ms();
+        const double scale = comp_done ? std::max(1.0, (double)comp_all / (double)comp_done) : 1.0;
+        auto target = [&](int64_t need) {
+            // exact when everything has been seen, else what the rest of the input would add (+10 %)
+            return scale <= 1.0 ? (size_t)need + 1 : (size_t)((double)need * scale * 1.1) + 4096;
+        };
+        bool ok = true;
+        if ((size_t)n_need + 1 > cap_n) {
+            const size_t want = target(n_need);
+            ok = ok && regrow(pos_end, (size_t)n_total, want) && regrow(fmq, (size_t)n_total, want) &&
+                 regrow(cig_off, (size_t)n_total, want + 1) && regrow(keys, (size_t)n_total, want);
+            if (want_seq) ok = ok && regrow(seq_off, (size_t)n_total, want);
+            if (ok) cap_n = want;
+        }
+        if (ok && (size_t)cig_need + 1 > cap_cig) {
+            const size_t want = target(cig_need);
+            ok = regrow(cigar, (size_t)cig_total, want);
+            if (ok) cap_cig = want;
+        }
+        if (ok && want_seq && (size_t)seq_need + 1 > cap_seq) {
+            const size_t want = target(seq_need);
+            ok = regrow(seq, (size_t)seq_total, want);
+            if (ok) cap_seq = want;
+        }
+        t_alloc += now_ms() - t0;
+        return ok;
+    }
+    void release_window_buffers() {
+        ctx->dev_put(comp);
+        ctx->dev_put(slab);
+        ctx->dev_put(blocks);
+        ctx->dev_put(info);
+        ctx->dev_put(bases);
+        ctx->dev_put(d_tid_map);
+        comp = slab = nullptr;
+        blocks = nullptr;
+        info = nullptr;
+        bases = nullptr;
+        d_tid_map = nullptr;
+        if (ev_win) cudaEventDestroy(ev_win);
+        ev_win = nullptr;
+    }
+    void release_batch() {
+        void *ps[] = {pos_end, fmq, cig_off, keys, seq_off, cigar, seq};
+        for (void *p : ps) ctx->dev_put(p);
+        pos_end = nullptr;
+        fmq = cig_off = seq_off = cigar = seq = nullptr;
+        keys = nullptr;
+    }
+};
+
+struct BamState {                       // per BAM, across its windows
+    const char *path;
+    int32_t bam_idx, n_ref = 0;
+    uint64_t hdr_end = 0;
+    unsigned long long last_key = 0;
+};
+
+// Walk the window's blocks, append their records to the batch.
+int flush_window(Decoder &D, BamState &B, int32_t nb) {
+    xg_ctx *ctx = D.ctx;
+    cudaStream_t st = ctx->stream;
+    if (nb <= 0) return XG_OK;
+    D.n_windows++;
+    cudaEventRecord(ctx->ev[0], st);
+    k_walk<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(D.blocks, nb, B.hdr_end, D.d_tid_map, B.n_ref, D.want_seq, D.info,
+                                                      D.cnt + 2);
+    cudaEventRecord(ctx->ev[1], st);
+    std::vector<BlkInfo> h_info((size_t)nb);
+    int h_cnt[8];
+    cudaMemcpyAsync(h_cnt, D.cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(h_info.data(), D.info, (size_t)nb * sizeof(BlkInfo), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return ctx->fail(XG_E_CUDA, std::string("device inflate: ") + cudaGetErrorString(e));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    D.t_walk += ms;
+    if (h_cnt[0]) return ctx->fail(XG_E_FORMAT, std::string("BGZF inflate failed (corrupt block) in '") + B.path + "'");
+    std::vector<unsigned long long> bases(3 * (size_t)nb);
+    int64_t kept = 0, cig = 0, seq = 0, n_all = 0, n_starts = 0;
+    for (int32_t b = 0; b < nb; b++) {
+        const BlkInfo &bi = h_info[(size_t)b];
+        if (bi.status == 2) return ctx->fail(XG_E_FORMAT, std::string("corrupt BAM record in '") + B.path + "'");
+        if (bi.status == 3) return ctx->fail(XG_E_FORMAT, std::string("'") + B.path + "' is not coordinate sorted");
+        if (bi.status == 1)
+            return ctx->fail(XG_E_UNSUPPORTED, std::string("records of '") + B.path + "' cross BGZF block boundaries");
+        if (bi.n_all) {
+            if (bi.first_key < B.last_key) return ctx->fail(XG_E_FORMAT, std::string("'") + B.path + "' is not coordinate sorted");
+            B.last_key = bi.last_key;
+        }
+        bases[(size_t)b] = (unsigned long long)(D.n_total + kept);
+        bases[(size_t)nb + b] = (unsigned long long)(D.cig_total + cig);
+        bases[2 * (size_t)nb + b] = (unsigned long long)(D.seq_total + seq);
+        n_all += bi.n_all;
+        kept += bi.n_kept;
+        cig += bi.cig;
+        seq += bi.seq;
+        n_starts += bi.n_starts;
+    }
+    D.max_aln = std::max(D.max_aln, h_cnt[2]);
+    D.max_span = std::max(D.max_span, h_cnt[3]);
+    D.n_seen += n_all;
+    if (D.cig_total + cig >= (1LL << 32) || D.seq_total + seq >= (1LL << 32))
+        return ctx->fail(XG_E_LIMIT, "batch too large for 32-bit stream offsets; decode fewer reads per batch");
+    if (kept > 0) {
+        if (!D.reserve(D.n_total + kept, D.cig_total + cig, D.seq_total + seq))
+            return ctx->fail(XG_E_UNSUPPORTED, "the read batch does not fit the device");
+        RunStart *d_starts = (RunStart *)ctx->dev_get(((size_t)n_starts + 1) * sizeof(RunStart));
+        if (!d_starts) return ctx->fail(XG_E_CUDA, "out of device memory");
+        cudaMemcpyAsync(D.bases, bases.data(), 3 * (size_t)nb * 8, cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(D.cnt + 4, 0, sizeof(int), st);
+        ExtractArgs a;
+        a.blocks = D.blocks;
+        a.info = D.info;
+        a.rec_base = D.bases;
+        a.cig_base = D.bases + nb;
+        a.seq_base = D.bases + 2 * (size_t)nb;
+        a.tid_map = D.d_tid_map;
+        a.n_blocks = nb;
+        a.bam_idx = B.bam_idx;
+        a.hdr_end = B.hdr_end;
+        a.want_seq = D.want_seq;
+        a.has_cell = D.cell_tag != nullptr;
+        a.has_umi = D.umi_tag != nullptr;
+        a.cell_tag = D.cell_tag ? ((uint32_t)(uint8_t)D.cell_tag[0] | ((uint32_t)(uint8_t)D.cell_tag[1] << 8)) : 0;
+        a.umi_tag = D.umi_tag ? ((uint32_t)(uint8_t)D.umi_tag[0] | ((uint32_t)(uint8_t)D.umi_tag[1] << 8)) : 0;
+        a.pos_end = D.pos_end;
+        a.fmq = D.fmq;
+        a.cig_off = D.cig_off;
+        a.seq_off = D.seq_off;
+        a.cigar = D.cigar;
+        a.seq = D.seq;
+        a.keys = D.keys;
+        a.starts = d_starts;
+        a.n_starts = D.cnt + 4;
+        a.n_need_host = D.cnt + 5;
+        cudaEventRecord(ctx->ev[0], st);
+        k_extract<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(a);
+        cudaEventRecord(ctx->ev[1], st);
+        const size_t s0 = D.starts.size();
+        D.starts.resize(s0 + (size_t)n_starts);
+        cudaMemcpyAsync(h_cnt, D.cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
+        if (n_starts) cudaMemcpyAsync(D.starts.data() + s0, d_starts, (size_t)n_starts * sizeof(RunStart), cudaMemcpyDeviceToHost, st);
+        e = cudaStreamSynchronize(st);
+        ctx->dev_put(d_starts);
+        if (e != cudaSuccess) return ctx->fail(XG_E_CUDA, std::string("device decode: ") + cudaGetErrorString(e));
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        D.t_extract += ms;
+        if (h_cnt[4] != (int)n_starts) return ctx->fail(XG_E_CUDA, "device decode: run starts do not add up");
+        if (h_cnt[5])
+            return ctx->fail(XG_E_UNSUPPORTED, "cell / UMI keys need the host intern table (" + std::to_string(h_cnt[5]) +
+                                                   " values are not short ACGTN-/digit strings)");
+        D.n_total += kept;
+        D.cig_total += cig;
+        D.seq_total += seq;
+    }
+    cudaEventRecord(D.ev_win, st);
+    return XG_OK;
+}
+
+// Stream one BAM through the window buffers.
+int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid_map, int32_t tid_map_len) {
+    xg_ctx *ctx = D.ctx;
+    const int fd = open(path, O_RDONLY);
+    struct stat stt;
+    if (fd < 0 || fstat(fd, &stt) != 0) {
+        if (fd >= 0) close(fd);
+        return ctx->fail(XG_E_IO, std::string("cannot open '") + path + "'");
+    }
+    const uint64_t csize = (uint64_t)stt.st_size;
     const size_t STAGE_BYTES = stage_bytes();
     uint8_t *stage[2] = {(uint8_t *)ctx->pinned_get(STAGE_HEAD + STAGE_BYTES), (uint8_t *)ctx->pinned_get(STAGE_HEAD + STAGE_BYTES)};
     cudaEvent_t done[2] = {nullptr, nullptr};
     auto finish = [&](int code, const std::string &msg) {
         cudaStreamSynchronize(ctx->copy_stream);       // staging buffers may still be in flight
+        cudaStreamSynchronize(ctx->stream);
         for (int k = 0; k < 2; k++) {
             if (stage[k]) ctx->pinned_put(stage[k]);
             if (done[k]) cudaEventDestroy(done[k]);
         }
+        close(fd);
         return code ? ctx->fail(code, msg) : XG_OK;
     };
     if (!stage[0] || !stage[1]) return finish(XG_E_NOMEM, "out of pinned host memory for the staging buffers");
     cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
+    if (csize == 0) return finish(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (empty file)");
     const int n_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    BamState B;
+    B.path = path;
+    B.bam_idx = bam_idx;
     uint64_t next_off = 0, uoff = 0;
     const uint8_t *prev_data = nullptr;
-    size_t prev_len = 0, n_blocks = 0;
+    size_t prev_len = 0;
     bool header_done = false;
     xg_dec::Header hdr;
-    std::vector<xg_dec::BgzfBlock> hb;            // the blocks of the current chunk (host descriptors)
+    std::vector<xg_dec::BgzfBlock> hb;            // the blocks completed by the current chunk
     std::vector<BgzfBlockDev> dv;
-    uint8_t *slab = nullptr;
-    size_t slab_cap = 0, slab_used = 0;
-    if (csize == 0) return finish(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (empty file)");
+    // the window being filled
+    uint64_t win_base = 0;                         // file offset of comp[0]
+    size_t win_infl = 0;
+    int32_t win_blocks = 0;
+    bool win_open = false;
+    const double t_loop = now_ms();
     uint64_t k = 0;
     for (uint64_t c0 = 0; c0 < csize; c0 += STAGE_BYTES, k++) {
         const int si = (int)(k & 1);
@@ -513,10 +706,10 @@ int stream_and_inflate(xg_ctx *ctx, const char *path, int fd, uint64_t csize, ui
         if (carry) memcpy(data - carry, prev_data + prev_len - carry, carry);
         const double t0 = now_ms();
         if (!pread_parallel(fd, data, len, c0, n_threads)) return finish(XG_E_IO, std::string("short read on '") + path + "'");
-        *t_read += now_ms() - t0;
-        cudaMemcpyAsync(comp + c0, data, len, cudaMemcpyHostToDevice, ctx->copy_stream);
-        const uint64_t view_end = c0 + len;
+        D.t_read += now_ms() - t0;
+        const uint64_t view_beg = next_off, view_end = c0 + len;
         hb.clear();
+        size_t chunk_infl = 0;
         while (next_off < view_end) {
             const uint8_t *p = data - (c0 - next_off);      // next_off >= c0 - carry
             uint32_t total = 0, hl = 0;
@@ -534,6 +727,7 @@ int stream_and_inflate(xg_ctx *ctx, const char *path, int fd, uint64_t csize, ui
             b.uoff = uoff;
             if (b.isize > 65536) return finish(XG_E_FORMAT, "BGZF block larger than 64 KiB");
             uoff += b.isize;
+            chunk_infl += b.isize;
             hb.push_back(b);
             next_off += total;
         }
@@ -555,168 +749,80 @@ int stream_and_inflate(xg_ctx *ctx, const char *path, int fd, uint64_t csize, ui
                 nb *= 2;
             }
             header_done = true;
+            B.hdr_end = hdr.end_off;
+            B.n_ref = (int32_t)hdr.names.size();
+            if (tid_map_len < B.n_ref) return finish(XG_E_ARG, "tid_map shorter than the BAM's contig list");
+            if ((size_t)B.n_ref + 1 > D.tid_cap) {
+                ctx->dev_put(D.d_tid_map);
+                D.tid_cap = (size_t)B.n_ref + 1;
+                D.d_tid_map = (int32_t *)ctx->dev_get(D.tid_cap * 4);
+                if (!D.d_tid_map) return finish(XG_E_CUDA, "out of device memory");
+            }
+            cudaMemcpyAsync(D.d_tid_map, tid_map, (size_t)B.n_ref * 4, cudaMemcpyHostToDevice, ctx->stream);
         }
-        if (n_blocks + hb.size() > cap_blocks)
-            return finish(XG_E_UNSUPPORTED, std::string("'") + path + "' has unusually small BGZF blocks");
-        // place the chunk's blocks in the slabs, hand their descriptors to the device, inflate
+        // does the chunk fit the open window?
+        if (win_open && ((size_t)(view_end - win_base) > D.comp_cap || win_infl + chunk_infl + 16 > D.slab_cap ||
+                         (size_t)win_blocks + hb.size() > D.blk_cap)) {
+            int rc = flush_window(D, B, win_blocks);
+            if (rc) return finish(rc, ctx->err);
+            win_open = false;
+        }
+        if (!win_open) {
+            // an empty window takes any chunk: grow the buffers if this one alone is too large
+            if (chunk_infl + 16 > D.slab_cap || hb.size() > D.blk_cap) {
+                cudaStreamSynchronize(ctx->stream);
+                if (chunk_infl + 16 > D.slab_cap) {
+                    ctx->dev_put(D.slab);
+                    D.slab_cap = chunk_infl + chunk_infl / 4 + 16;
+                    D.slab = (uint8_t *)ctx->dev_get(D.slab_cap);
+                }
+                if (hb.size() > D.blk_cap) {
+                    ctx->dev_put(D.blocks);
+                    ctx->dev_put(D.info);
+                    ctx->dev_put(D.bases);
+                    D.blk_cap = hb.size() + hb.size() / 4;
+                    D.blocks = (BgzfBlockDev *)ctx->dev_get((D.blk_cap + 1) * sizeof(BgzfBlockDev));
+                    D.info = (BlkInfo *)ctx->dev_get((D.blk_cap + 1) * sizeof(BlkInfo));
+                    D.bases = (unsigned long long *)ctx->dev_get((3 * D.blk_cap + 1) * 8);
+                }
+                if (!D.slab || !D.blocks || !D.info || !D.bases)
+                    return finish(XG_E_UNSUPPORTED, "the inflate window does not fit the device");
+            }
+            win_open = true;
+            win_base = view_beg;       // a fresh window starts at the carried bytes of the cut block
+            win_infl = 0;
+            win_blocks = 0;
+            cudaStreamWaitEvent(ctx->copy_stream, D.ev_win, 0);     // the previous window has left the buffers
+        }
+        const uint64_t up_off = win_blocks == 0 && win_infl == 0 && win_base == view_beg ? view_beg : c0;
+        cudaMemcpyAsync(D.comp + (up_off - win_base), data - (c0 - up_off), (size_t)(view_end - up_off),
+                        cudaMemcpyHostToDevice, ctx->copy_stream);
         dv.resize(hb.size());
         for (size_t i = 0; i < hb.size(); i++) {
-            if (!slab || slab_used + hb[i].isize + 16 > slab_cap) {
-                // what is left of the file at the ratio seen so far (+10%), at least 64 MiB
-                const double ratio = next_off ? (double)uoff / (double)next_off : 4.0;
-                size_t want = (size_t)((double)(csize - std::min<uint64_t>(csize, hb[i].coff)) * ratio * 1.1) + (64u << 20);
-                size_t free_b = 0, total_b = 0;
-                cudaMemGetInfo(&free_b, &total_b);
-                if (want + (2ull << 30) > free_b + ctx->dev_idle_bytes())
-                    return finish(XG_E_UNSUPPORTED, "BAM too large to inflate on this device in one piece");
-                const double ta = now_ms();
-                slab = (uint8_t *)ctx->dev_get(want);
-                ctx->timing[9] += now_ms() - ta;
-                if (!slab) return finish(XG_E_CUDA, "out of device memory for the inflated BAM");
-                db.slabs.push_back(slab);
-                slab_cap = want;
-                slab_used = 0;
-            }
-            dv[i].coff = hb[i].coff;
+            dv[i].coff = hb[i].coff - win_base;
             dv[i].clen = hb[i].clen;
             dv[i].isize = hb[i].isize;
             dv[i].uoff = hb[i].uoff;
-            dv[i].uptr = slab + slab_used;
-            slab_used += hb[i].isize;
+            dv[i].uptr = D.slab + win_infl;
+            win_infl += hb[i].isize;
         }
         if (!dv.empty())
-            cudaMemcpyAsync(db.blocks + n_blocks, dv.data(), dv.size() * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice,
+            cudaMemcpyAsync(D.blocks + win_blocks, dv.data(), dv.size() * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice,
                             ctx->copy_stream);
         cudaEventRecord(done[si], ctx->copy_stream);
         cudaStreamWaitEvent(ctx->stream, done[si], 0);
-        launch_inflate(ctx->stream, comp, db.blocks + n_blocks, (int32_t)dv.size(), d_bad);
-        n_blocks += hb.size();
+        launch_inflate(ctx->stream, D.comp, D.blocks + win_blocks, (int32_t)dv.size(), D.cnt + 0);
+        win_blocks += (int32_t)hb.size();
+        D.comp_done += len;
         prev_data = data;
         prev_len = len;
     }
-    db.n_blocks = (int32_t)n_blocks;
-    db.usize = uoff;
-    db.hdr_end = hdr.end_off;
-    db.n_ref = (int32_t)hdr.names.size();
+    D.t_stream += now_ms() - t_loop;
+    if (win_open) {
+        int rc = flush_window(D, B, win_blocks);
+        if (rc) return finish(rc, ctx->err);
+    }
     return finish(XG_OK, "");
-}
-
-// Stream one BAM's compressed bytes to the device, inflate them and walk the records.  On
-// success db holds the inflated stream and the per-block sizing.
-int inflate_and_walk(xg_ctx *ctx, const char *path, const int32_t *tid_map, int32_t tid_map_len, int want_seq,
-                     int *d_counters, DevBam &db, double *t_read, double *t_h2d, double *t_walk) {
-    const int fd = open(path, O_RDONLY);
-    struct stat stt;
-    if (fd < 0 || fstat(fd, &stt) != 0) {
-        if (fd >= 0) close(fd);
-        return ctx->fail(XG_E_IO, std::string("cannot open '") + path + "'");
-    }
-    const size_t csize = (size_t)stt.st_size;
-    db.ctx = ctx;
-    if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
-        close(fd);
-        return ctx->fail(XG_E_CUDA, "cannot create the copy stream");
-    }
-    size_t free_b = 0, total_b = 0;
-    cudaMemGetInfo(&free_b, &total_b);
-    if (csize + (2ull << 30) > free_b + ctx->dev_idle_bytes()) {
-        close(fd);
-        return ctx->fail(XG_E_UNSUPPORTED, "BAM too large to inflate on this device in one piece");
-    }
-    // htslib fills blocks to ~64 KiB of payload; a file whose blocks average under 1 KiB
-    // compressed is not worth a device pass
-    const size_t cap_blocks = csize / 1024 + 4096;
-    double t_a0 = now_ms();
-    uint8_t *comp = (uint8_t *)ctx->dev_get(csize + 16);
-    db.blocks = (BgzfBlockDev *)ctx->dev_get((cap_blocks + 1) * sizeof(BgzfBlockDev));
-    db.info = (BlkInfo *)ctx->dev_get((cap_blocks + 1) * sizeof(BlkInfo));
-    db.bases = (unsigned long long *)ctx->dev_get((3 * cap_blocks + 1) * 8);
-    ctx->timing[9] += now_ms() - t_a0;
-    auto bail = [&](int code, const std::string &msg) {
-        cudaStreamSynchronize(ctx->stream);
-        ctx->dev_put(comp);
-        db.release();
-        return ctx->fail(code, msg);
-    };
-    if (!comp || !db.blocks || !db.info || !db.bases) {
-        close(fd);
-        return bail(XG_E_CUDA, "out of device memory for the compressed BAM");
-    }
-    cudaStream_t st = ctx->stream;
-    cudaMemsetAsync(d_counters, 0, 8 * sizeof(int), st);
-    cudaEventRecord(ctx->ev[6], st);
-    cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[6], 0);      // comp may be a recycled buffer still in use
-    int rc = stream_and_inflate(ctx, path, fd, csize, comp, cap_blocks, d_counters + 0, db, t_read);
-    close(fd);
-    cudaEventRecord(ctx->ev[7], st);                            // all inflate kernels queued before this
-    if (rc) {
-        const std::string msg = ctx->err;
-        return bail(rc, msg);
-    }
-    lap("stream");
-    if (tid_map_len < db.n_ref) return bail(XG_E_ARG, "tid_map shorter than the BAM's contig list");
-    const size_t nb = (size_t)db.n_blocks;
-    db.tid_map = (int32_t *)ctx->dev_get(((size_t)db.n_ref + 1) * 4);
-    if (!db.tid_map) return bail(XG_E_CUDA, "out of device memory");
-    cudaMemcpyAsync(db.tid_map, tid_map, (size_t)db.n_ref * 4, cudaMemcpyHostToDevice, st);
-    if (nb) {
-        k_walk<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(db.blocks, db.n_blocks, db.hdr_end, db.tid_map, db.n_ref, want_seq,
-                                                          db.info, d_counters + 2);
-    }
-    cudaEventRecord(ctx->ev[4], st);
-    db.h_info.resize(nb);
-    int h_cnt[8];
-    cudaMemcpyAsync(h_cnt, d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
-    if (nb) cudaMemcpyAsync(db.h_info.data(), db.info, nb * sizeof(BlkInfo), cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return bail(XG_E_CUDA, std::string("device inflate: ") + cudaGetErrorString(e));
-    lap("inflate sync");
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]);
-    *t_h2d += ms;                                               // read + copy + inflate, overlapped
-    cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[4]);
-    *t_walk += ms;
-    ctx->dev_put(comp);
-    comp = nullptr;
-    if (h_cnt[0]) return bail(XG_E_FORMAT, std::string("BGZF inflate failed (corrupt block) in '") + path + "'");
-    // per-block checks + sizes
-    std::vector<unsigned long long> bases(3 * nb);
-    unsigned long long last_key = 0;
-    for (size_t b = 0; b < nb; b++) {
-        const BlkInfo &bi = db.h_info[b];
-        if (bi.status == 2) return bail(XG_E_FORMAT, std::string("corrupt BAM record in '") + path + "'");
-        if (bi.status == 3) return bail(XG_E_FORMAT, std::string("'") + path + "' is not coordinate sorted");
-        if (bi.status == 1)
-            return bail(XG_E_UNSUPPORTED, std::string("records of '") + path + "' cross BGZF block boundaries");
-        if (bi.n_all) {
-            if (bi.first_key < last_key) return bail(XG_E_FORMAT, std::string("'") + path + "' is not coordinate sorted");
-            last_key = bi.last_key;
-        }
-        bases[b] = (unsigned long long)db.n_kept;
-        bases[nb + b] = (unsigned long long)db.cig;
-        bases[2 * nb + b] = (unsigned long long)db.seq;
-        db.n_all += bi.n_all;
-        db.n_kept += bi.n_kept;
-        db.cig += bi.cig;
-        db.seq += bi.seq;
-        db.n_starts += bi.n_starts;
-    }
-    db.h_info.clear();
-    db.h_info.shrink_to_fit();
-    // stash the block-local bases; the caller adds the per-BAM offsets in the kernel arguments
-    if (nb) {
-        e = cudaMemcpy(db.bases, bases.data(), 3 * nb * 8, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) return bail(XG_E_CUDA, std::string("device decode: ") + cudaGetErrorString(e));
-    }
-    db.max_aln = h_cnt[2];
-    db.max_span = h_cnt[3];
-    lap("block sizes");
-    return XG_OK;
-}
-
-__global__ void k_add_base(unsigned long long *v, int64_t n, unsigned long long add) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] += add;
 }
 
 }  // namespace
@@ -789,140 +895,93 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     for (double &t : ctx->timing) t = 0;
     g_lap_on = getenv("XG_DECODE_TIMING") != nullptr;
     g_lap_t = t_begin;
-    XG_GET(cnt, int, "gd_counters", 8);
-    std::vector<DevBam> bams((size_t)n_bams);
-    auto release_all = [&] {
-        for (auto &b : bams)
-            if (b.ctx) b.release();
-    };
-    double t_read = 0, t_h2d = 0, t_walk = 0;
-    int64_t n_total = 0, n_seen = 0, cig_total = 0, seq_total = 0, n_starts = 0;
-    int32_t max_aln = 0, max_span = 0;
-    cudaEventRecord(ctx->ev[2], ctx->stream);
+    if (!ctx->copy_stream) XG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    Decoder D;
+    D.ctx = ctx;
+    D.want_seq = want_seq;
+    D.cell_tag = cell_tag;
+    D.umi_tag = umi_tag;
+    D.cnt = (int *)ctx->get("gd_counters", 8 * sizeof(int));
+    if (!D.cnt) return XG_E_CUDA;
+    // window buffers: as large as the largest BAM needs, at most XG_DECODE_WINDOW compressed bytes
+    uint64_t max_csize = 0;
     for (int32_t b = 0; b < n_bams; b++) {
-        int rc = inflate_and_walk(ctx, paths[b], tid_map[b], tid_map_len[b], want_seq, cnt, bams[b], &t_read, &t_h2d, &t_walk);
+        struct stat stt;
+        if (stat(paths[b], &stt) != 0) return ctx->fail(XG_E_IO, std::string("cannot open '") + paths[b] + "'");
+        D.comp_all += (uint64_t)stt.st_size;
+        max_csize = std::max<uint64_t>(max_csize, (uint64_t)stt.st_size);
+    }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t avail = free_b + ctx->dev_idle_bytes();
+    // window: a tenth of the free memory in compressed bytes (the inflated window takes up to 6x that, the
+    // batch the rest), so a BAM up to ~17 GB goes through in one window on an empty B200
+    const size_t stage = stage_bytes();
+    const size_t window = std::max<size_t>(env_bytes("XG_DECODE_WINDOW", std::max<size_t>((size_t)2 << 30, avail / 10)), stage);
+    D.comp_cap = std::max<size_t>(std::min<size_t>((size_t)max_csize, window), stage) + STAGE_HEAD + 16;
+    D.slab_cap = std::max<size_t>(std::min<size_t>(D.comp_cap * 6, avail / 3), 1u << 20);
+    D.blk_cap = D.comp_cap / 1024 + 4096;
+    D.comp = (uint8_t *)ctx->dev_get(D.comp_cap);
+    D.slab = (uint8_t *)ctx->dev_get(D.slab_cap);
+    D.blocks = (BgzfBlockDev *)ctx->dev_get((D.blk_cap + 1) * sizeof(BgzfBlockDev));
+    D.info = (BlkInfo *)ctx->dev_get((D.blk_cap + 1) * sizeof(BlkInfo));
+    D.bases = (unsigned long long *)ctx->dev_get((3 * D.blk_cap + 1) * 8);
+    auto bail = [&](int code, const std::string &msg) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        D.release_window_buffers();
+        D.release_batch();
+        return ctx->fail(code, msg);
+    };
+    if (!D.comp || !D.slab || !D.blocks || !D.info || !D.bases)
+        return bail(XG_E_UNSUPPORTED, "the inflate window does not fit the device");
+    if (cudaEventCreateWithFlags(&D.ev_win, cudaEventDisableTiming) != cudaSuccess) return bail(XG_E_CUDA, "cudaEventCreate");
+    cudaStream_t st = ctx->stream;
+    cudaMemsetAsync(D.cnt, 0, 8 * sizeof(int), st);
+    cudaEventRecord(ctx->ev[2], st);
+    cudaEventRecord(D.ev_win, st);
+    lap("setup");
+    std::vector<int64_t> bam_end((size_t)n_bams, 0);
+    for (int32_t b = 0; b < n_bams; b++) {
+        int rc = decode_bam(D, paths[b], b, tid_map[b], tid_map_len[b]);
         if (rc) {
-            release_all();
-            return rc;
+            const std::string msg = ctx->err;
+            return bail(rc, msg);
         }
-        n_total += bams[b].n_kept;
-        n_seen += bams[b].n_all;
-        cig_total += bams[b].cig;
-        seq_total += bams[b].seq;
-        n_starts += bams[b].n_starts;
-        max_aln = std::max(max_aln, bams[b].max_aln);
-        max_span = std::max(max_span, bams[b].max_span);
+        bam_end[(size_t)b] = D.n_total;
     }
-    lap("inflate+walk");
-    if (cig_total >= (1LL << 32) || seq_total >= (1LL << 32)) {
-        release_all();
-        return ctx->fail(XG_E_LIMIT, "batch too large for 32-bit stream offsets; decode fewer reads per batch");
-    }
+    lap("bams");
+    D.release_window_buffers();
+    const int64_t n_total = D.n_total;
+    if (!D.reserve(n_total, D.cig_total, D.seq_total)) return bail(XG_E_UNSUPPORTED, "the read batch does not fit the device");
     xg_dreads *d = new xg_dreads();
     d->pooled = true;
     d->n_reads = n_total;
-    d->n_cigar = cig_total;
-    d->n_seq_words = seq_total;
-    d->max_aln_len = max_aln;
-    d->max_span = max_span;
+    d->n_cigar = D.cig_total;
+    d->n_seq_words = D.seq_total;
+    d->max_aln_len = D.max_aln;
+    d->max_span = D.max_span;
+    d->pos_end = D.pos_end;
+    d->fmq = D.fmq;
+    d->cig_off = D.cig_off;
+    d->keys = D.keys;
+    d->cigar = D.cigar;
+    d->seq_off = D.seq_off;
+    d->seq = D.seq;
     auto fail_free = [&](int code, const std::string &msg) {
-        release_all();
+        cudaStreamSynchronize(ctx->stream);
         xg_dreads_free(ctx, d);
         return ctx->fail(code, msg);
     };
-    const size_t n = (size_t)n_total;
-    d->pos_end = (int2 *)ctx->dev_get(n * 8 + 16);
-    d->fmq = (uint32_t *)ctx->dev_get(n * 4 + 16);
-    d->cig_off = (uint32_t *)ctx->dev_get((n + 1) * 4 + 16);
-    d->keys = (ulonglong2 *)ctx->dev_get(n * 16 + 16);
-    d->cigar = (uint32_t *)ctx->dev_get((size_t)cig_total * 4 + 16);
-    if (want_seq) {
-        d->seq_off = (uint32_t *)ctx->dev_get(n * 4 + 16);
-        d->seq = (uint32_t *)ctx->dev_get((size_t)seq_total * 4 + 16);
-    }
-    RunStart *d_starts = nullptr;
-    if (!d->pos_end || !d->fmq || !d->cig_off || !d->keys || !d->cigar || (want_seq && (!d->seq_off || !d->seq)) ||
-        cudaMalloc(&d_starts, ((size_t)n_starts + 1) * sizeof(RunStart)) != cudaSuccess) {
-        cudaGetLastError();
-        return fail_free(XG_E_CUDA, "out of device memory for the read batch");
-    }
-    lap("alloc");
-    cudaStream_t st = ctx->stream;
-    cudaMemsetAsync(cnt, 0, 8 * sizeof(int), st);
-    cudaEventRecord(ctx->ev[0], st);
-    int64_t rec0 = 0, cig0 = 0, seq0 = 0;
-    for (int32_t b = 0; b < n_bams; b++) {
-        DevBam &db = bams[b];
-        const int64_t nb = db.n_blocks;
-        if (nb && db.n_kept) {
-            if (rec0) k_add_base<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(db.bases, nb, (unsigned long long)rec0);
-            if (cig0) k_add_base<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(db.bases + nb, nb, (unsigned long long)cig0);
-            if (seq0) k_add_base<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(db.bases + 2 * nb, nb, (unsigned long long)seq0);
-            ExtractArgs a;
-            a.blocks = db.blocks;
-            a.info = db.info;
-            a.rec_base = db.bases;
-            a.cig_base = db.bases + nb;
-            a.seq_base = db.bases + 2 * nb;
-            a.tid_map = db.tid_map;
-            a.n_blocks = db.n_blocks;
-            a.bam_idx = b;
-            a.hdr_end = db.hdr_end;
-            a.want_seq = want_seq;
-            a.has_cell = cell_tag != nullptr;
-            a.has_umi = umi_tag != nullptr;
-            a.cell_tag = cell_tag ? ((uint32_t)(uint8_t)cell_tag[0] | ((uint32_t)(uint8_t)cell_tag[1] << 8)) : 0;
-            a.umi_tag = umi_tag ? ((uint32_t)(uint8_t)umi_tag[0] | ((uint32_t)(uint8_t)umi_tag[1] << 8)) : 0;
-            a.pos_end = d->pos_end;
-            a.fmq = d->fmq;
-            a.cig_off = d->cig_off;
-            a.seq_off = d->seq_off;
-            a.cigar = d->cigar;
-            a.seq = d->seq;
-            a.keys = d->keys;
-            a.starts = d_starts;
-            a.n_starts = cnt + 4;
-            a.n_need_host = cnt + 5;
-            k_extract<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(a);
-        }
-        rec0 += db.n_kept;
-        cig0 += db.cig;
-        seq0 += db.seq;
-    }
-    cudaEventRecord(ctx->ev[1], st);
-    const uint32_t sentinel = (uint32_t)cig_total;
-    cudaMemcpyAsync(d->cig_off + n, &sentinel, 4, cudaMemcpyHostToDevice, st);
-    int h_cnt[8];
-    cudaMemcpyAsync(h_cnt, cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    lap("extract");
-    release_all();
-    if (e != cudaSuccess) {
-        cudaFree(d_starts);
-        return fail_free(XG_E_CUDA, std::string("device decode: ") + cudaGetErrorString(e));
-    }
-    {
-        float xms = 0;
-        cudaEventElapsedTime(&xms, ctx->ev[0], ctx->ev[1]);
-        ctx->timing[3] = xms;               // extract kernels
-    }
-    if (h_cnt[5]) {
-        cudaFree(d_starts);
-        return fail_free(XG_E_UNSUPPORTED, "cell / UMI keys need the host intern table (" + std::to_string(h_cnt[5]) +
-                                               " values are not short ACGTN-/digit strings)");
-    }
-    std::vector<RunStart> starts((size_t)h_cnt[4]);
-    if (!starts.empty()) cudaMemcpy(starts.data(), d_starts, starts.size() * sizeof(RunStart), cudaMemcpyDeviceToHost);
-    cudaFree(d_starts);
-    lap("release");
+    const uint32_t sentinel = (uint32_t)D.cig_total;
+    cudaMemcpyAsync(d->cig_off + n_total, &sentinel, 4, cudaMemcpyHostToDevice, st);
+    std::vector<RunStart> &starts = D.starts;
     std::sort(starts.begin(), starts.end(), [](const RunStart &x, const RunStart &y) { return x.rec < y.rec; });
     // runs: maximal stretches of kept records of one contig of one BAM (decode.cpp's run_tid)
-    int64_t bam_end = 0;
     size_t si = 0;
     for (int32_t b = 0; b < n_bams; b++) {
-        bam_end += bams[b].n_kept;
         int32_t run_tid = -2;
-        for (; si < starts.size() && starts[si].rec < bam_end; si++) {
+        for (; si < starts.size() && starts[si].rec < bam_end[(size_t)b]; si++) {
             if (starts[si].tid == run_tid) continue;
             run_tid = starts[si].tid;
             if (!d->h_runs.empty() && d->h_runs.back().rec_end < 0) d->h_runs.back().rec_end = starts[si].rec;
@@ -933,7 +992,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
             r.rec_end = -1;
             d->h_runs.push_back(r);
         }
-        if (!d->h_runs.empty() && d->h_runs.back().rec_end < 0) d->h_runs.back().rec_end = bam_end;
+        if (!d->h_runs.empty() && d->h_runs.back().rec_end < 0) d->h_runs.back().rec_end = bam_end[(size_t)b];
     }
     for (size_t r = 0; r < d->h_runs.size(); r++)
         for (int64_t s = d->h_runs[r].rec_beg; s < d->h_runs[r].rec_end; s += XG_TILE) {
@@ -957,7 +1016,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
         cudaMemcpyAsync(d->h_tiles.data(), d->tiles, (size_t)d->n_tiles * sizeof(xg_tile), cudaMemcpyDeviceToHost, st);
     }
     cudaEventRecord(ctx->ev[3], st);
-    e = cudaStreamSynchronize(st);
+    cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail_free(XG_E_CUDA, std::string("device decode: ") + cudaGetErrorString(e));
     lap("runs+tiles");
     int rc = xg_make_tile_pmax(ctx, d);
@@ -966,20 +1025,24 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
         return rc;
     }
     lap("pmax");
-    d->bytes = (int64_t)(n * 32 + (size_t)cig_total * 4 + (size_t)seq_total * 4 + (want_seq ? n * 4 : 0));
+    const size_t n = (size_t)n_total;
+    d->bytes = (int64_t)(n * 32 + (size_t)D.cig_total * 4 + (size_t)D.seq_total * 4 + (want_seq ? n * 4 : 0));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
-    ctx->timing[0] = ms;                    // device span incl. H2D of the compressed files
-    ctx->timing[2] = t_walk;                // walk kernels
-    ctx->timing[4] = t_h2d;                 // file read + H2D of the compressed bytes + inflate, pipelined
-    ctx->timing[8] = t_read;                // file read + block scan on the host
+    ctx->timing[0] = ms;                    // device span of the call
+    ctx->timing[2] = D.t_walk;              // walk kernels
+    ctx->timing[3] = D.t_extract;           // extract kernels
+    ctx->timing[4] = D.t_stream;            // file read + H2D + inflate (pipelined) incl. the windows' walk / extract
+    ctx->timing[5] = D.n_windows;
+    ctx->timing[8] = D.t_read;              // time inside pread
+    ctx->timing[9] = D.t_alloc;             // growing the batch
     {
         const double t_f0 = now_ms();
         ctx->dev_trim(8ull << 30);          // keep small inputs' buffers for the next call, give the rest back
         ctx->timing[10] = now_ms() - t_f0;
     }
     ctx->timing[12] = now_ms() - t_begin;   // whole call
-    if (n_records_seen) *n_records_seen = n_seen;
+    if (n_records_seen) *n_records_seen = D.n_seen;
     *out = d;
     return XG_OK;
 }
