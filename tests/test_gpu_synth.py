@@ -222,3 +222,25 @@ def test_basefc_row_segments_equal_sorted_result(gpu_ctx, fc_batch, tmp_path):
     out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
     lib.write_mtx_rows(str(tmp_path / "b.mtx"), seg, out_row, int(emitted.sum()))
     assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "b.mtx"), "rb").read()
+
+
+def test_basefc_row_segments_degenerate_inputs(gpu_ctx, fc_batch):
+    """no features; only features that fetch nothing (unknown contig, empty window): empty rows"""
+    w, p = fc_batch, gpu_params(Conf())
+    z = np.zeros(0, dtype=np.int32)
+    seg = gpu_ctx.basefc(w.dreads, z, z, z, w.cell_keys, 2000, p, segments=True)
+    assert seg.nnz == 0 and len(seg.row_cnt) == 0
+    gid = np.array([-1, int(w.gid[0]), -1], dtype=np.int32)
+    beg = np.array([0, 5, 10], dtype=np.int32)
+    end = np.array([100, 5, 20], dtype=np.int32)
+    seg = gpu_ctx.basefc(w.dreads, gid, beg, end, w.cell_keys, 2000, p, segments=True)
+    ref = gpu_ctx.basefc(w.dreads, gid, beg, end, w.cell_keys, 2000, p)
+    assert seg.nnz == len(ref[2]) == 0 and list(seg.row_cnt) == [0, 0, 0]
+    # one real feature between two empty ones
+    gid = np.array([-1, int(w.gid[5]), -1], dtype=np.int32)
+    beg = np.array([0, int(w.beg[5]), 10], dtype=np.int32)
+    end = np.array([100, int(w.end[5]), 20], dtype=np.int32)
+    seg = gpu_ctx.basefc(w.dreads, gid, beg, end, w.cell_keys, 2000, p, segments=True)
+    ref = [np.array(x) for x in gpu_ctx.basefc(w.dreads, gid, beg, end, w.cell_keys, 2000, p)[:3]]
+    for a, b in zip(seg.to_sorted(), ref):
+        assert np.array_equal(a, b)

@@ -82,15 +82,12 @@ void launch_inflate_s(cudaStream_t st, const uint8_t *comp, const BgzfBlockDev *
                                                                                               n_bad);
 }
 
+// One warp per BGZF block.  Sub-warp groups (2-8 blocks per warp, inflate_group<16/8/4>) were measured
+// slower: 102 / 156 / 267 ms against 76 ms on the same file -- divergent decoders serialise.
 inline void launch_inflate(cudaStream_t st, const uint8_t *comp, const BgzfBlockDev *blocks, int32_t n_blocks,
                            int *n_bad) {
     if (n_blocks <= 0) return;
-    static const int S = [] {
-        const char *e = getenv("XG_INFLATE_S");
-        return e ? atoi(e) : 32;
-    }();
-    if (S == 16) launch_inflate_s<16>(st, comp, blocks, n_blocks, n_bad);     // experiments only: slower
-    else launch_inflate_s<32>(st, comp, blocks, n_blocks, n_bad);
+    launch_inflate_s<32>(st, comp, blocks, n_blocks, n_bad);
 }
 
 __device__ __forceinline__ unsigned long long sort_key(int32_t tid, int32_t pos) {
