@@ -156,7 +156,7 @@ class Batch(object):
         w2 = time.perf_counter()
         t_p = ctx.timing()
         launches += int(t_p[2])
-        keep = (totals.sum(axis=1) >= 1).astype(np.uint8)        # min_count=1, min_maf=0 (pipeline values)
+        keep = ((totals[:, 0] + totals[:, 1] + totals[:, 2] + totals[:, 3] + totals[:, 4]) >= 1).astype(np.uint8)   # min_count=1, min_maf=0 (pipeline values)
         ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, keep, True)
         w3 = time.perf_counter()
         t_c = ctx.timing()
@@ -180,7 +180,7 @@ class Batch(object):
         d_bf = ctx.map_reads(self.h_baf)          # zero-copy: 8 B/read over PCIe, rest on demand
         totals, st = ctx.baf_pileup(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
         ctx.timing_pairs = ctx.timing()[6]            # (read, SNP) pairs: records fetched on demand
-        keep = (totals.sum(axis=1) >= 1).astype(np.uint8)
+        keep = ((totals[:, 0] + totals[:, 1] + totals[:, 2] + totals[:, 3] + totals[:, 4]) >= 1).astype(np.uint8)
         ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, keep, True)
         st.close()
         d_bf.close()
