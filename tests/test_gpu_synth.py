@@ -244,3 +244,47 @@ def test_basefc_row_segments_degenerate_inputs(gpu_ctx, fc_batch):
     ref = [np.array(x) for x in gpu_ctx.basefc(w.dreads, gid, beg, end, w.cell_keys, 2000, p)[:3]]
     for a, b in zip(seg.to_sorted(), ref):
         assert np.array_equal(a, b)
+
+
+def test_baf_full_size_properties(gpu_ctx):
+    """Bench-scale baf batch (config 2 shape: 50M reads, 5 000 cells, 200 000 SNPs): the run is
+    reproducible; AD entries sit on DP entries and never exceed them; counting the regions in two halves and stacking the rows equals the whole
+    run; dropping every SNP empties the matrices."""
+    from xcltk_b200 import workload
+    n = int(float(os.environ.get("XG_TEST_BIG_READS", "5e7")))
+    b = workload.make_baf_workload(gpu_ctx, n, 5000, 200000, seed=17)
+    p = gpu_params(Conf(min_include=0), False)
+
+    def run(reg_ptr, reg_snp, keep=None):
+        totals, st = gpu_ctx.baf_pileup(b.dreads, b.snp_gid, b.snp_pos, b.cell_keys, 5000, p)
+        k = ((totals[:, :5].sum(axis=1) >= 1).astype(np.uint8)) if keep is None else keep
+        out = gpu_ctx.baf_count(st, reg_ptr, reg_snp, b.hap_of, k, True)
+        st.close()
+        return totals, [[np.array(x) for x in m[:3]] for m in out]
+
+    totals, (ad, dp, oth) = run(b.reg_ptr, b.reg_snp)
+    totals2, (ad2, dp2, oth2) = run(b.reg_ptr, b.reg_snp)
+    assert np.array_equal(totals, totals2)
+    for x, y in zip((ad, dp, oth), (ad2, dp2, oth2)):
+        assert all(np.array_equal(u, v) for u, v in zip(x, y))
+    assert len(dp[2]) > 1000 and int(totals.sum()) > 0       # (regions overlap: a SNP counts in each of them)
+    n_cols = 5000
+    key_dp = dp[0].astype(np.int64) * n_cols + dp[1]
+    key_ad = ad[0].astype(np.int64) * n_cols + ad[1]
+    pos = np.searchsorted(key_dp, key_ad)
+    assert np.all(pos < len(key_dp)) and np.array_equal(key_dp[pos], key_ad)      # AD ⊂ DP
+    assert np.all(ad[2] <= dp[2][pos]) and np.all(ad[2] > 0) and np.all(dp[2] > 0)
+    # two halves of the regions, rows stacked
+    n_reg = len(b.reg_ptr) - 1
+    h = n_reg // 2
+    parts = []
+    for lo, hi in ((0, h), (h, n_reg)):
+        rp = (b.reg_ptr[lo:hi + 1] - b.reg_ptr[lo]).astype(np.int64)
+        rs = b.reg_snp[b.reg_ptr[lo]:b.reg_ptr[hi]]
+        _, mats = run(rp, rs)
+        parts.append([(m[0] + lo, m[1], m[2]) for m in mats])
+    for k, whole in enumerate((ad, dp, oth)):
+        for j in range(3):
+            assert np.array_equal(np.concatenate([parts[0][k][j], parts[1][k][j]]), whole[j])
+    _, (ad0, dp0, oth0) = run(b.reg_ptr, b.reg_snp, keep=np.zeros(len(b.snp_gid), dtype=np.uint8))
+    assert len(ad0[2]) == len(dp0[2]) == len(oth0[2]) == 0
