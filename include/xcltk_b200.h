@@ -160,15 +160,18 @@ int xg_map_reads(xg_ctx *ctx, const xg_reads *host, xg_dreads **out);
 /* Device decoder: BGZF inflate + BAM record parse on the GPU; the compressed files cross PCIe
  * once and the batch is left in HBM, array for array what xg_decode_bams + xg_upload_reads
  * produce.  Replaces pysam.AlignmentFile + fetch() (xcltk/rdr/fc/core.py:75,100;
- * xcltk/baf/fc/core.py:60,99).  Arguments as xg_decode_bams.  Returns XG_E_UNSUPPORTED -- and
- * the caller falls back to xg_decode_bams + xg_upload_reads -- when a BAM's records cross BGZF
- * block boundaries (htslib-written files never do, unless a record exceeds 64 KiB), when a
- * cell / UMI value needs the host intern table (query-name keys, non-ACGTN-/digit strings,
- * numeric tags), or when the inflated file does not fit the device.  n_records_seen may be NULL. */
+ * xcltk/baf/fc/core.py:60,99).  Arguments as xg_decode_bams; the files go through the device in
+ * windows, so device memory is bounded by a window plus the batch.  Cell / UMI values that do
+ * not pack into 63 bits (query names with `--UMItag None`, free-text barcodes, integer tags) are
+ * gathered on the device and interned by `ks` on the host; with ks == NULL such input is declined.
+ * Returns XG_E_UNSUPPORTED -- and the caller falls back to xg_decode_bams + xg_upload_reads --
+ * when a BAM's records cross BGZF block boundaries (htslib-written files never do, unless a
+ * record exceeds 64 KiB), for float-typed UMI tags, or when a window or the batch does not fit
+ * the device.  n_records_seen may be NULL.                                                    */
 int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
                           const int32_t *const *tid_map, const int32_t *tid_map_len,
                           const char *cell_tag, const char *umi_tag, int32_t want_seq,
-                          xg_dreads **out, int64_t *n_records_seen);
+                          xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen);
 /* Validation entry: inflate a whole BGZF file on the device into out[0, cap).  With out == NULL
  * (or cap too small) only *n_out, the inflated size, is set.                               */
 int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t cap, int64_t *n_out);

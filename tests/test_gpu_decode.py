@@ -15,10 +15,11 @@ from util import GOLD
 pytestmark = pytest.mark.gpu
 
 
-def host_decode(paths, maps, cell_tag, umi_tag, want_seq):
+def host_decode(paths, maps, cell_tag, umi_tag, want_seq, with_ks=False):
     from xcltk_b200 import lib
     ks = lib.KeySpace()
-    return lib.decode_bams(paths, maps, cell_tag, umi_tag, want_seq, ks, 4)
+    h = lib.decode_bams(paths, maps, cell_tag, umi_tag, want_seq, ks, 4)
+    return (h, ks) if with_ks else h
 
 
 def full_maps(paths):
@@ -26,13 +27,31 @@ def full_maps(paths):
     return [np.arange(len(lib.bam_references(p)), dtype=np.int32) for p in paths]
 
 
-def assert_same_batch(dev, seen, host):
+def assert_same_keys(got, exp, ks_got, ks_exp):
+    """packed / special keys must be identical; interned ones (bit 63, opaque ids of two
+    keyspaces) must name the same strings"""
+    got, exp = got.reshape(-1), exp.reshape(-1)
+    special = np.uint64(0xFFFFFFFFFFFFFFFE)
+    ig = ((got >> np.uint64(63)) == 1) & (got < special)
+    ie = ((exp >> np.uint64(63)) == 1) & (exp < special)
+    assert np.array_equal(ig, ie)
+    assert np.array_equal(got[~ig], exp[~ie])
+    if ig.any():
+        assert ks_got is not None and ks_exp is not None
+        pairs = np.unique(np.stack([got[ig], exp[ie]], axis=1), axis=0)
+        assert len(np.unique(pairs[:, 0])) == len(pairs) == len(np.unique(pairs[:, 1]))     # a bijection
+        for a, b in pairs[:: max(1, len(pairs) // 3000)]:
+            assert ks_got.decode(int(a)) == ks_exp.decode(int(b))
+
+
+def assert_same_batch(dev, seen, host, ks_dev=None, ks_host=None):
     got = dev.download()
     info = dev.info()
     assert info["n_reads"] == host.n == got.n
     assert seen == host.n_records_seen
     assert (info["max_aln_len"], info["max_span"]) == (host.max_aln_len, host.max_span)
-    for name in ("pos_end", "fmq", "cig_off", "keys", "cigar"):
+    assert_same_keys(got.keys, host.keys, ks_dev, ks_host)
+    for name in ("pos_end", "fmq", "cig_off", "cigar"):
         assert np.array_equal(getattr(got, name), getattr(host, name)), name
     assert got.has_seq == host.has_seq
     if host.has_seq:
@@ -132,8 +151,8 @@ def test_device_decode_refuses_what_needs_the_host(gpu_ctx, tmp_path):
     assert gpu_ctx.decode_bams([p], maps, "CB", "UB", True) is None
     assert "block boundaries" in gpu_ctx.decode_fallback_reason
     q = tenx_bam(tmp_path, 5000, 14, "q.bam")
-    assert gpu_ctx.decode_bams([q], maps, "CB", None, True) is None   # query-name keys are interned
-    assert "intern" in gpu_ctx.decode_fallback_reason
+    assert gpu_ctx.decode_bams([q], maps, "CB", None, True) is None   # query-name keys need a keyspace
+    assert "keyspace" in gpu_ctx.decode_fallback_reason
     # ... and the host decoder reads both
     assert host_decode([p], maps, "CB", "UB", True).n == host_decode([q], maps, "CB", None, True).n
     with pytest.raises(lib.XgError):
@@ -187,8 +206,8 @@ def test_device_decode_golden_bams(gpu_ctx, tmp_path, path):
     with gzip.open(path, "rb") as f1, gzip.open(p, "rb") as f2:
         assert f1.read() == f2.read()
     res = gpu_ctx.decode_bams([p], maps, "CB", "UB", True)
-    if res is None:                                    # sample-mode BAMs may carry free-text tags
-        assert "intern" in gpu_ctx.decode_fallback_reason
+    if res is None:                                    # hand-built BAMs may carry free-text tags
+        assert "keyspace" in gpu_ctx.decode_fallback_reason
         return
     assert_same_batch(res[0], res[1], host)
     res[0].close()
@@ -341,3 +360,68 @@ def test_device_decode_empty_and_header_heavy_bams(gpu_ctx, tmp_path):
         assert res is not None, (name, gpu_ctx.decode_fallback_reason)
         assert_same_batch(res[0], res[1], host)
         res[0].close()
+
+
+def _odd_key_records(seed, n):
+    """values that do not pack into 63 bits: free-text and long barcodes, integer UMI tags
+    (zero is falsy -> EMPTY), one-character tags outside ACGTN-, and repeats of all of them"""
+    rng = random.Random(seed)
+    cbs = ["cell_%d" % i for i in range(40)] + ["ACGT" * 6 + "-1", "acgtacgt", "ACGT", "", "N-1"]
+    recs, pos = [], 0
+    for i in range(n):
+        pos += rng.randrange(0, 30)
+        tags = []
+        r = rng.random()
+        if r < 0.8:
+            tags.append(("CB", "Z", rng.choice(cbs)))
+        elif r < 0.9:
+            tags.append(("CB", "A", rng.choice("QxA!")))
+        r = rng.random()
+        if r < 0.4:
+            tags.append(("UB", "Z", rng.choice(["umi%d" % rng.randrange(200), "ACGTACGTAC", "ACGT" * 8, ""])))
+        elif r < 0.8:
+            typ = rng.choice("cCsSiI")
+            lo, hi = {"c": (-128, 127), "C": (0, 255), "s": (-32768, 32767), "S": (0, 65535),
+                      "i": (-2 ** 31, 2 ** 31 - 1), "I": (0, 2 ** 32 - 1)}[typ]
+            tags.append(("UB", typ, rng.choice([0, 1, -1, 7, lo, hi, rng.randint(lo, hi)]) if lo < 0 else
+                         rng.choice([0, 1, 7, hi, rng.randint(lo, hi)])))
+        elif r < 0.9:
+            tags.append(("UB", "A", rng.choice("zZ#A")))
+        recs.append(("read:%d:%s" % (i // 2, "x" * rng.randrange(0, 12)), rng.choice([0, 16, 99, 147]), 0, pos, 30,
+                     [(0, 50)], "ACGTN" * 10, tags))
+    return recs
+
+
+@pytest.mark.parametrize("cell_tag,umi_tag", [("CB", "UB"), ("CB", None), (None, None), (None, "UB")])
+def test_device_decode_interns_odd_keys_through_the_keyspace(gpu_ctx, tmp_path, monkeypatch, cell_tag, umi_tag):
+    """free-text barcodes, integer UMI tags, query names (--UMItag None): gathered on the device,
+    interned by the host keyspace, patched into the batch -- same strings as the host decoder,
+    also across windows and two BAMs"""
+    from xcltk_b200 import lib, synth
+    monkeypatch.setenv("XG_STAGE_BYTES", str(132 << 10))
+    monkeypatch.setenv("XG_DECODE_WINDOW", str(200000))
+    paths = []
+    for k, n in enumerate((9000, 4000)):
+        p = str(tmp_path / ("odd%d.bam" % k))
+        synth.write_bam(p, [("chr1", 10000000)], _odd_key_records(20 + k, n), level=1)
+        paths.append(p)
+    maps = full_maps(paths)
+    host, ks_host = host_decode(paths, maps, cell_tag, umi_tag, True, with_ks=True)
+    ks = lib.KeySpace()
+    res = gpu_ctx.decode_bams(paths, maps, cell_tag, umi_tag, True, ks)
+    assert res is not None, gpu_ctx.decode_fallback_reason
+    assert ks.n_interned() == ks_host.n_interned() > (0 if (cell_tag, umi_tag) == (None, "UB") else 40)
+    assert gpu_ctx.timing()[6] > 0                       # values that went through the keyspace
+    assert_same_batch(res[0], res[1], host, ks, ks_host)
+    res[0].close()
+
+
+def test_device_decode_leaves_float_umis_to_the_host(gpu_ctx, tmp_path):
+    from xcltk_b200 import lib, synth
+    recs = [("r%d" % i, 0, 0, 10 * i, 30, [(0, 50)], "A" * 50, [("CB", "Z", "ACGT"), ("UB", "f", 1.5 + i)]) for i in range(50)]
+    p = str(tmp_path / "f.bam")
+    synth.write_bam(p, [("chr1", 100000)], recs)
+    maps = full_maps([p])
+    assert gpu_ctx.decode_bams([p], maps, "CB", "UB", True, lib.KeySpace()) is None
+    assert "float" in gpu_ctx.decode_fallback_reason
+    assert host_decode([p], maps, "CB", "UB", True).n == 50

@@ -27,6 +27,7 @@
 #include "bamfile.hpp"
 #include "common.cuh"
 #include "inflate.cuh"
+#include "keys.hpp"
 #include "owner.hpp"
 
 namespace {
@@ -246,16 +247,99 @@ __device__ __forceinline__ bool pack_key(const uint8_t *s, const uint8_t *end, b
     return true;
 }
 
-// decode.cpp: tag_key() for the value at `t` (type byte first)
-__device__ __forceinline__ bool tag_key_dev(const uint8_t *t, const uint8_t *end, bool is_cell, unsigned long long *out) {
-    const uint32_t typ = t[0];
-    if (typ == 'Z' || typ == 'H') return pack_key(t + 1, end, true, 0, out);
-    if (typ == 'A') return pack_key(t + 1, end, false, 1, out);
-    if (is_cell) {
-        *out = XG_KEY_NOMATCH;
-        return true;
+// What a cell / UMI value turns into.  status 0: `key` is final (packed, NONE, EMPTY, NOMATCH);
+// 1: the value needs the host's intern table -- the string [s, s + n), or for an integer UMI tag
+// the spelling "\x01<decimal>" of decode.cpp's tag_key() (n counts its bytes); 2: a value this
+// decoder does not spell (float UMI tag).
+struct KeyRef {
+    int status;
+    unsigned long long key;
+    const uint8_t *s;
+    uint32_t n;
+    long long iv;
+    bool is_int;
+};
+
+__device__ __forceinline__ uint32_t dec_digits(unsigned long long v) {
+    uint32_t d = 1;
+    while (v >= 10) {
+        v /= 10;
+        d++;
     }
-    return false;    // numeric UMI: interned under a type-tagged spelling on the host
+    return d;
+}
+
+// decode.cpp: tag_key() for the value at `t` (type byte first)
+__device__ __forceinline__ KeyRef key_ref_tag(const uint8_t *t, const uint8_t *end, bool is_cell) {
+    KeyRef k;
+    k.status = 0;
+    k.key = XG_KEY_NOMATCH;
+    k.s = nullptr;
+    k.n = 0;
+    k.iv = 0;
+    k.is_int = false;
+    const uint32_t typ = t[0];
+    const uint8_t *v = t + 1;
+    if (typ == 'Z' || typ == 'H' || typ == 'A') {
+        uint32_t n = 1;
+        if (typ != 'A') {
+            n = 0;
+            while (v + n < end && v[n]) n++;
+        }
+        if (pack_key(v, end, false, (int)n, &k.key)) return k;
+        k.status = 1;
+        k.s = v;
+        k.n = n;
+        return k;
+    }
+    if (is_cell) return k;                      // not a string: never equals a barcode
+    switch (typ) {
+        case 'c': k.iv = (signed char)v[0]; break;
+        case 'C': k.iv = v[0]; break;
+        case 's': k.iv = (short)ld16u(v); break;
+        case 'S': k.iv = (long long)ld16u(v); break;
+        case 'i': k.iv = (int)ld32u(v); break;
+        case 'I': k.iv = (long long)ld32u(v); break;
+        case 'f':
+            if (ld32u(v) == 0u || ld32u(v) == 0x80000000u) k.key = XG_KEY_EMPTY;      // 0.0f / -0.0f: falsy
+            else k.status = 2;
+            return k;
+        default: return k;                      // NOMATCH
+    }
+    if (k.iv == 0) {
+        k.key = XG_KEY_EMPTY;                   // `if umi:` -- a zero is falsy
+        return k;
+    }
+    k.status = 1;
+    k.is_int = true;
+    k.n = 1 + (k.iv < 0 ? 1u : 0u) + dec_digits(k.iv < 0 ? (unsigned long long)(-k.iv) : (unsigned long long)k.iv);
+    return k;
+}
+
+__device__ __forceinline__ KeyRef key_ref_name(const uint8_t *r, const uint8_t *end, uint32_t l_name) {
+    KeyRef k;
+    k.status = 0;
+    k.s = r + 36;
+    k.n = l_name ? l_name - 1 : 0;
+    k.iv = 0;
+    k.is_int = false;
+    if (!pack_key(k.s, end, false, (int)k.n, &k.key)) k.status = 1;
+    return k;
+}
+
+__device__ __forceinline__ void key_ref_write(const KeyRef &k, uint8_t *dst) {
+    if (!k.is_int) {
+        for (uint32_t i = 0; i < k.n; i++) dst[i] = k.s[i];
+        return;
+    }
+    dst[0] = 1;                                 // "\x01%lld"
+    uint32_t at = k.n;
+    unsigned long long v = k.iv < 0 ? (unsigned long long)(-k.iv) : (unsigned long long)k.iv;
+    do {
+        dst[--at] = (uint8_t)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    if (k.iv < 0) dst[--at] = '-';
 }
 
 struct RunStart {
@@ -280,20 +364,82 @@ struct ExtractArgs {
     ulonglong2 *keys;
     RunStart *starts;
     int *n_starts;
-    int *n_need_host;
+    int *n_need_host;                     // values for the host's intern table
+    int *n_unspelled;                     // values this decoder cannot hand over (float UMI tags)
+    uint2 *hk;                            // per block: such values, bytes of their strings
 };
+
+// one pass over the aux fields finds both tags (first occurrence wins, as bam_aux_get)
+__device__ __forceinline__ void find_tags(const ExtractArgs &a, const uint8_t *p, const uint8_t *rend,
+                                          const uint8_t **t_cell_out, const uint8_t **t_umi_out) {
+    const uint8_t *t_cell = nullptr, *t_umi = nullptr;
+    int want = (a.has_cell ? 1 : 0) + (a.has_umi ? 1 : 0);
+    while (want > 0 && p + 3 <= rend) {
+        const uint32_t tag = ld16u(p), typ = p[2];
+        if (a.has_cell && !t_cell && tag == a.cell_tag) {
+            t_cell = p + 2;
+            want--;
+        }
+        // host order: the cell tag is looked up first, then the UMI tag, each from the start;
+        // identical tags resolve to the same field
+        if (a.has_umi && !t_umi && tag == a.umi_tag) {
+            t_umi = p + 2;
+            want--;
+        }
+        const uint8_t *v = p + 3;
+        unsigned long long sz;
+        if (typ == 'A' || typ == 'c' || typ == 'C') sz = 1;
+        else if (typ == 's' || typ == 'S') sz = 2;
+        else if (typ == 'i' || typ == 'I' || typ == 'f') sz = 4;
+        else if (typ == 'Z' || typ == 'H') {
+            const uint8_t *z = v;
+            while (z < rend && *z) z++;
+            if (z >= rend) break;
+            sz = (unsigned long long)(z - v) + 1;
+        } else if (typ == 'B') {
+            if (v + 5 > rend) break;
+            const uint32_t st = v[0], cnt = ld32u(v + 1);
+            const unsigned long long es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+            sz = 5 + es * cnt;
+        } else break;
+        p = v + sz;
+    }
+    *t_cell_out = t_cell;
+    *t_umi_out = t_umi;
+}
+
+// the two keys of a record
+__device__ __forceinline__ void record_keys(const ExtractArgs &a, const uint8_t *r, uint32_t bs, const RecGeom &q,
+                                            KeyRef *ck, KeyRef *uk) {
+    const uint8_t *sq = r + 36 + q.l_name + 4ull * q.n_cig;
+    const uint8_t *p = sq + (q.l_seq + 1) / 2 + q.l_seq, *rend = r + 4 + bs;
+    const uint8_t *t_cell, *t_umi;
+    find_tags(a, p, rend, &t_cell, &t_umi);
+    ck->status = uk->status = 0;
+    ck->key = uk->key = XG_KEY_NONE;
+    if (t_cell) *ck = key_ref_tag(t_cell, rend, true);
+    if (a.has_umi) {
+        if (t_umi) *uk = key_ref_tag(t_umi, rend, false);
+    } else {
+        *uk = key_ref_name(r, rend, q.l_name);
+    }
+}
 
 __global__ void k_extract(const ExtractArgs a) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.n_blocks) return;
     const BlkInfo bi = a.info[b];
-    if (bi.n_kept == 0) return;
+    if (bi.n_kept == 0) {
+        a.hk[b] = make_uint2(0u, 0u);
+        return;
+    }
     const BgzfBlockDev bk = a.blocks[b];
     uint32_t off = bk.uoff < a.hdr_end ? (uint32_t)(a.hdr_end - bk.uoff) : 0u;
     const uint32_t end = bk.isize;
     unsigned long long g = a.rec_base[b], co = a.cig_base[b], so = a.seq_base[b];
     int32_t prev_tid = -2;
-    int need_host = 0;
+    uint32_t hk_n = 0, hk_bytes = 0;
+    int unspelled = 0;
     while (off < end) {
         const uint8_t *r = bk.uptr + off;
         const uint32_t bs = ld32u(r);
@@ -326,48 +472,17 @@ __global__ void k_extract(const ExtractArgs a) {
                 a.seq[so++] = v;
             }
         }
-        // aux fields: one pass finds both tags (first occurrence wins, as bam_aux_get)
-        const uint8_t *p = sq + seq_bytes + q.l_seq, *rend = r + 4 + bs;
-        const uint8_t *t_cell = nullptr, *t_umi = nullptr;
-        int want = (a.has_cell ? 1 : 0) + (a.has_umi ? 1 : 0);
-        while (want > 0 && p + 3 <= rend) {
-            const uint32_t tag = ld16u(p), typ = p[2];
-            if (a.has_cell && !t_cell && tag == a.cell_tag) {
-                t_cell = p + 2;
-                want--;
+        KeyRef ck, uk;
+        record_keys(a, r, bs, q, &ck, &uk);
+        for (const KeyRef *k : {&ck, &uk}) {
+            if (k->status == 1) {
+                hk_n++;
+                hk_bytes += k->n;
+            } else if (k->status == 2) {
+                unspelled++;
             }
-            // host order: the cell tag is looked up first, then the UMI tag, each from the start;
-            // identical tags resolve to the same field
-            if (a.has_umi && !t_umi && tag == a.umi_tag) {
-                t_umi = p + 2;
-                want--;
-            }
-            const uint8_t *v = p + 3;
-            unsigned long long sz;
-            if (typ == 'A' || typ == 'c' || typ == 'C') sz = 1;
-            else if (typ == 's' || typ == 'S') sz = 2;
-            else if (typ == 'i' || typ == 'I' || typ == 'f') sz = 4;
-            else if (typ == 'Z' || typ == 'H') {
-                const uint8_t *z = v;
-                while (z < rend && *z) z++;
-                if (z >= rend) break;
-                sz = (unsigned long long)(z - v) + 1;
-            } else if (typ == 'B') {
-                if (v + 5 > rend) break;
-                const uint32_t st = v[0], cnt = ld32u(v + 1);
-                const unsigned long long es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
-                sz = 5 + es * cnt;
-            } else break;
-            p = v + sz;
         }
-        unsigned long long ck = XG_KEY_NONE, uk = XG_KEY_NONE;
-        if (t_cell && !tag_key_dev(t_cell, rend, true, &ck)) need_host++;
-        if (a.has_umi) {
-            if (t_umi && !tag_key_dev(t_umi, rend, false, &uk)) need_host++;
-        } else {
-            if (!pack_key(r + 36, rend, false, q.l_name ? (int)q.l_name - 1 : 0, &uk)) need_host++;
-        }
-        a.keys[g] = make_ulonglong2(ck, uk);
+        a.keys[g] = make_ulonglong2(ck.key, uk.key);      // a key still to come from the host holds a placeholder
         if (tid != prev_tid) {
             const int s = atomicAdd(a.n_starts, 1);
             a.starts[s] = RunStart{(long long)g, tid, a.bam_idx};
@@ -375,7 +490,56 @@ __global__ void k_extract(const ExtractArgs a) {
         }
         g++;
     }
-    if (need_host) atomicAdd(a.n_need_host, need_host);
+    a.hk[b] = make_uint2(hk_n, hk_bytes);
+    if (hk_n) atomicMax(a.n_need_host, 1);
+    if (unspelled) atomicMax(a.n_unspelled, 1);
+}
+
+// Values for the host's intern table: which key of which record, and the string.
+struct KeyReq {
+    long long rec;
+    unsigned long long off;  // into the string buffer
+    unsigned int len, which; // which: 0 cell, 1 UMI
+};
+
+__global__ void k_keys_gather(const ExtractArgs a, const unsigned long long *req_base, const unsigned long long *str_base,
+                              KeyReq *reqs, uint8_t *strs) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.n_blocks) return;
+    if (a.hk[b].x == 0) return;
+    const BgzfBlockDev bk = a.blocks[b];
+    uint32_t off = bk.uoff < a.hdr_end ? (uint32_t)(a.hdr_end - bk.uoff) : 0u;
+    const uint32_t end = bk.isize;
+    unsigned long long g = a.rec_base[b], ri = req_base[b], so = str_base[b];
+    while (off < end) {
+        const uint8_t *r = bk.uptr + off;
+        const uint32_t bs = ld32u(r);
+        const int32_t tid = (int32_t)ld32u(r + 4);
+        off += 4u + bs;
+        if (tid < 0 || a.tid_map[tid] < 0) continue;
+        const RecGeom q = rec_geom(r, bs, false);
+        KeyRef ck, uk;
+        record_keys(a, r, bs, q, &ck, &uk);
+        if (ck.status == 1) {
+            reqs[ri++] = KeyReq{(long long)g, so, ck.n, 0u};
+            key_ref_write(ck, strs + so);
+            so += ck.n;
+        }
+        if (uk.status == 1) {
+            reqs[ri++] = KeyReq{(long long)g, so, uk.n, 1u};
+            key_ref_write(uk, strs + so);
+            so += uk.n;
+        }
+        g++;
+    }
+}
+
+__global__ void k_keys_patch(const KeyReq *reqs, const unsigned long long *vals, long long n, ulonglong2 *keys) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const KeyReq q = reqs[i];
+    if (q.which) keys[q.rec].y = vals[i];
+    else keys[q.rec].x = vals[i];
 }
 
 __global__ void k_tile_index2(const int2 *pos_end, xg_tile *tiles, int32_t n_tiles) {
@@ -454,7 +618,12 @@ struct Decoder {
     xg_ctx *ctx = nullptr;
     int want_seq = 0;
     const char *cell_tag = nullptr, *umi_tag = nullptr;
-    int *cnt = nullptr;                       // device counters: [0] bad blocks, [2] max aln, [3] max span, [4] starts, [5] keys for the host
+    xg_keyspace *ks = nullptr;                // interns the values that do not pack into 63 bits
+    int *cnt = nullptr;                       // device counters: [0] bad blocks, [2] max aln, [3] max span, [4] starts,
+                                              // [5] values for the host's intern table, [6] values not spelled here
+    uint2 *hk = nullptr;                      // per block of the window: such values, bytes of their strings
+    int64_t n_interned = 0;
+    double t_keys = 0;
     // window buffers, shared by all BAMs of the call
     uint8_t *comp = nullptr, *slab = nullptr;
     size_t comp_cap = 0, slab_cap = 0, blk_cap = 0, tid_cap = 0;
@@ -523,10 +692,12 @@ struct Decoder {
         ctx->dev_put(info);
         ctx->dev_put(bases);
         ctx->dev_put(d_tid_map);
+        ctx->dev_put(hk);
         comp = slab = nullptr;
         blocks = nullptr;
         info = nullptr;
         bases = nullptr;
+        hk = nullptr;
         d_tid_map = nullptr;
         if (ev_win) cudaEventDestroy(ev_win);
         ev_win = nullptr;
@@ -546,6 +717,68 @@ struct BamState {                       // per BAM, across its windows
     uint64_t hdr_end = 0;
     unsigned long long last_key = 0;
 };
+
+// The values of the window that do not pack into 63 bits: their strings are gathered on the
+// device, interned by the host's keyspace (several threads; the keyspace is sharded) and the
+// keys patched into the batch.  Query-name UMIs (`--UMItag None`) take this path for every read.
+int intern_keys(Decoder &D, const ExtractArgs &a, int32_t nb) {
+    xg_ctx *ctx = D.ctx;
+    cudaStream_t st = ctx->stream;
+    const double t0 = now_ms();
+    std::vector<uint2> hk((size_t)nb);
+    cudaError_t e = cudaMemcpy(hk.data(), D.hk, (size_t)nb * sizeof(uint2), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return ctx->fail(XG_E_CUDA, std::string("device decode: ") + cudaGetErrorString(e));
+    std::vector<unsigned long long> base(2 * (size_t)nb);
+    unsigned long long n_req = 0, n_bytes = 0;
+    for (int32_t b = 0; b < nb; b++) {
+        base[(size_t)b] = n_req;
+        base[(size_t)nb + b] = n_bytes;
+        n_req += hk[(size_t)b].x;
+        n_bytes += hk[(size_t)b].y;
+    }
+    unsigned long long *d_base = (unsigned long long *)ctx->dev_get(2 * (size_t)nb * 8 + 16);
+    KeyReq *d_reqs = (KeyReq *)ctx->dev_get((size_t)n_req * sizeof(KeyReq) + 16);
+    uint8_t *d_strs = (uint8_t *)ctx->dev_get((size_t)n_bytes + 16);
+    unsigned long long *d_vals = (unsigned long long *)ctx->dev_get((size_t)n_req * 8 + 16);
+    auto done = [&](int code, const std::string &msg) {
+        cudaStreamSynchronize(st);
+        ctx->dev_put(d_base);
+        ctx->dev_put(d_reqs);
+        ctx->dev_put(d_strs);
+        ctx->dev_put(d_vals);
+        return code ? ctx->fail(code, msg) : XG_OK;
+    };
+    if (!d_base || !d_reqs || !d_strs || !d_vals) return done(XG_E_UNSUPPORTED, "the key strings do not fit the device");
+    cudaMemcpyAsync(d_base, base.data(), 2 * (size_t)nb * 8, cudaMemcpyHostToDevice, st);
+    k_keys_gather<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(a, d_base, d_base + nb, d_reqs, d_strs);
+    std::vector<KeyReq> reqs((size_t)n_req);
+    std::vector<uint8_t> strs((size_t)n_bytes + 1);
+    cudaMemcpyAsync(reqs.data(), d_reqs, (size_t)n_req * sizeof(KeyReq), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(strs.data(), d_strs, (size_t)n_bytes, cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(XG_E_CUDA, std::string("device decode: ") + cudaGetErrorString(e));
+    std::vector<unsigned long long> vals((size_t)n_req);
+    {
+        const int n_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        const size_t per = ((size_t)n_req + n_threads - 1) / n_threads;
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++) {
+            const size_t lo = std::min((size_t)n_req, per * t), hi = std::min((size_t)n_req, per * (t + 1));
+            if (lo >= hi) continue;
+            th.emplace_back([&, lo, hi] {
+                for (size_t i = lo; i < hi; i++)
+                    vals[i] = D.ks->encode((const char *)strs.data() + reqs[i].off, (int64_t)reqs[i].len);
+            });
+        }
+        for (auto &t : th) t.join();
+    }
+    cudaMemcpyAsync(d_vals, vals.data(), (size_t)n_req * 8, cudaMemcpyHostToDevice, st);
+    if (n_req) k_keys_patch<<<(unsigned)((n_req + 255) / 256), 256, 0, st>>>(d_reqs, d_vals, (long long)n_req, D.keys);
+    D.n_interned += (int64_t)n_req;
+    int rc = done(XG_OK, "");
+    D.t_keys += now_ms() - t0;
+    return rc;
+}
 
 // Walk the window's blocks, append their records to the batch.
 int flush_window(Decoder &D, BamState &B, int32_t nb) {
@@ -625,6 +858,9 @@ int flush_window(Decoder &D, BamState &B, int32_t nb) {
         a.starts = d_starts;
         a.n_starts = D.cnt + 4;
         a.n_need_host = D.cnt + 5;
+        a.n_unspelled = D.cnt + 6;
+        a.hk = D.hk;
+        cudaMemsetAsync(D.cnt + 5, 0, 2 * sizeof(int), st);
         cudaEventRecord(ctx->ev[0], st);
         k_extract<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(a);
         cudaEventRecord(ctx->ev[1], st);
@@ -638,9 +874,15 @@ int flush_window(Decoder &D, BamState &B, int32_t nb) {
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
         D.t_extract += ms;
         if (h_cnt[4] != (int)n_starts) return ctx->fail(XG_E_CUDA, "device decode: run starts do not add up");
-        if (h_cnt[5])
-            return ctx->fail(XG_E_UNSUPPORTED, "cell / UMI keys need the host intern table (" + std::to_string(h_cnt[5]) +
-                                                   " values are not short ACGTN-/digit strings)");
+        if (h_cnt[6])
+            return ctx->fail(XG_E_UNSUPPORTED, "float-typed UMI tags are left to the host decoder");
+        if (h_cnt[5]) {
+            if (!D.ks)
+                return ctx->fail(XG_E_UNSUPPORTED, "cell / UMI values need the host intern table (not short "
+                                                   "ACGTN-/digit strings) and no keyspace was given");
+            int rc = intern_keys(D, a, nb);
+            if (rc) return rc;
+        }
         D.n_total += kept;
         D.cig_total += cig;
         D.seq_total += seq;
@@ -778,11 +1020,13 @@ int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid
                     ctx->dev_put(D.info);
                     ctx->dev_put(D.bases);
                     D.blk_cap = hb.size() + hb.size() / 4;
+                    ctx->dev_put(D.hk);
                     D.blocks = (BgzfBlockDev *)ctx->dev_get((D.blk_cap + 1) * sizeof(BgzfBlockDev));
                     D.info = (BlkInfo *)ctx->dev_get((D.blk_cap + 1) * sizeof(BlkInfo));
                     D.bases = (unsigned long long *)ctx->dev_get((3 * D.blk_cap + 1) * 8);
+                    D.hk = (uint2 *)ctx->dev_get((D.blk_cap + 1) * sizeof(uint2));
                 }
-                if (!D.slab || !D.blocks || !D.info || !D.bases)
+                if (!D.slab || !D.blocks || !D.info || !D.bases || !D.hk)
                     return finish(XG_E_UNSUPPORTED, "the inflate window does not fit the device");
             }
             win_open = true;
@@ -882,7 +1126,7 @@ int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t 
 
 int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
                           const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag, int32_t want_seq,
-                          xg_dreads **out, int64_t *n_records_seen) {
+                          xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen) {
     if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
     if (n_bams < 0 || !out) return ctx->fail(XG_E_ARG, "xg_decode_bams_device: bad argument");
     if (cell_tag && strlen(cell_tag) != 2) return ctx->fail(XG_E_ARG, "cell tag must have 2 characters");
@@ -898,6 +1142,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     D.want_seq = want_seq;
     D.cell_tag = cell_tag;
     D.umi_tag = umi_tag;
+    D.ks = ks;
     D.cnt = (int *)ctx->get("gd_counters", 8 * sizeof(int));
     if (!D.cnt) return XG_E_CUDA;
     // window buffers: as large as the largest BAM needs, at most XG_DECODE_WINDOW compressed bytes
@@ -923,6 +1168,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     D.blocks = (BgzfBlockDev *)ctx->dev_get((D.blk_cap + 1) * sizeof(BgzfBlockDev));
     D.info = (BlkInfo *)ctx->dev_get((D.blk_cap + 1) * sizeof(BlkInfo));
     D.bases = (unsigned long long *)ctx->dev_get((3 * D.blk_cap + 1) * 8);
+    D.hk = (uint2 *)ctx->dev_get((D.blk_cap + 1) * sizeof(uint2));
     auto bail = [&](int code, const std::string &msg) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamSynchronize(ctx->stream);
@@ -930,7 +1176,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
         D.release_batch();
         return ctx->fail(code, msg);
     };
-    if (!D.comp || !D.slab || !D.blocks || !D.info || !D.bases)
+    if (!D.comp || !D.slab || !D.blocks || !D.info || !D.bases || !D.hk)
         return bail(XG_E_UNSUPPORTED, "the inflate window does not fit the device");
     if (cudaEventCreateWithFlags(&D.ev_win, cudaEventDisableTiming) != cudaSuccess) return bail(XG_E_CUDA, "cudaEventCreate");
     cudaStream_t st = ctx->stream;
@@ -1033,6 +1279,8 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     ctx->timing[5] = D.n_windows;
     ctx->timing[8] = D.t_read;              // time inside pread
     ctx->timing[9] = D.t_alloc;             // growing the batch
+    ctx->timing[6] = (double)D.n_interned;  // values interned by the host's keyspace
+    ctx->timing[7] = D.t_keys;              // ... and the time that took
     {
         const double t_f0 = now_ms();
         ctx->dev_trim(8ull << 30);          // keep small inputs' buffers for the next call, give the rest back

@@ -81,11 +81,11 @@ def device_decode_enabled():
     return os.environ.get("XCLTK_B200_DEVICE_DECODE", "1") not in ("0", "", "no", "false")
 
 
-def _device_decode(ctx, sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq):
+def _device_decode(ctx, sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, keyspace=None):
     """(dreads, stats) or None."""
     if not device_decode_enabled():
         return None
-    res = ctx.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq)
+    res = ctx.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, keyspace)
     if res is None:
         return None
     dreads, seen = res
@@ -110,7 +110,7 @@ def load_reads(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads=0, de
     ks = lib.KeySpace()
     bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
     gid_of, tid_maps = build_tid_maps(bam_refs, list(chroms))
-    dev = _device_decode(ctx, sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq)
+    dev = _device_decode(ctx, sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, ks)
     if dev is not None:
         return ReadBatch(ctx, dev[0], ks, gid_of, dev[1])
     host = lib.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, ks, n_threads)
@@ -162,7 +162,7 @@ def load_reads_multi(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads
     bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
     gid_of, tid_maps = build_tid_maps(bam_refs, list(chroms))
     devs = parallel.run_on_devices(len(ctxs), lambda k: _device_decode(ctxs[k], sam_fn_list, tid_maps, cell_tag,
-                                                                       umi_tag, want_seq))
+                                                                       umi_tag, want_seq, ks))
     if all(d is not None for d in devs):
         runs, tiles = devs[0][0].index()
         return MultiBatch([ReadBatch(c, d[0], ks, gid_of, d[1]) for c, d in zip(ctxs, devs)], runs, _tile_pos(runs, tiles))

@@ -117,7 +117,7 @@ SYMBOLS = {
     "xg_dreads_info": (None, [_P, c_i64p]),
     "xg_dreads_index": (None, [_P, C.POINTER(Run), C.POINTER(Tile)]),
     "xg_decode_bams_device": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(c_i32p), c_i32p,
-                                        C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(_P), c_i64p]),
+                                        C.c_char_p, C.c_char_p, C.c_int32, _P, C.POINTER(_P), c_i64p]),
     "xg_bgzf_inflate_device": (C.c_int, [_P, C.c_char_p, c_u8p, C.c_int64, c_i64p]),
     "xg_coo_free": (None, [C.POINTER(Coo)]),
     "xg_basefc": (C.c_int, [_P, _P, C.POINTER(Features), C.POINTER(Barcodes), C.POINTER(Params),
@@ -447,9 +447,11 @@ class Context(object):
         self._check(self.lib.xg_upload_reads(self.h, host_reads.ptr, C.byref(d)))
         return DeviceReads(self, d)
 
-    def decode_bams(self, paths, tid_maps, cell_tag, umi_tag, want_seq):
+    def decode_bams(self, paths, tid_maps, cell_tag, umi_tag, want_seq, keyspace=None):
         """BGZF inflate + BAM parse on the device (xg_decode_bams_device).  Returns
-        (DeviceReads, n_records_seen), or None when the files need the host decoder."""
+        (DeviceReads, n_records_seen), or None when the files need the host decoder.
+        keyspace: interns the cell / UMI values that do not pack into 63 bits (query names,
+        free-text barcodes); without it such files are left to the host decoder."""
         n = len(paths)
         cpaths = (C.c_char_p * n)(*[p.encode() for p in paths])
         maps = [np.ascontiguousarray(m, dtype=np.int32) for m in tid_maps]
@@ -460,7 +462,8 @@ class Context(object):
         rc = self.lib.xg_decode_bams_device(self.h, n, cpaths, cmaps, as_ptr(lens, c_i32p),
                                             cell_tag.encode() if cell_tag else None,
                                             umi_tag.encode() if umi_tag else None,
-                                            1 if want_seq else 0, C.byref(d), C.byref(seen))
+                                            1 if want_seq else 0, keyspace.h if keyspace is not None else None,
+                                            C.byref(d), C.byref(seen))
         if rc == XG_E_UNSUPPORTED:
             self.decode_fallback_reason = self.lib.xg_last_error(self.h).decode()
             return None
