@@ -411,7 +411,10 @@ def test_device_decode_interns_odd_keys_through_the_keyspace(gpu_ctx, tmp_path, 
     res = gpu_ctx.decode_bams(paths, maps, cell_tag, umi_tag, True, ks)
     assert res is not None, gpu_ctx.decode_fallback_reason
     assert ks.n_interned() == ks_host.n_interned() > (0 if (cell_tag, umi_tag) == (None, "UB") else 40)
-    assert gpu_ctx.timing()[6] > 0                       # values that went through the keyspace
+    t = gpu_ctx.timing()
+    assert t[6] > 0 and 0 < t[11] <= t[6]                # values handed over / distinct strings per window
+    if (cell_tag, umi_tag) == ("CB", "UB"):
+        assert t[11] < t[6] / 2                          # 45 barcodes over thousands of reads: interned once per window
     assert_same_batch(res[0], res[1], host, ks, ks_host)
     res[0].close()
 

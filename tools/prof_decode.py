@@ -19,19 +19,20 @@ if not os.path.exists(path):
 print("bam: %.1f MB written in %.1f s" % (os.path.getsize(path) / 1e6, time.time() - t0), flush=True)
 ctx = engine.get_context(0)
 maps = [np.arange(len(contigs), dtype=np.int32)]
+umi = None if os.environ.get("PROF_UMI", "UB") == "None" else "UB"       # None: query-name keys, interned on the host
 for want_seq in (False, True):
     for rep in range(2):
         t0 = time.time()
-        dev, seen = ctx.decode_bams([path], maps, "CB", "UB", want_seq)
+        dev, seen = ctx.decode_bams([path], maps, "CB", umi, want_seq, lib.KeySpace())
         dt = time.time() - t0
         t = ctx.timing()
         print("device want_seq=%d: %.3f s  %.1f Mreads/s | pread %.0f ms, read+h2d+inflate %.1f ms, walk %.1f ms, "
-              "extract %.1f ms, alloc %.0f ms, trim %.0f ms, call %.0f ms" % (want_seq, dt, seen / dt / 1e6, t[8], t[4], t[2], t[3], t[9], t[10], t[12]),
+              "extract %.1f ms, alloc %.0f ms, trim %.0f ms, interned %d (%d distinct) in %.0f ms, call %.0f ms" % (want_seq, dt, seen / dt / 1e6, t[8], t[4], t[2], t[3], t[9], t[10], int(t[6]), int(t[11]), t[7], t[12]),
               flush=True)
         dev.close()
     t0 = time.time()
     ks = lib.KeySpace()
-    host = lib.decode_bams([path], maps, "CB", "UB", want_seq, ks, threads)
+    host = lib.decode_bams([path], maps, "CB", umi, want_seq, ks, threads)
     t1 = time.time()
     d = ctx.upload(host)
     t2 = time.time()

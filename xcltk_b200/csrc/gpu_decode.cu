@@ -534,6 +534,46 @@ __global__ void k_keys_gather(const ExtractArgs a, const unsigned long long *req
     }
 }
 
+// Equal strings of a window are interned once: hash every string, then elect a representative
+// per distinct string in an open-addressing table of request indices (a slot holds index + 1;
+// hashes and bytes are complete before the election starts, so a loser can compare at once).
+__global__ void k_keys_hash(const KeyReq *reqs, const uint8_t *strs, long long n, unsigned long long *hash) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const KeyReq q = reqs[i];
+    unsigned long long h = 1469598103934665603ull ^ q.len;
+    for (unsigned int k = 0; k < q.len; k++) h = (h ^ strs[q.off + k]) * 1099511628211ull;
+    hash[i] = mix64(h);
+}
+
+__global__ void k_keys_elect(const KeyReq *reqs, const uint8_t *strs, const unsigned long long *hash, long long n,
+                             unsigned int *slots, unsigned int cap, unsigned int *rep) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const KeyReq q = reqs[i];
+    const unsigned long long h = hash[i];
+    unsigned int s = hash_to_range(h, cap);
+    while (true) {
+        unsigned int cur = slots[s];
+        if (cur == 0) cur = atomicCAS(&slots[s], 0u, (unsigned int)i + 1u);
+        if (cur == 0) {
+            rep[i] = (unsigned int)i;
+            return;
+        }
+        const unsigned int r = cur - 1u;
+        if (hash[r] == h) {
+            const KeyReq qr = reqs[r];
+            bool same = qr.len == q.len;
+            for (unsigned int k = 0; same && k < q.len; k++) same = strs[qr.off + k] == strs[q.off + k];
+            if (same) {
+                rep[i] = r;
+                return;
+            }
+        }
+        s = s + 1 == cap ? 0 : s + 1;
+    }
+}
+
 __global__ void k_keys_patch(const KeyReq *reqs, const unsigned long long *vals, long long n, ulonglong2 *keys) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -622,7 +662,7 @@ struct Decoder {
     int *cnt = nullptr;                       // device counters: [0] bad blocks, [2] max aln, [3] max span, [4] starts,
                                               // [5] values for the host's intern table, [6] values not spelled here
     uint2 *hk = nullptr;                      // per block of the window: such values, bytes of their strings
-    int64_t n_interned = 0;
+    int64_t n_interned = 0, n_distinct = 0;  // values handed to the host / strings it had to intern
     double t_keys = 0;
     // window buffers, shared by all BAMs of the call
     uint8_t *comp = nullptr, *slab = nullptr;
@@ -751,26 +791,58 @@ int intern_keys(Decoder &D, const ExtractArgs &a, int32_t nb) {
     if (!d_base || !d_reqs || !d_strs || !d_vals) return done(XG_E_UNSUPPORTED, "the key strings do not fit the device");
     cudaMemcpyAsync(d_base, base.data(), 2 * (size_t)nb * 8, cudaMemcpyHostToDevice, st);
     k_keys_gather<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(a, d_base, d_base + nb, d_reqs, d_strs);
+    // one representative per distinct string (requests are indexed with 32 bits here)
+    if (n_req >= 0xffffffffull) return done(XG_E_UNSUPPORTED, "too many values for the intern table in one window");
+    const unsigned int cap = (unsigned int)std::min<unsigned long long>(2 * n_req + 16, 0xfffffff0ull);
+    unsigned long long *d_hash = d_vals;            // the hashes are done with before the values arrive
+    unsigned int *d_slots = (unsigned int *)ctx->dev_get((size_t)cap * 4 + 16);
+    unsigned int *d_rep = (unsigned int *)ctx->dev_get((size_t)n_req * 4 + 16);
+    if (!d_slots || !d_rep) {
+        ctx->dev_put(d_slots);
+        ctx->dev_put(d_rep);
+        return done(XG_E_UNSUPPORTED, "the key strings do not fit the device");
+    }
+    cudaMemsetAsync(d_slots, 0, (size_t)cap * 4, st);
+    k_keys_hash<<<(unsigned)((n_req + 255) / 256), 256, 0, st>>>(d_reqs, d_strs, (long long)n_req, d_hash);
+    k_keys_elect<<<(unsigned)((n_req + 255) / 256), 256, 0, st>>>(d_reqs, d_strs, d_hash, (long long)n_req, d_slots, cap,
+                                                                d_rep);
     std::vector<KeyReq> reqs((size_t)n_req);
     std::vector<uint8_t> strs((size_t)n_bytes + 1);
+    std::vector<unsigned int> rep((size_t)n_req);
     cudaMemcpyAsync(reqs.data(), d_reqs, (size_t)n_req * sizeof(KeyReq), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(strs.data(), d_strs, (size_t)n_bytes, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(rep.data(), d_rep, (size_t)n_req * 4, cudaMemcpyDeviceToHost, st);
     e = cudaStreamSynchronize(st);
+    ctx->dev_put(d_slots);
+    ctx->dev_put(d_rep);
     if (e != cudaSuccess) return done(XG_E_CUDA, std::string("device decode: ") + cudaGetErrorString(e));
     std::vector<unsigned long long> vals((size_t)n_req);
     {
         const int n_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         const size_t per = ((size_t)n_req + n_threads - 1) / n_threads;
-        std::vector<std::thread> th;
-        for (int t = 0; t < n_threads; t++) {
-            const size_t lo = std::min((size_t)n_req, per * t), hi = std::min((size_t)n_req, per * (t + 1));
-            if (lo >= hi) continue;
-            th.emplace_back([&, lo, hi] {
-                for (size_t i = lo; i < hi; i++)
+        auto over_slices = [&](auto body) {
+            std::vector<std::thread> th;
+            for (int t = 0; t < n_threads; t++) {
+                const size_t lo = std::min((size_t)n_req, per * t), hi = std::min((size_t)n_req, per * (t + 1));
+                if (lo < hi) th.emplace_back([=] { body(lo, hi); });
+            }
+            for (auto &t : th) t.join();
+        };
+        std::atomic<long long> n_distinct(0);
+        over_slices([&](size_t lo, size_t hi) {           // representatives go through the keyspace ...
+            long long nd = 0;
+            for (size_t i = lo; i < hi; i++)
+                if (rep[i] == (unsigned int)i) {
                     vals[i] = D.ks->encode((const char *)strs.data() + reqs[i].off, (int64_t)reqs[i].len);
-            });
-        }
-        for (auto &t : th) t.join();
+                    nd++;
+                }
+            n_distinct += nd;
+        });
+        over_slices([&](size_t lo, size_t hi) {           // ... the others take their representative's key
+            for (size_t i = lo; i < hi; i++)
+                if (rep[i] != (unsigned int)i) vals[i] = vals[rep[i]];
+        });
+        D.n_distinct += n_distinct;
     }
     cudaMemcpyAsync(d_vals, vals.data(), (size_t)n_req * 8, cudaMemcpyHostToDevice, st);
     if (n_req) k_keys_patch<<<(unsigned)((n_req + 255) / 256), 256, 0, st>>>(d_reqs, d_vals, (long long)n_req, D.keys);
@@ -1281,6 +1353,7 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     ctx->timing[9] = D.t_alloc;             // growing the batch
     ctx->timing[6] = (double)D.n_interned;  // values interned by the host's keyspace
     ctx->timing[7] = D.t_keys;              // ... and the time that took
+    ctx->timing[11] = (double)D.n_distinct; // ... distinct strings per window among them
     {
         const double t_f0 = now_ms();
         ctx->dev_trim(8ull << 30);          // keep small inputs' buffers for the next call, give the rest back

@@ -76,7 +76,7 @@ inline int64_t key_unpack(uint64_t k, char *buf, int64_t cap) {
 }  // namespace xg
 
 struct xg_keyspace {
-    static const int NSHARD = 64;
+    static const int NSHARD = 256;
     struct Shard {
         std::mutex mu;
         std::unordered_map<std::string, uint64_t> map;
