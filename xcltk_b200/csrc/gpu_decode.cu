@@ -1158,7 +1158,7 @@ int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t 
     uint8_t *comp = nullptr, *ubuf = nullptr;
     BgzfBlockDev *dblk = nullptr;
     XG_GET(cnt, int, "gd_counters", 8);
-    if (cudaMalloc(&comp, f.size() + 16) != cudaSuccess || cudaMalloc(&ubuf, usize + 16) != cudaSuccess ||
+    if (cudaMalloc(&comp, f.size() + 4096) != cudaSuccess || cudaMalloc(&ubuf, usize + 16) != cudaSuccess ||     // a corrupt last block may be read a batch of symbols past its end
         cudaMalloc(&dblk, (blocks.size() + 1) * sizeof(BgzfBlockDev)) != cudaSuccess) {
         cudaGetLastError();
         cudaFree(comp);
