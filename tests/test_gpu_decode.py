@@ -428,3 +428,36 @@ def test_device_decode_leaves_float_umis_to_the_host(gpu_ctx, tmp_path):
     assert gpu_ctx.decode_bams([p], maps, "CB", "UB", True, lib.KeySpace()) is None
     assert "float" in gpu_ctx.decode_fallback_reason
     assert host_decode([p], maps, "CB", "UB", True).n == 50
+
+
+def test_device_decode_survives_random_corruption(gpu_ctx, tmp_path):
+    """bit flips anywhere in the file end in a format error, a decline or a (differently) valid
+    stream -- never in a CUDA fault: the context decodes the intact file right afterwards.
+    (Neither decoder verifies the gzip CRC32, so a flipped literal byte passes; htslib would
+    reject it.)"""
+    from xcltk_b200 import lib
+    good = tenx_bam(tmp_path, 3000, 41, "good.bam")
+    raw = open(good, "rb").read()
+    maps = full_maps([good])
+    rng = random.Random(7)
+    seen_kinds = set()
+    for k in range(60):
+        b = bytearray(raw)
+        for _ in range(rng.choice([1, 1, 2, 6])):
+            b[rng.randrange(100, len(b) - 30)] ^= 1 << rng.randrange(8)
+        p = str(tmp_path / "bad.bam")
+        with open(p, "wb") as fp:
+            fp.write(bytes(b))
+        try:
+            res = gpu_ctx.decode_bams([p], maps, "CB", "UB", True, lib.KeySpace())
+            if res is not None:
+                res[0].close()
+            seen_kinds.add("decoded" if res is not None else "declined")
+        except lib.XgError as e:
+            assert e.code in (-3, -2), str(e)            # XG_E_FORMAT / XG_E_IO, not XG_E_CUDA
+            seen_kinds.add("error")
+    assert "error" in seen_kinds
+    host = host_decode([good], maps, "CB", "UB", True)
+    dev, seen = gpu_ctx.decode_bams([good], maps, "CB", "UB", True)
+    assert_same_batch(dev, seen, host)
+    dev.close()
