@@ -43,6 +43,23 @@ int main(int argc, char **argv) {
         zs.next_in = &f[off + 12 + xlen]; zs.avail_in = clen; zs.next_out = exp.data(); zs.avail_out = isize;
         inflate(&zs, Z_FINISH); inflateEnd(&zs);
         int r = isize ? xg_inflate::inflate_group<1>(g, &f[off + 12 + xlen], clen, got.data(), isize) : 0;
+        // the lane-parallel CRC's arithmetic: 32 chunk CRCs combined must give the block's CRC32
+        {
+            const unsigned chunk = (isize + 31u) / 32u;
+            unsigned total = 0;
+            for (unsigned lane = 0; lane < 32; lane++) {
+                const unsigned beg = std::min(isize, lane * chunk), end = std::min(isize, beg + chunk);
+                if (end == beg) continue;
+                const unsigned ci = (unsigned)crc32(crc32(0L, Z_NULL, 0), exp.data() + beg, end - beg);
+                total ^= xg_inflate::crc_multmodp(xg_inflate::crc_x8n(isize - end), ci);
+            }
+            unsigned trailer;
+            memcpy(&trailer, &f[off + bsize - 8], 4);
+            if (isize && (total != trailer || total != (unsigned)crc32(crc32(0L, Z_NULL, 0), exp.data(), isize))) {
+                printf("block %d: combined CRC %08x, trailer %08x\n", bi, total, trailer);
+                bad++;
+            }
+        }
         if (r != (int)isize || memcmp(got.data(), exp.data(), isize)) {
             if (bad < 5) {
                 size_t k = 0; while (k < isize && got[k] == exp[k]) k++;

@@ -431,10 +431,9 @@ def test_device_decode_leaves_float_umis_to_the_host(gpu_ctx, tmp_path):
 
 
 def test_device_decode_survives_random_corruption(gpu_ctx, tmp_path):
-    """bit flips anywhere in the file end in a format error, a decline or a (differently) valid
-    stream -- never in a CUDA fault: the context decodes the intact file right afterwards.
-    (Neither decoder verifies the gzip CRC32, so a flipped literal byte passes; htslib would
-    reject it.)"""
+    """bit flips anywhere in the file end in a format error (both decoders verify the gzip CRC32
+    of every block, as htslib does), a decline or -- flips in bytes nobody reads -- a valid
+    stream; never in a CUDA fault: the context decodes the intact file right afterwards."""
     from xcltk_b200 import lib
     good = tenx_bam(tmp_path, 3000, 41, "good.bam")
     raw = open(good, "rb").read()

@@ -13,6 +13,7 @@ struct BgzfBlock {
     uint32_t clen;    // deflate payload length
     uint32_t isize;   // uncompressed length
     uint64_t uoff;    // offset in the uncompressed stream
+    uint32_t crc;     // CRC32 of the uncompressed bytes (gzip trailer)
 };
 
 // Byte buffer without the value-initialisation of std::vector::resize (GBs of memset).

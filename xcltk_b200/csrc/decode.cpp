@@ -132,6 +132,7 @@ int scan_bgzf(const Bytes &f, std::vector<BgzfBlock> &blocks, const char *path, 
         b.coff = off + hdr;
         b.clen = total - hdr - 8;
         b.isize = rd32(&f[off + total - 4]);
+        b.crc = rd32(&f[off + total - 8]);
         b.uoff = uoff;
         if (b.isize > 65536) return fail(XG_E_FORMAT, "BGZF block larger than 64 KiB");
         uoff += b.isize;
@@ -164,14 +165,15 @@ int inflate_blocks(const uint8_t *f, uint64_t f_base, const BgzfBlock *blocks, s
             zs.next_out = &out[bk.uoff - base];
             zs.avail_out = bk.isize;
             int rc = inflate(&zs, Z_FINISH);
-            if (rc != Z_STREAM_END || zs.avail_out != 0) {
+            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+                (uint32_t)crc32(crc32(0L, Z_NULL, 0), &out[bk.uoff - base], bk.isize) != bk.crc) {     // as htslib checks
                 bad = 1;
                 break;
             }
         }
         inflateEnd(&zs);
     });
-    if (bad) return fail(XG_E_FORMAT, "BGZF inflate failed (corrupt block)");
+    if (bad) return fail(XG_E_FORMAT, "BGZF inflate failed (corrupt block or CRC mismatch)");
     return XG_OK;
 }
 

@@ -67,7 +67,14 @@ __global__ void __launch_bounds__(INFLATE_THREADS) k_inflate(const uint8_t *comp
     const BgzfBlockDev bk = blocks[b];
     if (bk.isize == 0) return;
     const int n = xg_inflate::inflate_group<S>(gs[grp], comp + bk.coff, bk.clen, bk.uptr, bk.isize);
-    if ((threadIdx.x & (S - 1)) == 0 && n != (int)bk.isize) atomicAdd(n_bad, 1);
+    bool bad = n != (int)bk.isize;
+    if (S == 32 && !bad) {
+        __syncwarp();                                  // the block's bytes, written by all lanes; the tables are idle now
+        xg_inflate::crc_build_table(gs[grp].lut);
+        __syncwarp();
+        bad = xg_inflate::crc32_warp(gs[grp].lut, bk.uptr, bk.isize) != bk.crc;    // gzip trailer, as htslib checks
+    }
+    if ((threadIdx.x & (S - 1)) == 0 && bad) atomicAdd(n_bad, 1);
 }
 
 template <int S>
@@ -871,7 +878,8 @@ int flush_window(Decoder &D, BamState &B, int32_t nb) {
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     D.t_walk += ms;
-    if (h_cnt[0]) return ctx->fail(XG_E_FORMAT, std::string("BGZF inflate failed (corrupt block) in '") + B.path + "'");
+    if (h_cnt[0])
+        return ctx->fail(XG_E_FORMAT, std::string("BGZF inflate failed (corrupt block or CRC mismatch) in '") + B.path + "'");
     std::vector<unsigned long long> bases(3 * (size_t)nb);
     int64_t kept = 0, cig = 0, seq = 0, n_all = 0, n_starts = 0;
     for (int32_t b = 0; b < nb; b++) {
@@ -1035,6 +1043,7 @@ int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid
             b.coff = next_off + hl;
             b.clen = total - hl - 8;
             memcpy(&b.isize, p + total - 4, 4);
+            memcpy(&b.crc, p + total - 8, 4);
             b.uoff = uoff;
             if (b.isize > 65536) return finish(XG_E_FORMAT, "BGZF block larger than 64 KiB");
             uoff += b.isize;
@@ -1117,6 +1126,8 @@ int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid
             dv[i].isize = hb[i].isize;
             dv[i].uoff = hb[i].uoff;
             dv[i].uptr = D.slab + win_infl;
+            dv[i].crc = hb[i].crc;
+            dv[i].pad_ = 0;
             win_infl += hb[i].isize;
         }
         if (!dv.empty())
@@ -1175,6 +1186,8 @@ int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t 
         dv[i].isize = blocks[i].isize;
         dv[i].uoff = blocks[i].uoff;
         dv[i].uptr = ubuf + blocks[i].uoff;
+        dv[i].crc = blocks[i].crc;
+        dv[i].pad_ = 0;
     }
     cudaMemcpyAsync(dblk, dv.data(), dv.size() * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(cnt, 0, 8 * sizeof(int), st);
@@ -1192,7 +1205,7 @@ int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t 
     cudaFree(ubuf);
     cudaFree(dblk);
     if (e != cudaSuccess) return ctx->fail(XG_E_CUDA, std::string("device inflate: ") + cudaGetErrorString(e));
-    if (bad) return ctx->fail(XG_E_FORMAT, "BGZF inflate failed (corrupt block)");
+    if (bad) return ctx->fail(XG_E_FORMAT, "BGZF inflate failed (corrupt block or CRC mismatch)");
     return XG_OK;
 }
 

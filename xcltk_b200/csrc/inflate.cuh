@@ -22,6 +22,8 @@ struct BgzfBlockDev {
     unsigned int isize;        // uncompressed bytes
     unsigned long long uoff;   // offset in the uncompressed stream
     unsigned char *uptr;       // where the block is inflated to (slabs: blocks are contiguous within one)
+    unsigned int crc;          // CRC32 of the uncompressed bytes (gzip trailer)
+    unsigned int pad_;
 };
 
 namespace xg_inflate {
@@ -395,5 +397,78 @@ __device__ int inflate_group(GroupSmem &g, const uint8_t *in, uint32_t n_in, uin
     }
     return (int)o;
 }
+
+// ---- CRC32 of the inflated block (gzip trailer check, as htslib does) -------------------------
+// Lane-parallel: every lane takes 1/32 of the block through the byte-wise table algorithm, the 32
+// CRCs are combined with crc(A||B) = crc(A) * x^(8|B|) mod P  xor  crc(B) (reflected polynomial
+// 0xEDB88320, the arithmetic zlib's crc32_combine uses).
+constexpr unsigned int CRC_POLY = 0xedb88320u;
+
+__device__ __forceinline__ unsigned int crc_multmodp(unsigned int a, unsigned int b) {
+    unsigned int m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) {
+            p ^= b;
+            if ((a & (m - 1)) == 0) break;
+        }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+    }
+    return p;
+}
+
+// x^(8 n) mod P
+__device__ __forceinline__ unsigned int crc_x8n(unsigned int n) {
+    unsigned int p = 1u << 31;               // x^0
+    unsigned int sq = 1u << 23;              // x^8
+    while (n) {
+        if (n & 1u) p = crc_multmodp(sq, p);
+        n >>= 1;
+        if (n) sq = crc_multmodp(sq, sq);
+    }
+    return p;
+}
+
+// table[i] for the byte-wise update; every warp builds its own copy (in its idle Huffman table)
+__device__ __forceinline__ void crc_build_table(unsigned int *table) {
+    for (unsigned int i = threadIdx.x & 31u; i < 256; i += 32) {
+        unsigned int c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ CRC_POLY : c >> 1;
+        table[i] = c;
+    }
+}
+
+#ifdef __CUDACC__
+// CRC32 of out[0, n) by one warp (all lanes call; the result is uniform).
+__device__ __forceinline__ unsigned int crc32_warp(const unsigned int *table, const uint8_t *out, unsigned int n) {
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int chunk = (n + 31u) / 32u;
+    const unsigned int beg = min(n, lane * chunk), end = min(n, beg + chunk);
+    unsigned int c = 0xffffffffu;
+    {
+        // 16-byte loads over the aligned body of the chunk (a byte load per step would make the
+        // 32 lanes' strided accesses the bottleneck), single bytes at its ragged ends
+        const uint8_t *p = out + beg, *pe = out + end;
+        while (p < pe && ((uintptr_t)p & 15)) c = table[(c ^ *p++) & 0xffu] ^ (c >> 8);
+        for (; p + 16 <= pe; p += 16) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(p);
+            const unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                c ^= w[j];
+#pragma unroll
+                for (int b = 0; b < 4; b++) c = table[c & 0xffu] ^ (c >> 8);
+            }
+        }
+        while (p < pe) c = table[(c ^ *p++) & 0xffu] ^ (c >> 8);
+    }
+    c ^= 0xffffffffu;                         // the CRC of this lane's chunk (of the empty string: 0)
+    // crc(A|B|C) = crc(A) x^(8(|B|+|C|)) + crc(B) x^(8|C|) + crc(C): every lane shifts its own CRC
+    // past the bytes that follow its chunk, the terms are xor-ed together
+    const unsigned int term = end > beg ? crc_multmodp(crc_x8n(n - end), c) : 0u;
+    const unsigned int total = __reduce_xor_sync(0xffffffffu, term);
+    return total;
+}
+#endif
 
 }  // namespace xg_inflate
