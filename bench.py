@@ -380,7 +380,7 @@ def main():
                 if best is not None:
                     tdv = ctx.timing()
                     device_decode = {"reads_per_s": n_dev / best, "sample_reads": n_dev, "call_ms": 1e3 * best,
-                                     "pipeline_ms_read_h2d_inflate": tdv[4], "extract_ms": tdv[3],
+                                     "stream_loop_ms": tdv[4], "extract_ms": tdv[3], "windows": int(tdv[5]),
                                      "note": "xg_decode_bams_device, same file: file -> HBM-resident batch; "
                                              "the C3 batch at this rate takes %.1f s" % (args.reads / (n_dev / best))}
                 else:
