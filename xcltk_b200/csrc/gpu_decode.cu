@@ -1,18 +1,19 @@
-// gpu_decode.cu -- BAM -> read batch entirely on the device: BGZF inflate + record parse.
+// gpu_decode.cu -- BAM -> read batch on the device: BGZF inflate + record parse.
 //
 // Same result, array for array, as the host decoder (decode.cpp: xg_decode_bams followed by
 // xg_upload_reads); replaces what the reference gets from pysam/htslib on its counting paths
 // (pysam.AlignmentFile + fetch(), xcltk/rdr/fc/core.py:75,100; xcltk/baf/fc/core.py:60,99).
-// The compressed file crosses PCIe once (~65 B/read instead of ~250 B/read inflated), every
-// BGZF block is inflated by one thread, and the records are parsed where they land.
+// The compressed file crosses PCIe once (~55 B/read), every BGZF block is inflated and
+// CRC-checked by one warp (inflate.cuh), and the records are parsed where they land, window by
+// window, into the batch arrays.
 //
 // Block-parallel parsing needs every BGZF block to start at a record boundary.  htslib
 // writes BAM that way (bam_write1 flushes the block before a record that does not fit, and
 // the header ends with a flush), so files from samtools / cellranger / STARsolo qualify; the
-// walk kernel verifies it and any other layout -- or a key that must be interned on the host
-// (query names, non-ACGTN barcodes, numeric tags) -- returns XG_E_UNSUPPORTED so that the
-// caller uses xg_decode_bams + xg_upload_reads instead.  Both decoders are decoders: neither
-// counts anything, and the counting kernels stay device-only.
+// walk kernel verifies it and any other layout returns XG_E_UNSUPPORTED so that the caller
+// uses xg_decode_bams + xg_upload_reads instead.  Cell / UMI values that do not pack into 63
+// bits are gathered here and interned by the host keyspace.  Both decoders are decoders:
+// neither counts anything, and the counting kernels stay device-only.
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
