@@ -698,6 +698,11 @@ __global__ void __launch_bounds__(256, 6) k_basefc_count(const __grid_constant__
     flush_pairs(P, S);
 }
 
+__global__ void k_snapshot_cursor(const unsigned long long *cursor, unsigned long long *host_slot) {
+    *host_slot = *cursor;
+    __threadfence_system();
+}
+
 // Zero the sets of the features that become active in this epoch.  The segments are laid
 // end to end in a virtual byte space (pre[] = exclusive prefix, pre[n_seg] = total).
 #define ZERO_CHUNK 16384
@@ -1098,11 +1103,16 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     // staging cursor is snapshotted so that the host can copy that epoch's rows out while the
     // later epochs are still being counted
     const bool staged_out = !ctx->row_order;
-    unsigned long long *h_cur = nullptr;
+    unsigned long long *h_cur = nullptr, *d_cur = nullptr;
     if (staged_out) {
         if (!ctx->d2h_stream) XG_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
         h_cur = (unsigned long long *)ctx->pinned_get(sizeof(unsigned long long) * (size_t)(pl.n_epochs + 1));
         if (!h_cur) return ctx->fail(XG_E_NOMEM, "out of pinned host memory");
+        if (cudaHostGetDevicePointer((void **)&d_cur, h_cur, 0) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->pinned_put(h_cur);
+            return ctx->fail(XG_E_CUDA, "pinned host memory is not mapped for the device");
+        }
     }
     int64_t h2d_bytes = 0;
     for (int32_t e = 0; e < pl.n_epochs; e++) {
@@ -1158,7 +1168,9 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
                 fin_work + e, cursor, seg_base, seg_nnz, st_col, st_val);
             launches++;
         }
-        if (h_cur) cudaMemcpyAsync(h_cur + e, cursor, 8, cudaMemcpyDeviceToHost, st_f);
+        // the snapshot is a store into mapped host memory, not a copy: a D2H of 8 bytes would queue
+        // behind the result copies on the copy engine and stall the finalize stream with them
+        if (h_cur) k_snapshot_cursor<<<1, 1, 0, st_f>>>(cursor, d_cur + e);
         cudaEventRecord(EV(3, e), st_f);
     }
     if (overlap) {
