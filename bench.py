@@ -90,10 +90,37 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: run on the CPUs of the GPU's NUMA node, so that the pinned buffers
+    this rank allocates (first touch) sit next to its PCIe root instead of across the socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:                                    # NVML does not see CUDA_VISIBLE_DEVICES: go by the PCI address
+            import torch
+            pr = torch.cuda.get_device_properties(local)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(
+                ("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         # stdout carries the one JSON line: NCCL's own banner / debug lines go to stderr
