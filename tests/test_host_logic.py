@@ -185,3 +185,34 @@ def test_write_mtx_rows_equals_csr_writer(tmp_path):
     assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "b.mtx"), "rb").read()
     for a, b in zip(seg.to_sorted(), (row, col, val)):
         assert np.array_equal(a, b)
+
+
+def test_snp_filter_is_the_references_scalar_expression():
+    """vectorised plp_snp filter == `snp_cnt < min_count or min(ref, alt) < snp_cnt * min_maf`
+    evaluated per SNP with Python ints / floats (baf/fc/core.py:238-246)"""
+    import random
+    import numpy as np
+    from xcltk_b200.baf.fc.main import BASE_IDX, snp_filter
+
+    class Obj(object):
+        pass
+    rng = random.Random(3)
+    for trial in range(200):
+        n = rng.randrange(0, 50)
+        snps = []
+        for _ in range(n):
+            s = Obj()
+            s.ref, s.alt = rng.choice("ACGTN"), rng.choice("ACGTN")
+            snps.append(s)
+        totals = np.array([[rng.choice([0, 0, 1, 2, 3, 7, 100, 2 ** 40]) for _ in range(5)] for _ in range(n)],
+                          dtype=np.int64).reshape(n, 5)
+        conf = Obj()
+        conf.min_count = rng.choice([0, 1, 3, 20, 2.5, 1.0])
+        conf.min_maf = rng.choice([0, 0.0, 0.1, 0.3, 0.5, 1, 0.05, 1 / 3.0])
+        exp = []
+        for i, s in enumerate(snps):
+            t = [int(x) for x in totals[i]]
+            cnt = sum(t)
+            skip = cnt < conf.min_count or min(t[BASE_IDX[s.ref]], t[BASE_IDX[s.alt]]) < cnt * conf.min_maf
+            exp.append(0 if skip else 1)
+        assert list(snp_filter(conf, snps, totals)) == exp
