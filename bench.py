@@ -174,8 +174,7 @@ class Batch(object):
         launches = 0
         w0 = time.perf_counter()
         # rows in completion order (what the Matrix-Market writer consumes): copied out under the kernels
-        seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments=True)
-        val = seg.val
+        seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
         w1 = time.perf_counter()
         t_fc = ctx.timing()
         launches += int(t_fc[2])
@@ -189,11 +188,11 @@ class Batch(object):
         t_c = ctx.timing()
         launches += int(t_c[2])
         st.close()
-        chk = (int(val.sum(dtype=np.int64)) + int(dp[2].sum()) + int(ad[2].sum())) if checksum else None
+        chk = (int(seg.val.sum(dtype=np.int64)) + int(dp[2].sum()) + int(ad[2].sum())) if checksum else None
         w4 = time.perf_counter()
-        return dict(nnz=len(val), checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w3 - w2), 1e3 * (w4 - w3)],
+        return dict(nnz=seg.nnz, checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w3 - w2), 1e3 * (w4 - w3)],
                     launches=launches, t_fc=t_fc, t_pileup=t_p, t_count=t_c,
-                    out_bytes=8 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])))
+                    out_bytes=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])))
 
     def make_host(self):
         self.h_fc = self.fc.dreads.download()         # pinned host record arrays
@@ -201,8 +200,7 @@ class Batch(object):
 
     def step_e2e(self):
         ctx, fc, bf = self.ctx, self.fc, self.baf
-        seg = ctx.basefc_host(self.h_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments=True)
-        val = seg.val
+        seg = ctx.basefc_host(self.h_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
         h2d_fc = int(ctx.timing()[13])
         d_bf = ctx.map_reads(self.h_baf)          # zero-copy: 8 B/read over PCIe, rest on demand
         totals, st = ctx.baf_pileup(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
@@ -212,8 +210,8 @@ class Batch(object):
         st.close()
         d_bf.close()
         return dict(h2d=h2d_fc + 8 * self.h_baf.n + 72 * int(self.ctx.timing_pairs),
-                    d2h=8 * (len(val) + len(ad[2]) + len(dp[2]) + len(oth[2])) + totals.nbytes +
-                    12 * len(fc.gid) + 8 * (3 * (len(bf.reg_ptr) - 1) + 3))  # col + val + row_beg/row_cnt | row_ptr
+                    d2h=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])) + totals.nbytes +
+                    12 * len(fc.gid) + 8 * (3 * (len(bf.reg_ptr) - 1) + 3))  # packed entries + row_beg/row_cnt | col + val + row_ptr
 
 
 def cpu_sample(ctx, args, n_sample, n_threads):

@@ -136,6 +136,10 @@ int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *row_ptr, co
 int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
                       const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const int32_t *col,
                       const int32_t *val, int32_t n_threads);
+/* ... and from the "narrow_rows" layout (colval16 + side list of large counts).                */
+int xg_write_mtx_rows16(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
+                        const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const uint32_t *colval16,
+                        int64_t n_over, const int64_t *over_idx, const int32_t *over_val, int32_t n_threads);
 
 /* ---- device side --------------------------------------------------------------------- */
 typedef struct xg_ctx xg_ctx;
@@ -147,7 +151,8 @@ const char *xg_last_error(xg_ctx *ctx);
 /* Options: "coo_rows" (default 1): 0 = results are CSR only (row == NULL; row_ptr, col, val),
  * which saves a third of the device->host result copy.  "row_order" (default 1): 0 = basefc
  * results keep the device's completion order of the rows (see xg_coo), which lets the result
- * copy overlap the counting.                                                                */
+ * copy overlap the counting.  "narrow_rows" (default 0): 1 = with "row_order" 0, entries are packed
+ * into 32 bits (see xg_coo).                                                                  */
 int xg_set_option(xg_ctx *ctx, const char *name, int64_t value);
 
 /* Host -> HBM copy of a decoded batch (the only cross-device traffic of the path).      */
@@ -234,6 +239,13 @@ typedef struct {
     const int64_t *row_ptr;   /* CSR offsets, n_rows + 1; NULL when "row_order" is 0 */
     const int64_t *row_beg;   /* "row_order" 0: first entry of every row, n_rows; else NULL */
     const int32_t *row_cnt;   /* "row_order" 0: entries of every row, n_rows; else NULL */
+    /* "narrow_rows" 1 (with "row_order" 0 and n_cols <= 65536): col and val are NULL and entry k is
+     * colval16[k] = column | count << 16; a count field of 65535 means "look entry k up in the side
+     * list" (over_idx ascending is not guaranteed; n_over entries).  Half the bytes per entry.   */
+    const uint32_t *colval16;
+    int64_t n_over;
+    const int64_t *over_idx;
+    const int32_t *over_val;
 } xg_coo;
 void xg_coo_free(xg_coo *m);
 

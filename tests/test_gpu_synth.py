@@ -208,6 +208,13 @@ def test_basefc_row_segments_equal_sorted_result(gpu_ctx, fc_batch, tmp_path):
     seg_h = gpu_ctx.basefc_host(w.host, w.gid, w.beg, w.end, w.cell_keys, 2000, p, segments=True)
     for a, b in zip(seg_h.to_sorted(), ref):
         assert np.array_equal(a, b)
+    # narrow entries (column | count << 16), resident and streamed, and the text written from them
+    for call, src in ((gpu_ctx.basefc, w.dreads), (gpu_ctx.basefc_host, w.host)):
+        for k in range(2):
+            seg_n = call(src, w.gid, w.beg, w.end, w.cell_keys, 2000, p, segments="narrow")
+            assert seg_n.cv16 is not None and seg_n.nnz == len(ref[2])
+            for a, b in zip(seg_n.to_sorted(), ref):
+                assert np.array_equal(a, b)
     # a smaller and a larger problem after the hint was set
     for sel in (slice(0, len(w.gid) // 3), slice(None)):
         seg = gpu_ctx.basefc(w.dreads, w.gid[sel], w.beg[sel], w.end[sel], w.cell_keys, 2000, p, segments=True)
@@ -222,6 +229,8 @@ def test_basefc_row_segments_equal_sorted_result(gpu_ctx, fc_batch, tmp_path):
     out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
     lib.write_mtx_rows(str(tmp_path / "b.mtx"), seg, out_row, int(emitted.sum()))
     assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "b.mtx"), "rb").read()
+    lib.write_mtx_rows(str(tmp_path / "c.mtx"), seg_n, out_row, int(emitted.sum()))
+    assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "c.mtx"), "rb").read()
 
 
 def test_basefc_row_segments_degenerate_inputs(gpu_ctx, fc_batch):
@@ -288,3 +297,28 @@ def test_baf_full_size_properties(gpu_ctx):
             assert np.array_equal(np.concatenate([parts[0][k][j], parts[1][k][j]]), whole[j])
     _, (ad0, dp0, oth0) = run(b.reg_ptr, b.reg_snp, keep=np.zeros(len(b.snp_gid), dtype=np.uint8))
     assert len(ad0[2]) == len(dp0[2]) == len(oth0[2]) == 0
+
+
+def test_basefc_narrow_entries_with_large_counts(gpu_ctx):
+    """sample mode, one column: every count is far beyond 16 bits and goes through the side list;
+    and more than 65536 columns switch the packing off"""
+    from xcltk_b200 import workload
+    w = workload.make_basefc_workload(gpu_ctx, 3000000, 50, 33472, seed=5, chroms={"20", "21", "22"})
+    conf = Conf()
+    conf.use_barcodes = lambda: False                      # every read -> column of its BAM (one BAM: column 0)
+    p = gpu_params(conf)
+    # whole-contig windows next to the genes: hundreds of thousands of molecules per entry
+    g = np.unique(w.gid).astype(np.int32)
+    gid = np.concatenate([g, w.gid[:300]]).astype(np.int32)
+    beg = np.concatenate([np.zeros(len(g), np.int32), w.beg[:300]]).astype(np.int32)
+    end = np.concatenate([np.full(len(g), 250000000, np.int32), w.end[:300]]).astype(np.int32)
+    ref = [np.array(x) for x in gpu_ctx.basefc(w.dreads, gid, beg, end, None, 1, p)[:3]]
+    assert ref[2].max() > 70000 and ref[2].min() < 65535
+    seg = gpu_ctx.basefc(w.dreads, gid, beg, end, None, 1, p, segments="narrow")
+    assert seg.cv16 is not None and len(seg.over[0]) == int((ref[2] >= 65535).sum()) > 0
+    for a, b in zip(seg.to_sorted(), ref):
+        assert np.array_equal(a, b)
+    p2 = gpu_params(Conf())
+    seg = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, np.arange(1, 70001, dtype=np.uint64) << np.uint64(40), 70000, p2,
+                         segments="narrow")
+    assert seg.cv16 is None                                # too many columns for 16 bits

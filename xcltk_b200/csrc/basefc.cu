@@ -698,6 +698,24 @@ __global__ void __launch_bounds__(256, 6) k_basefc_count(const __grid_constant__
     flush_pairs(P, S);
 }
 
+// "narrow" result entries: column | count << 16; a count that does not fit goes to the side list
+__global__ void k_pack_rows(const int32_t *col, const int32_t *val, uint32_t *packed, long long from, long long to,
+                            long long *over_idx, int32_t *over_val, unsigned int *over_n, unsigned int over_cap) {
+    const long long i = from + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= to) return;
+    const uint32_t c = (uint32_t)col[i], v = (uint32_t)val[i];
+    uint32_t v16 = v;
+    if (v >= 0xffffu) {
+        v16 = 0xffffu;
+        const unsigned int k = atomicAdd(over_n, 1u);
+        if (k < over_cap) {
+            over_idx[k] = i;
+            over_val[k] = (int32_t)v;
+        }
+    }
+    packed[i] = c | (v16 << 16);
+}
+
 __global__ void k_snapshot_cursor(const unsigned long long *cursor, unsigned long long *host_slot) {
     *host_slot = *cursor;
     __threadfence_system();
@@ -1194,14 +1212,53 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         };
         int64_t cap = ctx->fx_nnz_hint > 0 ? ctx->fx_nnz_hint + ctx->fx_nnz_hint / 8 + 1024 : 0;
         cap = std::min<int64_t>(cap, pl.staging_cap + 1);
+        // "narrow" results: column and count of an entry in one 32-bit word (16 bits each; counts of
+        // 65535 and more go to a side list).  Halves the bytes of the result copy, which is what a
+        // host shared by several GPUs runs out of first.
+        bool narrow = ctx->narrow_rows && n_cols <= 65536;
+        const int64_t OVER_CAP = 1 << 20;
+        uint32_t *d_packed = nullptr;
+        long long *d_over_idx = nullptr;
+        int32_t *d_over_val = nullptr;
+        unsigned int *d_over_n = nullptr;
+        if (narrow) {
+            d_packed = (uint32_t *)ctx->get("fx_packed", sizeof(uint32_t) * (size_t)(pl.staging_cap + 1));
+            d_over_idx = (long long *)ctx->get("fx_over_idx", sizeof(long long) * (size_t)OVER_CAP);
+            d_over_val = (int32_t *)ctx->get("fx_over_val", sizeof(int32_t) * (size_t)OVER_CAP);
+            d_over_n = (unsigned int *)ctx->get("fx_over_n", 16);
+            if (!d_packed || !d_over_idx || !d_over_val || !d_over_n) return give_up(XG_E_CUDA, ctx->err);
+            cudaMemsetAsync(d_over_n, 0, 4, ctx->d2h_stream);
+        }
         int32_t *h_col = nullptr, *h_val = nullptr;
-        if (cap > 0) {
-            h_col = (int32_t *)ctx->pinned_get((size_t)cap * 4);
-            h_val = (int32_t *)ctx->pinned_get((size_t)cap * 4);
+        uint32_t *h_packed = nullptr;
+        auto host_buffers = [&](int64_t n_cap) {
+            for (void *q : o->bufs) ctx->pinned_put(q);
+            o->bufs.clear();
+            h_col = h_val = nullptr;
+            h_packed = nullptr;
+            if (narrow) {
+                h_packed = (uint32_t *)ctx->pinned_get((size_t)n_cap * 4);
+                if (h_packed) o->bufs.push_back(h_packed);
+                return h_packed != nullptr;
+            }
+            h_col = (int32_t *)ctx->pinned_get((size_t)n_cap * 4);
+            h_val = (int32_t *)ctx->pinned_get((size_t)n_cap * 4);
             if (h_col) o->bufs.push_back(h_col);
             if (h_val) o->bufs.push_back(h_val);
-            if (!h_col || !h_val) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
-        }
+            return h_col && h_val;
+        };
+        auto queue_rows = [&](int64_t from, int64_t to) {       // staging entries [from, to) -> host
+            const size_t n = (size_t)(to - from);
+            if (narrow) {
+                k_pack_rows<<<(unsigned)((n + 255) / 256), 256, 0, ctx->d2h_stream>>>(st_col, st_val, d_packed, from, to, d_over_idx,
+                                                                                    d_over_val, d_over_n, (unsigned int)OVER_CAP);
+                cudaMemcpyAsync(h_packed + from, d_packed + from, n * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+            } else {
+                cudaMemcpyAsync(h_col + from, st_col + from, n * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+                cudaMemcpyAsync(h_val + from, st_val + from, n * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+            }
+        };
+        if (cap > 0 && !host_buffers(cap)) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
         int64_t done = 0;            // entries already queued for the host
         bool fits = cap > 0;
         for (int32_t e = 0; e < pl.n_epochs && fits; e++) {
@@ -1213,8 +1270,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
                 break;
             }
             if (cur > done) {
-                cudaMemcpyAsync(h_col + done, st_col + done, (size_t)(cur - done) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
-                cudaMemcpyAsync(h_val + done, st_val + done, (size_t)(cur - done) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+                queue_rows(done, cur);
                 done = cur;
             }
         }
@@ -1225,19 +1281,36 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         const int64_t nnz = (int64_t)nnz_u;
         if (!fits || nnz > cap) {
             cudaStreamSynchronize(ctx->d2h_stream);
-            for (void *q : o->bufs) ctx->pinned_put(q);
-            o->bufs.clear();
             cap = nnz + nnz / 8 + 1024;
-            h_col = (int32_t *)ctx->pinned_get((size_t)cap * 4);
-            h_val = (int32_t *)ctx->pinned_get((size_t)cap * 4);
-            if (h_col) o->bufs.push_back(h_col);
-            if (h_val) o->bufs.push_back(h_val);
-            if (!h_col || !h_val) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
+            if (!host_buffers(cap)) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
+            if (narrow) cudaMemsetAsync(d_over_n, 0, 4, ctx->d2h_stream);
             done = 0;
         }
-        if (nnz > done) {
-            cudaMemcpyAsync(h_col + done, st_col + done, (size_t)(nnz - done) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
-            cudaMemcpyAsync(h_val + done, st_val + done, (size_t)(nnz - done) * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+        if (nnz > done) queue_rows(done, nnz);
+        unsigned int n_over = 0;
+        if (narrow) {
+            cudaMemcpyAsync(&n_over, d_over_n, 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+            ce = cudaStreamSynchronize(ctx->d2h_stream);
+            if (ce != cudaSuccess) return give_up(XG_E_CUDA, std::string("result D2H: ") + cudaGetErrorString(ce));
+            if ((int64_t)n_over > OVER_CAP) {       // too many large counts for the side list: plain 32-bit columns
+                narrow = false;
+                if (!host_buffers(cap)) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
+                if (nnz > 0) queue_rows(0, nnz);
+                n_over = 0;
+            }
+        }
+        long long *h_over_idx = nullptr;
+        int32_t *h_over_val = nullptr;
+        if (narrow) {
+            h_over_idx = (long long *)ctx->pinned_get(((size_t)n_over + 1) * 8);
+            h_over_val = (int32_t *)ctx->pinned_get(((size_t)n_over + 1) * 4);
+            if (h_over_idx) o->bufs.push_back(h_over_idx);
+            if (h_over_val) o->bufs.push_back(h_over_val);
+            if (!h_over_idx || !h_over_val) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
+            if (n_over) {
+                cudaMemcpyAsync(h_over_idx, d_over_idx, (size_t)n_over * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+                cudaMemcpyAsync(h_over_val, d_over_val, (size_t)n_over * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+            }
         }
         int64_t *h_beg = (int64_t *)ctx->pinned_get((size_t)(n_rows + 1) * 8);
         int32_t *h_cnt = (int32_t *)ctx->pinned_get((size_t)(n_rows + 1) * 4);
@@ -1258,6 +1331,10 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         o->m.n_cols = n_cols;
         o->m.col = h_col;
         o->m.val = h_val;
+        o->m.colval16 = h_packed;
+        o->m.n_over = narrow ? (int64_t)n_over : 0;
+        o->m.over_idx = (const int64_t *)h_over_idx;
+        o->m.over_val = h_over_val;
         o->m.row_beg = h_beg;
         o->m.row_cnt = h_cnt;
         *out = &o->m;

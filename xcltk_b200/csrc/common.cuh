@@ -52,6 +52,7 @@ struct xg_ctx {
     std::string err;
     double timing[16] = {};
     bool coo_rows = true;                  // results carry the row array (else CSR: row_ptr only)
+    bool narrow_rows = false;              // ... and, with row_order 0, 16-bit column | 16-bit count per entry
     bool row_order = true;                 // basefc results sorted by row (else rows as completed + row_beg/row_cnt)
     // growable named scratch buffers (avoid cudaMalloc/cudaFree on every call)
     struct Buf {

@@ -74,6 +74,10 @@ int xg_set_option(xg_ctx *ctx, const char *name, int64_t value) {
         ctx->coo_rows = value != 0;
         return XG_OK;
     }
+    if (std::string(name) == "narrow_rows") {
+        ctx->narrow_rows = value != 0;
+        return XG_OK;
+    }
     if (std::string(name) == "row_order") {
         ctx->row_order = value != 0;
         return XG_OK;

@@ -18,6 +18,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "bamfile.hpp"
@@ -695,9 +696,11 @@ inline char *put_int(char *p, uint32_t v) {
 }
 }  // namespace
 
-extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
-                                 const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const int32_t *col,
-                                 const int32_t *val, int32_t n_threads) {
+namespace {
+// entry(k, &col, &val): column (0-based) and count of entry k
+template <class Entry>
+int write_rows_impl(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
+                    const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, Entry entry, int32_t n_threads) {
     if (!path || !row_beg || !row_cnt || !out_row || n_rows_in < 0)
         return fail(XG_E_ARG, "xg_write_mtx: bad argument");
     if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
@@ -748,11 +751,13 @@ extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int6
                 char *p = b.p.get();
                 for (int32_t r = r0; r < r1; r++)
                     for (int64_t k = row_beg[r]; k < row_beg[r] + row_cnt[r]; k++) {
+                        uint32_t c, v;
+                        entry(k, &c, &v);
                         p = put_int(p, (uint32_t)out_row[r]);
                         *p++ = '\t';
-                        p = put_int(p, (uint32_t)col[k] + 1u);
+                        p = put_int(p, c + 1u);
                         *p++ = '\t';
-                        p = put_int(p, (uint32_t)val[k]);
+                        p = put_int(p, v);
                         *p++ = '\n';
                     }
                 b.n = (size_t)(p - b.p.get());
@@ -768,6 +773,37 @@ extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int6
     if (fclose(fp) != 0) ok = false;
     if (!ok) return fail(XG_E_IO, std::string("short write on '") + path + "'");
     return XG_OK;
+}
+}  // namespace
+
+extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
+                                 const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const int32_t *col,
+                                 const int32_t *val, int32_t n_threads) {
+    if (!col || !val) return fail(XG_E_ARG, "xg_write_mtx: bad argument");
+    return write_rows_impl(path, n_rows_in, row_beg, row_cnt, out_row, n_rows_out, n_cols,
+                           [=](int64_t k, uint32_t *c, uint32_t *v) {
+                               *c = (uint32_t)col[k];
+                               *v = (uint32_t)val[k];
+                           },
+                           n_threads);
+}
+
+extern "C" int xg_write_mtx_rows16(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
+                                   const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const uint32_t *colval16,
+                                   int64_t n_over, const int64_t *over_idx, const int32_t *over_val,
+                                   int32_t n_threads) {
+    if (!colval16 || n_over < 0 || (n_over && (!over_idx || !over_val))) return fail(XG_E_ARG, "xg_write_mtx: bad argument");
+    std::unordered_map<int64_t, uint32_t> over;
+    for (int64_t i = 0; i < n_over; i++) over[over_idx[i]] = (uint32_t)over_val[i];
+    const std::unordered_map<int64_t, uint32_t> *ov = &over;
+    return write_rows_impl(path, n_rows_in, row_beg, row_cnt, out_row, n_rows_out, n_cols,
+                           [=](int64_t k, uint32_t *c, uint32_t *v) {
+                               const uint32_t w = colval16[k];
+                               *c = w & 0xffffu;
+                               *v = w >> 16;
+                               if (*v == 0xffffu) *v = ov->at(k);
+                           },
+                           n_threads);
 }
 
 extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *row_ptr, const int32_t *out_row,

@@ -68,7 +68,8 @@ class Barcodes(C.Structure):
 class Coo(C.Structure):
     _fields_ = [("nnz", C.c_int64), ("n_rows", C.c_int32), ("n_cols", C.c_int32),
                 ("row", c_i32p), ("col", c_i32p), ("val", c_i32p), ("row_ptr", c_i64p),
-                ("row_beg", c_i64p), ("row_cnt", c_i32p)]
+                ("row_beg", c_i64p), ("row_cnt", c_i32p),
+                ("colval16", c_u32p), ("n_over", C.c_int64), ("over_idx", c_i64p), ("over_val", c_i32p)]
 
 
 class Snps(C.Structure):
@@ -103,6 +104,8 @@ SYMBOLS = {
     "xg_host_last_error": (C.c_char_p, []),
     "xg_write_mtx_rows": (C.c_int, [C.c_char_p, C.c_int32, c_i64p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p,
                                     c_i32p, C.c_int32]),
+    "xg_write_mtx_rows16": (C.c_int, [C.c_char_p, C.c_int32, c_i64p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_u32p,
+                                      C.c_int64, c_i64p, c_i32p, C.c_int32]),
     "xg_write_mtx": (C.c_int, [C.c_char_p, C.c_int32, c_i64p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p,
                                C.c_int32]),
     "xg_create": (C.c_int, [C.c_int32, C.POINTER(_P)]),
@@ -353,13 +356,31 @@ class LazyRows(object):
 
 class RowSegments(object):
     """basefc result with the rows in the order the device completed them (context option
-    row_order = 0): row r is col/val[row_beg[r] : row_beg[r] + row_cnt[r]], sorted by col.  This
-    is what the Matrix-Market writer consumes (write_mtx_rows); to_sorted() gives (row, col, val)
-    sorted by (row, col) for everything else."""
+    row_order = 0): row r is entries [row_beg[r], row_beg[r] + row_cnt[r]), sorted by col.  The
+    entries are either `col` / `val` (int32 each) or, with the narrow_rows option, `cv16` (uint32:
+    column | count << 16, counts >= 65535 in the side list `over`); `.col` / `.val` unpack on
+    demand.  This is what the Matrix-Market writer consumes (write_mtx_rows); to_sorted() gives
+    (row, col, val) sorted by (row, col) for everything else."""
 
-    def __init__(self, row_beg, row_cnt, col, val, shape):
-        self.row_beg, self.row_cnt, self.col, self.val, self.shape = row_beg, row_cnt, col, val, shape
-        self.nnz = len(val)
+    def __init__(self, row_beg, row_cnt, col, val, shape, cv16=None, over=None):
+        self.row_beg, self.row_cnt, self.shape = row_beg, row_cnt, shape
+        self._col, self._val, self.cv16, self.over = col, val, cv16, over
+        self.nnz = len(val) if cv16 is None else len(cv16)
+
+    @property
+    def col(self):
+        if self._col is None:
+            self._col = (np.asarray(self.cv16) & np.uint32(0xffff)).astype(np.int32)
+        return self._col
+
+    @property
+    def val(self):
+        if self._val is None:
+            v = (np.asarray(self.cv16) >> np.uint32(16)).astype(np.int32)
+            if self.over is not None and len(self.over[0]):
+                v[self.over[0]] = self.over[1]
+            self._val = v
+        return self._val
 
     def to_sorted(self):
         cnt = self.row_cnt.astype(np.int64)
@@ -370,16 +391,23 @@ class RowSegments(object):
 
 
 def write_mtx_rows(path, seg, out_row, n_rows_out, n_threads=0):
-    """RowSegments -> MatrixMarket text (xg_write_mtx_rows)."""
+    """RowSegments -> MatrixMarket text (xg_write_mtx_rows / xg_write_mtx_rows16)."""
     lib = load()
     out_row = np.ascontiguousarray(out_row, dtype=np.int32)
-    col, val = seg.col, seg.val
-    if seg.nnz == 0:
-        col = np.zeros(1, dtype=np.int32)
-        val = np.zeros(1, dtype=np.int32)
-    rc = lib.xg_write_mtx_rows(path.encode(), len(seg.row_cnt), as_ptr(seg.row_beg, c_i64p),
-                               as_ptr(seg.row_cnt, c_i32p), as_ptr(out_row, c_i32p), int(n_rows_out),
-                               int(seg.shape[1]), as_ptr(col, c_i32p), as_ptr(val, c_i32p), n_threads)
+    args = (path.encode(), len(seg.row_cnt), as_ptr(seg.row_beg, c_i64p), as_ptr(seg.row_cnt, c_i32p),
+            as_ptr(out_row, c_i32p), int(n_rows_out), int(seg.shape[1]))
+    if seg.cv16 is not None:
+        cv = seg.cv16 if seg.nnz else np.zeros(1, dtype=np.uint32)
+        oi = np.ascontiguousarray(seg.over[0], dtype=np.int64) if seg.over is not None else np.zeros(0, np.int64)
+        ov = np.ascontiguousarray(seg.over[1], dtype=np.int32) if seg.over is not None else np.zeros(0, np.int32)
+        rc = lib.xg_write_mtx_rows16(*args, as_ptr(cv, c_u32p), len(oi), as_ptr(oi, c_i64p) if len(oi) else None,
+                                     as_ptr(ov, c_i32p) if len(ov) else None, n_threads)
+    else:
+        col, val = seg.col, seg.val
+        if seg.nnz == 0:
+            col = np.zeros(1, dtype=np.int32)
+            val = np.zeros(1, dtype=np.int32)
+        rc = lib.xg_write_mtx_rows(*args, as_ptr(col, c_i32p), as_ptr(val, c_i32p), n_threads)
     if rc != 0:
         raise XgError(rc, lib.xg_host_last_error().decode())
 
@@ -394,6 +422,17 @@ def coo_to_numpy(lib, pcoo, copy_below=1 << 16, ctx_obj=None):
     if bool(m.row_beg):                       # rows in completion order
         row_beg = np_view(m.row_beg, shape[0], np.int64).copy()
         row_cnt = np_view(m.row_cnt, shape[0], np.int32).copy()
+        if bool(m.colval16):                  # narrow entries
+            n_over = int(m.n_over)
+            over = (np_view(m.over_idx, n_over, np.int64).copy(), np_view(m.over_val, n_over, np.int32).copy())
+            v = np_view(m.colval16, nnz, np.uint32)
+            if nnz <= copy_below:
+                cv = v.copy()
+                lib.xg_coo_free(pcoo)
+            else:
+                cv = v.view(_View)
+                cv._owner = _CooOwner(lib, pcoo, ctx_obj)
+            return RowSegments(row_beg, row_cnt, None, None, shape, cv16=cv, over=over)
         views = [np_view(p, nnz, np.int32) for p in (m.col, m.val)]
         if nnz <= copy_below:
             cv = [v.copy() for v in views]
@@ -493,7 +532,8 @@ class Context(object):
 
     def basefc(self, dreads, gid, beg, end, cell_keys, n_samples, params, segments=False):
         """(row, col, val, shape) sorted by (row, col); segments=True: a RowSegments (rows in
-        completion order, copied out while the counting is still running)."""
+        completion order, copied out while the counting is still running); segments="narrow": the
+        same with 32-bit packed entries when there are at most 65536 columns."""
         gid = np.ascontiguousarray(gid, dtype=np.int32)
         beg = np.ascontiguousarray(beg, dtype=np.int32)
         end = np.ascontiguousarray(end, dtype=np.int32)
@@ -502,6 +542,7 @@ class Context(object):
         b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
         out = C.POINTER(Coo)()
         self.lib.xg_set_option(self.h, b"row_order", 0 if segments else 1)
+        self.lib.xg_set_option(self.h, b"narrow_rows", 1 if segments == "narrow" else 0)
         try:
             self._check(self.lib.xg_basefc(self.h, dreads.h, C.byref(f), C.byref(b), C.byref(params.c),
                                            C.byref(out)))
@@ -519,6 +560,7 @@ class Context(object):
         b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
         out = C.POINTER(Coo)()
         self.lib.xg_set_option(self.h, b"row_order", 0 if segments else 1)
+        self.lib.xg_set_option(self.h, b"narrow_rows", 1 if segments == "narrow" else 0)
         try:
             self._check(self.lib.xg_basefc_host(self.h, host_reads.ptr, C.byref(f), C.byref(b), C.byref(params.c),
                                                 C.byref(out)))

@@ -292,7 +292,7 @@ def count_features(conf, batch=None):
             conf.shard_sizes = [len(s) for s in shards]
         else:
             params = engine.make_params(conf, batch.stats["max_aln_len"], with_include=True)
-            seg = bool(getattr(conf, "row_segments", False))     # fc_core: rows as completed, for the MTX writer
+            seg = "narrow" if getattr(conf, "row_segments", False) else False   # fc_core: rows as completed, packed
             if batch.dreads is None:       # pinned host batch: H2D streamed under the kernels
                 res = batch.ctx.basefc_host(batch.host, gid, beg, end, cell_keys, len(conf.samples), params,
                                             segments=seg)
