@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--baf-reads", type=float, default=50e6, help="baf reads per GPU (C2)")
     ap.add_argument("--baf-cells", type=int, default=5000)
     ap.add_argument("--snps", type=int, default=200000)
-    ap.add_argument("--cpu-sample", type=float, default=4e6, help="reads of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=float, default=3e8, help="reads of the CPU legs (default: the whole C3 basefc batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
