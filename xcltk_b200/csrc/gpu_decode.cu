@@ -680,6 +680,8 @@ struct Decoder {
     unsigned long long *bases = nullptr;      // 3 x blk_cap
     int32_t *d_tid_map = nullptr;
     cudaEvent_t ev_win = nullptr;             // the window buffers are free again
+    cudaStream_t ist2 = nullptr;              // every other chunk is inflated here: a launch is about one wave of CTAs,
+    cudaEvent_t ev_i2 = nullptr;              // two streams let the tail of one overlap the head of the next
     // the batch under construction (capacities in elements)
     int2 *pos_end = nullptr;
     uint32_t *fmq = nullptr, *cig_off = nullptr, *seq_off = nullptr, *cigar = nullptr, *seq = nullptr;
@@ -748,7 +750,8 @@ struct Decoder {
         hk = nullptr;
         d_tid_map = nullptr;
         if (ev_win) cudaEventDestroy(ev_win);
-        ev_win = nullptr;
+        if (ev_i2) cudaEventDestroy(ev_i2);
+        ev_win = ev_i2 = nullptr;
     }
     void release_batch() {
         void *ps[] = {pos_end, fmq, cig_off, keys, seq_off, cigar, seq};
@@ -866,6 +869,7 @@ int flush_window(Decoder &D, BamState &B, int32_t nb) {
     cudaStream_t st = ctx->stream;
     if (nb <= 0) return XG_OK;
     D.n_windows++;
+    if (D.ist2) cudaStreamWaitEvent(st, D.ev_i2, 0);        // the chunks inflated on the second stream
     cudaEventRecord(ctx->ev[0], st);
     k_walk<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(D.blocks, nb, B.hdr_end, D.d_tid_map, B.n_ref, D.want_seq, D.info,
                                                       D.cnt + 2);
@@ -987,6 +991,7 @@ int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid
     cudaEvent_t done[2] = {nullptr, nullptr};
     auto finish = [&](int code, const std::string &msg) {
         cudaStreamSynchronize(ctx->copy_stream);       // staging buffers may still be in flight
+        if (D.ist2) cudaStreamSynchronize(D.ist2);
         cudaStreamSynchronize(ctx->stream);
         for (int k = 0; k < 2; k++) {
             if (stage[k]) ctx->pinned_put(stage[k]);
@@ -1135,8 +1140,10 @@ int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid
             cudaMemcpyAsync(D.blocks + win_blocks, dv.data(), dv.size() * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice,
                             ctx->copy_stream);
         cudaEventRecord(done[si], ctx->copy_stream);
-        cudaStreamWaitEvent(ctx->stream, done[si], 0);
-        launch_inflate(ctx->stream, D.comp, D.blocks + win_blocks, (int32_t)dv.size(), D.cnt + 0);
+        cudaStream_t ist = (k & 1) && D.ist2 ? D.ist2 : ctx->stream;
+        cudaStreamWaitEvent(ist, done[si], 0);
+        launch_inflate(ist, D.comp, D.blocks + win_blocks, (int32_t)dv.size(), D.cnt + 0);
+        if (ist != ctx->stream) cudaEventRecord(D.ev_i2, ist);
         win_blocks += (int32_t)hb.size();
         D.comp_done += len;
         prev_data = data;
@@ -1264,11 +1271,18 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
     };
     if (!D.comp || !D.slab || !D.blocks || !D.info || !D.bases || !D.hk)
         return bail(XG_E_UNSUPPORTED, "the inflate window does not fit the device");
-    if (cudaEventCreateWithFlags(&D.ev_win, cudaEventDisableTiming) != cudaSuccess) return bail(XG_E_CUDA, "cudaEventCreate");
+    if (cudaEventCreateWithFlags(&D.ev_win, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&D.ev_i2, cudaEventDisableTiming) != cudaSuccess)
+        return bail(XG_E_CUDA, "cudaEventCreate");
+    if (!ctx->aux[2])
+        for (auto &s2 : ctx->aux)
+            if (!s2 && cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess) return bail(XG_E_CUDA, "cudaStreamCreate");
+    if (!getenv("XG_INFLATE_ONE_STREAM")) D.ist2 = ctx->aux[2];
     cudaStream_t st = ctx->stream;
     cudaMemsetAsync(D.cnt, 0, 8 * sizeof(int), st);
     cudaEventRecord(ctx->ev[2], st);
     cudaEventRecord(D.ev_win, st);
+    cudaEventRecord(D.ev_i2, st);
     lap("setup");
     std::vector<int64_t> bam_end((size_t)n_bams, 0);
     for (int32_t b = 0; b < n_bams; b++) {
