@@ -216,3 +216,32 @@ def test_snp_filter_is_the_references_scalar_expression():
             skip = cnt < conf.min_count or min(t[BASE_IDX[s.ref]], t[BASE_IDX[s.alt]]) < cnt * conf.min_maf
             exp.append(0 if skip else 1)
         assert list(snp_filter(conf, snps, totals)) == exp
+
+
+def test_write_mtx_rows16_narrow_entries_and_side_list(tmp_path):
+    """the packed layout (column | count << 16, counts >= 65535 in a side list) writes the text
+    of the plain layout"""
+    import numpy as np
+    from xcltk_b200 import lib
+    rng = np.random.RandomState(9)
+    n_rows, n_cols = 120, 4000
+    cnt = rng.randint(0, 30, size=n_rows).astype(np.int32)
+    beg = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int64)
+    nnz = int(cnt.sum())
+    col = np.concatenate([np.sort(rng.choice(n_cols, c, replace=False)) for c in cnt] + [np.zeros(0, int)]).astype(np.int32)
+    val = rng.randint(1, 300, size=nnz).astype(np.int32)
+    big = rng.choice(nnz, 25, replace=False)
+    val[big] = rng.randint(65535, 5000000, size=25)
+    val[big[0]] = 65535                                   # exactly the escape value
+    plain = lib.RowSegments(beg, cnt, col, val, (n_rows, n_cols))
+    cv = (col.astype(np.uint32) | (np.minimum(val, 65535).astype(np.uint32) << np.uint32(16)))
+    over_idx = np.nonzero(val >= 65535)[0].astype(np.int64)
+    perm = rng.permutation(len(over_idx))                 # the side list is not ordered
+    narrow = lib.RowSegments(beg, cnt, None, None, (n_rows, n_cols), cv16=cv, over=(over_idx[perm], val[over_idx][perm]))
+    assert np.array_equal(narrow.col, col) and np.array_equal(narrow.val, val)
+    emitted = cnt > 0
+    out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
+    lib.write_mtx_rows(str(tmp_path / "a.mtx"), plain, out_row, int(emitted.sum()), 2)
+    lib.write_mtx_rows(str(tmp_path / "b.mtx"), narrow, out_row, int(emitted.sum()), 3)
+    a, b = open(str(tmp_path / "a.mtx"), "rb").read(), open(str(tmp_path / "b.mtx"), "rb").read()
+    assert a == b and b"\t65535\n" in a
