@@ -5,6 +5,7 @@ xcltk/rdr/fc/main.py:191-235, xcltk/baf/fc/main.py:156-211): one context per GPU
 read batch is uploaded once and every feature / SNP is evaluated against it on the device.
 """
 
+import logging
 import math
 import os
 
@@ -87,6 +88,8 @@ def _device_decode(ctx, sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, keys
         return None
     res = ctx.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, keyspace)
     if res is None:
+        logging.getLogger(__name__).info("device decoder declined (%s); decoding on the host.",
+                                         getattr(ctx, "decode_fallback_reason", "?"))
         return None
     dreads, seen = res
     i = dreads.info()
