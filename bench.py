@@ -355,6 +355,25 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, n_epochs),
                 "note": "launch durations from CUDA events on the launching streams; epochs overlap, so the "
                         "sum over-counts (conservative)"}
+    # the same kernel with the epochs' streams serialised (extra calls outside the timed region): its launch
+    # durations without a neighbour on the SMs
+    prev_overlap = os.environ.get("XG_OVERLAP")
+    try:
+        os.environ["XG_OVERLAP"] = "0"
+        ts = []
+        for _ in range(2):
+            batch.ctx.basefc(batch.fc.dreads, batch.fc.gid, batch.fc.beg, batch.fc.end, batch.fc.cell_keys,
+                             batch.fc.n_cells, batch.fc.params, segments="narrow")
+            ts.append(batch.ctx.timing()[1])
+        a2 = alg_bytes / (ts[-1] * 1e-3) / 1e9
+        roofline["serialised"] = {"achieved": a2, "frac": a2 / peak, "avg_launch_ms": ts[-1] / max(1, n_epochs)}
+    except Exception as ex:
+        roofline["serialised"] = {"error": str(ex)[:120]}
+    finally:
+        if prev_overlap is None:
+            os.environ.pop("XG_OVERLAP", None)
+        else:
+            os.environ["XG_OVERLAP"] = prev_overlap
 
     e2e = None
     if not args.no_e2e:
