@@ -393,7 +393,7 @@ def main():
             e2e = {"value": None, "unit": "reads/s", "error": str(ex)[:200]}
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:      # the CPU and decode legs: rank 0 at N=1 only
         from oracle import oracle  # noqa: F401
         run, host = cpu_sample(ctx, args, args.cpu_sample, os.cpu_count() or 1)
         run()
@@ -405,7 +405,7 @@ def main():
     decode = None
     device_decode = None
     file_to_matrix = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:      # the CPU and decode legs: rank 0 at N=1 only
         # host BGZF/BAM decode throughput (the stage before the path) on a bounded sample
         try:
             import tempfile
