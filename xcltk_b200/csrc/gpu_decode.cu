@@ -988,19 +988,25 @@ int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid
     const uint64_t csize = (uint64_t)stt.st_size;
     const size_t STAGE_BYTES = stage_bytes();
     uint8_t *stage[2] = {(uint8_t *)ctx->pinned_get(STAGE_HEAD + STAGE_BYTES), (uint8_t *)ctx->pinned_get(STAGE_HEAD + STAGE_BYTES)};
+    // the chunk's block descriptors travel through pinned memory too: a copy from pageable memory
+    // synchronises the stream first, i.e. waits for the chunk's own bytes to arrive
+    constexpr size_t DESC_STAGE = 1u << 20;
+    BgzfBlockDev *desc_stage[2] = {(BgzfBlockDev *)ctx->pinned_get(DESC_STAGE), (BgzfBlockDev *)ctx->pinned_get(DESC_STAGE)};
     cudaEvent_t done[2] = {nullptr, nullptr};
     auto finish = [&](int code, const std::string &msg) {
         cudaStreamSynchronize(ctx->copy_stream);       // staging buffers may still be in flight
         if (D.ist2) cudaStreamSynchronize(D.ist2);
         cudaStreamSynchronize(ctx->stream);
         for (int k = 0; k < 2; k++) {
+            if (desc_stage[k]) ctx->pinned_put(desc_stage[k]);
             if (stage[k]) ctx->pinned_put(stage[k]);
             if (done[k]) cudaEventDestroy(done[k]);
         }
         close(fd);
         return code ? ctx->fail(code, msg) : XG_OK;
     };
-    if (!stage[0] || !stage[1]) return finish(XG_E_NOMEM, "out of pinned host memory for the staging buffers");
+    if (!stage[0] || !stage[1] || !desc_stage[0] || !desc_stage[1])
+        return finish(XG_E_NOMEM, "out of pinned host memory for the staging buffers");
     cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming);
     if (csize == 0) return finish(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (empty file)");
@@ -1136,9 +1142,15 @@ int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid
             dv[i].pad_ = 0;
             win_infl += hb[i].isize;
         }
-        if (!dv.empty())
-            cudaMemcpyAsync(D.blocks + win_blocks, dv.data(), dv.size() * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice,
+        if (!dv.empty()) {
+            const BgzfBlockDev *src = dv.data();
+            if (dv.size() * sizeof(BgzfBlockDev) <= DESC_STAGE) {
+                memcpy(desc_stage[si], dv.data(), dv.size() * sizeof(BgzfBlockDev));
+                src = desc_stage[si];
+            }
+            cudaMemcpyAsync(D.blocks + win_blocks, src, dv.size() * sizeof(BgzfBlockDev), cudaMemcpyHostToDevice,
                             ctx->copy_stream);
+        }
         cudaEventRecord(done[si], ctx->copy_stream);
         cudaStream_t ist = (k & 1) && D.ist2 ? D.ist2 : ctx->stream;
         cudaStreamWaitEvent(ist, done[si], 0);
