@@ -801,7 +801,10 @@ extern "C" int xg_write_mtx_rows16(const char *path, int32_t n_rows_in, const in
                                const uint32_t w = colval16[k];
                                *c = w & 0xffffu;
                                *v = w >> 16;
-                               if (*v == 0xffffu) *v = ov->at(k);
+                               if (*v == 0xffffu) {
+                                   auto it = ov->find(k);
+                                   if (it != ov->end()) *v = it->second;      // (an entry missing from the list keeps 65535)
+                               }
                            },
                            n_threads);
 }
