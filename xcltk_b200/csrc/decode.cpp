@@ -414,9 +414,26 @@ void xg_reads_free(xg_reads *r) {
     delete o;
 }
 
+static int decode_bams_impl(int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
+                            const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag,
+                            int32_t want_seq, int32_t n_threads, xg_keyspace *ks, xg_reads **out);
+
+// no C++ exception crosses the C boundary
 int xg_decode_bams(int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
                    const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag,
                    int32_t want_seq, int32_t n_threads, xg_keyspace *ks, xg_reads **out) {
+    try {
+        return decode_bams_impl(n_bams, paths, tid_map, tid_map_len, cell_tag, umi_tag, want_seq, n_threads, ks, out);
+    } catch (const std::bad_alloc &) {
+        return fail(XG_E_NOMEM, "out of host memory while decoding");
+    } catch (const std::exception &e) {
+        return fail(XG_E_IO, std::string("decode failed: ") + e.what());
+    }
+}
+
+static int decode_bams_impl(int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
+                            const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag,
+                            int32_t want_seq, int32_t n_threads, xg_keyspace *ks, xg_reads **out) {
     if (n_bams < 0 || !out || !ks) return fail(XG_E_ARG, "xg_decode_bams: bad argument");
     if (cell_tag && strlen(cell_tag) != 2) return fail(XG_E_ARG, "cell tag must have 2 characters");
     if (umi_tag && strlen(umi_tag) != 2) return fail(XG_E_ARG, "UMI tag must have 2 characters");
@@ -780,12 +797,16 @@ extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int6
                                  const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const int32_t *col,
                                  const int32_t *val, int32_t n_threads) {
     if (!col || !val) return fail(XG_E_ARG, "xg_write_mtx: bad argument");
-    return write_rows_impl(path, n_rows_in, row_beg, row_cnt, out_row, n_rows_out, n_cols,
-                           [=](int64_t k, uint32_t *c, uint32_t *v) {
-                               *c = (uint32_t)col[k];
-                               *v = (uint32_t)val[k];
-                           },
-                           n_threads);
+    try {
+        return write_rows_impl(path, n_rows_in, row_beg, row_cnt, out_row, n_rows_out, n_cols,
+                               [=](int64_t k, uint32_t *c, uint32_t *v) {
+                                   *c = (uint32_t)col[k];
+                                   *v = (uint32_t)val[k];
+                               },
+                               n_threads);
+    } catch (const std::exception &e) {
+        return fail(XG_E_NOMEM, std::string("xg_write_mtx: ") + e.what());
+    }
 }
 
 extern "C" int xg_write_mtx_rows16(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
@@ -793,6 +814,7 @@ extern "C" int xg_write_mtx_rows16(const char *path, int32_t n_rows_in, const in
                                    int64_t n_over, const int64_t *over_idx, const int32_t *over_val,
                                    int32_t n_threads) {
     if (!colval16 || n_over < 0 || (n_over && (!over_idx || !over_val))) return fail(XG_E_ARG, "xg_write_mtx: bad argument");
+    try {
     std::unordered_map<int64_t, uint32_t> over;
     for (int64_t i = 0; i < n_over; i++) over[over_idx[i]] = (uint32_t)over_val[i];
     const std::unordered_map<int64_t, uint32_t> *ov = &over;
@@ -807,6 +829,9 @@ extern "C" int xg_write_mtx_rows16(const char *path, int32_t n_rows_in, const in
                                }
                            },
                            n_threads);
+    } catch (const std::exception &e) {
+        return fail(XG_E_NOMEM, std::string("xg_write_mtx: ") + e.what());
+    }
 }
 
 extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *row_ptr, const int32_t *out_row,

@@ -1229,9 +1229,29 @@ int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t 
     return XG_OK;
 }
 
+static int decode_bams_device_impl(xg_ctx *ctx, int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
+                                   const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag,
+                                   int32_t want_seq, xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen);
+
+// no C++ exception crosses the C boundary (host vectors of the block index, the key strings ...)
 int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
                           const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag, int32_t want_seq,
                           xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen) {
+    try {
+        return decode_bams_device_impl(ctx, n_bams, paths, tid_map, tid_map_len, cell_tag, umi_tag, want_seq, ks, out,
+                                       n_records_seen);
+    } catch (const std::exception &e) {
+        if (ctx && ctx->stream) {
+            cudaStreamSynchronize(ctx->stream);
+            if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        }
+        return ctx ? ctx->fail(XG_E_NOMEM, std::string("device decode: ") + e.what()) : XG_E_NOMEM;
+    }
+}
+
+static int decode_bams_device_impl(xg_ctx *ctx, int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
+                                   const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag,
+                                   int32_t want_seq, xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen) {
     if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
     if (n_bams < 0 || !out) return ctx->fail(XG_E_ARG, "xg_decode_bams_device: bad argument");
     if (cell_tag && strlen(cell_tag) != 2) return ctx->fail(XG_E_ARG, "cell tag must have 2 characters");
