@@ -1,48 +1,53 @@
-"""Logging in the reference's line format `[I::module::func] msg`
-(xcltk/utils/xlog.py:7-89; basefc logs to stderr, rdr/fc/main.py:84)."""
+"""Log lines shaped like the reference's: `[I::module::func] msg`, with `::<time>` appended
+to the bracket when a date format is set (xcltk/utils/xlog.py:7-89; basefc logs to stderr,
+rdr/fc/main.py:84)."""
 
 import logging
 
-_LEVEL = {logging.DEBUG: "D", logging.INFO: "I", logging.WARNING: "W",
-          logging.ERROR: "E", logging.CRITICAL: "C"}
+_LETTER = dict(zip((logging.DEBUG, logging.INFO, logging.WARNING, logging.ERROR, logging.CRITICAL), "DIWEC"))
 
 
-class XFormatter(logging.Formatter):
+class LineFormatter(logging.Formatter):
+    """One bracketed prefix, then the message; tracebacks / stack text follow on their own lines."""
+
     def __init__(self, datefmt=None):
-        super().__init__(fmt=None, datefmt=datefmt)
+        logging.Formatter.__init__(self, None, datefmt)
 
-    def format(self, record):
-        record.message = record.getMessage()
-        head = "[" + _LEVEL.get(record.levelno, "U")
-        if record.module:
-            head += "::%s" % record.module
-        if record.funcName:
-            head += "::%s" % record.funcName
+    def _prefix(self, rec):
+        parts = [_LETTER.get(rec.levelno, "U")]
+        parts.extend(x for x in (rec.module, rec.funcName) if x)
         if self.datefmt:
-            head += "::" + self.formatTime(record, self.datefmt)
-        s = head + "] " + (str(record.message) if record.message else "")
-        if record.exc_info and not record.exc_text:
-            record.exc_text = self.formatException(record.exc_info)
-        if record.exc_text:
-            s = s.rstrip("\n") + "\n" + record.exc_text
-        if record.stack_info:
-            s = s.rstrip("\n") + "\n" + self.formatStack(record.stack_info)
-        return s
+            parts.append(self.formatTime(rec, self.datefmt))
+        return "[%s] " % "::".join(parts)
+
+    def format(self, rec):
+        rec.message = rec.getMessage()
+        text = self._prefix(rec) + (str(rec.message) if rec.message else "")
+        if rec.exc_info and not rec.exc_text:
+            rec.exc_text = self.formatException(rec.exc_info)
+        for extra in (rec.exc_text, self.formatStack(rec.stack_info) if rec.stack_info else None):
+            if extra:
+                text = text + ("" if text.endswith("\n") else "\n") + extra
+        return text
 
 
-def init_logging(log_file=None, stream=None, fh_level=logging.DEBUG,
-                 fh_datefmt="%Y-%m-%d %H:%M:%S", ch_level=logging.INFO, ch_datefmt=None):
+XFormatter = LineFormatter      # the reference's name for it
+
+
+def _attach(handler, level, datefmt, to):
+    handler.setLevel(level)
+    handler.setFormatter(LineFormatter(datefmt))
+    to.append(handler)
+
+
+def init_logging(log_file=None, stream=None, fh_level=logging.DEBUG, fh_datefmt="%Y-%m-%d %H:%M:%S",
+                 ch_level=logging.INFO, ch_datefmt=None):
+    """File handler (timestamps) and / or stream handler (none), root logger at DEBUG."""
     if log_file is None and stream is None:
         raise ValueError("at least one of 'log_file' and 'stream' should not be None.")
-    handlers = []
+    sinks = []
     if log_file:
-        fh = logging.FileHandler(log_file, mode="w")
-        fh.setLevel(fh_level)
-        fh.setFormatter(XFormatter(datefmt=fh_datefmt))
-        handlers.append(fh)
+        _attach(logging.FileHandler(log_file, mode="w"), fh_level, fh_datefmt, sinks)
     if stream:
-        ch = logging.StreamHandler(stream=stream)
-        ch.setLevel(ch_level)
-        ch.setFormatter(XFormatter(datefmt=ch_datefmt))
-        handlers.append(ch)
-    logging.basicConfig(level=logging.DEBUG, handlers=handlers)
+        _attach(logging.StreamHandler(stream), ch_level, ch_datefmt, sinks)
+    logging.basicConfig(level=logging.DEBUG, handlers=sinks)
