@@ -214,3 +214,25 @@ def test_real_smartseq_bam_and_committed_arrays():
     names = [ks.decode(int(k)) for k in hr.keys[:, 1]]
     umi_names, umi_idx = z["umi_names"], z["umi_idx"]
     assert [str(x) for x in umi_names[umi_idx]] == names
+
+
+def test_host_decoder_checks_the_gzip_crc(tmp_path):
+    """a block whose trailer CRC32 does not match its inflated bytes is rejected (as htslib does)"""
+    import struct
+    recs = [("r%d" % i, 0, 0, 10 * i, 30, [(0, 20)], "ACGT" * 5, [("CB", "Z", "ACGT-1"), ("UB", "Z", "ACGTAA")])
+            for i in range(200)]
+    good = _write(tmp_path, recs, name="good.bam")
+    raw = bytearray(open(good, "rb").read())
+    # second block = first record block: its size from the BC subfield, CRC at the end - 8
+    off = 0
+    bsize = struct.unpack_from("<H", raw, off + 16)[0] + 1
+    off += bsize
+    bsize = struct.unpack_from("<H", raw, off + 16)[0] + 1
+    raw[off + bsize - 8] ^= 0x01
+    bad = str(tmp_path / "badcrc.bam")
+    open(bad, "wb").write(bytes(raw))
+    hr, _ = decode([good])
+    assert hr.n == 200
+    with pytest.raises(lib.XgError) as ei:
+        decode([bad])
+    assert ei.value.code == -3 and "CRC" in str(ei.value)
