@@ -50,6 +50,66 @@ def test_basefc_matches_oracle(gpu_ctx, fc_batch, kw):
     assert np.all(np.diff(row.astype(np.int64) * 2000 + col) > 0)          # sorted by (row, col), unique
 
 
+@pytest.mark.parametrize("env", [
+    {"XG_SEG_MODE": "0"},                               # a (cell, UMI) set per feature, no pair words
+    {"XG_SEG_MAX": "0"},                                # pair-word mode, but every feature keeps a set
+    {"XG_SEG_MAX": "1000"},                             # light features in segments, the rest in sets
+    {"XG_SEG_MAX": "100000000", "XG_EPOCH_TILES": "97"},     # every feature a segment; heavy ones split by hash
+    {"XG_HIST_COLS": "700"},                            # three column ranges per row
+    {"XG_CNT_CTAS": "3"},
+])
+def test_basefc_counting_modes_match_oracle(gpu_ctx, fc_batch, monkeypatch, env):
+    """Every way the counting kernel can route a (feature, cell, UMI) triple gives the oracle's matrix."""
+    from oracle import oracle
+    conf, w = Conf(), fc_batch
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    row, col, val, _ = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, gpu_params(conf))
+    t = gpu_ctx.timing()
+    o_row, o_col, o_val = oracle.basefc(w.host, w.gid, w.beg, w.end, w.cell_keys, 2000, oracle.params(conf), 4)
+    assert np.array_equal(row, o_row) and np.array_equal(col, o_col) and np.array_equal(val, o_val)
+    if env.get("XG_SEG_MODE") == "0" or env.get("XG_SEG_MAX") == "0":
+        assert t[14] == 0 and t[15] > 0            # no segment features
+    if env.get("XG_SEG_MAX") == "1000":
+        assert t[14] > 0 and t[15] > 0             # both kinds
+
+
+def test_basefc_heavy_segments_are_partitioned(gpu_ctx):
+    """Few wide features: every segment holds far more pair words than the dedup table of a finalize CTA."""
+    from oracle import oracle
+    from xcltk_b200 import workload
+    w = workload.make_basefc_workload(gpu_ctx, 3000000, 3000, 0, seed=13, chroms={"21", "22"}, bins_kb=2000)
+    conf = Conf(min_include=0.5)
+    row, col, val, _ = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 3000, gpu_params(conf))
+    assert gpu_ctx.timing()[14] > 0 and gpu_ctx.timing()[15] == 0
+    host = w.dreads.download()
+    o = oracle.basefc(host, w.gid, w.beg, w.end, w.cell_keys, 3000, oracle.params(conf), 4)
+    assert np.array_equal(row, o[0]) and np.array_equal(col, o[1]) and np.array_equal(val, o[2])
+
+
+def test_basefc_umi_keys_that_do_not_fit_a_pair_word(gpu_ctx):
+    """UMI keys with bits below bit 24 (strings longer than 13 symbols): the kernel notices, the call is
+    redone with a set per feature, and the batch remembers."""
+    from oracle import oracle
+    from xcltk_b200 import workload
+    w = workload.make_basefc_workload(gpu_ctx, 400000, 500, 33472, seed=17, chroms={"19", "20", "21", "22"})
+    host = w.dreads.download()
+    umi = host.keys[:, 1]
+    real = (umi != np.uint64(0xFFFFFFFFFFFFFFFF)) & (umi != np.uint64(0))
+    # a 14th and 15th symbol: bits 21..26 -- distinct UMIs stay distinct, equal ones stay equal
+    umi[real] |= ((umi[real] >> np.uint64(40)) & np.uint64(0x3F)) << np.uint64(21) | np.uint64(1 << 21)
+    d = gpu_ctx.upload(host)
+    conf = Conf()
+    for _ in range(2):                # second call: straight to the sets
+        row, col, val, _ = gpu_ctx.basefc(d, w.gid, w.beg, w.end, w.cell_keys, 500, gpu_params(conf))
+        assert gpu_ctx.timing()[14] == 0 and gpu_ctx.timing()[15] > 0
+        o = oracle.basefc(host, w.gid, w.beg, w.end, w.cell_keys, 500, oracle.params(conf), 4)
+        assert len(val) > 1000
+        assert np.array_equal(row, o[0]) and np.array_equal(col, o[1]) and np.array_equal(val, o[2])
+    d.close()
+    host.close()
+
+
 def test_basefc_epoch_size_and_overlap_invariance(gpu_ctx, fc_batch, monkeypatch):
     w, conf = fc_batch, Conf()
     ref = None

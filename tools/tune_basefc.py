@@ -1,0 +1,72 @@
+"""basefc on the bench shape under several settings of the library's tuning knobs (env vars read per call).
+
+    python tools/tune_basefc.py [reads] [cells] [features] -- KEY=VAL,KEY=VAL ...
+
+Prints one line per setting: wall ms of the call, device span, summed counting-kernel time, epochs, pool GB,
+nnz and the result checksum (which must not depend on the setting).  The first setting is also checked
+against the CPU oracle on a small batch of the same generator.
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+from xcltk_b200 import engine, workload  # noqa: E402
+
+args = sys.argv[1:]
+sets = [""]
+if "--" in args:
+    k = args.index("--")
+    sets = args[k + 1:] or [""]
+    args = args[:k]
+n_reads = int(float(args[0])) if len(args) > 0 else 300000000
+n_cells = int(args[1]) if len(args) > 1 else 10000
+n_feat = int(args[2]) if len(args) > 2 else 60000
+
+ctx = engine.get_context(0)
+
+
+def apply(setting):
+    keys = []
+    for kv in filter(None, setting.split(",")):
+        k, v = kv.split("=")
+        os.environ[k] = v
+        keys.append(k)
+    return keys
+
+
+if os.environ.get("TUNE_CHECK", "1") != "0":
+    from oracle import oracle
+    w = workload.make_basefc_workload(ctx, 1500000, 2000, 60000, seed=3)
+    host = w.dreads.download()
+    conf = workload.Conf()
+    exp = oracle.basefc(host, w.gid, w.beg, w.end, w.cell_keys, 2000, oracle.params(conf), os.cpu_count() or 1)
+    for setting in sets:
+        keys = apply(setting)
+        row, col, val, _ = ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, w.params)
+        ok = all(np.array_equal(a, b) for a, b in zip((row, col, val), exp))
+        print("parity[%s] vs oracle (1.5M reads): %s nnz %d sum %d (oracle nnz %d sum %d)" % (
+            setting, "OK" if ok else "MISMATCH", len(val), int(val.sum()), len(exp[2]), int(exp[2].sum())), flush=True)
+        for k in keys:
+            os.environ.pop(k, None)
+    host.close()
+    w.dreads.close()
+
+w = workload.make_basefc_workload(ctx, n_reads, n_cells, n_feat, seed=7)
+for setting in sets:
+    keys = apply(setting)
+    best = None
+    for rep in range(3):
+        t = time.perf_counter()
+        seg = ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, n_cells, w.params, segments="narrow")
+        dt = 1e3 * (time.perf_counter() - t)
+        tm = ctx.timing()
+        line = (dt, tm[0], tm[3], tm[1], int(tm[5]), tm[6] / 1e9, seg.nnz, int(seg.val.sum(dtype=np.int64)), int(tm[14]), int(tm[15]))
+        if best is None or line[0] < best[0]:
+            best = line
+    print("[%s] call %.2f ms  device %.2f  epochs-span %.2f  count-kernels %.2f ms  epochs %d  pool %.2f GB  nnz %d  sum %d  seg/set feats %d/%d" % (
+        (setting,) + best), flush=True)
+    for k in keys:
+        os.environ.pop(k, None)

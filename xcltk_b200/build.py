@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "_lib")
+LIBDIR = os.environ.get("XG_LIBDIR") or os.path.join(HERE, "_lib")    # XG_LIBDIR: side builds for debugging
 LIB = os.path.join(LIBDIR, "libxcltk_b200.so")
 
 CU = ["ctx.cu", "basefc.cu", "baf.cu", "synth.cu", "gpu_decode.cu"]
@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
         if not os.path.exists(src):
             continue
         obj = os.path.join(LIBDIR, f + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("XG_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:

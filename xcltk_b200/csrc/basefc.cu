@@ -25,6 +25,15 @@
 
 #include "compact.cuh"
 
+// XG_DEBUG_SYNC=1: synchronise and report after every launch (locates a faulting / hanging kernel)
+#define XG_DBG(name)                                                                          \
+    do {                                                                                      \
+        if (dbg_sync) {                                                                       \
+            cudaError_t e_ = cudaDeviceSynchronize();                                         \
+            fprintf(stderr, "[xg] %s: %s\n", name, cudaGetErrorString(e_));                   \
+        }                                                                                     \
+    } while (0)
+
 namespace {
 
 struct FeatIndexHost {
@@ -198,25 +207,33 @@ struct FeatCache {
 // last, and then reused by later features.  The pool therefore stays about as large as the
 // state of the features under the current genomic window, so that it can live in the 126 MB
 // L2 instead of streaming through HBM.
+// cap > 0: a set (slots, cursor, log); cap == 0: a segment of log_cap 8-byte pair words
+#define SEG_TBL_SLOTS 8192                         // dedup table of the finalize CTAs (64-bit words)
+#define SEG_PART_WORDS (SEG_TBL_SLOTS * 2 / 5)     // a segment with more words is split by hash first
 static inline uint64_t plan_blk_bytes(uint32_t cap, uint32_t log_cap) {
+    // a segment that may have to be split carries a scratch half of the same size
+    if (!cap) return ((((uint64_t)log_cap * 8) + 15) & ~15ull) * (log_cap > SEG_PART_WORDS ? 2 : 1);
     return (uint64_t)cap * 16 + 16 + ((((uint64_t)log_cap * 4) + 15) & ~15ull);
 }
 
 struct EpochPlan {
     int32_t n_epochs = 0, epoch_tiles = 0;
-    std::vector<uint64_t> blk_off;      // per sorted feature: byte offset of its set
-    std::vector<uint32_t> tbl_cap;      // slots of its set (0 = feature never active)
-    std::vector<uint32_t> log_cap;      // entries of its new-element log (= candidate reads)
+    std::vector<uint64_t> blk_off;      // per sorted feature: byte offset of its block
+    std::vector<uint32_t> tbl_cap;      // slots of its set (0 = segment feature, or never active)
+    std::vector<uint32_t> log_cap;      // candidate reads: entries of its log / pair words of its segment
     uint64_t pool_bytes = 0;
     std::vector<int32_t> zero_ptr, fin_ptr;           // per epoch ranges
     std::vector<uint64_t> zseg_off, zseg_pre;
     std::vector<int32_t> fin_feat;
     int64_t staging_cap = 0;
+    int64_t n_seg_feat = 0, n_set_feat = 0;
 };
 
+// seg_max: features with at most this many candidate reads collect pair words in a segment
+// (0: every feature keeps a set)
 int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const std::vector<int32_t> &tlo,
               const std::vector<int32_t> &thi, int32_t n_tiles, int32_t n_cols, int32_t epoch_tiles,
-              EpochPlan &pl) {
+              uint64_t seg_max, EpochPlan &pl) {
     size_t m = cand.size();
     pl.epoch_tiles = epoch_tiles;
     pl.n_epochs = std::max(1, (n_tiles + epoch_tiles - 1) / epoch_tiles);
@@ -228,7 +245,12 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
         if (cand[j] == 0) continue;
         unsigned long long cap = cand[j] + cand[j] / 4 + 8;
         if (cap >= (1ull << 32)) return ctx->fail(XG_E_LIMIT, "feature window exceeds 2^32 reads");
-        pl.tbl_cap[j] = (uint32_t)cap;
+        if (cand[j] <= seg_max) {
+            pl.n_seg_feat++;
+        } else {
+            pl.tbl_cap[j] = (uint32_t)cap;
+            pl.n_set_feat++;
+        }
         pl.log_cap[j] = (uint32_t)cand[j];
         pl.staging_cap += (int64_t)std::min<unsigned long long>(cand[j], (unsigned long long)n_cols);
         starts[(size_t)(tlo[j] / epoch_tiles)].push_back((int32_t)j);
@@ -253,15 +275,14 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
     pl.zero_ptr.assign((size_t)pl.n_epochs + 1, 0);
     pl.fin_ptr.assign((size_t)pl.n_epochs + 1, 0);
     for (int32_t e = 0; e < pl.n_epochs; e++) {
-        // a block is reused two epochs after its feature ended, so that zeroing the blocks of
-        // epoch e never races with the (overlapped) counting of epoch e-1
+        // a block is reused two epochs after its feature ended, so that zeroing / filling the blocks of
+        // epoch e never races with the (overlapped) finalize of epoch e-1
         if (e > 1)
             for (int32_t j : ends[(size_t)e - 2])
                 release(pl.blk_off[(size_t)j], plan_blk_bytes(pl.tbl_cap[(size_t)j], pl.log_cap[(size_t)j]));
         uint64_t pre = 0;
         for (int32_t j : starts[(size_t)e]) {
             uint64_t need = plan_blk_bytes(pl.tbl_cap[(size_t)j], pl.log_cap[(size_t)j]), off = UINT64_MAX;
-            const uint64_t zero_len = (uint64_t)pl.tbl_cap[(size_t)j] * 16 + 16;   // set + cursor
             for (auto it = free_blocks.begin(); it != free_blocks.end(); ++it)
                 if (it->second >= need) {
                     off = it->first;
@@ -282,87 +303,204 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
                 pl.pool_bytes = off + need;
             }
             pl.blk_off[(size_t)j] = off;
-            pl.zseg_off.push_back(off);
-            pl.zseg_pre.push_back(pre);
-            pre += zero_len;
+            if (pl.tbl_cap[(size_t)j]) {         // a set is zeroed before its first epoch; a segment only has a cursor
+                pl.zseg_off.push_back(off);
+                pl.zseg_pre.push_back(pre);
+                pre += (uint64_t)pl.tbl_cap[(size_t)j] * 16 + 16;   // set + cursor
+            } else if (off / 16 >= 0xFFFFFFFFull) {
+                return ctx->fail(XG_E_LIMIT, "segment pool exceeds 64 GiB; use smaller epochs (XG_EPOCH_TILES)");
+            }
         }
         pl.zseg_pre.push_back(pre);      // terminator of the epoch: total bytes
         pl.zseg_off.push_back(0);
         pl.zero_ptr[(size_t)e + 1] = (int32_t)pl.zseg_off.size();
-        for (int32_t j : ends[(size_t)e]) pl.fin_feat.push_back(j);
+        // heavy rows first: the persistent finalize CTAs end closer together
+        std::vector<int32_t> fin(ends[(size_t)e]);
+        std::stable_sort(fin.begin(), fin.end(), [&](int32_t a, int32_t b) { return cand[(size_t)a] > cand[(size_t)b]; });
+        for (int32_t j : fin) pl.fin_feat.push_back(j);
         pl.fin_ptr[(size_t)e + 1] = (int32_t)pl.fin_feat.size();
     }
     return XG_OK;
 }
 
-#define SB_MAX 512       // boundaries staged in shared memory per tile
-#define PAIR_CAP 1024    // (feature, cell, UMI) triples staged per tile
-#define RPT 4            // records per thread (XG_TILE / 256)
-#define PB 2             // staged pairs a thread keeps in flight in the insert phase
+// ---- the counting kernel ------------------------------------------------------------------
+#define CNT_THREADS 256
+#define CNT_WARPS 8
+#define CHUNK 64         // records per warp iteration: two consecutive records per lane
+#define SB_MAX 128       // boundaries of a tile's window staged in shared memory
+#define STAB_CAP 128     // stabbing-list entries of those boundaries staged in shared memory
+#define CIG_CAP 1024     // CIGAR words of the tile staged in shared memory
+#define WPAIR_CAP 96     // (feature, cell, UMI) pairs a warp stages before it appends them
+#define FILT_BITS 11     // tile-local duplicate filter: 2^FILT_BITS direct-mapped 64-bit entries
+#define INCL_CAP 256     // include-threshold table entries kept in shared memory
+#define LEGACY_BIT 0x80000000u
+#define NO_SEG 0xFFFFFFFFu
 
-// per sorted feature: where its block lives.  Block layout:
-//   [ set: cap x 16 B ][ cursor: 16 B ][ log: log_cap x 4 B ]
-// The log receives the cell of every NEW (cell, UMI) element, so that the row can be reduced
-// from n_new x 4 B instead of a scan of the whole (mostly empty or duplicate-free) set.
+// per sorted feature: where its state lives in the pool.
+//   cap > 0  : "set" feature -- [ set: cap x 16 B ][ cursor: 16 B ][ log: log_cap x 4 B ]; the log
+//              receives the cell of every NEW (cell, UMI) element (heavy features, and every
+//              feature of a batch whose UMI keys do not leave their low 24 bits free)
+//   cap == 0 : "segment" feature -- log_cap x 8 B of appended pair words `umi | cell`, deduplicated
+//              by the finalize CTA in shared memory (log_cap = candidate reads = upper bound)
 struct __align__(16) FeatDesc {
     unsigned long long blk_off;
     uint32_t cap, log_cap;
 };
-__host__ __device__ __forceinline__ uint64_t blk_zero_bytes(uint32_t cap) { return (uint64_t)cap * 16 + 16; }
-__host__ __device__ __forceinline__ uint64_t blk_bytes(uint32_t cap, uint32_t log_cap) {
-    return blk_zero_bytes(cap) + ((((uint64_t)log_cap * 4) + 15) & ~15ull);
-}
+
+// Everything the counting kernel needs to know about a tile, in one 64-byte line that the CTA
+// fetches two tiles ahead with a bulk copy.
+struct __align__(16) TileDesc {
+    int64_t rec_beg;
+    int32_t n_rec;
+    int32_t col;          // sample-ID mode: the column of the tile's BAM
+    int32_t bx, by;       // boundaries [bx, by) under the tile's window; bx < 0: no feature, skip
+    int32_t st_lo, st_n;  // stabbing entries of the segments [bx, by)
+    uint32_t c_lo, c_hi;  // CIGAR words of the tile's records (c_lo one word back: a >=255-op count)
+    int32_t jmin;         // smallest sorted-feature index a record of the tile can meet
+    int32_t b0, b1;       // boundary range of the contig (windows too wide to stage)
+    int32_t pad[3];
+};
+static_assert(sizeof(TileDesc) == 64, "TileDesc is one 64-byte line");
 
 struct BasefcDev {
     const int2 *pos_end;
     const uint32_t *fmq, *cig_off, *cigar;
     const ulonglong2 *keys;
-    const xg_run *runs;
-    const xg_tile *tiles;
-    const int2 *tile_bnd;         // per tile: boundaries [x, y) under its window
-    const int32_t *sf_goff, *sf_end, *bnd_goff, *bnd, *stab_off, *fb;
-    const int4 *stab4;            // stabbing lists: {sorted feature, beg, end, 0}
-    int32_t n_gid;
+    const TileDesc *tdesc;
+    const int32_t *sf_end, *bnd, *stab_off, *fb;
+    const int4 *stab4;            // stabbing lists: {sorted feature, beg, end, segment offset / 16 or NO_SEG}
+    const uint32_t *segoff16;     // per sorted feature: the same offset (features met through `fb`)
+    uint32_t *seg_cur;            // per sorted feature: pairs appended so far
     uint8_t *pool;
     const FeatDesc *fdesc;
-    int32_t tile0;                // first tile of this launch (epoch)
-    int32_t ablate;               // profiling only: 1 skip inserts, 2 stop after cell lookup, 3 after loads
+    unsigned int *work;           // tile counter of this launch
+    unsigned int *flags;          // bit 0: a UMI key did not fit the pair word (the call is redone with sets)
+    int32_t tile0, tile1;         // tiles [tile0, tile1) of this launch (epoch)
+    int32_t seg_mode;             // 1: pair words + duplicate filter; 0: every feature is a set
+    int32_t col_bits;             // bits of a column index (pair word: umi | col, filter: umi | local feature | col)
     BarcodeTable bc;
     FilterParams fp;
     const int32_t *incl_tab;
     int32_t incl_tab_len, incl_len;
 };
 
-// per tile: the range of boundaries that its window [first_pos, max_end) can touch
-__global__ void k_tile_bounds(const xg_tile *tiles, const xg_run *runs, int32_t n_tiles, int32_t n_gid,
-                              const int32_t *bnd_goff, const int32_t *bnd, const int32_t *stab_off,
-                              const int32_t *fb, int2 *out) {
+struct __align__(16) PairEnt {
+    unsigned long long a;         // segment: pair word; set: UMI key
+    uint32_t j;                   // sorted feature (| LEGACY_BIT: a set feature)
+    uint32_t b;                   // segment: pool offset / 16; set: column
+};
+
+struct IdxStage {                 // the slice of the interval index under one tile (bulk-copied)
+    int4 stab4[STAB_CAP];
+    uint32_t cigar[CIG_CAP + 4];
+    int32_t bnd[SB_MAX + 4];
+    int32_t stab_off[SB_MAX + 8];
+};
+
+struct CountSmem {
+    IdxStage idx[2];
+    TileDesc desc[4];
+    unsigned long long filt[1 << FILT_BITS];
+    PairEnt pairs[CNT_WARPS][WPAIR_CAP];
+    unsigned long long bar_idx[2], bar_desc[4];
+    int32_t incl[INCL_CAP];
+    int t_ring[4];
+    int np[CNT_WARPS];
+};
+
+// ---- mbarrier / bulk-copy (TMA) primitives
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (16-byte aligned, size a multiple of 16) completing on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Tile descriptors: window of the tile in the interval index (two binary searches), the slice of
+// stabbing entries and CIGAR words under it, the smallest feature index it can meet.
+__global__ void k_tile_desc(const xg_tile *tiles, const xg_run *runs, int32_t n_tiles, int32_t n_gid,
+                            const int32_t *sf_goff, const int32_t *bnd_goff, const int32_t *bnd,
+                            const int32_t *stab_off, const int4 *stab4, const int32_t *fb,
+                            const uint32_t *cig_off, TileDesc *out) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     const xg_tile tl = tiles[t];
-    const int32_t gid = runs[tl.run].gid;
-    if (gid < 0 || gid >= n_gid || bnd_goff[gid] == bnd_goff[gid + 1]) {
-        out[t] = make_int2(-1, -1);
-        return;
+    const xg_run run = runs[tl.run];
+    const int32_t gid = run.gid;
+    TileDesc d;
+    memset(&d, 0, sizeof(d));
+    d.rec_beg = tl.rec_beg;
+    d.n_rec = tl.n_rec;
+    d.col = run.bam_idx;
+    d.bx = d.by = -1;
+    if (cig_off) {
+        const uint32_t c_first = cig_off[tl.rec_beg];
+        d.c_lo = c_first ? c_first - 1 : 0;
+        d.c_hi = cig_off[tl.rec_beg + tl.n_rec];
     }
-    const int32_t b0 = bnd_goff[gid], b1 = bnd_goff[gid + 1];
-    int32_t lo = b0, hi = b1;
-    while (lo < hi) {              // upper_bound(first_pos)
-        int32_t mid = (lo + hi) >> 1;
-        if (bnd[mid] <= tl.first_pos) lo = mid + 1; else hi = mid;
+    if (gid >= 0 && gid < n_gid && sf_goff[gid] != sf_goff[gid + 1] && bnd_goff[gid] != bnd_goff[gid + 1]) {
+        const int32_t b0 = bnd_goff[gid], b1 = bnd_goff[gid + 1];
+        int32_t lo = b0, hi = b1;
+        while (lo < hi) {              // upper_bound(first_pos)
+            int32_t mid = (lo + hi) >> 1;
+            if (bnd[mid] <= tl.first_pos) lo = mid + 1; else hi = mid;
+        }
+        const int32_t x = max(b0, lo - 1);
+        hi = b1;
+        while (lo < hi) {              // lower_bound(max_end)
+            int32_t mid = (lo + hi) >> 1;
+            if (bnd[mid] < tl.max_end) lo = mid + 1; else hi = mid;
+        }
+        const int32_t y = max(x, lo);
+        // features that a record of this tile can overlap: those stabbing a segment in [x, y] or
+        // beginning at a boundary in (x, y).  None (e.g. another GPU's genomic chunk): skip the tile.
+        const int32_t y_seg = min(y + 1, b1);
+        const bool any = stab_off[y_seg] > stab_off[x] || fb[y] > fb[min(x + 1, y)];
+        if (any) {
+            d.bx = x;
+            d.by = y;
+            d.st_lo = stab_off[x];
+            d.st_n = stab_off[y] - d.st_lo;
+            d.b0 = b0;
+            d.b1 = b1;
+            d.jmin = stab_off[x + 1] > stab_off[x] ? stab4[stab_off[x]].x : fb[min(x + 1, b1)];
+        }
     }
-    int32_t x = max(b0, lo - 1);
-    hi = b1;
-    while (lo < hi) {              // lower_bound(max_end)
-        int32_t mid = (lo + hi) >> 1;
-        if (bnd[mid] < tl.max_end) lo = mid + 1; else hi = mid;
-    }
-    const int32_t y = max(x, lo);
-    // features that a record of this tile can overlap: those stabbing a segment in [x, y] or
-    // beginning at a boundary in (x, y).  None (e.g. another GPU's genomic chunk): skip the tile.
-    const int32_t y_seg = min(y + 1, b1);
-    const bool any = stab_off[y_seg] > stab_off[x] || fb[y] > fb[min(x + 1, y)];
-    out[t] = any ? make_int2(x, y) : make_int2(-1, -1);
+    out[t] = d;
+}
+
+// streaming calls: the CIGAR range of a tile is known once its records are in HBM
+__global__ void k_tile_cig(const xg_tile *tiles, int32_t t0, int32_t t1, const uint32_t *cig_off, TileDesc *out) {
+    int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1) return;
+    const xg_tile tl = tiles[t];
+    const uint32_t c_first = cig_off[tl.rec_beg];
+    out[t].c_lo = c_first ? c_first - 1 : 0;
+    out[t].c_hi = cig_off[tl.rec_beg + tl.n_rec];
+}
+
+// per call: the segment offsets of the plan go into the stabbing entries
+__global__ void k_patch_stab(int4 *stab4, int32_t n, const uint32_t *segoff16) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) stab4[k].w = (int32_t)segoff16[stab4[k].x];
 }
 
 __device__ __forceinline__ uint32_t set_home(uint64_t umi, uint32_t col, uint32_t cap) {
@@ -370,8 +508,7 @@ __device__ __forceinline__ uint32_t set_home(uint64_t umi, uint32_t col, uint32_
 }
 
 // (cell, UMI) -> the feature's set, starting at slot s whose content `cur` was already loaded.
-// Empty slot: b == 0.
-// Returns true when the element is new.
+// Empty slot: b == 0.  Returns true when the element is new.
 __device__ __forceinline__ bool set_insert_from(xg_e128 *tbl, uint32_t cap, uint32_t s, xg_e128 cur,
                                                 xg_e128 want) {
     for (uint32_t probe = 0; probe < cap; probe++) {
@@ -390,7 +527,7 @@ __device__ __forceinline__ bool set_insert_from(xg_e128 *tbl, uint32_t cap, uint
 }
 
 // Append the cell of a new element to the feature's log.  Lanes of the warp that append to
-// the same feature are grouped with match_any: one cursor atomic per group.
+// the same feature are grouped with match_any: one cursor atomic per group.  Whole warp.
 __device__ __forceinline__ void log_append(xg_e128 *tbl, uint32_t cap, bool is_new, uint32_t col) {
     const unsigned active = __ballot_sync(0xffffffffu, is_new);
     if (!is_new) return;
@@ -404,17 +541,19 @@ __device__ __forceinline__ void log_append(xg_e128 *tbl, uint32_t cap, bool is_n
     log[base + __popc(peers & ((1u << lane) - 1u))] = col;
 }
 
-#define CIG_CAP 1024     // CIGAR words of the tile staged in shared memory
-#define STAB_CAP 256     // stabbing-list entries of the tile's boundaries staged in shared memory
-
-struct PairStage {
-    unsigned long long umi[PAIR_CAP];
-    uint32_t j[PAIR_CAP], col[PAIR_CAP];
-    int4 stab4[STAB_CAP];
-    uint32_t cigar[CIG_CAP];
-    int32_t bnd[SB_MAX], stab_off[SB_MAX + 1];
-    int n_pairs;
-};
+__device__ __forceinline__ void set_insert_direct(const BasefcDev &P, uint32_t j, uint64_t umi, uint32_t col) {
+    const FeatDesc fd = P.fdesc[j];
+    if (!fd.cap) return;
+    xg_e128 want;
+    want.a = umi;
+    want.b = (unsigned long long)col + 1ull;
+    xg_e128 *tbl = (xg_e128 *)(P.pool + fd.blk_off);
+    const uint32_t s = set_home(umi, col, fd.cap);
+    if (set_insert_from(tbl, fd.cap, s, ld128_relaxed(&tbl[s]), want)) {
+        uint32_t *cursor = (uint32_t *)(tbl + fd.cap);
+        cursor[4 + atomicAdd(cursor, 1u)] = col;
+    }
+}
 
 // m = number of aligned (M/=/X) reference positions p of the read with s0 <= p < e0
 // (== len([x for x in read.positions if s <= x <= e]), rdr/fc/core.py:40-43)
@@ -435,267 +574,386 @@ __device__ __forceinline__ int32_t included_len(const uint32_t *cig, uint32_t n_
     return m;
 }
 
-// include test of one (read, feature) pair; a passing pair is staged for the insert phase
-__device__ __forceinline__ void emit_pair(const BasefcDev &P, PairStage &S, int32_t j, int32_t s0, int32_t e0,
-                                          int32_t pos, int32_t end, const uint32_t *cig, uint32_t n_ops,
-                                          int32_t aln, int32_t need, uint64_t umi, uint32_t col) {
-    int32_t m;
-    if (n_ops == 0) {
-        int32_t a = max(pos, s0), b = min(end, e0);
-        m = b > a ? b - a : 0;
-    } else if (s0 <= pos && end <= e0) {
-        m = aln;                  // the read lies inside the feature: every aligned position counts
-    } else {
-        m = included_len(cig, n_ops, pos, s0, e0);
-    }
-    if (m < need) return;
-    int slot = atomicAdd(&S.n_pairs, 1);
-    if (slot < PAIR_CAP) {
-        S.umi[slot] = umi;
-        S.j[slot] = (uint32_t)j;
-        S.col[slot] = col;
-    } else {                       // stage full (very deep feature overlap): insert right away
-        const FeatDesc fd = P.fdesc[j];
-        if (fd.cap) {
-            xg_e128 want;
-            want.a = umi;
-            want.b = (unsigned long long)col + 1ull;
-            xg_e128 *tbl = (xg_e128 *)(P.pool + fd.blk_off);
-            uint32_t s = set_home(umi, col, fd.cap);
-            if (set_insert_from(tbl, fd.cap, s, ld128_relaxed(&tbl[s]), want)) {
-                uint32_t *cursor = (uint32_t *)(tbl + fd.cap);
-                cursor[4 + atomicAdd(cursor, 1u)] = col;
-            }
-        }
-    }
-}
+// what a lane knows about the record it is working on
+struct RecCtx {
+    int32_t pos, end, aln, need;
+    const uint32_t *cig;
+    uint32_t n_ops, col;
+    uint64_t umi;         // the UMI key as stored
+    uint64_t umi_c;       // ... with its low 24 bits free (seg_mode)
+};
 
-// Insert phase: all lanes insert staged pairs; descriptor and home-slot loads of a batch are
-// issued together before any of them is consumed.  Ends with the stage empty.
-// Insert phase: all lanes insert the staged (feature, cell, UMI) triples into the features'
-// sets; the descriptor and home-slot loads of a batch are issued together before any of them
-// is consumed.  Ends with the stage empty.  (A tile-local dedup table in shared memory and a
-// CAS-first probe were tried and measured slower: the phase is issue-bound, not L2-bound.)
-__device__ __forceinline__ void flush_pairs(const BasefcDev &P, PairStage &S) {
-    const int np = P.ablate == 1 ? 0 : min(S.n_pairs, PAIR_CAP);
-    for (int p0 = 0; p0 < np; p0 += 256 * PB) {
-        xg_e128 *tbl[PB];
-        uint32_t cap[PB], home[PB];
-        xg_e128 cur[PB];
-#pragma unroll
-        for (int r = 0; r < PB; r++) {
-            const int p = p0 + r * 256 + threadIdx.x;
-            cap[r] = 0;
-            if (p < np) {
-                const FeatDesc fd = P.fdesc[S.j[p]];
-                cap[r] = fd.cap;
-                tbl[r] = (xg_e128 *)(P.pool + fd.blk_off);
-            }
+// The warp's staged pairs go to their features: a segment pair is appended at a cursor position
+// reserved once per (warp, feature) group (match_any); a set pair is inserted with a 128-bit CAS.
+__device__ __forceinline__ void flush_warp(const BasefcDev &P, CountSmem &S, int w, int lane) {
+    __syncwarp();
+    const int np = min(__shfl_sync(0xffffffffu, S.np[w], 0), WPAIR_CAP);     // one value for the whole warp
+    for (int p0 = 0; p0 < np; p0 += 32) {
+        const int p = p0 + lane;
+        const bool act = p < np;
+        PairEnt e;
+        e.a = 0;
+        e.j = 0;
+        e.b = 0;
+        if (act) e = S.pairs[w][p];
+        const bool seg = act && !(e.j & LEGACY_BIT);
+        const unsigned segm = __ballot_sync(0xffffffffu, seg);
+        if (seg) {
+            const unsigned peers = __match_any_sync(segm, e.j);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&P.seg_cur[e.j], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const uint32_t at = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            *(unsigned long long *)(P.pool + (uint64_t)e.b * 16 + (uint64_t)at * 8) = e.a;
         }
-#pragma unroll
-        for (int r = 0; r < PB; r++) {
-            const int p = p0 + r * 256 + threadIdx.x;
-            if (cap[r]) {
-                home[r] = set_home(S.umi[p], S.col[p], cap[r]);
-                cur[r] = ld128_relaxed(tbl[r] + home[r]);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < PB; r++) {
-            const int p = p0 + r * 256 + threadIdx.x;
+        const bool leg = act && !seg;
+        if (__ballot_sync(0xffffffffu, leg)) {
+            xg_e128 *tbl = nullptr;
+            uint32_t cap = 0;
             bool is_new = false;
-            uint32_t col = 0;
-            if (cap[r]) {
-                xg_e128 want;
-                col = S.col[p];
-                want.a = S.umi[p];
-                want.b = (unsigned long long)col + 1ull;
-                is_new = set_insert_from(tbl[r], cap[r], home[r], cur[r], want);
+            if (leg) {
+                const FeatDesc fd = P.fdesc[e.j & ~LEGACY_BIT];
+                if (fd.cap) {
+                    cap = fd.cap;
+                    tbl = (xg_e128 *)(P.pool + fd.blk_off);
+                    xg_e128 want;
+                    want.a = e.a;
+                    want.b = (unsigned long long)e.b + 1ull;
+                    const uint32_t s = set_home(e.a, e.b, cap);
+                    is_new = set_insert_from(tbl, cap, s, ld128_relaxed(&tbl[s]), want);
+                }
             }
-            log_append(tbl[r], cap[r], is_new, col);     // whole warp: uses match_any
+            log_append(tbl, cap, is_new, e.b);
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) S.n_pairs = 0;
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0) S.np[w] = 0;
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(256, 6) k_basefc_count(const __grid_constant__ BasefcDev P) {
-    __shared__ PairStage S;
-    const int t = P.tile0 + blockIdx.x;
-    const xg_tile tile = P.tiles[t];
-    const xg_run run = P.runs[tile.run];
-    const int32_t gid = run.gid;
-    if (gid < 0 || gid >= P.n_gid) return;
-    if (P.sf_goff[gid] == P.sf_goff[gid + 1]) return;
-    const int32_t b0 = P.bnd_goff[gid], b1 = P.bnd_goff[gid + 1];
-    const int2 tb = P.tile_bnd[t];
-    if (tb.x < 0) return;          // no feature under this tile's window: its records are never read
-    const int32_t nb = tb.y - tb.x;
-
-    // ---- the thread's records: independent, coalesced loads issued up front
-    int2 pe[RPT];
-    uint32_t fq[RPT], co[RPT];
-    ulonglong2 ky[RPT];
-#pragma unroll
-    for (int r = 0; r < RPT; r++) {
-        const int32_t k = threadIdx.x + r * 256;
-        const bool live = k < tile.n_rec;
-        const int64_t i = tile.rec_beg + (live ? k : 0);
-        pe[r] = __ldcs(&P.pos_end[i]);         // streamed once: evict-first, keep L2 for the pool
-        fq[r] = __ldcs(&P.fmq[i]);
-        co[r] = __ldcs(&P.cig_off[i]);
-        ky[r] = __ldcs(&P.keys[i]);
-        if (!live) ky[r].y = XG_KEY_NONE;          // an absent UMI drops the record
-    }
-    // ---- stage the slice of the interval index under the tile window and the tile's CIGAR words
-    const uint32_t c_first = __ldg(&P.cig_off[tile.rec_beg]);
-    const uint32_t c_lo = c_first ? c_first - 1 : 0;      // one word back: a >=255-op count word
-    const uint32_t c_hi = __ldg(&P.cig_off[tile.rec_beg + tile.n_rec]);
-    const bool cig_staged = c_hi - c_lo <= CIG_CAP;
-    const bool staged = nb <= SB_MAX;
-    int32_t st_lo = 0, st_n = 0;
-    if (staged) {
-        st_lo = __ldg(&P.stab_off[tb.x]);
-        st_n = __ldg(&P.stab_off[tb.y]) - st_lo;
-        for (int k = threadIdx.x; k < nb; k += blockDim.x) S.bnd[k] = __ldg(&P.bnd[tb.x + k]);
-        for (int k = threadIdx.x; k <= nb; k += blockDim.x) S.stab_off[k] = __ldg(&P.stab_off[tb.x + k]);
-        if (st_n <= STAB_CAP)
-            for (int k = threadIdx.x; k < st_n; k += blockDim.x) S.stab4[k] = __ldg(&P.stab4[st_lo + k]);
-    }
-    const bool stab_staged = staged && st_n <= STAB_CAP;
-    if (cig_staged)
-        for (uint32_t k = threadIdx.x; k < c_hi - c_lo; k += blockDim.x) S.cigar[k] = __ldg(&P.cigar[c_lo + k]);
-    if (threadIdx.x == 0) S.n_pairs = 0;
-
-    // ---- cell lookup: the home slots of the records are probed together
-    int32_t colv[RPT];
-    if (P.fp.use_cell_tag) {
-        ulonglong2 slot[RPT];
-        uint32_t hs[RPT];
-#pragma unroll
-        for (int r = 0; r < RPT; r++) {
-            hs[r] = (uint32_t)mix64(ky[r].x) & P.bc.mask;
-            slot[r] = __ldg(&P.bc.slots[hs[r]]);
-        }
-#pragma unroll
-        for (int r = 0; r < RPT; r++) {
-            int32_t c = -1;
-            if (ky[r].x != XG_KEY_NONE) {
-                ulonglong2 e = slot[r];
-                uint32_t s = hs[r];
-                while (true) {
-                    if (e.x == ky[r].x) {
-                        c = (int32_t)e.y;
-                        break;
-                    }
-                    if (e.x == XG_KEY_NONE) break;
-                    s = (s + 1) & P.bc.mask;
-                    e = __ldg(&P.bc.slots[s]);
-                }
-            }
-            colv[r] = c;
-        }
+// include test of one (read, feature) pair; a passing pair that the tile has not seen yet is staged
+__device__ __forceinline__ void emit_pair(const BasefcDev &P, CountSmem &S, const TileDesc &td, int w,
+                                          const RecCtx &r, int32_t j, int32_t s0, int32_t e0, uint32_t segoff) {
+    int32_t m;
+    if (r.n_ops == 0) {
+        int32_t a = max(r.pos, s0), b = min(r.end, e0);
+        m = b > a ? b - a : 0;
+    } else if (s0 <= r.pos && r.end <= e0) {
+        m = r.aln;                // the read lies inside the feature: every aligned position counts
     } else {
-#pragma unroll
-        for (int r = 0; r < RPT; r++) colv[r] = run.bam_idx;
+        m = included_len(r.cig, r.n_ops, r.pos, s0, e0);
     }
-    __syncthreads();
-
-    // ---- phase 1: filters, overlapping features, include test; passing pairs are staged
-#pragma unroll
-    for (int r = 0; r < RPT; r++) {
-        do {
-        const uint32_t fmq = fq[r];
-        const uint64_t umi = ky[r].y;
-        if (P.ablate == 3) {
-            if (umi == 12345 && fmq == 77 && pe[r].x == 3) S.n_pairs = 1;
-            break;
+    if (m < r.need) return;
+    if (P.seg_mode) {
+        // duplicate filter: (UMI, feature, cell) fits 64 bits when the feature is numbered from the
+        // tile's first one.  A hit means that the same triple went out earlier in this tile; a miss
+        // (or a triple the filter cannot express) is passed on -- the features' own dedup is exact.
+        const uint32_t jl = (uint32_t)(j - td.jmin);
+        if (jl < (1u << (24 - P.col_bits))) {
+            const unsigned long long fk = r.umi_c | ((unsigned long long)jl << P.col_bits) | r.col;
+            const uint32_t h = (uint32_t)((fk * 0x9E3779B97F4A7C15ULL) >> (64 - FILT_BITS));
+            if (S.filt[h] == fk) return;
+            S.filt[h] = fk;
         }
-        if (umi == XG_KEY_NONE || umi == XG_KEY_EMPTY) break;   // has_tag / `if umi:`
-        if (!read_passes_flags(P.fp, fmq)) break;
-        if (colv[r] < 0) break;                                   // cell tag absent or not listed
-        const uint32_t col = (uint32_t)colv[r];
-        if (P.ablate == 2) {
-            if (col == 0x7fffffff) S.n_pairs = 1;
-            break;
-        }
-        const int32_t pos = pe[r].x, end = pe[r].y;
-        uint32_t n_ops = fmq >> 24;               // aligned length = len(read.positions)
-        const uint32_t *cig = nullptr;
-        int32_t aln;
-        if (n_ops == 0) {
-            aln = end - pos;
+    }
+    const bool seg = segoff != NO_SEG;
+    // the counter is the warp's own: only lanes of this warp contend for it
+    const int slot = atomicAdd(&S.np[w], 1);
+    if (slot < WPAIR_CAP) {
+        PairEnt e;
+        if (seg) {
+            e.a = r.umi_c | r.col;
+            e.j = (uint32_t)j;
+            e.b = segoff;
         } else {
-            cig = cig_staged ? &S.cigar[co[r] - c_lo] : P.cigar + co[r];
-            if (n_ops == 255) n_ops = cig[-1];
-            aln = 0;
-            for (uint32_t q = 0; q < n_ops; q++) {
-                uint32_t w = cig[q];
-                if (cig_aligned(w & 15u)) aln += (int32_t)(w >> 4);
-            }
+            e.a = r.umi;
+            e.j = (uint32_t)j | LEGACY_BIT;
+            e.b = r.col;
         }
-        if (aln < P.fp.min_len) break;
-        const int32_t need = P.incl_tab ? __ldg(&P.incl_tab[min(aln, P.incl_tab_len - 1)]) : P.incl_len;
+        S.pairs[w][slot] = e;
+    } else if (seg) {              // stage full (very deep feature overlap): append right away
+        const uint32_t at = atomicAdd(&P.seg_cur[j], 1u);
+        *(unsigned long long *)(P.pool + (uint64_t)segoff * 16 + (uint64_t)at * 8) = r.umi_c | r.col;
+    } else {
+        set_insert_direct(P, (uint32_t)j, r.umi, r.col);
+    }
+}
 
-        // first boundary > pos (global index)
-        int32_t ub;
-        if (staged) {
-            int32_t lo = 0;
-            if (nb <= 8) {                     // few boundaries under the tile: branch-free count
-                for (int k = 0; k < nb; k++) lo += S.bnd[k] <= pos;
-            } else {
-                int32_t hi = nb;
-                while (lo < hi) {
-                    int32_t mid = (lo + hi) >> 1;
-                    if (S.bnd[mid] <= pos) lo = mid + 1; else hi = mid;
-                }
+// One record: filters (check_read), the features it overlaps, include test per feature.
+__device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, const TileDesc &td, const IdxStage &X,
+                                             int w, bool staged, bool stab_staged, bool cig_staged, int32_t bx_al,
+                                             uint32_t c_al, int2 pe, uint32_t fmq, uint32_t co, uint64_t umi,
+                                             int32_t colv) {
+    if (umi == XG_KEY_NONE || umi == XG_KEY_EMPTY) return;       // has_tag / `if umi:`
+    if (!read_passes_flags(P.fp, fmq)) return;
+    if (colv < 0) return;                                         // cell tag absent or not listed
+    RecCtx r;
+    r.umi = umi;
+    r.umi_c = umi;
+    r.col = (uint32_t)colv;
+    if (P.seg_mode) {
+        if (umi >> 63) {                                          // interned id: moved above the column bits
+            const unsigned long long id = umi & 0x7fffffffffffffffULL;
+            if (id >> 39) {
+                atomicOr(P.flags, 1u);
+                return;
             }
-            ub = tb.x + lo;
+            r.umi_c = (1ULL << 63) | (id << 24);
+        } else if (umi & 0xffffffULL) {                           // packed string longer than 13 symbols
+            atomicOr(P.flags, 1u);
+            return;
+        }
+    }
+    r.pos = pe.x;
+    r.end = pe.y;
+    r.n_ops = fmq >> 24;                      // aligned length = len(read.positions)
+    r.cig = nullptr;
+    if (r.n_ops == 0) {
+        r.aln = r.end - r.pos;
+    } else {
+        r.cig = cig_staged ? &X.cigar[co - c_al] : P.cigar + co;
+        if (r.n_ops == 255) r.n_ops = r.cig[-1];
+        int32_t aln = 0;
+        for (uint32_t q = 0; q < r.n_ops; q++) {
+            const uint32_t cw = r.cig[q];
+            if (cig_aligned(cw & 15u)) aln += (int32_t)(cw >> 4);
+        }
+        r.aln = aln;
+    }
+    if (r.aln < P.fp.min_len) return;
+    if (P.incl_tab) {
+        const int32_t k = min(r.aln, P.incl_tab_len - 1);
+        r.need = k < INCL_CAP ? S.incl[k] : __ldg(&P.incl_tab[k]);
+    } else {
+        r.need = P.incl_len;
+    }
+
+    // first boundary > pos (global index)
+    const int32_t nb = td.by - td.bx;
+    int32_t ub;
+    if (staged) {
+        const int32_t *sb = X.bnd + (td.bx - bx_al);
+        int32_t lo = 0;
+        if (nb <= 8) {                         // few boundaries under the tile: branch-free count
+            for (int k = 0; k < nb; k++) lo += sb[k] <= r.pos;
         } else {
-            int32_t lo = b0, hi = b1;
+            int32_t hi = nb;
             while (lo < hi) {
                 int32_t mid = (lo + hi) >> 1;
-                if (__ldg(&P.bnd[mid]) <= pos) lo = mid + 1; else hi = mid;
-            }
-            ub = lo;
-        }
-        // (1) features covering `pos`: stabbing list of the segment [bnd[ub-1], bnd[ub])
-        if (ub > b0) {
-            int32_t s0i, s1i;
-            if (staged && ub > tb.x) {
-                s0i = S.stab_off[ub - 1 - tb.x];
-                s1i = S.stab_off[ub - tb.x];
-            } else {
-                s0i = __ldg(&P.stab_off[ub - 1]);
-                s1i = __ldg(&P.stab_off[ub]);
-            }
-            for (int32_t s = s0i; s < s1i; s++) {
-                const int4 f = (stab_staged && s >= st_lo) ? S.stab4[s - st_lo] : __ldg(&P.stab4[s]);
-                emit_pair(P, S, f.x, f.y, f.z, pos, end, cig, n_ops, aln, need, umi, col);
+                if (sb[mid] <= r.pos) lo = mid + 1; else hi = mid;
             }
         }
-        // (2) features beginning at a boundary inside (pos, end); every boundary from tb.y on is
-        // >= the tile's max end, so a staged tile never looks past its staged range
-        const int32_t kb_end = staged ? tb.y : b1;
-        for (int32_t kb = ub; kb < kb_end; kb++) {
-            const int32_t bv = staged ? S.bnd[kb - tb.x] : __ldg(&P.bnd[kb]);
-            if (bv >= end) break;
-            const int32_t j1 = __ldg(&P.fb[kb + 1]);
-            for (int32_t j = __ldg(&P.fb[kb]); j < j1; j++)
-                emit_pair(P, S, j, bv, __ldg(&P.sf_end[j]), pos, end, cig, n_ops, aln, need, umi, col);
+        ub = td.bx + lo;
+    } else {
+        int32_t lo = td.b0, hi = td.b1;
+        while (lo < hi) {
+            int32_t mid = (lo + hi) >> 1;
+            if (__ldg(&P.bnd[mid]) <= r.pos) lo = mid + 1; else hi = mid;
         }
-        } while (false);
-        // deep feature overlap: drain the stage between rounds so that the next 256 records
-        // find room (the direct-insert path of emit_pair stays the last resort)
-        if (r + 1 < RPT) {
-            __syncthreads();
-            if (S.n_pairs > PAIR_CAP / 2) flush_pairs(P, S);
+        ub = lo;
+    }
+    // (1) features covering `pos`: stabbing list of the segment [bnd[ub-1], bnd[ub])
+    if (ub > td.b0) {
+        int32_t s0i, s1i;
+        if (staged && ub > td.bx) {
+            s0i = X.stab_off[ub - 1 - bx_al];
+            s1i = X.stab_off[ub - bx_al];
+        } else {
+            s0i = __ldg(&P.stab_off[ub - 1]);
+            s1i = __ldg(&P.stab_off[ub]);
+        }
+        for (int32_t s = s0i; s < s1i; s++) {
+            const int4 f = (stab_staged && s >= td.st_lo) ? X.stab4[s - td.st_lo] : __ldg(&P.stab4[s]);
+            emit_pair(P, S, td, w, r, f.x, f.y, f.z, (uint32_t)f.w);
         }
     }
+    // (2) features beginning at a boundary inside (pos, end); every boundary from `by` on is
+    // >= the tile's max end, so a staged tile never looks past its staged range
+    const int32_t kb_end = staged ? td.by : td.b1;
+    for (int32_t kb = ub; kb < kb_end; kb++) {
+        const int32_t bv = staged ? X.bnd[kb - bx_al] : __ldg(&P.bnd[kb]);
+        if (bv >= r.end) break;
+        const int32_t j1 = __ldg(&P.fb[kb + 1]);
+        for (int32_t j = __ldg(&P.fb[kb]); j < j1; j++)
+            emit_pair(P, S, td, w, r, j, bv, __ldg(&P.sf_end[j]), __ldg(&P.segoff16[j]));
+    }
+}
+
+// Persistent CTAs take tiles from a work counter.  One elected thread runs the staging pipeline:
+// tile k+3's index is fetched from the counter, tile k+2's descriptor and tile k+1's slice of the
+// interval index (boundaries, stabbing lists, CIGAR words) are brought into shared memory by bulk
+// copies completing on mbarriers while the warps count tile k.  Inside a tile the warps work
+// on their own: 64-record chunks, 128-bit record loads issued one chunk ahead, pairs staged per
+// warp and appended per warp -- two CTA barriers per tile (the filter is cleared between them).
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __grid_constant__ BasefcDev P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    CountSmem &S = *reinterpret_cast<CountSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int32_t n_launch = P.tile1 - P.tile0;
+
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 2; k++) mbar_init(&S.bar_idx[k], 1);
+        for (int k = 0; k < 4; k++) mbar_init(&S.bar_desc[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < CNT_WARPS) S.np[threadIdx.x] = 0;
+    if (P.incl_tab)
+        for (int k = threadIdx.x; k < INCL_CAP && k < P.incl_tab_len; k += CNT_THREADS) S.incl[k] = __ldg(&P.incl_tab[k]);
     __syncthreads();
 
-    flush_pairs(P, S);
+    // ---- elected thread: state of the staging pipeline
+    int t_pend = -1;                 // tile k+3 (counter value on its way)
+    uint32_t n_issued = 0;           // index slices issued so far (buffer = n & 1, parity = (n >> 1) & 1)
+    auto fetch_tile = [&]() -> int {
+        const unsigned int v = atomicAdd(P.work, 1u);
+        return v < (unsigned int)n_launch ? P.tile0 + (int)v : -1;
+    };
+    auto issue_desc = [&](int k, int t) {         // descriptor of tile t -> ring slot k & 3
+        S.t_ring[k & 3] = t;
+        if (t < 0) return;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&S.bar_desc[k & 3], (uint32_t)sizeof(TileDesc));
+        bulk_g2s(&S.desc[k & 3], &P.tdesc[t], (uint32_t)sizeof(TileDesc), &S.bar_desc[k & 3]);
+    };
+    auto issue_idx = [&](const TileDesc &d) {     // the slice of the index under tile d -> next buffer
+        IdxStage &X = S.idx[n_issued & 1];
+        unsigned long long *bar = &S.bar_idx[n_issued & 1];
+        n_issued++;
+        const int32_t bx_al = d.bx & ~3;
+        const uint32_t c_al = d.c_lo & ~3u;
+        uint32_t n_bnd = 0, n_so = 0, n_st = 0, n_cg = 0;
+        if (d.by - bx_al <= SB_MAX) {
+            n_bnd = (uint32_t)((d.by - bx_al + 3) & ~3) * 4u;
+            n_so = (uint32_t)((d.by + 1 - bx_al + 3) & ~3) * 4u;
+            if (d.st_n <= STAB_CAP) n_st = (uint32_t)d.st_n * 16u;
+        }
+        if (d.c_hi - c_al <= CIG_CAP) n_cg = ((d.c_hi - c_al + 3u) & ~3u) * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, n_bnd + n_so + n_st + n_cg);
+        if (n_bnd) bulk_g2s(X.bnd, P.bnd + bx_al, n_bnd, bar);
+        if (n_so) bulk_g2s(X.stab_off, P.stab_off + bx_al, n_so, bar);
+        if (n_st) bulk_g2s(X.stab4, P.stab4 + d.st_lo, n_st, bar);
+        if (n_cg) bulk_g2s(X.cigar, P.cigar + c_al, n_cg, bar);
+    };
+    if (threadIdx.x == 0) {
+        const int t0 = fetch_tile(), t1 = fetch_tile();
+        issue_desc(0, t0);
+        issue_desc(1, t1);
+        t_pend = fetch_tile();
+        if (t0 >= 0) {
+            mbar_wait(&S.bar_desc[0], 0);
+            if (S.desc[0].bx >= 0) issue_idx(S.desc[0]);
+        }
+    }
+    uint32_t n_used = 0;             // index slices consumed so far (every thread counts alike)
+
+    for (int k = 0;; k++) {
+        __syncthreads();             // A: every warp is done with tile k-1
+        const int t = S.t_ring[k & 3];
+        if (t < 0) break;
+        mbar_wait(&S.bar_desc[k & 3], (uint32_t)(k >> 2) & 1u);
+        const TileDesc &td = S.desc[k & 3];          // stays put until tile k+2 is done with
+        const bool live = td.bx >= 0;
+        if (live && P.seg_mode) {    // clear the duplicate filter
+            uint4 *f4 = reinterpret_cast<uint4 *>(S.filt);
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (int q = threadIdx.x; q < (1 << FILT_BITS) / 2; q += CNT_THREADS) f4[q] = z;
+        }
+        __syncthreads();             // B: filter cleared, everybody has read the descriptor
+        if (threadIdx.x == 0) {      // pipeline: descriptor of tile k+2, index slice of tile k+1
+            const int t2 = t_pend;
+            t_pend = t2 >= 0 ? fetch_tile() : -1;
+            issue_desc(k + 2, t2);
+            if (S.t_ring[(k + 1) & 3] >= 0) {
+                mbar_wait(&S.bar_desc[(k + 1) & 3], (uint32_t)((k + 1) >> 2) & 1u);
+                if (S.desc[(k + 1) & 3].bx >= 0) {
+                    // tile k+1 takes the buffer after tile k's; tile k's own slice was issued earlier
+                    issue_idx(S.desc[(k + 1) & 3]);
+                }
+            }
+        }
+        if (!live) continue;         // no feature under this tile's window: its records are never read
+        const IdxStage &X = S.idx[n_used & 1];
+        mbar_wait(&S.bar_idx[n_used & 1], (n_used >> 1) & 1u);
+        n_used++;
+
+        const int32_t bx_al = td.bx & ~3;
+        const uint32_t c_al = td.c_lo & ~3u;
+        const bool staged = td.by - bx_al <= SB_MAX;
+        const bool stab_staged = staged && td.st_n <= STAB_CAP;
+        const bool cig_staged = td.c_hi - c_al <= CIG_CAP;
+        const int64_t base = td.rec_beg & ~1LL, rec_end = td.rec_beg + td.n_rec;
+        const int n_chunks = (int)((rec_end - base + CHUNK - 1) / CHUNK);
+
+        // ---- the warp's chunks: records of the next chunk are loaded while this one is counted
+        int4 pe2 = make_int4(0, 0, 0, 0);
+        uint2 fq2 = make_uint2(0, 0), co2 = make_uint2(0, 0);
+        ulonglong2 ky0 = make_ulonglong2(XG_KEY_NONE, XG_KEY_NONE), ky1 = ky0;
+        auto load_chunk = [&](int c) {
+            const int64_t i0 = base + (int64_t)c * CHUNK + 2 * lane;
+            const bool v0 = i0 >= td.rec_beg && i0 < rec_end, v1 = i0 + 1 < rec_end;
+            ky0 = ky1 = make_ulonglong2(XG_KEY_NONE, XG_KEY_NONE);         // an absent UMI drops the record
+            if (v0 || (v1 && i0 + 1 >= td.rec_beg)) {
+                pe2 = __ldcs(reinterpret_cast<const int4 *>(P.pos_end + i0));   // streamed once: evict-first
+                fq2 = __ldcs(reinterpret_cast<const uint2 *>(P.fmq + i0));
+                co2 = __ldcs(reinterpret_cast<const uint2 *>(P.cig_off + i0));
+                if (v0) ky0 = __ldcs(&P.keys[i0]);
+                if (v1) ky1 = __ldcs(&P.keys[i0 + 1]);
+            }
+        };
+        int c = w;
+        if (c < n_chunks) load_chunk(c);
+        while (c < n_chunks) {
+            const int4 pe = pe2;
+            const uint2 fq = fq2, co = co2;
+            const ulonglong2 k0 = ky0, k1 = ky1;
+            const int cn = c + CNT_WARPS;
+            if (cn < n_chunks) load_chunk(cn);
+            // cell lookup: the home slots of both records are probed together
+            int32_t col0 = td.col, col1 = td.col;
+            if (P.fp.use_cell_tag) {
+                const uint32_t h0 = (uint32_t)mix64(k0.x) & P.bc.mask, h1 = (uint32_t)mix64(k1.x) & P.bc.mask;
+                ulonglong2 e0 = __ldg(&P.bc.slots[h0]), e1 = __ldg(&P.bc.slots[h1]);
+                col0 = col1 = -1;
+                if (k0.x != XG_KEY_NONE) {
+                    uint32_t s = h0;
+                    while (true) {
+                        if (e0.x == k0.x) {
+                            col0 = (int32_t)e0.y;
+                            break;
+                        }
+                        if (e0.x == XG_KEY_NONE) break;
+                        s = (s + 1) & P.bc.mask;
+                        e0 = __ldg(&P.bc.slots[s]);
+                    }
+                }
+                if (k1.x != XG_KEY_NONE) {
+                    uint32_t s = h1;
+                    while (true) {
+                        if (e1.x == k1.x) {
+                            col1 = (int32_t)e1.y;
+                            break;
+                        }
+                        if (e1.x == XG_KEY_NONE) break;
+                        s = (s + 1) & P.bc.mask;
+                        e1 = __ldg(&P.bc.slots[s]);
+                    }
+                }
+            }
+            count_record(P, S, td, X, w, staged, stab_staged, cig_staged, bx_al, c_al, make_int2(pe.x, pe.y), fq.x,
+                         co.x, k0.y, col0);
+            // Drain the stage between the two records when it is more than half full.  The decision is
+            // lane 0's: a lane that read the counter for itself could see it already raised by lanes
+            // that skipped the flush and went on to their second record, and part ways with them.
+            if (__shfl_sync(0xffffffffu, S.np[w], 0) > WPAIR_CAP / 2) flush_warp(P, S, w, lane);
+            count_record(P, S, td, X, w, staged, stab_staged, cig_staged, bx_al, c_al, make_int2(pe.z, pe.w), fq.y,
+                         co.y, k1.y, col1);
+            flush_warp(P, S, w, lane);
+            c = cn;
+        }
+    }
 }
 
 // "narrow" result entries: column | count << 16; a count that does not fit goes to the side list
@@ -742,43 +1000,193 @@ __global__ void __launch_bounds__(256) k_zero_segments(uint8_t *pool, const uint
     }
 }
 
-// Reduce a feature whose last epoch just finished to its row of the matrix: histogram of its
-// new-element log (one cell index per distinct (cell, UMI)) in shared memory plus a bitmap of
-// the touched cells; the set bits enumerated in order give the non-zeros in column order (the
-// reference's emit loop, rdr/fc/core.py:109-117).  The row goes to a staging area at an
-// atomically reserved offset; k_gather_rows puts the rows in input order.  Persistent CTAs
-// take features from a work counter; histogram and bitmap are cleared while they are read, so
-// the next feature starts clean.  When the cells do not fit the histogram (n_cols > hist_cols)
-// the log is read once per column range, first to count, then to write.
-__global__ void __launch_bounds__(256) k_basefc_finalize(const uint8_t *pool, const FeatDesc *fdesc,
-                                                         const int32_t *sf_row, const int32_t *fin_feat,
-                                                         int32_t n_fin, int32_t n_cols, int32_t hist_cols,
-                                                         unsigned int *work, unsigned long long *cursor,
-                                                         int64_t *seg_base, int32_t *seg_nnz, int32_t *st_col,
-                                                         int32_t *st_val) {
-    extern __shared__ uint32_t smem[];
-    uint32_t *hist = smem;                          // hist_cols
-    uint32_t *bitmap = smem + hist_cols;            // (hist_cols + 31) / 32
-    __shared__ int warp_tot[8];
-    __shared__ long long base_s;
-    __shared__ int f_s;
+// Reduce a feature whose last epoch just finished to its row of the matrix.
+//   segment feature: its pair words (umi | cell; duplicates across tiles are still in) are deduplicated
+//     in a shared-memory open-addressing table (64-bit CAS); every NEW word adds one to its cell.  A
+//     segment with more words than the table takes at 40 % load is first split by hash into partitions
+//     of that size (count, prefix, scatter into the scratch half of its block -- two more sweeps,
+//     from L2), and the partitions go through the table one after the other.  Should a partition
+//     still overflow the table (skewed input) it is swept once per hash sub-partition, with twice the
+//     sub-partitions after every overflow.
+//   set feature: its new-element log holds one cell index per distinct (cell, UMI).
+// Either way the counts land in a shared-memory histogram over cells plus a bitmap of the touched
+// cells; the set bits enumerated in order give the non-zeros in column order (the reference's emit
+// loop, rdr/fc/core.py:109-117).  The row goes to a staging area at an atomically reserved offset;
+// k_gather_rows puts the rows in input order.  Persistent CTAs take features from a work counter;
+// histogram and bitmap are cleared while they are read, so the next feature starts clean.  When the
+// cells do not fit the histogram (n_cols > hist_cols) the source is read once per column range,
+// first to count, then to write.
+#define FIN_THREADS 512
+#define FIN_WARPS (FIN_THREADS / 32)
+#define FIN_PARTS 1024       // hash partitions of a heavy segment (their counters live in the idle table)
+#define FIN_ILP 4            // pair words a thread has in flight in a sweep
+
+__device__ __forceinline__ uint64_t pair_hash(unsigned long long pw) {
+    uint64_t h = pw * 0x9E3779B97F4A7C15ULL;
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ULL;
+    return h;
+}
+// partition of a pair word among n_part (bits 32..63 of the hash; the table slot uses the top bits
+// after a second multiply, the sub-partition the low word)
+__device__ __forceinline__ uint32_t pair_part(uint64_t h, uint32_t n_part) {
+    return (uint32_t)(((h >> 32) * (uint64_t)n_part) >> 32);
+}
+
+struct FinShared {
+    int warp_tot[FIN_WARPS];
+    long long base_s;
+    int f_s, ovf_s;
+    uint32_t part_off[FIN_PARTS + 1];
+};
+
+// Deduplicate words[0, n) whose cell lies in [c_lo, c_lo + nc) into hist / bitmap.  Block-wide.
+__device__ __forceinline__ void fin_dedup_range(unsigned long long *tbl, int32_t tbl_slots, uint32_t *hist,
+                                                uint32_t *bitmap, FinShared &F, const unsigned long long *words,
+                                                uint32_t n, uint32_t c_lo, int nc, uint32_t expect) {
+    if (n == 0) return;
+    // table of this sweep: 2.5 x the expected words, power of two
+    uint32_t n_sub = (uint32_t)(((uint64_t)expect * 5 / 2 + (uint64_t)tbl_slots - 1) / (uint64_t)tbl_slots);
+    if (n_sub == 0) n_sub = 1;
+    uint32_t tsz = 64;
+    const uint64_t per = (uint64_t)expect / n_sub + 1;
+    while (tsz < (uint32_t)tbl_slots && (uint64_t)tsz * 2 < per * 5) tsz <<= 1;
+    const int shift = 64 - (31 - __clz((int)tsz));
+    const uint32_t probe_max = min(tsz, 96u);
+    for (uint32_t sub = 0; sub < n_sub; sub++) {
+        for (uint32_t s = threadIdx.x; s < tsz; s += FIN_THREADS) tbl[s] = 0ULL;
+        __syncthreads();
+        for (uint32_t s0 = threadIdx.x; s0 < n; s0 += FIN_THREADS * FIN_ILP) {
+            unsigned long long pw[FIN_ILP];
+#pragma unroll
+            for (int q = 0; q < FIN_ILP; q++) {
+                const uint32_t s = s0 + (uint32_t)q * FIN_THREADS;
+                pw[q] = s < n ? words[s] : 0ULL;
+            }
+#pragma unroll
+            for (int q = 0; q < FIN_ILP; q++) {
+                if (pw[q] == 0ULL) continue;
+                const uint32_t col = (uint32_t)(pw[q] & 0xffffffULL) - c_lo;
+                if (col >= (uint32_t)nc) continue;
+                const uint64_t h = pair_hash(pw[q]);
+                if (n_sub > 1 && (uint32_t)(((h & 0xffffffffULL) * n_sub) >> 32) != sub) continue;
+                uint32_t slot = (uint32_t)((h * 0x9E3779B97F4A7C15ULL) >> shift);
+                uint32_t probe = 0;
+                for (; probe < probe_max; probe++) {
+                    const unsigned long long old = atomicCAS(&tbl[slot], 0ULL, pw[q]);
+                    if (old == 0ULL) {
+                        if (atomicAdd(&hist[col], 1u) == 0) atomicOr(&bitmap[col >> 5], 1u << (col & 31));
+                        break;
+                    }
+                    if (old == pw[q]) break;
+                    slot = (slot + 1) & (tsz - 1);
+                }
+                if (probe == probe_max) F.ovf_s = 1;     // the caller forgets the column range and asks again, finer
+            }
+        }
+        __syncthreads();
+        if (F.ovf_s) return;
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) k_basefc_finalize(
+    const uint8_t *pool, const FeatDesc *fdesc, const uint32_t *seg_cur, const int32_t *sf_row,
+    const int32_t *fin_feat, int32_t n_fin, int32_t n_cols, int32_t hist_cols, int32_t tbl_slots,
+    uint32_t part_min, unsigned int *work, unsigned long long *cursor, int64_t *seg_base, int32_t *seg_nnz,
+    int32_t *st_col, int32_t *st_val) {
+    extern __shared__ __align__(16) uint8_t fin_smem[];
+    unsigned long long *tbl = reinterpret_cast<unsigned long long *>(fin_smem);      // tbl_slots (power of two)
+    uint32_t *hist = reinterpret_cast<uint32_t *>(tbl + tbl_slots);                   // hist_cols
+    uint32_t *bitmap = hist + hist_cols;                                              // (hist_cols + 31) / 32
+    __shared__ FinShared F;
     const int n_words_max = (hist_cols + 31) >> 5;
-    for (int c = threadIdx.x; c < hist_cols; c += blockDim.x) hist[c] = 0;
-    for (int c = threadIdx.x; c < n_words_max; c += blockDim.x) bitmap[c] = 0;
+    for (int c = threadIdx.x; c < hist_cols; c += FIN_THREADS) hist[c] = 0;
+    for (int c = threadIdx.x; c < n_words_max; c += FIN_THREADS) bitmap[c] = 0;
+    if (threadIdx.x == 0) F.ovf_s = 0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n_pass = (n_cols + hist_cols - 1) / hist_cols;
+    const uint32_t part_words = (uint32_t)tbl_slots * 2 / 5;      // words a partition should hold (40 % load)
 
     while (true) {
         __syncthreads();
-        if (threadIdx.x == 0) f_s = (int)atomicAdd(work, 1u);
+        if (threadIdx.x == 0) F.f_s = (int)atomicAdd(work, 1u);
         __syncthreads();
-        const int f = f_s;
+        const int f = F.f_s;
         if (f >= n_fin) break;
         const int32_t j = fin_feat[f];
         const FeatDesc fd = fdesc[j];
-        const uint32_t *cur_p = (const uint32_t *)(pool + fd.blk_off + (size_t)fd.cap * 16);
-        const uint32_t n_new = cur_p[0];
-        const uint32_t *log = cur_p + 4;
+        const bool is_set = fd.cap != 0;
+        const uint32_t *log = nullptr;
+        const unsigned long long *seg = nullptr;
+        uint32_t n_src;
+        if (is_set) {
+            const uint32_t *cur_p = (const uint32_t *)(pool + fd.blk_off + (size_t)fd.cap * 16);
+            n_src = cur_p[0];
+            log = cur_p + 4;
+        } else {
+            n_src = seg_cur[j];
+            seg = (const unsigned long long *)(pool + fd.blk_off);
+        }
+        // ---- a heavy segment is split by hash into the scratch half of its block
+        uint32_t n_part = 1;
+        if (!is_set && n_src > part_words && fd.log_cap > part_min) {
+            n_part = min((uint32_t)FIN_PARTS, (n_src + part_words - 1) / part_words);
+            uint32_t *cnt = reinterpret_cast<uint32_t *>(tbl);          // the table is idle: counters, then cursors
+            for (uint32_t q = threadIdx.x; q < n_part; q += FIN_THREADS) cnt[q] = 0;
+            __syncthreads();
+            for (uint32_t s0 = threadIdx.x; s0 < n_src; s0 += FIN_THREADS * FIN_ILP) {
+                unsigned long long pw[FIN_ILP];
+#pragma unroll
+                for (int q = 0; q < FIN_ILP; q++) {
+                    const uint32_t s = s0 + (uint32_t)q * FIN_THREADS;
+                    pw[q] = s < n_src ? seg[s] : 0ULL;
+                }
+#pragma unroll
+                for (int q = 0; q < FIN_ILP; q++)
+                    if (pw[q]) atomicAdd(&cnt[pair_part(pair_hash(pw[q]), n_part)], 1u);
+            }
+            __syncthreads();
+            // exclusive prefix over the n_part <= FIN_PARTS counters (two per thread)
+            {
+                const uint32_t q0 = 2 * threadIdx.x, q1 = q0 + 1;
+                const uint32_t a = q0 < n_part ? cnt[q0] : 0u, b = q1 < n_part ? cnt[q1] : 0u;
+                uint32_t incl = a + b;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += y;
+                }
+                if (lane == 31) F.warp_tot[w] = (int)incl;
+                __syncthreads();
+                uint32_t before = 0;
+                for (int q = 0; q < w; q++) before += (uint32_t)F.warp_tot[q];
+                const uint32_t excl = before + incl - (a + b);
+                if (q0 <= n_part) F.part_off[q0] = excl;
+                if (q1 <= n_part) F.part_off[q1] = excl + a;
+                __syncthreads();
+                if (q0 < n_part) cnt[q0] = excl;
+                if (q1 < n_part) cnt[q1] = excl + a;
+                if (threadIdx.x == 0) F.part_off[n_part] = n_src;
+                __syncthreads();
+            }
+            unsigned long long *scr = const_cast<unsigned long long *>(seg) + ((((size_t)fd.log_cap) + 1) & ~(size_t)1);
+            for (uint32_t s0 = threadIdx.x; s0 < n_src; s0 += FIN_THREADS * FIN_ILP) {
+                unsigned long long pw[FIN_ILP];
+#pragma unroll
+                for (int q = 0; q < FIN_ILP; q++) {
+                    const uint32_t s = s0 + (uint32_t)q * FIN_THREADS;
+                    pw[q] = s < n_src ? seg[s] : 0ULL;
+                }
+#pragma unroll
+                for (int q = 0; q < FIN_ILP; q++)
+                    if (pw[q]) scr[atomicAdd(&cnt[pair_part(pair_hash(pw[q]), n_part)], 1u)] = pw[q];
+            }
+            __syncthreads();
+            seg = scr;
+        } else if (threadIdx.x == 0) {
+            F.part_off[0] = 0;
+            F.part_off[1] = n_src;
+        }
+        __syncthreads();
         long long base = 0;
         // stage 0 (only when n_pass > 1): count; stage 1: write
         for (int stage = (n_pass > 1 ? 0 : 1); stage < 2; stage++) {
@@ -787,20 +1195,40 @@ __global__ void __launch_bounds__(256) k_basefc_finalize(const uint8_t *pool, co
                 const uint32_t c_lo = (uint32_t)pass * (uint32_t)hist_cols;
                 const int nc = min(hist_cols, n_cols - (int)c_lo);
                 const int nw = (nc + 31) >> 5;
-                for (uint32_t s = threadIdx.x; s < n_new; s += blockDim.x) {
-                    const uint32_t col = log[s] - c_lo;
-                    if (col < (uint32_t)nc && atomicAdd(&hist[col], 1u) == 0)
-                        atomicOr(&bitmap[col >> 5], 1u << (col & 31));
+                if (is_set) {
+                    for (uint32_t s = threadIdx.x; s < n_src; s += FIN_THREADS) {
+                        const uint32_t col = log[s] - c_lo;
+                        if (col < (uint32_t)nc && atomicAdd(&hist[col], 1u) == 0)
+                            atomicOr(&bitmap[col >> 5], 1u << (col & 31));
+                    }
+                    __syncthreads();
+                } else {
+                    uint32_t grow = 1;
+                    while (true) {
+                        for (uint32_t part = 0; part < n_part; part++) {
+                            const uint32_t p0 = F.part_off[part], pn = F.part_off[part + 1] - p0;
+                            fin_dedup_range(tbl, tbl_slots, hist, bitmap, F, seg + p0, pn, c_lo, nc,
+                                            (pn / (uint32_t)n_pass + 1) * grow);
+                            if (F.ovf_s) break;
+                        }
+                        if (!F.ovf_s) break;
+                        // a sweep overflowed the table: forget this column range, go again with finer sub-partitions
+                        __syncthreads();
+                        for (int c = threadIdx.x; c < nc; c += FIN_THREADS) hist[c] = 0;
+                        for (int c = threadIdx.x; c < nw; c += FIN_THREADS) bitmap[c] = 0;
+                        if (threadIdx.x == 0) F.ovf_s = 0;
+                        grow *= 2;
+                        __syncthreads();
+                    }
                 }
-                __syncthreads();
                 const bool writing = (stage == 1);
                 if (!writing || n_pass == 1) {            // non-zero cells of this range
                     int nz = 0;
-                    for (int k = threadIdx.x; k < nw; k += blockDim.x) nz += __popc(bitmap[k]);
+                    for (int k = threadIdx.x; k < nw; k += FIN_THREADS) nz += __popc(bitmap[k]);
                     for (int d = 16; d > 0; d >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, d);
-                    if (lane == 0) warp_tot[w] = nz;
+                    if (lane == 0) F.warp_tot[w] = nz;
                     __syncthreads();
-                    for (int k = 0; k < 8; k++) total_nz += warp_tot[k];
+                    for (int k = 0; k < FIN_WARPS; k++) total_nz += F.warp_tot[k];
                     __syncthreads();
                 }
                 if (writing && n_pass == 1) {             // single range: reserve now
@@ -809,13 +1237,13 @@ __global__ void __launch_bounds__(256) k_basefc_finalize(const uint8_t *pool, co
                         long long b = total_nz ? (long long)atomicAdd(cursor, (unsigned long long)total_nz) : 0;
                         seg_base[row] = b;
                         seg_nnz[row] = total_nz;
-                        base_s = b;
+                        F.base_s = b;
                     }
                     __syncthreads();
-                    base = base_s;
+                    base = F.base_s;
                 }
                 // ordered walk over the bitmap words; clears histogram and bitmap as it goes
-                for (int k0 = 0; k0 < nw; k0 += blockDim.x) {
+                for (int k0 = 0; k0 < nw; k0 += FIN_THREADS) {
                     const int k = k0 + threadIdx.x;
                     uint32_t bits = k < nw ? bitmap[k] : 0u;
                     int cnt = __popc(bits), incl = cnt;
@@ -823,11 +1251,11 @@ __global__ void __launch_bounds__(256) k_basefc_finalize(const uint8_t *pool, co
                         int y = __shfl_up_sync(0xffffffffu, incl, d);
                         if (lane >= d) incl += y;
                     }
-                    if (lane == 31) warp_tot[w] = incl;
+                    if (lane == 31) F.warp_tot[w] = incl;
                     __syncthreads();
                     int before = 0, tot = 0;
-                    for (int q = 0; q < 8; q++) {
-                        const int x = warp_tot[q];
+                    for (int q = 0; q < FIN_WARPS; q++) {
+                        const int x = F.warp_tot[q];
                         if (q < w) before += x;
                         tot += x;
                     }
@@ -854,10 +1282,10 @@ __global__ void __launch_bounds__(256) k_basefc_finalize(const uint8_t *pool, co
                     long long b = total_nz ? (long long)atomicAdd(cursor, (unsigned long long)total_nz) : 0;
                     seg_base[row] = b;
                     seg_nnz[row] = total_nz;
-                    base_s = b;
+                    F.base_s = b;
                 }
                 __syncthreads();
-                base = base_s;
+                base = F.base_s;
             }
         }
     }
@@ -879,7 +1307,7 @@ static int upload_vec(xg_ctx *ctx, const std::vector<T> &v, const char *name, co
 // but empty, and every epoch's slice is copied from the pinned host batch `src` on a copy
 // stream just ahead of the epoch that counts it (H2D overlaps the kernels).
 static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, const xg_features *feats,
-                      const xg_barcodes *cells, const xg_params *par, xg_coo **out) {
+                      const xg_barcodes *cells, const xg_params *par, xg_coo **out, bool force_sets = false) {
     if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
     if (!rd || !feats || !cells || !par || !out) return ctx->fail(XG_E_ARG, "xg_basefc: null argument");
     if (feats->n < 0 || cells->n_samples <= 0) return ctx->fail(XG_E_ARG, "xg_basefc: empty sample list");
@@ -889,6 +1317,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_CUDA(cudaSetDevice(ctx->device));
     for (double &t : ctx->timing) t = 0;
     int launches = 0;
+    const bool dbg_sync = getenv("XG_DEBUG_SYNC") && atoi(getenv("XG_DEBUG_SYNC")) != 0;
     const int32_t n_rows = feats->n, n_cols = cells->n_samples;
 
     int32_t n_gid = 0;
@@ -948,9 +1377,9 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     P.cig_off = rd->cig_off;
     P.cigar = rd->cigar;
     P.keys = rd->keys;
-    P.runs = rd->runs;
-    P.tiles = rd->tiles;
-    P.n_gid = n_gid;
+    if (((uintptr_t)rd->pos_end | (uintptr_t)rd->fmq | (uintptr_t)rd->cig_off | (uintptr_t)rd->keys |
+         (uintptr_t)rd->cigar) & 15)
+        return ctx->fail(XG_E_ARG, "xg_basefc: record arrays must be 16-byte aligned");
     const int32_t *d_sf_row = nullptr;
     const int32_t *d_sf_beg = nullptr;
     if (!index_cached) {
@@ -974,11 +1403,11 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         fc->valid = true;
     }
     // the named scratch buffers keep their addresses between calls
-    P.sf_goff = (const int32_t *)ctx->scratch["fx_sf_goff"].p;
+    const int32_t *d_sf_goff = (const int32_t *)ctx->scratch["fx_sf_goff"].p;
     d_sf_beg = (const int32_t *)ctx->scratch["fx_sf_beg"].p;
     P.sf_end = (const int32_t *)ctx->scratch["fx_sf_end"].p;
     d_sf_row = (const int32_t *)ctx->scratch["fx_sf_row"].p;
-    P.bnd_goff = (const int32_t *)ctx->scratch["fx_bnd_goff"].p;
+    const int32_t *d_bnd_goff = (const int32_t *)ctx->scratch["fx_bnd_goff"].p;
     P.bnd = (const int32_t *)ctx->scratch["fx_bnd"].p;
     P.stab_off = (const int32_t *)ctx->scratch["fx_stab_off"].p;
     P.stab4 = (const int4 *)ctx->scratch["fx_stab4"].p;
@@ -1006,8 +1435,8 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_GET(d_cand, unsigned long long, "fx_cand", m + 1);
     XG_GET(d_tlo, int32_t, "fx_tlo", m + 1);
     XG_GET(d_thi, int32_t, "fx_thi", m + 1);
-    XG_GET(d_tile_bnd, int2, "fx_tile_bnd", rd->n_tiles + 1);
-    P.tile_bnd = d_tile_bnd;
+    XG_GET(d_tdesc, TileDesc, "fx_tdesc", rd->n_tiles + 1);
+    P.tdesc = d_tdesc;
     cudaEventRecord(ctx->ev[0], ctx->stream);
     XG_CUDA(cudaMemsetAsync(d_cand, 0, sizeof(unsigned long long) * (m + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(d_tlo, 0x7f, sizeof(int32_t) * (m + 1), ctx->stream));
@@ -1019,12 +1448,15 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
             d_jobs, (int32_t)jobs.size(), n_warps, rd->tiles, rd->tile_pmax, rd->pos_end, src ? 0 : 1, d_sf_beg,
             P.sf_end, d_cand, d_tlo, d_thi);
         launches++;
+        XG_DBG("k_feature_windows");
     }
     if (rd->n_tiles > 0) {
-        k_tile_bounds<<<(rd->n_tiles + 255) / 256, 256, 0, ctx->stream>>>(rd->tiles, rd->runs, rd->n_tiles, n_gid,
-                                                                       P.bnd_goff, P.bnd, P.stab_off, P.fb,
-                                                                       d_tile_bnd);
+        // streaming call: the records (and with them the tiles' CIGAR ranges) arrive epoch by epoch
+        k_tile_desc<<<(rd->n_tiles + 255) / 256, 256, 0, ctx->stream>>>(
+            rd->tiles, rd->runs, rd->n_tiles, n_gid, d_sf_goff, d_bnd_goff, P.bnd, P.stab_off, P.stab4, P.fb,
+            src ? nullptr : rd->cig_off, d_tdesc);
         launches++;
+        XG_DBG("k_tile_desc");
     }
     if (m) {
         XG_CUDA(cudaMemcpyAsync(cand.data(), d_cand, sizeof(unsigned long long) * m, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1037,16 +1469,35 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     // ---- pool layout over epochs
     int32_t epoch_tiles = src ? 8192 : 65536;     // streaming: finer epochs = finer H2D / kernel overlap
     if (const char *e = getenv(src ? "XG_EPOCH_TILES_HOST" : "XG_EPOCH_TILES")) epoch_tiles = std::max(1, atoi(e));
+    // Pair-word mode: a (cell, UMI) pair is one 64-bit word `umi | cell` (every UMI key of the batch leaves
+    // its low 24 bits free: packed strings of up to 13 symbols, interned ids below 2^39), features collect
+    // their words in segments.  The kernel verifies the keys it meets; a key that does not fit raises a
+    // flag and the call is redone with a set per feature (and the batch remembers it).
+    bool seg_mode = !force_sets && n_cols <= (1 << 24) && rd->umi_compact != 0;
+    if (const char *e = getenv("XG_SEG_MODE")) seg_mode = seg_mode && atoi(e) != 0;
+    uint64_t seg_max = 1ull << 22;             // heavier features keep a set in global memory
+    if (const char *e = getenv("XG_SEG_MAX")) seg_max = (uint64_t)atoll(e);
     EpochPlan pl;
     t_ph = now();
-    if ((rc = make_plan(ctx, cand, tlo, thi, rd->n_tiles, n_cols, epoch_tiles, pl))) return rc;
+    if ((rc = make_plan(ctx, cand, tlo, thi, rd->n_tiles, n_cols, epoch_tiles, seg_mode ? seg_max : 0, pl))) return rc;
     const double ms_plan = ms_since(t_ph);
     t_ph = now();
     const int32_t *d_fin_feat = nullptr;
     const uint64_t *d_zoff = nullptr, *d_zpre = nullptr;
     std::vector<FeatDesc> fdesc(m);
-    for (size_t j = 0; j < m; j++) fdesc[j] = FeatDesc{pl.blk_off[j], pl.tbl_cap[j], pl.log_cap[j]};
+    std::vector<uint32_t> segoff16(m);
+    for (size_t j = 0; j < m; j++) {
+        fdesc[j] = FeatDesc{pl.blk_off[j], pl.tbl_cap[j], pl.log_cap[j]};
+        segoff16[j] = (!pl.tbl_cap[j] && pl.log_cap[j]) ? (uint32_t)(pl.blk_off[j] / 16) : NO_SEG;
+    }
     if ((rc = upload_vec(ctx, fdesc, "fx_fdesc", &P.fdesc))) return rc;
+    if ((rc = upload_vec(ctx, segoff16, "fx_segoff16", &P.segoff16))) return rc;
+    if (!ix.stab.empty()) {
+        k_patch_stab<<<(unsigned)((ix.stab.size() + 255) / 256), 256, 0, ctx->stream>>>(
+            (int4 *)ctx->scratch["fx_stab4"].p, (int32_t)ix.stab.size(), P.segoff16);
+        launches++;
+        XG_DBG("k_patch_stab");
+    }
     if ((rc = upload_vec(ctx, pl.fin_feat, "fx_fin_feat", &d_fin_feat))) return rc;
     if ((rc = upload_vec(ctx, pl.zseg_off, "fx_zseg_off", &d_zoff))) return rc;
     if ((rc = upload_vec(ctx, pl.zseg_pre, "fx_zseg_pre", &d_zpre))) return rc;
@@ -1059,7 +1510,9 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         XG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     P.incl_len = par->min_incl_len;
-    if (const char *e = getenv("XG_ABLATE")) P.ablate = atoi(e);
+    P.seg_mode = seg_mode ? 1 : 0;
+    P.col_bits = 1;
+    while ((1 << P.col_bits) < n_cols) P.col_bits++;
     P.fp.min_mapq = par->min_mapq;
     P.fp.min_len = par->min_len;
     P.fp.incl_flag = par->incl_flag;
@@ -1076,16 +1529,29 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_GET(st_col, int32_t, "fx_st_col", pl.staging_cap + 1);
     XG_GET(st_val, int32_t, "fx_st_val", pl.staging_cap + 1);
     XG_GET(cursor, unsigned long long, "fx_cursor", 2);
-    XG_GET(fin_work, unsigned int, "fx_fin_work", pl.n_epochs + 1);
+    XG_GET(fin_work, unsigned int, "fx_fin_work", 2 * (pl.n_epochs + 1) + 4);
+    unsigned int *cnt_work = fin_work + pl.n_epochs + 1;          // tile counters of the counting launches
+    unsigned int *d_flags = fin_work + 2 * (pl.n_epochs + 1);
+    XG_GET(seg_cur, uint32_t, "fx_seg_cur", m + 1);
     P.pool = pool;
+    P.seg_cur = seg_cur;
+    P.flags = d_flags;
     XG_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors above are about to die
     const double ms_upload = ms_since(t_ph);
 
-    // shared-memory histogram (+ bitmap) of the finalize kernel: all cells if they fit
-    const int32_t hist_cols = std::min(n_cols, 40 * 1024);
-    const size_t hist_bytes = (size_t)hist_cols * 4 + (size_t)((hist_cols + 31) / 32) * 4;
+    // shared memory of the finalize kernel: dedup table of the segment features (pair-word mode),
+    // histogram (+ bitmap) over the cells -- all cells if they fit
+    const int32_t tbl_slots = seg_mode ? SEG_TBL_SLOTS : 0;
+    int32_t hist_cols = std::min(n_cols, seg_mode ? 10 * 1024 : 40 * 1024);
+    if (seg_mode && n_cols > hist_cols) hist_cols = std::min(n_cols, 36 * 1024);     // one CTA per SM, fewer column ranges
+    if (const char *e = getenv("XG_HIST_COLS")) hist_cols = std::max(32, std::min(n_cols, atoi(e)));
+    const size_t hist_bytes = (size_t)tbl_slots * 8 + (size_t)hist_cols * 4 + (size_t)((hist_cols + 31) / 32) * 4;
     XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-    const int fin_ctas_per_sm = std::max(1, std::min(8, (int)(200 * 1024 / (hist_bytes + 1024))));
+    const int fin_ctas_per_sm = std::max(1, std::min(4, (int)(220 * 1024 / (hist_bytes + 2048))));
+    int cnt_ctas_per_sm = 4;
+    if (const char *e = getenv("XG_CNT_CTAS")) cnt_ctas_per_sm = atoi(e) == 3 ? 3 : 4;
+    void (*count_kernel)(const BasefcDev) = cnt_ctas_per_sm == 3 ? k_basefc_count<3> : k_basefc_count<4>;
+    XG_CUDA(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CountSmem)));
 
     // ---- device: epochs.  zero(e) -> count(e) -> finalize(e) per epoch; with overlap the three
     // kinds run on their own streams and count(e+1) fills the SMs while count(e) drains:
@@ -1107,8 +1573,9 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_CUDA(cudaMemsetAsync(seg_nnz, 0, sizeof(int32_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(seg_base, 0, sizeof(int64_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
-    XG_CUDA(cudaMemsetAsync(fin_work, 0, sizeof(unsigned int) * (size_t)(pl.n_epochs + 1), ctx->stream));
-    launches += 5;
+    XG_CUDA(cudaMemsetAsync(fin_work, 0, sizeof(unsigned int) * (size_t)(2 * (pl.n_epochs + 1) + 4), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(seg_cur, 0, sizeof(uint32_t) * (m + 1), ctx->stream));
+    launches += 6;
     cudaEventRecord(ev_init, ctx->stream);
     cudaStream_t st_z = overlap ? ctx->aux[0] : ctx->stream, st_f = overlap ? ctx->aux[1] : ctx->stream;
     if (overlap) {
@@ -1163,15 +1630,24 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
             k_zero_segments<<<(unsigned)((total + ZERO_CHUNK - 1) / ZERO_CHUNK), 256, 0, st_z>>>(
                 pool, d_zoff + z0, d_zpre + z0, n_seg);
             launches++;
+            XG_DBG("k_zero_segments");
         }
         cudaEventRecord(EV(0, e), st_z);
         if (overlap) cudaStreamWaitEvent(st_c, EV(0, e), 0);
         const int32_t t0 = e * pl.epoch_tiles, t1 = std::min(rd->n_tiles, t0 + pl.epoch_tiles);
+        if (src && t1 > t0) {      // the CIGAR ranges of the tiles whose records have just arrived
+            k_tile_cig<<<(t1 - t0 + 255) / 256, 256, 0, st_c>>>(rd->tiles, t0, t1, rd->cig_off, d_tdesc);
+            launches++;
+            XG_DBG("k_tile_cig");
+        }
         cudaEventRecord(EV(1, e), st_c);
         if (t1 > t0 && m > 0) {
             P.tile0 = t0;
-            k_basefc_count<<<t1 - t0, 256, 0, st_c>>>(P);
+            P.tile1 = t1;
+            P.work = cnt_work + e;
+            count_kernel<<<std::min(t1 - t0, 148 * cnt_ctas_per_sm), CNT_THREADS, sizeof(CountSmem), st_c>>>(P);
             launches++;
+            XG_DBG("k_basefc_count");
         }
         cudaEventRecord(EV(2, e), st_c);
         const int32_t n_fin = pl.fin_ptr[(size_t)e + 1] - pl.fin_ptr[(size_t)e];
@@ -1181,10 +1657,11 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         }
         if (n_fin > 0) {
             const int grid = std::min(n_fin, 148 * fin_ctas_per_sm);
-            k_basefc_finalize<<<grid, 256, hist_bytes, st_f>>>(
-                pool, P.fdesc, d_sf_row, d_fin_feat + pl.fin_ptr[(size_t)e], n_fin, n_cols, hist_cols,
-                fin_work + e, cursor, seg_base, seg_nnz, st_col, st_val);
+            k_basefc_finalize<<<grid, FIN_THREADS, hist_bytes, st_f>>>(
+                pool, P.fdesc, seg_cur, d_sf_row, d_fin_feat + pl.fin_ptr[(size_t)e], n_fin, n_cols, hist_cols,
+                tbl_slots, (uint32_t)SEG_PART_WORDS, fin_work + e, cursor, seg_base, seg_nnz, st_col, st_val);
             launches++;
+            XG_DBG("k_basefc_finalize");
         }
         // the snapshot is a store into mapped host memory, not a copy: a D2H of 8 bytes would queue
         // behind the result copies on the copy engine and stall the finalize stream with them
@@ -1369,6 +1846,18 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     ctx->timing[11] = ms_upload;
     ctx->timing[12] = ms_since(t_call);
     ctx->timing[13] = (double)h2d_bytes;
+    ctx->timing[14] = (double)pl.n_seg_feat;
+    ctx->timing[15] = (double)pl.n_set_feat;
+    if (seg_mode) {               // did every UMI key fit the pair word?
+        unsigned int h_flags = 0;
+        XG_CUDA(cudaMemcpy(&h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost));
+        if (h_flags & 1u) {
+            xg_coo_free(*out);
+            *out = nullptr;
+            const_cast<xg_dreads *>(rd)->umi_compact = 0;
+            return basefc_run(ctx, rd, src, feats, cells, par, out, true);
+        }
+    }
     return XG_OK;
 }
 
@@ -1398,11 +1887,11 @@ extern "C" int xg_basefc_host(xg_ctx *ctx, const xg_reads *h, const xg_features 
     d->h_tiles.assign(h->tiles, h->tiles + h->n_tiles);
     d->pooled = true;
     const size_t n = (size_t)h->n_reads;
-    d->pos_end = (int2 *)ctx->dev_get(n * 8 + 16);
-    d->fmq = (uint32_t *)ctx->dev_get(n * 4 + 16);
-    d->cig_off = (uint32_t *)ctx->dev_get((n + 1) * 4 + 16);
-    d->keys = (ulonglong2 *)ctx->dev_get(n * 16 + 16);
-    d->cigar = (uint32_t *)ctx->dev_get((size_t)h->n_cigar * 4 + 16);
+    d->pos_end = (int2 *)ctx->dev_get(n * 8 + 64);
+    d->fmq = (uint32_t *)ctx->dev_get(n * 4 + 64);
+    d->cig_off = (uint32_t *)ctx->dev_get((n + 1) * 4 + 64);
+    d->keys = (ulonglong2 *)ctx->dev_get(n * 16 + 64);
+    d->cigar = (uint32_t *)ctx->dev_get((size_t)h->n_cigar * 4 + 64);
     d->runs = (xg_run *)ctx->dev_get((size_t)h->n_runs * sizeof(xg_run) + 16);
     d->tiles = (xg_tile *)ctx->dev_get((size_t)h->n_tiles * sizeof(xg_tile) + 16);
     int rc = XG_OK;

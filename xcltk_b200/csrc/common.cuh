@@ -38,6 +38,7 @@ struct xg_dreads {
     int64_t bytes = 0;
     bool pooled = false;         // buffers came from xg_ctx::dev_get
     bool mapped = false;         // xg_map_reads: only pos_end / runs / tiles are device copies
+    int8_t umi_compact = -1;     // 0: a UMI key of the batch does not fit a pair word (learnt by xg_basefc)
 };
 
 struct xg_ctx {

@@ -155,7 +155,7 @@ int xg_upload_reads(xg_ctx *ctx, const xg_reads *h, xg_dreads **out) {
     d->pooled = true;
     for (auto &c : cps) {
         if (!c.src) continue;
-        *c.dst = ctx->dev_get(c.bytes ? c.bytes : 16);
+        *c.dst = ctx->dev_get(c.bytes + 64);      // slack: the kernels load records in aligned pairs / quads
         if (!*c.dst) {
             xg_dreads_free(ctx, d);
             return ctx->fail(XG_E_CUDA, "out of device memory for the read batch");

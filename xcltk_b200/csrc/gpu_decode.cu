@@ -696,7 +696,7 @@ struct Decoder {
 
     template <class T>
     bool regrow(T *&p, size_t used, size_t want) {      // new buffer of `want` elements holding the first `used`
-        T *q = (T *)ctx->dev_get(want * sizeof(T) + 16);
+        T *q = (T *)ctx->dev_get(want * sizeof(T) + 64);
         if (!q) return false;
         if (p && used) cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream);
         if (p) {

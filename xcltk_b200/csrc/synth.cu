@@ -363,7 +363,7 @@ extern "C" int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *sp, xg_dreads 
         return ctx->fail(code, msg);
     };
 #define SYN_MALLOC(ptr, bytes)                                                        \
-    if (cudaMalloc((void **)&(ptr), (bytes) ? (bytes) : 16) != cudaSuccess) {         \
+    if (cudaMalloc((void **)&(ptr), (bytes) + 64) != cudaSuccess) {                   \
         cudaGetLastError();                                                           \
         return fail_free(XG_E_CUDA, "cudaMalloc failed in xg_synth_reads");           \
     }
