@@ -208,7 +208,7 @@ struct FeatCache {
 // state of the features under the current genomic window, so that it can live in the 126 MB
 // L2 instead of streaming through HBM.
 // cap > 0: a set (slots, cursor, log); cap == 0: a segment of log_cap 8-byte pair words
-#define SEG_TBL_SLOTS 8192                         // dedup table of the finalize CTAs (64-bit words)
+#define SEG_TBL_SLOTS 4096                         // dedup table of the finalize CTAs (64-bit words)
 #define SEG_PART_WORDS (SEG_TBL_SLOTS * 2 / 5)     // a segment with more words is split by hash first
 static inline uint64_t plan_blk_bytes(uint32_t cap, uint32_t log_cap) {
     // a segment that may have to be split carries a scratch half of the same size
@@ -222,9 +222,9 @@ struct EpochPlan {
     std::vector<uint32_t> tbl_cap;      // slots of its set (0 = segment feature, or never active)
     std::vector<uint32_t> log_cap;      // candidate reads: entries of its log / pair words of its segment
     uint64_t pool_bytes = 0;
-    std::vector<int32_t> zero_ptr, fin_ptr;           // per epoch ranges
+    std::vector<int32_t> zero_ptr, fin_ptr, fin_set_ptr;    // per epoch ranges
     std::vector<uint64_t> zseg_off, zseg_pre;
-    std::vector<int32_t> fin_feat;
+    std::vector<int32_t> fin_feat, fin_set;           // features ending in the epoch: segments / sets
     int64_t staging_cap = 0;
     int64_t n_seg_feat = 0, n_set_feat = 0;
 };
@@ -256,52 +256,40 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
         starts[(size_t)(tlo[j] / epoch_tiles)].push_back((int32_t)j);
         ends[(size_t)((thi[j] - 1) / epoch_tiles)].push_back((int32_t)j);
     }
-    std::map<uint64_t, uint64_t> free_blocks;   // first-fit free list keyed by offset
-    auto release = [&](uint64_t off, uint64_t len) {
-        auto it = free_blocks.emplace(off, len).first;
-        auto nx = std::next(it);
-        if (nx != free_blocks.end() && it->first + it->second == nx->first) {
-            it->second += nx->second;
-            free_blocks.erase(nx);
-        }
-        if (it != free_blocks.begin()) {
-            auto pv = std::prev(it);
-            if (pv->first + pv->second == it->first) {
-                pv->second += it->second;
-                free_blocks.erase(it);
+    // Pool layout.  A block is needed from its feature's first epoch to the finalize of its last one, and
+    // zero(e) / count(e) are ordered after finalize(e-2): a feature that lives in one or two epochs takes its
+    // block from the arena of its first epoch -- three arenas in rotation, each as large as the busiest
+    // epoch -- and the few that live longer get a place of their own behind the arenas.  O(features), no
+    // free list: the planner sits on the critical path of every call.
+    std::vector<uint64_t> epoch_bytes((size_t)pl.n_epochs, 0);
+    std::vector<int32_t> end_epoch(m, 0);
+    for (int32_t e = 0; e < pl.n_epochs; e++)
+        for (int32_t j : ends[(size_t)e]) end_epoch[(size_t)j] = e;
+    uint64_t long_bytes = 0;
+    for (int32_t e = 0; e < pl.n_epochs; e++)
+        for (int32_t j : starts[(size_t)e]) {
+            const uint64_t need = plan_blk_bytes(pl.tbl_cap[(size_t)j], pl.log_cap[(size_t)j]);
+            if (end_epoch[(size_t)j] <= e + 1) {
+                pl.blk_off[(size_t)j] = epoch_bytes[(size_t)e];          // offset inside the arena, for now
+                epoch_bytes[(size_t)e] += need;
+            } else {
+                pl.blk_off[(size_t)j] = long_bytes;
+                long_bytes += need;
             }
         }
-    };
+    uint64_t arena = 0;
+    for (uint64_t b : epoch_bytes) arena = std::max(arena, b);
+    arena = (arena + 255) & ~255ull;
+    const int n_arenas = std::min(3, pl.n_epochs);
+    pl.pool_bytes = arena * (uint64_t)n_arenas + long_bytes;
     pl.zero_ptr.assign((size_t)pl.n_epochs + 1, 0);
     pl.fin_ptr.assign((size_t)pl.n_epochs + 1, 0);
+    pl.fin_set_ptr.assign((size_t)pl.n_epochs + 1, 0);
     for (int32_t e = 0; e < pl.n_epochs; e++) {
-        // a block is reused two epochs after its feature ended, so that zeroing / filling the blocks of
-        // epoch e never races with the (overlapped) finalize of epoch e-1
-        if (e > 1)
-            for (int32_t j : ends[(size_t)e - 2])
-                release(pl.blk_off[(size_t)j], plan_blk_bytes(pl.tbl_cap[(size_t)j], pl.log_cap[(size_t)j]));
         uint64_t pre = 0;
         for (int32_t j : starts[(size_t)e]) {
-            uint64_t need = plan_blk_bytes(pl.tbl_cap[(size_t)j], pl.log_cap[(size_t)j]), off = UINT64_MAX;
-            for (auto it = free_blocks.begin(); it != free_blocks.end(); ++it)
-                if (it->second >= need) {
-                    off = it->first;
-                    uint64_t rest = it->second - need;
-                    free_blocks.erase(it);
-                    if (rest) free_blocks.emplace(off + need, rest);
-                    break;
-                }
-            if (off == UINT64_MAX) {
-                off = pl.pool_bytes;
-                if (!free_blocks.empty()) {      // extend a free block that touches the pool end
-                    auto last = std::prev(free_blocks.end());
-                    if (last->first + last->second == pl.pool_bytes) {
-                        off = last->first;
-                        free_blocks.erase(last);
-                    }
-                }
-                pl.pool_bytes = off + need;
-            }
+            const uint64_t off = pl.blk_off[(size_t)j] +
+                                 (end_epoch[(size_t)j] <= e + 1 ? arena * (uint64_t)(e % n_arenas) : arena * (uint64_t)n_arenas);
             pl.blk_off[(size_t)j] = off;
             if (pl.tbl_cap[(size_t)j]) {         // a set is zeroed before its first epoch; a segment only has a cursor
                 pl.zseg_off.push_back(off);
@@ -314,11 +302,20 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
         pl.zseg_pre.push_back(pre);      // terminator of the epoch: total bytes
         pl.zseg_off.push_back(0);
         pl.zero_ptr[(size_t)e + 1] = (int32_t)pl.zseg_off.size();
-        // heavy rows first: the persistent finalize CTAs end closer together
-        std::vector<int32_t> fin(ends[(size_t)e]);
-        std::stable_sort(fin.begin(), fin.end(), [&](int32_t a, int32_t b) { return cand[(size_t)a] > cand[(size_t)b]; });
-        for (int32_t j : fin) pl.fin_feat.push_back(j);
+        // heavy rows first (by power of two: a bucket pass, not a sort -- the planner is on the critical path):
+        // the persistent finalize CTAs end closer together
+        {
+            std::vector<int32_t> bucket[33];
+            for (int32_t j : ends[(size_t)e]) {
+                int b = 0;
+                for (unsigned long long c = cand[(size_t)j]; c > 1; c >>= 1) b++;
+                bucket[std::min(b, 32)].push_back(j);
+            }
+            for (int b = 32; b >= 0; b--)
+                for (int32_t j : bucket[b]) (pl.tbl_cap[(size_t)j] ? pl.fin_set : pl.fin_feat).push_back(j);
+        }
         pl.fin_ptr[(size_t)e + 1] = (int32_t)pl.fin_feat.size();
+        pl.fin_set_ptr[(size_t)e + 1] = (int32_t)pl.fin_set.size();
     }
     return XG_OK;
 }
@@ -326,7 +323,7 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
 // ---- the counting kernel ------------------------------------------------------------------
 #define CNT_THREADS 256
 #define CNT_WARPS 8
-#define CHUNK 64         // records per warp iteration: two consecutive records per lane
+#define CHUNK 32         // records per warp iteration: one per lane
 #define SB_MAX 128       // boundaries of a tile's window staged in shared memory
 #define STAB_CAP 128     // stabbing-list entries of those boundaries staged in shared memory
 #define CIG_CAP 1024     // CIGAR words of the tile staged in shared memory
@@ -406,6 +403,7 @@ struct CountSmem {
     int32_t incl[INCL_CAP];
     int t_ring[4];
     int np[CNT_WARPS];
+    int chunk_ctr[2];             // next chunk of the current / the next tile (warps claim chunks)
 };
 
 // ---- mbarrier / bulk-copy (TMA) primitives
@@ -633,7 +631,7 @@ __device__ __forceinline__ void flush_warp(const BasefcDev &P, CountSmem &S, int
 }
 
 // include test of one (read, feature) pair; a passing pair that the tile has not seen yet is staged
-__device__ __forceinline__ void emit_pair(const BasefcDev &P, CountSmem &S, const TileDesc &td, int w,
+__device__ __forceinline__ void emit_pair(const BasefcDev &P, CountSmem &S, int32_t jmin, int w,
                                           const RecCtx &r, int32_t j, int32_t s0, int32_t e0, uint32_t segoff) {
     int32_t m;
     if (r.n_ops == 0) {
@@ -649,10 +647,10 @@ __device__ __forceinline__ void emit_pair(const BasefcDev &P, CountSmem &S, cons
         // duplicate filter: (UMI, feature, cell) fits 64 bits when the feature is numbered from the
         // tile's first one.  A hit means that the same triple went out earlier in this tile; a miss
         // (or a triple the filter cannot express) is passed on -- the features' own dedup is exact.
-        const uint32_t jl = (uint32_t)(j - td.jmin);
+        const uint32_t jl = (uint32_t)(j - jmin);
         if (jl < (1u << (24 - P.col_bits))) {
             const unsigned long long fk = r.umi_c | ((unsigned long long)jl << P.col_bits) | r.col;
-            const uint32_t h = (uint32_t)((fk * 0x9E3779B97F4A7C15ULL) >> (64 - FILT_BITS));
+            const uint32_t h = ((((uint32_t)fk * 0x85EBCA6Bu) ^ (uint32_t)(fk >> 32)) * 0x9E3779B1u) >> (32 - FILT_BITS);
             if (S.filt[h] == fk) return;
             S.filt[h] = fk;
         }
@@ -680,10 +678,16 @@ __device__ __forceinline__ void emit_pair(const BasefcDev &P, CountSmem &S, cons
     }
 }
 
+// the tile's fields the record path needs, read once per tile into registers
+struct TileRegs {
+    int32_t bx, by, b0, b1, st_lo, jmin, bx_al;
+    uint32_t c_al;
+    bool staged, stab_staged, cig_staged;
+};
+
 // One record: filters (check_read), the features it overlaps, include test per feature.
-__device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, const TileDesc &td, const IdxStage &X,
-                                             int w, bool staged, bool stab_staged, bool cig_staged, int32_t bx_al,
-                                             uint32_t c_al, int2 pe, uint32_t fmq, uint32_t co, uint64_t umi,
+__device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, const TileRegs &T, const IdxStage &X,
+                                             int w, int2 pe, uint32_t fmq, uint32_t co, uint64_t umi,
                                              int32_t colv) {
     if (umi == XG_KEY_NONE || umi == XG_KEY_EMPTY) return;       // has_tag / `if umi:`
     if (!read_passes_flags(P.fp, fmq)) return;
@@ -712,7 +716,7 @@ __device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, c
     if (r.n_ops == 0) {
         r.aln = r.end - r.pos;
     } else {
-        r.cig = cig_staged ? &X.cigar[co - c_al] : P.cigar + co;
+        r.cig = T.cig_staged ? &X.cigar[co - T.c_al] : P.cigar + co;
         if (r.n_ops == 255) r.n_ops = r.cig[-1];
         int32_t aln = 0;
         for (uint32_t q = 0; q < r.n_ops; q++) {
@@ -730,10 +734,10 @@ __device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, c
     }
 
     // first boundary > pos (global index)
-    const int32_t nb = td.by - td.bx;
+    const int32_t nb = T.by - T.bx;
     int32_t ub;
-    if (staged) {
-        const int32_t *sb = X.bnd + (td.bx - bx_al);
+    if (T.staged) {
+        const int32_t *sb = X.bnd + (T.bx - T.bx_al);
         int32_t lo = 0;
         if (nb <= 8) {                         // few boundaries under the tile: branch-free count
             for (int k = 0; k < nb; k++) lo += sb[k] <= r.pos;
@@ -744,9 +748,9 @@ __device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, c
                 if (sb[mid] <= r.pos) lo = mid + 1; else hi = mid;
             }
         }
-        ub = td.bx + lo;
+        ub = T.bx + lo;
     } else {
-        int32_t lo = td.b0, hi = td.b1;
+        int32_t lo = T.b0, hi = T.b1;
         while (lo < hi) {
             int32_t mid = (lo + hi) >> 1;
             if (__ldg(&P.bnd[mid]) <= r.pos) lo = mid + 1; else hi = mid;
@@ -754,29 +758,29 @@ __device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, c
         ub = lo;
     }
     // (1) features covering `pos`: stabbing list of the segment [bnd[ub-1], bnd[ub])
-    if (ub > td.b0) {
+    if (ub > T.b0) {
         int32_t s0i, s1i;
-        if (staged && ub > td.bx) {
-            s0i = X.stab_off[ub - 1 - bx_al];
-            s1i = X.stab_off[ub - bx_al];
+        if (T.staged && ub > T.bx) {
+            s0i = X.stab_off[ub - 1 - T.bx_al];
+            s1i = X.stab_off[ub - T.bx_al];
         } else {
             s0i = __ldg(&P.stab_off[ub - 1]);
             s1i = __ldg(&P.stab_off[ub]);
         }
         for (int32_t s = s0i; s < s1i; s++) {
-            const int4 f = (stab_staged && s >= td.st_lo) ? X.stab4[s - td.st_lo] : __ldg(&P.stab4[s]);
-            emit_pair(P, S, td, w, r, f.x, f.y, f.z, (uint32_t)f.w);
+            const int4 f = (T.stab_staged && s >= T.st_lo) ? X.stab4[s - T.st_lo] : __ldg(&P.stab4[s]);
+            emit_pair(P, S, T.jmin, w, r, f.x, f.y, f.z, (uint32_t)f.w);
         }
     }
     // (2) features beginning at a boundary inside (pos, end); every boundary from `by` on is
     // >= the tile's max end, so a staged tile never looks past its staged range
-    const int32_t kb_end = staged ? td.by : td.b1;
+    const int32_t kb_end = T.staged ? T.by : T.b1;
     for (int32_t kb = ub; kb < kb_end; kb++) {
-        const int32_t bv = staged ? X.bnd[kb - bx_al] : __ldg(&P.bnd[kb]);
+        const int32_t bv = T.staged ? X.bnd[kb - T.bx_al] : __ldg(&P.bnd[kb]);
         if (bv >= r.end) break;
         const int32_t j1 = __ldg(&P.fb[kb + 1]);
         for (int32_t j = __ldg(&P.fb[kb]); j < j1; j++)
-            emit_pair(P, S, td, w, r, j, bv, __ldg(&P.sf_end[j]), __ldg(&P.segoff16[j]));
+            emit_pair(P, S, T.jmin, w, r, j, bv, __ldg(&P.sf_end[j]), __ldg(&P.segoff16[j]));
     }
 }
 
@@ -799,6 +803,7 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < CNT_WARPS) S.np[threadIdx.x] = 0;
+    if (threadIdx.x < 2) S.chunk_ctr[threadIdx.x] = 0;
     if (P.incl_tab)
         for (int k = threadIdx.x; k < INCL_CAP && k < P.incl_tab_len; k += CNT_THREADS) S.incl[k] = __ldg(&P.incl_tab[k]);
     __syncthreads();
@@ -874,85 +879,85 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
                 }
             }
         }
+        if (threadIdx.x == 0) S.chunk_ctr[(k + 1) & 1] = 0;       // nobody looks at it before barrier A of tile k+1
         if (!live) continue;         // no feature under this tile's window: its records are never read
         const IdxStage &X = S.idx[n_used & 1];
         mbar_wait(&S.bar_idx[n_used & 1], (n_used >> 1) & 1u);
         n_used++;
 
-        const int32_t bx_al = td.bx & ~3;
-        const uint32_t c_al = td.c_lo & ~3u;
-        const bool staged = td.by - bx_al <= SB_MAX;
-        const bool stab_staged = staged && td.st_n <= STAB_CAP;
-        const bool cig_staged = td.c_hi - c_al <= CIG_CAP;
-        const int64_t base = td.rec_beg & ~1LL, rec_end = td.rec_beg + td.n_rec;
-        const int n_chunks = (int)((rec_end - base + CHUNK - 1) / CHUNK);
+        TileRegs T;
+        T.bx = td.bx;
+        T.by = td.by;
+        T.b0 = td.b0;
+        T.b1 = td.b1;
+        T.st_lo = td.st_lo;
+        T.jmin = td.jmin;
+        T.bx_al = T.bx & ~3;
+        T.c_al = td.c_lo & ~3u;
+        T.staged = T.by - T.bx_al <= SB_MAX;
+        T.stab_staged = T.staged && td.st_n <= STAB_CAP;
+        T.cig_staged = td.c_hi - T.c_al <= CIG_CAP;
+        const int64_t rec_beg = td.rec_beg;
+        const int32_t n_rec = td.n_rec, tile_col = td.col;
+        const int n_chunks = (n_rec + CHUNK - 1) / CHUNK;
 
-        // ---- the warp's chunks: records of the next chunk are loaded while this one is counted
-        int4 pe2 = make_int4(0, 0, 0, 0);
-        uint2 fq2 = make_uint2(0, 0), co2 = make_uint2(0, 0);
-        ulonglong2 ky0 = make_ulonglong2(XG_KEY_NONE, XG_KEY_NONE), ky1 = ky0;
+        // ---- the warp's chunks, claimed from the tile's counter one ahead: the records of the next
+        // chunk are on their way (coalesced 8 / 4 / 4 / 16-byte loads) while this one is counted.  (A third
+        // stage that also kept the next chunk's barcode slot in flight was measured slower: the registers
+        // it needs spill.)
+        int2 pe_n = make_int2(0, 0);
+        uint32_t fq_n = 0, co_n = 0;
+        ulonglong2 ky_n = make_ulonglong2(XG_KEY_NONE, XG_KEY_NONE);
+        auto claim = [&]() -> int {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&S.chunk_ctr[k & 1], 1);
+            return __shfl_sync(0xffffffffu, c, 0);
+        };
         auto load_chunk = [&](int c) {
-            const int64_t i0 = base + (int64_t)c * CHUNK + 2 * lane;
-            const bool v0 = i0 >= td.rec_beg && i0 < rec_end, v1 = i0 + 1 < rec_end;
-            ky0 = ky1 = make_ulonglong2(XG_KEY_NONE, XG_KEY_NONE);         // an absent UMI drops the record
-            if (v0 || (v1 && i0 + 1 >= td.rec_beg)) {
-                pe2 = __ldcs(reinterpret_cast<const int4 *>(P.pos_end + i0));   // streamed once: evict-first
-                fq2 = __ldcs(reinterpret_cast<const uint2 *>(P.fmq + i0));
-                co2 = __ldcs(reinterpret_cast<const uint2 *>(P.cig_off + i0));
-                if (v0) ky0 = __ldcs(&P.keys[i0]);
-                if (v1) ky1 = __ldcs(&P.keys[i0 + 1]);
+            const int r = c * CHUNK + lane;
+            ky_n = make_ulonglong2(XG_KEY_NONE, XG_KEY_NONE);            // an absent UMI drops the record
+            if (r < n_rec) {
+                const int64_t i = rec_beg + r;
+                pe_n = __ldcs(&P.pos_end[i]);                             // streamed once: evict-first
+                fq_n = __ldcs(&P.fmq[i]);
+                co_n = __ldcs(&P.cig_off[i]);
+                ky_n = __ldcs(&P.keys[i]);
             }
         };
-        int c = w;
+        int c = claim();
         if (c < n_chunks) load_chunk(c);
         while (c < n_chunks) {
-            const int4 pe = pe2;
-            const uint2 fq = fq2, co = co2;
-            const ulonglong2 k0 = ky0, k1 = ky1;
-            const int cn = c + CNT_WARPS;
+            const int2 pe = pe_n;
+            const uint32_t fq = fq_n, co = co_n;
+            const ulonglong2 ky = ky_n;
+            const int cn = claim();
             if (cn < n_chunks) load_chunk(cn);
-            // cell lookup: the home slots of both records are probed together
-            int32_t col0 = td.col, col1 = td.col;
+            // cell lookup
+            int32_t colv = tile_col;
             if (P.fp.use_cell_tag) {
-                const uint32_t h0 = (uint32_t)mix64(k0.x) & P.bc.mask, h1 = (uint32_t)mix64(k1.x) & P.bc.mask;
-                ulonglong2 e0 = __ldg(&P.bc.slots[h0]), e1 = __ldg(&P.bc.slots[h1]);
-                col0 = col1 = -1;
-                if (k0.x != XG_KEY_NONE) {
-                    uint32_t s = h0;
+                colv = -1;
+                if (ky.x != XG_KEY_NONE) {
+                    uint32_t sl = barcode_home(ky.x, P.bc.shift);
                     while (true) {
-                        if (e0.x == k0.x) {
-                            col0 = (int32_t)e0.y;
+                        const ulonglong2 e = __ldg(&P.bc.slots[sl]);
+                        if (e.x == ky.x) {
+                            colv = (int32_t)e.y;
                             break;
                         }
-                        if (e0.x == XG_KEY_NONE) break;
-                        s = (s + 1) & P.bc.mask;
-                        e0 = __ldg(&P.bc.slots[s]);
-                    }
-                }
-                if (k1.x != XG_KEY_NONE) {
-                    uint32_t s = h1;
-                    while (true) {
-                        if (e1.x == k1.x) {
-                            col1 = (int32_t)e1.y;
-                            break;
-                        }
-                        if (e1.x == XG_KEY_NONE) break;
-                        s = (s + 1) & P.bc.mask;
-                        e1 = __ldg(&P.bc.slots[s]);
+                        if (e.x == XG_KEY_NONE) break;
+                        sl = (sl + 1) & P.bc.mask;
                     }
                 }
             }
-            count_record(P, S, td, X, w, staged, stab_staged, cig_staged, bx_al, c_al, make_int2(pe.x, pe.y), fq.x,
-                         co.x, k0.y, col0);
-            // Drain the stage between the two records when it is more than half full.  The decision is
-            // lane 0's: a lane that read the counter for itself could see it already raised by lanes
-            // that skipped the flush and went on to their second record, and part ways with them.
+            count_record(P, S, T, X, w, pe, fq, co, ky.y, colv);
+            __syncwarp();
+            // Append the staged pairs when the stage is more than half full (32 at a time keep the lanes
+            // busy).  The decision is lane 0's: a lane reading the counter for itself could see it already
+            // raised by lanes that went on to the next record, and part ways with them.
             if (__shfl_sync(0xffffffffu, S.np[w], 0) > WPAIR_CAP / 2) flush_warp(P, S, w, lane);
-            count_record(P, S, td, X, w, staged, stab_staged, cig_staged, bx_al, c_al, make_int2(pe.z, pe.w), fq.y,
-                         co.y, k1.y, col1);
-            flush_warp(P, S, w, lane);
             c = cn;
         }
+        flush_warp(P, S, w, lane);
     }
 }
 
@@ -1000,26 +1005,31 @@ __global__ void __launch_bounds__(256) k_zero_segments(uint8_t *pool, const uint
     }
 }
 
-// Reduce a feature whose last epoch just finished to its row of the matrix.
-//   segment feature: its pair words (umi | cell; duplicates across tiles are still in) are deduplicated
-//     in a shared-memory open-addressing table (64-bit CAS); every NEW word adds one to its cell.  A
-//     segment with more words than the table takes at 40 % load is first split by hash into partitions
-//     of that size (count, prefix, scatter into the scratch half of its block -- two more sweeps,
-//     from L2), and the partitions go through the table one after the other.  Should a partition
-//     still overflow the table (skewed input) it is swept once per hash sub-partition, with twice the
-//     sub-partitions after every overflow.
-//   set feature: its new-element log holds one cell index per distinct (cell, UMI).
-// Either way the counts land in a shared-memory histogram over cells plus a bitmap of the touched
-// cells; the set bits enumerated in order give the non-zeros in column order (the reference's emit
-// loop, rdr/fc/core.py:109-117).  The row goes to a staging area at an atomically reserved offset;
-// k_gather_rows puts the rows in input order.  Persistent CTAs take features from a work counter;
-// histogram and bitmap are cleared while they are read, so the next feature starts clean.  When the
-// cells do not fit the histogram (n_cols > hist_cols) the source is read once per column range,
-// first to count, then to write.
-#define FIN_THREADS 512
-#define FIN_WARPS (FIN_THREADS / 32)
-#define FIN_PARTS 1024       // hash partitions of a heavy segment (their counters live in the idle table)
-#define FIN_ILP 4            // pair words a thread has in flight in a sweep
+// ---- finalize: a feature whose last epoch just finished becomes its row of the matrix -----------------
+// The non-zeros of a row leave in column order (the reference's emit loop, rdr/fc/core.py:109-117), to a
+// staging area at an atomically reserved offset; k_gather_rows puts the rows in input order.  Persistent
+// CTAs take features from a work counter.
+//
+// Segment features (k_basefc_finalize_segs).  The feature's pair words (umi | cell; duplicates across
+// tiles are still in) are reduced in shared memory by small CTAs, five to an SM, so that one feature's
+// latencies hide behind another's:
+//   phase 1  every word sets the bit of its cell in a bitmap over all cells; the prefix popcounts of the
+//            bitmap give the row's size (reserved right away) and every cell's rank in the row;
+//   phase 2  the words go into an open-addressing table (64-bit CAS); every NEW word adds one to a counter
+//            indexed by its cell's rank;
+//   output   cell / counter pairs in rank order.
+// A light feature (<= FS_CAP words) keeps its words in registers between the phases.  A heavy one is first
+// split by column range into the scratch half of its block (count, prefix, scatter: two sweeps from L2), so
+// that a range's words fit the table and its cells the counters; ranges go through phase 2 one after
+// the other.  A range that still holds too many words (skewed cells) is swept once per hash sub-partition,
+// with twice the sub-partitions after a table overflow.
+#define FS_THREADS 256
+#define FS_WARPS (FS_THREADS / 32)
+#define FS_TBL SEG_TBL_SLOTS          // table slots (64-bit)
+#define FS_CAP SEG_PART_WORDS         // words a table pass should hold (40 % load); also the rank counters
+#define FS_REG 7                      // words a thread keeps in registers (FS_REG * FS_THREADS >= FS_CAP)
+#define FS_RANGES 1024                // column ranges of a heavy feature (counters live in the idle table)
+static_assert(FS_REG * FS_THREADS >= FS_CAP, "a light feature must fit the registers of its CTA");
 
 __device__ __forceinline__ uint64_t pair_hash(unsigned long long pw) {
     uint64_t h = pw * 0x9E3779B97F4A7C15ULL;
@@ -1027,166 +1037,330 @@ __device__ __forceinline__ uint64_t pair_hash(unsigned long long pw) {
     h *= 0xBF58476D1CE4E5B9ULL;
     return h;
 }
-// partition of a pair word among n_part (bits 32..63 of the hash; the table slot uses the top bits
-// after a second multiply, the sub-partition the low word)
-__device__ __forceinline__ uint32_t pair_part(uint64_t h, uint32_t n_part) {
-    return (uint32_t)(((h >> 32) * (uint64_t)n_part) >> 32);
-}
 
-struct FinShared {
-    int warp_tot[FIN_WARPS];
+struct FsShared {
+    uint32_t warp_tot[FS_WARPS];
     long long base_s;
-    int f_s, ovf_s;
-    uint32_t part_off[FIN_PARTS + 1];
+    int ovf_s;
+    int f_s[2];                       // this / the next work item (fetched one ahead)
+    uint32_t range_off[FS_RANGES + 1];
 };
 
-// Deduplicate words[0, n) whose cell lies in [c_lo, c_lo + nc) into hist / bitmap.  Block-wide.
-__device__ __forceinline__ void fin_dedup_range(unsigned long long *tbl, int32_t tbl_slots, uint32_t *hist,
-                                                uint32_t *bitmap, FinShared &F, const unsigned long long *words,
-                                                uint32_t n, uint32_t c_lo, int nc, uint32_t expect) {
-    if (n == 0) return;
-    // table of this sweep: 2.5 x the expected words, power of two
-    uint32_t n_sub = (uint32_t)(((uint64_t)expect * 5 / 2 + (uint64_t)tbl_slots - 1) / (uint64_t)tbl_slots);
-    if (n_sub == 0) n_sub = 1;
+// table of a pass over n words: a power of two >= 2.5 n, 64 .. FS_TBL slots
+__device__ __forceinline__ uint32_t fs_table_size(uint32_t n) {
     uint32_t tsz = 64;
-    const uint64_t per = (uint64_t)expect / n_sub + 1;
-    while (tsz < (uint32_t)tbl_slots && (uint64_t)tsz * 2 < per * 5) tsz <<= 1;
-    const int shift = 64 - (31 - __clz((int)tsz));
-    const uint32_t probe_max = min(tsz, 96u);
-    for (uint32_t sub = 0; sub < n_sub; sub++) {
-        for (uint32_t s = threadIdx.x; s < tsz; s += FIN_THREADS) tbl[s] = 0ULL;
-        __syncthreads();
-        for (uint32_t s0 = threadIdx.x; s0 < n; s0 += FIN_THREADS * FIN_ILP) {
-            unsigned long long pw[FIN_ILP];
+    while (tsz < FS_TBL && tsz * 2 < n * 5) tsz <<= 1;
+    return tsz;
+}
+
+// rank of cell `col` in the row: set bits below it
+__device__ __forceinline__ uint32_t fs_rank(const uint32_t *bitmap, const uint32_t *pre, uint32_t col) {
+    return pre[col >> 5] + (uint32_t)__popc(bitmap[col >> 5] & ((1u << (col & 31)) - 1u));
+}
+
+// one word into the table; a NEW word counts for its cell.  false: the table is too full
+__device__ __forceinline__ bool fs_insert(unsigned long long *tbl, uint32_t tsz, int shift, unsigned long long pw,
+                                          uint64_t h, uint32_t *cnt, uint32_t r, uint32_t probe_max) {
+    uint32_t slot = (uint32_t)((h * 0x9E3779B97F4A7C15ULL) >> shift);
+    for (uint32_t probe = 0; probe < probe_max; probe++) {
+        const unsigned long long old = atomicCAS(&tbl[slot], 0ULL, pw);
+        if (old == 0ULL) {
+            atomicAdd(&cnt[r], 1u);
+            return true;
+        }
+        if (old == pw) return true;
+        slot = (slot + 1) & (tsz - 1);
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
+    const uint8_t *pool, const FeatDesc *fdesc, const uint32_t *seg_cur, const int32_t *sf_row,
+    const int32_t *fin_feat, int32_t n_fin, int32_t n_cols, unsigned int *work, unsigned long long *cursor,
+    int64_t *seg_base, int32_t *seg_nnz, int32_t *st_col, int32_t *st_val) {
+    extern __shared__ __align__(16) uint8_t fin_smem[];
+    const int bm_words = (n_cols + 31) >> 5;
+    unsigned long long *tbl = reinterpret_cast<unsigned long long *>(fin_smem);      // FS_TBL
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(tbl + FS_TBL);                       // FS_CAP rank counters
+    uint32_t *bitmap = cnt + FS_CAP;                                                  // bm_words
+    uint32_t *pre = bitmap + bm_words;                                                // bm_words + 1
+    __shared__ FsShared F;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        F.ovf_s = 0;
+        F.f_s[0] = (int)atomicAdd(work, 1u);
+    }
+    for (int c = threadIdx.x; c < bm_words; c += FS_THREADS) bitmap[c] = 0;
+    for (int c = threadIdx.x; c < FS_CAP; c += FS_THREADS) cnt[c] = 0;
+
+    for (int it = 0;; it++) {
+        __syncthreads();             // the previous feature is out; bitmap and counters are clean
+        const int f = F.f_s[it & 1];
+        if (f >= n_fin) break;
+        if (threadIdx.x == 0) F.f_s[(it + 1) & 1] = (int)atomicAdd(work, 1u);     // consumed after the next barrier
+        const int32_t j = fin_feat[f];
+        const FeatDesc fd = fdesc[j];
+        const uint32_t n = seg_cur[j];
+        const unsigned long long *seg = (const unsigned long long *)(pool + fd.blk_off);
+        const bool light = n <= FS_CAP;
+
+        // ---- phase 1: bitmap of the row's cells (a light feature's words stay in registers)
+        unsigned long long pw[FS_REG];
+        if (light) {
 #pragma unroll
-            for (int q = 0; q < FIN_ILP; q++) {
-                const uint32_t s = s0 + (uint32_t)q * FIN_THREADS;
-                pw[q] = s < n ? words[s] : 0ULL;
+            for (int q = 0; q < FS_REG; q++) {
+                const uint32_t s = threadIdx.x + (uint32_t)q * FS_THREADS;
+                pw[q] = s < n ? seg[s] : 0ULL;
             }
+            const uint32_t tsz0 = fs_table_size(n);
+            for (uint32_t s = threadIdx.x; s < tsz0; s += FS_THREADS) tbl[s] = 0ULL;
 #pragma unroll
-            for (int q = 0; q < FIN_ILP; q++) {
-                if (pw[q] == 0ULL) continue;
-                const uint32_t col = (uint32_t)(pw[q] & 0xffffffULL) - c_lo;
-                if (col >= (uint32_t)nc) continue;
-                const uint64_t h = pair_hash(pw[q]);
-                if (n_sub > 1 && (uint32_t)(((h & 0xffffffffULL) * n_sub) >> 32) != sub) continue;
-                uint32_t slot = (uint32_t)((h * 0x9E3779B97F4A7C15ULL) >> shift);
-                uint32_t probe = 0;
-                for (; probe < probe_max; probe++) {
-                    const unsigned long long old = atomicCAS(&tbl[slot], 0ULL, pw[q]);
-                    if (old == 0ULL) {
-                        if (atomicAdd(&hist[col], 1u) == 0) atomicOr(&bitmap[col >> 5], 1u << (col & 31));
-                        break;
-                    }
-                    if (old == pw[q]) break;
-                    slot = (slot + 1) & (tsz - 1);
+            for (int q = 0; q < FS_REG; q++)
+                if (pw[q]) {
+                    const uint32_t col = (uint32_t)(pw[q] & 0xffffffULL);
+                    atomicOr(&bitmap[col >> 5], 1u << (col & 31));
                 }
-                if (probe == probe_max) F.ovf_s = 1;     // the caller forgets the column range and asks again, finer
+        } else {
+            for (uint32_t s0 = threadIdx.x; s0 < n; s0 += FS_THREADS * 4) {
+                unsigned long long v[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t s = s0 + (uint32_t)q * FS_THREADS;
+                    v[q] = s < n ? seg[s] : 0ULL;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (v[q]) {
+                        const uint32_t col = (uint32_t)(v[q] & 0xffffffULL);
+                        atomicOr(&bitmap[col >> 5], 1u << (col & 31));
+                    }
             }
         }
         __syncthreads();
-        if (F.ovf_s) return;
+        // ---- prefix popcounts: pre[k] = set bits in words [0, k); the row's size; its place in the staging area
+        {
+            const int per = (bm_words + FS_THREADS - 1) / FS_THREADS;
+            const int k0 = threadIdx.x * per, k1 = min(bm_words, k0 + per);
+            uint32_t mine = 0;
+            for (int k = k0; k < k1; k++) mine += (uint32_t)__popc(bitmap[k]);
+            uint32_t incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += y;
+            }
+            if (lane == 31) F.warp_tot[w] = incl;
+            __syncthreads();
+            uint32_t run = incl - mine;
+            for (int q = 0; q < w; q++) run += F.warp_tot[q];
+            for (int k = k0; k < k1; k++) {
+                pre[k] = run;
+                run += (uint32_t)__popc(bitmap[k]);
+            }
+            if (threadIdx.x == FS_THREADS - 1) {
+                pre[bm_words] = run;
+                const int32_t row = sf_row[j];
+                const long long b = run ? (long long)atomicAdd(cursor, (unsigned long long)run) : 0;
+                seg_base[row] = b;
+                seg_nnz[row] = (int32_t)run;
+                F.base_s = b;
+            }
+        }
+        __syncthreads();
+        const long long base = F.base_s;
+
+        if (light) {
+            // ---- phase 2 from the registers, then the row
+            const uint32_t tsz = fs_table_size(n);
+            const int shift = 64 - (31 - __clz((int)tsz));
+            // the table is at most 40 % full: with the whole table as probe limit an insert cannot fail
+#pragma unroll
+            for (int q = 0; q < FS_REG; q++)
+                if (pw[q]) {
+                    const uint32_t col = (uint32_t)(pw[q] & 0xffffffULL);
+                    fs_insert(tbl, tsz, shift, pw[q], pair_hash(pw[q]), cnt, fs_rank(bitmap, pre, col), tsz);
+                }
+            __syncthreads();
+            for (int k = threadIdx.x; k < bm_words; k += FS_THREADS) {
+                uint32_t bits = bitmap[k];
+                if (!bits) continue;
+                uint32_t r = pre[k];
+                bitmap[k] = 0;
+                while (bits) {
+                    const int bpos = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    st_col[base + r] = (k << 5) + bpos;
+                    st_val[base + r] = (int32_t)cnt[r];
+                    cnt[r] = 0;
+                    r++;
+                }
+            }
+            continue;
+        }
+
+        // ---- heavy feature: split by column range into the scratch half of the block
+        // range width: a power of two (>= 32 cells) with about 3/4 FS_CAP expected words and at most FS_CAP cells
+        int wshift = 5;
+        while (wshift < 10 && ((uint64_t)n << (wshift + 1)) <= (uint64_t)(FS_CAP * 3 / 4) * (uint64_t)n_cols) wshift++;
+        while (wshift > 5 && (1u << wshift) > FS_CAP) wshift--;
+        while (((n_cols - 1) >> wshift) + 1 > FS_RANGES) wshift++;      // very many cells: wider ranges, hash sub-partitions
+        const uint32_t n_rng = (uint32_t)((n_cols - 1) >> wshift) + 1;
+        uint32_t *rc = reinterpret_cast<uint32_t *>(tbl);             // the table is idle: counters, then cursors
+        for (uint32_t q = threadIdx.x; q < n_rng; q += FS_THREADS) rc[q] = 0;
+        __syncthreads();
+        for (uint32_t s0 = threadIdx.x; s0 < n; s0 += FS_THREADS * 4) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t s = s0 + (uint32_t)q * FS_THREADS;
+                v[q] = s < n ? seg[s] : 0ULL;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (v[q]) atomicAdd(&rc[(uint32_t)(v[q] & 0xffffffULL) >> wshift], 1u);
+        }
+        __syncthreads();
+        {   // exclusive prefix over the n_rng counters
+            const int per = (int)((n_rng + FS_THREADS - 1) / FS_THREADS);
+            const uint32_t k0 = threadIdx.x * (uint32_t)per, k1 = min(n_rng, k0 + (uint32_t)per);
+            uint32_t mine = 0;
+            for (uint32_t k = k0; k < k1; k++) mine += rc[k];
+            uint32_t incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += y;
+            }
+            if (lane == 31) F.warp_tot[w] = incl;
+            __syncthreads();
+            uint32_t run = incl - mine;
+            for (int q = 0; q < w; q++) run += F.warp_tot[q];
+            for (uint32_t k = k0; k < k1; k++) {
+                const uint32_t c = rc[k];
+                F.range_off[k] = run;
+                rc[k] = run;
+                run += c;
+            }
+            if (threadIdx.x == FS_THREADS - 1) F.range_off[n_rng] = n;
+        }
+        __syncthreads();
+        unsigned long long *scr = const_cast<unsigned long long *>(seg) + ((((size_t)fd.log_cap) + 1) & ~(size_t)1);
+        for (uint32_t s0 = threadIdx.x; s0 < n; s0 += FS_THREADS * 4) {
+            unsigned long long v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t s = s0 + (uint32_t)q * FS_THREADS;
+                v[q] = s < n ? seg[s] : 0ULL;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (v[q]) scr[atomicAdd(&rc[(uint32_t)(v[q] & 0xffffffULL) >> wshift], 1u)] = v[q];
+        }
+        __syncthreads();
+        // ---- the ranges, one after the other
+        for (uint32_t rg = 0; rg < n_rng; rg++) {
+            const uint32_t p0 = F.range_off[rg], m = F.range_off[rg + 1] - p0;
+            if (m == 0) continue;
+            const uint32_t c0 = rg << wshift, c1 = min((uint32_t)n_cols, c0 + (1u << wshift));
+            const uint32_t k_lo = c0 >> 5, k_hi = (c1 + 31) >> 5;
+            const uint32_t rank0 = pre[k_lo];
+            const uint32_t nz_r = pre[k_hi] - rank0;
+            // cells of the range that do not fit the counters are taken in windows of FS_CAP ranks
+            for (uint32_t win = 0; win < nz_r; win += FS_CAP) {
+                uint32_t n_sub = (m + FS_CAP - 1) / FS_CAP;
+                while (true) {
+                    uint32_t tsz = 64;
+                    const uint32_t per = m / n_sub + 1;
+                    while (tsz < FS_TBL && tsz * 2 < per * 5) tsz <<= 1;
+                    const int shift = 64 - (31 - __clz((int)tsz));
+                    for (uint32_t sub = 0; sub < n_sub; sub++) {
+                        for (uint32_t s = threadIdx.x; s < tsz; s += FS_THREADS) tbl[s] = 0ULL;
+                        __syncthreads();
+                        for (uint32_t s0 = threadIdx.x; s0 < m; s0 += FS_THREADS * 4) {
+                            unsigned long long v[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint32_t s = s0 + (uint32_t)q * FS_THREADS;
+                                v[q] = s < m ? scr[p0 + s] : 0ULL;
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                if (!v[q]) continue;
+                                const uint64_t h = pair_hash(v[q]);
+                                if (n_sub > 1 && (uint32_t)(((h & 0xffffffffULL) * n_sub) >> 32) != sub) continue;
+                                const uint32_t r = fs_rank(bitmap, pre, (uint32_t)(v[q] & 0xffffffULL)) - rank0 - win;
+                                if (r >= FS_CAP) continue;                       // another window of this range
+                                if (!fs_insert(tbl, tsz, shift, v[q], h, cnt, r, min(tsz, 96u))) F.ovf_s = 1;
+                            }
+                        }
+                        __syncthreads();
+                        if (F.ovf_s) break;
+                    }
+                    if (!F.ovf_s) break;
+                    // a pass overflowed the table: forget the window's counts, sweep again with finer sub-partitions
+                    __syncthreads();
+                    for (uint32_t c = threadIdx.x; c < FS_CAP; c += FS_THREADS) cnt[c] = 0;
+                    if (threadIdx.x == 0) F.ovf_s = 0;
+                    n_sub *= 2;
+                    __syncthreads();
+                }
+                // the window's part of the row
+                for (uint32_t k = k_lo + threadIdx.x; k < k_hi; k += FS_THREADS) {
+                    uint32_t bits = bitmap[k];
+                    uint32_t r = pre[k];
+                    while (bits) {
+                        const int bpos = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const uint32_t rr = r - rank0 - win;
+                        if (rr < FS_CAP) {
+                            st_col[base + r] = (int32_t)((k << 5) + (uint32_t)bpos);
+                            st_val[base + r] = (int32_t)cnt[rr];
+                        }
+                        r++;
+                    }
+                }
+                __syncthreads();
+                for (uint32_t c = threadIdx.x; c < min(nz_r - win, (uint32_t)FS_CAP); c += FS_THREADS) cnt[c] = 0;
+                __syncthreads();
+            }
+        }
+        for (int k = threadIdx.x; k < bm_words; k += FS_THREADS) bitmap[k] = 0;
     }
 }
 
-__global__ void __launch_bounds__(FIN_THREADS) k_basefc_finalize(
-    const uint8_t *pool, const FeatDesc *fdesc, const uint32_t *seg_cur, const int32_t *sf_row,
-    const int32_t *fin_feat, int32_t n_fin, int32_t n_cols, int32_t hist_cols, int32_t tbl_slots,
-    uint32_t part_min, unsigned int *work, unsigned long long *cursor, int64_t *seg_base, int32_t *seg_nnz,
-    int32_t *st_col, int32_t *st_val) {
+// Set features (and every feature of a batch whose UMI keys do not fit the pair word): the feature's
+// new-element log holds one cell index per distinct (cell, UMI); it is reduced through a shared-memory
+// histogram over the cells plus a bitmap of the touched cells, cleared while they are read so that the next
+// feature starts clean.  When the cells do not fit the histogram (n_cols > hist_cols) the log is read once
+// per column range, first to count, then to write.
+#define FIN_THREADS 512
+#define FIN_WARPS (FIN_THREADS / 32)
+
+__global__ void __launch_bounds__(FIN_THREADS) k_basefc_finalize_sets(
+    const uint8_t *pool, const FeatDesc *fdesc, const int32_t *sf_row, const int32_t *fin_feat, int32_t n_fin,
+    int32_t n_cols, int32_t hist_cols, unsigned int *work, unsigned long long *cursor, int64_t *seg_base,
+    int32_t *seg_nnz, int32_t *st_col, int32_t *st_val) {
     extern __shared__ __align__(16) uint8_t fin_smem[];
-    unsigned long long *tbl = reinterpret_cast<unsigned long long *>(fin_smem);      // tbl_slots (power of two)
-    uint32_t *hist = reinterpret_cast<uint32_t *>(tbl + tbl_slots);                   // hist_cols
+    uint32_t *hist = reinterpret_cast<uint32_t *>(fin_smem);                          // hist_cols
     uint32_t *bitmap = hist + hist_cols;                                              // (hist_cols + 31) / 32
-    __shared__ FinShared F;
+    __shared__ int warp_tot[FIN_WARPS];
+    __shared__ long long base_s;
+    __shared__ int f_s;
     const int n_words_max = (hist_cols + 31) >> 5;
     for (int c = threadIdx.x; c < hist_cols; c += FIN_THREADS) hist[c] = 0;
     for (int c = threadIdx.x; c < n_words_max; c += FIN_THREADS) bitmap[c] = 0;
-    if (threadIdx.x == 0) F.ovf_s = 0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n_pass = (n_cols + hist_cols - 1) / hist_cols;
-    const uint32_t part_words = (uint32_t)tbl_slots * 2 / 5;      // words a partition should hold (40 % load)
 
     while (true) {
         __syncthreads();
-        if (threadIdx.x == 0) F.f_s = (int)atomicAdd(work, 1u);
+        if (threadIdx.x == 0) f_s = (int)atomicAdd(work, 1u);
         __syncthreads();
-        const int f = F.f_s;
+        const int f = f_s;
         if (f >= n_fin) break;
         const int32_t j = fin_feat[f];
         const FeatDesc fd = fdesc[j];
-        const bool is_set = fd.cap != 0;
-        const uint32_t *log = nullptr;
-        const unsigned long long *seg = nullptr;
-        uint32_t n_src;
-        if (is_set) {
-            const uint32_t *cur_p = (const uint32_t *)(pool + fd.blk_off + (size_t)fd.cap * 16);
-            n_src = cur_p[0];
-            log = cur_p + 4;
-        } else {
-            n_src = seg_cur[j];
-            seg = (const unsigned long long *)(pool + fd.blk_off);
-        }
-        // ---- a heavy segment is split by hash into the scratch half of its block
-        uint32_t n_part = 1;
-        if (!is_set && n_src > part_words && fd.log_cap > part_min) {
-            n_part = min((uint32_t)FIN_PARTS, (n_src + part_words - 1) / part_words);
-            uint32_t *cnt = reinterpret_cast<uint32_t *>(tbl);          // the table is idle: counters, then cursors
-            for (uint32_t q = threadIdx.x; q < n_part; q += FIN_THREADS) cnt[q] = 0;
-            __syncthreads();
-            for (uint32_t s0 = threadIdx.x; s0 < n_src; s0 += FIN_THREADS * FIN_ILP) {
-                unsigned long long pw[FIN_ILP];
-#pragma unroll
-                for (int q = 0; q < FIN_ILP; q++) {
-                    const uint32_t s = s0 + (uint32_t)q * FIN_THREADS;
-                    pw[q] = s < n_src ? seg[s] : 0ULL;
-                }
-#pragma unroll
-                for (int q = 0; q < FIN_ILP; q++)
-                    if (pw[q]) atomicAdd(&cnt[pair_part(pair_hash(pw[q]), n_part)], 1u);
-            }
-            __syncthreads();
-            // exclusive prefix over the n_part <= FIN_PARTS counters (two per thread)
-            {
-                const uint32_t q0 = 2 * threadIdx.x, q1 = q0 + 1;
-                const uint32_t a = q0 < n_part ? cnt[q0] : 0u, b = q1 < n_part ? cnt[q1] : 0u;
-                uint32_t incl = a + b;
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += y;
-                }
-                if (lane == 31) F.warp_tot[w] = (int)incl;
-                __syncthreads();
-                uint32_t before = 0;
-                for (int q = 0; q < w; q++) before += (uint32_t)F.warp_tot[q];
-                const uint32_t excl = before + incl - (a + b);
-                if (q0 <= n_part) F.part_off[q0] = excl;
-                if (q1 <= n_part) F.part_off[q1] = excl + a;
-                __syncthreads();
-                if (q0 < n_part) cnt[q0] = excl;
-                if (q1 < n_part) cnt[q1] = excl + a;
-                if (threadIdx.x == 0) F.part_off[n_part] = n_src;
-                __syncthreads();
-            }
-            unsigned long long *scr = const_cast<unsigned long long *>(seg) + ((((size_t)fd.log_cap) + 1) & ~(size_t)1);
-            for (uint32_t s0 = threadIdx.x; s0 < n_src; s0 += FIN_THREADS * FIN_ILP) {
-                unsigned long long pw[FIN_ILP];
-#pragma unroll
-                for (int q = 0; q < FIN_ILP; q++) {
-                    const uint32_t s = s0 + (uint32_t)q * FIN_THREADS;
-                    pw[q] = s < n_src ? seg[s] : 0ULL;
-                }
-#pragma unroll
-                for (int q = 0; q < FIN_ILP; q++)
-                    if (pw[q]) scr[atomicAdd(&cnt[pair_part(pair_hash(pw[q]), n_part)], 1u)] = pw[q];
-            }
-            __syncthreads();
-            seg = scr;
-        } else if (threadIdx.x == 0) {
-            F.part_off[0] = 0;
-            F.part_off[1] = n_src;
-        }
-        __syncthreads();
+        const uint32_t *cur_p = (const uint32_t *)(pool + fd.blk_off + (size_t)fd.cap * 16);
+        const uint32_t n_new = cur_p[0];
+        const uint32_t *log = cur_p + 4;
         long long base = 0;
         // stage 0 (only when n_pass > 1): count; stage 1: write
         for (int stage = (n_pass > 1 ? 0 : 1); stage < 2; stage++) {
@@ -1195,40 +1369,20 @@ __global__ void __launch_bounds__(FIN_THREADS) k_basefc_finalize(
                 const uint32_t c_lo = (uint32_t)pass * (uint32_t)hist_cols;
                 const int nc = min(hist_cols, n_cols - (int)c_lo);
                 const int nw = (nc + 31) >> 5;
-                if (is_set) {
-                    for (uint32_t s = threadIdx.x; s < n_src; s += FIN_THREADS) {
-                        const uint32_t col = log[s] - c_lo;
-                        if (col < (uint32_t)nc && atomicAdd(&hist[col], 1u) == 0)
-                            atomicOr(&bitmap[col >> 5], 1u << (col & 31));
-                    }
-                    __syncthreads();
-                } else {
-                    uint32_t grow = 1;
-                    while (true) {
-                        for (uint32_t part = 0; part < n_part; part++) {
-                            const uint32_t p0 = F.part_off[part], pn = F.part_off[part + 1] - p0;
-                            fin_dedup_range(tbl, tbl_slots, hist, bitmap, F, seg + p0, pn, c_lo, nc,
-                                            (pn / (uint32_t)n_pass + 1) * grow);
-                            if (F.ovf_s) break;
-                        }
-                        if (!F.ovf_s) break;
-                        // a sweep overflowed the table: forget this column range, go again with finer sub-partitions
-                        __syncthreads();
-                        for (int c = threadIdx.x; c < nc; c += FIN_THREADS) hist[c] = 0;
-                        for (int c = threadIdx.x; c < nw; c += FIN_THREADS) bitmap[c] = 0;
-                        if (threadIdx.x == 0) F.ovf_s = 0;
-                        grow *= 2;
-                        __syncthreads();
-                    }
+                for (uint32_t s = threadIdx.x; s < n_new; s += FIN_THREADS) {
+                    const uint32_t col = log[s] - c_lo;
+                    if (col < (uint32_t)nc && atomicAdd(&hist[col], 1u) == 0)
+                        atomicOr(&bitmap[col >> 5], 1u << (col & 31));
                 }
+                __syncthreads();
                 const bool writing = (stage == 1);
                 if (!writing || n_pass == 1) {            // non-zero cells of this range
                     int nz = 0;
                     for (int k = threadIdx.x; k < nw; k += FIN_THREADS) nz += __popc(bitmap[k]);
                     for (int d = 16; d > 0; d >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, d);
-                    if (lane == 0) F.warp_tot[w] = nz;
+                    if (lane == 0) warp_tot[w] = nz;
                     __syncthreads();
-                    for (int k = 0; k < FIN_WARPS; k++) total_nz += F.warp_tot[k];
+                    for (int k = 0; k < FIN_WARPS; k++) total_nz += warp_tot[k];
                     __syncthreads();
                 }
                 if (writing && n_pass == 1) {             // single range: reserve now
@@ -1237,10 +1391,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_basefc_finalize(
                         long long b = total_nz ? (long long)atomicAdd(cursor, (unsigned long long)total_nz) : 0;
                         seg_base[row] = b;
                         seg_nnz[row] = total_nz;
-                        F.base_s = b;
+                        base_s = b;
                     }
                     __syncthreads();
-                    base = F.base_s;
+                    base = base_s;
                 }
                 // ordered walk over the bitmap words; clears histogram and bitmap as it goes
                 for (int k0 = 0; k0 < nw; k0 += FIN_THREADS) {
@@ -1251,11 +1405,11 @@ __global__ void __launch_bounds__(FIN_THREADS) k_basefc_finalize(
                         int y = __shfl_up_sync(0xffffffffu, incl, d);
                         if (lane >= d) incl += y;
                     }
-                    if (lane == 31) F.warp_tot[w] = incl;
+                    if (lane == 31) warp_tot[w] = incl;
                     __syncthreads();
                     int before = 0, tot = 0;
                     for (int q = 0; q < FIN_WARPS; q++) {
-                        const int x = F.warp_tot[q];
+                        const int x = warp_tot[q];
                         if (q < w) before += x;
                         tot += x;
                     }
@@ -1282,10 +1436,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_basefc_finalize(
                     long long b = total_nz ? (long long)atomicAdd(cursor, (unsigned long long)total_nz) : 0;
                     seg_base[row] = b;
                     seg_nnz[row] = total_nz;
-                    F.base_s = b;
+                    base_s = b;
                 }
                 __syncthreads();
-                base = F.base_s;
+                base = base_s;
             }
         }
     }
@@ -1473,7 +1627,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     // its low 24 bits free: packed strings of up to 13 symbols, interned ids below 2^39), features collect
     // their words in segments.  The kernel verifies the keys it meets; a key that does not fit raises a
     // flag and the call is redone with a set per feature (and the batch remembers it).
-    bool seg_mode = !force_sets && n_cols <= (1 << 24) && rd->umi_compact != 0;
+    bool seg_mode = !force_sets && n_cols <= (1 << 19) && rd->umi_compact != 0;      // cell bitmap + ranks in shared memory
     if (const char *e = getenv("XG_SEG_MODE")) seg_mode = seg_mode && atoi(e) != 0;
     uint64_t seg_max = 1ull << 22;             // heavier features keep a set in global memory
     if (const char *e = getenv("XG_SEG_MAX")) seg_max = (uint64_t)atoll(e);
@@ -1482,7 +1636,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     if ((rc = make_plan(ctx, cand, tlo, thi, rd->n_tiles, n_cols, epoch_tiles, seg_mode ? seg_max : 0, pl))) return rc;
     const double ms_plan = ms_since(t_ph);
     t_ph = now();
-    const int32_t *d_fin_feat = nullptr;
+    const int32_t *d_fin_feat = nullptr, *d_fin_set = nullptr;
     const uint64_t *d_zoff = nullptr, *d_zpre = nullptr;
     std::vector<FeatDesc> fdesc(m);
     std::vector<uint32_t> segoff16(m);
@@ -1499,6 +1653,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         XG_DBG("k_patch_stab");
     }
     if ((rc = upload_vec(ctx, pl.fin_feat, "fx_fin_feat", &d_fin_feat))) return rc;
+    if ((rc = upload_vec(ctx, pl.fin_set, "fx_fin_set", &d_fin_set))) return rc;
     if ((rc = upload_vec(ctx, pl.zseg_off, "fx_zseg_off", &d_zoff))) return rc;
     if ((rc = upload_vec(ctx, pl.zseg_pre, "fx_zseg_pre", &d_zpre))) return rc;
     if (par->min_incl_tab) {
@@ -1529,9 +1684,10 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_GET(st_col, int32_t, "fx_st_col", pl.staging_cap + 1);
     XG_GET(st_val, int32_t, "fx_st_val", pl.staging_cap + 1);
     XG_GET(cursor, unsigned long long, "fx_cursor", 2);
-    XG_GET(fin_work, unsigned int, "fx_fin_work", 2 * (pl.n_epochs + 1) + 4);
+    XG_GET(fin_work, unsigned int, "fx_fin_work", 3 * (pl.n_epochs + 1) + 4);
     unsigned int *cnt_work = fin_work + pl.n_epochs + 1;          // tile counters of the counting launches
-    unsigned int *d_flags = fin_work + 2 * (pl.n_epochs + 1);
+    unsigned int *set_work = fin_work + 2 * (pl.n_epochs + 1);    // work counters of the set finalize launches
+    unsigned int *d_flags = fin_work + 3 * (pl.n_epochs + 1);
     XG_GET(seg_cur, uint32_t, "fx_seg_cur", m + 1);
     P.pool = pool;
     P.seg_cur = seg_cur;
@@ -1539,27 +1695,31 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors above are about to die
     const double ms_upload = ms_since(t_ph);
 
-    // shared memory of the finalize kernel: dedup table of the segment features (pair-word mode),
-    // histogram (+ bitmap) over the cells -- all cells if they fit
-    const int32_t tbl_slots = seg_mode ? SEG_TBL_SLOTS : 0;
-    int32_t hist_cols = std::min(n_cols, seg_mode ? 10 * 1024 : 40 * 1024);
-    if (seg_mode && n_cols > hist_cols) hist_cols = std::min(n_cols, 36 * 1024);     // one CTA per SM, fewer column ranges
+    // shared memory of the finalize kernels.  Segments: dedup table, rank counters, bitmap over the cells and
+    // its prefix popcounts.  Sets: histogram (+ bitmap) over the cells -- all cells if they fit.
+    const int bm_words = (n_cols + 31) / 32;
+    const size_t segs_bytes = (size_t)FS_TBL * 8 + (size_t)FS_CAP * 4 + (size_t)(2 * bm_words + 1) * 4;
+    XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_bytes));
+    const int segs_ctas_per_sm = std::max(1, std::min(8, (int)(224 * 1024 / (segs_bytes + sizeof(FsShared) + 1280))));
+    int32_t hist_cols = std::min(n_cols, 40 * 1024);
     if (const char *e = getenv("XG_HIST_COLS")) hist_cols = std::max(32, std::min(n_cols, atoi(e)));
-    const size_t hist_bytes = (size_t)tbl_slots * 8 + (size_t)hist_cols * 4 + (size_t)((hist_cols + 31) / 32) * 4;
-    XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+    const size_t hist_bytes = (size_t)hist_cols * 4 + (size_t)((hist_cols + 31) / 32) * 4;
+    XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_sets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
     const int fin_ctas_per_sm = std::max(1, std::min(4, (int)(220 * 1024 / (hist_bytes + 2048))));
     int cnt_ctas_per_sm = 4;
     if (const char *e = getenv("XG_CNT_CTAS")) cnt_ctas_per_sm = atoi(e) == 3 ? 3 : 4;
     void (*count_kernel)(const BasefcDev) = cnt_ctas_per_sm == 3 ? k_basefc_count<3> : k_basefc_count<4>;
     XG_CUDA(cudaFuncSetAttribute(count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CountSmem)));
 
-    // ---- device: epochs.  zero(e) -> count(e) -> finalize(e) per epoch; with overlap the three
-    // kinds run on their own streams and count(e+1) fills the SMs while count(e) drains:
-    //   zero(e)     waits finalize(e-2)           (its blocks were released by then)
-    //   count(e)    waits zero(e)                 (alternating between two streams)
-    //   finalize(e) waits count(e), count(e-1)
-    bool overlap = pl.n_epochs > 1;
-    if (const char *e = getenv("XG_OVERLAP")) overlap = overlap && atoi(e) != 0;
+    // ---- device: epochs.  zero(e) -> count(e) -> finalize(e) per epoch:
+    //   zero(e)     after finalize(e-2)           (the arena of epoch e is free again)
+    //   count(e)    after zero(e)
+    //   finalize(e) after count(e)
+    // XG_OVERLAP=1: zero / finalize kernels on their own streams next to the counting kernel.  The counting
+    // kernel is persistent and fills the GPU by itself, so by default the kernels of the epochs follow one
+    // another on one stream and only the result copy runs beside them.
+    bool overlap = false;
+    if (const char *e = getenv("XG_OVERLAP")) overlap = pl.n_epochs > 1 && atoi(e) != 0;
     if ((overlap || src) && !ctx->aux[0])
         for (auto &st : ctx->aux) XG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (src && !ctx->copy_stream) XG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -1573,7 +1733,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_CUDA(cudaMemsetAsync(seg_nnz, 0, sizeof(int32_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(seg_base, 0, sizeof(int64_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
-    XG_CUDA(cudaMemsetAsync(fin_work, 0, sizeof(unsigned int) * (size_t)(2 * (pl.n_epochs + 1) + 4), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(fin_work, 0, sizeof(unsigned int) * (size_t)(3 * (pl.n_epochs + 1) + 4), ctx->stream));
     XG_CUDA(cudaMemsetAsync(seg_cur, 0, sizeof(uint32_t) * (m + 1), ctx->stream));
     launches += 6;
     cudaEventRecord(ev_init, ctx->stream);
@@ -1601,7 +1761,8 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     }
     int64_t h2d_bytes = 0;
     for (int32_t e = 0; e < pl.n_epochs; e++) {
-        cudaStream_t st_c = overlap ? ((e & 1) ? ctx->aux[2] : ctx->stream) : ctx->stream;
+        // the counting kernels are persistent (they fill the GPU on their own): one stream for all of them
+        cudaStream_t st_c = ctx->stream;
         if (src) {      // this epoch's records: host -> HBM on the copy stream
             const int32_t ta = e * pl.epoch_tiles, tb_ = std::min(rd->n_tiles, ta + pl.epoch_tiles);
             if (tb_ > ta) {
@@ -1651,17 +1812,26 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         }
         cudaEventRecord(EV(2, e), st_c);
         const int32_t n_fin = pl.fin_ptr[(size_t)e + 1] - pl.fin_ptr[(size_t)e];
+        const int32_t n_fin_set = pl.fin_set_ptr[(size_t)e + 1] - pl.fin_set_ptr[(size_t)e];
         if (overlap) {
             cudaStreamWaitEvent(st_f, EV(2, e), 0);
             if (e > 0) cudaStreamWaitEvent(st_f, EV(2, e - 1), 0);
         }
         if (n_fin > 0) {
-            const int grid = std::min(n_fin, 148 * fin_ctas_per_sm);
-            k_basefc_finalize<<<grid, FIN_THREADS, hist_bytes, st_f>>>(
-                pool, P.fdesc, seg_cur, d_sf_row, d_fin_feat + pl.fin_ptr[(size_t)e], n_fin, n_cols, hist_cols,
-                tbl_slots, (uint32_t)SEG_PART_WORDS, fin_work + e, cursor, seg_base, seg_nnz, st_col, st_val);
+            const int grid = std::min(n_fin, 148 * segs_ctas_per_sm);
+            k_basefc_finalize_segs<<<grid, FS_THREADS, segs_bytes, st_f>>>(
+                pool, P.fdesc, seg_cur, d_sf_row, d_fin_feat + pl.fin_ptr[(size_t)e], n_fin, n_cols, fin_work + e,
+                cursor, seg_base, seg_nnz, st_col, st_val);
             launches++;
-            XG_DBG("k_basefc_finalize");
+            XG_DBG("k_basefc_finalize_segs");
+        }
+        if (n_fin_set > 0) {
+            const int grid = std::min(n_fin_set, 148 * fin_ctas_per_sm);
+            k_basefc_finalize_sets<<<grid, FIN_THREADS, hist_bytes, st_f>>>(
+                pool, P.fdesc, d_sf_row, d_fin_set + pl.fin_set_ptr[(size_t)e], n_fin_set, n_cols, hist_cols,
+                set_work + e, cursor, seg_base, seg_nnz, st_col, st_val);
+            launches++;
+            XG_DBG("k_basefc_finalize_sets");
         }
         // the snapshot is a store into mapped host memory, not a copy: a D2H of 8 bytes would queue
         // behind the result copies on the copy engine and stall the finalize stream with them

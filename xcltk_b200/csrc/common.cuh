@@ -252,7 +252,7 @@ __host__ __device__ __forceinline__ uint32_t hash_to_range(uint64_t h, uint32_t 
     return (uint32_t)(((h >> 32) * (uint64_t)cap) >> 32);
 }
 
-__device__ __forceinline__ bool cig_aligned(uint32_t op) { return op == 0 || op == 7 || op == 8; }
+__device__ __forceinline__ bool cig_aligned(uint32_t op) { return (0x181u >> op) & 1u; }       // M, =, X
 __device__ __forceinline__ bool cig_skips_ref(uint32_t op) { return op == 2 || op == 3; }
 
 // Cell-barcode lookup table (open addressing, linear probing; empty = XG_KEY_NONE).
@@ -260,9 +260,15 @@ __device__ __forceinline__ bool cig_skips_ref(uint32_t op) { return op == 2 || o
 struct BarcodeTable {
     const ulonglong2 *slots;
     uint32_t mask;
+    uint32_t shift;      // 32 - log2(slots)
 };
+// home slot: the two halves of the key folded, one 32-bit multiply, top bits (a 64-bit mix costs
+// four times the instructions and the packed barcode strings spread their entropy over both halves)
+__host__ __device__ __forceinline__ uint32_t barcode_home(uint64_t key, uint32_t shift) {
+    return (((uint32_t)key ^ (uint32_t)(key >> 32)) * 0x9E3779B1u) >> shift;
+}
 __device__ __forceinline__ int32_t barcode_lookup(const BarcodeTable &t, uint64_t key) {
-    uint32_t s = (uint32_t)mix64(key) & t.mask;
+    uint32_t s = barcode_home(key, t.shift);
     while (true) {
         const ulonglong2 e = __ldg(&t.slots[s]);
         if (e.x == key) return (int32_t)e.y;

@@ -334,14 +334,17 @@ int xg_make_tile_pmax(xg_ctx *ctx, xg_dreads *d) {
 // Build the open-addressing cell-barcode table on the host and upload it.
 // Replaces the dict lookup `smp in self.cell_cnt` (rdr/fc/mcount.py:119-127).
 int xg_build_barcode_table(xg_ctx *ctx, const xg_barcodes *cells, BarcodeTable *out) {
-    uint32_t cap = 16;
-    while (cap < (uint32_t)cells->n * 2u + 2u) cap <<= 1;
+    uint32_t cap = 16, log2cap = 4;
+    while (cap < (uint32_t)cells->n * 2u + 2u) {
+        cap <<= 1;
+        log2cap++;
+    }
     std::vector<ulonglong2> tab(cap, make_ulonglong2(XG_KEY_NONE, 0));
     for (int32_t i = 0; i < cells->n; i++) {
         uint64_t key = cells->keys[i];
         if (key == XG_KEY_NONE || key == XG_KEY_NOMATCH)
             return ctx->fail(XG_E_ARG, "invalid barcode key");
-        uint32_t s = (uint32_t)mix64(key) & (cap - 1);
+        uint32_t s = barcode_home(key, 32 - log2cap);
         while (tab[s].x != XG_KEY_NONE) {
             if (tab[s].x == key) return ctx->fail(XG_E_ARG, "duplicate barcode key");
             s = (s + 1) & (cap - 1);
@@ -353,5 +356,6 @@ int xg_build_barcode_table(xg_ctx *ctx, const xg_barcodes *cells, BarcodeTable *
     XG_CUDA(cudaStreamSynchronize(ctx->stream));   // tab goes out of scope
     out->slots = dt;
     out->mask = cap - 1;
+    out->shift = 32 - log2cap;
     return XG_OK;
 }
