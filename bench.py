@@ -4,13 +4,19 @@
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-A step = one pass of both hot paths over one batch per GPU:
+A step = one pass of both hot paths over one library:
   basefc on config C3 (10k cells, 300M reads, ~60k features: hg38 genes + seeded nested intervals)
   baf fc  on config C2 (5k cells, 50M reads chr1-22, 200k phased het SNPs)
 `value` = reads counted / step time with the records already resident in HBM; `e2e` = the
 same through the C-ABI with HOST (pinned) record buffers, H2D upload and D2H result copy
-inside the timed region.  Multi-GPU: one batch (library) per GPU, no collective ("weak").
-The reference arm times the CPU oracle (a C port of the reference's algorithm; the
+inside the timed region.
+Multi-GPU (`--scaling strong`, the default): ONE library cut into N contiguous genomic chunks balanced by
+reads, one per GPU -- its features / regions and the reads that can overlap them (halo included); disjoint
+rows, no collective in the data path (NCCL carries the barrier, the timing maximum and the parity checksum).
+The rows of all ranks are checked against the unsharded matrix (order-independent checksum, outside the timed
+region).  `--scaling weak`: one whole library per GPU (round 1's line).
+At N=1 the GPU's matrices are compared entry by entry with the CPU oracle's on the SAME batch; a mismatch
+fails the run.  The reference arm times the CPU oracle (a C port of the reference's algorithm; the
 reference itself is Python on pysam and cannot run on the box) on a bounded sample.
 """
 
@@ -27,8 +33,17 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-C_BAR = 1.43                      # mean CIGAR ops per read of the synthetic mix
-BASEFC_BYTES_PER_READ = 28 + 4 * C_BAR
+C_BAR_NOMINAL = 1.43              # mean CIGAR ops per read of the synthetic mix; measured per batch below
+
+
+def matrix_checksum(row, col, val):
+    """Order-independent, shard-additive checksum of sparse entries (wraps modulo 2^64)."""
+    with np.errstate(over="ignore"):
+        x = (np.asarray(row).astype(np.uint64) << np.uint64(32)) ^ np.asarray(col).astype(np.uint64)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+        return int((x * (np.asarray(val).astype(np.uint64) * np.uint64(2) + np.uint64(1))).sum(dtype=np.uint64))
 
 
 def peaks():
@@ -160,14 +175,22 @@ def sum_over_ranks(dist, local, x):
 class Batch(object):
     """One GPU's workload: device-resident records + the pinned host copy used by e2e."""
 
-    def __init__(self, ctx, args, rank):
+    def __init__(self, ctx, args, rank, world):
         from xcltk_b200 import workload
         self.ctx = ctx
-        seed = 7 + 1000 * rank
-        self.fc = workload.make_basefc_workload(ctx, args.reads, args.cells, args.features, seed=seed)
-        self.baf = workload.make_baf_workload(ctx, args.baf_reads, args.baf_cells, args.snps, seed=seed + 1)
-        self.n_reads = args.reads + args.baf_reads
+        if args.scaling == "strong":
+            part = (rank, world) if world > 1 else None
+            seed = 7
+        else:
+            part, seed = None, 7 + 1000 * rank
+        self.fc = workload.make_basefc_workload(ctx, args.reads, args.cells, args.features, seed=seed, part=part)
+        self.baf = workload.make_baf_workload(ctx, args.baf_reads, args.baf_cells, args.snps, seed=seed + 1, part=part)
+        self.n_reads = self.fc.n_reads + self.baf.n_reads          # records this GPU holds (halos included)
         self.keep = None
+
+    def keep_mask(self, totals):
+        # min_count = 1, min_maf = 0 (the values xcltk baf passes, baf/pipeline.py:355)
+        return ((totals[:, 0] + totals[:, 1] + totals[:, 2] + totals[:, 3] + totals[:, 4]) >= 1).astype(np.uint8)
 
     def step_device(self, checksum=False):
         ctx, fc, bf = self.ctx, self.fc, self.baf
@@ -182,16 +205,20 @@ class Batch(object):
         w2 = time.perf_counter()
         t_p = ctx.timing()
         launches += int(t_p[2])
-        keep = ((totals[:, 0] + totals[:, 1] + totals[:, 2] + totals[:, 3] + totals[:, 4]) >= 1).astype(np.uint8)   # min_count=1, min_maf=0 (pipeline values)
-        ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, keep, True)
+        ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, self.keep_mask(totals), True)
         w3 = time.perf_counter()
         t_c = ctx.timing()
         launches += int(t_c[2])
         st.close()
-        chk = (int(seg.val.sum(dtype=np.int64)) + int(dp[2].sum()) + int(ad[2].sum())) if checksum else None
+        chk = None
+        if checksum:                 # rows numbered as in the whole matrix, so that the shards add up
+            r, c, v = seg.to_sorted()
+            chk = matrix_checksum(fc.feat_index[r], c, v)
+            for k, m in enumerate((ad, dp, oth)):
+                chk = (chk + matrix_checksum(bf.feat_index[m[0]] + (k + 1) * (1 << 24), m[1], m[2])) % (1 << 64)
         w4 = time.perf_counter()
         return dict(nnz=seg.nnz, checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w3 - w2), 1e3 * (w4 - w3)],
-                    launches=launches, t_fc=t_fc, t_pileup=t_p, t_count=t_c,
+                    launches=launches, t_fc=t_fc, t_pileup=t_p, t_count=t_c, baf_nnz=len(ad[2]) + len(dp[2]) + len(oth[2]),
                     out_bytes=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])))
 
     def make_host(self):
@@ -205,13 +232,41 @@ class Batch(object):
         d_bf = ctx.map_reads(self.h_baf)          # zero-copy: 8 B/read over PCIe, rest on demand
         totals, st = ctx.baf_pileup(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
         ctx.timing_pairs = ctx.timing()[6]            # (read, SNP) pairs: records fetched on demand
-        keep = ((totals[:, 0] + totals[:, 1] + totals[:, 2] + totals[:, 3] + totals[:, 4]) >= 1).astype(np.uint8)
-        ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, keep, True)
+        ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, self.keep_mask(totals), True)
         st.close()
         d_bf.close()
         return dict(h2d=h2d_fc + 8 * self.h_baf.n + 72 * int(self.ctx.timing_pairs),
                     d2h=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])) + totals.nbytes +
                     12 * len(fc.gid) + 8 * (3 * (len(bf.reg_ptr) - 1) + 3))  # packed entries + row_beg/row_cnt | col + val + row_ptr
+
+    def oracle_parity(self, n_threads):
+        """The CPU oracle on this very batch (outside the timed region): its matrices against the GPU's,
+        entry by entry; the oracle's wall time is the CPU baseline."""
+        from oracle import oracle
+        from xcltk_b200 import workload
+        ctx, fc, bf = self.ctx, self.fc, self.baf
+        conf = workload.Conf()
+        conf_b = workload.Conf()
+        conf_b.min_include = 0
+        letters = "ACGT"
+        ref_s, alt_s = "".join(letters[x] for x in bf.snp_ref), "".join(letters[x] for x in bf.snp_alt)
+        t = time.perf_counter()
+        o_fc = oracle.basefc(self.h_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, oracle.params(conf), n_threads)
+        t_fc = time.perf_counter() - t
+        t = time.perf_counter()
+        o_baf = oracle.baf(self.h_baf, bf.snp_gid, bf.snp_pos, ref_s, alt_s, bf.snp_ref_hap, 1 - bf.snp_ref_hap,
+                           bf.reg_ptr, bf.reg_snp, bf.cell_keys, bf.n_cells, oracle.params(conf_b), 1, 0, True, n_threads)
+        t_baf = time.perf_counter() - t
+        seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
+        g_fc = seg.to_sorted()
+        ok_fc = all(np.array_equal(a, b) for a, b in zip(g_fc, o_fc))
+        totals, st = ctx.baf_pileup(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
+        g_baf = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, self.keep_mask(totals), True)
+        st.close()
+        ok_baf = all(np.array_equal(g[k], o[k]) for g, o in zip(g_baf, o_baf) for k in range(3))
+        return dict(basefc=bool(ok_fc), baf=bool(ok_baf), nnz=int(len(o_fc[2])),
+                    baf_nnz=int(sum(len(o[2]) for o in o_baf)),
+                    against="oracle/xg_oracle.c on the same C3 + C2 batch, entry by entry"), t_fc + t_baf
 
 
 def cpu_sample(ctx, args, n_sample, n_threads):
@@ -280,20 +335,27 @@ def main():
     ap.add_argument("--cpu-sample", type=float, default=3e8, help="reads of the CPU legs (default: the whole C3 basefc batch)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = one library cut into N genomic chunks; weak = one library per GPU")
     args = ap.parse_args()
     args.reads, args.baf_reads, args.cpu_sample = int(args.reads), int(args.baf_reads), int(args.cpu_sample)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank, world, local, dist = dist_setup(args.gpus)
     from xcltk_b200 import engine
+    strong = args.scaling == "strong"
     workload_name = ("basefc C3 (%d cells, %.0fM reads, %d features: hg38 genes + nested) + baf fc C2 "
-                     "(%d cells, %.0fM reads chr1-22, %d phased het SNPs), per GPU" % (
+                     "(%d cells, %.0fM reads chr1-22, %d phased het SNPs), %s" % (
                          args.cells, args.reads / 1e6, args.features, args.baf_cells, args.baf_reads / 1e6,
-                         args.snps))
-    config = {"workload": workload_name, "reads_per_gpu": args.reads + args.baf_reads,
-              "partition": "one batch (library) per GPU, no collective",
-              "l2_policy": "inputs (%.1f GB of records per step) are larger than L2" % (
-                  (args.reads * BASEFC_BYTES_PER_READ + args.baf_reads * 8) / 1e9)}
+                         args.snps, "one library over all GPUs" if strong else "per GPU"))
+    bytes_nominal = args.reads * (28 + 4 * C_BAR_NOMINAL) + args.baf_reads * 8
+    config = {"workload": workload_name,
+              "reads_per_step": (args.reads + args.baf_reads) * (1 if strong else world),
+              "partition": ("contiguous genomic chunks of one library balanced by reads, one per GPU (features / "
+                            "regions by start position, reads with halo); disjoint rows, no collective"
+                            if strong else "one batch (library) per GPU, no collective"),
+              "l2_policy": "inputs (%.1f GB of records per step%s) are larger than L2" % (
+                  bytes_nominal / 1e9, ", 1/N of it per GPU" if strong else " and GPU")}
 
     if args.impl == "reference":
         if rank != 0:
@@ -307,7 +369,7 @@ def main():
         v = run.n_reads / (sum(ts) / len(ts))
         line = {"impl": "reference", "metric": "reads/sec counted (basefc + baf fc)", "value": v, "unit": "reads/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "u64 keys / i32 counts", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "reads/s", "cores": n_thr, "kind": "port",
                                  "sample": "basefc on %d reads of the C3 generator + baf fc on the matching share of C2 "
@@ -318,9 +380,9 @@ def main():
         return
 
     ctx = engine.get_context(local)
-    batch = Batch(ctx, args, rank)
-    for _ in range(args.warmup):
-        info = batch.step_device(checksum=True)
+    batch = Batch(ctx, args, rank, world)
+    for k in range(args.warmup):
+        info = batch.step_device(checksum=(k == args.warmup - 1))
     checksum = info["checksum"]
     sampler = ClockSampler(local)
     barrier_sync(dist, local)
@@ -331,54 +393,84 @@ def main():
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
     dt = max_over_ranks(dist, local, dt)
-    total_reads = sum_over_ranks(dist, local, float(batch.n_reads))
+    # reads counted per step: the library once (strong: halo reads are not counted twice), or one library per GPU
+    total_reads = float(args.reads + args.baf_reads) * (1 if strong else world)
+    held_reads = sum_over_ranks(dist, local, float(batch.n_reads))
     value = total_reads * args.steps / dt
     info = infos[-1]
+    nnz_all = sum_over_ranks(dist, local, float(info["nnz"]))
 
-    # roofline of the dominant kernel (k_basefc_count): algorithmic bytes / its summed launch time
+    # ---- multi-GPU parity: the shards' rows add up to the unsharded matrices (rank 0 counts the whole library)
+    parity = None
+    if strong and world > 1:
+        import torch
+        t = torch.tensor([checksum - (1 << 64) if checksum >= (1 << 63) else checksum], dtype=torch.int64,
+                         device="cuda:%d" % local)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)          # int64 addition wraps like the checksum does
+        sharded = int(t.item()) % (1 << 64)
+        if rank == 0:
+            whole = Batch(ctx, args, 0, 1)
+            ref = whole.step_device(checksum=True)
+            parity = {"sharded_vs_unsharded": bool(ref["checksum"] == sharded), "checksum": sharded,
+                      "unsharded_checksum": ref["checksum"], "unsharded_nnz": int(ref["nnz"]), "sharded_nnz": int(nnz_all),
+                      "against": "the same library counted on one GPU (rank 0), all four matrices"}
+            whole.fc.dreads.close()
+            whole.baf.dreads.close()
+            del whole
+        barrier_sync(dist, local)
+
+    # ---- roofline of the dominant kernel (k_basefc_count): algorithmic bytes / its summed launch time
     peak, peak_src = peaks()
     t_cnt_ms = float(np.mean([i["t_fc"][1] for i in infos]))
     n_epochs = int(info["t_fc"][5])
-    alg_bytes = args.reads * BASEFC_BYTES_PER_READ + 12.0 * info["nnz"]
+    # c-bar of THIS batch: CIGAR words stored for the non-simple reads + one op for every simple read
+    inf_fc = batch.fc.dreads.info()
+    c_bar, c_bar_src = C_BAR_NOMINAL, "nominal mix (SURVEY.md 8d)"
+    if not (args.no_e2e and args.no_cpu):
+        try:
+            batch.make_host()
+            n_simple = int(np.count_nonzero((batch.h_fc.fmq >> np.uint32(24)) == 0))
+            c_bar = (inf_fc["n_cigar"] + n_simple) / float(max(1, inf_fc["n_reads"]))
+            c_bar_src = "this batch: (stored CIGAR words + simple reads) / reads"
+        except Exception:
+            pass
+    bytes_per_read = 28 + 4 * c_bar
+    alg_bytes = batch.fc.n_reads * bytes_per_read + 12.0 * info["nnz"]
     achieved = alg_bytes / (t_cnt_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
         try:
             with open(tj) as fp:
-                traffic = json.load(fp).get("k_basefc_count_bytes_per_launch")
+                tr = json.load(fp)
+            # measured DRAM bytes per read of the profiled launch, scaled to this run's reads per launch
+            traffic = tr["k_basefc_count"]["dram_bytes"] / tr["k_basefc_count"]["reads"] * batch.fc.n_reads / max(1, n_epochs)
+            traffic_src = {k: tr.get(k) for k in ("commit", "report", "when")}
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_basefc_count", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
                 "launches_per_step": n_epochs, "avg_launch_ms": t_cnt_ms / max(1, n_epochs),
                 "algorithmic_bytes_per_launch": alg_bytes / max(1, n_epochs),
-                "note": "launch durations from CUDA events on the launching streams; epochs overlap, so the "
-                        "sum over-counts (conservative)"}
-    # the same kernel with the epochs' streams serialised (extra calls outside the timed region): its launch
-    # durations without a neighbour on the SMs
-    prev_overlap = os.environ.get("XG_OVERLAP")
-    try:
-        os.environ["XG_OVERLAP"] = "0"
-        ts = []
-        for _ in range(2):
-            batch.ctx.basefc(batch.fc.dreads, batch.fc.gid, batch.fc.beg, batch.fc.end, batch.fc.cell_keys,
-                             batch.fc.n_cells, batch.fc.params, segments="narrow")
-            ts.append(batch.ctx.timing()[1])
-        a2 = alg_bytes / (ts[-1] * 1e-3) / 1e9
-        roofline["serialised"] = {"achieved": a2, "frac": a2 / peak, "avg_launch_ms": ts[-1] / max(1, n_epochs)}
-    except Exception as ex:
-        roofline["serialised"] = {"error": str(ex)[:120]}
-    finally:
-        if prev_overlap is None:
-            os.environ.pop("XG_OVERLAP", None)
-        else:
-            os.environ["XG_OVERLAP"] = prev_overlap
+                "c_bar": c_bar, "c_bar_source": c_bar_src, "bytes_per_read": bytes_per_read,
+                "reads_this_gpu": batch.fc.n_reads,
+                "note": "launch durations from CUDA events on the launching stream; the counting launches of the "
+                        "epochs follow one another on one stream (rank 0's GPU)"}
+    # ---- and of the baf pileup's scan kernel: 8 B of every read, 71.7 B of the reads that cover a SNP, the
+    # SNP table, 12 B per result entry.  (read, SNP) pairs stand in for the covering reads.
+    t_scan_ms = float(np.mean([i["t_pileup"][1] for i in infos]))
+    n_pairs = float(info["t_pileup"][6])
+    baf_alg = 8.0 * batch.baf.n_reads + (20 + 4 * c_bar + 46) * n_pairs + 8.0 * len(batch.baf.snp_pos) + 12.0 * info["baf_nnz"]
+    roofline_baf = {"bound": "hbm", "kernel": "k_baf_scan", "achieved": baf_alg / (max(t_scan_ms, 1e-6) * 1e-3) / 1e9,
+                    "peak": peak, "unit": "GB/s", "frac": baf_alg / (max(t_scan_ms, 1e-6) * 1e-3) / 1e9 / peak,
+                    "avg_launch_ms": t_scan_ms, "algorithmic_bytes_per_launch": baf_alg, "read_snp_pairs": n_pairs,
+                    "traffic": None}
 
     e2e = None
     if not args.no_e2e:
         try:
-            batch.make_host()
+            if not hasattr(batch, "h_fc"):
+                batch.make_host()
             for _ in range(2):
                 batch.step_e2e()
             barrier_sync(dist, local)
@@ -386,21 +478,27 @@ def main():
             for _ in range(args.steps):
                 io = batch.step_e2e()
             barrier_sync(dist, local)
-            de = max_over_ranks(dist, local, time.perf_counter() - t0)
+            de_local = time.perf_counter() - t0
+            de = max_over_ranks(dist, local, de_local)
             e2e = {"value": total_reads * args.steps / de, "unit": "reads/s", "h2d_bytes_per_step": io["h2d"],
-                   "d2h_bytes_per_step": io["d2h"], "ms_per_step": 1e3 * de / args.steps}
+                   "d2h_bytes_per_step": io["d2h"], "ms_per_step": 1e3 * de / args.steps,
+                   "rank0_h2d_gb_s": io["h2d"] * args.steps / de_local / 1e9,
+                   "rank0_d2h_gb_s": io["d2h"] * args.steps / de_local / 1e9,
+                   "bytes": "rank 0's; every rank moves its own chunk"}
         except Exception as ex:            # e.g. not enough pinned host memory on the box
             e2e = {"value": None, "unit": "reads/s", "error": str(ex)[:200]}
 
+    # ---- N = 1: parity against the CPU oracle on this batch; its wall time is the CPU baseline
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:      # the CPU and decode legs: rank 0 at N=1 only
-        from oracle import oracle  # noqa: F401
-        run, host = cpu_sample(ctx, args, args.cpu_sample, os.cpu_count() or 1)
-        run()
-        t = run()
-        cpu = {"value": run.n_reads / t, "unit": "reads/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": "the step on the CPU with the C oracle: basefc on %d reads of the C3 generator + baf fc on the "
-                         "matching share of C2 (%d reads), %.1f s" % (args.cpu_sample, run.n_reads, t)}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        if not hasattr(batch, "h_fc"):
+            batch.make_host()
+        n_thr = os.cpu_count() or 1
+        parity, t_cpu = batch.oracle_parity(n_thr)
+        cpu = {"value": (args.reads + args.baf_reads) / t_cpu, "unit": "reads/s", "cores": n_thr, "kind": "port",
+               "sample": "the whole step on the CPU with the C oracle (oracle/xg_oracle.c, OpenMP over features / SNPs): "
+                         "basefc on the %d reads of the C3 batch + baf fc on the %d reads of the C2 batch the GPU "
+                         "counted, %.1f s" % (args.reads, args.baf_reads, t_cpu)}
 
     decode = None
     device_decode = None
@@ -473,25 +571,28 @@ def main():
     if rank == 0:
         line = {"metric": "reads/sec counted (basefc + baf fc)", "value": value, "unit": "reads/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "u64 keys / i32 counts", "data": "synthetic", "config": config,
                 "e2e": e2e, "gpu_launches": int(sum(i["launches"] for i in infos)), "clocks": clocks,
-                "roofline": roofline, "cpu_baseline": cpu, "host_decode": decode, "device_decode": device_decode, "file_to_matrix": file_to_matrix,
+                "parity": parity, "roofline": roofline, "roofline_baf": roofline_baf, "cpu_baseline": cpu, "host_decode": decode, "device_decode": device_decode, "file_to_matrix": file_to_matrix,
                 "detail": {"basefc_device_ms": float(np.mean([i["t_fc"][0] for i in infos])),
                            "basefc_epoch_span_ms": float(np.mean([i["t_fc"][3] for i in infos])),
                            "basefc_count_kernel_ms": t_cnt_ms,
                            "baf_pileup_ms": float(np.mean([i["t_pileup"][0] for i in infos])),
                            "baf_scan_kernel_ms": float(np.mean([i["t_pileup"][1] for i in infos])),
                            "baf_count_ms": float(np.mean([i["t_count"][0] for i in infos])),
-                           "basefc_nnz": info["nnz"], "checksum": checksum,
+                           "basefc_nnz": int(nnz_all), "checksum": checksum, "reads_held_by_all_gpus": held_reads,
                            "wall_ms_basefc_pileup_count_checksum": [float(x) for x in np.mean(
                                [i["wall_ms"] for i in infos], axis=0)],
                            "basefc_host_ms_index_windows_plan_upload_call": [float(x) for x in info["t_fc"][8:13]],
-                           "basefc_reads_per_s_kernels_only": args.reads / (
+                           "basefc_reads_per_s_kernels_only": batch.fc.n_reads / (
                                float(np.mean([i["t_fc"][3] for i in infos])) * 1e-3)}}
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not all(v for v in parity.values() if isinstance(v, bool)):
+        sys.stderr.write("bench.py: PARITY MISMATCH %r\n" % (parity,))
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -305,8 +305,15 @@ typedef struct {
     const uint8_t *snp_ref;   /* base codes 0..3 */
     const uint8_t *snp_alt;
     const uint8_t *snp_ref_hap;
+    /* total_reads > 0: generate only reads [first_read, first_read + n_reads) of a library of total_reads
+     * (every field of read i depends on i, seed and the library size only), so that several GPUs can each
+     * hold one genomic chunk of ONE library                                                   */
+    int64_t first_read;
+    int64_t total_reads;
 } xg_synth_params;
 int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *p, xg_dreads **out, uint64_t *barcode_keys);
+/* Index of the first read at or after (gid, pos) in the library of p->n_reads reads (host only). */
+int64_t xg_synth_read_index(const xg_synth_params *p, int32_t gid, int32_t pos);
 
 /* Timing of the last xg_basefc / xg_baf_* call (CUDA events on the library's streams, ms):
  * [0] device span of the call  [1] sum of the dominant counting kernel's launches

@@ -382,3 +382,59 @@ def test_basefc_narrow_entries_with_large_counts(gpu_ctx):
     seg = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, np.arange(1, 70001, dtype=np.uint64) << np.uint64(40), 70000, p2,
                          segments="narrow")
     assert seg.cv16 is None                                # too many columns for 16 bits
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_genomic_chunks_of_one_library_give_the_unsharded_rows(gpu_ctx, world):
+    """bench.py --scaling strong on one GPU: every chunk (its features + the reads that can overlap them, generated
+    as a slice of the same library) yields exactly its rows of the unsharded basefc and baf matrices."""
+    from xcltk_b200 import workload
+    chroms = {"19", "20", "21", "22"}
+    conf = Conf()
+    full = workload.make_basefc_workload(gpu_ctx, 1200000, 400, 9000, seed=31, chroms=chroms)
+    f_row, f_col, f_val, _ = gpu_ctx.basefc(full.dreads, full.gid, full.beg, full.end, full.cell_keys, 400, gpu_params(conf))
+    key_full = {}
+    for r, c, v in zip(f_row.tolist(), f_col.tolist(), f_val.tolist()):
+        key_full.setdefault(r, []).append((c, v))
+    seen_rows, held = set(), 0
+    for rank in range(world):
+        w = workload.make_basefc_workload(gpu_ctx, 1200000, 400, 9000, seed=31, chroms=chroms, part=(rank, world))
+        assert np.array_equal(w.cell_keys, full.cell_keys)
+        held += w.n_reads
+        row, col, val, _ = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 400, gpu_params(conf))
+        got = {}
+        for r, c, v in zip(row.tolist(), col.tolist(), val.tolist()):
+            got.setdefault(int(w.feat_index[r]), []).append((c, v))
+        for k, g in enumerate(w.feat_index.tolist()):
+            assert g not in seen_rows
+            seen_rows.add(g)
+            assert got.get(g, []) == key_full.get(g, []), (rank, k, g)
+        w.dreads.close()
+    assert seen_rows == set(range(len(full.gid)))
+    assert held < 1200000 * 1.2                         # halos are small next to the chunks
+    full.dreads.close()
+
+    # baf: regions follow their chunk, the SNP table is shared
+    fb = workload.make_baf_workload(gpu_ctx, 600000, 300, 4000, seed=33, chroms=chroms)
+    totals, st = gpu_ctx.baf_pileup(fb.dreads, fb.snp_gid, fb.snp_pos, fb.cell_keys, 300, fb.params)
+    keep = (totals.sum(axis=1) >= 1).astype(np.uint8)
+    full_m = gpu_ctx.baf_count(st, fb.reg_ptr, fb.reg_snp, fb.hap_of, keep, True)
+    st.close()
+    full_rows = [{} for _ in range(3)]
+    for k in range(3):
+        for r, c, v in zip(full_m[k][0].tolist(), full_m[k][1].tolist(), full_m[k][2].tolist()):
+            full_rows[k].setdefault(r, []).append((c, v))
+    for rank in range(world):
+        w = workload.make_baf_workload(gpu_ctx, 600000, 300, 4000, seed=33, chroms=chroms, part=(rank, world))
+        totals, st = gpu_ctx.baf_pileup(w.dreads, w.snp_gid, w.snp_pos, w.cell_keys, 300, w.params)
+        keep = (totals.sum(axis=1) >= 1).astype(np.uint8)
+        m = gpu_ctx.baf_count(st, w.reg_ptr, w.reg_snp, w.hap_of, keep, True)
+        st.close()
+        for k in range(3):
+            got = {}
+            for r, c, v in zip(m[k][0].tolist(), m[k][1].tolist(), m[k][2].tolist()):
+                got.setdefault(int(w.feat_index[r]), []).append((c, v))
+            for g in w.feat_index.tolist():
+                assert got.get(g, []) == full_rows[k].get(g, []), (rank, k, g)
+        w.dreads.close()
+    fb.dreads.close()

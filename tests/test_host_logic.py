@@ -245,3 +245,33 @@ def test_write_mtx_rows16_narrow_entries_and_side_list(tmp_path):
     lib.write_mtx_rows(str(tmp_path / "b.mtx"), narrow, out_row, int(emitted.sum()), 3)
     a, b = open(str(tmp_path / "a.mtx"), "rb").read(), open(str(tmp_path / "b.mtx"), "rb").read()
     assert a == b and b"\t65535\n" in a
+
+
+def test_genomic_chunks_partition_the_library():
+    """bench.py --scaling strong: the chunks' features are a disjoint cover of the feature list, and every chunk's
+    read range reaches from HALO_BP before its first feature to the end of its last one (reads are sorted)."""
+    import numpy as np
+    from xcltk_b200 import lib, workload
+    feats = workload.extend_features(workload.load_genes({"20", "21", "22"}), 3000, seed=5)
+    gid_of = {"20": 0, "21": 1, "22": 2}
+    gid, beg, end = workload.feature_arrays(feats + [("7", 10, 20, "other_contig"), ("21", 0, 50, "start0")], gid_of)
+    sg, sb, se = workload.merged_spans(feats, gid_of)
+    n_total, seed = 5000000, 11
+    for world in (1, 2, 3, 8):
+        seen = np.zeros(len(gid), dtype=np.int32)
+        prev_i0 = -1
+        for rank in range(world):
+            idx, i0, n = workload.genomic_chunk(None, n_total, seed, sg, sb, se, gid, beg, end, (rank, world))
+            seen[idx] += 1
+            ok = idx[(gid[idx] >= 0) & (end[idx] > beg[idx])]
+            if len(ok) == 0:
+                continue
+            assert i0 >= prev_i0 and 0 <= i0 and i0 + n <= n_total
+            prev_i0 = i0
+            first = ok[np.lexsort((beg[ok], gid[ok]))[0]]
+            lo = lib.synth_read_index(n_total, sg, sb, se, int(gid[first]), max(0, int(beg[first]) - workload.HALO_BP), seed)
+            assert i0 == lo
+            for f in ok[:50]:        # the reads at a feature's end still belong to the chunk
+                hi = lib.synth_read_index(n_total, sg, sb, se, int(gid[f]), int(end[f]), seed)
+                assert i0 + n >= hi
+        assert np.all(seen == 1)

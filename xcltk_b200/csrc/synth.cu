@@ -18,7 +18,8 @@
 namespace {
 
 struct SynthDev {
-    int64_t n_reads;
+    int64_t n_reads;       // reads of this batch: reads [i_base, i_base + n_reads) of a library of n_total
+    int64_t i_base, n_total;
     uint64_t G;            // total span length
     uint64_t seed;
     int32_t n_cells, n_cells_all, read_len, want_seq, seq_words;
@@ -119,12 +120,13 @@ __host__ __device__ inline CigarPlan plan_cigar(uint64_t seed, uint64_t i, int32
 
 #define SYNTH_CHUNK 1024
 
-__global__ void __launch_bounds__(256) k_synth_count(uint64_t seed, int64_t n, int32_t L, int32_t *chunk_words) {
+__global__ void __launch_bounds__(256) k_synth_count(uint64_t seed, int64_t n, int64_t i_base, int32_t L,
+                                                     int32_t *chunk_words) {
     int64_t c = blockIdx.x;
     int cnt = 0;
     for (int k = threadIdx.x; k < SYNTH_CHUNK; k += blockDim.x) {
         int64_t i = c * SYNTH_CHUNK + k;
-        if (i < n) cnt += plan_cigar(seed, (uint64_t)i, L).n;
+        if (i < n) cnt += plan_cigar(seed, (uint64_t)(i_base + i), L).n;
     }
     __shared__ int s[256];
     s[threadIdx.x] = cnt;
@@ -143,7 +145,8 @@ __global__ void __launch_bounds__(1024) k_synth_fill(const __grid_constant__ Syn
     CigarPlan cp;
     cp.n = 0;
     cp.rlen = P.read_len;
-    if (live) cp = plan_cigar(P.seed, (uint64_t)i, P.read_len);
+    const uint64_t gi = (uint64_t)(P.i_base + i);      // the read's index in the whole library
+    if (live) cp = plan_cigar(P.seed, gi, P.read_len);
     // in-chunk exclusive scan of cigar words (Hillis-Steele; 1024 threads)
     scan[threadIdx.x] = live ? cp.n : 0;
     __syncthreads();
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(1024) k_synth_fill(const __grid_constant__ Syn
     const uint32_t coff = (uint32_t)(P.chunk_cig_base[blockIdx.x] + scan[threadIdx.x] - cp.n);
 
     // position
-    uint64_t u = span_coord(P.seed, (uint64_t)i, P.G, (uint64_t)P.n_reads);
+    uint64_t u = span_coord(P.seed, gi, P.G, (uint64_t)P.n_total);
     int lo = 0, hi = P.n_spans;             // last span with pre <= u
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(1024) k_synth_fill(const __grid_constant__ Syn
     atomicMax(&P.maxes[1], end - pos);
 
     // flags / mapq
-    uint64_t h = hsh(P.seed, (uint64_t)i, 3);
+    uint64_t h = hsh(P.seed, gi, 3);
     uint32_t flag = (h & 1) ? 16u : 0u;
     uint32_t r = (uint32_t)((h >> 8) % 100);
     if (r < 4) flag |= 256u;
@@ -189,13 +192,13 @@ __global__ void __launch_bounds__(1024) k_synth_fill(const __grid_constant__ Syn
     P.fmq[i] = flag | (mq << 16) | ((uint32_t)cp.n << 24);
 
     // molecule -> cell, UMI
-    const uint64_t grp = (uint64_t)i / 96, w = (uint64_t)i % 96;
+    const uint64_t grp = gi / 96, w = gi % 96;
     uint64_t mol = grp * 32 + (w & 31);
-    if (hsh(P.seed, (uint64_t)i, 4) % 10 == 0) mol = (uint64_t)P.n_reads + (uint64_t)i;   // singleton
+    if (hsh(P.seed, gi, 4) % 10 == 0) mol = (uint64_t)P.n_total + gi;   // singleton
     const uint64_t hm = hsh(P.seed, mol, 5);
     const uint32_t cell = (uint32_t)(hm % (uint64_t)P.n_cells_all);
     uint64_t ck = cell_key(P.seed, cell), uk = umi_key(hm >> 20);
-    const uint32_t tg = (uint32_t)(hsh(P.seed, (uint64_t)i, 6) % 1000);
+    const uint32_t tg = (uint32_t)(hsh(P.seed, gi, 6) % 1000);
     if (tg < 10) ck = XG_KEY_NONE;
     else if (tg < 20) uk = XG_KEY_NONE;
     else if (tg < 25) uk = XG_KEY_EMPTY;
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(1024) k_synth_fill(const __grid_constant__ Syn
         P.seq_off[i] = so;
         uint32_t *sq = P.seq + so;
         for (int wd = 0; wd < P.seq_words; wd++) {
-            uint64_t hb = hsh(P.seed, (uint64_t)i * 16 + (uint64_t)wd, 7);
+            uint64_t hb = hsh(P.seed, gi * 16 + (uint64_t)wd, 7);
             uint32_t word = 0;
             for (int b = 0; b < 8; b++) word |= (1u << ((hb >> (2 * b)) & 3u)) << (4 * b);
             sq[wd] = word;
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(1024) k_synth_fill(const __grid_constant__ Syn
                     }
                 }
                 if (q < 0) continue;
-                uint64_t hs = hsh(P.seed, (uint64_t)i * 64 + (uint64_t)(s - a), 9);
+                uint64_t hs = hsh(P.seed, gi * 64 + (uint64_t)(s - a), 9);
                 uint32_t rr = (uint32_t)(hs % 100);
                 uint32_t code;
                 if (rr < 2) {
@@ -285,6 +288,8 @@ extern "C" int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *sp, xg_dreads 
         return ctx->fail(XG_E_ARG, "xg_synth_reads: bad parameters");
     XG_CUDA(cudaSetDevice(ctx->device));
     const int64_t N = sp->n_reads;
+    const int64_t NT = sp->total_reads > 0 ? sp->total_reads : N, I0 = sp->total_reads > 0 ? sp->first_read : 0;
+    if (I0 < 0 || I0 + N > NT) return ctx->fail(XG_E_ARG, "xg_synth_reads: slice outside the library");
     // span prefix + per-gid boundaries
     std::vector<uint64_t> pre((size_t)sp->n_spans + 1, 0);
     int32_t n_gid = 0;
@@ -297,19 +302,19 @@ extern "C" int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *sp, xg_dreads 
         n_gid = std::max(n_gid, sp->span_gid[s] + 1);
     }
     const uint64_t G = pre.back();
-    if ((double)G * (double)N > 9.0e18) return ctx->fail(XG_E_LIMIT, "n_reads * span length overflows");
+    if ((double)G * (double)NT > 9.0e18) return ctx->fail(XG_E_LIMIT, "n_reads * span length overflows");
     const int32_t seq_words = sp->want_seq ? ((sp->read_len + 1) / 2 + 3) / 4 : 0;
     if ((double)N * seq_words >= 4294967296.0) return ctx->fail(XG_E_LIMIT, "sequence stream exceeds 2^32 words");
 
     // runs: reads of each gid are contiguous; first read with coord >= boundary (pure function)
     xg_dreads *d = new xg_dreads();
-    auto first_at_least = [&](uint64_t bound) -> int64_t {
-        int64_t lo = 0, hi = N;
+    auto first_at_least = [&](uint64_t bound) -> int64_t {       // in this batch's own numbering
+        int64_t lo = 0, hi = NT;
         while (lo < hi) {
             int64_t mid = (lo + hi) / 2;
-            if (span_coord(sp->seed, (uint64_t)mid, G, (uint64_t)N) >= bound) hi = mid; else lo = mid + 1;
+            if (span_coord(sp->seed, (uint64_t)mid, G, (uint64_t)NT) >= bound) hi = mid; else lo = mid + 1;
         }
-        return lo;
+        return std::min(std::max(lo, I0), I0 + N) - I0;
     };
     {
         int32_t s = 0;
@@ -408,7 +413,7 @@ extern "C" int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *sp, xg_dreads 
     cudaMemcpyAsync(d->tiles, d->h_tiles.data(), d->h_tiles.size() * sizeof(xg_tile), cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(maxes, 0, 16, st);
 
-    k_synth_count<<<(unsigned)n_chunks, 256, 0, st>>>(sp->seed, N, sp->read_len, chunk_words);
+    k_synth_count<<<(unsigned)n_chunks, 256, 0, st>>>(sp->seed, N, I0, sp->read_len, chunk_words);
     k_exclusive_scan<<<1, 1024, 0, st>>>(chunk_words, chunk_base, (int32_t)n_chunks);
     int64_t n_cig = 0;
     cudaMemcpyAsync(&n_cig, chunk_base + n_chunks, 8, cudaMemcpyDeviceToHost, st);
@@ -426,6 +431,8 @@ extern "C" int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *sp, xg_dreads 
     SynthDev P;
     memset(&P, 0, sizeof(P));
     P.n_reads = N;
+    P.i_base = I0;
+    P.n_total = NT;
     P.G = G;
     P.seed = sp->seed;
     P.n_cells = sp->n_cells;
@@ -485,4 +492,28 @@ extern "C" int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *sp, xg_dreads 
     }
     *out = d;
     return XG_OK;
+}
+
+// First read of the library p describes (p->n_reads reads in all; first_read / total_reads ignored) that lies at
+// or after position `pos` of contig `gid` -- how a caller cuts the library into genomic chunks.
+extern "C" int64_t xg_synth_read_index(const xg_synth_params *sp, int32_t gid, int32_t pos) {
+    if (!sp || sp->n_reads <= 0 || sp->n_spans <= 0) return -1;
+    std::vector<uint64_t> pre((size_t)sp->n_spans + 1, 0);
+    for (int32_t s = 0; s < sp->n_spans; s++)
+        pre[(size_t)s + 1] = pre[(size_t)s] + (uint64_t)(sp->span_end[s] - sp->span_beg[s]);
+    // coordinate of (gid, pos) in the concatenated span space: a position in a gap counts as the next span's start
+    uint64_t bound = pre.back();
+    for (int32_t s = 0; s < sp->n_spans; s++) {
+        if (sp->span_gid[s] < gid || (sp->span_gid[s] == gid && sp->span_end[s] <= pos)) continue;
+        bound = pre[(size_t)s];
+        if (sp->span_gid[s] == gid && pos > sp->span_beg[s]) bound += (uint64_t)(pos - sp->span_beg[s]);
+        break;
+    }
+    const uint64_t G = pre.back(), N = (uint64_t)sp->n_reads;
+    int64_t lo = 0, hi = sp->n_reads;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) / 2;
+        if (span_coord(sp->seed, (uint64_t)mid, G, N) >= bound) hi = mid; else lo = mid + 1;
+    }
+    return lo;
 }

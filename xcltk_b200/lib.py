@@ -81,7 +81,8 @@ class SynthParams(C.Structure):
                 ("want_seq", C.c_int32), ("seed", C.c_uint64),
                 ("n_spans", C.c_int32), ("span_gid", c_i32p), ("span_beg", c_i32p), ("span_end", c_i32p),
                 ("n_snps", C.c_int32), ("snp_gid", c_i32p), ("snp_pos", c_i32p),
-                ("snp_ref", c_u8p), ("snp_alt", c_u8p), ("snp_ref_hap", c_u8p)]
+                ("snp_ref", c_u8p), ("snp_alt", c_u8p), ("snp_ref_hap", c_u8p),
+                ("first_read", C.c_int64), ("total_reads", C.c_int64)]
 
 
 # every symbol include/xcltk_b200.h declares: name -> (restype, argtypes)
@@ -134,6 +135,7 @@ SYMBOLS = {
                                C.POINTER(C.POINTER(Coo))]),
     "xg_baf_state_free": (None, [_P, _P]),
     "xg_synth_reads": (C.c_int, [_P, C.POINTER(SynthParams), C.POINTER(_P), c_u64p]),
+    "xg_synth_read_index": (C.c_int64, [C.POINTER(SynthParams), C.c_int32, C.c_int32]),
     "xg_last_timing": (None, [_P, C.POINTER(C.c_double)]),
     "xg_version": (C.c_char_p, []),
 }
@@ -593,13 +595,15 @@ class Context(object):
         return tuple(coo_to_numpy(self.lib, m, ctx_obj=self) for m in (ad, dp, oth))
 
     def synth_reads(self, n_reads, n_cells, span_gid, span_beg, span_end, seed=7, read_len=91,
-                    want_seq=False, snps=None):
+                    want_seq=False, snps=None, first_read=0, total_reads=0):
+        """total_reads > 0: only reads [first_read, first_read + n_reads) of a library of total_reads."""
         sg = np.ascontiguousarray(span_gid, dtype=np.int32)
         sb = np.ascontiguousarray(span_beg, dtype=np.int32)
         se = np.ascontiguousarray(span_end, dtype=np.int32)
         p = SynthParams()
         p.n_reads, p.n_cells, p.read_len, p.want_seq, p.seed = n_reads, n_cells, read_len, int(want_seq), seed
         p.n_spans, p.span_gid, p.span_beg, p.span_end = len(sg), as_ptr(sg, c_i32p), as_ptr(sb, c_i32p), as_ptr(se, c_i32p)
+        p.first_read, p.total_reads = int(first_read), int(total_reads)
         keep = [sg, sb, se]
         if snps is not None:
             arrs = [np.ascontiguousarray(snps[0], dtype=np.int32), np.ascontiguousarray(snps[1], dtype=np.int32)] + \
@@ -618,11 +622,25 @@ class Context(object):
             self.lib.xg_destroy(self.h)
             self.h = None
 
+    def synth_read_index(self, n_total, span_gid, span_beg, span_end, gid, pos, seed=7):
+        return synth_read_index(n_total, span_gid, span_beg, span_end, gid, pos, seed)
+
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+
+def synth_read_index(n_total, span_gid, span_beg, span_end, gid, pos, seed=7):
+    """First read of the synthetic library (xg_synth_reads) at or after (gid, pos).  Host only."""
+    sg = np.ascontiguousarray(span_gid, dtype=np.int32)
+    sb = np.ascontiguousarray(span_beg, dtype=np.int32)
+    se = np.ascontiguousarray(span_end, dtype=np.int32)
+    p = SynthParams()
+    p.n_reads, p.seed = int(n_total), seed
+    p.n_spans, p.span_gid, p.span_beg, p.span_end = len(sg), as_ptr(sg, c_i32p), as_ptr(sb, c_i32p), as_ptr(se, c_i32p)
+    return int(load().xg_synth_read_index(C.byref(p), int(gid), int(pos)))
 
 
 class DeviceReads(object):

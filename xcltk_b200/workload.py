@@ -107,8 +107,47 @@ def feature_arrays(feats, gid_of):
     return gid, beg, end
 
 
-def make_basefc_workload(ctx, n_reads, n_cells, n_features=33472, seed=7, chroms=None, bins_kb=None):
-    """Config 1 (chr22 only: chroms={'22'}), config 3 (n_features ~ 60k) or config 5 (bins)."""
+HALO_BP = 6000        # longest reference span of a synthetic read (91 bases + a 5 000 bp intron), rounded up
+
+
+def genomic_chunk(ctx, n_total, seed, sg, sb, se, gid, beg, end, part):
+    """One of `world` contiguous genomic chunks of a synthetic library, balanced by reads (the north star's
+    multi-GPU split; the reference cuts its feature list into contiguous chunks the same way,
+    rdr/fc/main.py:191-212).  Returns (feature indices of the chunk, first read, number of reads): the
+    features whose start lies in the chunk, and every read that can overlap one of them (halo included).
+    Reads are spread uniformly over the concatenated spans, so equal span length = equal reads."""
+    rank, world = part
+    lens = (se - sb).astype(np.int64)
+    pre = np.concatenate([[0], np.cumsum(lens)])
+    total = int(pre[-1])
+    # coordinate of every feature start in the concatenated span space (starts lie inside spans)
+    key_span = sg.astype(np.int64) << 32 | sb.astype(np.int64)
+    key_feat = gid.astype(np.int64) << 32 | beg.astype(np.int64)
+    si = np.clip(np.searchsorted(key_span, key_feat, side="right") - 1, 0, len(sg) - 1)
+    u = pre[si] + np.clip(beg.astype(np.int64) - sb[si], 0, lens[si])
+    valid = (gid >= 0) & (end > beg)
+    lo_u, hi_u = total * rank // world, total * (rank + 1) // world
+    mine = np.nonzero(valid & (u >= lo_u) & (u < hi_u))[0]
+    if rank == world - 1:          # features that can never be fetched travel with the last chunk (empty rows)
+        mine = np.concatenate([mine, np.nonzero(~valid)[0]])
+        mine.sort()
+    ok = mine[valid[mine]]
+    if len(ok) == 0:
+        return mine, 0, 0
+    order = np.lexsort((beg[ok], gid[ok]))
+    first = ok[order[0]]
+    last_key = np.max(gid[ok].astype(np.int64) << 32 | end[ok].astype(np.int64))
+    g0, p0 = int(gid[first]), max(0, int(beg[first]) - HALO_BP)
+    g1, p1 = int(last_key >> 32), int(last_key & 0xFFFFFFFF)
+    i0 = lib.synth_read_index(n_total, sg, sb, se, g0, p0, seed=seed)
+    i1 = lib.synth_read_index(n_total, sg, sb, se, g1, p1, seed=seed)
+    return mine, i0, max(0, i1 - i0)
+
+
+def make_basefc_workload(ctx, n_reads, n_cells, n_features=33472, seed=7, chroms=None, bins_kb=None, part=None):
+    """Config 1 (chr22 only: chroms={'22'}), config 3 (n_features ~ 60k) or config 5 (bins).
+    part = (rank, world): only that genomic chunk of the library -- its features (w.feat_index gives their
+    rows in the whole matrix) and the reads that can overlap them."""
     w = Workload()
     if bins_kb:
         feats = [f for f in bin_features(bins_kb) if chroms is None or f[0] in chroms]
@@ -121,14 +160,27 @@ def make_basefc_workload(ctx, n_reads, n_cells, n_features=33472, seed=7, chroms
     w.feats, w.gid_of = feats, gid_of
     w.gid, w.beg, w.end = feature_arrays(feats, gid_of)
     sg, sb, se = merged_spans(feats, gid_of)
-    w.dreads, w.cell_keys = ctx.synth_reads(n_reads, n_cells, sg, sb, se, seed=seed, want_seq=False)
-    w.n_reads, w.n_cells = n_reads, n_cells
+    w.n_rows_total = len(w.gid)
+    if part is None:
+        w.feat_index = np.arange(len(w.gid))
+        w.dreads, w.cell_keys = ctx.synth_reads(n_reads, n_cells, sg, sb, se, seed=seed, want_seq=False)
+        w.n_reads = n_reads
+    else:
+        idx, i0, n_loc = genomic_chunk(ctx, n_reads, seed, sg, sb, se, w.gid, w.beg, w.end, part)
+        w.feat_index, w.first_read = idx, i0
+        w.gid, w.beg, w.end = w.gid[idx], w.beg[idx], w.end[idx]
+        w.dreads, w.cell_keys = ctx.synth_reads(max(1, n_loc), n_cells, sg, sb, se, seed=seed, want_seq=False,
+                                                first_read=i0, total_reads=n_reads)
+        w.n_reads = n_loc
+    w.n_cells = n_cells
     w.params = engine.make_params(Conf(), 91, with_include=True)
     return w
 
 
-def make_baf_workload(ctx, n_reads, n_cells, n_snps=200000, seed=7, chroms=None):
-    """Config 2: chr1-22 reads, 5k cells, 200k phased het SNPs inside gene spans."""
+def make_baf_workload(ctx, n_reads, n_cells, n_snps=200000, seed=7, chroms=None, part=None):
+    """Config 2: chr1-22 reads, 5k cells, 200k phased het SNPs inside gene spans.
+    part = (rank, world): the regions of that genomic chunk (w.feat_index: their rows in the whole matrices),
+    the whole SNP table, and the reads that can overlap the chunk's regions."""
     w = Workload()
     auto = [c for c in HG38_CHROMS[:22] if chroms is None or c in chroms]
     genes = load_genes(set(auto))
@@ -148,10 +200,20 @@ def make_baf_workload(ctx, n_reads, n_cells, n_snps=200000, seed=7, chroms=None)
     w.snp_ref = rng.randint(0, 4, size=len(u)).astype(np.uint8)
     w.snp_alt = ((w.snp_ref + rng.randint(1, 4, size=len(u))) % 4).astype(np.uint8)
     w.snp_ref_hap = rng.randint(0, 2, size=len(u)).astype(np.uint8)
-    w.dreads, w.cell_keys = ctx.synth_reads(
-        n_reads, n_cells, sg, sb, se, seed=seed, want_seq=True,
-        snps=(w.snp_gid, w.snp_pos, w.snp_ref, w.snp_alt, w.snp_ref_hap))
-    w.n_reads, w.n_cells = n_reads, n_cells
+    w.n_rows_total = len(w.gid)
+    snps = (w.snp_gid, w.snp_pos, w.snp_ref, w.snp_alt, w.snp_ref_hap)
+    if part is None:
+        w.feat_index = np.arange(len(w.gid))
+        w.dreads, w.cell_keys = ctx.synth_reads(n_reads, n_cells, sg, sb, se, seed=seed, want_seq=True, snps=snps)
+        w.n_reads = n_reads
+    else:
+        idx, i0, n_loc = genomic_chunk(ctx, n_reads, seed, sg, sb, se, w.gid, w.beg, w.end, part)
+        w.feat_index, w.first_read = idx, i0
+        w.gid, w.beg, w.end = w.gid[idx], w.beg[idx], w.end[idx]
+        w.dreads, w.cell_keys = ctx.synth_reads(max(1, n_loc), n_cells, sg, sb, se, seed=seed, want_seq=True,
+                                                snps=snps, first_read=i0, total_reads=n_reads)
+        w.n_reads = n_loc
+    w.n_cells = n_cells
     w.params = engine.make_params(Conf(), 91, with_include=False)
     # region -> SNP lists (start0 <= pos0 < end0), hap table
     order = np.lexsort((w.snp_pos, w.snp_gid))
