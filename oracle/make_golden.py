@@ -304,6 +304,7 @@ def case_bch869():
     d = fresh("bch869_smartseq")
     src = os.path.join(REF, "preprocess/deprecated/merge_smartseq")
     bam = os.path.join(src, "BCH869.output.bam")
+    shutil.copyfile(bam, os.path.join(d, "BCH869.output.bam"))      # travels: the GPU tests decode it on the device
     # inputs the reference reads
     with open(os.path.join(src, "BCH869.output.492.RG.barcodes.tsv")) as fp:
         barcodes = [x.strip() for x in fp if x.strip()]
@@ -374,6 +375,67 @@ def case_bch869():
 
 
 CASES["bch869"] = case_bch869
+
+
+# ------------------------------------------------------------------ config C1 at its full shape
+def case_c1_full(n_reads=1000000, n_bc=500, seed=7):
+    """BASELINE.json configs[0] / SURVEY.md 8(d) C1 as named: ~1M reads on chr22 (BAM contig `chr22`, features
+    without the prefix: the sam_fetch fallback), 500 barcodes, ALL 33 472 rows of the hg38 gene table.  The BAM
+    (tens of MB) does not travel; the fixture holds the decoded record arrays -- what the counting kernels see --
+    and the files the unmodified reference wrote from the BAM itself."""
+    import numpy as np
+    from xcltk_b200 import lib
+    d = fresh("c1_full_chr22")
+    rng = random.Random(seed)
+    feats_all = synth.load_features(os.path.join(REF, "data/anno/annotate_genes_hg38_update_20230126.txt"))
+    assert len(feats_all) == 33472
+    bcs = synth.make_barcodes(rng, n_bc)
+    refs, recs = synth.gen_10x_records(seed, [("22", 50818468)], [f for f in feats_all if f[0] == "22"], n_reads, bcs,
+                                       chr_prefix="chr")
+    tmp = tempfile.mkdtemp()
+    bam = os.path.join(tmp, "c1.bam")
+    synth.write_bam(bam, refs, recs)
+    shuffled = list(bcs)
+    rng.shuffle(shuffled)
+    synth.write_lines(os.path.join(d, "barcodes.tsv"), shuffled)
+    import gzip
+    with gzip.GzipFile(os.path.join(d, "features.tsv.gz"), "wb", mtime=0) as out:
+        for c, s, e, n in feats_all:
+            out.write(("%s\t%d\t%d\t%s\n" % (c, s, e, n)).encode())
+    ks = lib.KeySpace()
+    hr = lib.decode_bams([bam], [np.arange(1, dtype=np.int32)], "CB", "UB", False, ks, 8)
+    cells, umis = {}, {}
+    cell_idx = np.full(hr.n, -1, dtype=np.int32)
+    umi_idx = np.full(hr.n, -1, dtype=np.int32)
+    special = {lib.XG_KEY_NONE: "\x00none", 0: ""}
+    for i in range(hr.n):
+        ck, uk = int(hr.keys[i, 0]), int(hr.keys[i, 1])
+        if ck != lib.XG_KEY_NONE:
+            cell_idx[i] = cells.setdefault(ks.decode(ck), len(cells))
+        if uk != lib.XG_KEY_NONE:
+            umi_idx[i] = umis.setdefault(ks.decode(uk) if uk else "", len(umis))
+    np.savez_compressed(
+        os.path.join(d, "reads.npz"), pos_end=hr.pos_end, fmq=hr.fmq, cig_off=np.append(hr.cig_off, len(hr.cigar)),
+        cigar=hr.cigar, seq_off=np.zeros(0, np.uint32), seq=np.zeros(0, np.uint32),
+        runs=np.array(hr.runs, dtype=np.int64), cell_idx=cell_idx, umi_idx=umi_idx,
+        cell_names=np.array(list(cells)), umi_names=np.array(list(umis)), ref_names=np.array([r[0] for r in refs]),
+        max_aln_len=hr.max_aln_len, max_span=hr.max_span)
+    print("  %d records decoded, %d cells, %d UMIs" % (hr.n, len(cells), len(umis)))
+    hr.close()
+    case = {"defaults": {"sam": [bam], "barcodes": "barcodes.tsv", "features": "features.tsv.gz",
+                         "reads_npz": "reads.npz"}, "runs": [
+        {"name": "rdr_defaults", "kind": "basefc", "kwargs": {"ncores": 8}},
+    ]}
+    finish_case(d, case)
+    # the BAM is gone after this: keep case.json free of the temporary path
+    case["defaults"]["sam"] = ["c1.bam (regenerate with oracle/make_golden.py c1_full)"]
+    with open(os.path.join(d, "case.json"), "w") as fp:
+        json.dump(case, fp, indent=1, sort_keys=True)
+        fp.write("\n")
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+CASES["c1_full"] = case_c1_full
 
 
 if __name__ == "__main__":

@@ -12,7 +12,7 @@ def load_npz_reads(path, chroms, use_cell_keys=True):
     z = np.load(path, allow_pickle=False)
     ks = lib.KeySpace()
     cell_keys = np.array([ks.encode(str(s)) for s in z["cell_names"]] + [lib.XG_KEY_NONE], dtype=np.uint64)
-    umi_keys = np.array([ks.encode(str(s)) for s in z["umi_names"]], dtype=np.uint64)
+    umi_keys = np.array([ks.encode(str(s)) for s in z["umi_names"]] + [lib.XG_KEY_NONE], dtype=np.uint64)   # -1: no tag
     keys = np.stack([cell_keys[z["cell_idx"]], umi_keys[z["umi_idx"]]], axis=1)
     index = {}
     for tid, name in enumerate(z["ref_names"]):

@@ -4,6 +4,7 @@ hand-built records and the losslessness of the 64-bit string keys."""
 
 import os
 import random
+import struct
 import sys
 
 import numpy as np
@@ -199,10 +200,9 @@ def test_packed_key_examples():
     assert ks.n_interned() == 2
 
 
-BCH869 = "/root/reference/preprocess/deprecated/merge_smartseq/BCH869.output.bam"
+BCH869 = os.path.join(GOLD, "bch869_smartseq", "BCH869.output.bam")     # copied from the reference's merge_smartseq/
 
 
-@pytest.mark.skipif(not os.path.exists(BCH869), reason="reference fixture only exists in the build container")
 def test_real_smartseq_bam_and_committed_arrays():
     """The reference's only real BAM: decoder vs the Python reader, and the committed
     tests/golden/bch869_smartseq/reads.npz is exactly what the decoder produces."""
@@ -236,3 +236,59 @@ def test_host_decoder_checks_the_gzip_crc(tmp_path):
     with pytest.raises(lib.XgError) as ei:
         decode([bad])
     assert ei.value.code == -3 and "CRC" in str(ei.value)
+
+
+def _mutated_bam(tmp_path, name, mutate):
+    """A valid BAM whose inflated bytes are edited and compressed again (CRCs right): only the record walk can object."""
+    import gzip
+    from xcltk_b200.synth import _bgzf_block
+    recs = [("r%d" % i, 0, 0, 10 * i, 30, [(0, 15), (3, 40), (0, 5)], "ACGT" * 5,
+             [("CB", "Z", "ACGT-1"), ("UB", "Z", "ACGTAA"), ("NH", "i", 1)]) for i in range(50)]
+    good = _write(tmp_path, recs, name="src_" + name)
+    raw = bytearray(gzip.open(good, "rb").read())
+    l_text = struct.unpack_from("<i", raw, 4)[0]
+    off = 8 + l_text
+    n_ref = struct.unpack_from("<i", raw, off)[0]
+    off += 4
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", raw, off)[0]
+        off += 4 + l_name + 4
+    mutate(raw, off)                      # off = block_size field of the first record
+    out = str(tmp_path / name)
+    with open(out, "wb") as fp:
+        for k in range(0, len(raw), 40000):
+            fp.write(_bgzf_block(bytes(raw[k:k + 40000])))
+        fp.write(_bgzf_block(b""))
+    return out
+
+
+@pytest.mark.parametrize("field", ["l_seq", "n_cigar", "l_name", "cigar_len", "tag_cut"])
+def test_host_decoder_rejects_records_whose_fields_point_outside(tmp_path, field):
+    """name / CIGAR / sequence lengths that do not fit the record, a reference span past 2^31 and a tag
+    value cut off by the record's end must be refused (or, for the tag, read as absent) -- never read past the buffer."""
+    import struct as st
+
+    def mutate(raw, off):
+        if field == "l_seq":
+            st.pack_into("<I", raw, off + 20, 0x3fffffff)
+        elif field == "n_cigar":
+            st.pack_into("<H", raw, off + 16, 0xffff)
+        elif field == "l_name":
+            raw[off + 12] = 255
+        elif field == "cigar_len":          # pos + reference length of record 0 passes 2^31
+            st.pack_into("<i", raw, off + 8, 2147483640)
+        elif field == "tag_cut":            # shrink the record so that its last tag's value is cut off; shift the rest
+            bs = st.unpack_from("<I", raw, off)[0]
+            del raw[off + 4 + bs - 2: off + 4 + bs]
+            st.pack_into("<I", raw, off, bs - 2)
+    p = _mutated_bam(tmp_path, field + ".bam", mutate)
+    if field == "tag_cut":
+        hr, ks = decode([p], cell_tag="NH", umi_tag="UB")
+        assert hr.n == 50
+        assert int(hr.keys[0, 0]) == lib.XG_KEY_NONE          # the cut tag is absent, the others are read
+        assert ks.decode(int(hr.keys[0, 1])) == "ACGTAA"
+        hr.close()
+        return
+    with pytest.raises(lib.XgError) as ei:
+        decode([p], want_seq=True)
+    assert ei.value.code == -3

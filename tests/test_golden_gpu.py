@@ -97,7 +97,7 @@ def test_region_sharded_over_gpus_matches_reference(case, run, reblock, tmp_path
 
 def _device_decoder_runs():
     """golden runs whose BAMs travel (the npz case has none)"""
-    return [(c, r) for c, r in golden_runs() if c != "bch869_smartseq"]
+    return [(c, r) for c, r in golden_runs() if not resolve(c, r)["reads_npz"]]
 
 
 @pytest.mark.parametrize("case,run", _device_decoder_runs())
@@ -135,3 +135,33 @@ def test_goldens_through_the_device_decoder(case, run, tmp_path, gpu_ctx, monkey
         compare_dirs(r["expected"], out, files)
         if used:       # query-name UMIs and free-text tags go through the keyspace: nothing is declined
             assert all(used), "the device decoder declined a BAM in htslib layout"
+
+
+@pytest.mark.parametrize("run", [r for c, r in golden_runs() if c == "bch869_smartseq"])
+def test_bch869_bam_file_matches_reference(run, tmp_path, gpu_ctx, monkeypatch):
+    """The reference's real BAM, as a file: device decoder (it is htslib-written) -> counting kernels -> the bytes
+    the unmodified reference wrote for it."""
+    from util import GOLD
+    from xcltk_b200 import engine
+    r = resolve("bch869_smartseq", run)
+    bam = os.path.join(GOLD, "bch869_smartseq", "BCH869.output.bam")
+    used = []
+    real = engine._device_decode
+
+    def spy(*a, **kw):
+        res = real(*a, **kw)
+        used.append(res is not None)
+        return res
+    monkeypatch.setattr(engine, "_device_decode", spy)
+    out = str(tmp_path / "out")
+    if r["kind"] == "basefc":
+        from xcltk_b200.rdr.fc.main import fc_wrapper
+        ret = fc_wrapper(bam, r["barcodes"], r["features"], out, **r["kwargs"])
+        files = RDR_FILES
+    else:
+        from xcltk_b200.baf.fc.main import afc_wrapper
+        ret = afc_wrapper(bam, r["barcodes"], r["features"], r["snps"], out, **r["kwargs"])
+        files = BAF_FILES
+    assert ret == int(read(r["expected"] + "/RETCODE")) == 0
+    compare_dirs(r["expected"], out, files)
+    assert used and all(used), "the device decoder declined the htslib-written BAM"

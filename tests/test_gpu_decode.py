@@ -184,12 +184,40 @@ def test_device_decode_rejects_unsorted_and_corrupt(gpu_ctx, tmp_path):
         assert e.code == -3
 
 
+BCH869 = os.path.join(GOLD, "bch869_smartseq", "BCH869.output.bam")     # the reference's own fixture, htslib-written
+
+
 def golden_bams():
     out = []
     for case in sorted(os.listdir(GOLD)):
         d = os.path.join(GOLD, case)
         out += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith(".bam")]
-    return out
+    return [p for p in out if p != BCH869]
+
+
+def test_real_htslib_bam_goes_through_the_device_decoder_as_it_is(gpu_ctx):
+    """BCH869.output.bam (preprocess/deprecated/merge_smartseq of the reference: samtools-merged SMART-seq reads,
+    paired, secondaries, N / I / D / S operations, RG tags) was written by htslib: k_inflate / k_walk / k_extract take
+    it without re-blocking, and give the host decoder's arrays -- and the arrays committed with the goldens."""
+    from xcltk_b200 import lib
+    maps = full_maps([BCH869])
+    host, ks_h = host_decode([BCH869], maps, "RG", None, True, with_ks=True)
+    assert host.n > 30000
+    ks_d = lib.KeySpace()
+    res = gpu_ctx.decode_bams([BCH869], maps, "RG", None, True, keyspace=ks_d)
+    assert res is not None, getattr(gpu_ctx, "decode_fallback_reason", "")
+    assert_same_batch(res[0], res[1], host, ks_d, ks_h)
+    got = res[0].download()
+    z = np.load(os.path.join(GOLD, "bch869_smartseq", "reads.npz"), allow_pickle=False)
+    for name in ("pos_end", "fmq", "cigar", "seq_off", "seq"):
+        assert np.array_equal(getattr(got, name), z[name]), name
+    assert np.array_equal(got.cig_off, z["cig_off"][:-1])
+    names = [str(x) for x in z["umi_names"]]
+    for i in range(0, got.n, 97):                     # query names (the counting key without a UMI tag)
+        assert ks_d.decode(int(got.keys[i, 1])) == names[int(z["umi_idx"][i])]
+    got.close()
+    res[0].close()
+    host.close()
 
 
 @pytest.mark.parametrize("path", golden_bams())

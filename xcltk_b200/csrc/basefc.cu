@@ -1104,7 +1104,20 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
         const unsigned long long *seg = (const unsigned long long *)(pool + fd.blk_off);
         const bool light = n <= FS_CAP;
 
-        // ---- phase 1: bitmap of the row's cells (a light feature's words stay in registers)
+        // range width of a heavy feature: a power of two (>= 32 cells) with about 3/4 FS_CAP expected words
+        int wshift = 5;
+        uint32_t n_rng = 1;
+        uint32_t *rc = reinterpret_cast<uint32_t *>(tbl);             // the table is idle: counters, then cursors
+        if (!light) {
+            while (wshift < 10 && ((uint64_t)n << (wshift + 1)) <= (uint64_t)(FS_CAP * 3 / 4) * (uint64_t)n_cols) wshift++;
+            while (((n_cols - 1) >> wshift) + 1 > FS_RANGES) wshift++;      // very many cells: wider ranges, rank windows
+            n_rng = (uint32_t)((n_cols - 1) >> wshift) + 1;
+            for (uint32_t q = threadIdx.x; q < n_rng; q += FS_THREADS) rc[q] = 0;
+            __syncthreads();
+        }
+
+        // ---- phase 1: bitmap of the row's cells.  A light feature's words stay in registers; a heavy one
+        // counts its words per column range in the same sweep.
         unsigned long long pw[FS_REG];
         if (light) {
 #pragma unroll
@@ -1133,6 +1146,7 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                     if (v[q]) {
                         const uint32_t col = (uint32_t)(v[q] & 0xffffffULL);
                         atomicOr(&bitmap[col >> 5], 1u << (col & 31));
+                        atomicAdd(&rc[col >> wshift], 1u);
                     }
             }
         }
@@ -1198,28 +1212,7 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
         }
 
         // ---- heavy feature: split by column range into the scratch half of the block
-        // range width: a power of two (>= 32 cells) with about 3/4 FS_CAP expected words and at most FS_CAP cells
-        int wshift = 5;
-        while (wshift < 10 && ((uint64_t)n << (wshift + 1)) <= (uint64_t)(FS_CAP * 3 / 4) * (uint64_t)n_cols) wshift++;
-        while (wshift > 5 && (1u << wshift) > FS_CAP) wshift--;
-        while (((n_cols - 1) >> wshift) + 1 > FS_RANGES) wshift++;      // very many cells: wider ranges, hash sub-partitions
-        const uint32_t n_rng = (uint32_t)((n_cols - 1) >> wshift) + 1;
-        uint32_t *rc = reinterpret_cast<uint32_t *>(tbl);             // the table is idle: counters, then cursors
-        for (uint32_t q = threadIdx.x; q < n_rng; q += FS_THREADS) rc[q] = 0;
-        __syncthreads();
-        for (uint32_t s0 = threadIdx.x; s0 < n; s0 += FS_THREADS * 4) {
-            unsigned long long v[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t s = s0 + (uint32_t)q * FS_THREADS;
-                v[q] = s < n ? seg[s] : 0ULL;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (v[q]) atomicAdd(&rc[(uint32_t)(v[q] & 0xffffffULL) >> wshift], 1u);
-        }
-        __syncthreads();
-        {   // exclusive prefix over the n_rng counters
+        {   // exclusive prefix over the n_rng counters (F.warp_tot was read before the last barrier)
             const int per = (int)((n_rng + FS_THREADS - 1) / FS_THREADS);
             const uint32_t k0 = threadIdx.x * (uint32_t)per, k1 = min(n_rng, k0 + (uint32_t)per);
             uint32_t mine = 0;
@@ -1255,7 +1248,7 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                 if (v[q]) scr[atomicAdd(&rc[(uint32_t)(v[q] & 0xffffffULL) >> wshift], 1u)] = v[q];
         }
         __syncthreads();
-        // ---- the ranges, one after the other
+        // ---- the ranges, one after the other: [clear table] sync [insert] sync [row part + counters back to zero]
         for (uint32_t rg = 0; rg < n_rng; rg++) {
             const uint32_t p0 = F.range_off[rg], m = F.range_off[rg + 1] - p0;
             if (m == 0) continue;
@@ -1267,11 +1260,10 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
             for (uint32_t win = 0; win < nz_r; win += FS_CAP) {
                 uint32_t n_sub = (m + FS_CAP - 1) / FS_CAP;
                 while (true) {
-                    uint32_t tsz = 64;
-                    const uint32_t per = m / n_sub + 1;
-                    while (tsz < FS_TBL && tsz * 2 < per * 5) tsz <<= 1;
+                    const uint32_t tsz = fs_table_size(m / n_sub + 1);
                     const int shift = 64 - (31 - __clz((int)tsz));
                     for (uint32_t sub = 0; sub < n_sub; sub++) {
+                        __syncthreads();             // the previous pass (or the previous range's row part) is done
                         for (uint32_t s = threadIdx.x; s < tsz; s += FS_THREADS) tbl[s] = 0ULL;
                         __syncthreads();
                         for (uint32_t s0 = threadIdx.x; s0 < m; s0 += FS_THREADS * 4) {
@@ -1291,18 +1283,16 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                                 if (!fs_insert(tbl, tsz, shift, v[q], h, cnt, r, min(tsz, 96u))) F.ovf_s = 1;
                             }
                         }
-                        __syncthreads();
-                        if (F.ovf_s) break;
                     }
+                    __syncthreads();
                     if (!F.ovf_s) break;
                     // a pass overflowed the table: forget the window's counts, sweep again with finer sub-partitions
                     __syncthreads();
                     for (uint32_t c = threadIdx.x; c < FS_CAP; c += FS_THREADS) cnt[c] = 0;
                     if (threadIdx.x == 0) F.ovf_s = 0;
                     n_sub *= 2;
-                    __syncthreads();
                 }
-                // the window's part of the row
+                // the window's part of the row; its counters go back to zero as they are read
                 for (uint32_t k = k_lo + threadIdx.x; k < k_hi; k += FS_THREADS) {
                     uint32_t bits = bitmap[k];
                     uint32_t r = pre[k];
@@ -1313,15 +1303,14 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                         if (rr < FS_CAP) {
                             st_col[base + r] = (int32_t)((k << 5) + (uint32_t)bpos);
                             st_val[base + r] = (int32_t)cnt[rr];
+                            cnt[rr] = 0;
                         }
                         r++;
                     }
                 }
-                __syncthreads();
-                for (uint32_t c = threadIdx.x; c < min(nz_r - win, (uint32_t)FS_CAP); c += FS_THREADS) cnt[c] = 0;
-                __syncthreads();
             }
         }
+        __syncthreads();
         for (int k = threadIdx.x; k < bm_words; k += FS_THREADS) bitmap[k] = 0;
     }
 }

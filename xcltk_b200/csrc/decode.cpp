@@ -303,7 +303,6 @@ const uint8_t *find_tag(const uint8_t *aux, const uint8_t *end, const char *tag)
         bool hit = p[0] == (uint8_t)tag[0] && p[1] == (uint8_t)tag[1];
         uint8_t t = p[2];
         const uint8_t *v = p + 3;
-        if (hit) return p + 2;
         size_t sz;
         switch (t) {
             case 'A': case 'c': case 'C': sz = 1; break;
@@ -325,6 +324,8 @@ const uint8_t *find_tag(const uint8_t *aux, const uint8_t *end, const char *tag)
             }
             default: return nullptr;
         }
+        if (sz > (size_t)(end - v)) return nullptr;      // truncated value: the tag does not exist
+        if (hit) return p + 2;
         p = v + sz;
     }
     return nullptr;
@@ -491,6 +492,21 @@ static int decode_bams_impl(int32_t n_bams, const char *const *paths, const int3
                     return fail(XG_E_FORMAT,
                                 std::string("'") + paths[b] + "' is not coordinate sorted");
                 if (map[tid] >= 0) {
+                    // geometry of a kept record (same test as the device decoder's rec_geom): name, CIGAR,
+                    // sequence and qualities must lie inside the record, or the passes below would read
+                    // past it; and pos + reference length must stay an int32
+                    const uint8_t *r = &bm.u[off + 4];
+                    const uint64_t l_name = r[8], n_cig = rd16(r + 12), l_seq = rd32(r + 16);
+                    const uint64_t need = 32 + l_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq;
+                    if (need > bs || l_seq >= 0x40000000u)
+                        return fail(XG_E_FORMAT, std::string("corrupt BAM record in '") + paths[b] + "'");
+                    int64_t rlen = 0;
+                    for (uint64_t k = 0; k < n_cig; k++) {
+                        const uint32_t cw = rd32(r + 32 + l_name + 4 * k);
+                        if (op_ref(cw & 15)) rlen += cw >> 4;
+                    }
+                    if ((int64_t)pos + std::max<int64_t>(rlen, 1) > INT32_MAX)
+                        return fail(XG_E_FORMAT, std::string("record ends beyond 2^31 in '") + paths[b] + "'");
                     if (tid != run_tid) {
                         bm.runs.push_back({map[tid], (int64_t)bm.rec.size(), (int64_t)bm.rec.size()});
                         run_tid = tid;
