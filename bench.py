@@ -190,7 +190,7 @@ class Batch(object):
 
     def keep_mask(self, totals):
         # min_count = 1, min_maf = 0 (the values xcltk baf passes, baf/pipeline.py:355)
-        return ((totals[:, 0] + totals[:, 1] + totals[:, 2] + totals[:, 3] + totals[:, 4]) >= 1).astype(np.uint8)
+        return (totals.sum(axis=1) >= 1).view(np.uint8)
 
     def step_device(self, checksum=False):
         ctx, fc, bf = self.ctx, self.fc, self.baf
@@ -201,7 +201,7 @@ class Batch(object):
         w1 = time.perf_counter()
         t_fc = ctx.timing()
         launches += int(t_fc[2])
-        totals, st = ctx.baf_pileup(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
+        totals, st = ctx.baf_pileup(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, reuse_totals=True)
         w2 = time.perf_counter()
         t_p = ctx.timing()
         launches += int(t_p[2])
@@ -230,7 +230,7 @@ class Batch(object):
         seg = ctx.basefc_host(self.h_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
         h2d_fc = int(ctx.timing()[13])
         d_bf = ctx.map_reads(self.h_baf)          # zero-copy: 8 B/read over PCIe, rest on demand
-        totals, st = ctx.baf_pileup(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
+        totals, st = ctx.baf_pileup(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, reuse_totals=True)
         ctx.timing_pairs = ctx.timing()[6]            # (read, SNP) pairs: records fetched on demand
         ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, self.keep_mask(totals), True)
         st.close()
@@ -260,7 +260,7 @@ class Batch(object):
         seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
         g_fc = seg.to_sorted()
         ok_fc = all(np.array_equal(a, b) for a, b in zip(g_fc, o_fc))
-        totals, st = ctx.baf_pileup(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params)
+        totals, st = ctx.baf_pileup(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, reuse_totals=True)
         g_baf = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, self.keep_mask(totals), True)
         st.close()
         ok_baf = all(np.array_equal(g[k], o[k]) for g, o in zip(g_baf, o_baf) for k in range(3))

@@ -208,7 +208,8 @@ def _count_shard(conf, ctx, dreads, keyspace, gid_of, max_aln_len, regs, snps):
     if conf.use_barcodes():
         cell_keys = np.array([keyspace.encode(b) for b in conf.barcodes], dtype=np.uint64)
     params = engine.make_params(conf, max_aln_len, with_include=False)
-    totals, state = ctx.baf_pileup(dreads, gid, pos0.astype(np.int32), cell_keys, len(conf.samples), params)
+    totals, state = ctx.baf_pileup(dreads, gid, pos0.astype(np.int32), cell_keys, len(conf.samples), params,
+                                   reuse_totals=True)
     t1 = ctx.timing()
     keep = snp_filter(conf, sub, totals)
     out = ctx.baf_count(state, reg_ptr, np.array(reg_snp, dtype=np.int32), hap_table(sub), keep, conf.no_dup_hap)

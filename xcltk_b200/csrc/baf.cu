@@ -17,6 +17,7 @@
 // (region, cell, UMI); the masks reduce to ref / alt / shared / other UMI counts per
 // (region, cell) and then to AD / DP / OTH (B9, B10).
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 
 #include "compact.cuh"
@@ -469,6 +470,10 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
     XG_CUDA(cudaSetDevice(ctx->device));
     for (double &t : ctx->timing) t = 0;
     int launches = 0;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+    };
 
     int32_t n_gid = 0;
     for (auto &r : rd->h_runs) n_gid = std::max(n_gid, r.gid + 1);
@@ -551,6 +556,7 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
     XG_GET(d_npairs, unsigned long long, "bf_npairs", 2);
     XG_GET(d_totals, unsigned long long, "bf_totals", (size_t)snps->n * 5 + 1);
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->timing[8] = ms_since(t_call);          // host: SNP table (cached), barcode table, buffers
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
     // scan; the pair buffer grows and the scan is repeated in the (rare) overflow case
@@ -632,8 +638,10 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
         xg_baf_state_free(ctx, st);
         return ctx->fail(XG_E_CUDA, std::string("baf pileup: ") + cudaGetErrorString(e));
     }
-    for (size_t k = 0; k < (size_t)snps->n * 5; k++) totals[k] = (int64_t)h_tot[k];
+    ctx->timing[9] = ms_since(t_call);          // ... + kernels + totals on the host
+    memcpy(totals, h_tot, sizeof(int64_t) * (size_t)snps->n * 5);       // counts < 2^31: the same bits as int64
     ctx->pinned_put(h_tot);
+    ctx->timing[10] = ms_since(t_call);         // ... + copy into the caller's array
     float t_all = 0, t_d2h = 0;
     cudaEventElapsedTime(&t_all, ctx->ev[0], ctx->ev[3]);
     cudaEventElapsedTime(&t_d2h, ctx->ev[4], ctx->ev[5]);
@@ -655,6 +663,10 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
     XG_CUDA(cudaSetDevice(ctx->device));
     for (double &t : ctx->timing) t = 0;
     int launches = 0;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+    };
     const int32_t n_cols = st->n_cols, n_snps = st->n_snps;
     // invert region -> SNP lists (cached on the device while the caller passes the same lists)
     const int64_t n_mem = reg_ptr[n_regions];
@@ -718,6 +730,7 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
     XG_GET(seg_base, int64_t, "bf_seg_base", 3 * (size_t)n_regions + 1);
     XG_GET(seg_nnz, int32_t, "bf_seg_nnz", 3 * (size_t)n_regions + 1);
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->timing[8] = ms_since(t_call);          // host: region lists (cached), hap / keep upload, buffers
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
     unsigned grid = (unsigned)((st->n_pairs + 255) / 256);
@@ -762,6 +775,7 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
         launches++;
         XG_CUDA(cudaGetLastError());
     }
+    const double ms_kernels = ms_since(t_call);
     xg_coo **outs[3] = {ad, dp, oth};
     const char *tags[3] = {"bfad", "bfdp", "bfot"};
     for (int wh = 0; wh < 3; wh++)
@@ -775,5 +789,7 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
     ctx->timing[0] = t_all;
     ctx->timing[2] = launches;
     ctx->timing[6] = (double)combos;
+    ctx->timing[9] = ms_kernels;                // ... + kernels queued (one sync for the candidate count)
+    ctx->timing[10] = ms_since(t_call);         // ... + the three results on the host
     return XG_OK;
 }

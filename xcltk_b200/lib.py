@@ -570,13 +570,20 @@ class Context(object):
             self.lib.xg_set_option(self.h, b"row_order", 1)
         return coo_to_numpy(self.lib, out, ctx_obj=self)
 
-    def baf_pileup(self, dreads, gid, pos, cell_keys, n_samples, params):
+    def baf_pileup(self, dreads, gid, pos, cell_keys, n_samples, params, reuse_totals=False):
+        """reuse_totals: the returned totals array is the context's own buffer, overwritten by the next pileup."""
         gid = np.ascontiguousarray(gid, dtype=np.int32)
         pos = np.ascontiguousarray(pos, dtype=np.int32)
         keys = np.ascontiguousarray(cell_keys if cell_keys is not None else [], dtype=np.uint64)
         s = Snps(len(gid), as_ptr(gid, c_i32p), as_ptr(pos, c_i32p))
         b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
-        totals = np.zeros((len(gid), 5), dtype=np.int64)
+        # the library fills every entry; the array is reused from call to call (fresh pages cost more than the
+        # copy itself) -- callers that keep the totals across pileups copy them
+        totals = getattr(self, "_totals_buf", None) if reuse_totals else None
+        if totals is None or totals.shape[0] != len(gid):
+            totals = np.zeros((len(gid), 5), dtype=np.int64)
+            if reuse_totals:
+                self._totals_buf = totals
         st = _P()
         self._check(self.lib.xg_baf_pileup(self.h, dreads.h, C.byref(s), C.byref(b), C.byref(params.c),
                                            as_ptr(totals, c_i64p), C.byref(st)))
