@@ -438,6 +438,63 @@ def case_c1_full(n_reads=1000000, n_bc=500, seed=7):
 CASES["c1_full"] = case_c1_full
 
 
+# ------------------------------------------------------------------ afc with the local-phasing pre-step
+def case_local_phasing(seed=23):
+    """afc_wrapper as `xcltk baf` calls it (baf/pipeline.py:341-360): cellsnp_dir given, so long regions
+    (>= 50 kb, >= 2 SNPs spanning >= 50 kb) have their SNPs re-phased by the EM before counting
+    (baf/fc/main.py:112-149).  BAM, barcodes, features and SNPs are those of c1_chr22_10x; the cellsnp-lite
+    directory is synthetic: two clones of cells with allelic ratios 0.15 / 0.85 in every region and a third of
+    the SNPs phased the wrong way round, so that the EM has flips to find."""
+    import gzip
+    import numpy as np
+    import scipy.io
+    import scipy.sparse
+    d = fresh("c2_local_phasing")
+    src = os.path.join(GOLD, "c1_chr22_10x")
+    with open(os.path.join(src, "barcodes.tsv")) as fp:
+        cells = [x.strip() for x in fp if x.strip()]
+    snps = []
+    with open(os.path.join(src, "snps.tsv")) as fp:
+        next(fp)
+        for line in fp:
+            c, pos, ref, alt, rh, ah = line.rstrip("\n").split("\t")
+            snps.append((c, int(pos), ref, alt, int(rh)))
+    rng = np.random.RandomState(seed)
+    n_snp, n_cell = len(snps), len(cells)
+    clone = rng.randint(0, 3, size=n_cell)                       # 0 / 1: the two CNA clones, 2: balanced cells
+    theta = np.where(clone == 0, 0.15, np.where(clone == 1, 0.85, 0.5))
+    wrong = rng.rand(n_snp) < 0.33                               # phased the wrong way round by "Eagle2"
+    DP = rng.poisson(1.2, size=(n_snp, n_cell)) * (rng.rand(n_snp, n_cell) < 0.6)
+    # ALT count: haplotype-1 allele is ALT iff ref_hap == 0; theta = fraction of haplotype 1
+    hap1_is_alt = np.array([s[4] == 0 for s in snps]) ^ wrong
+    p = np.where(hap1_is_alt[:, None], theta[None, :], 1 - theta[None, :])
+    AD = rng.binomial(DP, p)
+    cs = os.path.join(d, "cellsnp")
+    os.makedirs(cs)
+    order = sorted(cells)                                        # cellsnp-lite writes its own (sorted) cell order
+    perm = [cells.index(c) for c in order]
+    synth.write_lines(os.path.join(cs, "cellSNP.samples.tsv"), order)
+    with gzip.GzipFile(os.path.join(cs, "cellSNP.base.vcf.gz"), "wb", mtime=0) as fp:
+        fp.write(b"##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\n")
+        for c, pos, ref, alt, _ in snps:
+            fp.write(("%s\t%d\t.\t%s\t%s\t.\tPASS\tAD=1;DP=2;OTH=0\n" % (c, pos, ref, alt)).encode())
+    for name, m in (("AD", AD), ("DP", DP), ("OTH", np.zeros_like(DP))):
+        scipy.io.mmwrite(os.path.join(cs, "cellSNP.tag.%s.mtx" % name), scipy.sparse.csr_matrix(m[:, perm]),
+                         field="integer")
+    synth.write_lines(os.path.join(d, "ref_cells.tsv"), [c for c, k in zip(cells, clone) if k == 2][:8])
+    rel = lambda f: os.path.join("..", "c1_chr22_10x", f)
+    case = {"defaults": {"kind": "baf", "sam": [rel("a.bam")], "barcodes": rel("barcodes.tsv"),
+                         "features": rel("features.tsv"), "snps": rel("snps.tsv")}, "runs": [
+        {"name": "pipeline_call", "kwargs": {"cellsnp_dir": "@cellsnp", "output_all_reg": True, "ncores": 4}},
+        {"name": "ref_cells", "kwargs": {"cellsnp_dir": "@cellsnp", "ref_cell_fn": "@ref_cells.tsv", "ncores": 4}},
+        {"name": "no_phasing", "kwargs": {"output_all_reg": True, "ncores": 4}},
+    ]}
+    finish_case(d, case)
+
+
+CASES["local_phasing"] = case_local_phasing
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (build container only)")

@@ -275,3 +275,20 @@ def test_genomic_chunks_partition_the_library():
                 hi = lib.synth_read_index(n_total, sg, sb, se, int(gid[f]), int(end[f]), seed)
                 assert i0 + n >= hi
         assert np.all(seen == 1)
+
+
+def test_reference_import_paths_resolve_to_this_build():
+    """Drop-in at the Python level: the reference's module paths and entry points (xcltk/rdr/fc/main.py:142,
+    xcltk/baf/fc/main.py:32, xcltk/xcltk.py:40, setup.py:58-62) import from the `xcltk` name."""
+    import importlib
+    import inspect
+    fc = importlib.import_module("xcltk.rdr.fc.main")
+    afc = importlib.import_module("xcltk.baf.fc.main")
+    cli = importlib.import_module("xcltk.xcltk")
+    assert fc.__file__.endswith(os.path.join("xcltk_b200", "rdr", "fc", "main.py"))
+    assert list(inspect.signature(fc.fc_wrapper).parameters)[:4] == ["sam_fn", "barcode_fn", "region_fn", "out_dir"]
+    sig = inspect.signature(afc.afc_wrapper).parameters
+    assert "cellsnp_dir" in sig and "ref_cell_fn" in sig and sig["output_all_reg"].default is False
+    assert callable(cli.main)
+    import xcltk
+    assert xcltk.__version__ == "0.5.2"

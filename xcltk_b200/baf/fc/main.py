@@ -17,7 +17,10 @@ import numpy as np
 
 from ... import engine
 from ...utils.zfile import zopen
+from ...utils.csp_io import load_data as csp_load_data
+from ...utils.grange import format_chrom
 from .config import Config
+from .phasing import reg_local_phasing
 from .utils import load_region_from_txt, load_snp_from_tsv, load_snp_from_vcf
 
 BASES = "ACGTN"
@@ -132,12 +135,35 @@ def prepare_config(conf):
         return -1
     info("%d SNPs loaded." % conf.snp_set.get_n())
 
-    if conf.cellsnp_dir is not None or conf.ref_cell_fn is not None:
-        # Local phasing (baf/fc/main.py:112-149, phasing.py, localphase.py) is a host-side
-        # numpy EM that needs the cellsnp-lite AnnData; it is outside this build's scope
-        # (SURVEY.md 8f N4).  Refuse loudly instead of silently skipping it.
-        error("local phasing (cellsnp_dir / ref_cell_fn) is not available in xcltk_b200.")
-        return -1
+    # cellsnp-lite counts for the local-phasing pre-step (baf/fc/main.py:419-463; always given by `xcltk baf`,
+    # baf/pipeline.py:352).  The reference's assertions are kept as assertions.
+    if conf.cellsnp_dir is not None:
+        assert os.path.exists(conf.cellsnp_dir)
+        snp_data = csp_load_data(conf.cellsnp_dir)
+        info("cellsnp SNP adata shape = %s." % str(snp_data.shape))
+        assert len(conf.samples) == snp_data.shape[0]
+        known = set(snp_data.cells.tolist())
+        for cell in conf.samples:
+            assert cell in known
+        if snp_data.shape[1] != conf.snp_set.get_n():
+            warn("n_snp: snp_adata=%d; snp_set=%d!" % (snp_data.shape[1], conf.snp_set.get_n()))
+            assert snp_data.shape[1] >= conf.snp_set.get_n()
+        idx_lst = []                       # SNPs that are still in the phased set
+        for i in range(snp_data.shape[1]):
+            if conf.snp_set.fetch(snp_data.chrom[i], int(snp_data.pos[i]), int(snp_data.pos[i]) + 1):
+                idx_lst.append(i)
+            elif conf.debug > 0:
+                warn("SNP '%s:%d' was filtered before!" % (snp_data.chrom[i], snp_data.pos[i]))
+        if len(idx_lst) < snp_data.shape[1]:
+            snp_data = snp_data.subset_snps(idx_lst)
+            info("SNP adata shape after subset: %s." % str(snp_data.shape))
+        conf.snp_adata = snp_data
+    if conf.ref_cell_fn is not None:
+        assert os.path.exists(conf.ref_cell_fn)
+        conf.ref_cells = np.atleast_1d(np.genfromtxt(conf.ref_cell_fn, dtype="str", delimiter="\t"))
+        assert len(conf.ref_cells) <= len(conf.samples)
+        for cell in conf.ref_cells:
+            assert cell in conf.samples
 
     if conf.cell_tag and conf.cell_tag.upper() == "NONE":
         conf.cell_tag = None
@@ -282,8 +308,39 @@ def afc_core(conf):
     info("#regions: total=%d; with_snps=%d." % (len(conf.reg_list), len(with_snps)))
     if not conf.output_all_reg:
         conf.reg_list = with_snps
-    info("#regions: total=%d; local_phasing=%d; local_phasing_failed=%d." % (len(conf.reg_list), 0, 0))
-    info("#SNPs: local_phasing=%d; local_phasing_flipped=%d." % (0, 0))
+    # local phasing inside long regions (baf/fc/main.py:107-149): host numpy EM on the cellsnp-lite counts; it
+    # may drop unexpressed SNPs from a region's list and swap the haplotype indices of (shared) SNP objects.
+    # The device gets the lists and haplotype tables as they are afterwards.
+    n_rlp = n_rlp_failed = n_slp = n_slp_flipped = 0
+    if conf.use_local_phasing():
+        data = conf.snp_adata
+        if conf.ref_cells is not None:
+            data = data.subset_cells(~np.isin(data.cells.astype(str), np.asarray(conf.ref_cells, dtype=str)))
+        chrom = np.array([format_chrom(c) for c in data.chrom], dtype=object)
+        for reg in conf.reg_list:
+            if reg.end - reg.start < conf.rlp_min_len:
+                continue
+            if reg.snp_list is None or len(reg.snp_list) < max(1, conf.rlp_min_n_snps):
+                continue
+            if reg.snp_list[-1].pos - reg.snp_list[0].pos + 1 < conf.rlp_min_gap:
+                continue
+            if conf.debug > 2:
+                debug("region '%s': do local phasing ..." % reg.name)
+            cols = np.nonzero((chrom == reg.chrom) & (data.pos >= reg.start) & (data.pos < reg.end))[0]
+            reg, flip = reg_local_phasing(reg, data.AD[:, cols].toarray(), data.DP[:, cols].toarray())
+            if flip is None:
+                n_rlp_failed += 1
+                if conf.debug > 1:
+                    debug("region '%s': local phasing failed." % reg.name)
+            else:
+                if conf.debug > 1:
+                    debug("region '%s': #SNPs - total=%d; flipped=%d" % (reg.name, len(reg.snp_list), np.sum(flip)))
+                n_slp_flipped += np.sum(flip)
+            n_slp += len(reg.snp_list)
+            n_rlp += 1
+        conf.snp_adata = conf.ref_cells = None
+    info("#regions: total=%d; local_phasing=%d; local_phasing_failed=%d." % (len(conf.reg_list), n_rlp, n_rlp_failed))
+    info("#SNPs: local_phasing=%d; local_phasing_flipped=%d." % (n_slp, n_slp_flipped))
 
     regs = conf.reg_list
     if len(regs) == 0:
