@@ -122,12 +122,13 @@ def test_snp_loaders_and_region_join():
     assert [snp.get_region_allele_index(b) for b in "GACTN"] == [1, 0, -1, -1, -1]
 
 
-def test_baf_refuses_local_phasing_and_empty_region_list(tmp_path):
+def test_baf_missing_cellsnp_dir_and_empty_region_list(tmp_path):
     from xcltk_b200.baf.fc.main import afc_wrapper
     d = os.path.join(GOLD, "d2_baf_mini")
     args = (os.path.join(d, "a.bam"), os.path.join(d, "barcodes.tsv"), os.path.join(d, "features.tsv"),
             os.path.join(d, "snps.tsv"), str(tmp_path / "o"))
-    assert afc_wrapper(*args, cellsnp_dir="/some/dir") == -1
+    with pytest.raises(AssertionError):                           # assert_e(conf.cellsnp_dir), baf/fc/main.py:420
+        afc_wrapper(*args, cellsnp_dir="/some/dir")
     far = str(tmp_path / "far.tsv")                               # no SNP in any region, output_all_reg=False:
     with open(far, "w") as fp:                                    # the reference divides by zero workers
         fp.write("9\t1\t100\tg\n")
