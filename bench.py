@@ -190,7 +190,8 @@ class Batch(object):
 
     def keep_mask(self, totals):
         # min_count = 1, min_maf = 0 (the values xcltk baf passes, baf/pipeline.py:355)
-        return (totals.sum(axis=1) >= 1).view(np.uint8)
+        t = totals
+        return ((t[:, 0] | t[:, 1] | t[:, 2] | t[:, 3] | t[:, 4]) > 0).view(np.uint8)      # counts are >= 0: sum >= 1 <=> any bit set
 
     def step_device(self, checksum=False):
         ctx, fc, bf = self.ctx, self.fc, self.baf
@@ -298,6 +299,105 @@ def cpu_sample(ctx, args, n_sample, n_threads):
     return run, (host, host_b)
 
 
+def file_legs(ctx, args):
+    """The user's call, file to file: fc_wrapper(BAM, barcodes, features, out_dir) -> features.tsv, barcodes.tsv,
+    matrix.mtx on disk (device decode + counting + Matrix-Market writer), on BAM files that hold exactly the records
+    of a synthetic batch (xg_write_bam): config C1 at its shape (chr22, 1M reads, 500 barcodes, all 33 472 hg38 gene
+    rows) and a slice of config C3 (10k cells, 60k features, --file-reads reads over the whole genome).  The
+    matrix.mtx the call wrote must be, byte for byte, the text written from the CPU oracle's matrix of the same
+    records (md5)."""
+    import hashlib
+    import shutil
+    import tempfile
+    from oracle import oracle
+    from xcltk_b200 import lib, workload
+    from xcltk_b200.rdr.fc.main import fc_wrapper
+    n_thr = os.cpu_count() or 1
+    conf = workload.Conf()
+    out, host_dec, dev_dec = {}, None, None
+
+    def md5(path):
+        h = hashlib.md5()
+        with open(path, "rb") as fp:
+            for blk in iter(lambda: fp.read(1 << 24), b""):
+                h.update(blk)
+        return h.hexdigest()
+
+    with tempfile.TemporaryDirectory() as td:
+        free = shutil.disk_usage(td).free
+        n_c3 = int(min(args.file_reads, max(2e6, (free - (4 << 30)) / 120.0)))       # ~90 B/read on disk + outputs
+        for name, n_reads, n_cells, chroms, all_rows in (("C1", 1000000, 500, {"22"}, True),
+                                                        ("C3_slice", n_c3, args.cells, None, False)):
+            w = workload.make_basefc_workload(ctx, n_reads, n_cells, 33472 if all_rows else args.features, seed=17,
+                                              chroms=chroms)
+            host = w.dreads.download()
+            names = [c for c in workload.HG38_CHROMS if chroms is None or c in chroms]
+            contigs = [("chr" + c, workload.HG38_LEN[c]) for c in names]      # BAM says chr22, the features say 22
+            bam = os.path.join(td, name + ".bam")
+            t = time.perf_counter()
+            lib.write_bam(bam, host, contigs, None, "CB", "UB", level=1, n_threads=n_thr)
+            t_write = time.perf_counter() - t
+            feats = workload.load_genes(None) if all_rows else w.feats
+            gid, beg, end = workload.feature_arrays(feats, w.gid_of)
+            ks = lib.KeySpace()
+            barcodes = [ks.decode(int(k)) for k in w.cell_keys]
+            bc_fn, ft_fn = os.path.join(td, name + ".barcodes.tsv"), os.path.join(td, name + ".features.tsv")
+            with open(bc_fn, "w") as fp:
+                fp.write("".join(b + "\n" for b in barcodes))
+            with open(ft_fn, "w") as fp:
+                fp.write("".join("%s\t%d\t%d\t%s\n" % f for f in feats))
+            # expected text: the oracle's matrix of the same records through the Matrix-Market writer
+            o_row, o_col, o_val = oracle.basefc(host, gid, beg, end, w.cell_keys, n_cells, oracle.params(conf), n_thr)
+            exp_fn = os.path.join(td, name + ".expected.mtx")
+            engine_write = __import__("xcltk_b200.engine", fromlist=["write_mtx"]).write_mtx
+            engine_write(exp_fn, len(gid), o_row, o_col, o_val, np.ones(len(gid), dtype=bool), n_cells, n_thr)
+            want = md5(exp_fn)
+            best = None
+            for k in range(2):
+                out_dir = os.path.join(td, "%s.out%d" % (name, k))
+                t = time.perf_counter()
+                ret = fc_wrapper(bam, bc_fn, ft_fn, out_dir, ncores=n_thr)
+                dt_f = time.perf_counter() - t
+                if ret != 0:
+                    raise RuntimeError("fc_wrapper returned %d" % ret)
+                best = dt_f if best is None else min(best, dt_f)
+            got = md5(os.path.join(out_dir, "matrix.mtx"))
+            out[name] = {"reads_per_s": n_reads / best, "reads": n_reads, "call_ms": 1e3 * best,
+                         "bam_bytes": os.path.getsize(bam), "mtx_bytes": os.path.getsize(os.path.join(out_dir, "matrix.mtx")),
+                         "matrix_md5": got, "matches_oracle_text": bool(got == want), "bam_write_s": t_write,
+                         "shape": "%d features x %d cells" % (len(gid), n_cells)}
+            maps = [np.arange(len(contigs), dtype=np.int32)]
+            if name == "C1":            # host decoder (the fallback for files the device decoder declines)
+                t = time.perf_counter()
+                hr = lib.decode_bams([bam], maps, "CB", "UB", False, lib.KeySpace(), n_thr)
+                dt = time.perf_counter() - t
+                host_dec = {"reads_per_s": hr.n / dt, "threads": n_thr, "sample_reads": hr.n, "file": "C1 BAM"}
+                hr.close()
+            else:                       # device decoder alone: file -> HBM-resident batch
+                bestd = None
+                for _ in range(3):
+                    t = time.perf_counter()
+                    res = ctx.decode_bams([bam], maps, "CB", "UB", False)
+                    dt = time.perf_counter() - t
+                    if res is None:
+                        break
+                    n_dev = res[0].n
+                    res[0].close()
+                    bestd = dt if bestd is None else min(bestd, dt)
+                if bestd is not None:
+                    tdv = ctx.timing()
+                    dev_dec = {"reads_per_s": n_dev / bestd, "sample_reads": n_dev, "call_ms": 1e3 * bestd,
+                               "stream_loop_ms": tdv[4], "extract_ms": tdv[3], "windows": int(tdv[5]), "file": "C3 slice BAM"}
+                else:
+                    dev_dec = {"declined": getattr(ctx, "decode_fallback_reason", "")}
+            host.close()
+            w.dreads.close()
+            os.remove(bam)
+    out["note"] = ("fc_wrapper(): BAM file -> features.tsv, barcodes.tsv, matrix.mtx on disk, best of 2; the BAMs hold "
+                   "the records of device-generated batches (xg_write_bam, htslib block layout, level 1)")
+    return out, host_dec, dev_dec
+
+
 _JSON_FD = None
 
 
@@ -333,12 +433,14 @@ def main():
     ap.add_argument("--baf-cells", type=int, default=5000)
     ap.add_argument("--snps", type=int, default=200000)
     ap.add_argument("--cpu-sample", type=float, default=3e8, help="reads of the CPU legs (default: the whole C3 basefc batch)")
+    ap.add_argument("--file-reads", type=float, default=6e7, help="reads of the C3 slice written to a BAM for the file-to-matrix leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = one library cut into N genomic chunks; weak = one library per GPU")
     args = ap.parse_args()
     args.reads, args.baf_reads, args.cpu_sample = int(args.reads), int(args.baf_reads), int(args.cpu_sample)
+    args.file_reads = int(args.file_reads)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank, world, local, dist = dist_setup(args.gpus)
@@ -503,70 +605,11 @@ def main():
     decode = None
     device_decode = None
     file_to_matrix = None
-    if rank == 0 and world == 1 and not args.no_cpu:      # the CPU and decode legs: rank 0 at N=1 only
-        # host BGZF/BAM decode throughput (the stage before the path) on a bounded sample
+    if rank == 0 and world == 1 and not args.no_cpu:      # the file legs: rank 0 at N=1 only
         try:
-            import tempfile
-            from xcltk_b200 import lib, synth
-            n_dec = 6000000
-            with tempfile.TemporaryDirectory() as td:
-                bam = os.path.join(td, "s.bam")
-                barcodes = synth.write_fast_bam(bam, n_dec, [("chr%d" % c, 100000000) for c in range(1, 6)], 1000,
-                                                seed=5, threads=os.cpu_count() or 1)
-                ks = lib.KeySpace()
-                t = time.perf_counter()
-                hr = lib.decode_bams([bam], [np.arange(5, dtype=np.int32)], "CB", "UB", False, ks, os.cpu_count() or 1)
-                dt_dec = time.perf_counter() - t
-                decode = {"reads_per_s": hr.n / dt_dec, "threads": os.cpu_count() or 1, "sample_reads": hr.n,
-                          "bam_bytes": os.path.getsize(bam),
-                          "note": "xg_decode_bams (host decoder, used for files the device decoder declines) on a "
-                                  "%d-read synthetic BAM; at this rate decoding the C3 batch takes %.0f s" % (hr.n, args.reads / (hr.n / dt_dec))}
-                hr.close()
-                # the same file through the device decoder (BGZF inflate + BAM parse on the GPU,
-                # batch left in HBM); first call warms the staging / slab pools
-                best = None
-                for _ in range(3):
-                    t = time.perf_counter()
-                    res = ctx.decode_bams([bam], [np.arange(5, dtype=np.int32)], "CB", "UB", False)
-                    dt_dev = time.perf_counter() - t
-                    if res is None:
-                        break
-                    n_dev = res[0].n
-                    res[0].close()
-                    best = dt_dev if best is None else min(best, dt_dev)
-                if best is not None:
-                    tdv = ctx.timing()
-                    device_decode = {"reads_per_s": n_dev / best, "sample_reads": n_dev, "call_ms": 1e3 * best,
-                                     "stream_loop_ms": tdv[4], "extract_ms": tdv[3], "windows": int(tdv[5]),
-                                     "note": "xg_decode_bams_device, same file: file -> HBM-resident batch; "
-                                             "the C3 batch at this rate takes %.1f s" % (args.reads / (n_dev / best))}
-                else:
-                    device_decode = {"declined": getattr(ctx, "decode_fallback_reason", "")}
-                # the user's call, file to file: fc_wrapper(BAM, barcodes, features, out_dir) ->
-                # features.tsv / barcodes.tsv / matrix.mtx on disk (device decode + basefc + MTX writer)
-                from xcltk_b200.rdr.fc.main import fc_wrapper
-                bc_fn, ft_fn = os.path.join(td, "barcodes.tsv"), os.path.join(td, "features.tsv")
-                with open(bc_fn, "w") as fp:
-                    fp.write("".join(b + "\n" for b in barcodes))
-                with open(ft_fn, "w") as fp:
-                    for c in range(1, 6):
-                        for k in range(2000):          # 50 kb windows, every other one overlapping its neighbour
-                            fp.write("chr%d\t%d\t%d\tw%d_%d\n" % (c, k * 50000 + 1, k * 50000 + (75000 if k & 1 else 50000), c, k))
-                best_f = None
-                for k in range(2):
-                    out_dir = os.path.join(td, "out%d" % k)
-                    t = time.perf_counter()
-                    ret = fc_wrapper(bam, bc_fn, ft_fn, out_dir, ncores=os.cpu_count() or 1)
-                    dt_f = time.perf_counter() - t
-                    if ret != 0:
-                        raise RuntimeError("fc_wrapper returned %d" % ret)
-                    best_f = dt_f if best_f is None else min(best_f, dt_f)
-                file_to_matrix = {"reads_per_s": n_dec / best_f, "sample_reads": n_dec, "call_ms": 1e3 * best_f,
-                                  "mtx_bytes": os.path.getsize(os.path.join(out_dir, "matrix.mtx")),
-                                  "note": "fc_wrapper(): BAM file -> features.tsv, barcodes.tsv, matrix.mtx on disk "
-                                          "(10000 windows x %d cells), best of 2" % len(barcodes)}
+            file_to_matrix, decode, device_decode = file_legs(ctx, args)
         except Exception as ex:
-            decode = {"error": str(ex)[:200]}
+            file_to_matrix = {"error": str(ex)[:300]}
 
     if rank == 0:
         line = {"metric": "reads/sec counted (basefc + baf fc)", "value": value, "unit": "reads/s",
@@ -590,8 +633,9 @@ def main():
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
-    if rank == 0 and parity is not None and not all(v for v in parity.values() if isinstance(v, bool)):
-        sys.stderr.write("bench.py: PARITY MISMATCH %r\n" % (parity,))
+    bad_file = [k for k, v in (file_to_matrix or {}).items() if isinstance(v, dict) and v.get("matches_oracle_text") is False]
+    if rank == 0 and ((parity is not None and not all(v for v in parity.values() if isinstance(v, bool))) or bad_file):
+        sys.stderr.write("bench.py: PARITY MISMATCH %r %r\n" % (parity, bad_file))
         sys.exit(3)
 
 

@@ -315,11 +315,21 @@ int xg_synth_reads(xg_ctx *ctx, const xg_synth_params *p, xg_dreads **out, uint6
 /* Index of the first read at or after (gid, pos) in the library of p->n_reads reads (host only). */
 int64_t xg_synth_read_index(const xg_synth_params *p, int32_t gid, int32_t pos);
 
+/* The inverse of the decoders (bench / tests; no reference counterpart): a coordinate-sorted, htslib-layout BAM
+ * holding exactly the records of `reads` (one BAM, runs in contig order; contig gid becomes tid gid): pos, flag, mapq,
+ * CIGAR, the 4-bit sequence if the batch has one (else pseudo-random bases of the right length), CB / UB tags
+ * spelled from the keys (cell_tag / umi_tag NULL: not written), query name "r<index>".  Host only.            */
+int xg_write_bam(const char *path, const xg_reads *reads, int32_t n_gid, const char *const *gid_names,
+                 const int64_t *gid_lens, xg_keyspace *ks, const char *cell_tag, const char *umi_tag,
+                 int32_t level, int32_t n_threads);
+
 /* Timing of the last xg_basefc / xg_baf_* call (CUDA events on the library's streams, ms):
  * [0] device span of the call  [1] sum of the dominant counting kernel's launches
  * [2] kernel launches          [3] span of the epoch loop + gather (basefc)
  * [4] result D2H               [5] epochs (basefc)   [6] pool bytes / pairs   [7] staging entries
- * [8..11] host phases of xg_basefc (ms): index build, windows, plan, uploads; [12] whole call. */
+ * [8..11] host phases of xg_basefc (ms): index build, windows, plan, uploads; [12] whole call;
+ * [13] bytes copied host -> device (xg_basefc_host); [14] / [15] features counted in segments / in sets.
+ * xg_baf_*: [8..10] host milestones of the call (ms since entry).                                   */
 void xg_last_timing(xg_ctx *ctx, double out[16]);
 
 const char *xg_version(void);

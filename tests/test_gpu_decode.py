@@ -488,3 +488,38 @@ def test_device_decode_survives_random_corruption(gpu_ctx, tmp_path):
     dev, seen = gpu_ctx.decode_bams([good], maps, "CB", "UB", True)
     assert_same_batch(dev, seen, host)
     dev.close()
+
+
+@pytest.mark.parametrize("want_seq", [False, True])
+def test_device_generated_batch_survives_the_file_round_trip(gpu_ctx, tmp_path, want_seq):
+    """records generated in HBM -> xg_write_bam -> device decoder: the batch comes back array for array (the file
+    legs of bench.py rest on this: the BAM holds exactly the records whose matrix is known)."""
+    from xcltk_b200 import lib, workload
+    if want_seq:
+        w = workload.make_baf_workload(gpu_ctx, 300000, 200, 3000, seed=41, chroms={"20", "21", "22"})
+        names = ["20", "21", "22"]
+    else:
+        w = workload.make_basefc_workload(gpu_ctx, 400000, 300, 33472, seed=40, chroms={"21", "22"})
+        names = ["21", "22"]
+    host = w.dreads.download()
+    contigs = [("chr" + c, workload.HG38_LEN[c]) for c in names]
+    p = str(tmp_path / "rt.bam")
+    lib.write_bam(p, host, contigs, None, "CB", "UB", level=1, n_threads=4)
+    maps = [np.arange(len(contigs), dtype=np.int32)]
+    res = gpu_ctx.decode_bams([p], maps, "CB", "UB", want_seq)
+    assert res is not None, getattr(gpu_ctx, "decode_fallback_reason", "")
+    if not want_seq:
+        assert_same_batch(res[0], res[1], host)
+    else:
+        # the generator fills whole sequence words; a BAM record holds ceil(91 / 2) bytes of them: compare the bases
+        got = res[0].download()
+        for name in ("pos_end", "fmq", "cig_off", "cigar", "keys", "seq_off"):
+            assert np.array_equal(getattr(got, name), getattr(host, name)), name
+        a = got.seq.view(np.uint8).reshape(got.n, -1)
+        b = host.seq.view(np.uint8).reshape(host.n, -1)
+        assert a.shape == b.shape and np.array_equal(a[:, :45], b[:, :45]) and np.array_equal(a[:, 45] >> 4, b[:, 45] >> 4)
+        assert got.runs == host.runs and got.tiles() == host.tiles()
+        got.close()
+    res[0].close()
+    host.close()
+    w.dreads.close()

@@ -858,3 +858,230 @@ extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *
     for (int32_t r = 0; r < n_rows_in; r++) cnt[(size_t)r] = (int32_t)(row_ptr[r + 1] - row_ptr[r]);
     return xg_write_mtx_rows(path, n_rows_in, row_ptr, cnt.data(), out_row, n_rows_out, n_cols, col, val, n_threads);
 }
+
+// ---- BAM writer for a record batch (bench / tests) -------------------------------------------------
+// The inverse of the decoders: a coordinate-sorted BAM whose records carry exactly what the batch holds --
+// pos, flag, mapq, CIGAR (a "simple" read gets its one M operation back), the 4-bit sequence when the batch has
+// one (else pseudo-random bases of the CIGAR's query length), constant qualities, CB:Z / UB:Z tags spelled from
+// the keys (absent key: no tag), query name "r<record index>".  Blocks are laid out as htslib lays them out
+// (whole records per BGZF block, the header in blocks of its own) and compressed by a pool of threads.
+// No reference counterpart: it exists so that the file-to-matrix measurement and the decoder tests can start
+// from a file of the very records whose matrix is known.
+extern "C" int xg_write_bam(const char *path, const xg_reads *r, int32_t n_gid, const char *const *gid_names,
+                            const int64_t *gid_lens, xg_keyspace *ks, const char *cell_tag, const char *umi_tag,
+                            int32_t level, int32_t n_threads) {
+    if (!path || !r || n_gid <= 0 || !gid_names || !gid_lens) return fail(XG_E_ARG, "xg_write_bam: bad argument");
+    if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+    if (n_threads <= 0) n_threads = 1;
+    if (level < 0 || level > 9) level = 1;
+    for (int32_t k = 0; k < r->n_runs; k++) {
+        if (r->runs[k].bam_idx != 0) return fail(XG_E_ARG, "xg_write_bam: batch holds more than one BAM");
+        if (r->runs[k].gid < 0 || r->runs[k].gid >= n_gid) return fail(XG_E_ARG, "xg_write_bam: run on an unnamed contig");
+        if (k && r->runs[k].gid <= r->runs[k - 1].gid) return fail(XG_E_ARG, "xg_write_bam: runs not in contig order");
+    }
+    const int64_t n = r->n_reads;
+    std::vector<int32_t> tid_of((size_t)n_gid, -1);
+    // header: the contigs in gid order (tid = gid)
+    std::string text = "@HD\tVN:1.6\tSO:coordinate\n";
+    for (int32_t g = 0; g < n_gid; g++) text += std::string("@SQ\tSN:") + gid_names[g] + "\tLN:" + std::to_string(gid_lens[g]) + "\n";
+    std::string head = std::string("BAM\1", 4);
+    auto put32 = [](std::string &s, uint32_t v) { s.append((const char *)&v, 4); };
+    put32(head, (uint32_t)text.size());
+    head += text;
+    put32(head, (uint32_t)n_gid);
+    for (int32_t g = 0; g < n_gid; g++) {
+        std::string nm = std::string(gid_names[g]) + '\0';
+        put32(head, (uint32_t)nm.size());
+        head += nm;
+        put32(head, (uint32_t)gid_lens[g]);
+    }
+    // per record: contig (from the runs) and byte size
+    std::vector<int32_t> rec_gid((size_t)n, 0);
+    for (int32_t k = 0; k < r->n_runs; k++)
+        for (int64_t i = r->runs[k].rec_beg; i < r->runs[k].rec_end; i++) rec_gid[(size_t)i] = r->runs[k].gid;
+    const bool has_seq = r->seq_off && r->seq;
+    auto cigar_of = [&](int64_t i, uint32_t *one, const uint32_t **cg) -> uint32_t {
+        const uint32_t ncw = r->fmq[i] >> 24;
+        if (ncw == 0) {
+            *one = (uint32_t)(r->pos_end[2 * i + 1] - r->pos_end[2 * i]) << 4;
+            *cg = one;
+            return 1;
+        }
+        *cg = r->cigar + r->cig_off[i];
+        return ncw == 255 ? r->cigar[r->cig_off[i] - 1] : ncw;
+    };
+    auto qlen_of = [](const uint32_t *cg, uint32_t nc) {
+        uint32_t q = 0;
+        for (uint32_t k = 0; k < nc; k++) {
+            const uint32_t op = cg[k] & 15;
+            if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) q += cg[k] >> 4;
+        }
+        return q;
+    };
+    auto key_text = [&](uint64_t key, char *buf) -> int64_t {       // -1: no tag
+        if (key == XG_KEY_NONE || key == XG_KEY_NOMATCH) return -1;
+        if (key == XG_KEY_EMPTY) return 0;
+        if (!(key >> 63)) return xg::key_unpack(key, buf, 64);
+        return ks ? ks->decode(key, buf, 256) : -1;
+    };
+    std::vector<uint32_t> rec_len((size_t)n);
+    auto size_range = [&](int64_t a, int64_t b) {
+        char buf[260];
+        for (int64_t i = a; i < b; i++) {
+            uint32_t one;
+            const uint32_t *cg;
+            const uint32_t nc = cigar_of(i, &one, &cg), q = qlen_of(cg, nc);
+            uint32_t len = 36 + 12 + 4 * nc + (q + 1) / 2 + q;          // fixed part, "r%010lld\0", CIGAR, SEQ, QUAL
+            if (cell_tag) {
+                const int64_t m = key_text(r->keys[2 * i], buf);
+                if (m >= 0) len += 3 + (uint32_t)m + 1;
+            }
+            if (umi_tag) {
+                const int64_t m = key_text(r->keys[2 * i + 1], buf);
+                if (m >= 0) len += 3 + (uint32_t)m + 1;
+            }
+            rec_len[(size_t)i] = len;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back(size_range, n * t / n_threads, n * (t + 1) / n_threads);
+        for (auto &x : th) x.join();
+    }
+    // blocks: as many whole records as fit 0xff00 bytes
+    const uint32_t PAYLOAD = 0xff00;
+    std::vector<int64_t> blk_first{0};
+    {
+        uint32_t acc = 0;
+        for (int64_t i = 0; i < n; i++) {
+            if (rec_len[(size_t)i] > PAYLOAD) return fail(XG_E_LIMIT, "xg_write_bam: record larger than a BGZF block");
+            if (acc + rec_len[(size_t)i] > PAYLOAD) {
+                blk_first.push_back(i);
+                acc = 0;
+            }
+            acc += rec_len[(size_t)i];
+        }
+        blk_first.push_back(n);
+    }
+    const size_t n_blk = blk_first.size() - 1;
+    auto bgzf = [&](const uint8_t *src, uint32_t len, std::vector<uint8_t> &out) -> bool {
+        uint8_t comp[0x10200];
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+        zs.next_in = const_cast<uint8_t *>(src);
+        zs.avail_in = len;
+        zs.next_out = comp;
+        zs.avail_out = sizeof comp;
+        const int rc = deflate(&zs, Z_FINISH);
+        const uint32_t clen = (uint32_t)zs.total_out;
+        deflateEnd(&zs);
+        if (rc != Z_STREAM_END || clen + 26 > 0x10000) return false;
+        const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+        out.insert(out.end(), hdr, hdr + 16);
+        const uint16_t bsize = (uint16_t)(clen + 25);
+        out.push_back((uint8_t)(bsize & 0xff));
+        out.push_back((uint8_t)(bsize >> 8));
+        out.insert(out.end(), comp, comp + clen);
+        const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, len);
+        for (int k = 0; k < 4; k++) out.push_back((uint8_t)(crc >> (8 * k)));
+        for (int k = 0; k < 4; k++) out.push_back((uint8_t)(len >> (8 * k)));
+        return true;
+    };
+    FILE *fp = fopen(path, "wb");
+    if (!fp) return fail(XG_E_IO, std::string("cannot write '") + path + "'");
+    std::atomic<bool> ok(true);
+    {
+        std::vector<uint8_t> hb;
+        for (size_t off = 0; off < head.size() && ok; off += PAYLOAD)      // the header in blocks of its own (bam_hdr_write flushes)
+            if (!bgzf((const uint8_t *)head.data() + off, (uint32_t)std::min<size_t>(PAYLOAD, head.size() - off), hb)) ok = false;
+        if (ok && fwrite(hb.data(), 1, hb.size(), fp) != hb.size()) ok = false;
+    }
+    auto build_block = [&](size_t b, std::vector<uint8_t> &raw) {
+        raw.clear();
+        char buf[260];
+        for (int64_t i = blk_first[b]; i < blk_first[b + 1]; i++) {
+            uint32_t one;
+            const uint32_t *cg;
+            const uint32_t nc = cigar_of(i, &one, &cg), q = qlen_of(cg, nc);
+            const size_t at = raw.size();
+            raw.resize(at + rec_len[(size_t)i]);
+            uint8_t *p = raw.data() + at;
+            auto w32 = [&](size_t o, uint32_t v) { memcpy(p + o, &v, 4); };
+            auto w16 = [&](size_t o, uint16_t v) { memcpy(p + o, &v, 2); };
+            w32(0, rec_len[(size_t)i] - 4);
+            w32(4, (uint32_t)rec_gid[(size_t)i]);
+            w32(8, (uint32_t)r->pos_end[2 * i]);
+            p[12] = 12;                                       // l_read_name incl. NUL
+            p[13] = (uint8_t)((r->fmq[i] >> 16) & 0xff);
+            w16(14, 4680);                                    // bin: not used by sequential readers
+            w16(16, (uint16_t)std::min<uint32_t>(nc, 65535));
+            w16(18, (uint16_t)(r->fmq[i] & 0xffff));
+            w32(20, q);
+            w32(24, 0xffffffffu);
+            w32(28, 0xffffffffu);
+            w32(32, 0);
+            snprintf((char *)p + 36, 12, "r%010lld", (long long)i);
+            size_t o = 48;
+            memcpy(p + o, cg, 4 * (size_t)nc);
+            o += 4 * (size_t)nc;
+            const size_t nb = (q + 1) / 2;
+            if (has_seq) {
+                memcpy(p + o, (const uint8_t *)(r->seq + r->seq_off[i]), nb);
+            } else {
+                uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ULL + 12345;
+                for (size_t k = 0; k < nb; k++) {
+                    h ^= h >> 29;
+                    h *= 0xBF58476D1CE4E5B9ULL;
+                    p[o + k] = (uint8_t)(((1u << (h & 3)) << 4) | (1u << ((h >> 2) & 3)));
+                }
+                if (q & 1) p[o + nb - 1] &= 0xf0;
+            }
+            o += nb;
+            memset(p + o, 0xff, q);
+            o += q;
+            const char *tags[2] = {cell_tag, umi_tag};
+            for (int t = 0; t < 2; t++) {
+                if (!tags[t]) continue;
+                const int64_t m = key_text(r->keys[2 * i + t], buf);
+                if (m < 0) continue;
+                p[o] = (uint8_t)tags[t][0];
+                p[o + 1] = (uint8_t)tags[t][1];
+                p[o + 2] = 'Z';
+                memcpy(p + o + 3, buf, (size_t)m);
+                p[o + 3 + m] = 0;
+                o += 4 + (size_t)m;
+            }
+        }
+    };
+    // groups of blocks: compressed by the pool, written in order
+    const size_t GROUP = (size_t)n_threads * 64;
+    std::vector<std::vector<uint8_t>> out(GROUP);
+    for (size_t b0 = 0; b0 < n_blk && ok; b0 += GROUP) {
+        const size_t b1 = std::min(n_blk, b0 + GROUP);
+        std::atomic<size_t> next(b0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([&]() {
+                std::vector<uint8_t> raw;
+                raw.reserve(0x10000);
+                for (;;) {
+                    const size_t b = next.fetch_add(1);
+                    if (b >= b1 || !ok) break;
+                    build_block(b, raw);
+                    out[b - b0].clear();
+                    if (!bgzf(raw.data(), (uint32_t)raw.size(), out[b - b0])) ok = false;
+                }
+            });
+        for (auto &x : th) x.join();
+        for (size_t b = b0; b < b1 && ok; b++)
+            if (fwrite(out[b - b0].data(), 1, out[b - b0].size(), fp) != out[b - b0].size()) ok = false;
+    }
+    static const uint8_t eof_block[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0,
+                                          0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok && fwrite(eof_block, 1, 28, fp) != 28) ok = false;
+    if (fclose(fp) != 0) ok = false;
+    if (!ok) return fail(XG_E_IO, std::string("writing '") + path + "' failed");
+    return XG_OK;
+}

@@ -136,6 +136,8 @@ SYMBOLS = {
     "xg_baf_state_free": (None, [_P, _P]),
     "xg_synth_reads": (C.c_int, [_P, C.POINTER(SynthParams), C.POINTER(_P), c_u64p]),
     "xg_synth_read_index": (C.c_int64, [C.POINTER(SynthParams), C.c_int32, C.c_int32]),
+    "xg_write_bam": (C.c_int, [C.c_char_p, C.POINTER(Reads), C.c_int32, C.POINTER(C.c_char_p), c_i64p, _P,
+                               C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]),
     "xg_last_timing": (None, [_P, C.POINTER(C.c_double)]),
     "xg_version": (C.c_char_p, []),
 }
@@ -637,6 +639,19 @@ class Context(object):
             self.close()
         except Exception:
             pass
+
+
+def write_bam(path, host_reads, contigs, keyspace=None, cell_tag="CB", umi_tag="UB", level=1, n_threads=0):
+    """HostReads -> BAM file (xg_write_bam).  contigs: [(name, length)] in gid order."""
+    lib = load()
+    names = (C.c_char_p * len(contigs))(*[c[0].encode() for c in contigs])
+    lens = np.array([c[1] for c in contigs], dtype=np.int64)
+    rc = lib.xg_write_bam(path.encode(), host_reads.ptr, len(contigs), names, as_ptr(lens, c_i64p),
+                          keyspace.h if keyspace is not None else None,
+                          cell_tag.encode() if cell_tag else None, umi_tag.encode() if umi_tag else None,
+                          level, n_threads)
+    if rc != 0:
+        raise XgError(rc, lib.xg_host_last_error().decode())
 
 
 def synth_read_index(n_total, span_gid, span_beg, span_end, gid, pos, seed=7):
