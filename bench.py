@@ -393,6 +393,58 @@ def file_legs(ctx, args):
             host.close()
             w.dreads.close()
             os.remove(bam)
+        # ---- config C4 (SMART-seq): 384 per-cell BAMs, no cell / UMI tags: sample IDs, reads collapsed by query name
+        n_bams, per_bam = 384, int(args.smartseq_reads)
+        chroms4 = None
+        names = list(workload.HG38_CHROMS)
+        contigs = [(c, workload.HG38_LEN[c]) for c in names]
+        paths = []
+        t = time.perf_counter()
+        w = workload.make_basefc_workload(ctx, per_bam, 40, 33472, seed=1000, chroms=chroms4)
+        for b in range(n_bams):
+            d = w.dreads if b == 0 else ctx.synth_reads(per_bam, 40, *w.spans, seed=1000 + b, want_seq=False)[0]
+            host = d.download()
+            p = os.path.join(td, "cell%03d.bam" % b)
+            lib.write_bam(p, host, contigs, None, None, None, level=1, n_threads=n_thr, name_from_umi=True)
+            paths.append(p)
+            host.close()
+            d.close()
+        t_write = time.perf_counter() - t
+        lst, ft_fn = os.path.join(td, "C4.lst"), os.path.join(td, "C4.features.tsv")
+        with open(lst, "w") as fp:
+            fp.write("".join(p + "\n" for p in paths))
+        with open(ft_fn, "w") as fp:
+            fp.write("".join("%s\t%d\t%d\t%s\n" % f for f in w.feats))
+        ids = ",".join("well%03d" % b for b in range(n_bams))
+        best = None
+        for k in range(2):
+            out_dir = os.path.join(td, "C4.out%d" % k)
+            t = time.perf_counter()
+            ret = fc_wrapper(None, None, ft_fn, out_dir, sam_list_fn=lst, sample_ids=ids, cell_tag=None, umi_tag=None,
+                             ncores=n_thr)
+            dt_f = time.perf_counter() - t
+            if ret != 0:
+                raise RuntimeError("fc_wrapper (C4) returned %d" % ret)
+            best = dt_f if best is None else min(best, dt_f)
+        # expected: the oracle on the host decoder's records of the same files (query names through the keyspace)
+        ks = lib.KeySpace()
+        maps = [np.arange(len(contigs), dtype=np.int32)] * n_bams
+        hr = lib.decode_bams(paths, maps, None, None, False, ks, n_thr)
+        gid, beg, end = workload.feature_arrays(w.feats, w.gid_of)
+        conf4 = workload.Conf()
+        conf4.excl_flag, conf4.cell_tag, conf4.umi_tag = 1796, None, None      # the no-UMI default (rdr/fc/main.py:425-429)
+        conf4.use_barcodes = lambda: False
+        conf4.use_umi = lambda: False
+        o_row, o_col, o_val = oracle.basefc(hr, gid, beg, end, None, n_bams, oracle.params(conf4), n_thr)
+        hr.close()
+        exp_fn = os.path.join(td, "C4.expected.mtx")
+        __import__("xcltk_b200.engine", fromlist=["write_mtx"]).write_mtx(
+            exp_fn, len(gid), o_row, o_col, o_val, np.ones(len(gid), dtype=bool), n_bams, n_thr)
+        got = md5(os.path.join(out_dir, "matrix.mtx"))
+        out["C4_smartseq"] = {"reads_per_s": n_bams * per_bam / best, "reads": n_bams * per_bam, "bams": n_bams,
+                              "call_ms": 1e3 * best, "matrix_md5": got, "matches_oracle_text": bool(got == md5(exp_fn)),
+                              "nnz": int(len(o_val)), "bam_write_s": t_write,
+                              "shape": "%d features x %d cells, sample IDs, query-name keys" % (len(gid), n_bams)}
     out["note"] = ("fc_wrapper(): BAM file -> features.tsv, barcodes.tsv, matrix.mtx on disk, best of 2; the BAMs hold "
                    "the records of device-generated batches (xg_write_bam, htslib block layout, level 1)")
     return out, host_dec, dev_dec
@@ -434,6 +486,7 @@ def main():
     ap.add_argument("--snps", type=int, default=200000)
     ap.add_argument("--cpu-sample", type=float, default=3e8, help="reads of the CPU legs (default: the whole C3 basefc batch)")
     ap.add_argument("--file-reads", type=float, default=6e7, help="reads of the C3 slice written to a BAM for the file-to-matrix leg")
+    ap.add_argument("--smartseq-reads", type=float, default=5e4, help="reads per BAM of the 384-BAM SMART-seq leg (C4)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],

@@ -318,10 +318,11 @@ int64_t xg_synth_read_index(const xg_synth_params *p, int32_t gid, int32_t pos);
 /* The inverse of the decoders (bench / tests; no reference counterpart): a coordinate-sorted, htslib-layout BAM
  * holding exactly the records of `reads` (one BAM, runs in contig order; contig gid becomes tid gid): pos, flag, mapq,
  * CIGAR, the 4-bit sequence if the batch has one (else pseudo-random bases of the right length), CB / UB tags
- * spelled from the keys (cell_tag / umi_tag NULL: not written), query name "r<index>".  Host only.            */
+ * spelled from the keys (cell_tag / umi_tag NULL: not written), query name "r<index>" or -- name_from_umi -- the
+ * UMI key's text (records of a molecule then share their name, like mates).  Host only.                   */
 int xg_write_bam(const char *path, const xg_reads *reads, int32_t n_gid, const char *const *gid_names,
                  const int64_t *gid_lens, xg_keyspace *ks, const char *cell_tag, const char *umi_tag,
-                 int32_t level, int32_t n_threads);
+                 int32_t name_from_umi, int32_t level, int32_t n_threads);
 
 /* Timing of the last xg_basefc / xg_baf_* call (CUDA events on the library's streams, ms):
  * [0] device span of the call  [1] sum of the dominant counting kernel's launches

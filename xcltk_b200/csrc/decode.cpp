@@ -863,13 +863,15 @@ extern "C" int xg_write_mtx(const char *path, int32_t n_rows_in, const int64_t *
 // The inverse of the decoders: a coordinate-sorted BAM whose records carry exactly what the batch holds --
 // pos, flag, mapq, CIGAR (a "simple" read gets its one M operation back), the 4-bit sequence when the batch has
 // one (else pseudo-random bases of the CIGAR's query length), constant qualities, CB:Z / UB:Z tags spelled from
-// the keys (absent key: no tag), query name "r<record index>".  Blocks are laid out as htslib lays them out
+// the keys (absent key: no tag), query name "r<record index>" -- or, with name_from_umi, the text of the record's
+// UMI key, so that records of one molecule share their name the way mates do (SMART-seq style input, counted
+// with --UMItag None).  Blocks are laid out as htslib lays them out
 // (whole records per BGZF block, the header in blocks of its own) and compressed by a pool of threads.
 // No reference counterpart: it exists so that the file-to-matrix measurement and the decoder tests can start
 // from a file of the very records whose matrix is known.
 extern "C" int xg_write_bam(const char *path, const xg_reads *r, int32_t n_gid, const char *const *gid_names,
                             const int64_t *gid_lens, xg_keyspace *ks, const char *cell_tag, const char *umi_tag,
-                            int32_t level, int32_t n_threads) {
+                            int32_t name_from_umi, int32_t level, int32_t n_threads) {
     if (!path || !r || n_gid <= 0 || !gid_names || !gid_lens) return fail(XG_E_ARG, "xg_write_bam: bad argument");
     if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
     if (n_threads <= 0) n_threads = 1;
@@ -931,7 +933,12 @@ extern "C" int xg_write_bam(const char *path, const xg_reads *r, int32_t n_gid, 
             uint32_t one;
             const uint32_t *cg;
             const uint32_t nc = cigar_of(i, &one, &cg), q = qlen_of(cg, nc);
-            uint32_t len = 36 + 12 + 4 * nc + (q + 1) / 2 + q;          // fixed part, "r%010lld\0", CIGAR, SEQ, QUAL
+            uint32_t l_name = 12;                                       // "r%010lld\0"
+            if (name_from_umi) {
+                const int64_t m = key_text(r->keys[2 * i + 1], buf);
+                if (m > 0 && m < 250) l_name = (uint32_t)m + 1;
+            }
+            uint32_t len = 36 + l_name + 4 * nc + (q + 1) / 2 + q;      // fixed part, name, CIGAR, SEQ, QUAL
             if (cell_tag) {
                 const int64_t m = key_text(r->keys[2 * i], buf);
                 if (m >= 0) len += 3 + (uint32_t)m + 1;
@@ -1010,10 +1017,16 @@ extern "C" int xg_write_bam(const char *path, const xg_reads *r, int32_t n_gid, 
             uint8_t *p = raw.data() + at;
             auto w32 = [&](size_t o, uint32_t v) { memcpy(p + o, &v, 4); };
             auto w16 = [&](size_t o, uint16_t v) { memcpy(p + o, &v, 2); };
+            uint32_t l_name = 12;
+            int64_t name_len = -1;
+            if (name_from_umi) {
+                name_len = key_text(r->keys[2 * i + 1], buf);
+                if (name_len > 0 && name_len < 250) l_name = (uint32_t)name_len + 1; else name_len = -1;
+            }
             w32(0, rec_len[(size_t)i] - 4);
             w32(4, (uint32_t)rec_gid[(size_t)i]);
             w32(8, (uint32_t)r->pos_end[2 * i]);
-            p[12] = 12;                                       // l_read_name incl. NUL
+            p[12] = (uint8_t)l_name;                          // l_read_name incl. NUL
             p[13] = (uint8_t)((r->fmq[i] >> 16) & 0xff);
             w16(14, 4680);                                    // bin: not used by sequential readers
             w16(16, (uint16_t)std::min<uint32_t>(nc, 65535));
@@ -1022,8 +1035,13 @@ extern "C" int xg_write_bam(const char *path, const xg_reads *r, int32_t n_gid, 
             w32(24, 0xffffffffu);
             w32(28, 0xffffffffu);
             w32(32, 0);
-            snprintf((char *)p + 36, 12, "r%010lld", (long long)i);
-            size_t o = 48;
+            if (name_len > 0) {
+                memcpy(p + 36, buf, (size_t)name_len);
+                p[36 + name_len] = 0;
+            } else {
+                snprintf((char *)p + 36, 12, "r%010lld", (long long)i);
+            }
+            size_t o = 36 + l_name;
             memcpy(p + o, cg, 4 * (size_t)nc);
             o += 4 * (size_t)nc;
             const size_t nb = (q + 1) / 2;

@@ -137,7 +137,7 @@ SYMBOLS = {
     "xg_synth_reads": (C.c_int, [_P, C.POINTER(SynthParams), C.POINTER(_P), c_u64p]),
     "xg_synth_read_index": (C.c_int64, [C.POINTER(SynthParams), C.c_int32, C.c_int32]),
     "xg_write_bam": (C.c_int, [C.c_char_p, C.POINTER(Reads), C.c_int32, C.POINTER(C.c_char_p), c_i64p, _P,
-                               C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]),
+                               C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]),
     "xg_last_timing": (None, [_P, C.POINTER(C.c_double)]),
     "xg_version": (C.c_char_p, []),
 }
@@ -641,7 +641,8 @@ class Context(object):
             pass
 
 
-def write_bam(path, host_reads, contigs, keyspace=None, cell_tag="CB", umi_tag="UB", level=1, n_threads=0):
+def write_bam(path, host_reads, contigs, keyspace=None, cell_tag="CB", umi_tag="UB", level=1, n_threads=0,
+              name_from_umi=False):
     """HostReads -> BAM file (xg_write_bam).  contigs: [(name, length)] in gid order."""
     lib = load()
     names = (C.c_char_p * len(contigs))(*[c[0].encode() for c in contigs])
@@ -649,7 +650,7 @@ def write_bam(path, host_reads, contigs, keyspace=None, cell_tag="CB", umi_tag="
     rc = lib.xg_write_bam(path.encode(), host_reads.ptr, len(contigs), names, as_ptr(lens, c_i64p),
                           keyspace.h if keyspace is not None else None,
                           cell_tag.encode() if cell_tag else None, umi_tag.encode() if umi_tag else None,
-                          level, n_threads)
+                          1 if name_from_umi else 0, level, n_threads)
     if rc != 0:
         raise XgError(rc, lib.xg_host_last_error().decode())
 

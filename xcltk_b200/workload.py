@@ -160,6 +160,7 @@ def make_basefc_workload(ctx, n_reads, n_cells, n_features=33472, seed=7, chroms
     w.feats, w.gid_of = feats, gid_of
     w.gid, w.beg, w.end = feature_arrays(feats, gid_of)
     sg, sb, se = merged_spans(feats, gid_of)
+    w.spans = (sg, sb, se)
     w.n_rows_total = len(w.gid)
     if part is None:
         w.feat_index = np.arange(len(w.gid))
@@ -177,7 +178,7 @@ def make_basefc_workload(ctx, n_reads, n_cells, n_features=33472, seed=7, chroms
     return w
 
 
-def make_baf_workload(ctx, n_reads, n_cells, n_snps=200000, seed=7, chroms=None, part=None):
+def make_baf_workload(ctx, n_reads, n_cells, n_snps=200000, seed=7, chroms=None, part=None, snp_seed=None):
     """Config 2: chr1-22 reads, 5k cells, 200k phased het SNPs inside gene spans.
     part = (rank, world): the regions of that genomic chunk (w.feat_index: their rows in the whole matrices),
     the whole SNP table, and the reads that can overlap the chunk's regions."""
@@ -188,7 +189,7 @@ def make_baf_workload(ctx, n_reads, n_cells, n_snps=200000, seed=7, chroms=None,
     w.feats, w.gid_of = genes, gid_of
     w.gid, w.beg, w.end = feature_arrays(genes, gid_of)
     sg, sb, se = merged_spans(genes, gid_of)
-    rng = np.random.RandomState(seed + 1)
+    rng = np.random.RandomState(seed + 1 if snp_seed is None else snp_seed)     # snp_seed: one SNP set for many batches
     # SNP positions uniform over the merged gene spans
     lens = (se - sb).astype(np.int64)
     cum = np.concatenate([[0], np.cumsum(lens)])
