@@ -8,7 +8,7 @@ ctx = engine.get_context(0)
 b = workload.make_baf_workload(ctx, n, 5000, 200000, seed=8)
 for rep in range(4):
     t0 = time.perf_counter()
-    totals, st = ctx.baf_pileup(b.dreads, b.snp_gid, b.snp_pos, b.cell_keys, 5000, b.params)
+    totals, st = ctx.baf_pileup(b.dreads, b.snp_gid, b.snp_pos, b.cell_keys, 5000, b.params, reuse_totals=True)
     t1 = time.perf_counter()
     tp = ctx.timing()
     keep = ((totals[:, 0] + totals[:, 1] + totals[:, 2] + totals[:, 3] + totals[:, 4]) >= 1).astype(np.uint8)
@@ -18,5 +18,5 @@ for rep in range(4):
     tc = ctx.timing()
     st.close()
     t4 = time.perf_counter()
-    print("pileup wall %.2f ms (device %.2f; host phases %.2f / %.2f / %.2f)  keep %.2f  count wall %.2f ms (device %.2f; host %.2f / %.2f / %.2f)  close %.2f" % (
-        1e3 * (t1 - t0), tp[0], tp[8], tp[9], tp[10], 1e3 * (t2 - t1), 1e3 * (t3 - t2), tc[0], tc[8], tc[9], tc[10], 1e3 * (t4 - t3)))
+    print("scan %.3f ms pairs %d | pileup wall %.2f ms (device %.2f; host phases %.2f / %.2f / %.2f)  keep %.2f  count wall %.2f ms (device %.2f; host %.2f / %.2f / %.2f)  close %.2f" % (
+        tp[1], int(tp[6]), 1e3 * (t1 - t0), tp[0], tp[8], tp[9], tp[10], 1e3 * (t2 - t1), 1e3 * (t3 - t2), tc[0], tc[8], tc[9], tc[10], 1e3 * (t4 - t3)))

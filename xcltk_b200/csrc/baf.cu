@@ -94,74 +94,190 @@ __device__ __forceinline__ uint32_t base_at(const BafScanDev &P, int64_t i, int3
     }
 }
 
-__global__ void __launch_bounds__(256) k_baf_scan(const __grid_constant__ BafScanDev P) {
-    const xg_tile tile = P.tiles[blockIdx.x];
-    const xg_run run = P.runs[tile.run];
-    const int32_t gid = run.gid;
-    if (gid < 0 || gid >= P.n_gid) return;
-    // SNPs inside the tile window [first_pos, max_end)
-    int32_t sa, sb;
-    {
-        int32_t g0 = P.snp_goff[gid], g1 = P.snp_goff[gid + 1];
+// Per tile: the SNPs inside its window [first_pos, max_end) -- two binary searches over the contig's sorted SNP
+// positions, one thread per tile, so that the scan CTAs find their range with one load (and tiles over no SNP are
+// passed over without touching their records).
+__global__ void k_baf_tile_snps(const xg_tile *tiles, const xg_run *runs, int32_t n_tiles, int32_t n_gid,
+                                const int32_t *snp_goff, const int32_t *snp_pos, int2 *out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const xg_tile tile = tiles[t];
+    const int32_t gid = runs[tile.run].gid;
+    int2 r = make_int2(0, 0);
+    if (gid >= 0 && gid < n_gid) {
+        const int32_t g0 = snp_goff[gid], g1 = snp_goff[gid + 1];
         int32_t lo = g0, hi = g1;
         while (lo < hi) {
             int32_t mid = (lo + hi) >> 1;
-            if (__ldg(&P.snp_pos[mid]) < tile.first_pos) lo = mid + 1; else hi = mid;
+            if (snp_pos[mid] < tile.first_pos) lo = mid + 1; else hi = mid;
         }
-        sa = lo;
+        r.x = lo;
         hi = g1;
         while (lo < hi) {
             int32_t mid = (lo + hi) >> 1;
-            if (__ldg(&P.snp_pos[mid]) < tile.max_end) lo = mid + 1; else hi = mid;
+            if (snp_pos[mid] < tile.max_end) lo = mid + 1; else hi = mid;
         }
-        sb = lo;
+        r.y = lo;
     }
-    if (sa == sb) return;     // no SNP under this tile: its records are never read
+    out[t] = r;
+}
 
-    for (int32_t k = threadIdx.x; k < tile.n_rec; k += blockDim.x) {
-        const int64_t i = tile.rec_beg + k;
-        const int2 pe = P.pos_end[i];
-        // first SNP with pos >= read.pos (fetch(chrom, pos-1, pos): pos0 in [read.pos, read.end))
-        int32_t lo = sa, hi = sb;
-        while (lo < hi) {
-            int32_t mid = (lo + hi) >> 1;
-            if (__ldg(&P.snp_pos[mid]) < pe.x) lo = mid + 1; else hi = mid;
+#define SCAN_SNP_CAP 256      // SNP positions of a tile staged in shared memory
+#define SCAN_RPT (XG_TILE / 256)
+
+// Persistent CTAs, two phases.
+//   Phase 1 streams the CTA's tiles (static stride): a tile's SNP positions are staged in shared memory, every
+//   thread loads its four records' (pos, end) up front (coalesced 8-byte loads) and finds the first SNP at or after
+//   pos among the staged positions.  A read that covers a SNP (about one in twenty) is only NOTED -- (tile, record,
+//   first SNP) appended to the CTA's own candidate list through a shared-memory cursor -- so that the stream never
+//   waits for the dependent flag / key / barcode / CIGAR / sequence loads of the few.
+//   Phase 2 takes the candidates 256 at a time, one per thread, so that those loads are in flight for all of them
+//   at once; the (read, SNP) pairs of a batch reserve their place in the pair list with one atomic.
+struct ScanCand {
+    uint32_t rec;         // tile * XG_TILE + record of the tile
+    int32_t snp;          // first sorted SNP at or after the read's pos
+};
+
+__global__ void __launch_bounds__(256) k_baf_scan(const __grid_constant__ BafScanDev P, const int2 *tile_snp,
+                                                  int32_t n_tiles, ScanCand *cand_all, uint32_t cand_cap) {
+    __shared__ int32_t s_snp[2][SCAN_SNP_CAP];
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_ncand;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    ScanCand *cand = cand_all + (size_t)blockIdx.x * cand_cap;       // this CTA's list (cand_cap = its tiles x XG_TILE)
+    if (threadIdx.x == 0) s_ncand = 0;
+    int buf = 0;
+    // ---- phase 1
+    for (int32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int2 rg = tile_snp[t];
+        if (rg.x >= rg.y) continue;       // no SNP under this tile: its records are never read
+        const int32_t sa = rg.x, ns = rg.y - rg.x;
+        const xg_tile tile = P.tiles[t];
+        const bool staged = ns <= SCAN_SNP_CAP;
+        int2 pe[SCAN_RPT];
+#pragma unroll
+        for (int r = 0; r < SCAN_RPT; r++) {
+            const int32_t k = threadIdx.x + r * 256;
+            pe[r] = k < tile.n_rec ? P.pos_end[tile.rec_beg + k] : make_int2(0, 0);
         }
-        if (lo >= sb || __ldg(&P.snp_pos[lo]) >= pe.y) continue;
-        const uint32_t fmq = P.fmq[i];
-        if (!read_passes_flags(P.fp, fmq)) continue;
-        const ulonglong2 ky = P.keys[i];
-        const uint64_t umi = ky.y;
-        if (umi == XG_KEY_NONE || umi == XG_KEY_EMPTY) continue;
-        uint32_t col;
-        if (P.fp.use_cell_tag) {
-            if (ky.x == XG_KEY_NONE) continue;
-            int32_t c = barcode_lookup(P.bc, ky.x);
-            if (c < 0) continue;
-            col = (uint32_t)c;
-        } else {
-            col = (uint32_t)run.bam_idx;
-        }
-        uint32_t n_ops = fmq >> 24;
-        const uint32_t *cig = nullptr;
-        int32_t aln;
-        if (n_ops == 0) {
-            aln = pe.y - pe.x;
-        } else {
-            cig = P.cigar + P.cig_off[i];
-            if (n_ops == 255) n_ops = __ldg(cig - 1);
-            aln = 0;
-            for (uint32_t q = 0; q < n_ops; q++) {
-                uint32_t w = __ldg(&cig[q]);
-                if (cig_aligned(w & 15u)) aln += (int32_t)(w >> 4);
+        int32_t *sn = s_snp[buf];
+        if (staged)
+            for (int k = threadIdx.x; k < ns; k += 256) sn[k] = __ldg(&P.snp_pos[sa + k]);
+        buf ^= 1;
+        __syncthreads();                  // staged; and the other buffer is free again
+#pragma unroll
+        for (int r = 0; r < SCAN_RPT; r++) {
+            const int32_t k = threadIdx.x + r * 256;
+            // first SNP with pos >= read.pos (fetch(chrom, pos-1, pos): pos0 in [read.pos, read.end))
+            int32_t lo = 0;
+            bool hit = false;
+            if (k < tile.n_rec) {
+                if (staged) {
+                    if (ns <= 8) {
+                        for (int q = 0; q < ns; q++) lo += sn[q] < pe[r].x;
+                    } else {
+                        int32_t hi = ns;
+                        while (lo < hi) {
+                            int32_t mid = (lo + hi) >> 1;
+                            if (sn[mid] < pe[r].x) lo = mid + 1; else hi = mid;
+                        }
+                    }
+                    hit = lo < ns && sn[lo] < pe[r].y;
+                } else {
+                    int32_t hi = ns;
+                    while (lo < hi) {
+                        int32_t mid = (lo + hi) >> 1;
+                        if (__ldg(&P.snp_pos[sa + mid]) < pe[r].x) lo = mid + 1; else hi = mid;
+                    }
+                    hit = lo < ns && __ldg(&P.snp_pos[sa + lo]) < pe[r].y;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_ncand, (uint32_t)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (hit) {
+                    ScanCand c;
+                    c.rec = (uint32_t)t * XG_TILE + (uint32_t)k;
+                    c.snp = sa + lo;
+                    cand[base + __popc(m & ((1u << lane) - 1u))] = c;
+                }
             }
         }
-        if (aln < P.fp.min_len) continue;
-        for (int32_t s = lo; s < sb; s++) {
-            const int32_t sp = __ldg(&P.snp_pos[s]);
-            if (sp >= pe.y) break;
-            const uint32_t code = base_at(P, i, pe.x, pe.y, n_ops, cig, sp);
-            unsigned long long o = atomicAdd(P.n_pairs, 1ull);
+    }
+    __syncthreads();
+    const uint32_t n_cand = s_ncand;
+    // ---- phase 2: one candidate per thread
+    for (uint32_t c0 = 0; c0 < n_cand; c0 += 256) {
+        const uint32_t ci = c0 + threadIdx.x;
+        uint32_t cnt = 0, col = 0, n_ops = 0;
+        int32_t lo = 0, sb = 0;
+        int64_t i = 0;
+        int2 pe = make_int2(0, 0);
+        uint64_t umi = 0;
+        const uint32_t *cig = nullptr;
+        do {
+            if (ci >= n_cand) break;
+            const ScanCand c = cand[ci];
+            const uint32_t t = c.rec / XG_TILE;
+            const xg_tile tile = P.tiles[t];
+            i = tile.rec_beg + (c.rec % XG_TILE);
+            lo = c.snp;
+            sb = tile_snp[t].y;
+            pe = P.pos_end[i];
+            const uint32_t fmq = P.fmq[i];
+            if (!read_passes_flags(P.fp, fmq)) break;
+            const ulonglong2 ky = P.keys[i];
+            umi = ky.y;
+            if (umi == XG_KEY_NONE || umi == XG_KEY_EMPTY) break;
+            if (P.fp.use_cell_tag) {
+                if (ky.x == XG_KEY_NONE) break;
+                int32_t cc = barcode_lookup(P.bc, ky.x);
+                if (cc < 0) break;
+                col = (uint32_t)cc;
+            } else {
+                col = (uint32_t)P.runs[tile.run].bam_idx;
+            }
+            n_ops = fmq >> 24;
+            int32_t aln;
+            if (n_ops == 0) {
+                aln = pe.y - pe.x;
+            } else {
+                cig = P.cigar + P.cig_off[i];
+                if (n_ops == 255) n_ops = __ldg(cig - 1);
+                aln = 0;
+                for (uint32_t q = 0; q < n_ops; q++) {
+                    uint32_t w = __ldg(&cig[q]);
+                    if (cig_aligned(w & 15u)) aln += (int32_t)(w >> 4);
+                }
+            }
+            if (aln < P.fp.min_len) break;
+            for (int32_t s = lo; s < sb && __ldg(&P.snp_pos[s]) < pe.y; s++) cnt++;
+        } while (false);
+        // the batch's pairs reserve their place: block-wide exclusive prefix sum, one atomic
+        uint32_t incl = cnt;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        __syncthreads();                  // s_warp / s_base of the previous batch have been read
+        if (lane == 31) s_warp[wp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int q = 0; q < 8; q++) {
+            const uint32_t x = s_warp[q];
+            if (q < wp) before += x;
+            total += x;
+        }
+        if (total == 0) continue;         // uniform: every thread sees the same total
+        if (threadIdx.x == 0) s_base = atomicAdd(P.n_pairs, (unsigned long long)total);
+        __syncthreads();
+        unsigned long long o = s_base + before + (incl - cnt);
+        for (uint32_t q = 0; q < cnt; q++, o++) {
+            const int32_t s = lo + (int32_t)q;
+            const uint32_t code = base_at(P, i, pe.x, pe.y, n_ops, cig, __ldg(&P.snp_pos[s]));
             if (o < P.cap_pairs) {
                 P.pr_snp[o] = (uint32_t)__ldg(&P.snp_idx[s]);
                 P.pr_colal[o] = col | (code << 24);
@@ -553,12 +669,24 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
     P.fp.use_cell_tag = par->use_cell_tag;
     P.fp.need_umi_tag = par->need_umi_tag;
     if (par->use_cell_tag && (rc = xg_build_barcode_table(ctx, cells, &P.bc))) return rc;
+    XG_GET(d_tile_snp, int2, "bf_tile_snp", rd->n_tiles + 1);
+    // candidate lists of the scan CTAs: room for every record of the tiles a CTA walks
+    const int scan_grid = std::max(1, std::min(rd->n_tiles, 148 * 8));
+    const uint32_t cand_cap = (uint32_t)((rd->n_tiles + scan_grid - 1) / scan_grid) * XG_TILE;
+    if ((uint64_t)rd->n_tiles * XG_TILE >= (1ull << 32))
+        return ctx->fail(XG_E_LIMIT, "xg_baf_pileup: more than 2^32 record slots in one batch");
+    XG_GET(d_cand, ScanCand, "bf_cand", (size_t)scan_grid * cand_cap + 1);
     XG_GET(d_npairs, unsigned long long, "bf_npairs", 2);
     XG_GET(d_totals, unsigned long long, "bf_totals", (size_t)snps->n * 5 + 1);
     XG_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->timing[8] = ms_since(t_call);          // host: SNP table (cached), barcode table, buffers
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
+    if (rd->n_tiles > 0 && any_snp) {
+        k_baf_tile_snps<<<(rd->n_tiles + 255) / 256, 256, 0, ctx->stream>>>(rd->tiles, rd->runs, rd->n_tiles, n_gid,
+                                                                          P.snp_goff, P.snp_pos, d_tile_snp);
+        launches++;
+    }
     // scan; the pair buffer grows and the scan is repeated in the (rare) overflow case
     unsigned long long cap_pairs = std::max<unsigned long long>(1ull << 16, (unsigned long long)rd->n_reads / 4);
     unsigned long long n_pairs = 0;
@@ -577,7 +705,7 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
         XG_CUDA(cudaMemsetAsync(d_npairs, 0, 16, ctx->stream));
         cudaEventRecord(ctx->ev[1], ctx->stream);
         if (rd->n_tiles > 0 && any_snp) {
-            k_baf_scan<<<rd->n_tiles, 256, 0, ctx->stream>>>(P);
+            k_baf_scan<<<scan_grid, 256, 0, ctx->stream>>>(P, d_tile_snp, rd->n_tiles, d_cand, cand_cap);
             launches++;
             XG_CUDA(cudaGetLastError());
         }
