@@ -177,6 +177,24 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
                           const int32_t *const *tid_map, const int32_t *tid_map_len,
                           const char *cell_tag, const char *umi_tag, int32_t want_seq,
                           xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen);
+/* The same for a byte range of every file: only the BGZF blocks in [range_lo[b], range_hi[b]) of BAM b are inflated
+ * and parsed (range_hi[b] = 0: the whole file); both offsets must be block starts (xg_bgzf_block_index) and the block
+ * at range_lo[b] must begin with a record (htslib's layout).  This is how one library is split between GPUs: every
+ * GPU decodes the blocks of its genomic chunk (+ halo) only.                                              */
+int xg_decode_bams_device_range(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
+                                const int32_t *const *tid_map, const int32_t *tid_map_len,
+                                const char *cell_tag, const char *umi_tag, int32_t want_seq, xg_keyspace *ks,
+                                const int64_t *range_lo, const int64_t *range_hi, xg_dreads **out,
+                                int64_t *n_records_seen);
+/* Host helpers for choosing the ranges (what the .bai linear index gives pysam's fetch, computed from the file):
+ * offsets of all BGZF blocks (n + 1 entries, the last = file size; release with xg_free_array), the block in which
+ * the first record starts (*aligned = 1: exactly at its beginning, as htslib writes), and the (tid, pos) of the
+ * record at the beginning of the block at `offset` (tid -2: empty / too short a block).                       */
+int xg_bgzf_block_index(const char *path, int64_t **offsets, int64_t *n_blocks, int64_t *first_record_block,
+                        int32_t *aligned);
+void xg_free_array(void *p);
+int xg_bam_block_probe(const char *path, int64_t offset, int32_t *tid, int32_t *pos);
+
 /* Validation entry: inflate a whole BGZF file on the device into out[0, cap).  With out == NULL
  * (or cap too small) only *n_out, the inflated size, is set.                               */
 int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t cap, int64_t *n_out);

@@ -319,3 +319,41 @@ def test_bam_writer_round_trip(tmp_path, want_seq):
     assert raw[:4] == b"BAM\x01"
     hr.close()
     h2.close()
+
+
+def test_block_index_and_probe(tmp_path):
+    """What the sharded loader reads off a BAM instead of a .bai: block offsets, the block of the first record,
+    and the position of the record that starts a block."""
+    import gzip
+    src = os.path.join(GOLD, "c1_chr22_10x", "a.bam")
+    p = str(tmp_path / "aligned.bam")
+    synth.reblock_bam(src, p)
+    off, first, aligned = lib.bgzf_block_index(p)
+    assert aligned and off[0] == 0 and off[-1] == os.path.getsize(p) and np.all(np.diff(off) > 0)
+    raw = open(p, "rb").read()
+    for o in off[:-1]:
+        assert raw[o:o + 4] == b"\x1f\x8b\x08\x04"
+    # the records of the file in order; the first record of every block is the record at the block's inflated offset
+    hr, _ = decode([p], want_seq=False)
+    pos = hr.pos_end[:, 0]
+    seen = 0
+    for i in range(first, len(off) - 1):
+        blk = gzip.decompress(raw[off[i]:off[i + 1]])
+        tid, ps = lib.bam_block_probe(p, int(off[i]))
+        if len(blk) == 0:
+            assert tid == -2
+            continue
+        assert (tid, ps) == (struct.unpack_from("<i", blk, 4)[0], struct.unpack_from("<i", blk, 8)[0])
+        assert ps == pos[seen]                      # whole records per block: counting records gives the same
+        n = 0
+        q = 0
+        while q < len(blk):
+            q += 4 + struct.unpack_from("<I", blk, q)[0]
+            n += 1
+        assert q == len(blk)
+        seen += n
+    assert seen == hr.n
+    # a BAM cut into blocks without regard to records is reported as such
+    _off, _first, al2 = lib.bgzf_block_index(src)
+    assert not al2
+    hr.close()

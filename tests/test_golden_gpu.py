@@ -165,3 +165,46 @@ def test_bch869_bam_file_matches_reference(run, tmp_path, gpu_ctx, monkeypatch):
     assert ret == int(read(r["expected"] + "/RETCODE")) == 0
     compare_dirs(r["expected"], out, files)
     assert used and all(used), "the device decoder declined the htslib-written BAM"
+
+
+@pytest.mark.parametrize("n_shards", [2, 5])
+@pytest.mark.parametrize("case,run", [("c1_chr22_10x", "rdr_defaults"), ("c1_chr22_10x", "rdr_umi_none"),
+                                      ("c1_chr22_10x", "baf_all_reg_dup"), ("c1_chr22_10x", "baf_count3_maf0.1")])
+def test_one_library_split_by_byte_ranges_matches_reference(case, run, n_shards, tmp_path, gpu_ctx, monkeypatch):
+    """The multi-GPU product path on one GPU (XCLTK_B200_EMULATE_SHARDS: the shards run one after the other on
+    device 0): the BAM is cut at BGZF block boundaries, every shard decodes only the blocks of its genomic chunk
+    (+ halo) and counts the features / regions that start in it; the merged rows are the reference's bytes."""
+    from xcltk_b200 import engine, synth
+    monkeypatch.setenv("XCLTK_B200_GPUS", str(n_shards))
+    monkeypatch.setenv("XCLTK_B200_EMULATE_SHARDS", "1")
+    r = resolve(case, run)
+    sams = []
+    for k, p in enumerate(r["sam"]):
+        q = str(tmp_path / ("%d_%s" % (k, os.path.basename(p))))
+        synth.reblock_bam(p, q)                         # htslib's block layout (the goldens' BAMs are cut blindly)
+        sams.append(q)
+    seen = []
+    real = engine.load_reads_sharded
+
+    def spy(*a, **kw):
+        b = real(*a, **kw)
+        seen.append(b)
+        return b
+    monkeypatch.setattr(engine, "load_reads_sharded", spy)
+    out = str(tmp_path / "out")
+    if r["kind"] == "basefc":
+        from xcltk_b200.rdr.fc.main import fc_wrapper
+        ret = fc_wrapper(",".join(sams), r["barcodes"], r["features"], out, **r["kwargs"])
+        files = RDR_FILES
+    else:
+        from xcltk_b200.baf.fc.main import afc_wrapper
+        ret = afc_wrapper(",".join(sams), r["barcodes"], r["features"], r["snps"], out, **r["kwargs"])
+        files = BAF_FILES
+    assert ret == 0
+    compare_dirs(r["expected"], out, files)
+    assert seen and seen[0] is not None, "the library was not split"
+    st = seen[0].stats
+    whole = os.path.getsize(sams[0])
+    decoded = sum(hi - lo for per in st["byte_ranges"] for lo, hi in per)
+    assert decoded < 1.6 * whole          # every shard decodes its part (+ halo), not the whole file
+    assert sum(len(s) for s in seen[0].shards) > 0

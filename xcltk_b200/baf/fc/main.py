@@ -256,14 +256,36 @@ def count_regions(conf, regs, batch=None):
         chroms = list(dict.fromkeys([s.chrom for s in snps]))
         threads = engine.n_decode_threads(conf.nproc)
         if n_dev > 1:
-            batch = engine.load_reads_multi(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True,
-                                            threads, devices=tuple(range(n_dev)))
+            batch = engine.load_reads_sharded(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True,
+                                              parallel.device_list(n_dev),
+                                              [r.chrom if r.snp_list else None for r in regs],
+                                              [r.start - 1 for r in regs], [r.end - 1 for r in regs])
+            if batch is None:
+                batch = engine.load_reads_multi(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True,
+                                                threads, devices=parallel.device_list(n_dev))
         else:
             batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, True, threads,
                                       mapped=True)
     try:
         shape = (len(regs), len(conf.samples))
-        if isinstance(batch, engine.MultiBatch):
+        if isinstance(batch, engine.ShardedBatch):
+            shards = batch.shards
+
+            def one(k):
+                b = batch.batches[k]
+                if b is None or len(shards[k]) == 0:
+                    z = np.zeros(0, np.int32)
+                    return ((z, z, z, shape),) * 3, [[0.0] * 16, [0.0] * 16]
+                return _count_shard(conf, b.ctx, b.dreads, b.keyspace, b.gid_of, b.stats["max_aln_len"],
+                                    [regs[i] for i in shards[k]], snps)
+            parts = parallel.run_on_devices(len(shards), one)
+            out = []
+            for w in range(3):
+                r, c, v = parallel.merge_coo([[np.array(x) for x in p[0][w][:3]] for p in parts], shards, len(regs))
+                out.append((r, c, v, shape))
+            out = tuple(out)
+            conf.last_timing = parts[0][1]
+        elif isinstance(batch, engine.MultiBatch):
             gid = np.array([batch.gid_of.get(r.chrom, -1) if r.snp_list else -1 for r in regs], dtype=np.int32)
             beg = np.array([r.start - 1 for r in regs], dtype=np.int64)
             load, total = parallel.reads_before(gid, beg, batch.runs, batch.pos_of_run)

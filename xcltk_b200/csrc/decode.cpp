@@ -1103,3 +1103,95 @@ extern "C" int xg_write_bam(const char *path, const xg_reads *r, int32_t n_gid, 
     if (!ok) return fail(XG_E_IO, std::string("writing '") + path + "' failed");
     return XG_OK;
 }
+
+// ---- splitting a BAM between GPUs (host side) --------------------------------------------------------
+// Offsets of the BGZF blocks of a file: the chain of block sizes is followed with one small read per block
+// (nothing is inflated).  *offsets (n + 1 entries, the last one = file size) is malloc'ed: xg_free_array().
+// *first_record_block: the block in which the first alignment record starts, and *aligned = 1 when it starts
+// exactly at that block's beginning (htslib flushes after the header), else 0.
+extern "C" int xg_bgzf_block_index(const char *path, int64_t **offsets, int64_t *n_blocks, int64_t *first_record_block,
+                                   int32_t *aligned) {
+    if (!path || !offsets || !n_blocks) return fail(XG_E_ARG, "xg_bgzf_block_index: null argument");
+    xg_dec::BamFile bf;
+    int rc = xg_dec::open_bam(path, bf, true);       // header only
+    if (rc) return rc;
+    const uint64_t hdr_usize = bf.h.end_off;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail(XG_E_IO, std::string("cannot open '") + path + "'");
+    std::vector<int64_t> off;
+    int64_t at = 0, first_blk = -1;
+    int32_t is_aligned = 0;
+    uint64_t usize = 0;
+    uint8_t h[18];
+    while (true) {
+        if (fseeko(fp, (off_t)at, SEEK_SET) != 0) break;
+        const size_t got = fread(h, 1, 18, fp);
+        if (got == 0) break;
+        uint32_t total = 0, hl = 0;
+        if (got < 18 || xg_dec::bgzf_block_header(h, 1u << 20, &total, &hl) < 0 || total < 26) {
+            fclose(fp);
+            return fail(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (bad block header)");
+        }
+        if (first_blk < 0) {                        // still inside the header: this block's inflated size
+            uint8_t t4[4];
+            if (fseeko(fp, (off_t)(at + total - 4), SEEK_SET) != 0 || fread(t4, 1, 4, fp) != 4) {
+                fclose(fp);
+                return fail(XG_E_FORMAT, std::string("truncated BGZF block in '") + path + "'");
+            }
+            const uint32_t isize = rd32(t4);
+            if (usize + isize > hdr_usize || (usize == hdr_usize && isize > 0)) {
+                first_blk = (int64_t)off.size();
+                is_aligned = usize == hdr_usize ? 1 : 0;
+            }
+            usize += isize;
+        }
+        off.push_back(at);
+        at += total;
+    }
+    fclose(fp);
+    off.push_back(at);
+    if (first_blk < 0) first_blk = (int64_t)off.size() - 1;       // no record at all
+    int64_t *o = (int64_t *)malloc(off.size() * sizeof(int64_t));
+    if (!o) return fail(XG_E_NOMEM, "out of memory");
+    memcpy(o, off.data(), off.size() * sizeof(int64_t));
+    *offsets = o;
+    *n_blocks = (int64_t)off.size() - 1;
+    if (first_record_block) *first_record_block = first_blk;
+    if (aligned) *aligned = is_aligned;
+    return XG_OK;
+}
+
+extern "C" void xg_free_array(void *p) { free(p); }
+
+// (tid, pos) of the record at the beginning of the block at `offset` (htslib writes whole records per block): one
+// block is read and inflated.  tid = -2: the block is empty (the EOF marker) or too short for a record header.
+extern "C" int xg_bam_block_probe(const char *path, int64_t offset, int32_t *tid, int32_t *pos) {
+    if (!path || !tid || !pos) return fail(XG_E_ARG, "xg_bam_block_probe: null argument");
+    *tid = -2;
+    *pos = -1;
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail(XG_E_IO, std::string("cannot open '") + path + "'");
+    std::vector<uint8_t> buf(0x10000 + 64);
+    if (fseeko(fp, (off_t)offset, SEEK_SET) != 0) {
+        fclose(fp);
+        return fail(XG_E_IO, "seek failed");
+    }
+    const size_t got = fread(buf.data(), 1, buf.size(), fp);
+    fclose(fp);
+    uint32_t total = 0, hl = 0;
+    if (got < 26 || xg_dec::bgzf_block_header(buf.data(), got, &total, &hl) != 0 || total > got)
+        return fail(XG_E_FORMAT, std::string("no BGZF block at the given offset of '") + path + "'");
+    xg_dec::BgzfBlock b;
+    b.coff = hl;
+    b.clen = total - hl - 8;
+    memcpy(&b.isize, buf.data() + total - 4, 4);
+    memcpy(&b.crc, buf.data() + total - 8, 4);
+    b.uoff = 0;
+    xg_dec::Bytes u;
+    int rc = xg_dec::inflate_blocks(buf.data(), 0, &b, 1, u, 1);
+    if (rc) return rc;
+    if (u.size() < 12) return XG_OK;
+    *tid = (int32_t)rd32(&u[4]);
+    *pos = (int32_t)rd32(&u[8]);
+    return XG_OK;
+}

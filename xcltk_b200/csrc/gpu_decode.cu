@@ -977,7 +977,11 @@ int flush_window(Decoder &D, BamState &B, int32_t nb) {
 }
 
 // Stream one BAM through the window buffers.
-int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid_map, int32_t tid_map_len) {
+// range_lo / range_hi (range_hi > 0): only the BGZF blocks in [range_lo, range_hi) of the file -- both must be block
+// starts (or the file's end), and the block at range_lo must begin with a record (htslib's layout; the caller takes
+// the offsets from xg_bgzf_block_index / xg_bam_block_probe).  The header is still read from the file's beginning.
+int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid_map, int32_t tid_map_len,
+               int64_t range_lo = 0, int64_t range_hi = 0) {
     xg_ctx *ctx = D.ctx;
     const int fd = open(path, O_RDONLY);
     struct stat stt;
@@ -985,7 +989,13 @@ int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid
         if (fd >= 0) close(fd);
         return ctx->fail(XG_E_IO, std::string("cannot open '") + path + "'");
     }
-    const uint64_t csize = (uint64_t)stt.st_size;
+    const uint64_t fsize = (uint64_t)stt.st_size;
+    const bool ranged = range_hi > 0;
+    if (ranged && (range_lo < 0 || range_lo > range_hi || (uint64_t)range_hi > fsize)) {
+        close(fd);
+        return ctx->fail(XG_E_ARG, "xg_decode_bams_device_range: byte range outside the file");
+    }
+    const uint64_t csize = ranged ? (uint64_t)range_hi : fsize;     // the streaming loop ends here
     const size_t STAGE_BYTES = stage_bytes();
     uint8_t *stage[2] = {(uint8_t *)ctx->pinned_get(STAGE_HEAD + STAGE_BYTES), (uint8_t *)ctx->pinned_get(STAGE_HEAD + STAGE_BYTES)};
     // the chunk's block descriptors travel through pinned memory too: a copy from pageable memory
@@ -1027,8 +1037,59 @@ int decode_bam(Decoder &D, const char *path, int32_t bam_idx, const int32_t *tid
     int32_t win_blocks = 0;
     bool win_open = false;
     const double t_loop = now_ms();
+    uint64_t c_begin = 0;
+    if (ranged && range_lo > 0) {
+        // the header comes from the file's first blocks (host inflate); the stream then starts at range_lo
+        const size_t len = (size_t)std::min<uint64_t>(STAGE_BYTES, fsize);
+        uint8_t *data = stage[0] + STAGE_HEAD;
+        if (!pread_parallel(fd, data, len, 0, n_threads)) return finish(XG_E_IO, std::string("short read on '") + path + "'");
+        uint64_t off = 0, uo = 0;
+        while (off < len) {
+            uint32_t total = 0, hl = 0;
+            int rc = xg_dec::bgzf_block_header(data + off, len - off, &total, &hl);
+            if (rc != 0 || off + total > len) break;
+            xg_dec::BgzfBlock b;
+            b.coff = off + hl;
+            b.clen = total - hl - 8;
+            memcpy(&b.isize, data + off + total - 4, 4);
+            memcpy(&b.crc, data + off + total - 8, 4);
+            b.uoff = uo;
+            uo += b.isize;
+            hb.push_back(b);
+            off += total;
+        }
+        size_t nb = 1;
+        while (true) {
+            if (hb.empty()) return finish(XG_E_FORMAT, std::string("'") + path + "' is not BGZF (bad block header)");
+            const size_t take = std::min(nb, hb.size());
+            xg_dec::Bytes u;
+            int rc = xg_dec::inflate_blocks(data, 0, hb.data(), take, u, 1);
+            if (rc) return finish(rc, xg_host_last_error());
+            rc = xg_dec::parse_header(u, hdr, path);
+            if (rc == XG_OK) break;
+            if (rc != XG_E_LIMIT) return finish(rc, xg_host_last_error());
+            if (take >= hb.size())
+                return finish(XG_E_UNSUPPORTED, std::string("BAM header of '") + path + "' does not end within the first staged chunk");
+            nb *= 2;
+        }
+        hb.clear();
+        header_done = true;
+        B.hdr_end = hdr.end_off;
+        B.n_ref = (int32_t)hdr.names.size();
+        if (tid_map_len < B.n_ref) return finish(XG_E_ARG, "tid_map shorter than the BAM's contig list");
+        if ((size_t)B.n_ref + 1 > D.tid_cap) {
+            ctx->dev_put(D.d_tid_map);
+            D.tid_cap = (size_t)B.n_ref + 1;
+            D.d_tid_map = (int32_t *)ctx->dev_get(D.tid_cap * 4);
+            if (!D.d_tid_map) return finish(XG_E_CUDA, "out of device memory");
+        }
+        cudaMemcpyAsync(D.d_tid_map, tid_map, (size_t)B.n_ref * 4, cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);          // stage[0] is about to be reused
+        c_begin = next_off = (uint64_t)range_lo;
+        uoff = hdr.end_off;                           // every block of the range lies behind the header
+    }
     uint64_t k = 0;
-    for (uint64_t c0 = 0; c0 < csize; c0 += STAGE_BYTES, k++) {
+    for (uint64_t c0 = c_begin; c0 < csize; c0 += STAGE_BYTES, k++) {
         const int si = (int)(k & 1);
         const size_t len = (size_t)std::min<uint64_t>(STAGE_BYTES, csize - c0);
         if (k >= 2) cudaEventSynchronize(done[si]);
@@ -1231,15 +1292,32 @@ int xg_bgzf_inflate_device(xg_ctx *ctx, const char *path, uint8_t *out, int64_t 
 
 static int decode_bams_device_impl(xg_ctx *ctx, int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
                                    const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag,
-                                   int32_t want_seq, xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen);
+                                   int32_t want_seq, xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen,
+                                   const int64_t *range_lo, const int64_t *range_hi);
 
 // no C++ exception crosses the C boundary (host vectors of the block index, the key strings ...)
+int xg_decode_bams_device_range(xg_ctx *ctx, int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
+                                const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag, int32_t want_seq,
+                                xg_keyspace *ks, const int64_t *range_lo, const int64_t *range_hi, xg_dreads **out,
+                                int64_t *n_records_seen) {
+    try {
+        return decode_bams_device_impl(ctx, n_bams, paths, tid_map, tid_map_len, cell_tag, umi_tag, want_seq, ks, out,
+                                       n_records_seen, range_lo, range_hi);
+    } catch (const std::exception &e) {
+        if (ctx && ctx->stream) {
+            cudaStreamSynchronize(ctx->stream);
+            if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        }
+        return ctx ? ctx->fail(XG_E_NOMEM, std::string("device decode: ") + e.what()) : XG_E_NOMEM;
+    }
+}
+
 int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
                           const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag, int32_t want_seq,
                           xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen) {
     try {
         return decode_bams_device_impl(ctx, n_bams, paths, tid_map, tid_map_len, cell_tag, umi_tag, want_seq, ks, out,
-                                       n_records_seen);
+                                       n_records_seen, nullptr, nullptr);
     } catch (const std::exception &e) {
         if (ctx && ctx->stream) {
             cudaStreamSynchronize(ctx->stream);
@@ -1251,7 +1329,8 @@ int xg_decode_bams_device(xg_ctx *ctx, int32_t n_bams, const char *const *paths,
 
 static int decode_bams_device_impl(xg_ctx *ctx, int32_t n_bams, const char *const *paths, const int32_t *const *tid_map,
                                    const int32_t *tid_map_len, const char *cell_tag, const char *umi_tag,
-                                   int32_t want_seq, xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen) {
+                                   int32_t want_seq, xg_keyspace *ks, xg_dreads **out, int64_t *n_records_seen,
+                                   const int64_t *range_lo, const int64_t *range_hi) {
     if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
     if (n_bams < 0 || !out) return ctx->fail(XG_E_ARG, "xg_decode_bams_device: bad argument");
     if (cell_tag && strlen(cell_tag) != 2) return ctx->fail(XG_E_ARG, "cell tag must have 2 characters");
@@ -1275,8 +1354,9 @@ static int decode_bams_device_impl(xg_ctx *ctx, int32_t n_bams, const char *cons
     for (int32_t b = 0; b < n_bams; b++) {
         struct stat stt;
         if (stat(paths[b], &stt) != 0) return ctx->fail(XG_E_IO, std::string("cannot open '") + paths[b] + "'");
-        D.comp_all += (uint64_t)stt.st_size;
-        max_csize = std::max<uint64_t>(max_csize, (uint64_t)stt.st_size);
+        const uint64_t part = range_hi && range_hi[b] > 0 ? (uint64_t)(range_hi[b] - range_lo[b]) : (uint64_t)stt.st_size;
+        D.comp_all += part;
+        max_csize = std::max<uint64_t>(max_csize, part);
     }
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
@@ -1318,7 +1398,8 @@ static int decode_bams_device_impl(xg_ctx *ctx, int32_t n_bams, const char *cons
     lap("setup");
     std::vector<int64_t> bam_end((size_t)n_bams, 0);
     for (int32_t b = 0; b < n_bams; b++) {
-        int rc = decode_bam(D, paths[b], b, tid_map[b], tid_map_len[b]);
+        int rc = decode_bam(D, paths[b], b, tid_map[b], tid_map_len[b], range_lo ? range_lo[b] : 0,
+                            range_hi ? range_hi[b] : 0);
         if (rc) {
             const std::string msg = ctx->err;
             return bail(rc, msg);

@@ -182,6 +182,159 @@ def load_reads_multi(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads
     return MultiBatch([ReadBatch(c, d, ks, gid_of, stats) for c, d in zip(ctxs, dreads)], runs, tile_pos)
 
 
+class ShardedBatch(object):
+    """One library cut into contiguous genomic chunks, one per GPU: batches[k] holds only the records of chunk k
+    (+ halo), shards[k] the indices of the units (features / regions) counted there."""
+
+    def __init__(self, batches, shards, keyspace, gid_of, stats):
+        self.batches, self.shards = batches, shards
+        self.keyspace, self.gid_of, self.stats = keyspace, gid_of, stats
+
+    def close(self):
+        for b in self.batches:
+            if b is not None:
+                b.close()
+
+
+_INF_KEY = (1 << 40, 0)
+
+
+def load_reads_sharded(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, devices, unit_chrom, unit_beg, unit_end,
+                       span=1 << 20):
+    """The north star's multi-GPU split for real files: the BAM is cut at BGZF block boundaries into len(devices)
+    contiguous byte ranges; a unit (feature / region; 0-based [beg, end)) belongs to the chunk its start falls
+    into; every GPU inflates and parses only the blocks that can hold reads overlapping its units -- its own
+    range, extended by a halo of `span` bp to the left and to the end of its last unit to the right -- with the
+    device decoder.  What pysam's fetch gets from the .bai index is read off the file itself: the offsets of the
+    blocks (xg_bgzf_block_index) and the position of a block's first record (xg_bam_block_probe, binary search).
+    The halo is verified afterwards: no read of the library may span more than `span` bp (else the cut is redone
+    with the span that was seen).  Returns None when the files cannot be split this way (device decoder off,
+    records not aligned to blocks, BAMs with different contig lists, too many BAMs): the caller then gives every
+    GPU the whole batch (load_reads_multi)."""
+    from . import parallel
+    n_dev = len(devices)
+    if not device_decode_enabled() or n_dev < 2 or len(sam_fn_list) > 8:
+        return None
+    ctxs = [get_context(d) for d in devices]
+    ks = lib.KeySpace()
+    bam_refs = [lib.bam_references(fn) for fn in sam_fn_list]
+    if any([r[0] for r in refs] != [r[0] for r in bam_refs[0]] for refs in bam_refs[1:]):
+        return None
+    gid_of, tid_maps = build_tid_maps(bam_refs, list(chroms))
+    tid_of_gid = {int(g): t for t, g in enumerate(tid_maps[0]) if g >= 0}
+    index = []
+    for fn in sam_fn_list:
+        off, first, aligned = lib.bgzf_block_index(fn)
+        if not aligned:
+            return None
+        index.append((off, first))
+    probe_cache = {}
+
+    def block_key(b, i):
+        """(tid, pos) of the first record of block i of BAM b; the unplaced tail and the end sort last"""
+        off, _first = index[b]
+        if i >= len(off) - 1:
+            return _INF_KEY
+        k = probe_cache.get((b, i))
+        if k is None:
+            tid, pos = lib.bam_block_probe(sam_fn_list[b], off[i])
+            k = probe_cache[(b, i)] = _INF_KEY if tid < 0 else (tid, pos)
+        return k
+
+    def first_block_with(b, key, strictly_greater):
+        """first block of BAM b whose first record is >= key (or > key)"""
+        off, first = index[b]
+        lo, hi = first, len(off) - 1
+        while lo < hi:
+            mid = (lo + hi) // 2
+            k = block_key(b, mid)
+            if (k > key) if strictly_greater else (k >= key):
+                hi = mid
+            else:
+                lo = mid + 1
+        return lo
+
+    # cut keys from the largest BAM: equal shares of its bytes
+    b0 = int(np.argmax([index[b][0][-1] for b in range(len(sam_fn_list))]))
+    off0, first0 = index[b0]
+    cuts = [(-1, -1)]
+    for g in range(1, n_dev):
+        i = int(np.searchsorted(off0, off0[first0] + (off0[-1] - off0[first0]) * g // n_dev))
+        cuts.append(max(cuts[-1], block_key(b0, max(first0, min(i, len(off0) - 1)))))
+    cuts.append(_INF_KEY)
+    # units -> chunks by their start
+    import bisect
+    n_unit = len(unit_beg)
+    keys = []
+    shards = [[] for _ in range(n_dev)]
+    for u in range(n_unit):
+        g = gid_of.get(unit_chrom[u], -1)
+        t = tid_of_gid.get(g, -1) if unit_end[u] > unit_beg[u] >= 0 else -1
+        keys.append((t, int(unit_beg[u])))
+        shards[0 if t < 0 else max(0, bisect.bisect_right(cuts, (t, int(unit_beg[u]))) - 1)].append(u)
+    shards = [np.array(s, dtype=np.int64) for s in shards]
+
+    def decode_with(span_bp):
+        ranges = []
+        for k in range(n_dev):
+            lo_key, hi_key = cuts[k], cuts[k + 1]
+            live = [u for u in shards[k] if keys[u][0] >= 0]
+            if live:
+                t_min, s_min = min(keys[u] for u in live)
+                lo_key = min(lo_key, (t_min, max(0, s_min - span_bp)))
+                hi_key = max(hi_key, max((keys[u][0], int(unit_end[u])) for u in live))
+            per_bam = []
+            for b in range(len(sam_fn_list)):
+                off, first = index[b]
+                i_lo = max(first, first_block_with(b, lo_key, True) - 1)
+                i_hi = first_block_with(b, hi_key, False)
+                per_bam.append((int(off[i_lo]), int(off[max(i_lo, i_hi)])))
+            ranges.append(per_bam)
+
+        def one(k):
+            if all(hi <= lo for lo, hi in ranges[k]):
+                return None
+            return _device_decode_range(ctxs[k], sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, ks, ranges[k])
+        return parallel.run_on_devices(n_dev, one), ranges
+
+    for attempt in range(2):
+        devs, ranges = decode_with(span)
+        if any(d is False for d in devs):           # the device decoder declined
+            for d in devs:
+                if d:
+                    d[0].close()
+            return None
+        seen_span = max([d[1]["max_span"] for d in devs if d] or [0])
+        if seen_span <= span:
+            break
+        for d in devs:
+            if d:
+                d[0].close()
+        span = int(seen_span)
+    else:
+        return None
+    batches = [ReadBatch(c, d[0], ks, gid_of, d[1]) if d else None for c, d in zip(ctxs, devs)]     # None: empty chunk
+    live = [b for b in batches if b is not None]
+    stats = {"n_reads": sum(b.stats["n_reads"] for b in live),
+             "n_records_seen": sum(b.stats["n_records_seen"] for b in live),
+             "max_aln_len": max([b.stats["max_aln_len"] for b in live] or [0]),
+             "max_span": max([b.stats["max_span"] for b in live] or [0]),
+             "bytes": sum(b.stats["bytes"] for b in live), "decoder": "device, sharded",
+             "byte_ranges": ranges, "halo_bp": span}
+    return ShardedBatch(batches, shards, ks, gid_of, stats)
+
+
+def _device_decode_range(ctx, sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, keyspace, ranges):
+    """(dreads, stats), or False when the device decoder declines."""
+    res = ctx.decode_bams(sam_fn_list, tid_maps, cell_tag, umi_tag, want_seq, keyspace, ranges=ranges)
+    if res is None:
+        return False
+    dreads, seen = res
+    i = dreads.info()
+    return dreads, {"n_reads": i["n_reads"], "n_records_seen": seen, "max_aln_len": i["max_aln_len"],
+                    "max_span": i["max_span"], "bytes": i["bytes"], "decoder": "device"}
+
+
 def make_params(conf, max_aln_len, with_include):
     tab, incl_len = (None, 0)
     if with_include:

@@ -138,6 +138,13 @@ SYMBOLS = {
     "xg_synth_read_index": (C.c_int64, [C.POINTER(SynthParams), C.c_int32, C.c_int32]),
     "xg_write_bam": (C.c_int, [C.c_char_p, C.POINTER(Reads), C.c_int32, C.POINTER(C.c_char_p), c_i64p, _P,
                                C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32]),
+    "xg_decode_bams_device_range": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(c_i32p), c_i32p,
+                                              C.c_char_p, C.c_char_p, C.c_int32, _P, c_i64p, c_i64p,
+                                              C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "xg_bgzf_block_index": (C.c_int, [C.c_char_p, C.POINTER(c_i64p), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int32)]),
+    "xg_free_array": (None, [_P]),
+    "xg_bam_block_probe": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "xg_last_timing": (None, [_P, C.POINTER(C.c_double)]),
     "xg_version": (C.c_char_p, []),
 }
@@ -490,11 +497,13 @@ class Context(object):
         self._check(self.lib.xg_upload_reads(self.h, host_reads.ptr, C.byref(d)))
         return DeviceReads(self, d)
 
-    def decode_bams(self, paths, tid_maps, cell_tag, umi_tag, want_seq, keyspace=None):
+    def decode_bams(self, paths, tid_maps, cell_tag, umi_tag, want_seq, keyspace=None, ranges=None):
         """BGZF inflate + BAM parse on the device (xg_decode_bams_device).  Returns
         (DeviceReads, n_records_seen), or None when the files need the host decoder.
         keyspace: interns the cell / UMI values that do not pack into 63 bits (query names,
-        free-text barcodes); without it such files are left to the host decoder."""
+        free-text barcodes); without it such files are left to the host decoder.
+        ranges: [(lo, hi)] byte offsets of BGZF block starts per BAM -- only those blocks are decoded
+        (xg_decode_bams_device_range; see bgzf_block_index / bam_block_probe)."""
         n = len(paths)
         cpaths = (C.c_char_p * n)(*[p.encode() for p in paths])
         maps = [np.ascontiguousarray(m, dtype=np.int32) for m in tid_maps]
@@ -502,11 +511,16 @@ class Context(object):
         lens = np.array([len(m) for m in maps], dtype=np.int32)
         d = _P()
         seen = C.c_int64(0)
-        rc = self.lib.xg_decode_bams_device(self.h, n, cpaths, cmaps, as_ptr(lens, c_i32p),
-                                            cell_tag.encode() if cell_tag else None,
-                                            umi_tag.encode() if umi_tag else None,
-                                            1 if want_seq else 0, keyspace.h if keyspace is not None else None,
-                                            C.byref(d), C.byref(seen))
+        args = (self.h, n, cpaths, cmaps, as_ptr(lens, c_i32p), cell_tag.encode() if cell_tag else None,
+                umi_tag.encode() if umi_tag else None, 1 if want_seq else 0,
+                keyspace.h if keyspace is not None else None)
+        if ranges is None:
+            rc = self.lib.xg_decode_bams_device(*args, C.byref(d), C.byref(seen))
+        else:
+            lo = np.array([r[0] for r in ranges], dtype=np.int64)
+            hi = np.array([r[1] for r in ranges], dtype=np.int64)
+            rc = self.lib.xg_decode_bams_device_range(*args, as_ptr(lo, c_i64p), as_ptr(hi, c_i64p), C.byref(d),
+                                                      C.byref(seen))
         if rc == XG_E_UNSUPPORTED:
             self.decode_fallback_reason = self.lib.xg_last_error(self.h).decode()
             return None
@@ -639,6 +653,28 @@ class Context(object):
             self.close()
         except Exception:
             pass
+
+
+def bgzf_block_index(path):
+    """(offsets of every BGZF block + the file size, block of the first record, starts-at-a-block-boundary)."""
+    lib = load()
+    p, n, first, al = c_i64p(), C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    rc = lib.xg_bgzf_block_index(path.encode(), C.byref(p), C.byref(n), C.byref(first), C.byref(al))
+    if rc != 0:
+        raise XgError(rc, lib.xg_host_last_error().decode())
+    off = np.ctypeslib.as_array(p, shape=(n.value + 1,)).copy()
+    lib.xg_free_array(C.cast(p, _P))
+    return off, int(first.value), bool(al.value)
+
+
+def bam_block_probe(path, offset):
+    """(tid, pos) of the record at the beginning of the BGZF block at `offset`; tid -2: no record there."""
+    lib = load()
+    tid, pos = C.c_int32(0), C.c_int32(0)
+    rc = lib.xg_bam_block_probe(path.encode(), int(offset), C.byref(tid), C.byref(pos))
+    if rc != 0:
+        raise XgError(rc, lib.xg_host_last_error().decode())
+    return int(tid.value), int(pos.value)
 
 
 def write_bam(path, host_reads, contigs, keyspace=None, cell_tag="CB", umi_tag="UB", level=1, n_threads=0,

@@ -89,8 +89,21 @@ def merge_coo(parts, shard_rows, n_rows):
     return row[order].astype(np.int32), col[order].astype(np.int32), val[order].astype(np.int32)
 
 
+def emulated():
+    """$XCLTK_B200_EMULATE_SHARDS=1: all shards on device 0, one after the other -- the sharded path on a
+    one-GPU box (tests)."""
+    import os
+    return os.environ.get("XCLTK_B200_EMULATE_SHARDS", "0") not in ("0", "", "no", "false")
+
+
+def device_list(n):
+    return (0,) * n if emulated() else tuple(range(n))
+
+
 def run_on_devices(n, fn):
     """fn(k) for k in range(n), one host thread per device (ctypes calls release the GIL)."""
+    if emulated():
+        return [fn(k) for k in range(n)]
     out, err = [None] * n, [None] * n
 
     def work(k):

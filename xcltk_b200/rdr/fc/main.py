@@ -267,8 +267,13 @@ def count_features(conf, batch=None):
         chroms = list(dict.fromkeys(r.chrom for r in regs))
         threads = engine.n_decode_threads(conf.nproc)
         if n_dev > 1:
-            batch = engine.load_reads_multi(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False,
-                                            threads, devices=tuple(range(n_dev)))
+            # one library cut into genomic chunks: every GPU decodes only the blocks of its chunk (+ halo) ...
+            batch = engine.load_reads_sharded(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False,
+                                              parallel.device_list(n_dev), [r.chrom for r in regs],
+                                              [r.start - 1 for r in regs], [r.end - 1 for r in regs])
+            if batch is None:      # ... or, when the files cannot be split, every GPU gets the whole batch
+                batch = engine.load_reads_multi(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False,
+                                                threads, devices=parallel.device_list(n_dev))
         else:
             batch = engine.load_reads(conf.sam_fn_list, chroms, conf.cell_tag, conf.umi_tag, False, threads,
                                       host_only=True)
@@ -277,7 +282,22 @@ def count_features(conf, batch=None):
         cell_keys = None
         if conf.use_barcodes():
             cell_keys = np.array([batch.keyspace.encode(b) for b in conf.barcodes], dtype=np.uint64)
-        if isinstance(batch, engine.MultiBatch):
+        if isinstance(batch, engine.ShardedBatch):
+            shards = batch.shards
+            empty = (np.zeros(0, np.int32),) * 3
+
+            def one(k):
+                b, sh = batch.batches[k], shards[k]
+                if b is None or len(sh) == 0:
+                    return empty + (None,)
+                params = engine.make_params(conf, b.stats["max_aln_len"], with_include=True)
+                r, c, v, _ = b.ctx.basefc(b.dreads, gid[sh], beg[sh], end[sh], cell_keys, len(conf.samples), params)
+                return np.array(r), np.array(c), np.array(v), b.ctx.timing()
+            parts = parallel.run_on_devices(len(shards), one)
+            row, col, val = parallel.merge_coo([p[:3] for p in parts], shards, len(regs))
+            conf.last_timing = next((p[3] for p in parts if p[3] is not None), [0.0] * 16)
+            conf.shard_sizes = [len(s) for s in shards]
+        elif isinstance(batch, engine.MultiBatch):
             load, total = parallel.reads_before(gid, beg, batch.runs, batch.pos_of_run)
             shards = parallel.partition(gid, beg, load, total, len(batch.batches))
 
