@@ -80,3 +80,36 @@ def test_baf_many_cell_bams_by_query_name(gpu_ctx, tmp_path, monkeypatch):
     compare_dirs(exp, got, BAF_FILES)
     with open(os.path.join(got, "xcltk.DP.mtx")) as fp:
         assert int(fp.read().split("\n", 3)[2].split("\t")[2]) > 500
+
+
+def test_sharded_file_counting_equals_unsharded_at_scale(gpu_ctx, tmp_path, monkeypatch):
+    """3M reads over chr19-22 with spliced reads (5 kb introns) and genes up to 1 Mb: the library split into 6 byte
+    ranges gives the matrix of the unsplit file, and no shard decodes much more than its share."""
+    from xcltk_b200 import engine, lib, workload
+    from xcltk_b200.rdr.fc import main as rdr_main
+    chroms = {"19", "20", "21", "22"}
+    w = workload.make_basefc_workload(gpu_ctx, 3000000, 800, 33472, seed=77, chroms=chroms)
+    host = w.dreads.download()
+    names = [c for c in workload.HG38_CHROMS if c in chroms]
+    bam = str(tmp_path / "lib.bam")
+    lib.write_bam(bam, host, [("chr" + c, workload.HG38_LEN[c]) for c in names], None, "CB", "UB", level=1, n_threads=4)
+    host.close()
+    ks = lib.KeySpace()
+    bc, ft = str(tmp_path / "bc.tsv"), str(tmp_path / "ft.tsv")
+    open(bc, "w").write("".join(ks.decode(int(k)) + "\n" for k in w.cell_keys))
+    open(ft, "w").write("".join("%s\t%d\t%d\t%s\n" % f for f in w.feats))
+    w.dreads.close()
+    one = str(tmp_path / "one")
+    assert rdr_main.fc_wrapper(bam, bc, ft, one, ncores=4) == 0
+    monkeypatch.setenv("XCLTK_B200_GPUS", "6")
+    monkeypatch.setenv("XCLTK_B200_EMULATE_SHARDS", "1")
+    seen = []
+    real = engine.load_reads_sharded
+    monkeypatch.setattr(engine, "load_reads_sharded", lambda *a, **kw: seen.append(real(*a, **kw)) or seen[-1])
+    six = str(tmp_path / "six")
+    assert rdr_main.fc_wrapper(bam, bc, ft, six, ncores=4) == 0
+    compare_dirs(one, six, RDR_FILES)
+    st = seen[0].stats
+    sizes = [sum(hi - lo for lo, hi in per) for per in st["byte_ranges"]]
+    assert max(sizes) < 0.35 * os.path.getsize(bam) and st["max_span"] <= st["halo_bp"]
+    assert st["n_reads"] < 1.25 * 3000000
