@@ -293,13 +293,23 @@ int xg_download_reads(xg_ctx *ctx, const xg_dreads *d, xg_reads **out) {
     }
     xg_run *runs = (xg_run *)pinned_alloc(sizeof(xg_run) * (d->h_runs.size() + 1));
     xg_tile *tiles = (xg_tile *)pinned_alloc(sizeof(xg_tile) * (d->h_tiles.size() + 1));
-    o->bufs.push_back(runs);
-    o->bufs.push_back(tiles);
+    if (runs) o->bufs.push_back(runs);
+    if (tiles) o->bufs.push_back(tiles);
+    auto drop = [&](int code, const std::string &msg) {      // the owner and what it holds go away on every error path
+        cudaStreamSynchronize(ctx->stream);
+        for (void *q : o->bufs) pinned_free(q);
+        delete o;
+        return ctx->fail(code, msg);
+    };
+    const bool seq_ok = !(d->seq_off && d->seq) || (o->r.seq_off && o->r.seq);
+    if (!runs || !tiles || !o->r.pos_end || !o->r.fmq || !o->r.cig_off || !o->r.keys || !o->r.cigar || !seq_ok)
+        return drop(XG_E_NOMEM, "out of pinned host memory for the downloaded batch");
     memcpy(runs, d->h_runs.data(), sizeof(xg_run) * d->h_runs.size());
     memcpy(tiles, d->h_tiles.data(), sizeof(xg_tile) * d->h_tiles.size());
     o->r.runs = runs;
     o->r.tiles = tiles;
-    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) return drop(XG_E_CUDA, std::string("D2H reads: ") + cudaGetErrorString(ce));
     *out = &o->r;
     return XG_OK;
 }

@@ -780,7 +780,11 @@ int write_rows_impl(const char *path, int32_t n_rows_in, const int64_t *row_beg,
                 Text &b = (*bufs)[s - s0];
                 int64_t n_ent = 0;
                 for (int32_t r = r0; r < r1; r++) n_ent += row_cnt[r];
-                b.p.reset(new char[(size_t)n_ent * 36 + 16]);
+                b.p.reset(new (std::nothrow) char[(size_t)n_ent * 36 + 16]);      // no exception may leave a worker thread
+                if (!b.p) {
+                    ok = false;
+                    return;
+                }
                 char *p = b.p.get();
                 for (int32_t r = r0; r < r1; r++)
                     for (int64_t k = row_beg[r]; k < row_beg[r] + row_cnt[r]; k++) {

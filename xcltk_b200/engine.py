@@ -177,8 +177,10 @@ def load_reads_multi(sam_fn_list, chroms, cell_tag, umi_tag, want_seq, n_threads
              "max_span": host.max_span, "bytes": host.nbytes()}
     runs = list(host.runs)
     tile_pos = _tile_pos(runs, host.tiles())
-    dreads = parallel.run_on_devices(len(ctxs), lambda k: ctxs[k].upload(host))
-    host.close()
+    try:
+        dreads = parallel.run_on_devices(len(ctxs), lambda k: ctxs[k].upload(host))
+    finally:
+        host.close()
     return MultiBatch([ReadBatch(c, d, ks, gid_of, stats) for c, d in zip(ctxs, dreads)], runs, tile_pos)
 
 

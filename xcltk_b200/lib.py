@@ -165,9 +165,15 @@ def load(rebuild=True):
     if rebuild:
         try:
             path = _build.build()
-        except Exception:
-            if not os.path.exists(path):
+        except Exception as ex:
+            # A library that is older than its sources must not stand in for them: only when there is no compiler
+            # (a box that got the prebuilt file) and the file exists is it loaded as it is.
+            import shutil
+            have_nvcc = bool(os.environ.get("NVCC") or shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"))
+            if have_nvcc or not os.path.exists(path):
                 raise
+            import logging
+            logging.getLogger(__name__).warning("no compiler here (%s); loading the prebuilt %s", ex, path)
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)           # AttributeError = missing export: fail loudly

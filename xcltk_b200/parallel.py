@@ -118,8 +118,24 @@ def run_on_devices(n, fn):
         t.join()
     for e in err:
         if e is not None:
+            for o in out:              # what the other devices produced must not outlive the failure
+                _close_result(o)
             raise e
     return out
+
+
+def _close_result(o):
+    """close() whatever a per-device worker returned (a batch, a tuple holding one ...)."""
+    if o is None:
+        return
+    if hasattr(o, "close"):
+        try:
+            o.close()
+        except Exception:
+            pass
+    elif isinstance(o, (tuple, list)):
+        for x in o:
+            _close_result(x)
 
 
 def n_devices(requested=None):
