@@ -188,10 +188,7 @@ class Batch(object):
         self.n_reads = self.fc.n_reads + self.baf.n_reads          # records this GPU holds (halos included)
         self.keep = None
 
-    def keep_mask(self, totals):
-        # min_count = 1, min_maf = 0 (the values xcltk baf passes, baf/pipeline.py:355)
-        t = totals
-        return ((t[:, 0] | t[:, 1] | t[:, 2] | t[:, 3] | t[:, 4]) > 0).view(np.uint8)      # counts are >= 0: sum >= 1 <=> any bit set
+    # SNP filter of the baf half: min_count = 1, min_maf = 0 (the values xcltk baf passes, baf/pipeline.py:355)
 
     def step_device(self, checksum=False):
         ctx, fc, bf = self.ctx, self.fc, self.baf
@@ -202,15 +199,12 @@ class Batch(object):
         w1 = time.perf_counter()
         t_fc = ctx.timing()
         launches += int(t_fc[2])
-        totals, st = ctx.baf_pileup(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, reuse_totals=True)
+        # pileup -> SNP filter (min_count 1, min_maf 0, on the device) -> region count: one library call
+        ad, dp, oth = ctx.baf_fc(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, bf.snp_ref,
+                                 bf.snp_alt, 1, 0.0, bf.reg_ptr, bf.reg_snp, bf.hap_of, True)
         w2 = time.perf_counter()
-        t_p = ctx.timing()
-        launches += int(t_p[2])
-        ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, self.keep_mask(totals), True)
-        w3 = time.perf_counter()
-        t_c = ctx.timing()
+        t_p = t_c = ctx.timing()
         launches += int(t_c[2])
-        st.close()
         chk = None
         if checksum:                 # rows numbered as in the whole matrix, so that the shards add up
             r, c, v = seg.to_sorted()
@@ -218,7 +212,7 @@ class Batch(object):
             for k, m in enumerate((ad, dp, oth)):
                 chk = (chk + matrix_checksum(bf.feat_index[m[0]] + (k + 1) * (1 << 24), m[1], m[2])) % (1 << 64)
         w4 = time.perf_counter()
-        return dict(nnz=seg.nnz, checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w3 - w2), 1e3 * (w4 - w3)],
+        return dict(nnz=seg.nnz, checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w4 - w2)],
                     launches=launches, t_fc=t_fc, t_pileup=t_p, t_count=t_c, baf_nnz=len(ad[2]) + len(dp[2]) + len(oth[2]),
                     out_bytes=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])))
 
@@ -231,13 +225,12 @@ class Batch(object):
         seg = ctx.basefc_host(self.h_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
         h2d_fc = int(ctx.timing()[13])
         d_bf = ctx.map_reads(self.h_baf)          # zero-copy: 8 B/read over PCIe, rest on demand
-        totals, st = ctx.baf_pileup(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, reuse_totals=True)
+        ad, dp, oth = ctx.baf_fc(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, bf.snp_ref,
+                                 bf.snp_alt, 1, 0.0, bf.reg_ptr, bf.reg_snp, bf.hap_of, True)
         ctx.timing_pairs = ctx.timing()[6]            # (read, SNP) pairs: records fetched on demand
-        ad, dp, oth = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, self.keep_mask(totals), True)
-        st.close()
         d_bf.close()
         return dict(h2d=h2d_fc + 8 * self.h_baf.n + 72 * int(self.ctx.timing_pairs),
-                    d2h=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])) + totals.nbytes +
+                    d2h=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])) +
                     12 * len(fc.gid) + 8 * (3 * (len(bf.reg_ptr) - 1) + 3))  # packed entries + row_beg/row_cnt | col + val + row_ptr
 
     def oracle_parity(self, n_threads):
@@ -261,9 +254,8 @@ class Batch(object):
         seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
         g_fc = seg.to_sorted()
         ok_fc = all(np.array_equal(a, b) for a, b in zip(g_fc, o_fc))
-        totals, st = ctx.baf_pileup(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, reuse_totals=True)
-        g_baf = ctx.baf_count(st, bf.reg_ptr, bf.reg_snp, bf.hap_of, self.keep_mask(totals), True)
-        st.close()
+        g_baf = ctx.baf_fc(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, bf.snp_ref, bf.snp_alt,
+                           1, 0.0, bf.reg_ptr, bf.reg_snp, bf.hap_of, True)
         ok_baf = all(np.array_equal(g[k], o[k]) for g, o in zip(g_baf, o_baf) for k in range(3))
         return dict(basefc=bool(ok_fc), baf=bool(ok_baf), nnz=int(len(o_fc[2])),
                     baf_nnz=int(sum(len(o[2]) for o in o_baf)),
@@ -674,11 +666,11 @@ def main():
                 "detail": {"basefc_device_ms": float(np.mean([i["t_fc"][0] for i in infos])),
                            "basefc_epoch_span_ms": float(np.mean([i["t_fc"][3] for i in infos])),
                            "basefc_count_kernel_ms": t_cnt_ms,
-                           "baf_pileup_ms": float(np.mean([i["t_pileup"][0] for i in infos])),
+                           "baf_device_ms": float(np.mean([i["t_count"][0] for i in infos])),
                            "baf_scan_kernel_ms": float(np.mean([i["t_pileup"][1] for i in infos])),
-                           "baf_count_ms": float(np.mean([i["t_count"][0] for i in infos])),
+                           "baf_host_ms_pileup_queued_done": [float(np.mean([i["t_count"][k] for i in infos])) for k in (8, 9, 10)],
                            "basefc_nnz": int(nnz_all), "checksum": checksum, "reads_held_by_all_gpus": held_reads,
-                           "wall_ms_basefc_pileup_count_checksum": [float(x) for x in np.mean(
+                           "wall_ms_basefc_baf_checksum": [float(x) for x in np.mean(
                                [i["wall_ms"] for i in infos], axis=0)],
                            "basefc_host_ms_index_windows_plan_upload_call": [float(x) for x in info["t_fc"][8:13]],
                            "basefc_reads_per_s_kernels_only": batch.fc.n_reads / (

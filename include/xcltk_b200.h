@@ -290,7 +290,7 @@ typedef struct {
 typedef struct xg_baf_state xg_baf_state;
 int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *reads, const xg_snps *snps,
                   const xg_barcodes *cells, const xg_params *par,
-                  int64_t *totals, xg_baf_state **state);
+                  int64_t *totals /* may be NULL: not copied out */, xg_baf_state **state);
 /* baf phase 2: replaces fc_fet1() aggregation + emit (baf/fc/core.py:143-194, 84-113).
  *   hap_of[8*i + code] for SNP i and base code (0..4 = A,C,G,T,N; 5 = other / IUPAC) is the
  *   region haplotype index 0 / 1, or 2 for "other allele", as SNP.get_region_allele_index
@@ -302,6 +302,22 @@ int xg_baf_count(xg_ctx *ctx, xg_baf_state *state, int32_t n_regions, const int6
                  const int32_t *reg_snp, const uint8_t *hap_of, const uint8_t *keep,
                  int32_t no_dup_hap, xg_coo **ad, xg_coo **dp, xg_coo **oth);
 void xg_baf_state_free(xg_ctx *ctx, xg_baf_state *state);
+/* baf, one call: xg_baf_pileup -> plp_snp's SNP filter ON THE DEVICE -> xg_baf_count; what one fc_features worker
+ * of the reference does for its regions (baf/fc/core.py:42-247).  The filter (baf/fc/core.py:238-246): SNP i is
+ * skipped iff  sum(tcount) < min_count  or  min(tcount[ref_idx[i]], tcount[alt_idx[i]]) < sum(tcount) * min_maf,
+ * evaluated in IEEE double exactly as Python evaluates int-with-float (counts < 2^53); ref_idx / alt_idx are
+ * MCount.base_idx of the SNP's alleles (0..4 = A,C,G,T,N; baf/fc/mcount.py:178).  The per-SNP totals never leave
+ * the device unless `totals` (n_snps x 5 int64) is given; `keep_out` (n_snps bytes) receives the filter if given.
+ * Same results as the three-step sequence with the filter evaluated by the caller; two host synchronisations
+ * and 8 MB of D2H less per call.                                                                             */
+typedef struct {
+    const uint8_t *ref_idx, *alt_idx;
+    double min_count, min_maf;
+} xg_snp_filter;
+int xg_baf_fc(xg_ctx *ctx, const xg_dreads *reads, const xg_snps *snps, const xg_barcodes *cells,
+              const xg_params *par, const xg_snp_filter *filt, int32_t n_regions, const int64_t *reg_ptr,
+              const int32_t *reg_snp, const uint8_t *hap_of, int32_t no_dup_hap, int64_t *totals,
+              uint8_t *keep_out, xg_coo **ad, xg_coo **dp, xg_coo **oth);
 
 /* Synthetic 10x-style records generated directly in HBM (bench / tests; no reference
  * counterpart -- SURVEY.md 8(d) C3 allows device-side generation for kernel-only runs).  */

@@ -18,6 +18,7 @@ import os
 import random
 import shutil
 import sys
+import time
 import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -82,7 +83,9 @@ def finish_case(case_dir, case):
     os.makedirs(exp)
     for run in case["runs"]:
         out = os.path.join(exp, run["name"])
+        t_ref = time.perf_counter()
         ret = run_reference(case_dir, case, run, out)
+        print("  reference wall time for %s: %.1f s" % (run["name"], time.perf_counter() - t_ref))
         with open(os.path.join(out, "RETCODE"), "w") as fp:
             fp.write("%d\n" % ret)
         left = sorted(f for f in os.listdir(out) if "pickle" in f or f[-1].isdigit())

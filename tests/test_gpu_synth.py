@@ -195,6 +195,40 @@ def test_baf_matches_oracle(gpu_ctx, baf_batch, min_count, min_maf, no_dup):
     assert len(dp[2]) > 100
     for got, exp in zip((ad, dp, oth), o):
         assert all(np.array_equal(g, e) for g, e in zip(got[:3], exp))
+    # the same through the one-call entry point, SNP filter evaluated on the device (xg_baf_fc)
+    f_ad, f_dp, f_oth, f_tot, f_keep = gpu_ctx.baf_fc(
+        b.dreads, b.snp_gid, b.snp_pos, b.cell_keys, 1000, gpu_params(conf, False), b.snp_ref, b.snp_alt, min_count,
+        min_maf, b.reg_ptr, b.reg_snp, b.hap_of, no_dup, want_totals=True, want_keep=True)
+    assert np.array_equal(f_tot, totals) and np.array_equal(f_keep, keep)
+    for got, exp in zip((f_ad, f_dp, f_oth), o):
+        assert all(np.array_equal(g, e) for g, e in zip(got[:3], exp))
+
+
+@pytest.mark.parametrize("min_count,min_maf", [(0, 0.0), (2.5, 0.0), (1, 1.0 / 3.0), (4, 0.5), (1, 0.1 + 0.2), (10 ** 9, 0.0)])
+def test_baf_device_snp_filter_is_pythons_arithmetic(gpu_ctx, baf_batch, min_count, min_maf):
+    """plp_snp's filter (baf/fc/core.py:238-246) on the device == Python ints against a float, SNP by SNP: thresholds
+    that are not representable (1/3, 0.1 + 0.2), a float min_count, ties (minor == cnt * maf), nothing / everything kept."""
+    b = baf_batch
+    p = gpu_params(Conf(min_include=0), False)
+    out = gpu_ctx.baf_fc(b.dreads, b.snp_gid, b.snp_pos, b.cell_keys, 1000, p, b.snp_ref, b.snp_alt, min_count, min_maf,
+                         b.reg_ptr, b.reg_snp, b.hap_of, True, want_totals=True, want_keep=True)
+    totals, keep = out[3], out[4]
+    exp = np.zeros(len(keep), dtype=np.uint8)
+    for i in range(len(keep)):
+        t = [int(x) for x in totals[i]]
+        cnt = sum(t)
+        if cnt < min_count:
+            continue
+        if min(t[b.snp_ref[i]], t[b.snp_alt[i]]) < cnt * min_maf:
+            continue
+        exp[i] = 1
+    assert np.array_equal(keep, exp)
+    assert (min_count != 0) or keep.all()
+    st_tot, st = gpu_ctx.baf_pileup(b.dreads, b.snp_gid, b.snp_pos, b.cell_keys, 1000, p)
+    ref = gpu_ctx.baf_count(st, b.reg_ptr, b.reg_snp, b.hap_of, exp, True)
+    st.close()
+    for x, y in zip(out[:3], ref):
+        assert all(np.array_equal(u, v) for u, v in zip(x[:3], y[:3]))
 
 
 def test_basefc_streamed_from_host_equals_resident(gpu_ctx, fc_batch, monkeypatch):

@@ -30,6 +30,8 @@ for want_seq in (False, True):
               "extract %.1f ms, alloc %.0f ms, trim %.0f ms, interned %d (%d distinct) in %.0f ms, call %.0f ms" % (want_seq, dt, seen / dt / 1e6, t[8], t[4], t[2], t[3], t[9], t[10], int(t[6]), int(t[11]), t[7], t[12]),
               flush=True)
         dev.close()
+    if os.environ.get("PROF_SKIP_HOST"):
+        continue
     t0 = time.time()
     ks = lib.KeySpace()
     host = lib.decode_bams([path], maps, "CB", umi, want_seq, ks, threads)

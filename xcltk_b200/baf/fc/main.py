@@ -234,14 +234,15 @@ def _count_shard(conf, ctx, dreads, keyspace, gid_of, max_aln_len, regs, snps):
     if conf.use_barcodes():
         cell_keys = np.array([keyspace.encode(b) for b in conf.barcodes], dtype=np.uint64)
     params = engine.make_params(conf, max_aln_len, with_include=False)
-    totals, state = ctx.baf_pileup(dreads, gid, pos0.astype(np.int32), cell_keys, len(conf.samples), params,
-                                   reuse_totals=True)
-    t1 = ctx.timing()
-    keep = snp_filter(conf, sub, totals)
-    out = ctx.baf_count(state, reg_ptr, np.array(reg_snp, dtype=np.int32), hap_table(sub), keep, conf.no_dup_hap)
-    t2 = ctx.timing()
-    state.close()
-    return out, [t1, t2]
+    # pileup -> plp_snp's filter (on the device, IEEE double as Python evaluates it; `snp_filter` above is the same
+    # test on the host, kept for the tests) -> region count, one library call
+    n = len(sub)
+    ref_i = np.fromiter((BASE_IDX[s.ref] for s in sub), dtype=np.uint8, count=n)
+    alt_i = np.fromiter((BASE_IDX[s.alt] for s in sub), dtype=np.uint8, count=n)
+    out = ctx.baf_fc(dreads, gid, pos0.astype(np.int32), cell_keys, len(conf.samples), params, ref_i, alt_i,
+                     conf.min_count, conf.min_maf, reg_ptr, np.array(reg_snp, dtype=np.int32), hap_table(sub),
+                     conf.no_dup_hap)
+    return out, [ctx.timing()]
 
 
 def count_regions(conf, regs, batch=None):

@@ -576,7 +576,7 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
                              const xg_barcodes *cells, const xg_params *par, int64_t *totals,
                              xg_baf_state **state) {
     if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
-    if (!rd || !snps || !cells || !par || !totals || !state)
+    if (!rd || !snps || !cells || !par || !state)          // totals == NULL: they stay on the device (xg_baf_fc)
         return ctx->fail(XG_E_ARG, "xg_baf_pileup: null argument");
     if (!rd->seq || !rd->seq_off) return ctx->fail(XG_E_ARG, "xg_baf_pileup: reads were decoded without sequences");
     if (cells->n_samples <= 0 || cells->n_samples >= (1 << 24))
@@ -751,24 +751,30 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
         cudaMemcpyAsync(st->pr_umi, P.pr_umi, n_pairs * 8, cudaMemcpyDeviceToDevice, ctx->stream);
     }
     cudaEventRecord(ctx->ev[3], ctx->stream);
-    unsigned long long *h_tot = (unsigned long long *)ctx->pinned_get(sizeof(unsigned long long) * ((size_t)snps->n * 5 + 1));
-    if (!h_tot) {
-        xg_baf_state_free(ctx, st);
-        return ctx->fail(XG_E_NOMEM, "out of pinned host memory");
+    unsigned long long *h_tot = nullptr;
+    if (totals) {
+        h_tot = (unsigned long long *)ctx->pinned_get(sizeof(unsigned long long) * ((size_t)snps->n * 5 + 1));
+        if (!h_tot) {
+            xg_baf_state_free(ctx, st);
+            return ctx->fail(XG_E_NOMEM, "out of pinned host memory");
+        }
     }
     cudaEventRecord(ctx->ev[4], ctx->stream);
-    cudaMemcpyAsync(h_tot, d_totals, sizeof(unsigned long long) * (size_t)snps->n * 5,
-                    cudaMemcpyDeviceToHost, ctx->stream);
+    if (totals)
+        cudaMemcpyAsync(h_tot, d_totals, sizeof(unsigned long long) * (size_t)snps->n * 5, cudaMemcpyDeviceToHost,
+                        ctx->stream);
     cudaEventRecord(ctx->ev[5], ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
-        ctx->pinned_put(h_tot);
+        if (h_tot) ctx->pinned_put(h_tot);
         xg_baf_state_free(ctx, st);
         return ctx->fail(XG_E_CUDA, std::string("baf pileup: ") + cudaGetErrorString(e));
     }
     ctx->timing[9] = ms_since(t_call);          // ... + kernels + totals on the host
-    memcpy(totals, h_tot, sizeof(int64_t) * (size_t)snps->n * 5);       // counts < 2^31: the same bits as int64
-    ctx->pinned_put(h_tot);
+    if (totals) {
+        memcpy(totals, h_tot, sizeof(int64_t) * (size_t)snps->n * 5);   // counts < 2^31: the same bits as int64
+        ctx->pinned_put(h_tot);
+    }
     ctx->timing[10] = ms_since(t_call);         // ... + copy into the caller's array
     float t_all = 0, t_d2h = 0;
     cudaEventElapsedTime(&t_all, ctx->ev[0], ctx->ev[3]);
@@ -782,11 +788,12 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
     return XG_OK;
 }
 
-extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, const int64_t *reg_ptr,
-                            const int32_t *reg_snp, const uint8_t *hap_of, const uint8_t *keep,
-                            int32_t no_dup_hap, xg_coo **ad, xg_coo **dp, xg_coo **oth) {
+// keep: the caller's SNP filter (host array) -- or keep_dev: the one k_baf_snp_filter left on the device
+static int baf_count_impl(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, const int64_t *reg_ptr,
+                          const int32_t *reg_snp, const uint8_t *hap_of, const uint8_t *keep, const uint8_t *keep_dev,
+                          int32_t no_dup_hap, xg_coo **ad, xg_coo **dp, xg_coo **oth) {
     if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
-    if (!st || n_regions < 0 || !reg_ptr || !hap_of || !keep || !ad || !dp || !oth)
+    if (!st || n_regions < 0 || !reg_ptr || !hap_of || (!keep && !keep_dev) || !ad || !dp || !oth)
         return ctx->fail(XG_E_ARG, "xg_baf_count: bad argument");
     XG_CUDA(cudaSetDevice(ctx->device));
     for (double &t : ctx->timing) t = 0;
@@ -849,7 +856,10 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
     R.snp_reg_ptr = (const int64_t *)ctx->scratch["bf_sr_ptr"].p;
     R.snp_reg = (const int32_t *)ctx->scratch["bf_sr"].p;
     if ((rc = upload_arr(ctx, hap_of, (size_t)n_snps * 8, "bf_hap_of", &R.hap_of))) return rc;
-    if ((rc = upload_arr(ctx, keep, (size_t)n_snps, "bf_keep", &R.keep))) return rc;
+    if (keep_dev)
+        R.keep = keep_dev;
+    else if ((rc = upload_arr(ctx, keep, (size_t)n_snps, "bf_keep", &R.keep)))
+        return rc;
     XG_GET(reg_cnt, int32_t, "bf_reg_cnt", n_regions + 1);
     XG_GET(reg_cur, int32_t, "bf_reg_cur", n_regions + 1);
     XG_GET(reg_log_off, int64_t, "bf_reg_log_off", n_regions + 2);
@@ -905,13 +915,9 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
     }
     const double ms_kernels = ms_since(t_call);
     xg_coo **outs[3] = {ad, dp, oth};
-    const char *tags[3] = {"bfad", "bfdp", "bfot"};
-    for (int wh = 0; wh < 3; wh++)
-        if ((rc = xg_staging_to_coo(ctx, tags[wh], n_regions, n_cols, seg_base + (size_t)wh * n_regions,
-                                    seg_nnz + (size_t)wh * n_regions, st_col + (size_t)wh * combos,
-                                    st_val + (size_t)wh * combos, outs[wh], &launches)))
-            return rc;
-    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((rc = xg_staging_to_coo3(ctx, "bf3", n_regions, n_cols, seg_base, seg_nnz, st_col, st_val, (int64_t)combos, outs,
+                                 &launches)))
+        return rc;
     float t_all = 0;
     cudaEventElapsedTime(&t_all, ctx->ev[0], ctx->ev[3]);
     ctx->timing[0] = t_all;
@@ -919,5 +925,75 @@ extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, co
     ctx->timing[6] = (double)combos;
     ctx->timing[9] = ms_kernels;                // ... + kernels queued (one sync for the candidate count)
     ctx->timing[10] = ms_since(t_call);         // ... + the three results on the host
+    return XG_OK;
+}
+
+extern "C" int xg_baf_count(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, const int64_t *reg_ptr,
+                            const int32_t *reg_snp, const uint8_t *hap_of, const uint8_t *keep,
+                            int32_t no_dup_hap, xg_coo **ad, xg_coo **dp, xg_coo **oth) {
+    if (ctx && !keep) return ctx->fail(XG_E_ARG, "xg_baf_count: bad argument");
+    return baf_count_impl(ctx, st, n_regions, reg_ptr, reg_snp, hap_of, keep, nullptr, no_dup_hap, ad, dp, oth);
+}
+
+// plp_snp's filter (baf/fc/core.py:238-246) on the device totals: skip iff `snp_cnt < min_count` or
+// `min(ref_cnt, alt_cnt) < snp_cnt * min_maf` -- Python's int-with-float arithmetic is IEEE double on values
+// < 2^53, which is what is evaluated here (one rounded multiply, no contraction).
+static __global__ void k_baf_snp_filter(const unsigned long long *tot, const uint8_t *ref_i, const uint8_t *alt_i,
+                                        int32_t n, double min_count, double min_maf, uint8_t *keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long *t = tot + (size_t)i * 5;
+    const unsigned long long cnt = t[0] + t[1] + t[2] + t[3] + t[4];
+    const unsigned long long minor = min(t[ref_i[i]], t[alt_i[i]]);
+    const bool skip = ((double)cnt < min_count) || ((double)minor < __dmul_rn((double)cnt, min_maf));
+    keep[i] = skip ? 0 : 1;
+}
+
+extern "C" int xg_baf_fc(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *snps, const xg_barcodes *cells,
+                         const xg_params *par, const xg_snp_filter *filt, int32_t n_regions, const int64_t *reg_ptr,
+                         const int32_t *reg_snp, const uint8_t *hap_of, int32_t no_dup_hap, int64_t *totals,
+                         uint8_t *keep_out, xg_coo **ad, xg_coo **dp, xg_coo **oth) {
+    if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
+    if (!snps || !filt || !filt->ref_idx || !filt->alt_idx) return ctx->fail(XG_E_ARG, "xg_baf_fc: null argument");
+    for (int32_t i = 0; i < snps->n; i++)
+        if (filt->ref_idx[i] > 4 || filt->alt_idx[i] > 4) return ctx->fail(XG_E_ARG, "xg_baf_fc: allele index out of range");
+    const auto t_call = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+    };
+    xg_baf_state *st = nullptr;
+    int rc = xg_baf_pileup(ctx, rd, snps, cells, par, totals, &st);
+    if (rc) return rc;
+    double tp[16];
+    for (int k = 0; k < 16; k++) tp[k] = ctx->timing[k];
+    const double ms_pileup = ms_since(t_call);
+    const uint8_t *d_ref = nullptr, *d_alt = nullptr;
+    uint8_t *d_keep = (uint8_t *)ctx->get("bf_keep", (size_t)snps->n + 16);
+    if (!d_keep || upload_arr(ctx, filt->ref_idx, (size_t)snps->n, "bf_ref_i", &d_ref) ||
+        upload_arr(ctx, filt->alt_idx, (size_t)snps->n, "bf_alt_i", &d_alt)) {
+        xg_baf_state_free(ctx, st);
+        return ctx->fail(XG_E_CUDA, "xg_baf_fc: out of device memory");
+    }
+    if (snps->n > 0)
+        k_baf_snp_filter<<<(snps->n + 255) / 256, 256, 0, ctx->stream>>>(
+            (const unsigned long long *)ctx->scratch["bf_totals"].p, d_ref, d_alt, snps->n, filt->min_count, filt->min_maf,
+            d_keep);
+    if (keep_out && snps->n > 0)          // pageable destination: the copy has landed when the call returns
+        cudaMemcpyAsync(keep_out, d_keep, (size_t)snps->n, cudaMemcpyDeviceToHost, ctx->stream);
+    rc = baf_count_impl(ctx, st, n_regions, reg_ptr, reg_snp, hap_of, nullptr, d_keep, no_dup_hap, ad, dp, oth);
+    xg_baf_state_free(ctx, st);
+    if (rc) return rc;
+    // timing of the fused call: device ms and launches of both halves; [8] / [9] / [10] = host ms at the end of the
+    // pileup / when the count kernels were queued / at the end
+    const double tc9 = ctx->timing[9];
+    ctx->timing[7] = ctx->timing[6];            // (region, cell, UMI) candidates
+    ctx->timing[6] = tp[6];                     // (read, SNP) pairs
+    ctx->timing[0] += tp[0];
+    ctx->timing[1] = tp[1];
+    ctx->timing[2] += tp[2] + 1;
+    ctx->timing[4] += tp[4];
+    ctx->timing[8] = ms_pileup;
+    ctx->timing[9] = ms_pileup + tc9;
+    ctx->timing[10] = ms_since(t_call);
     return XG_OK;
 }

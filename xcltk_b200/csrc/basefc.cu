@@ -222,18 +222,19 @@ struct EpochPlan {
     std::vector<uint32_t> tbl_cap;      // slots of its set (0 = segment feature, or never active)
     std::vector<uint32_t> log_cap;      // candidate reads: entries of its log / pair words of its segment
     uint64_t pool_bytes = 0;
-    std::vector<int32_t> zero_ptr, fin_ptr, fin_set_ptr;    // per epoch ranges
+    std::vector<int32_t> zero_ptr, fin_ptr, fin_set_ptr, fin_big_ptr;    // per epoch ranges
     std::vector<uint64_t> zseg_off, zseg_pre;
-    std::vector<int32_t> fin_feat, fin_set;           // features ending in the epoch: segments / sets
+    std::vector<int32_t> fin_feat, fin_set, fin_big;  // features ending in the epoch: segments / sets / big segments
     int64_t staging_cap = 0;
     int64_t n_seg_feat = 0, n_set_feat = 0;
 };
 
 // seg_max: features with at most this many candidate reads collect pair words in a segment
 // (0: every feature keeps a set)
+// seg_big: a segment feature with more candidate reads is reduced by a CTA of FS_BIG_THREADS threads
 int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const std::vector<int32_t> &tlo,
               const std::vector<int32_t> &thi, int32_t n_tiles, int32_t n_cols, int32_t epoch_tiles,
-              uint64_t seg_max, EpochPlan &pl) {
+              uint64_t seg_max, uint64_t seg_big, EpochPlan &pl) {
     size_t m = cand.size();
     pl.epoch_tiles = epoch_tiles;
     pl.n_epochs = std::max(1, (n_tiles + epoch_tiles - 1) / epoch_tiles);
@@ -285,6 +286,7 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
     pl.zero_ptr.assign((size_t)pl.n_epochs + 1, 0);
     pl.fin_ptr.assign((size_t)pl.n_epochs + 1, 0);
     pl.fin_set_ptr.assign((size_t)pl.n_epochs + 1, 0);
+    pl.fin_big_ptr.assign((size_t)pl.n_epochs + 1, 0);
     for (int32_t e = 0; e < pl.n_epochs; e++) {
         uint64_t pre = 0;
         for (int32_t j : starts[(size_t)e]) {
@@ -312,10 +314,12 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
                 bucket[std::min(b, 32)].push_back(j);
             }
             for (int b = 32; b >= 0; b--)
-                for (int32_t j : bucket[b]) (pl.tbl_cap[(size_t)j] ? pl.fin_set : pl.fin_feat).push_back(j);
+                for (int32_t j : bucket[b])
+                    (pl.tbl_cap[(size_t)j] ? pl.fin_set : cand[(size_t)j] > seg_big ? pl.fin_big : pl.fin_feat).push_back(j);
         }
         pl.fin_ptr[(size_t)e + 1] = (int32_t)pl.fin_feat.size();
         pl.fin_set_ptr[(size_t)e + 1] = (int32_t)pl.fin_set.size();
+        pl.fin_big_ptr[(size_t)e + 1] = (int32_t)pl.fin_big.size();
     }
     return XG_OK;
 }
@@ -1023,13 +1027,16 @@ __global__ void __launch_bounds__(256) k_zero_segments(uint8_t *pool, const uint
 // that a range's words fit the table and its cells the counters; ranges go through phase 2 one after
 // the other.  A range that still holds too many words (skewed cells) is swept once per hash sub-partition,
 // with twice the sub-partitions after a table overflow.
-#define FS_THREADS 256
-#define FS_WARPS (FS_THREADS / 32)
+#define FS_THREADS 256                // CTA of the features of ordinary size, four or five to an SM
+#define FS_BIG_THREADS 1024           // CTA of a big feature (its passes are bound by the loads one CTA keeps in flight,
+                                      // and by a barrier + a memory round trip per column range)
 #define FS_TBL SEG_TBL_SLOTS          // table slots (64-bit)
 #define FS_CAP SEG_PART_WORDS         // words a table pass should hold (40 % load); also the rank counters
 #define FS_REG 7                      // words a thread keeps in registers (FS_REG * FS_THREADS >= FS_CAP)
 #define FS_RANGES 1024                // column ranges of a heavy feature (counters live in the idle table)
-static_assert(FS_REG * FS_THREADS >= FS_CAP, "a light feature must fit the registers of its CTA");
+#define FS_TBL_LOG2 12                // ordinary CTAs: 4096-slot table (FS_TBL)
+#define FS_BIG_TBL_LOG2 14            // big CTAs: 16384 slots -- a quarter of the ranges, each a barrier and a round trip
+static_assert((1 << FS_TBL_LOG2) == FS_TBL, "table size");
 
 __device__ __forceinline__ uint64_t pair_hash(unsigned long long pw) {
     uint64_t h = pw * 0x9E3779B97F4A7C15ULL;
@@ -1039,17 +1046,18 @@ __device__ __forceinline__ uint64_t pair_hash(unsigned long long pw) {
 }
 
 struct FsShared {
-    uint32_t warp_tot[FS_WARPS];
+    uint32_t warp_tot[32];
     long long base_s;
     int ovf_s;
+    int ovf_b[2];                     // ... of the fast range passes, one per counter bank
     int f_s[2];                       // this / the next work item (fetched one ahead)
     uint32_t range_off[FS_RANGES + 1];
 };
 
 // table of a pass over n words: a power of two >= 2.5 n, 64 .. FS_TBL slots
-__device__ __forceinline__ uint32_t fs_table_size(uint32_t n) {
+__device__ __forceinline__ uint32_t fs_table_size(uint32_t n, uint32_t tbl_max = FS_TBL) {
     uint32_t tsz = 64;
-    while (tsz < FS_TBL && tsz * 2 < n * 5) tsz <<= 1;
+    while (tsz < tbl_max && tsz * 2 < n * 5) tsz <<= 1;
     return tsz;
 }
 
@@ -1074,24 +1082,57 @@ __device__ __forceinline__ bool fs_insert(unsigned long long *tbl, uint32_t tsz,
     return false;
 }
 
-__global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
+// The same for the ranges of a heavy feature, which go through the table one after the other WITHOUT clearing it:
+// every word carries its range in the upper bits of its cell, so an entry of an earlier range is as good as an
+// empty slot and is overwritten in place.  (The table is cleared once per feature.)
+template <int TBL_LOG2>
+__device__ __forceinline__ bool fs_insert_range(unsigned long long *tbl, unsigned long long pw, uint64_t h, uint32_t rg,
+                                                int wshift, uint32_t *cnt, uint32_t r) {
+    constexpr uint32_t TBL = 1u << TBL_LOG2;
+    uint32_t slot = (uint32_t)((h * 0x9E3779B97F4A7C15ULL) >> (64 - TBL_LOG2));
+    for (uint32_t probe = 0; probe < 96;) {
+        const unsigned long long old = *(volatile unsigned long long *)&tbl[slot];
+        if (old == pw) return true;
+        if (old != 0ULL && (((uint32_t)old & 0xffffffu) >> wshift) == rg) {     // a word of this range: next slot
+            slot = (slot + 1) & (TBL - 1);
+            probe++;
+            continue;
+        }
+        if (atomicCAS(&tbl[slot], old, pw) == old) {
+            atomicAdd(&cnt[r], 1u);
+            return true;
+        }
+        // lost the slot to another word of this range (or to this very word): look at it again
+    }
+    return false;
+}
+
+// 48 registers: five ordinary CTAs fit an SM, and an SM that holds a big CTA has room for an ordinary one
+template <int THREADS, int TBL_LOG2>
+__global__ void __maxnreg__(48) k_basefc_finalize_segs(
     const uint8_t *pool, const FeatDesc *fdesc, const uint32_t *seg_cur, const int32_t *sf_row,
     const int32_t *fin_feat, int32_t n_fin, int32_t n_cols, unsigned int *work, unsigned long long *cursor,
     int64_t *seg_base, int32_t *seg_nnz, int32_t *st_col, int32_t *st_val) {
     extern __shared__ __align__(16) uint8_t fin_smem[];
+    // table slots; words a table pass should hold (40 % load: the light / heavy limit); cells of a range on the fast
+    // path = one counter bank; the counters (a light feature uses both banks as one)
+    constexpr uint32_t TBL = 1u << TBL_LOG2, CAP = TBL * 2 / 5, RCELLS = TBL / 4, CNT = 2 * RCELLS;
+    constexpr uint32_t LIGHT = CAP < FS_REG * THREADS ? CAP : FS_REG * THREADS;     // words a CTA keeps in registers
+    static_assert(LIGHT >= SEG_PART_WORDS, "a feature without a scratch half must be light");
     const int bm_words = (n_cols + 31) >> 5;
-    unsigned long long *tbl = reinterpret_cast<unsigned long long *>(fin_smem);      // FS_TBL
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(tbl + FS_TBL);                       // FS_CAP rank counters
-    uint32_t *bitmap = cnt + FS_CAP;                                                  // bm_words
+    unsigned long long *tbl = reinterpret_cast<unsigned long long *>(fin_smem);      // TBL
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(tbl + TBL);                       // CNT rank counters
+    uint32_t *bitmap = cnt + CNT;                                                  // bm_words
     uint32_t *pre = bitmap + bm_words;                                                // bm_words + 1
     __shared__ FsShared F;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         F.ovf_s = 0;
+        F.ovf_b[0] = F.ovf_b[1] = 0;
         F.f_s[0] = (int)atomicAdd(work, 1u);
     }
-    for (int c = threadIdx.x; c < bm_words; c += FS_THREADS) bitmap[c] = 0;
-    for (int c = threadIdx.x; c < FS_CAP; c += FS_THREADS) cnt[c] = 0;
+    for (int c = threadIdx.x; c < bm_words; c += THREADS) bitmap[c] = 0;
+    for (int c = threadIdx.x; c < CNT; c += THREADS) cnt[c] = 0;
 
     for (int it = 0;; it++) {
         __syncthreads();             // the previous feature is out; bitmap and counters are clean
@@ -1102,17 +1143,17 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
         const FeatDesc fd = fdesc[j];
         const uint32_t n = seg_cur[j];
         const unsigned long long *seg = (const unsigned long long *)(pool + fd.blk_off);
-        const bool light = n <= FS_CAP;
+        const bool light = n <= LIGHT;
 
-        // range width of a heavy feature: a power of two (>= 32 cells) with about 3/4 FS_CAP expected words
+        // range width of a heavy feature: a power of two (>= 32 cells) with about 3/4 CAP expected words
         int wshift = 5;
         uint32_t n_rng = 1;
         uint32_t *rc = reinterpret_cast<uint32_t *>(tbl);             // the table is idle: counters, then cursors
         if (!light) {
-            while (wshift < 10 && ((uint64_t)n << (wshift + 1)) <= (uint64_t)(FS_CAP * 3 / 4) * (uint64_t)n_cols) wshift++;
+            while (wshift < TBL_LOG2 - 2 && ((uint64_t)n << (wshift + 1)) <= (uint64_t)(CAP * 3 / 4) * (uint64_t)n_cols) wshift++;
             while (((n_cols - 1) >> wshift) + 1 > FS_RANGES) wshift++;      // very many cells: wider ranges, rank windows
             n_rng = (uint32_t)((n_cols - 1) >> wshift) + 1;
-            for (uint32_t q = threadIdx.x; q < n_rng; q += FS_THREADS) rc[q] = 0;
+            for (uint32_t q = threadIdx.x; q < n_rng; q += THREADS) rc[q] = 0;
             __syncthreads();
         }
 
@@ -1122,11 +1163,11 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
         if (light) {
 #pragma unroll
             for (int q = 0; q < FS_REG; q++) {
-                const uint32_t s = threadIdx.x + (uint32_t)q * FS_THREADS;
+                const uint32_t s = threadIdx.x + (uint32_t)q * THREADS;
                 pw[q] = s < n ? seg[s] : 0ULL;
             }
-            const uint32_t tsz0 = fs_table_size(n);
-            for (uint32_t s = threadIdx.x; s < tsz0; s += FS_THREADS) tbl[s] = 0ULL;
+            const uint32_t tsz0 = fs_table_size(n, TBL);
+            for (uint32_t s = threadIdx.x; s < tsz0; s += THREADS) tbl[s] = 0ULL;
 #pragma unroll
             for (int q = 0; q < FS_REG; q++)
                 if (pw[q]) {
@@ -1134,11 +1175,11 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                     atomicOr(&bitmap[col >> 5], 1u << (col & 31));
                 }
         } else {
-            for (uint32_t s0 = threadIdx.x; s0 < n; s0 += FS_THREADS * 4) {
+            for (uint32_t s0 = threadIdx.x; s0 < n; s0 += THREADS * 4) {
                 unsigned long long v[4];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const uint32_t s = s0 + (uint32_t)q * FS_THREADS;
+                    const uint32_t s = s0 + (uint32_t)q * THREADS;
                     v[q] = s < n ? seg[s] : 0ULL;
                 }
 #pragma unroll
@@ -1153,7 +1194,7 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
         __syncthreads();
         // ---- prefix popcounts: pre[k] = set bits in words [0, k); the row's size; its place in the staging area
         {
-            const int per = (bm_words + FS_THREADS - 1) / FS_THREADS;
+            const int per = (bm_words + THREADS - 1) / THREADS;
             const int k0 = threadIdx.x * per, k1 = min(bm_words, k0 + per);
             uint32_t mine = 0;
             for (int k = k0; k < k1; k++) mine += (uint32_t)__popc(bitmap[k]);
@@ -1170,7 +1211,7 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                 pre[k] = run;
                 run += (uint32_t)__popc(bitmap[k]);
             }
-            if (threadIdx.x == FS_THREADS - 1) {
+            if (threadIdx.x == THREADS - 1) {
                 pre[bm_words] = run;
                 const int32_t row = sf_row[j];
                 const long long b = run ? (long long)atomicAdd(cursor, (unsigned long long)run) : 0;
@@ -1184,7 +1225,7 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
 
         if (light) {
             // ---- phase 2 from the registers, then the row
-            const uint32_t tsz = fs_table_size(n);
+            const uint32_t tsz = fs_table_size(n, TBL);
             const int shift = 64 - (31 - __clz((int)tsz));
             // the table is at most 40 % full: with the whole table as probe limit an insert cannot fail
 #pragma unroll
@@ -1194,7 +1235,7 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                     fs_insert(tbl, tsz, shift, pw[q], pair_hash(pw[q]), cnt, fs_rank(bitmap, pre, col), tsz);
                 }
             __syncthreads();
-            for (int k = threadIdx.x; k < bm_words; k += FS_THREADS) {
+            for (int k = threadIdx.x; k < bm_words; k += THREADS) {
                 uint32_t bits = bitmap[k];
                 if (!bits) continue;
                 uint32_t r = pre[k];
@@ -1213,7 +1254,7 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
 
         // ---- heavy feature: split by column range into the scratch half of the block
         {   // exclusive prefix over the n_rng counters (F.warp_tot was read before the last barrier)
-            const int per = (int)((n_rng + FS_THREADS - 1) / FS_THREADS);
+            const int per = (int)((n_rng + THREADS - 1) / THREADS);
             const uint32_t k0 = threadIdx.x * (uint32_t)per, k1 = min(n_rng, k0 + (uint32_t)per);
             uint32_t mine = 0;
             for (uint32_t k = k0; k < k1; k++) mine += rc[k];
@@ -1232,15 +1273,15 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                 rc[k] = run;
                 run += c;
             }
-            if (threadIdx.x == FS_THREADS - 1) F.range_off[n_rng] = n;
+            if (threadIdx.x == THREADS - 1) F.range_off[n_rng] = n;
         }
         __syncthreads();
         unsigned long long *scr = const_cast<unsigned long long *>(seg) + ((((size_t)fd.log_cap) + 1) & ~(size_t)1);
-        for (uint32_t s0 = threadIdx.x; s0 < n; s0 += FS_THREADS * 4) {
+        for (uint32_t s0 = threadIdx.x; s0 < n; s0 += THREADS * 4) {
             unsigned long long v[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const uint32_t s = s0 + (uint32_t)q * FS_THREADS;
+                const uint32_t s = s0 + (uint32_t)q * THREADS;
                 v[q] = s < n ? seg[s] : 0ULL;
             }
 #pragma unroll
@@ -1248,7 +1289,23 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                 if (v[q]) scr[atomicAdd(&rc[(uint32_t)(v[q] & 0xffffffULL) >> wshift], 1u)] = v[q];
         }
         __syncthreads();
-        // ---- the ranges, one after the other: [clear table] sync [insert] sync [row part + counters back to zero]
+        // ---- the table (it held the range cursors) is cleared once; the row's cells go out in the same breath
+        for (uint32_t s2 = threadIdx.x; s2 < TBL; s2 += THREADS) tbl[s2] = 0ULL;
+        for (int k = threadIdx.x; k < bm_words; k += THREADS) {
+            uint32_t bits = bitmap[k];
+            uint32_t r = pre[k];
+            while (bits) {
+                const int bpos = __ffs(bits) - 1;
+                bits &= bits - 1;
+                st_col[base + r] = (k << 5) + bpos;
+                r++;
+            }
+        }
+        __syncthreads();
+        // ---- the ranges, one after the other.  Fast path (the range's words fit a table pass, its cells a counter
+        // bank): [insert into bank b] sync [bank b -> the row's counts, coalesced, and back to zero]; the next
+        // range inserts into the other bank meanwhile, so a range costs ONE barrier.
+        uint32_t bank = 0;
         for (uint32_t rg = 0; rg < n_rng; rg++) {
             const uint32_t p0 = F.range_off[rg], m = F.range_off[rg + 1] - p0;
             if (m == 0) continue;
@@ -1256,22 +1313,55 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
             const uint32_t k_lo = c0 >> 5, k_hi = (c1 + 31) >> 5;
             const uint32_t rank0 = pre[k_lo];
             const uint32_t nz_r = pre[k_hi] - rank0;
-            // cells of the range that do not fit the counters are taken in windows of FS_CAP ranks
-            for (uint32_t win = 0; win < nz_r; win += FS_CAP) {
-                uint32_t n_sub = (m + FS_CAP - 1) / FS_CAP;
+            bool slow = m > CAP || nz_r > RCELLS;
+            if (!slow) {
+                uint32_t *cb = cnt + bank * RCELLS;
+                for (uint32_t s0 = threadIdx.x; s0 < m; s0 += THREADS * 4) {
+                    unsigned long long v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t s2 = s0 + (uint32_t)q * THREADS;
+                        v[q] = s2 < m ? scr[p0 + s2] : 0ULL;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (!v[q]) continue;
+                        const uint32_t r = fs_rank(bitmap, pre, (uint32_t)(v[q] & 0xffffffULL)) - rank0;
+                        if (!fs_insert_range<TBL_LOG2>(tbl, v[q], pair_hash(v[q]), rg, wshift, cb, r)) F.ovf_b[bank] = 1;
+                    }
+                }
+                __syncthreads();
+                if (!F.ovf_b[bank]) {       // (the flag of the OTHER bank may already be written by the next range)
+                    for (uint32_t r = threadIdx.x; r < nz_r; r += THREADS) {
+                        st_val[base + rank0 + r] = (int32_t)cb[r];
+                        cb[r] = 0;
+                    }
+                    bank ^= 1;
+                    continue;
+                }
+                // 96 probes were not enough (never with a sane hash): forget the attempt, take the careful path
+                __syncthreads();
+                for (uint32_t r = threadIdx.x; r < RCELLS; r += THREADS) cb[r] = 0;
+                if (threadIdx.x == 0) F.ovf_b[bank] = 0;
+                slow = true;
+            }
+            // ---- careful path: [clear table] sync [insert] sync per hash sub-partition, rank windows of CAP cells
+            __syncthreads();                 // both banks are idle from here on
+            for (uint32_t win = 0; win < nz_r; win += CAP) {
+                uint32_t n_sub = (m + CAP - 1) / CAP;
                 while (true) {
-                    const uint32_t tsz = fs_table_size(m / n_sub + 1);
+                    const uint32_t tsz = fs_table_size(m / n_sub + 1, TBL);
                     const int shift = 64 - (31 - __clz((int)tsz));
                     for (uint32_t sub = 0; sub < n_sub; sub++) {
-                        __syncthreads();             // the previous pass (or the previous range's row part) is done
-                        for (uint32_t s = threadIdx.x; s < tsz; s += FS_THREADS) tbl[s] = 0ULL;
+                        __syncthreads();             // the previous pass (or the previous window's row part) is done
+                        for (uint32_t s2 = threadIdx.x; s2 < tsz; s2 += THREADS) tbl[s2] = 0ULL;
                         __syncthreads();
-                        for (uint32_t s0 = threadIdx.x; s0 < m; s0 += FS_THREADS * 4) {
+                        for (uint32_t s0 = threadIdx.x; s0 < m; s0 += THREADS * 4) {
                             unsigned long long v[4];
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
-                                const uint32_t s = s0 + (uint32_t)q * FS_THREADS;
-                                v[q] = s < m ? scr[p0 + s] : 0ULL;
+                                const uint32_t s2 = s0 + (uint32_t)q * THREADS;
+                                v[q] = s2 < m ? scr[p0 + s2] : 0ULL;
                             }
 #pragma unroll
                             for (int q = 0; q < 4; q++) {
@@ -1279,7 +1369,7 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                                 const uint64_t h = pair_hash(v[q]);
                                 if (n_sub > 1 && (uint32_t)(((h & 0xffffffffULL) * n_sub) >> 32) != sub) continue;
                                 const uint32_t r = fs_rank(bitmap, pre, (uint32_t)(v[q] & 0xffffffULL)) - rank0 - win;
-                                if (r >= FS_CAP) continue;                       // another window of this range
+                                if (r >= CAP) continue;                       // another window of this range
                                 if (!fs_insert(tbl, tsz, shift, v[q], h, cnt, r, min(tsz, 96u))) F.ovf_s = 1;
                             }
                         }
@@ -1288,30 +1378,24 @@ __global__ void __launch_bounds__(FS_THREADS, 5) k_basefc_finalize_segs(
                     if (!F.ovf_s) break;
                     // a pass overflowed the table: forget the window's counts, sweep again with finer sub-partitions
                     __syncthreads();
-                    for (uint32_t c = threadIdx.x; c < FS_CAP; c += FS_THREADS) cnt[c] = 0;
+                    for (uint32_t c = threadIdx.x; c < CAP; c += THREADS) cnt[c] = 0;
                     if (threadIdx.x == 0) F.ovf_s = 0;
                     n_sub *= 2;
                 }
-                // the window's part of the row; its counters go back to zero as they are read
-                for (uint32_t k = k_lo + threadIdx.x; k < k_hi; k += FS_THREADS) {
-                    uint32_t bits = bitmap[k];
-                    uint32_t r = pre[k];
-                    while (bits) {
-                        const int bpos = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        const uint32_t rr = r - rank0 - win;
-                        if (rr < FS_CAP) {
-                            st_col[base + r] = (int32_t)((k << 5) + (uint32_t)bpos);
-                            st_val[base + r] = (int32_t)cnt[rr];
-                            cnt[rr] = 0;
-                        }
-                        r++;
-                    }
+                // the window's counts; the counters go back to zero as they are read
+                const uint32_t n_w = min(nz_r - win, (uint32_t)CAP);
+                for (uint32_t r = threadIdx.x; r < n_w; r += THREADS) {
+                    st_val[base + rank0 + win + r] = (int32_t)cnt[r];
+                    cnt[r] = 0;
                 }
             }
+            // the table holds what the last pass left: the fast path must not take those entries for duplicates of a
+            // later range's words -- they carry THIS range's number, which no later range has; nothing to do.
+            __syncthreads();
+            bank = 0;
         }
         __syncthreads();
-        for (int k = threadIdx.x; k < bm_words; k += FS_THREADS) bitmap[k] = 0;
+        for (int k = threadIdx.x; k < bm_words; k += THREADS) bitmap[k] = 0;
     }
 }
 
@@ -1622,10 +1706,17 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     if (const char *e = getenv("XG_SEG_MAX")) seg_max = (uint64_t)atoll(e);
     EpochPlan pl;
     t_ph = now();
-    if ((rc = make_plan(ctx, cand, tlo, thi, rd->n_tiles, n_cols, epoch_tiles, seg_mode ? seg_max : 0, pl))) return rc;
+    // The reduction of a feature is one CTA's work and its passes are bound by the loads that CTA keeps in flight:
+    // the few features with very many reads (a long tail in expression data) would be the critical path of their
+    // epoch.  They get CTAs of 1024 threads, launched beside the ordinary ones.
+    uint64_t seg_big = 49152;
+    if (const char *e = getenv("XG_SEG_BIG")) seg_big = (uint64_t)atoll(e);
+    if (((size_t)10 << FS_BIG_TBL_LOG2) + (size_t)(2 * ((n_cols + 31) / 32) + 1) * 4 + sizeof(FsShared) + 1280 > 200 * 1024)
+        seg_big = ~0ull;                      // so many cells that the big CTA's shared memory does not fit: no big CTAs
+    if ((rc = make_plan(ctx, cand, tlo, thi, rd->n_tiles, n_cols, epoch_tiles, seg_mode ? seg_max : 0, seg_big, pl))) return rc;
     const double ms_plan = ms_since(t_ph);
     t_ph = now();
-    const int32_t *d_fin_feat = nullptr, *d_fin_set = nullptr;
+    const int32_t *d_fin_feat = nullptr, *d_fin_set = nullptr, *d_fin_big = nullptr;
     const uint64_t *d_zoff = nullptr, *d_zpre = nullptr;
     std::vector<FeatDesc> fdesc(m);
     std::vector<uint32_t> segoff16(m);
@@ -1643,6 +1734,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     }
     if ((rc = upload_vec(ctx, pl.fin_feat, "fx_fin_feat", &d_fin_feat))) return rc;
     if ((rc = upload_vec(ctx, pl.fin_set, "fx_fin_set", &d_fin_set))) return rc;
+    if ((rc = upload_vec(ctx, pl.fin_big, "fx_fin_big", &d_fin_big))) return rc;
     if ((rc = upload_vec(ctx, pl.zseg_off, "fx_zseg_off", &d_zoff))) return rc;
     if ((rc = upload_vec(ctx, pl.zseg_pre, "fx_zseg_pre", &d_zpre))) return rc;
     if (par->min_incl_tab) {
@@ -1673,10 +1765,11 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_GET(st_col, int32_t, "fx_st_col", pl.staging_cap + 1);
     XG_GET(st_val, int32_t, "fx_st_val", pl.staging_cap + 1);
     XG_GET(cursor, unsigned long long, "fx_cursor", 2);
-    XG_GET(fin_work, unsigned int, "fx_fin_work", 3 * (pl.n_epochs + 1) + 4);
+    XG_GET(fin_work, unsigned int, "fx_fin_work", 4 * (pl.n_epochs + 1) + 4);
     unsigned int *cnt_work = fin_work + pl.n_epochs + 1;          // tile counters of the counting launches
     unsigned int *set_work = fin_work + 2 * (pl.n_epochs + 1);    // work counters of the set finalize launches
-    unsigned int *d_flags = fin_work + 3 * (pl.n_epochs + 1);
+    unsigned int *big_work = fin_work + 3 * (pl.n_epochs + 1);    // ... of the big-segment finalize launches
+    unsigned int *d_flags = fin_work + 4 * (pl.n_epochs + 1);
     XG_GET(seg_cur, uint32_t, "fx_seg_cur", m + 1);
     P.pool = pool;
     P.seg_cur = seg_cur;
@@ -1687,8 +1780,26 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     // shared memory of the finalize kernels.  Segments: dedup table, rank counters, bitmap over the cells and
     // its prefix popcounts.  Sets: histogram (+ bitmap) over the cells -- all cells if they fit.
     const int bm_words = (n_cols + 31) / 32;
-    const size_t segs_bytes = (size_t)FS_TBL * 8 + (size_t)FS_CAP * 4 + (size_t)(2 * bm_words + 1) * 4;
-    XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_bytes));
+    auto segs_smem = [&](int tbl_log2) {
+        return ((size_t)8 << tbl_log2) + ((size_t)2 << tbl_log2) + (size_t)(2 * bm_words + 1) * 4;    // table, counters, bitmap + prefix
+    };
+    int big_variant = 0;      // EXPERIMENT
+    if (const char *e = getenv("XG_BIG_VARIANT")) big_variant = atoi(e);
+    const int bv_log2[6] = {14, 13, 14, 13, 12, 12}, bv_thr[6] = {1024, 512, 512, 1024, 1024, 512};
+    const size_t segs_bytes = segs_smem(FS_TBL_LOG2), big_bytes = segs_smem(bv_log2[big_variant]);
+    XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<FS_THREADS, FS_TBL_LOG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)segs_bytes));
+    // big CTAs need the large table; with so many cells that it does not fit, big features go the ordinary way
+    const bool big_ok = big_bytes + sizeof(FsShared) + 1280 <= 200 * 1024;
+    if (big_ok)
+    {
+        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<1024, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(14)));
+        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<512, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(13)));
+        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<512, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(14)));
+        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<1024, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(13)));
+        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<1024, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(12)));
+        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<512, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(12)));
+    }
     const int segs_ctas_per_sm = std::max(1, std::min(8, (int)(224 * 1024 / (segs_bytes + sizeof(FsShared) + 1280))));
     int32_t hist_cols = std::min(n_cols, 40 * 1024);
     if (const char *e = getenv("XG_HIST_COLS")) hist_cols = std::max(32, std::min(n_cols, atoi(e)));
@@ -1709,20 +1820,21 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     // another on one stream and only the result copy runs beside them.
     bool overlap = false;
     if (const char *e = getenv("XG_OVERLAP")) overlap = pl.n_epochs > 1 && atoi(e) != 0;
-    if ((overlap || src) && !ctx->aux[0])
+    const bool fork_big = !pl.fin_big.empty();
+    if ((overlap || src || fork_big) && !ctx->aux[0])
         for (auto &st : ctx->aux) XG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     if (src && !ctx->copy_stream) XG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    while ((int32_t)ctx->ev_pool.size() < 5 * pl.n_epochs + 1) {
+    while ((int32_t)ctx->ev_pool.size() < 6 * pl.n_epochs + 1) {
         cudaEvent_t ev;
         XG_CUDA(cudaEventCreate(&ev));
         ctx->ev_pool.push_back(ev);
     }
-    auto EV = [&](int kind, int32_t e) { return ctx->ev_pool[(size_t)5 * e + kind]; };   // 0 Z, 1 S, 2 C, 3 F, 4 H2D
-    cudaEvent_t ev_init = ctx->ev_pool[(size_t)5 * pl.n_epochs];
+    auto EV = [&](int kind, int32_t e) { return ctx->ev_pool[(size_t)6 * e + kind]; };   // 0 Z, 1 S, 2 C, 3 F, 4 H2D, 5 big F
+    cudaEvent_t ev_init = ctx->ev_pool[(size_t)6 * pl.n_epochs];
     XG_CUDA(cudaMemsetAsync(seg_nnz, 0, sizeof(int32_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(seg_base, 0, sizeof(int64_t) * (size_t)(n_rows + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(cursor, 0, 16, ctx->stream));
-    XG_CUDA(cudaMemsetAsync(fin_work, 0, sizeof(unsigned int) * (size_t)(3 * (pl.n_epochs + 1) + 4), ctx->stream));
+    XG_CUDA(cudaMemsetAsync(fin_work, 0, sizeof(unsigned int) * (size_t)(4 * (pl.n_epochs + 1) + 4), ctx->stream));
     XG_CUDA(cudaMemsetAsync(seg_cur, 0, sizeof(uint32_t) * (m + 1), ctx->stream));
     launches += 6;
     cudaEventRecord(ev_init, ctx->stream);
@@ -1806,9 +1918,33 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
             cudaStreamWaitEvent(st_f, EV(2, e), 0);
             if (e > 0) cudaStreamWaitEvent(st_f, EV(2, e - 1), 0);
         }
+        // big segments first, on a stream of their own: their few large CTAs take their SMs before the ordinary
+        // finalize CTAs fill the rest, and both kernels run side by side
+        const int32_t n_big = pl.fin_big_ptr[(size_t)e + 1] - pl.fin_big_ptr[(size_t)e];
+        if (n_big > 0) {
+            cudaStream_t st_b = overlap ? st_f : ctx->aux[1];
+            if (!overlap) cudaStreamWaitEvent(st_b, EV(2, e), 0);
+            const int per_sm = std::max(1, std::min((int)(220 * 1024 / (big_bytes + sizeof(FsShared) + 1280)), 2048 * 3 / 4 / bv_thr[big_variant]));
+            const int gridb = std::min(n_big, 148 * per_sm);
+#define BV(T, L)                                                                                                             \
+    k_basefc_finalize_segs<T, L><<<gridb, T, big_bytes, st_b>>>(pool, P.fdesc, seg_cur, d_sf_row,                               \
+                                                                 d_fin_big + pl.fin_big_ptr[(size_t)e], n_big, n_cols,          \
+                                                                 big_work + e, cursor, seg_base, seg_nnz, st_col, st_val)
+            switch (big_variant) {
+                case 0: BV(1024, 14); break;
+                case 1: BV(512, 13); break;
+                case 2: BV(512, 14); break;
+                case 3: BV(1024, 13); break;
+                case 4: BV(1024, 12); break;
+                default: BV(512, 12); break;
+            }
+            launches++;
+            XG_DBG("k_basefc_finalize_segs<big>");
+            if (!overlap) cudaEventRecord(EV(5, e), st_b);
+        }
         if (n_fin > 0) {
             const int grid = std::min(n_fin, 148 * segs_ctas_per_sm);
-            k_basefc_finalize_segs<<<grid, FS_THREADS, segs_bytes, st_f>>>(
+            k_basefc_finalize_segs<FS_THREADS, FS_TBL_LOG2><<<grid, FS_THREADS, segs_bytes, st_f>>>(
                 pool, P.fdesc, seg_cur, d_sf_row, d_fin_feat + pl.fin_ptr[(size_t)e], n_fin, n_cols, fin_work + e,
                 cursor, seg_base, seg_nnz, st_col, st_val);
             launches++;
@@ -1824,6 +1960,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         }
         // the snapshot is a store into mapped host memory, not a copy: a D2H of 8 bytes would queue
         // behind the result copies on the copy engine and stall the finalize stream with them
+        if (n_big > 0 && !overlap) cudaStreamWaitEvent(st_f, EV(5, e), 0);      // join: the epoch's rows are all reserved
         if (h_cur) k_snapshot_cursor<<<1, 1, 0, st_f>>>(cursor, d_cur + e);
         cudaEventRecord(EV(3, e), st_f);
     }

@@ -171,6 +171,15 @@ struct xg_ctx {
     int64_t bf_snp_sorted = 0;
     bool bf_sr_valid = false;              // ... and of the inverted region -> SNP lists of xg_baf_count
     uint64_t bf_sr_hash = 0;
+    // the two most recent barcode tables (basefc and baf alternate with different cell lists): scratch "bc_slots0/1"
+    struct BcCache {
+        bool valid = false;
+        uint64_t hash = 0;
+        uint64_t used = 0;
+        const void *slots = nullptr;
+        uint32_t mask = 0, shift = 0;
+    } bc_cache[2];
+    uint64_t bc_clock = 0;
     // cache of the last interval index built by xg_basefc (owned by basefc.cu)
     void *fx_cache = nullptr;
     void (*fx_cache_free)(void *) = nullptr;

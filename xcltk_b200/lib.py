@@ -76,6 +76,10 @@ class Snps(C.Structure):
     _fields_ = [("n", C.c_int32), ("gid", c_i32p), ("pos", c_i32p)]
 
 
+class SnpFilter(C.Structure):
+    _fields_ = [("ref_idx", c_u8p), ("alt_idx", c_u8p), ("min_count", C.c_double), ("min_maf", C.c_double)]
+
+
 class SynthParams(C.Structure):
     _fields_ = [("n_reads", C.c_int64), ("n_cells", C.c_int32), ("read_len", C.c_int32),
                 ("want_seq", C.c_int32), ("seed", C.c_uint64),
@@ -134,6 +138,9 @@ SYMBOLS = {
                                C.POINTER(C.POINTER(Coo)), C.POINTER(C.POINTER(Coo)),
                                C.POINTER(C.POINTER(Coo))]),
     "xg_baf_state_free": (None, [_P, _P]),
+    "xg_baf_fc": (C.c_int, [_P, _P, C.POINTER(Snps), C.POINTER(Barcodes), C.POINTER(Params), C.POINTER(SnpFilter),
+                            C.c_int32, c_i64p, c_i32p, c_u8p, C.c_int32, c_i64p, c_u8p,
+                            C.POINTER(C.POINTER(Coo)), C.POINTER(C.POINTER(Coo)), C.POINTER(C.POINTER(Coo))]),
     "xg_synth_reads": (C.c_int, [_P, C.POINTER(SynthParams), C.POINTER(_P), c_u64p]),
     "xg_synth_read_index": (C.c_int64, [C.POINTER(SynthParams), C.c_int32, C.c_int32]),
     "xg_write_bam": (C.c_int, [C.c_char_p, C.POINTER(Reads), C.c_int32, C.POINTER(C.c_char_p), c_i64p, _P,
@@ -622,6 +629,39 @@ class Context(object):
                                           as_ptr(keep, c_u8p), 1 if no_dup_hap else 0,
                                           C.byref(ad), C.byref(dp), C.byref(oth)))
         return tuple(coo_to_numpy(self.lib, m, ctx_obj=self) for m in (ad, dp, oth))
+
+    def baf_fc(self, dreads, gid, pos, cell_keys, n_samples, params, ref_idx, alt_idx, min_count, min_maf,
+               reg_ptr, reg_snp, hap_of, no_dup_hap, want_totals=False, want_keep=False):
+        """Pileup, the SNP filter on the device and the region count in one library call (xg_baf_fc).
+        Returns (ad, dp, oth[, totals][, keep])."""
+        gid = np.ascontiguousarray(gid, dtype=np.int32)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        keys = np.ascontiguousarray(cell_keys if cell_keys is not None else [], dtype=np.uint64)
+        ref_idx = np.ascontiguousarray(ref_idx, dtype=np.uint8)
+        alt_idx = np.ascontiguousarray(alt_idx, dtype=np.uint8)
+        reg_ptr = np.ascontiguousarray(reg_ptr, dtype=np.int64)
+        reg_snp = np.ascontiguousarray(reg_snp, dtype=np.int32)
+        hap_of = np.ascontiguousarray(hap_of, dtype=np.uint8)
+        if len(ref_idx) != len(gid) or len(alt_idx) != len(gid) or hap_of.size != 8 * len(gid):
+            raise ValueError("baf_fc: per-SNP arrays of different lengths")
+        s = Snps(len(gid), as_ptr(gid, c_i32p), as_ptr(pos, c_i32p))
+        b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
+        f = SnpFilter(as_ptr(ref_idx, c_u8p), as_ptr(alt_idx, c_u8p), float(min_count), float(min_maf))
+        totals = np.zeros((len(gid), 5), dtype=np.int64) if want_totals else None
+        keep = np.zeros(len(gid), dtype=np.uint8) if want_keep else None
+        ad, dp, oth = C.POINTER(Coo)(), C.POINTER(Coo)(), C.POINTER(Coo)()
+        self._check(self.lib.xg_baf_fc(self.h, dreads.h, C.byref(s), C.byref(b), C.byref(params.c), C.byref(f),
+                                       len(reg_ptr) - 1, as_ptr(reg_ptr, c_i64p), as_ptr(reg_snp, c_i32p),
+                                       as_ptr(hap_of, c_u8p), 1 if no_dup_hap else 0,
+                                       as_ptr(totals, c_i64p) if want_totals else None,
+                                       as_ptr(keep, c_u8p) if want_keep else None,
+                                       C.byref(ad), C.byref(dp), C.byref(oth)))
+        out = tuple(coo_to_numpy(self.lib, m, ctx_obj=self) for m in (ad, dp, oth))
+        if want_totals:
+            out += (totals,)
+        if want_keep:
+            out += (keep,)
+        return out
 
     def synth_reads(self, n_reads, n_cells, span_gid, span_beg, span_end, seed=7, read_len=91,
                     want_seq=False, snps=None, first_read=0, total_reads=0):
