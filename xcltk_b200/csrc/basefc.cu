@@ -1709,7 +1709,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     // The reduction of a feature is one CTA's work and its passes are bound by the loads that CTA keeps in flight:
     // the few features with very many reads (a long tail in expression data) would be the critical path of their
     // epoch.  They get CTAs of 1024 threads, launched beside the ordinary ones.
-    uint64_t seg_big = 49152;
+    uint64_t seg_big = 4096;                  // candidate reads; about 1 600 words, the light / heavy limit of the ordinary CTAs
     if (const char *e = getenv("XG_SEG_BIG")) seg_big = (uint64_t)atoll(e);
     if (((size_t)10 << FS_BIG_TBL_LOG2) + (size_t)(2 * ((n_cols + 31) / 32) + 1) * 4 + sizeof(FsShared) + 1280 > 200 * 1024)
         seg_big = ~0ull;                      // so many cells that the big CTA's shared memory does not fit: no big CTAs
@@ -1783,23 +1783,14 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     auto segs_smem = [&](int tbl_log2) {
         return ((size_t)8 << tbl_log2) + ((size_t)2 << tbl_log2) + (size_t)(2 * bm_words + 1) * 4;    // table, counters, bitmap + prefix
     };
-    int big_variant = 0;      // EXPERIMENT
-    if (const char *e = getenv("XG_BIG_VARIANT")) big_variant = atoi(e);
-    const int bv_log2[6] = {14, 13, 14, 13, 12, 12}, bv_thr[6] = {1024, 512, 512, 1024, 1024, 512};
-    const size_t segs_bytes = segs_smem(FS_TBL_LOG2), big_bytes = segs_smem(bv_log2[big_variant]);
+    const size_t segs_bytes = segs_smem(FS_TBL_LOG2), big_bytes = segs_smem(FS_BIG_TBL_LOG2);
     XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<FS_THREADS, FS_TBL_LOG2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)segs_bytes));
     // big CTAs need the large table; with so many cells that it does not fit, big features go the ordinary way
     const bool big_ok = big_bytes + sizeof(FsShared) + 1280 <= 200 * 1024;
     if (big_ok)
-    {
-        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<1024, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(14)));
-        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<512, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(13)));
-        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<512, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(14)));
-        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<1024, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(13)));
-        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<1024, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(12)));
-        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<512, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segs_smem(12)));
-    }
+        XG_CUDA(cudaFuncSetAttribute(k_basefc_finalize_segs<FS_BIG_THREADS, FS_BIG_TBL_LOG2>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_bytes));
     const int segs_ctas_per_sm = std::max(1, std::min(8, (int)(224 * 1024 / (segs_bytes + sizeof(FsShared) + 1280))));
     int32_t hist_cols = std::min(n_cols, 40 * 1024);
     if (const char *e = getenv("XG_HIST_COLS")) hist_cols = std::max(32, std::min(n_cols, atoi(e)));
@@ -1924,20 +1915,9 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         if (n_big > 0) {
             cudaStream_t st_b = overlap ? st_f : ctx->aux[1];
             if (!overlap) cudaStreamWaitEvent(st_b, EV(2, e), 0);
-            const int per_sm = std::max(1, std::min((int)(220 * 1024 / (big_bytes + sizeof(FsShared) + 1280)), 2048 * 3 / 4 / bv_thr[big_variant]));
-            const int gridb = std::min(n_big, 148 * per_sm);
-#define BV(T, L)                                                                                                             \
-    k_basefc_finalize_segs<T, L><<<gridb, T, big_bytes, st_b>>>(pool, P.fdesc, seg_cur, d_sf_row,                               \
-                                                                 d_fin_big + pl.fin_big_ptr[(size_t)e], n_big, n_cols,          \
-                                                                 big_work + e, cursor, seg_base, seg_nnz, st_col, st_val)
-            switch (big_variant) {
-                case 0: BV(1024, 14); break;
-                case 1: BV(512, 13); break;
-                case 2: BV(512, 14); break;
-                case 3: BV(1024, 13); break;
-                case 4: BV(1024, 12); break;
-                default: BV(512, 12); break;
-            }
+            k_basefc_finalize_segs<FS_BIG_THREADS, FS_BIG_TBL_LOG2><<<std::min(n_big, 148), FS_BIG_THREADS, big_bytes, st_b>>>(
+                pool, P.fdesc, seg_cur, d_sf_row, d_fin_big + pl.fin_big_ptr[(size_t)e], n_big, n_cols, big_work + e,
+                cursor, seg_base, seg_nnz, st_col, st_val);
             launches++;
             XG_DBG("k_basefc_finalize_segs<big>");
             if (!overlap) cudaEventRecord(EV(5, e), st_b);
