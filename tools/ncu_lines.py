@@ -19,8 +19,9 @@ rep, kre = sys.argv[1], sys.argv[2]
 mangled = sys.argv[3] if len(sys.argv) > 3 else None
 min_share = float(sys.argv[4]) if len(sys.argv) > 4 else 0.7
 
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
-                     capture_output=True, text=True).stdout
+# NCU_LAUNCH_SKIP=n: the (n+1)-th matching launch of the report
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre, "--launch-skip",
+                      os.environ.get("NCU_LAUNCH_SKIP", "0"), "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 start = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 kname = rows[start - 1][1] if start else ""

@@ -433,74 +433,123 @@ __device__ __forceinline__ void record_keys(const ExtractArgs &a, const uint8_t 
     }
 }
 
-__global__ void k_extract(const ExtractArgs a) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per BGZF block.  The record starts are a chain (each record gives the next one's offset): the warp walks
+// 32 links with uniform loads -- one transaction each -- and lane i keeps link i; then every lane takes ITS record:
+// geometry, a warp prefix sum places its CIGAR / sequence words and its record slot behind the block's base offsets
+// (exactly what k_walk counted), the fixed-size fields of 32 consecutive records leave as coalesced stores, and the
+// aux fields of 32 records are parsed side by side instead of one after the other.
+#define EXTRACT_THREADS 128
+__global__ void __launch_bounds__(EXTRACT_THREADS) k_extract(const ExtractArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int b = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (b >= a.n_blocks) return;
     const BlkInfo bi = a.info[b];
     if (bi.n_kept == 0) {
-        a.hk[b] = make_uint2(0u, 0u);
+        if (lane == 0) a.hk[b] = make_uint2(0u, 0u);
         return;
     }
     const BgzfBlockDev bk = a.blocks[b];
-    uint32_t off = bk.uoff < a.hdr_end ? (uint32_t)(a.hdr_end - bk.uoff) : 0u;
+    uint32_t off = bk.uoff < a.hdr_end ? (uint32_t)(a.hdr_end - bk.uoff) : 0u;      // uniform: the next link
     const uint32_t end = bk.isize;
-    unsigned long long g = a.rec_base[b], co = a.cig_base[b], so = a.seq_base[b];
-    int32_t prev_tid = -2;
+    unsigned long long g0 = a.rec_base[b], co0 = a.cig_base[b], so0 = a.seq_base[b];
+    int32_t prev_tid = -2;                 // contig of the last kept record before this batch
     uint32_t hk_n = 0, hk_bytes = 0;
     int unspelled = 0;
+    const uint32_t lt = (1u << lane) - 1u;
     while (off < end) {
-        const uint8_t *r = bk.uptr + off;
-        const uint32_t bs = ld32u(r);
-        const int32_t tid = (int32_t)ld32u(r + 4);
-        off += 4u + bs;
-        if (tid < 0 || a.tid_map[tid] < 0) continue;
-        const RecGeom q = rec_geom(r, bs, a.want_seq != 0);
-        a.pos_end[g] = make_int2(q.pos, q.end);
-        a.fmq[g] = q.fmq;
-        const uint8_t *cig = r + 36 + q.l_name;
-        const uint32_t ncw = q.fmq >> 24;
-        if (ncw == 0) {
-            a.cig_off[g] = (uint32_t)co;
-        } else if (q.n_cig == 0) {
-            a.cig_off[g] = (uint32_t)co;
-            a.cigar[co++] = 6;
-        } else {
-            if (ncw == 255) a.cigar[co++] = q.n_cig;
-            a.cig_off[g] = (uint32_t)co;
-            for (uint32_t i = 0; i < q.n_cig; i++) a.cigar[co++] = ld32u(cig + 4 * i);
+        uint32_t my_off = 0xFFFFFFFFu;
+        for (int i = 0; i < 32 && off < end; i++) {
+            if (lane == i) my_off = off;
+            off += 4u + ld32u(bk.uptr + off);          // k_walk has checked every link of the chain
         }
-        const uint8_t *sq = cig + 4ull * q.n_cig;
-        const uint32_t seq_bytes = (q.l_seq + 1) / 2;
-        if (a.want_seq) {
-            a.seq_off[g] = q.seq_words ? (uint32_t)so : 0xFFFFFFFFu;
-            for (uint32_t w = 0; w < q.seq_words; w++) {
-                uint32_t v = ld32u(sq + 4 * w);
-                const uint32_t left = seq_bytes - 4 * w;
-                if (left < 4) v &= (1u << (8 * left)) - 1u;
-                a.seq[so++] = v;
+        const bool valid = my_off != 0xFFFFFFFFu;
+        const uint8_t *r = bk.uptr + (valid ? my_off : 0u);
+        uint32_t bs = 0;
+        int32_t tid = -1;
+        if (valid) {
+            bs = ld32u(r);
+            tid = (int32_t)ld32u(r + 4);
+        }
+        const bool kept = valid && tid >= 0 && a.tid_map[tid] >= 0;
+        RecGeom q;
+        q.n_words = q.seq_words = 0;
+        if (kept) q = rec_geom(r, bs, a.want_seq != 0);
+        const uint32_t kmask = __ballot_sync(0xffffffffu, kept);
+        // inclusive warp scans of the CIGAR and sequence words
+        uint32_t ci = kept ? q.n_words : 0u, si = kept ? q.seq_words : 0u;
+        const uint32_t my_c = ci, my_s = si;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t yc = __shfl_up_sync(0xffffffffu, ci, d), ys = __shfl_up_sync(0xffffffffu, si, d);
+            if (lane >= d) {
+                ci += yc;
+                si += ys;
             }
         }
-        KeyRef ck, uk;
-        record_keys(a, r, bs, q, &ck, &uk);
-        for (const KeyRef *k : {&ck, &uk}) {
-            if (k->status == 1) {
-                hk_n++;
-                hk_bytes += k->n;
-            } else if (k->status == 2) {
-                unspelled++;
+        const uint32_t tot_c = __shfl_sync(0xffffffffu, ci, 31), tot_s = __shfl_sync(0xffffffffu, si, 31);
+        // contig of the kept record before mine (run starts)
+        const uint32_t below = kmask & lt;
+        const int src = below ? 31 - __clz((int)below) : 0;
+        const int32_t tid_before = __shfl_sync(0xffffffffu, tid, src);
+        const int32_t my_prev = below ? tid_before : prev_tid;
+        if (kmask) prev_tid = __shfl_sync(0xffffffffu, tid, 31 - __clz((int)kmask));
+        if (kept) {
+            const unsigned long long g = g0 + (unsigned long long)__popc(below);
+            unsigned long long co = co0 + (ci - my_c), so = so0 + (si - my_s);
+            a.pos_end[g] = make_int2(q.pos, q.end);
+            a.fmq[g] = q.fmq;
+            const uint8_t *cig = r + 36 + q.l_name;
+            const uint32_t ncw = q.fmq >> 24;
+            if (ncw == 0) {
+                a.cig_off[g] = (uint32_t)co;
+            } else if (q.n_cig == 0) {
+                a.cig_off[g] = (uint32_t)co;
+                a.cigar[co++] = 6;
+            } else {
+                if (ncw == 255) a.cigar[co++] = q.n_cig;
+                a.cig_off[g] = (uint32_t)co;
+                for (uint32_t i = 0; i < q.n_cig; i++) a.cigar[co++] = ld32u(cig + 4 * i);
+            }
+            const uint8_t *sq = cig + 4ull * q.n_cig;
+            const uint32_t seq_bytes = (q.l_seq + 1) / 2;
+            if (a.want_seq) {
+                a.seq_off[g] = q.seq_words ? (uint32_t)so : 0xFFFFFFFFu;
+                for (uint32_t w = 0; w < q.seq_words; w++) {
+                    uint32_t v = ld32u(sq + 4 * w);
+                    const uint32_t left = seq_bytes - 4 * w;
+                    if (left < 4) v &= (1u << (8 * left)) - 1u;
+                    a.seq[so++] = v;
+                }
+            }
+            KeyRef ck, uk;
+            record_keys(a, r, bs, q, &ck, &uk);
+            for (const KeyRef *k : {&ck, &uk}) {
+                if (k->status == 1) {
+                    hk_n++;
+                    hk_bytes += k->n;
+                } else if (k->status == 2) {
+                    unspelled++;
+                }
+            }
+            a.keys[g] = make_ulonglong2(ck.key, uk.key);      // a key still to come from the host holds a placeholder
+            if (tid != my_prev) {
+                const int s2 = atomicAdd(a.n_starts, 1);
+                a.starts[s2] = RunStart{(long long)g, tid, a.bam_idx};
             }
         }
-        a.keys[g] = make_ulonglong2(ck.key, uk.key);      // a key still to come from the host holds a placeholder
-        if (tid != prev_tid) {
-            const int s = atomicAdd(a.n_starts, 1);
-            a.starts[s] = RunStart{(long long)g, tid, a.bam_idx};
-            prev_tid = tid;
-        }
-        g++;
+        g0 += (unsigned long long)__popc(kmask);
+        co0 += tot_c;
+        so0 += tot_s;
     }
-    a.hk[b] = make_uint2(hk_n, hk_bytes);
-    if (hk_n) atomicMax(a.n_need_host, 1);
-    if (unspelled) atomicMax(a.n_unspelled, 1);
+    for (int d = 16; d > 0; d >>= 1) {
+        hk_n += __shfl_xor_sync(0xffffffffu, hk_n, d);
+        hk_bytes += __shfl_xor_sync(0xffffffffu, hk_bytes, d);
+        unspelled += __shfl_xor_sync(0xffffffffu, unspelled, d);
+    }
+    if (lane == 0) {
+        a.hk[b] = make_uint2(hk_n, hk_bytes);
+        if (hk_n) atomicMax(a.n_need_host, 1);
+        if (unspelled) atomicMax(a.n_unspelled, 1);
+    }
 }
 
 // Values for the host's intern table: which key of which record, and the string.
@@ -947,7 +996,7 @@ int flush_window(Decoder &D, BamState &B, int32_t nb) {
         a.hk = D.hk;
         cudaMemsetAsync(D.cnt + 5, 0, 2 * sizeof(int), st);
         cudaEventRecord(ctx->ev[0], st);
-        k_extract<<<(unsigned)((nb + 63) / 64), 64, 0, st>>>(a);
+        k_extract<<<(unsigned)(((unsigned long long)nb * 32 + EXTRACT_THREADS - 1) / EXTRACT_THREADS), EXTRACT_THREADS, 0, st>>>(a);
         cudaEventRecord(ctx->ev[1], st);
         const size_t s0 = D.starts.size();
         D.starts.resize(s0 + (size_t)n_starts);
