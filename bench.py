@@ -186,7 +186,15 @@ class Batch(object):
         self.fc = workload.make_basefc_workload(ctx, args.reads, args.cells, args.features, seed=seed, part=part)
         self.baf = workload.make_baf_workload(ctx, args.baf_reads, args.baf_cells, args.snps, seed=seed + 1, part=part)
         self.n_reads = self.fc.n_reads + self.baf.n_reads          # records this GPU holds (halos included)
-        self.keep = None
+        # The two halves of a step are independent calls (xcltk's rdr and baf modules): unless --serial-calls, the baf
+        # call is issued from a second host thread through a context (stream, scratch) of its own on the same GPU,
+        # so that its host phases and short kernels run beside basefc's instead of after them.
+        self.ctx_baf, self.pool = ctx, None
+        if not args.serial_calls:
+            from concurrent.futures import ThreadPoolExecutor
+            from xcltk_b200 import lib
+            self.ctx_baf = lib.Context(ctx.device)
+            self.pool = ThreadPoolExecutor(1)
 
     # SNP filter of the baf half: min_count = 1, min_maf = 0 (the values xcltk baf passes, baf/pipeline.py:355)
 
@@ -194,16 +202,23 @@ class Batch(object):
         ctx, fc, bf = self.ctx, self.fc, self.baf
         launches = 0
         w0 = time.perf_counter()
+
+        def baf_call():
+            # pileup -> SNP filter (min_count 1, min_maf 0, on the device) -> region count: one library call
+            t = time.perf_counter()
+            out = self.ctx_baf.baf_fc(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, bf.snp_ref,
+                                      bf.snp_alt, 1, 0.0, bf.reg_ptr, bf.reg_snp, bf.hap_of, True)
+            return out, self.ctx_baf.timing(), time.perf_counter() - t
+
+        fut = self.pool.submit(baf_call) if self.pool else None
         # rows in completion order (what the Matrix-Market writer consumes): copied out under the kernels
         seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
         w1 = time.perf_counter()
         t_fc = ctx.timing()
         launches += int(t_fc[2])
-        # pileup -> SNP filter (min_count 1, min_maf 0, on the device) -> region count: one library call
-        ad, dp, oth = ctx.baf_fc(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, bf.snp_ref,
-                                 bf.snp_alt, 1, 0.0, bf.reg_ptr, bf.reg_snp, bf.hap_of, True)
+        (ad, dp, oth), t_c, w_baf = fut.result() if fut else baf_call()
         w2 = time.perf_counter()
-        t_p = t_c = ctx.timing()
+        t_p = t_c
         launches += int(t_c[2])
         chk = None
         if checksum:                 # rows numbered as in the whole matrix, so that the shards add up
@@ -212,7 +227,7 @@ class Batch(object):
             for k, m in enumerate((ad, dp, oth)):
                 chk = (chk + matrix_checksum(bf.feat_index[m[0]] + (k + 1) * (1 << 24), m[1], m[2])) % (1 << 64)
         w4 = time.perf_counter()
-        return dict(nnz=seg.nnz, checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w4 - w2)],
+        return dict(nnz=seg.nnz, checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * w_baf, 1e3 * (w2 - w0), 1e3 * (w4 - w2)],
                     launches=launches, t_fc=t_fc, t_pileup=t_p, t_count=t_c, baf_nnz=len(ad[2]) + len(dp[2]) + len(oth[2]),
                     out_bytes=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])))
 
@@ -480,6 +495,8 @@ def main():
     ap.add_argument("--file-reads", type=float, default=6e7, help="reads of the C3 slice written to a BAM for the file-to-matrix leg")
     ap.add_argument("--smartseq-reads", type=float, default=5e4, help="reads per BAM of the 384-BAM SMART-seq leg (C4)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--serial-calls", action="store_true",
+                    help="issue the baf call after the basefc call instead of beside it (second host thread + context)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N > 1: strong = one library cut into N genomic chunks; weak = one library per GPU")
@@ -501,6 +518,9 @@ def main():
               "partition": ("contiguous genomic chunks of one library balanced by reads, one per GPU (features / "
                             "regions by start position, reads with halo); disjoint rows, no collective"
                             if strong else "one batch (library) per GPU, no collective"),
+              "calls": ("basefc and baf fc issued one after the other" if args.serial_calls else
+                        "basefc and baf fc are independent calls, issued side by side from two host threads (a context and stream "
+                        "each) on the same GPU; a step ends when both have returned their matrices"),
               "l2_policy": "inputs (%.1f GB of records per step%s) are larger than L2" % (
                   bytes_nominal / 1e9, ", 1/N of it per GPU" if strong else " and GPU")}
 
@@ -670,7 +690,7 @@ def main():
                            "baf_scan_kernel_ms": float(np.mean([i["t_pileup"][1] for i in infos])),
                            "baf_host_ms_pileup_queued_done": [float(np.mean([i["t_count"][k] for i in infos])) for k in (8, 9, 10)],
                            "basefc_nnz": int(nnz_all), "checksum": checksum, "reads_held_by_all_gpus": held_reads,
-                           "wall_ms_basefc_baf_checksum": [float(x) for x in np.mean(
+                           "wall_ms_basefc_baf_both_checksum": [float(x) for x in np.mean(
                                [i["wall_ms"] for i in infos], axis=0)],
                            "basefc_host_ms_index_windows_plan_upload_call": [float(x) for x in info["t_fc"][8:13]],
                            "basefc_reads_per_s_kernels_only": batch.fc.n_reads / (

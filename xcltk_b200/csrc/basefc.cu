@@ -194,12 +194,6 @@ __global__ void __launch_bounds__(256) k_feature_windows(const WinJob *jobs, int
     }
 }
 
-struct FeatCache {
-    bool valid = false;
-    uint64_t hash = 0;
-    FeatIndexHost ix;
-};
-
 // ---- epoch plan ------------------------------------------------------------------------
 // The read stream is cut into epochs of `epoch_tiles` tiles.  A feature owns a block of the
 // pool (its (cell, UMI) set) from the first epoch that can hold one of its reads to the last;
@@ -227,6 +221,20 @@ struct EpochPlan {
     std::vector<int32_t> fin_feat, fin_set, fin_big;  // features ending in the epoch: segments / sets / big segments
     int64_t staging_cap = 0;
     int64_t n_seg_feat = 0, n_set_feat = 0;
+    // planner scratch
+    std::vector<int32_t> first_e, last_e, start_ptr, end_ptr, starts, ends, sc, ec;
+    std::vector<uint8_t> bucket_of;
+    std::vector<uint64_t> epoch_bytes;
+    // The plan object lives in the context and is reused from call to call: vectors of this size are mmap'ed
+    // afresh by every allocation, and the page faults of a new plan cost more than computing it.
+    void reset() {
+        n_epochs = epoch_tiles = 0;
+        pool_bytes = 0;
+        staging_cap = n_seg_feat = n_set_feat = 0;
+        for (auto *v : {&zero_ptr, &fin_ptr, &fin_set_ptr, &fin_big_ptr, &fin_feat, &fin_set, &fin_big}) v->clear();
+        zseg_off.clear();
+        zseg_pre.clear();
+    }
 };
 
 // seg_max: features with at most this many candidate reads collect pair words in a segment
@@ -235,91 +243,118 @@ struct EpochPlan {
 int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const std::vector<int32_t> &tlo,
               const std::vector<int32_t> &thi, int32_t n_tiles, int32_t n_cols, int32_t epoch_tiles,
               uint64_t seg_max, uint64_t seg_big, EpochPlan &pl) {
-    size_t m = cand.size();
+    // The planner sits on the critical path of every call (the GPU waits for it): flat arrays and counting sorts,
+    // O(features), no per-epoch containers, no sort, no free list.
+    const size_t m = cand.size();
     pl.epoch_tiles = epoch_tiles;
     pl.n_epochs = std::max(1, (n_tiles + epoch_tiles - 1) / epoch_tiles);
+    const size_t ne = (size_t)pl.n_epochs;
     pl.blk_off.assign(m, 0);
     pl.tbl_cap.assign(m, 0);
     pl.log_cap.assign(m, 0);
-    std::vector<std::vector<int32_t>> starts((size_t)pl.n_epochs), ends((size_t)pl.n_epochs);
+    // first / last epoch of every active feature; features per first epoch and per (last epoch, log2 bucket)
+    std::vector<int32_t> &first_e = pl.first_e, &last_e = pl.last_e, &start_ptr = pl.start_ptr, &end_ptr = pl.end_ptr;
+    std::vector<uint8_t> &bucket_of = pl.bucket_of;
+    first_e.resize(m);
+    last_e.resize(m);
+    bucket_of.resize(m);
+    start_ptr.assign(ne + 1, 0);
+    end_ptr.assign(ne * 33 + 1, 0);
     for (size_t j = 0; j < m; j++) {
-        if (cand[j] == 0) continue;
-        unsigned long long cap = cand[j] + cand[j] / 4 + 8;
+        const unsigned long long c = cand[j];
+        if (c == 0) {
+            first_e[j] = -1;
+            continue;
+        }
+        const unsigned long long cap = c + c / 4 + 8;
         if (cap >= (1ull << 32)) return ctx->fail(XG_E_LIMIT, "feature window exceeds 2^32 reads");
-        if (cand[j] <= seg_max) {
+        if (c <= seg_max) {
             pl.n_seg_feat++;
         } else {
             pl.tbl_cap[j] = (uint32_t)cap;
             pl.n_set_feat++;
         }
-        pl.log_cap[j] = (uint32_t)cand[j];
-        pl.staging_cap += (int64_t)std::min<unsigned long long>(cand[j], (unsigned long long)n_cols);
-        starts[(size_t)(tlo[j] / epoch_tiles)].push_back((int32_t)j);
-        ends[(size_t)((thi[j] - 1) / epoch_tiles)].push_back((int32_t)j);
+        pl.log_cap[j] = (uint32_t)c;
+        pl.staging_cap += (int64_t)std::min<unsigned long long>(c, (unsigned long long)n_cols);
+        const int32_t fe = tlo[j] / epoch_tiles, le = (thi[j] - 1) / epoch_tiles;
+        first_e[j] = fe;
+        last_e[j] = le;
+        const int bk = std::min(63 - __builtin_clzll(c), 32);            // floor(log2(c)), c >= 1
+        bucket_of[j] = (uint8_t)bk;
+        start_ptr[(size_t)fe + 1]++;
+        end_ptr[(size_t)le * 33 + (size_t)(32 - bk) + 1]++;               // heavy buckets first within an epoch
+    }
+    for (size_t e = 0; e < ne; e++) start_ptr[e + 1] += start_ptr[e];
+    for (size_t k = 0; k < ne * 33; k++) end_ptr[k + 1] += end_ptr[k];
+    std::vector<int32_t> &starts = pl.starts, &ends = pl.ends;
+    starts.resize((size_t)start_ptr[ne]);
+    ends.resize((size_t)end_ptr[ne * 33]);
+    {
+        std::vector<int32_t> &sc = pl.sc, &ec = pl.ec;
+        sc.assign(start_ptr.begin(), start_ptr.end() - 1);
+        ec.assign(end_ptr.begin(), end_ptr.end() - 1);
+        for (size_t j = 0; j < m; j++) {
+            if (first_e[j] < 0) continue;
+            starts[(size_t)sc[(size_t)first_e[j]]++] = (int32_t)j;
+            ends[(size_t)ec[(size_t)last_e[j] * 33 + (size_t)(32 - bucket_of[j])]++] = (int32_t)j;
+        }
     }
     // Pool layout.  A block is needed from its feature's first epoch to the finalize of its last one, and
     // zero(e) / count(e) are ordered after finalize(e-2): a feature that lives in one or two epochs takes its
     // block from the arena of its first epoch -- three arenas in rotation, each as large as the busiest
-    // epoch -- and the few that live longer get a place of their own behind the arenas.  O(features), no
-    // free list: the planner sits on the critical path of every call.
-    std::vector<uint64_t> epoch_bytes((size_t)pl.n_epochs, 0);
-    std::vector<int32_t> end_epoch(m, 0);
-    for (int32_t e = 0; e < pl.n_epochs; e++)
-        for (int32_t j : ends[(size_t)e]) end_epoch[(size_t)j] = e;
+    // epoch -- and the few that live longer get a place of their own behind the arenas.
+    std::vector<uint64_t> &epoch_bytes = pl.epoch_bytes;
+    epoch_bytes.assign(ne, 0);
     uint64_t long_bytes = 0;
-    for (int32_t e = 0; e < pl.n_epochs; e++)
-        for (int32_t j : starts[(size_t)e]) {
-            const uint64_t need = plan_blk_bytes(pl.tbl_cap[(size_t)j], pl.log_cap[(size_t)j]);
-            if (end_epoch[(size_t)j] <= e + 1) {
-                pl.blk_off[(size_t)j] = epoch_bytes[(size_t)e];          // offset inside the arena, for now
-                epoch_bytes[(size_t)e] += need;
+    for (size_t e = 0; e < ne; e++)
+        for (int32_t k = start_ptr[e]; k < start_ptr[e + 1]; k++) {
+            const size_t j = (size_t)starts[(size_t)k];
+            const uint64_t need = plan_blk_bytes(pl.tbl_cap[j], pl.log_cap[j]);
+            if (last_e[j] <= (int32_t)e + 1) {
+                pl.blk_off[j] = epoch_bytes[e];                     // offset inside the arena, for now
+                epoch_bytes[e] += need;
             } else {
-                pl.blk_off[(size_t)j] = long_bytes;
+                pl.blk_off[j] = long_bytes;
                 long_bytes += need;
             }
         }
     uint64_t arena = 0;
-    for (uint64_t b : epoch_bytes) arena = std::max(arena, b);
+    for (uint64_t bts : epoch_bytes) arena = std::max(arena, bts);
     arena = (arena + 255) & ~255ull;
     const int n_arenas = std::min(3, pl.n_epochs);
     pl.pool_bytes = arena * (uint64_t)n_arenas + long_bytes;
-    pl.zero_ptr.assign((size_t)pl.n_epochs + 1, 0);
-    pl.fin_ptr.assign((size_t)pl.n_epochs + 1, 0);
-    pl.fin_set_ptr.assign((size_t)pl.n_epochs + 1, 0);
-    pl.fin_big_ptr.assign((size_t)pl.n_epochs + 1, 0);
-    for (int32_t e = 0; e < pl.n_epochs; e++) {
+    pl.zero_ptr.assign(ne + 1, 0);
+    pl.fin_ptr.assign(ne + 1, 0);
+    pl.fin_set_ptr.assign(ne + 1, 0);
+    pl.fin_big_ptr.assign(ne + 1, 0);
+    pl.fin_feat.reserve(ends.size());
+    for (size_t e = 0; e < ne; e++) {
         uint64_t pre = 0;
-        for (int32_t j : starts[(size_t)e]) {
-            const uint64_t off = pl.blk_off[(size_t)j] +
-                                 (end_epoch[(size_t)j] <= e + 1 ? arena * (uint64_t)(e % n_arenas) : arena * (uint64_t)n_arenas);
-            pl.blk_off[(size_t)j] = off;
-            if (pl.tbl_cap[(size_t)j]) {         // a set is zeroed before its first epoch; a segment only has a cursor
+        for (int32_t k = start_ptr[e]; k < start_ptr[e + 1]; k++) {
+            const size_t j = (size_t)starts[(size_t)k];
+            const uint64_t off = pl.blk_off[j] + (last_e[j] <= (int32_t)e + 1 ? arena * (uint64_t)(e % (size_t)n_arenas)
+                                                                              : arena * (uint64_t)n_arenas);
+            pl.blk_off[j] = off;
+            if (pl.tbl_cap[j]) {                 // a set is zeroed before its first epoch; a segment only has a cursor
                 pl.zseg_off.push_back(off);
                 pl.zseg_pre.push_back(pre);
-                pre += (uint64_t)pl.tbl_cap[(size_t)j] * 16 + 16;   // set + cursor
+                pre += (uint64_t)pl.tbl_cap[j] * 16 + 16;           // set + cursor
             } else if (off / 16 >= 0xFFFFFFFFull) {
                 return ctx->fail(XG_E_LIMIT, "segment pool exceeds 64 GiB; use smaller epochs (XG_EPOCH_TILES)");
             }
         }
         pl.zseg_pre.push_back(pre);      // terminator of the epoch: total bytes
         pl.zseg_off.push_back(0);
-        pl.zero_ptr[(size_t)e + 1] = (int32_t)pl.zseg_off.size();
-        // heavy rows first (by power of two: a bucket pass, not a sort -- the planner is on the critical path):
-        // the persistent finalize CTAs end closer together
-        {
-            std::vector<int32_t> bucket[33];
-            for (int32_t j : ends[(size_t)e]) {
-                int b = 0;
-                for (unsigned long long c = cand[(size_t)j]; c > 1; c >>= 1) b++;
-                bucket[std::min(b, 32)].push_back(j);
-            }
-            for (int b = 32; b >= 0; b--)
-                for (int32_t j : bucket[b])
-                    (pl.tbl_cap[(size_t)j] ? pl.fin_set : cand[(size_t)j] > seg_big ? pl.fin_big : pl.fin_feat).push_back(j);
+        pl.zero_ptr[e + 1] = (int32_t)pl.zseg_off.size();
+        // finalize order: heavy rows first (`ends` is bucketed by power of two), so that the persistent CTAs end
+        // closer together
+        for (int32_t k = end_ptr[e * 33]; k < end_ptr[(e + 1) * 33]; k++) {
+            const int32_t j = ends[(size_t)k];
+            (pl.tbl_cap[(size_t)j] ? pl.fin_set : cand[(size_t)j] > seg_big ? pl.fin_big : pl.fin_feat).push_back(j);
         }
-        pl.fin_ptr[(size_t)e + 1] = (int32_t)pl.fin_feat.size();
-        pl.fin_set_ptr[(size_t)e + 1] = (int32_t)pl.fin_set.size();
-        pl.fin_big_ptr[(size_t)e + 1] = (int32_t)pl.fin_big.size();
+        pl.fin_ptr[e + 1] = (int32_t)pl.fin_feat.size();
+        pl.fin_set_ptr[e + 1] = (int32_t)pl.fin_set.size();
+        pl.fin_big_ptr[e + 1] = (int32_t)pl.fin_big.size();
     }
     return XG_OK;
 }
@@ -346,6 +381,19 @@ int make_plan(xg_ctx *ctx, const std::vector<unsigned long long> &cand, const st
 struct __align__(16) FeatDesc {
     unsigned long long blk_off;
     uint32_t cap, log_cap;
+};
+
+// What a context keeps between calls: the interval index of the last feature set (valid while the caller passes the
+// same one) and the host-side working arrays of a call, reused so that they are not paged in anew every time.
+struct FeatCache {
+    bool valid = false;
+    uint64_t hash = 0;
+    FeatIndexHost ix;
+    EpochPlan plan;
+    std::vector<unsigned long long> cand;
+    std::vector<int32_t> tlo, thi;
+    std::vector<FeatDesc> fdesc;
+    std::vector<uint32_t> segoff16;
 };
 
 // Everything the counting kernel needs to know about a tile, in one 64-byte line that the CTA
@@ -1668,8 +1716,11 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     XG_CUDA(cudaMemsetAsync(d_cand, 0, sizeof(unsigned long long) * (m + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(d_tlo, 0x7f, sizeof(int32_t) * (m + 1), ctx->stream));
     XG_CUDA(cudaMemsetAsync(d_thi, 0xff, sizeof(int32_t) * (m + 1), ctx->stream));
-    std::vector<unsigned long long> cand(m, 0);
-    std::vector<int32_t> tlo(m, INT32_MAX), thi(m, -1);
+    std::vector<unsigned long long> &cand = fc->cand;
+    std::vector<int32_t> &tlo = fc->tlo, &thi = fc->thi;
+    cand.assign(m, 0);
+    tlo.assign(m, INT32_MAX);
+    thi.assign(m, -1);
     if (n_warps > 0) {
         k_feature_windows<<<(unsigned)((n_warps + 7) / 8), 256, 0, ctx->stream>>>(
             d_jobs, (int32_t)jobs.size(), n_warps, rd->tiles, rd->tile_pmax, rd->pos_end, src ? 0 : 1, d_sf_beg,
@@ -1704,7 +1755,8 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     if (const char *e = getenv("XG_SEG_MODE")) seg_mode = seg_mode && atoi(e) != 0;
     uint64_t seg_max = 1ull << 22;             // heavier features keep a set in global memory
     if (const char *e = getenv("XG_SEG_MAX")) seg_max = (uint64_t)atoll(e);
-    EpochPlan pl;
+    EpochPlan &pl = fc->plan;
+    pl.reset();
     t_ph = now();
     // The reduction of a feature is one CTA's work and its passes are bound by the loads that CTA keeps in flight:
     // the few features with very many reads (a long tail in expression data) would be the critical path of their
@@ -1718,8 +1770,10 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     t_ph = now();
     const int32_t *d_fin_feat = nullptr, *d_fin_set = nullptr, *d_fin_big = nullptr;
     const uint64_t *d_zoff = nullptr, *d_zpre = nullptr;
-    std::vector<FeatDesc> fdesc(m);
-    std::vector<uint32_t> segoff16(m);
+    std::vector<FeatDesc> &fdesc = fc->fdesc;
+    std::vector<uint32_t> &segoff16 = fc->segoff16;
+    fdesc.resize(m);
+    segoff16.resize(m);
     for (size_t j = 0; j < m; j++) {
         fdesc[j] = FeatDesc{pl.blk_off[j], pl.tbl_cap[j], pl.log_cap[j]};
         segoff16[j] = (!pl.tbl_cap[j] && pl.log_cap[j]) ? (uint32_t)(pl.blk_off[j] / 16) : NO_SEG;

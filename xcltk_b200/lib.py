@@ -491,6 +491,7 @@ class Context(object):
 
     def __init__(self, device=0):
         self.lib = load()
+        self.device = device
         self.h = _P()
         rc = self.lib.xg_create(device, C.byref(self.h))
         if rc != 0:
