@@ -905,6 +905,13 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
         }
     }
     uint32_t n_used = 0;             // index slices consumed so far (every thread counts alike)
+    // A warp that runs out of chunks in tile k claims its first chunk of tile k+1 and issues that chunk's record
+    // loads BEFORE it waits for the others at the tile's end: the loads' DRAM latency passes under the barrier
+    // instead of after it.
+    int pre_c = -1;
+    int2 pe_n = make_int2(0, 0);
+    uint32_t fq_n = 0, co_n = 0;
+    ulonglong2 ky_n = make_ulonglong2(XG_KEY_NONE, XG_KEY_NONE);
 
     for (int k = 0;; k++) {
         __syncthreads();             // A: every warp is done with tile k-1
@@ -918,6 +925,7 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (int q = threadIdx.x; q < (1 << FILT_BITS) / 2; q += CNT_THREADS) f4[q] = z;
         }
+        if (threadIdx.x == 0) S.chunk_ctr[(k + 1) & 1] = 0;       // tile k-1 was its last user; tile k+1's claims come after B
         __syncthreads();             // B: filter cleared, everybody has read the descriptor
         if (threadIdx.x == 0) {      // pipeline: descriptor of tile k+2, index slice of tile k+1
             const int t2 = t_pend;
@@ -931,7 +939,6 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
                 }
             }
         }
-        if (threadIdx.x == 0) S.chunk_ctr[(k + 1) & 1] = 0;       // nobody looks at it before barrier A of tile k+1
         if (!live) continue;         // no feature under this tile's window: its records are never read
         const IdxStage &X = S.idx[n_used & 1];
         mbar_wait(&S.bar_idx[n_used & 1], (n_used >> 1) & 1u);
@@ -957,27 +964,29 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
         // chunk are on their way (coalesced 8 / 4 / 4 / 16-byte loads) while this one is counted.  (A third
         // stage that also kept the next chunk's barcode slot in flight was measured slower: the registers
         // it needs spill.)
-        int2 pe_n = make_int2(0, 0);
-        uint32_t fq_n = 0, co_n = 0;
-        ulonglong2 ky_n = make_ulonglong2(XG_KEY_NONE, XG_KEY_NONE);
         auto claim = [&]() -> int {
             int c = 0;
             if (lane == 0) c = atomicAdd(&S.chunk_ctr[k & 1], 1);
             return __shfl_sync(0xffffffffu, c, 0);
         };
-        auto load_chunk = [&](int c) {
+        auto load_from = [&](int64_t beg, int32_t n, int c) {
             const int r = c * CHUNK + lane;
             ky_n = make_ulonglong2(XG_KEY_NONE, XG_KEY_NONE);            // an absent UMI drops the record
-            if (r < n_rec) {
-                const int64_t i = rec_beg + r;
+            if (r < n) {
+                const int64_t i = beg + r;
                 pe_n = __ldcs(&P.pos_end[i]);                             // streamed once: evict-first
                 fq_n = __ldcs(&P.fmq[i]);
                 co_n = __ldcs(&P.cig_off[i]);
                 ky_n = __ldcs(&P.keys[i]);
             }
         };
-        int c = claim();
-        if (c < n_chunks) load_chunk(c);
+        auto load_chunk = [&](int c) { load_from(rec_beg, n_rec, c); };
+        int c = pre_c;
+        if (c < 0) {                 // nothing claimed at the end of the previous tile
+            c = claim();
+            if (c < n_chunks) load_chunk(c);
+        }
+        pre_c = -1;
         while (c < n_chunks) {
             const int2 pe = pe_n;
             const uint32_t fq = fq_n, co = co_n;
@@ -1010,6 +1019,17 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
             c = cn;
         }
         flush_warp(P, S, w, lane);
+        // the first chunk of the next tile (its descriptor arrived two tiles ago; its counter was reset before B)
+        if (S.t_ring[(k + 1) & 3] >= 0) {
+            mbar_wait(&S.bar_desc[(k + 1) & 3], (uint32_t)((k + 1) >> 2) & 1u);
+            const TileDesc &nd = S.desc[(k + 1) & 3];
+            if (nd.bx >= 0) {
+                int cx = 0;
+                if (lane == 0) cx = atomicAdd(&S.chunk_ctr[(k + 1) & 1], 1);
+                pre_c = __shfl_sync(0xffffffffu, cx, 0);
+                if (pre_c * CHUNK < nd.n_rec) load_from(nd.rec_beg, nd.n_rec, pre_c);
+            }
+        }
     }
 }
 
