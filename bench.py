@@ -632,6 +632,14 @@ def main():
                     "peak": peak, "unit": "GB/s", "frac": baf_alg / (max(t_scan_ms, 1e-6) * 1e-3) / 1e9 / peak,
                     "avg_launch_ms": t_scan_ms, "algorithmic_bytes_per_launch": baf_alg, "read_snp_pairs": n_pairs,
                     "traffic": None}
+    try:
+        with open(tj) as fp:
+            tb = json.load(fp).get("k_baf_scan")
+        if tb:       # measured DRAM bytes per read of the profiled launch, scaled to this GPU's reads
+            roofline_baf["traffic"] = tb["dram_bytes"] / tb["reads"] * batch.baf.n_reads
+            roofline_baf["traffic_source"] = traffic_src
+    except Exception:
+        pass
 
     e2e = None
     if not args.no_e2e:

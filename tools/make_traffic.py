@@ -28,17 +28,18 @@ def dram_bytes(rep, kernel):
     tot = 0.0
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(r[ci[m]].replace(",", "")) * UNIT[units[ci[m]]]
-    return tot, float(r[ci["gpu__time_duration.sum"]].replace(",", ""))
+    tu = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[units[ci["gpu__time_duration.sum"]]]
+    return tot, float(r[ci["gpu__time_duration.sum"]].replace(",", "")) * tu
 
 
 out = {"commit": subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip(),
        "when": datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%MZ"),
        "report": os.path.basename(sys.argv[1])}
 b, ms = dram_bytes(sys.argv[1], "k_basefc_count")
-out["k_basefc_count"] = {"dram_bytes": b, "reads": int(float(sys.argv[2])), "duration_under_ncu": ms}
+out["k_basefc_count"] = {"dram_bytes": b, "reads": int(float(sys.argv[2])), "duration_under_ncu_ms": ms}
 if len(sys.argv) > 4:
     b, ms = dram_bytes(sys.argv[3], "k_baf_scan")
-    out["k_baf_scan"] = {"dram_bytes": b, "reads": int(float(sys.argv[4])), "duration_under_ncu": ms, "report": os.path.basename(sys.argv[3])}
+    out["k_baf_scan"] = {"dram_bytes": b, "reads": int(float(sys.argv[4])), "duration_under_ncu_ms": ms, "report": os.path.basename(sys.argv[3])}
 with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as fp:
     json.dump(out, fp, indent=1)
     fp.write("\n")

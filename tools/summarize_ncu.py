@@ -1,7 +1,7 @@
 """Turn ncu outputs into small text summaries for profiles/ (run in the build container).
 
   python tools/summarize_ncu.py launches <launches.csv> > profiles/rNN_launches.txt
-  python tools/summarize_ncu.py report <prof.ncu-rep>   > profiles/rNN_<kernel>.txt
+  python tools/summarize_ncu.py report <prof.ncu-rep> [kernel name substring]  > profiles/rNN_<kernel>.txt
 """
 import collections
 import csv
@@ -45,11 +45,14 @@ def launches(path):
     print("%-30s %6s %12.3f" % ("total", "", tot))
 
 
-def report(path):
+def report(path, pick=None):
+    """pick: substring of the kernel name (metrics and source page of that kernel only)"""
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     for v in rows[2:]:
+        if pick and pick not in v[hdr.index("Kernel Name")]:
+            continue
         print("== kernel:", v[hdr.index("Kernel Name")][:100])
         for i, h in enumerate(hdr):
             if h in KEYS:
@@ -63,6 +66,8 @@ def report(path):
             blocks.append(cur)
         elif cur is not None:
             cur["rows"].append(r)
+    if pick:
+        blocks = [b for b in blocks if pick in b["name"]]
     for b in blocks[:1]:
         hdr = b["rows"][0]
         data = [r for r in b["rows"][1:] if len(r) == len(hdr)]
@@ -82,4 +87,4 @@ def report(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report}[sys.argv[1]](*sys.argv[2:4])

@@ -54,7 +54,8 @@ if os.environ.get("TUNE_CHECK", "1") != "0":
     host.close()
     w.dreads.close()
 
-w = workload.make_basefc_workload(ctx, n_reads, n_cells, n_feat, seed=7)
+part = tuple(int(x) for x in os.environ["TUNE_PART"].split(",")) if os.environ.get("TUNE_PART") else None     # "rank,world"
+w = workload.make_basefc_workload(ctx, n_reads, n_cells, n_feat, seed=7, part=part)
 for setting in sets:
     keys = apply(setting)
     best = None
