@@ -456,6 +456,8 @@ struct CountSmem {
     int t_ring[4];
     int np[CNT_WARPS];
     int chunk_ctr[2];             // next chunk of the current / the next tile (warps claim chunks)
+    int t_pend;                   // the elected thread's pipeline state lives here, not in everybody's registers:
+    uint32_t n_issued;            // tile k+3 (counter value on its way); index slices issued so far
 };
 
 // ---- mbarrier / bulk-copy (TMA) primitives
@@ -732,7 +734,8 @@ __device__ __forceinline__ void emit_pair(const BasefcDev &P, CountSmem &S, int3
 
 // the tile's fields the record path needs, read once per tile into registers
 struct TileRegs {
-    int32_t bx, by, b0, b1, st_lo, jmin, bx_al;
+    int32_t bx, by, b0, st_lo, jmin;
+    const TileDesc *td;           // the rest stays in shared memory (the contig's last boundary: wide windows only)
     uint32_t c_al;
     bool staged, stab_staged, cig_staged;
 };
@@ -789,7 +792,7 @@ __device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, c
     const int32_t nb = T.by - T.bx;
     int32_t ub;
     if (T.staged) {
-        const int32_t *sb = X.bnd + (T.bx - T.bx_al);
+        const int32_t *sb = X.bnd + (T.bx - (T.bx & ~3));
         int32_t lo = 0;
         if (nb <= 8) {                         // few boundaries under the tile: branch-free count
             for (int k = 0; k < nb; k++) lo += sb[k] <= r.pos;
@@ -802,7 +805,7 @@ __device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, c
         }
         ub = T.bx + lo;
     } else {
-        int32_t lo = T.b0, hi = T.b1;
+        int32_t lo = T.b0, hi = T.td->b1;
         while (lo < hi) {
             int32_t mid = (lo + hi) >> 1;
             if (__ldg(&P.bnd[mid]) <= r.pos) lo = mid + 1; else hi = mid;
@@ -813,8 +816,8 @@ __device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, c
     if (ub > T.b0) {
         int32_t s0i, s1i;
         if (T.staged && ub > T.bx) {
-            s0i = X.stab_off[ub - 1 - T.bx_al];
-            s1i = X.stab_off[ub - T.bx_al];
+            s0i = X.stab_off[ub - 1 - (T.bx & ~3)];
+            s1i = X.stab_off[ub - (T.bx & ~3)];
         } else {
             s0i = __ldg(&P.stab_off[ub - 1]);
             s1i = __ldg(&P.stab_off[ub]);
@@ -826,9 +829,9 @@ __device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, c
     }
     // (2) features beginning at a boundary inside (pos, end); every boundary from `by` on is
     // >= the tile's max end, so a staged tile never looks past its staged range
-    const int32_t kb_end = T.staged ? T.by : T.b1;
+    const int32_t kb_end = T.staged ? T.by : T.td->b1;
     for (int32_t kb = ub; kb < kb_end; kb++) {
-        const int32_t bv = T.staged ? X.bnd[kb - T.bx_al] : __ldg(&P.bnd[kb]);
+        const int32_t bv = T.staged ? X.bnd[kb - (T.bx & ~3)] : __ldg(&P.bnd[kb]);
         if (bv >= r.end) break;
         const int32_t j1 = __ldg(&P.fb[kb + 1]);
         for (int32_t j = __ldg(&P.fb[kb]); j < j1; j++)
@@ -861,8 +864,7 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
     __syncthreads();
 
     // ---- elected thread: state of the staging pipeline
-    int t_pend = -1;                 // tile k+3 (counter value on its way)
-    uint32_t n_issued = 0;           // index slices issued so far (buffer = n & 1, parity = (n >> 1) & 1)
+    // S.t_pend: tile k+3; S.n_issued: index slices issued so far (buffer = n & 1, parity = (n >> 1) & 1)
     auto fetch_tile = [&]() -> int {
         const unsigned int v = atomicAdd(P.work, 1u);
         return v < (unsigned int)n_launch ? P.tile0 + (int)v : -1;
@@ -875,9 +877,9 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
         bulk_g2s(&S.desc[k & 3], &P.tdesc[t], (uint32_t)sizeof(TileDesc), &S.bar_desc[k & 3]);
     };
     auto issue_idx = [&](const TileDesc &d) {     // the slice of the index under tile d -> next buffer
-        IdxStage &X = S.idx[n_issued & 1];
-        unsigned long long *bar = &S.bar_idx[n_issued & 1];
-        n_issued++;
+        IdxStage &X = S.idx[S.n_issued & 1];
+        unsigned long long *bar = &S.bar_idx[S.n_issued & 1];
+        S.n_issued++;
         const int32_t bx_al = d.bx & ~3;
         const uint32_t c_al = d.c_lo & ~3u;
         uint32_t n_bnd = 0, n_so = 0, n_st = 0, n_cg = 0;
@@ -895,10 +897,11 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
         if (n_cg) bulk_g2s(X.cigar, P.cigar + c_al, n_cg, bar);
     };
     if (threadIdx.x == 0) {
+        S.n_issued = 0;
         const int t0 = fetch_tile(), t1 = fetch_tile();
         issue_desc(0, t0);
         issue_desc(1, t1);
-        t_pend = fetch_tile();
+        S.t_pend = fetch_tile();
         if (t0 >= 0) {
             mbar_wait(&S.bar_desc[0], 0);
             if (S.desc[0].bx >= 0) issue_idx(S.desc[0]);
@@ -928,8 +931,8 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
         if (threadIdx.x == 0) S.chunk_ctr[(k + 1) & 1] = 0;       // tile k-1 was its last user; tile k+1's claims come after B
         __syncthreads();             // B: filter cleared, everybody has read the descriptor
         if (threadIdx.x == 0) {      // pipeline: descriptor of tile k+2, index slice of tile k+1
-            const int t2 = t_pend;
-            t_pend = t2 >= 0 ? fetch_tile() : -1;
+            const int t2 = S.t_pend;
+            S.t_pend = t2 >= 0 ? fetch_tile() : -1;
             issue_desc(k + 2, t2);
             if (S.t_ring[(k + 1) & 3] >= 0) {
                 mbar_wait(&S.bar_desc[(k + 1) & 3], (uint32_t)((k + 1) >> 2) & 1u);
@@ -948,12 +951,11 @@ __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __
         T.bx = td.bx;
         T.by = td.by;
         T.b0 = td.b0;
-        T.b1 = td.b1;
+        T.td = &td;
         T.st_lo = td.st_lo;
         T.jmin = td.jmin;
-        T.bx_al = T.bx & ~3;
         T.c_al = td.c_lo & ~3u;
-        T.staged = T.by - T.bx_al <= SB_MAX;
+        T.staged = T.by - (T.bx & ~3) <= SB_MAX;
         T.stab_staged = T.staged && td.st_n <= STAB_CAP;
         T.cig_staged = td.c_hi - T.c_al <= CIG_CAP;
         const int64_t rec_beg = td.rec_beg;
@@ -1766,7 +1768,13 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
 
     // ---- pool layout over epochs
     int32_t epoch_tiles = src ? 8192 : 65536;     // streaming: finer epochs = finer H2D / kernel overlap
-    if (const char *e = getenv(src ? "XG_EPOCH_TILES_HOST" : "XG_EPOCH_TILES")) epoch_tiles = std::max(1, atoi(e));
+    if (const char *e = getenv(src ? "XG_EPOCH_TILES_HOST" : "XG_EPOCH_TILES")) {
+        epoch_tiles = std::max(1, atoi(e));
+    } else if (!src && rd->n_tiles > 0) {
+        // equal epochs: a short last epoch costs its launches, its drain and its finalize like a full one
+        const int32_t n_ep = (rd->n_tiles + epoch_tiles - 1) / epoch_tiles;
+        epoch_tiles = (rd->n_tiles + n_ep - 1) / n_ep;
+    }
     // Pair-word mode: a (cell, UMI) pair is one 64-bit word `umi | cell` (every UMI key of the batch leaves
     // its low 24 bits free: packed strings of up to 13 symbols, interned ids below 2^39), features collect
     // their words in segments.  The kernel verifies the keys it meets; a key that does not fit raises a
