@@ -277,6 +277,14 @@ class Batch(object):
                     against="oracle/xg_oracle.c on the same C3 + C2 batch, entry by entry"), t_fc + t_baf
 
 
+# The reference's OWN Python path cannot travel to the GPU box (no /root/reference there): timed once in the build
+# container (unmodified xcltk v0.5.2 on the pysam shim, 8 worker processes, basefc on the C1 golden: 1M reads in 41.9 s;
+# `python oracle/make_golden.py c1_full` prints it) and quoted as a labelled constant next to the C port's live number.
+REFERENCE_PYTHON = {"value": 2.39e4, "unit": "reads/s", "cores": 8, "kind": "constant, not timed in this run",
+                    "what": "unmodified reference (Python, multiprocessing) on the pysam shim, basefc, C1 golden (1M reads, "
+                            "500 barcodes, 33 472 features), build container"}
+
+
 def cpu_sample(ctx, args, n_sample, n_threads):
     """A bounded sample of the basefc workload (same generator, fewer reads) for the CPU legs."""
     from xcltk_b200 import workload
@@ -673,7 +681,8 @@ def main():
         cpu = {"value": (args.reads + args.baf_reads) / t_cpu, "unit": "reads/s", "cores": n_thr, "kind": "port",
                "sample": "the whole step on the CPU with the C oracle (oracle/xg_oracle.c, OpenMP over features / SNPs): "
                          "basefc on the %d reads of the C3 batch + baf fc on the %d reads of the C2 batch the GPU "
-                         "counted, %.1f s" % (args.reads, args.baf_reads, t_cpu)}
+                         "counted, %.1f s" % (args.reads, args.baf_reads, t_cpu),
+               "reference_python": REFERENCE_PYTHON}
 
     decode = None
     device_decode = None

@@ -7,15 +7,16 @@
 //   MCount/SCount.push_read    xcltk/rdr/fc/mcount.py:34-43,102-132 (cell lookup, UMI set)
 //   sam_fetch                  xcltk/utils/sam.py:85-118  (reads overlapping the feature)
 //
-// The reference walks features and re-fetches the reads of each one.  Here the reads are
-// streamed ONCE in file order (coalesced, one CTA per tile of <= 1024 records); each read finds
-// the features it overlaps through a per-contig interval index (sorted boundaries + per-segment
-// stabbing lists + start-sorted features), evaluates the include test arithmetically on its CIGAR
-// and inserts (cell, UMI) into the feature's open-addressing set with a 128-bit CAS.  When the
-// last read that can touch a feature has been streamed, one CTA scans the feature's set into a
-// shared-memory histogram over cells and writes the row's non-zeros in column order.  Features
-// are counted independently (a read overlapping k features is evaluated k times), exactly as
-// the reference does.
+// The reference walks features and re-fetches the reads of each one.  Here the reads are streamed ONCE in file
+// order by persistent CTAs (tiles of <= 1024 records from a work counter; tile descriptors, the slice of the interval
+// index under the tile and its CIGAR words staged in shared memory by bulk copies); each read finds the features it
+// overlaps through a per-contig interval index (sorted boundaries + per-segment stabbing lists + start-sorted
+// features) and evaluates the include test arithmetically on its CIGAR.  A passing (feature, cell, UMI) is one 64-bit
+// pair word `umi | cell`: it goes through a tile-local duplicate filter and is APPENDED to the feature's segment of a
+// pool; when the last read that can touch a feature has been streamed, one CTA deduplicates the segment in shared
+// memory and writes the row's non-zeros in column order.  What does not fit a pair word (or a segment) keeps an
+// open-addressing (cell, UMI) set in global memory (128-bit CAS).  Features are counted independently (a read
+// overlapping k features is evaluated k times), exactly as the reference does.
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -843,8 +844,8 @@ __device__ __forceinline__ void count_record(const BasefcDev &P, CountSmem &S, c
 // tile k+3's index is fetched from the counter, tile k+2's descriptor and tile k+1's slice of the
 // interval index (boundaries, stabbing lists, CIGAR words) are brought into shared memory by bulk
 // copies completing on mbarriers while the warps count tile k.  Inside a tile the warps work
-// on their own: 64-record chunks, 128-bit record loads issued one chunk ahead, pairs staged per
-// warp and appended per warp -- two CTA barriers per tile (the filter is cleared between them).
+// on their own: 32-record chunks claimed from a counter, the record loads issued one chunk ahead, pairs
+// staged per warp and appended per warp -- two CTA barriers per tile (the filter is cleared between them).
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(CNT_THREADS, MIN_CTAS) k_basefc_count(const __grid_constant__ BasefcDev P) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
