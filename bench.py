@@ -212,7 +212,7 @@ class Batch(object):
 
         fut = self.pool.submit(baf_call) if self.pool else None
         # rows in completion order (what the Matrix-Market writer consumes): copied out under the kernels
-        seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
+        seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="tiny")
         w1 = time.perf_counter()
         t_fc = ctx.timing()
         launches += int(t_fc[2])
@@ -229,7 +229,7 @@ class Batch(object):
         w4 = time.perf_counter()
         return dict(nnz=seg.nnz, checksum=chk, wall_ms=[1e3 * (w1 - w0), 1e3 * w_baf, 1e3 * (w2 - w0), 1e3 * (w4 - w2)],
                     launches=launches, t_fc=t_fc, t_pileup=t_p, t_count=t_c, baf_nnz=len(ad[2]) + len(dp[2]) + len(oth[2]),
-                    out_bytes=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])))
+                    out_bytes=2 * seg.nnz + 16 * len(seg.over[0]) + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])))
 
     def make_host(self):
         self.h_fc = self.fc.dreads.download()         # pinned host record arrays
@@ -237,7 +237,7 @@ class Batch(object):
 
     def step_e2e(self):
         ctx, fc, bf = self.ctx, self.fc, self.baf
-        seg = ctx.basefc_host(self.h_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
+        seg = ctx.basefc_host(self.h_fc, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="tiny")
         h2d_fc = int(ctx.timing()[13])
         d_bf = ctx.map_reads(self.h_baf)          # zero-copy: 8 B/read over PCIe, rest on demand
         ad, dp, oth = ctx.baf_fc(d_bf, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, bf.snp_ref,
@@ -245,7 +245,7 @@ class Batch(object):
         ctx.timing_pairs = ctx.timing()[6]            # (read, SNP) pairs: records fetched on demand
         d_bf.close()
         return dict(h2d=h2d_fc + 8 * self.h_baf.n + 72 * int(self.ctx.timing_pairs),
-                    d2h=4 * seg.nnz + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])) +
+                    d2h=2 * seg.nnz + 16 * len(seg.over[0]) + 8 * (len(ad[2]) + len(dp[2]) + len(oth[2])) +
                     12 * len(fc.gid) + 8 * (3 * (len(bf.reg_ptr) - 1) + 3))  # packed entries + row_beg/row_cnt | col + val + row_ptr
 
     def oracle_parity(self, n_threads):
@@ -266,7 +266,7 @@ class Batch(object):
         o_baf = oracle.baf(self.h_baf, bf.snp_gid, bf.snp_pos, ref_s, alt_s, bf.snp_ref_hap, 1 - bf.snp_ref_hap,
                            bf.reg_ptr, bf.reg_snp, bf.cell_keys, bf.n_cells, oracle.params(conf_b), 1, 0, True, n_threads)
         t_baf = time.perf_counter() - t
-        seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="narrow")
+        seg = ctx.basefc(fc.dreads, fc.gid, fc.beg, fc.end, fc.cell_keys, fc.n_cells, fc.params, segments="tiny")
         g_fc = seg.to_sorted()
         ok_fc = all(np.array_equal(a, b) for a, b in zip(g_fc, o_fc))
         g_baf = ctx.baf_fc(bf.dreads, bf.snp_gid, bf.snp_pos, bf.cell_keys, bf.n_cells, bf.params, bf.snp_ref, bf.snp_alt,

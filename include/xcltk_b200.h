@@ -140,6 +140,11 @@ int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int64_t *row_be
 int xg_write_mtx_rows16(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
                         const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const uint32_t *colval16,
                         int64_t n_over, const int64_t *over_idx, const int32_t *over_val, int32_t n_threads);
+/* ... and from the 16-bit layout ("narrow_rows" 2: coldelta16 + side list, see xg_coo).          */
+int xg_write_mtx_rows_tiny(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
+                           const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const uint16_t *coldelta16,
+                           int64_t n_over, const int64_t *over_idx, const int32_t *over_col, const int32_t *over_val,
+                           int32_t n_threads);
 
 /* ---- device side --------------------------------------------------------------------- */
 typedef struct xg_ctx xg_ctx;
@@ -151,7 +156,7 @@ const char *xg_last_error(xg_ctx *ctx);
 /* Options: "coo_rows" (default 1): 0 = results are CSR only (row == NULL; row_ptr, col, val),
  * which saves a third of the device->host result copy.  "row_order" (default 1): 0 = basefc
  * results keep the device's completion order of the rows (see xg_coo), which lets the result
- * copy overlap the counting.  "narrow_rows" (default 0): 1 = with "row_order" 0, entries are packed
+ * copy overlap the counting.  "narrow_rows" (default 0; 2 = the 16-bit layout, see xg_coo.coldelta16): 1 = with "row_order" 0, entries are packed
  * into 32 bits (see xg_coo).                                                                  */
 int xg_set_option(xg_ctx *ctx, const char *name, int64_t value);
 
@@ -264,6 +269,13 @@ typedef struct {
     int64_t n_over;
     const int64_t *over_idx;
     const int32_t *over_val;
+    /* "narrow_rows" 2 (with "row_order" 0): col, val and colval16 are NULL and entry k is the 16-bit word
+     * coldelta16[k] = (column - previous column of the row - 1) << 4 | count  (count 1..15, gap <= 4095 columns);
+     * the word 0 means "look entry k up in the side list": over_idx / over_col / over_val, n_over entries in no
+     * particular order -- always the first entry of a row, else entries whose gap or count does not fit.
+     * A quarter of the bytes of (col, val): the result copy is what a host shared by several GPUs runs out of. */
+    const uint16_t *coldelta16;
+    const int32_t *over_col;
 } xg_coo;
 void xg_coo_free(xg_coo *m);
 

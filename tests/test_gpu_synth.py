@@ -309,6 +309,15 @@ def test_basefc_row_segments_equal_sorted_result(gpu_ctx, fc_batch, tmp_path):
             assert seg_n.cv16 is not None and seg_n.nnz == len(ref[2])
             for a, b in zip(seg_n.to_sorted(), ref):
                 assert np.array_equal(a, b)
+    # 16-bit entries (column delta | small count; first of a row, wide gaps and large counts in the side list)
+    for call, src in ((gpu_ctx.basefc, w.dreads), (gpu_ctx.basefc_host, w.host)):
+        for k in range(2):
+            seg_t = call(src, w.gid, w.beg, w.end, w.cell_keys, 2000, p, segments="tiny")
+            assert seg_t.tiny is not None and seg_t.tiny.dtype == np.uint16 and seg_t.nnz == len(ref[2])
+            n_rows_nz = int((np.asarray(seg_t.row_cnt) > 0).sum())
+            assert n_rows_nz <= len(seg_t.over[0]) < seg_t.nnz // 4         # every row start, few others
+            for a, b in zip(seg_t.to_sorted(), ref):
+                assert np.array_equal(a, b)
     # a smaller and a larger problem after the hint was set
     for sel in (slice(0, len(w.gid) // 3), slice(None)):
         seg = gpu_ctx.basefc(w.dreads, w.gid[sel], w.beg[sel], w.end[sel], w.cell_keys, 2000, p, segments=True)
@@ -325,6 +334,8 @@ def test_basefc_row_segments_equal_sorted_result(gpu_ctx, fc_batch, tmp_path):
     assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "b.mtx"), "rb").read()
     lib.write_mtx_rows(str(tmp_path / "c.mtx"), seg_n, out_row, int(emitted.sum()))
     assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "c.mtx"), "rb").read()
+    lib.write_mtx_rows(str(tmp_path / "d.mtx"), seg_t, out_row, int(emitted.sum()), n_threads=3)
+    assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "d.mtx"), "rb").read()
 
 
 def test_basefc_row_segments_degenerate_inputs(gpu_ctx, fc_batch):
@@ -416,6 +427,17 @@ def test_basefc_narrow_entries_with_large_counts(gpu_ctx):
     seg = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, np.arange(1, 70001, dtype=np.uint64) << np.uint64(40), 70000, p2,
                          segments="narrow")
     assert seg.cv16 is None                                # too many columns for 16 bits
+    # the 16-bit layout: counts in the tens of thousands all go through the side list; 70 000 columns are fine
+    seg = gpu_ctx.basefc(w.dreads, gid, beg, end, None, 1, p, segments="tiny")
+    assert seg.tiny is not None and len(seg.over[0]) >= int((ref[2] > 15).sum())
+    for a, b in zip(seg.to_sorted(), ref):
+        assert np.array_equal(a, b)
+    keys70k = np.arange(1, 70001, dtype=np.uint64) << np.uint64(40)
+    r70 = [np.array(x) for x in gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, keys70k, 70000, p2)[:3]]
+    seg = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, keys70k, 70000, p2, segments="tiny")
+    assert seg.tiny is not None
+    for a, b in zip(seg.to_sorted(), r70):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("world", [2, 5])

@@ -248,6 +248,61 @@ def test_write_mtx_rows16_narrow_entries_and_side_list(tmp_path):
     assert a == b and b"\t65535\n" in a
 
 
+def test_write_mtx_rows_tiny_delta_entries_and_side_list(tmp_path):
+    """the 16-bit layout ((column - previous column - 1) << 4 | count; first of a row, gaps > 4095 and counts > 15 in
+    a side list of (idx, val, col) in no particular order) decodes to, and writes the text of, the plain layout; the
+    rows sit in the staging order of the device (not row order), with a gap of unused entries between two of them"""
+    import numpy as np
+    from xcltk_b200 import lib
+    rng = np.random.RandomState(11)
+    n_rows, n_cols = 300, 60000
+    cnt = rng.randint(0, 40, size=n_rows).astype(np.int32)
+    cnt[5] = 0
+    cnt[17] = 1
+    order = rng.permutation(n_rows)                       # completion order
+    beg = np.zeros(n_rows, dtype=np.int64)
+    at = 0
+    for r in order:
+        beg[r] = at
+        at += int(cnt[r])
+    nnz = at
+    col = np.zeros(nnz, dtype=np.int32)
+    val = rng.randint(1, 12, size=nnz).astype(np.int32)
+    for r in range(n_rows):
+        span = n_cols if r % 3 else 900                   # sparse rows: wide gaps; dense rows: small ones
+        col[beg[r]:beg[r] + cnt[r]] = np.sort(rng.choice(span, cnt[r], replace=False))
+    val[rng.choice(nnz, 40, replace=False)] = rng.randint(16, 3000000, size=40)
+    val[3] = 15
+    val[4] = 16                                           # the largest count that fits, the smallest that does not
+    plain = lib.RowSegments(beg, cnt, col, val, (n_rows, n_cols))
+    # encode as k_pack_rows_tiny does
+    first = np.zeros(nnz, dtype=bool)
+    first[beg[cnt > 0]] = True
+    prev = np.concatenate([[0], col[:-1]])
+    d = col.astype(np.int64) - prev - 1
+    fits = ~first & (d >= 0) & (d <= 4094) & (val <= 15)
+    w = np.where(fits, (d << 4) | val, 0).astype(np.uint16)
+    idx = np.nonzero(~fits)[0].astype(np.int64)
+    perm = rng.permutation(len(idx))
+    tiny = lib.RowSegments(beg, cnt, None, None, (n_rows, n_cols), over=(idx[perm], val[idx][perm], col[idx][perm]), tiny=w)
+    assert tiny.nnz == nnz and np.array_equal(tiny.col, col) and np.array_equal(tiny.val, val)
+    assert (w[~first] != 0).sum() > nnz // 2              # most entries do travel as 16 bits
+    for a, b in zip(tiny.to_sorted(), plain.to_sorted()):
+        assert np.array_equal(a, b)
+    emitted = cnt > 0
+    emitted[5] = True                                     # an empty row that is emitted all the same
+    out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
+    lib.write_mtx_rows(str(tmp_path / "a.mtx"), plain, out_row, int(emitted.sum()), 2)
+    for k, threads in enumerate((1, 5)):
+        lib.write_mtx_rows(str(tmp_path / ("t%d.mtx" % k)), tiny, out_row, int(emitted.sum()), threads)
+        assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / ("t%d.mtx" % k)), "rb").read()
+    empty = lib.RowSegments(np.zeros(3, np.int64), np.zeros(3, np.int32), None, None, (3, 10),
+                            over=(np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32)), tiny=np.zeros(0, np.uint16))
+    assert empty.nnz == 0 and len(empty.col) == 0 and len(empty.val) == 0
+    lib.write_mtx_rows(str(tmp_path / "e.mtx"), empty, np.array([1, 2, 3], np.int32), 3, 2)
+    assert open(str(tmp_path / "e.mtx")).read().splitlines()[-1] == "3\t10\t0"
+
+
 def test_genomic_chunks_partition_the_library():
     """bench.py --scaling strong: the chunks' features are a disjoint cover of the feature list, and every chunk's
     read range reaches from HALO_BP before its first feature to the end of its last one (reads are sorted)."""

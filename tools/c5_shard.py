@@ -38,7 +38,7 @@ print("shard %d/%d of a %.2e-read library: %d bins, %d reads generated in %.1f s
 best = None
 for rep in range(4):
     t = time.perf_counter()
-    seg = ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, cells, w.params, segments="narrow")
+    seg = ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, cells, w.params, segments=os.environ.get("TUNE_SEGMENTS", "tiny"))
     dt = 1e3 * (time.perf_counter() - t)
     tm = ctx.timing()
     line = (dt, tm[0], tm[3], tm[1], int(tm[5]), tm[6] / 1e9, seg.nnz, int(tm[14]), int(tm[15]))

@@ -6,7 +6,7 @@ from xcltk_b200 import engine, workload
 n_reads = int(float(sys.argv[1])) if len(sys.argv) > 1 else 300000000
 ctx = engine.get_context(0)
 w = workload.make_basefc_workload(ctx, n_reads, 10000, 60000, seed=7)
-seg = ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 10000, w.params, segments="narrow")
+seg = ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 10000, w.params, segments=os.environ.get("TUNE_SEGMENTS", "tiny"))
 cnt = np.asarray(seg.row_cnt, dtype=np.int64)
 r, c, v = seg.to_sorted()
 words = np.bincount(r, weights=v, minlength=len(cnt)).astype(np.int64)      # distinct (cell, UMI) per feature <= appended words

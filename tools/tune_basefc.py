@@ -61,12 +61,17 @@ for setting in sets:
     best = None
     for rep in range(3):
         t = time.perf_counter()
-        seg = ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, n_cells, w.params, segments="narrow")
+        seg = ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, n_cells, w.params, segments=os.environ.get("TUNE_SEGMENTS", "tiny"))
         dt = 1e3 * (time.perf_counter() - t)
         tm = ctx.timing()
         line = (dt, tm[0], tm[3], tm[1], int(tm[5]), tm[6] / 1e9, seg.nnz, int(seg.val.sum(dtype=np.int64)), int(tm[14]), int(tm[15]))
+        if os.environ.get("TUNE_VERBOSE"):
+            print("      rep %d: wall %.2f  in-library %.2f  host front %.2f+%.2f+%.2f+%.2f  result tail (host) %.2f" % (
+                rep, dt, tm[12], tm[8], tm[9], tm[10], tm[11], tm[4]))
         if best is None or line[0] < best[0]:
             best = line
+    if getattr(seg, "over", None) is not None:
+        print("    side-list entries: %d of %d" % (len(seg.over[0]), seg.nnz))
     print("[%s] call %.2f ms  device %.2f  epochs-span %.2f  count-kernels %.2f ms  epochs %d  pool %.2f GB  nnz %d  sum %d  seg/set feats %d/%d" % (
         (setting,) + best), flush=True)
     for k in keys:

@@ -1054,6 +1054,37 @@ __global__ void k_pack_rows(const int32_t *col, const int32_t *val, uint32_t *pa
     packed[i] = c | (v16 << 16);
 }
 
+// "tiny" result entries (narrow_rows = 2): 16 bits each -- (column - previous column of the row - 1) << 4 | count.
+// An entry that does not fit (the first of its row, a gap of more than 4095 columns, a count above 15) is the word
+// 0 and goes to the side list with its column and count.  A quarter of the bytes of (col, val) pairs.
+__global__ void k_mark_row_starts(const int64_t *seg_base, const int32_t *seg_nnz, int32_t n_rows, uint32_t *bits) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows || seg_nnz[r] <= 0) return;
+    const int64_t i = seg_base[r];
+    atomicOr(&bits[i >> 5], 1u << (i & 31));
+}
+__global__ void k_pack_rows_tiny(const int32_t *col, const int32_t *val, const uint32_t *row_start, uint16_t *tiny,
+                                 long long from, long long to, long long *over_idx, int32_t *over_col, int32_t *over_val,
+                                 unsigned int *over_n, unsigned int over_cap) {
+    const long long i = from + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= to) return;
+    const uint32_t c = (uint32_t)col[i], v = (uint32_t)val[i];
+    const bool first = (row_start[i >> 5] >> (i & 31)) & 1u;
+    const uint32_t d = first ? 0xFFFFFFFFu : c - (uint32_t)col[i - 1] - 1u;     // columns ascend within a row
+    uint32_t w = 0;
+    if (d <= 4094u && v >= 1u && v <= 15u) {
+        w = (d << 4) | v;
+    } else {
+        const unsigned int k = atomicAdd(over_n, 1u);
+        if (k < over_cap) {
+            over_idx[k] = i;
+            over_col[k] = (int32_t)c;
+            over_val[k] = (int32_t)v;
+        }
+    }
+    tiny[i] = (uint16_t)w;
+}
+
 __global__ void k_snapshot_cursor(const unsigned long long *cursor, unsigned long long *host_slot) {
     *host_slot = *cursor;
     __threadfence_system();
@@ -2051,27 +2082,47 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         // "narrow" results: column and count of an entry in one 32-bit word (16 bits each; counts of
         // 65535 and more go to a side list).  Halves the bytes of the result copy, which is what a
         // host shared by several GPUs runs out of first.
-        bool narrow = ctx->narrow_rows && n_cols <= 65536;
-        const int64_t OVER_CAP = 1 << 20;
+        bool narrow = ctx->narrow_rows == 1 && n_cols <= 65536;
+        // "tiny" results: 16 bits per entry (column delta | small count), the rest in a side list
+        bool tiny = ctx->narrow_rows == 2;
+        const int64_t OVER_CAP = tiny ? (1 << 23) : (1 << 20);
         uint32_t *d_packed = nullptr;
+        uint16_t *d_tiny = nullptr;
+        uint32_t *d_row_start = nullptr;
         long long *d_over_idx = nullptr;
-        int32_t *d_over_val = nullptr;
+        int32_t *d_over_val = nullptr, *d_over_col = nullptr;
         unsigned int *d_over_n = nullptr;
-        if (narrow) {
-            d_packed = (uint32_t *)ctx->get("fx_packed", sizeof(uint32_t) * (size_t)(pl.staging_cap + 1));
+        const size_t row_start_words = (size_t)(pl.staging_cap + 32) / 32 + 1;
+        if (narrow || tiny) {
+            if (narrow) d_packed = (uint32_t *)ctx->get("fx_packed", sizeof(uint32_t) * (size_t)(pl.staging_cap + 1));
+            if (tiny) {
+                d_tiny = (uint16_t *)ctx->get("fx_tiny", sizeof(uint16_t) * (size_t)(pl.staging_cap + 2));
+                d_row_start = (uint32_t *)ctx->get("fx_row_start", sizeof(uint32_t) * row_start_words);
+                d_over_col = (int32_t *)ctx->get("fx_over_col", sizeof(int32_t) * (size_t)OVER_CAP);
+            }
             d_over_idx = (long long *)ctx->get("fx_over_idx", sizeof(long long) * (size_t)OVER_CAP);
             d_over_val = (int32_t *)ctx->get("fx_over_val", sizeof(int32_t) * (size_t)OVER_CAP);
             d_over_n = (unsigned int *)ctx->get("fx_over_n", 16);
-            if (!d_packed || !d_over_idx || !d_over_val || !d_over_n) return give_up(XG_E_CUDA, ctx->err);
+            if ((narrow && !d_packed) || (tiny && (!d_tiny || !d_row_start || !d_over_col)) || !d_over_idx || !d_over_val ||
+                !d_over_n)
+                return give_up(XG_E_CUDA, ctx->err);
             cudaMemsetAsync(d_over_n, 0, 4, ctx->d2h_stream);
+            if (tiny) cudaMemsetAsync(d_row_start, 0, sizeof(uint32_t) * row_start_words, ctx->d2h_stream);
         }
         int32_t *h_col = nullptr, *h_val = nullptr;
         uint32_t *h_packed = nullptr;
+        uint16_t *h_tiny = nullptr;
         auto host_buffers = [&](int64_t n_cap) {
             for (void *q : o->bufs) ctx->pinned_put(q);
             o->bufs.clear();
             h_col = h_val = nullptr;
             h_packed = nullptr;
+            h_tiny = nullptr;
+            if (tiny) {
+                h_tiny = (uint16_t *)ctx->pinned_get((size_t)n_cap * 2 + 16);
+                if (h_tiny) o->bufs.push_back(h_tiny);
+                return h_tiny != nullptr;
+            }
             if (narrow) {
                 h_packed = (uint32_t *)ctx->pinned_get((size_t)n_cap * 4);
                 if (h_packed) o->bufs.push_back(h_packed);
@@ -2085,7 +2136,14 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         };
         auto queue_rows = [&](int64_t from, int64_t to) {       // staging entries [from, to) -> host
             const size_t n = (size_t)(to - from);
-            if (narrow) {
+            if (tiny) {
+                // the rows finished so far have their places (seg_base / seg_nnz): mark their first entries
+                k_mark_row_starts<<<(n_rows + 255) / 256, 256, 0, ctx->d2h_stream>>>(seg_base, seg_nnz, n_rows, d_row_start);
+                k_pack_rows_tiny<<<(unsigned)((n + 255) / 256), 256, 0, ctx->d2h_stream>>>(
+                    st_col, st_val, d_row_start, d_tiny, from, to, d_over_idx, d_over_col, d_over_val, d_over_n,
+                    (unsigned int)OVER_CAP);
+                cudaMemcpyAsync(h_tiny + from, d_tiny + from, n * 2, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+            } else if (narrow) {
                 k_pack_rows<<<(unsigned)((n + 255) / 256), 256, 0, ctx->d2h_stream>>>(st_col, st_val, d_packed, from, to, d_over_idx,
                                                                                     d_over_val, d_over_n, (unsigned int)OVER_CAP);
                 cudaMemcpyAsync(h_packed + from, d_packed + from, n * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
@@ -2119,33 +2177,39 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
             cudaStreamSynchronize(ctx->d2h_stream);
             cap = nnz + nnz / 8 + 1024;
             if (!host_buffers(cap)) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
-            if (narrow) cudaMemsetAsync(d_over_n, 0, 4, ctx->d2h_stream);
+            if (narrow || tiny) cudaMemsetAsync(d_over_n, 0, 4, ctx->d2h_stream);
             done = 0;
         }
         if (nnz > done) queue_rows(done, nnz);
         unsigned int n_over = 0;
-        if (narrow) {
+        if (narrow || tiny) {
             cudaMemcpyAsync(&n_over, d_over_n, 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
             ce = cudaStreamSynchronize(ctx->d2h_stream);
             if (ce != cudaSuccess) return give_up(XG_E_CUDA, std::string("result D2H: ") + cudaGetErrorString(ce));
-            if ((int64_t)n_over > OVER_CAP) {       // too many large counts for the side list: plain 32-bit columns
-                narrow = false;
+            if ((int64_t)n_over > OVER_CAP) {       // too many entries for the side list: plain 32-bit columns
+                narrow = tiny = false;
                 if (!host_buffers(cap)) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
                 if (nnz > 0) queue_rows(0, nnz);
                 n_over = 0;
             }
         }
         long long *h_over_idx = nullptr;
-        int32_t *h_over_val = nullptr;
-        if (narrow) {
+        int32_t *h_over_val = nullptr, *h_over_col = nullptr;
+        if (narrow || tiny) {
             h_over_idx = (long long *)ctx->pinned_get(((size_t)n_over + 1) * 8);
             h_over_val = (int32_t *)ctx->pinned_get(((size_t)n_over + 1) * 4);
             if (h_over_idx) o->bufs.push_back(h_over_idx);
             if (h_over_val) o->bufs.push_back(h_over_val);
-            if (!h_over_idx || !h_over_val) return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
+            if (tiny) {
+                h_over_col = (int32_t *)ctx->pinned_get(((size_t)n_over + 1) * 4);
+                if (h_over_col) o->bufs.push_back(h_over_col);
+            }
+            if (!h_over_idx || !h_over_val || (tiny && !h_over_col))
+                return give_up(XG_E_NOMEM, "out of pinned host memory for the result");
             if (n_over) {
                 cudaMemcpyAsync(h_over_idx, d_over_idx, (size_t)n_over * 8, cudaMemcpyDeviceToHost, ctx->d2h_stream);
                 cudaMemcpyAsync(h_over_val, d_over_val, (size_t)n_over * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+                if (tiny) cudaMemcpyAsync(h_over_col, d_over_col, (size_t)n_over * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream);
             }
         }
         int64_t *h_beg = (int64_t *)ctx->pinned_get((size_t)(n_rows + 1) * 8);
@@ -2168,9 +2232,11 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         o->m.col = h_col;
         o->m.val = h_val;
         o->m.colval16 = h_packed;
-        o->m.n_over = narrow ? (int64_t)n_over : 0;
+        o->m.n_over = (narrow || tiny) ? (int64_t)n_over : 0;
         o->m.over_idx = (const int64_t *)h_over_idx;
         o->m.over_val = h_over_val;
+        o->m.coldelta16 = h_tiny;
+        o->m.over_col = h_over_col;
         o->m.row_beg = h_beg;
         o->m.row_cnt = h_cnt;
         *out = &o->m;

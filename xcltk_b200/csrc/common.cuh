@@ -53,7 +53,8 @@ struct xg_ctx {
     std::string err;
     double timing[16] = {};
     bool coo_rows = true;                  // results carry the row array (else CSR: row_ptr only)
-    bool narrow_rows = false;              // ... and, with row_order 0, 16-bit column | 16-bit count per entry
+    int narrow_rows = 0;                   // ... and, with row_order 0: 1 = 16-bit column | 16-bit count per entry,
+                                           // 2 = 16 bits per entry (column delta | small count) + side list
     bool row_order = true;                 // basefc results sorted by row (else rows as completed + row_beg/row_cnt)
     // growable named scratch buffers (avoid cudaMalloc/cudaFree on every call)
     struct Buf {

@@ -75,7 +75,7 @@ int xg_set_option(xg_ctx *ctx, const char *name, int64_t value) {
         return XG_OK;
     }
     if (std::string(name) == "narrow_rows") {
-        ctx->narrow_rows = value != 0;
+        ctx->narrow_rows = value == 2 ? 2 : value != 0 ? 1 : 0;
         return XG_OK;
     }
     if (std::string(name) == "row_order") {

@@ -786,10 +786,11 @@ int write_rows_impl(const char *path, int32_t n_rows_in, const int64_t *row_beg,
                     return;
                 }
                 char *p = b.p.get();
+                Entry ent = entry;              // the thread's own copy: an entry reader may carry state along a row
                 for (int32_t r = r0; r < r1; r++)
                     for (int64_t k = row_beg[r]; k < row_beg[r] + row_cnt[r]; k++) {
-                        uint32_t c, v;
-                        entry(k, &c, &v);
+                        uint32_t c = 0, v = 0;
+                        ent(k, k == row_beg[r], &c, &v);
                         p = put_int(p, (uint32_t)out_row[r]);
                         *p++ = '\t';
                         p = put_int(p, c + 1u);
@@ -819,7 +820,7 @@ extern "C" int xg_write_mtx_rows(const char *path, int32_t n_rows_in, const int6
     if (!col || !val) return fail(XG_E_ARG, "xg_write_mtx: bad argument");
     try {
         return write_rows_impl(path, n_rows_in, row_beg, row_cnt, out_row, n_rows_out, n_cols,
-                               [=](int64_t k, uint32_t *c, uint32_t *v) {
+                               [=](int64_t k, bool, uint32_t *c, uint32_t *v) {
                                    *c = (uint32_t)col[k];
                                    *v = (uint32_t)val[k];
                                },
@@ -839,7 +840,7 @@ extern "C" int xg_write_mtx_rows16(const char *path, int32_t n_rows_in, const in
     for (int64_t i = 0; i < n_over; i++) over[over_idx[i]] = (uint32_t)over_val[i];
     const std::unordered_map<int64_t, uint32_t> *ov = &over;
     return write_rows_impl(path, n_rows_in, row_beg, row_cnt, out_row, n_rows_out, n_cols,
-                           [=](int64_t k, uint32_t *c, uint32_t *v) {
+                           [=](int64_t k, bool, uint32_t *c, uint32_t *v) {
                                const uint32_t w = colval16[k];
                                *c = w & 0xffffu;
                                *v = w >> 16;
@@ -849,6 +850,64 @@ extern "C" int xg_write_mtx_rows16(const char *path, int32_t n_rows_in, const in
                                }
                            },
                            n_threads);
+    } catch (const std::exception &e) {
+        return fail(XG_E_NOMEM, std::string("xg_write_mtx: ") + e.what());
+    }
+}
+
+// ... and from the 16-bit layout ("narrow_rows" 2): entry k = (column - previous column of the row - 1) << 4 | count,
+// the word 0 = look the entry up in the side list (every row's first entry is there).  The side list is sorted by
+// entry index once; a reader walks a row with a cursor into it.
+namespace {
+struct TinyReader {
+    const uint16_t *w;
+    const int64_t *idx;
+    const int32_t *col, *val;      // side list sorted by idx
+    int64_t n;
+    int64_t cur = 0;
+    uint32_t prev = 0;
+    bool bad = false;
+    void operator()(int64_t k, bool first, uint32_t *c, uint32_t *v) {
+        const uint32_t x = w[k];
+        if (x) {
+            prev += (x >> 4) + 1u;
+            *c = prev;
+            *v = x & 15u;
+            return;
+        }
+        if (first || cur >= n || idx[cur] != k) cur = std::lower_bound(idx, idx + n, k) - idx;
+        if (cur < n && idx[cur] == k) {
+            prev = (uint32_t)col[cur];
+            *v = (uint32_t)val[cur];
+            cur++;
+        } else {
+            bad = true;             // (an entry missing from the list: the device list overflowed)
+            *v = 0;
+        }
+        *c = prev;
+    }
+};
+}  // namespace
+
+extern "C" int xg_write_mtx_rows_tiny(const char *path, int32_t n_rows_in, const int64_t *row_beg, const int32_t *row_cnt,
+                                      const int32_t *out_row, int32_t n_rows_out, int32_t n_cols, const uint16_t *coldelta16,
+                                      int64_t n_over, const int64_t *over_idx, const int32_t *over_col,
+                                      const int32_t *over_val, int32_t n_threads) {
+    if (!coldelta16 || n_over < 0 || (n_over && (!over_idx || !over_col || !over_val)))
+        return fail(XG_E_ARG, "xg_write_mtx: bad argument");
+    try {
+        std::vector<int64_t> ord((size_t)n_over);
+        for (int64_t i = 0; i < n_over; i++) ord[(size_t)i] = i;
+        std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return over_idx[a] < over_idx[b]; });
+        std::vector<int64_t> s_idx((size_t)n_over);
+        std::vector<int32_t> s_col((size_t)n_over), s_val((size_t)n_over);
+        for (int64_t i = 0; i < n_over; i++) {
+            s_idx[(size_t)i] = over_idx[ord[(size_t)i]];
+            s_col[(size_t)i] = over_col[ord[(size_t)i]];
+            s_val[(size_t)i] = over_val[ord[(size_t)i]];
+        }
+        TinyReader rd{coldelta16, s_idx.data(), s_col.data(), s_val.data(), n_over};
+        return write_rows_impl(path, n_rows_in, row_beg, row_cnt, out_row, n_rows_out, n_cols, rd, n_threads);
     } catch (const std::exception &e) {
         return fail(XG_E_NOMEM, std::string("xg_write_mtx: ") + e.what());
     }

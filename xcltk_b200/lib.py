@@ -18,6 +18,7 @@ XG_TILE = 1024
 
 c_i32p = C.POINTER(C.c_int32)
 c_u32p = C.POINTER(C.c_uint32)
+c_u16p = C.POINTER(C.c_uint16)
 c_i64p = C.POINTER(C.c_int64)
 c_u64p = C.POINTER(C.c_uint64)
 c_u8p = C.POINTER(C.c_uint8)
@@ -69,7 +70,8 @@ class Coo(C.Structure):
     _fields_ = [("nnz", C.c_int64), ("n_rows", C.c_int32), ("n_cols", C.c_int32),
                 ("row", c_i32p), ("col", c_i32p), ("val", c_i32p), ("row_ptr", c_i64p),
                 ("row_beg", c_i64p), ("row_cnt", c_i32p),
-                ("colval16", c_u32p), ("n_over", C.c_int64), ("over_idx", c_i64p), ("over_val", c_i32p)]
+                ("colval16", c_u32p), ("n_over", C.c_int64), ("over_idx", c_i64p), ("over_val", c_i32p),
+                ("coldelta16", c_u16p), ("over_col", c_i32p)]
 
 
 class Snps(C.Structure):
@@ -111,6 +113,8 @@ SYMBOLS = {
                                     c_i32p, C.c_int32]),
     "xg_write_mtx_rows16": (C.c_int, [C.c_char_p, C.c_int32, c_i64p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_u32p,
                                       C.c_int64, c_i64p, c_i32p, C.c_int32]),
+    "xg_write_mtx_rows_tiny": (C.c_int, [C.c_char_p, C.c_int32, c_i64p, c_i32p, c_i32p, C.c_int32, C.c_int32, c_u16p,
+                                         C.c_int64, c_i64p, c_i32p, c_i32p, C.c_int32]),
     "xg_write_mtx": (C.c_int, [C.c_char_p, C.c_int32, c_i64p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p,
                                C.c_int32]),
     "xg_create": (C.c_int, [C.c_int32, C.POINTER(_P)]),
@@ -386,20 +390,48 @@ class RowSegments(object):
     demand.  This is what the Matrix-Market writer consumes (write_mtx_rows); to_sorted() gives
     (row, col, val) sorted by (row, col) for everything else."""
 
-    def __init__(self, row_beg, row_cnt, col, val, shape, cv16=None, over=None):
+    def __init__(self, row_beg, row_cnt, col, val, shape, cv16=None, over=None, tiny=None):
+        """tiny: the 16-bit layout (narrow_rows = 2): (column - previous column of the row - 1) << 4 | count per entry,
+        0 = the entry is in the side list `over` = (idx, val, col) -- every row's first entry is."""
         self.row_beg, self.row_cnt, self.shape = row_beg, row_cnt, shape
-        self._col, self._val, self.cv16, self.over = col, val, cv16, over
-        self.nnz = len(val) if cv16 is None else len(cv16)
+        self._col, self._val, self.cv16, self.over, self.tiny = col, val, cv16, over, tiny
+        self.nnz = len(tiny) if tiny is not None else len(val) if cv16 is None else len(cv16)
+
+    def _unpack_tiny(self):
+        w = np.asarray(self.tiny)
+        n = len(w)
+        val = (w & np.uint16(15)).astype(np.int32)
+        if n == 0:
+            self._col, self._val = np.zeros(0, np.int32), val
+            return
+        step = (w >> np.uint16(4)).astype(np.int64) + 1
+        esc = w == 0
+        step[esc] = 0
+        run = np.cumsum(step)
+        idx, oval, ocol = self.over
+        if int(esc.sum()) != len(idx):
+            raise XgError(-1, "16-bit result layout: side list does not match the escape words")
+        off = np.zeros(n, dtype=np.int64)
+        off[idx] = ocol.astype(np.int64) - run[idx]
+        last = np.maximum.accumulate(np.where(esc, np.arange(n, dtype=np.int64), 0))     # entry 0 starts a row
+        val[idx] = oval
+        self._col, self._val = (run + off[last]).astype(np.int32), val
 
     @property
     def col(self):
         if self._col is None:
-            self._col = (np.asarray(self.cv16) & np.uint32(0xffff)).astype(np.int32)
+            if self.tiny is not None:
+                self._unpack_tiny()
+            else:
+                self._col = (np.asarray(self.cv16) & np.uint32(0xffff)).astype(np.int32)
         return self._col
 
     @property
     def val(self):
         if self._val is None:
+            if self.tiny is not None:
+                self._unpack_tiny()
+                return self._val
             v = (np.asarray(self.cv16) >> np.uint32(16)).astype(np.int32)
             if self.over is not None and len(self.over[0]):
                 v[self.over[0]] = self.over[1]
@@ -420,7 +452,15 @@ def write_mtx_rows(path, seg, out_row, n_rows_out, n_threads=0):
     out_row = np.ascontiguousarray(out_row, dtype=np.int32)
     args = (path.encode(), len(seg.row_cnt), as_ptr(seg.row_beg, c_i64p), as_ptr(seg.row_cnt, c_i32p),
             as_ptr(out_row, c_i32p), int(n_rows_out), int(seg.shape[1]))
-    if seg.cv16 is not None:
+    if seg.tiny is not None:
+        tw = seg.tiny if seg.nnz else np.zeros(1, dtype=np.uint16)
+        oi = np.ascontiguousarray(seg.over[0], dtype=np.int64)
+        ov = np.ascontiguousarray(seg.over[1], dtype=np.int32)
+        oc = np.ascontiguousarray(seg.over[2], dtype=np.int32)
+        rc = lib.xg_write_mtx_rows_tiny(*args, as_ptr(tw, c_u16p), len(oi), as_ptr(oi, c_i64p) if len(oi) else None,
+                                        as_ptr(oc, c_i32p) if len(oi) else None, as_ptr(ov, c_i32p) if len(oi) else None,
+                                        n_threads)
+    elif seg.cv16 is not None:
         cv = seg.cv16 if seg.nnz else np.zeros(1, dtype=np.uint32)
         oi = np.ascontiguousarray(seg.over[0], dtype=np.int64) if seg.over is not None else np.zeros(0, np.int64)
         ov = np.ascontiguousarray(seg.over[1], dtype=np.int32) if seg.over is not None else np.zeros(0, np.int32)
@@ -446,6 +486,19 @@ def coo_to_numpy(lib, pcoo, copy_below=1 << 16, ctx_obj=None):
     if bool(m.row_beg):                       # rows in completion order
         row_beg = np_view(m.row_beg, shape[0], np.int64).copy()
         row_cnt = np_view(m.row_cnt, shape[0], np.int32).copy()
+        if bool(m.coldelta16):                # 16-bit entries
+            n_over = int(m.n_over)
+            views = [np_view(m.coldelta16, nnz, np.uint16), np_view(m.over_idx, n_over, np.int64),
+                     np_view(m.over_val, n_over, np.int32), np_view(m.over_col, n_over, np.int32)]
+            if nnz <= copy_below:
+                views = [v.copy() for v in views]
+                lib.xg_coo_free(pcoo)
+            else:                             # the side list holds about one entry per row: views, not copies
+                owner = _CooOwner(lib, pcoo, ctx_obj)
+                for k, v in enumerate(views):
+                    views[k] = v.view(_View)
+                    views[k]._owner = owner
+            return RowSegments(row_beg, row_cnt, None, None, shape, over=(views[1], views[2], views[3]), tiny=views[0])
         if bool(m.colval16):                  # narrow entries
             n_over = int(m.n_over)
             over = (np_view(m.over_idx, n_over, np.int64).copy(), np_view(m.over_val, n_over, np.int32).copy())
@@ -565,7 +618,8 @@ class Context(object):
     def basefc(self, dreads, gid, beg, end, cell_keys, n_samples, params, segments=False):
         """(row, col, val, shape) sorted by (row, col); segments=True: a RowSegments (rows in
         completion order, copied out while the counting is still running); segments="narrow": the
-        same with 32-bit packed entries when there are at most 65536 columns."""
+        same with 32-bit packed entries when there are at most 65536 columns; segments="tiny": 16-bit entries
+        (column delta | small count) + a side list -- a quarter of the bytes, for matrices of small counts."""
         gid = np.ascontiguousarray(gid, dtype=np.int32)
         beg = np.ascontiguousarray(beg, dtype=np.int32)
         end = np.ascontiguousarray(end, dtype=np.int32)
@@ -574,7 +628,7 @@ class Context(object):
         b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
         out = C.POINTER(Coo)()
         self.lib.xg_set_option(self.h, b"row_order", 0 if segments else 1)
-        self.lib.xg_set_option(self.h, b"narrow_rows", 1 if segments == "narrow" else 0)
+        self.lib.xg_set_option(self.h, b"narrow_rows", {"narrow": 1, "tiny": 2}.get(segments, 0))
         try:
             self._check(self.lib.xg_basefc(self.h, dreads.h, C.byref(f), C.byref(b), C.byref(params.c),
                                            C.byref(out)))
@@ -592,7 +646,7 @@ class Context(object):
         b = Barcodes(len(keys), as_ptr(keys, c_u64p), n_samples)
         out = C.POINTER(Coo)()
         self.lib.xg_set_option(self.h, b"row_order", 0 if segments else 1)
-        self.lib.xg_set_option(self.h, b"narrow_rows", 1 if segments == "narrow" else 0)
+        self.lib.xg_set_option(self.h, b"narrow_rows", {"narrow": 1, "tiny": 2}.get(segments, 0))
         try:
             self._check(self.lib.xg_basefc_host(self.h, host_reads.ptr, C.byref(f), C.byref(b), C.byref(params.c),
                                                 C.byref(out)))

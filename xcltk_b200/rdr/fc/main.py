@@ -312,7 +312,9 @@ def count_features(conf, batch=None):
             conf.shard_sizes = [len(s) for s in shards]
         else:
             params = engine.make_params(conf, batch.stats["max_aln_len"], with_include=True)
-            seg = "narrow" if getattr(conf, "row_segments", False) else False   # fc_core: rows as completed, packed
+            # fc_core: rows as completed, packed -- 16 bits per entry for the UMI counts of barcoded data (small numbers),
+            # column | count in 32 bits for read counts per sample
+            seg = ("tiny" if conf.use_barcodes() and conf.use_umi() else "narrow") if getattr(conf, "row_segments", False) else False
             if batch.dreads is None:       # pinned host batch: H2D streamed under the kernels
                 res = batch.ctx.basefc_host(batch.host, gid, beg, end, cell_keys, len(conf.samples), params,
                                             segments=seg)
