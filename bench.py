@@ -194,6 +194,8 @@ class Batch(object):
             from concurrent.futures import ThreadPoolExecutor
             from xcltk_b200 import lib
             self.ctx_baf = lib.Context(ctx.device)
+            if not os.environ.get("BENCH_NO_PRIORITY"):      # its short kernels go first whenever both contexts wait for SMs
+                self.ctx_baf.lib.xg_set_option(self.ctx_baf.h, b"stream_priority", 1)
             self.pool = ThreadPoolExecutor(1)
 
     # SNP filter of the baf half: min_count = 1, min_maf = 0 (the values xcltk baf passes, baf/pipeline.py:355)

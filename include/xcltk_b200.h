@@ -157,7 +157,8 @@ const char *xg_last_error(xg_ctx *ctx);
  * which saves a third of the device->host result copy.  "row_order" (default 1): 0 = basefc
  * results keep the device's completion order of the rows (see xg_coo), which lets the result
  * copy overlap the counting.  "narrow_rows" (default 0; 2 = the 16-bit layout, see xg_coo.coldelta16): 1 = with "row_order" 0, entries are packed
- * into 32 bits (see xg_coo).                                                                  */
+ * into 32 bits (see xg_coo).  "stream_priority" 1: the context's stream is recreated with the device's
+ * greatest priority (a context whose short kernels run beside another context's long ones).    */
 int xg_set_option(xg_ctx *ctx, const char *name, int64_t value);
 
 /* Host -> HBM copy of a decoded batch (the only cross-device traffic of the path).      */

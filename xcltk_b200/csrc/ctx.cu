@@ -82,6 +82,20 @@ int xg_set_option(xg_ctx *ctx, const char *name, int64_t value) {
         ctx->row_order = value != 0;
         return XG_OK;
     }
+    if (std::string(name) == "stream_priority") {
+        // 1: the context's stream gets the device's greatest priority -- for a context whose short kernels run
+        // beside another context's long ones on the same GPU (their CTAs are scheduled first whenever both wait)
+        if (!ctx->stream) return ctx->fail(XG_E_CUDA, "context has no device");
+        XG_CUDA(cudaSetDevice(ctx->device));
+        int least = 0, greatest = 0;
+        XG_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        cudaStream_t st = nullptr;
+        XG_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, value ? greatest : least));
+        XG_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaStreamDestroy(ctx->stream);
+        ctx->stream = st;
+        return XG_OK;
+    }
     return ctx->fail(XG_E_ARG, std::string("unknown option '") + name + "'");
 }
 
