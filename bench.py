@@ -647,7 +647,7 @@ def main():
             tb = json.load(fp).get("k_baf_scan")
         if tb:       # measured DRAM bytes per read of the profiled launch, scaled to this GPU's reads
             roofline_baf["traffic"] = tb["dram_bytes"] / tb["reads"] * batch.baf.n_reads
-            roofline_baf["traffic_source"] = traffic_src
+            roofline_baf["traffic_source"] = dict(traffic_src or {}, report=tb.get("report", (traffic_src or {}).get("report")))
     except Exception:
         pass
 

@@ -4,7 +4,7 @@
 #   python tools/summarize_ncu.py launches gpurun_out/rNN_launches.csv > profiles/rNN_launches_bench.txt
 #   python tools/summarize_ncu.py report gpurun_out/rNN_basefc.ncu-rep > profiles/rNN_k_basefc_ncu_full.txt   (count + finalize)
 #   python tools/ncu_lines.py gpurun_out/rNN_basefc.ncu-rep k_basefc_count > profiles/rNN_k_basefc_count_lines.txt
-#   python tools/make_traffic.py gpurun_out/rNN_basefc.ncu-rep 67108864 gpurun_out/rNN_baf.ncu-rep 50000000
+#   python tools/make_traffic.py gpurun_out/rNN_basefc.ncu-rep <reads of the captured launch> gpurun_out/rNN_baf.ncu-rep 50000000
 R=${1:-r02}
 set -x
 mkdir -p gpurun_out
