@@ -291,6 +291,12 @@ int xg_basefc(xg_ctx *ctx, const xg_dreads *reads, const xg_features *feats,
  * costs about max(H2D, kernels) instead of their sum.  This is the end-to-end entry point. */
 int xg_basefc_host(xg_ctx *ctx, const xg_reads *host, const xg_features *feats,
                    const xg_barcodes *cells, const xg_params *par, xg_coo **out);
+/* Matrix-Market text written on the device (replaces merge_mtx, rdr/fc/utils.py:54-94): the rows of the LAST xg_basefc call of this context with "row_order" 0
+ * are still in its staging area; they are formatted there (one warp per row, rows placed in input order by a scan)
+ * and the text leaves through pinned buffers that writer threads pwrite() in parallel.  The same bytes as the
+ * writers above (out_row[r]: 1-based output row of input row r, 0 = not emitted; n_rows_in = rows of that call). */
+int xg_basefc_write_mtx_device(xg_ctx *ctx, const char *path, int32_t n_rows_in, const int32_t *out_row,
+                               int32_t n_rows_out, int32_t n_threads);
 
 /* baf phase 1: replaces plp_snp() up to mcnt.stat() (baf/fc/core.py:198-237; first-read-wins
  * per (SNP, cell, UMI): baf/fc/mcount.py:109-127; allele: :39-60 + utils/sam.py:4-40).

@@ -336,6 +336,17 @@ def test_basefc_row_segments_equal_sorted_result(gpu_ctx, fc_batch, tmp_path):
     assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "c.mtx"), "rb").read()
     lib.write_mtx_rows(str(tmp_path / "d.mtx"), seg_t, out_row, int(emitted.sum()), n_threads=3)
     assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / "d.mtx"), "rb").read()
+    # ... and the text formatted on the device from the staging area of the last call (every result layout)
+    for k, mode in enumerate((True, "narrow", "tiny")):
+        gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, p, segments=mode)
+        gpu_ctx.basefc_write_mtx(str(tmp_path / ("g%d.mtx" % k)), out_row, int(emitted.sum()), n_threads=2 + k)
+        assert open(str(tmp_path / "a.mtx"), "rb").read() == open(str(tmp_path / ("g%d.mtx" % k)), "rb").read()
+    gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, p)          # a sorted result leaves no staged rows
+    with pytest.raises(lib.XgError):
+        gpu_ctx.basefc_write_mtx(str(tmp_path / "x.mtx"), out_row, int(emitted.sum()))
+    seg = gpu_ctx.basefc(w.dreads, w.gid, w.beg, w.end, w.cell_keys, 2000, p, segments=True)
+    with pytest.raises(lib.XgError):                      # a non-empty row without an output row
+        gpu_ctx.basefc_write_mtx(str(tmp_path / "x.mtx"), np.zeros(n, np.int32), 0)
 
 
 def test_basefc_row_segments_degenerate_inputs(gpu_ctx, fc_batch):

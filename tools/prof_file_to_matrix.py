@@ -30,6 +30,14 @@ for k in range(2):
     t = time.perf_counter()
     fc_wrapper(bam, bc_fn, ft_fn, os.path.join(td, "warm%d" % k), ncores=os.cpu_count() or 1)
     print("call %d: %.1f ms" % (k, 1e3 * (time.perf_counter() - t)), flush=True)
+for mode in ("0", "1", "0", "1"):              # Matrix-Market text on the host / on the device
+    os.environ["XCLTK_B200_DEVICE_MTX"] = mode
+    t = time.perf_counter()
+    fc_wrapper(bam, bc_fn, ft_fn, os.path.join(td, "ab" + mode), ncores=os.cpu_count() or 1)
+    print("XCLTK_B200_DEVICE_MTX=%s: %.1f ms" % (mode, 1e3 * (time.perf_counter() - t)), flush=True)
+os.environ.pop("XCLTK_B200_DEVICE_MTX")
+if os.environ.get("PROF_AB_ONLY"):
+    sys.exit(0)
 pr = cProfile.Profile()
 pr.enable()
 fc_wrapper(bam, bc_fn, ft_fn, os.path.join(td, "prof"), ncores=os.cpu_count() or 1)

@@ -17,12 +17,16 @@
 // memory and writes the row's non-zeros in column order.  What does not fit a pair word (or a segment) keeps an
 // open-addressing (cell, UMI) set in global memory (128-bit CAS).  Features are counted independently (a read
 // overlapping k features is evaluated k times), exactly as the reference does.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <iterator>
 #include <map>
+#include <thread>
 
 #include "compact.cuh"
 
@@ -1644,6 +1648,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         return ctx->fail(XG_E_ARG, "xg_basefc: barcode mode needs one key per column");
     if (rd->mapped) return ctx->fail(XG_E_ARG, "xg_basefc: needs an uploaded batch (xg_upload_reads), not xg_map_reads");
     XG_CUDA(cudaSetDevice(ctx->device));
+    ctx->fx_res_valid = false;
     for (double &t : ctx->timing) t = 0;
     int launches = 0;
     const bool dbg_sync = getenv("XG_DEBUG_SYNC") && atoi(getenv("XG_DEBUG_SYNC")) != 0;
@@ -2225,6 +2230,10 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
         cudaEventSynchronize(ctx->ev[3]);
         ctx->pinned_put(h_cur);
         ctx->fx_nnz_hint = nnz;
+        ctx->fx_res_valid = true;
+        ctx->fx_res_nnz = nnz;
+        ctx->fx_res_rows = n_rows;
+        ctx->fx_res_cols = n_cols;
         ctx->timing[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_tail).count();
         o->m.nnz = nnz;
         o->m.n_rows = n_rows;
@@ -2331,4 +2340,169 @@ extern "C" int xg_basefc_host(xg_ctx *ctx, const xg_reads *h, const xg_features 
     cudaStreamSynchronize(ctx->stream);
     xg_dreads_free(ctx, d);
     return rc;
+}
+
+// ---- Matrix-Market text on the device ----------------------------------------------------------
+// Replaces merge_mtx (rdr/fc/utils.py:54-94) for the rows of the last xg_basefc call with "row_order" 0, which are
+// still in the staging area: one warp per row sizes its lines ("<output row>\t<column + 1>\t<count>\n"), a scan
+// places the rows in input order, one warp per row writes its lines, and the text leaves through a ring of pinned
+// buffers that writer threads pwrite() at their offsets (several at a time: the page cache takes them in parallel).
+namespace {
+__device__ __forceinline__ int mtx_digits(uint32_t v) {
+    return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6
+           : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
+}
+__device__ __forceinline__ char *mtx_put(char *p, uint32_t v, int nd) {
+    for (int k = nd - 1; k >= 0; k--) {
+        p[k] = (char)('0' + v % 10u);
+        v /= 10u;
+    }
+    return p + nd;
+}
+__global__ void k_mtx_row_bytes(int32_t n_rows, const int64_t *seg_base, const int32_t *seg_nnz, const int32_t *st_col,
+                                const int32_t *st_val, const int32_t *out_row, int32_t *row_bytes) {
+    const int r = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const int32_t n = seg_nnz[r], orow = out_row[r];
+    int bytes = 0;
+    if (n > 0 && orow > 0) {
+        const int64_t b = seg_base[r];
+        const int dr = mtx_digits((uint32_t)orow) + 3;
+        for (int k = lane; k < n; k += 32) bytes += dr + mtx_digits((uint32_t)st_col[b + k] + 1u) + mtx_digits((uint32_t)st_val[b + k]);
+    }
+    for (int d = 16; d > 0; d >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, d);
+    if (lane == 0) row_bytes[r] = bytes;
+}
+__global__ void k_mtx_write(int32_t n_rows, const int64_t *seg_base, const int32_t *seg_nnz, const int32_t *st_col,
+                            const int32_t *st_val, const int32_t *out_row, const int64_t *row_off, char *text) {
+    const int r = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (r >= n_rows) return;
+    const int32_t n = seg_nnz[r], orow = out_row[r];
+    if (n <= 0 || orow <= 0) return;
+    const int64_t b = seg_base[r];
+    const int dr = mtx_digits((uint32_t)orow);
+    int64_t at = row_off[r];
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int k = k0 + lane;
+        uint32_t c = 0, v = 0;
+        int dc = 0, dv = 0, len = 0;
+        if (k < n) {
+            c = (uint32_t)st_col[b + k] + 1u;
+            v = (uint32_t)st_val[b + k];
+            dc = mtx_digits(c);
+            dv = mtx_digits(v);
+            len = dr + dc + dv + 3;
+        }
+        int incl = len;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        if (k < n) {
+            char *p = text + at + (incl - len);
+            p = mtx_put(p, (uint32_t)orow, dr);
+            *p++ = '\t';
+            p = mtx_put(p, c, dc);
+            *p++ = '\t';
+            p = mtx_put(p, v, dv);
+            *p = '\n';
+        }
+        at += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+}  // namespace
+
+extern "C" int xg_basefc_write_mtx_device(xg_ctx *ctx, const char *path, int32_t n_rows_in, const int32_t *out_row,
+                                          int32_t n_rows_out, int32_t n_threads) {
+    if (!ctx || !ctx->stream) return ctx ? ctx->fail(XG_E_CUDA, "context has no device") : XG_E_ARG;
+    if (!path || !out_row || n_rows_in < 0) return ctx->fail(XG_E_ARG, "xg_basefc_write_mtx_device: bad argument");
+    if (!ctx->fx_res_valid || ctx->fx_res_rows != n_rows_in)
+        return ctx->fail(XG_E_ARG, "xg_basefc_write_mtx_device: no basefc result with \"row_order\" 0 of that many rows on this context");
+    XG_CUDA(cudaSetDevice(ctx->device));
+    const int32_t n_rows = n_rows_in;
+    const int64_t *seg_base = (const int64_t *)ctx->scratch["fx_seg_base"].p;
+    const int32_t *seg_nnz = (const int32_t *)ctx->scratch["fx_seg_nnz"].p;
+    const int32_t *st_col = (const int32_t *)ctx->scratch["fx_st_col"].p;
+    const int32_t *st_val = (const int32_t *)ctx->scratch["fx_st_val"].p;
+    XG_GET(d_out_row, int32_t, "mx_out_row", n_rows + 1);
+    XG_GET(d_row_bytes, int32_t, "mx_row_bytes", n_rows + 1);
+    XG_GET(d_row_off, int64_t, "mx_row_off", n_rows + 2);
+    for (int32_t r = 0; r < n_rows; r++)
+        if (out_row[r] < 0 || out_row[r] > n_rows_out) return ctx->fail(XG_E_ARG, "xg_basefc_write_mtx_device: output row out of range");
+    XG_CUDA(cudaMemcpyAsync(d_out_row, out_row, sizeof(int32_t) * (size_t)n_rows, cudaMemcpyHostToDevice, ctx->stream));
+    long long total = 0;
+    const unsigned grid = (unsigned)(((unsigned long long)n_rows * 32 + 255) / 256);
+    if (n_rows > 0) {
+        k_mtx_row_bytes<<<grid, 256, 0, ctx->stream>>>(n_rows, seg_base, seg_nnz, st_col, st_val, d_out_row, d_row_bytes);
+        k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(d_row_bytes, d_row_off, n_rows);
+        XG_CUDA(cudaMemcpyAsync(&total, d_row_off + n_rows, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    char *d_text = (char *)ctx->get("mx_text", (size_t)total + 64);
+    if (!d_text) return XG_E_CUDA;
+    if (total > 0) k_mtx_write<<<grid, 256, 0, ctx->stream>>>(n_rows, seg_base, seg_nnz, st_col, st_val, d_out_row, d_row_off, d_text);
+    XG_CUDA(cudaGetLastError());
+    // every staged entry of an emitted row is a line: a row with entries but no output row would be lost
+    char header[160];
+    // (the count of lines = entries of the rows that have an output row; checked against the result's nnz by the caller)
+    std::vector<int32_t> h_cnt((size_t)n_rows + 1);
+    XG_CUDA(cudaMemcpyAsync(h_cnt.data(), seg_nnz, sizeof(int32_t) * (size_t)n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+    XG_CUDA(cudaStreamSynchronize(ctx->stream));
+    long long lines = 0;
+    for (int32_t r = 0; r < n_rows; r++) {
+        if (h_cnt[(size_t)r] > 0 && out_row[r] <= 0) return ctx->fail(XG_E_ARG, "xg_write_mtx: non-empty row without an output row");
+        lines += h_cnt[(size_t)r];
+    }
+    const int hl = snprintf(header, sizeof header, "%%%%MatrixMarket matrix coordinate integer general\n%%%%\n%d\t%d\t%lld\n",
+                            n_rows_out, ctx->fx_res_cols, lines);
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return ctx->fail(XG_E_IO, std::string("cannot write '") + path + "'");
+    bool ok = write(fd, header, (size_t)hl) == hl;
+    // ring of pinned buffers: the copy of chunk c + 1 runs while the writers of the chunks before it pwrite()
+    // (a small matrix takes one small buffer: pinning memory costs more than writing it)
+    const size_t CHUNK_B = std::min<size_t>((size_t)32 << 20, ((size_t)std::max<long long>(total, 1) + 4095) & ~(size_t)4095);
+    const int n_buf = (int)std::max<long long>(1, std::min<long long>(std::min(n_threads > 0 ? n_threads : 4, 8),
+                                                                     (total + (long long)CHUNK_B - 1) / (long long)CHUNK_B));
+    std::vector<char *> buf((size_t)n_buf, nullptr);
+    std::vector<std::thread> wr((size_t)n_buf);
+    std::vector<char> failed((size_t)n_buf, 0);
+    for (int k = 0; k < n_buf; k++)
+        if (!(buf[(size_t)k] = (char *)ctx->pinned_get(CHUNK_B))) ok = false;
+    int c = 0;
+    for (long long off = 0; ok && off < total; off += (long long)CHUNK_B, c++) {
+        const int k = c % n_buf;
+        if (wr[(size_t)k].joinable()) wr[(size_t)k].join();
+        const size_t len = (size_t)std::min<long long>((long long)CHUNK_B, total - off);
+        if (cudaMemcpyAsync(buf[(size_t)k], d_text + off, len, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            ok = false;
+            break;
+        }
+        char *src = buf[(size_t)k];
+        char *flag = &failed[(size_t)k];
+        const long long file_off = (long long)hl + off;
+        wr[(size_t)k] = std::thread([fd, src, len, file_off, flag] {
+            size_t done = 0;
+            while (done < len) {
+                const ssize_t w = pwrite(fd, src + done, len - done, (off_t)(file_off + (long long)done));
+                if (w <= 0) {
+                    *flag = 1;
+                    return;
+                }
+                done += (size_t)w;
+            }
+        });
+    }
+    for (auto &t : wr)
+        if (t.joinable()) t.join();
+    for (int k = 0; k < n_buf; k++) {
+        if (buf[(size_t)k]) ctx->pinned_put(buf[(size_t)k]);
+        if (failed[(size_t)k]) ok = false;
+    }
+    if (close(fd) != 0) ok = false;
+    if (!ok) {
+        cudaGetLastError();
+        return ctx->fail(XG_E_IO, std::string("short write on '") + path + "'");
+    }
+    return XG_OK;
 }

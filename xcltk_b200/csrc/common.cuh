@@ -47,6 +47,11 @@ struct xg_ctx {
     cudaStream_t copy_stream = nullptr;    // xg_basefc_host: H2D of the next epoch
     cudaStream_t d2h_stream = nullptr;     // "row_order" 0: result rows copied out while later epochs run
     int64_t fx_nnz_hint = 0;               // nnz of the last basefc call (sizes the pinned result up front)
+    // the rows of the last basefc call with "row_order" 0 are still in the staging area (scratch "fx_st_col" /
+    // "fx_st_val", places in "fx_seg_base" / "fx_seg_nnz") until the next call: xg_basefc_write_mtx_device formats them
+    bool fx_res_valid = false;
+    int64_t fx_res_nnz = 0;
+    int32_t fx_res_rows = 0, fx_res_cols = 0;
     cudaStream_t aux[3] = {};              // overlapped epochs: zero, finalize, second count stream
     cudaEvent_t ev[8] = {};
     std::vector<cudaEvent_t> ev_pool;     // per-epoch timing events

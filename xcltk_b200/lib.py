@@ -142,6 +142,7 @@ SYMBOLS = {
                                C.POINTER(C.POINTER(Coo)), C.POINTER(C.POINTER(Coo)),
                                C.POINTER(C.POINTER(Coo))]),
     "xg_baf_state_free": (None, [_P, _P]),
+    "xg_basefc_write_mtx_device": (C.c_int, [_P, C.c_char_p, C.c_int32, c_i32p, C.c_int32, C.c_int32]),
     "xg_baf_fc": (C.c_int, [_P, _P, C.POINTER(Snps), C.POINTER(Barcodes), C.POINTER(Params), C.POINTER(SnpFilter),
                             C.c_int32, c_i64p, c_i32p, c_u8p, C.c_int32, c_i64p, c_u8p,
                             C.POINTER(C.POINTER(Coo)), C.POINTER(C.POINTER(Coo)), C.POINTER(C.POINTER(Coo))]),
@@ -635,6 +636,14 @@ class Context(object):
         finally:
             self.lib.xg_set_option(self.h, b"row_order", 1)
         return coo_to_numpy(self.lib, out, ctx_obj=self)
+
+    def basefc_write_mtx(self, path, out_row, n_rows_out, n_threads=0):
+        """Matrix-Market text of the LAST basefc(..., segments=...) result of this context, formatted on the device
+        from the rows still in its staging area (xg_basefc_write_mtx_device): out_row[r] = 1-based output row of
+        input row r, 0 = not emitted."""
+        out_row = np.ascontiguousarray(out_row, dtype=np.int32)
+        self._check(self.lib.xg_basefc_write_mtx_device(self.h, path.encode(), len(out_row), as_ptr(out_row, c_i32p),
+                                                        int(n_rows_out), int(n_threads)))
 
     def basefc_host(self, host_reads, gid, beg, end, cell_keys, n_samples, params, segments=False):
         """basefc straight from a pinned host batch: H2D streamed under the counting kernels."""

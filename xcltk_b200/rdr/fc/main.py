@@ -324,6 +324,7 @@ def count_features(conf, batch=None):
             conf.last_timing = batch.ctx.timing()
             if seg:
                 conf.last_stats = dict(batch.stats)
+                conf.last_ctx = batch.ctx            # its staging area still holds the rows (device-side MTX text)
                 return res
             row, col, val, _shape = res
         conf.last_stats = dict(batch.stats)
@@ -359,8 +360,14 @@ def fc_core(conf):
                          for r, e in zip(regs, emitted) if e))
     if isinstance(res, lib.RowSegments):
         out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
-        lib.write_mtx_rows(conf.out_mtx_fn, res, out_row, int(np.count_nonzero(emitted)),
-                           engine.n_decode_threads(conf.nproc))
+        ctx = getattr(conf, "last_ctx", None)
+        if ctx is not None and os.environ.get("XCLTK_B200_DEVICE_MTX", "1") not in ("0", "", "no", "false"):
+            # merge_mtx on the device: the rows are still in the context's staging area
+            ctx.basefc_write_mtx(conf.out_mtx_fn, out_row, int(np.count_nonzero(emitted)),
+                                 engine.n_decode_threads(conf.nproc))
+        else:
+            lib.write_mtx_rows(conf.out_mtx_fn, res, out_row, int(np.count_nonzero(emitted)),
+                               engine.n_decode_threads(conf.nproc))
     else:
         engine.write_mtx(conf.out_mtx_fn, n_reg, row, col, val, emitted, len(conf.samples),
                          engine.n_decode_threads(conf.nproc))
