@@ -678,8 +678,7 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
     XG_GET(d_cand, ScanCand, "bf_cand", (size_t)scan_grid * cand_cap + 1);
     XG_GET(d_npairs, unsigned long long, "bf_npairs", 2);
     XG_GET(d_totals, unsigned long long, "bf_totals", (size_t)snps->n * 5 + 1);
-    XG_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->timing[8] = ms_since(t_call);          // host: SNP table (cached), barcode table, buffers
+    ctx->timing[8] = ms_since(t_call);          // host: SNP table (cached), barcode table, buffers (nothing to wait for)
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
     if (rd->n_tiles > 0 && any_snp) {
@@ -764,6 +763,16 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
         cudaMemcpyAsync(h_tot, d_totals, sizeof(unsigned long long) * (size_t)snps->n * 5, cudaMemcpyDeviceToHost,
                         ctx->stream);
     cudaEventRecord(ctx->ev[5], ctx->stream);
+    if (!totals) {
+        // xg_baf_fc: the totals stay on the device and the count follows on the same stream -- nothing to wait for
+        // here (a call that has a short kernel's worth of work pays every synchronisation in full when another
+        // context keeps the GPU busy); the caller reads the scan's time from ev[1] / ev[2] at its end
+        ctx->timing[2] = launches;
+        ctx->timing[6] = (double)n_pairs;
+        ctx->timing[9] = ctx->timing[10] = ms_since(t_call);
+        *state = st;
+        return XG_OK;
+    }
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         if (h_tot) ctx->pinned_put(h_tot);
@@ -867,8 +876,7 @@ static int baf_count_impl(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, cons
     XG_GET(work, unsigned int, "bf_work", 4);
     XG_GET(seg_base, int64_t, "bf_seg_base", 3 * (size_t)n_regions + 1);
     XG_GET(seg_nnz, int32_t, "bf_seg_nnz", 3 * (size_t)n_regions + 1);
-    XG_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->timing[8] = ms_since(t_call);          // host: region lists (cached), hap / keep upload, buffers
+    ctx->timing[8] = ms_since(t_call);          // host: region lists (cached), hap / keep upload, buffers (nothing to wait for)
 
     cudaEventRecord(ctx->ev[0], ctx->stream);
     unsigned grid = (unsigned)((st->n_pairs + 255) / 256);
@@ -962,6 +970,8 @@ extern "C" int xg_baf_fc(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *snps, 
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
     };
     xg_baf_state *st = nullptr;
+    XG_CUDA(cudaSetDevice(ctx->device));
+    cudaEventRecord(ctx->ev[6], ctx->stream);
     int rc = xg_baf_pileup(ctx, rd, snps, cells, par, totals, &st);
     if (rc) return rc;
     double tp[16];
@@ -988,8 +998,16 @@ extern "C" int xg_baf_fc(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *snps, 
     const double tc9 = ctx->timing[9];
     ctx->timing[7] = ctx->timing[6];            // (region, cell, UMI) candidates
     ctx->timing[6] = tp[6];                     // (read, SNP) pairs
-    ctx->timing[0] += tp[0];
-    ctx->timing[1] = tp[1];
+    if (totals) {
+        ctx->timing[0] += tp[0];
+        ctx->timing[1] = tp[1];
+    } else {                                    // the pileup did not wait: its events have passed by now
+        float t_all = 0, t_scan = 0;
+        cudaEventElapsedTime(&t_all, ctx->ev[6], ctx->ev[3]);
+        cudaEventElapsedTime(&t_scan, ctx->ev[1], ctx->ev[2]);
+        ctx->timing[0] = t_all;
+        ctx->timing[1] = t_scan;
+    }
     ctx->timing[2] += tp[2] + 1;
     ctx->timing[4] += tp[4];
     ctx->timing[8] = ms_pileup;
