@@ -600,17 +600,7 @@ extern "C" int xg_baf_pileup(xg_ctx *ctx, const xg_dreads *rd, const xg_snps *sn
     // table depends on the SNP list only: it is kept on the device while the caller passes
     // the same list (hash of the arrays).
     uint64_t sh = 1469598103934665603ull;
-    auto mixh = [&](const void *p, size_t n) {
-        const uint8_t *q = (const uint8_t *)p;
-        size_t k = 0;
-        for (; k + 8 <= n; k += 8) {               // word-wise FNV-style mix
-            uint64_t wv;
-            memcpy(&wv, q + k, 8);
-            sh = (sh ^ wv) * 1099511628211ull;
-            sh ^= sh >> 29;
-        }
-        for (; k < n; k++) sh = (sh ^ q[k]) * 1099511628211ull;
-    };
+    auto mixh = [&](const void *p, size_t n) { xg_mix_bytes(sh, p, n); };
     mixh(&n_gid, sizeof n_gid);
     mixh(&snps->n, sizeof snps->n);
     mixh(snps->gid, sizeof(int32_t) * (size_t)snps->n);
@@ -815,17 +805,7 @@ static int baf_count_impl(xg_ctx *ctx, xg_baf_state *st, int32_t n_regions, cons
     // invert region -> SNP lists (cached on the device while the caller passes the same lists)
     const int64_t n_mem = reg_ptr[n_regions];
     uint64_t sh = 1469598103934665603ull;
-    auto mixh = [&](const void *p, size_t n) {
-        const uint8_t *q = (const uint8_t *)p;
-        size_t k = 0;
-        for (; k + 8 <= n; k += 8) {
-            uint64_t wv;
-            memcpy(&wv, q + k, 8);
-            sh = (sh ^ wv) * 1099511628211ull;
-            sh ^= sh >> 29;
-        }
-        for (; k < n; k++) sh = (sh ^ q[k]) * 1099511628211ull;
-    };
+    auto mixh = [&](const void *p, size_t n) { xg_mix_bytes(sh, p, n); };
     mixh(&n_snps, sizeof n_snps);
     mixh(&n_regions, sizeof n_regions);
     mixh(reg_ptr, sizeof(int64_t) * ((size_t)n_regions + 1));

@@ -1670,17 +1670,7 @@ static int basefc_run(xg_ctx *ctx, const xg_dreads *rd, const xg_reads *src, con
     // the interval index depends on the features only: reuse it (host copy and the uploaded
     // device arrays, which live in named scratch buffers) while the caller passes the same set
     uint64_t fh = 1469598103934665603ull;
-    auto mixh = [&](const void *p, size_t n) {
-        const uint8_t *b = (const uint8_t *)p;
-        size_t k = 0;
-        for (; k + 8 <= n; k += 8) {               // word-wise FNV-style mix
-            uint64_t wv;
-            memcpy(&wv, b + k, 8);
-            fh = (fh ^ wv) * 1099511628211ull;
-            fh ^= fh >> 29;
-        }
-        for (; k < n; k++) fh = (fh ^ b[k]) * 1099511628211ull;
-    };
+    auto mixh = [&](const void *p, size_t n) { xg_mix_bytes(fh, p, n); };
     mixh(&n_gid, sizeof n_gid);
     mixh(&feats->n, sizeof feats->n);
     mixh(feats->gid, sizeof(int32_t) * (size_t)feats->n);
