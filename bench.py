@@ -370,7 +370,7 @@ def file_legs(ctx, args):
             engine_write(exp_fn, len(gid), o_row, o_col, o_val, np.ones(len(gid), dtype=bool), n_cells, n_thr)
             want = md5(exp_fn)
             best = None
-            for k in range(2):
+            for k in range(3):            # (the page cache's write-back makes single calls jumpy: +/- 100 ms and more)
                 out_dir = os.path.join(td, "%s.out%d" % (name, k))
                 t = time.perf_counter()
                 ret = fc_wrapper(bam, bc_fn, ft_fn, out_dir, ncores=n_thr)
@@ -462,7 +462,7 @@ def file_legs(ctx, args):
                               "call_ms": 1e3 * best, "matrix_md5": got, "matches_oracle_text": bool(got == md5(exp_fn)),
                               "nnz": int(len(o_val)), "bam_write_s": t_write,
                               "shape": "%d features x %d cells, sample IDs, query-name keys" % (len(gid), n_bams)}
-    out["note"] = ("fc_wrapper(): BAM file -> features.tsv, barcodes.tsv, matrix.mtx on disk, best of 2; the BAMs hold "
+    out["note"] = ("fc_wrapper(): BAM file -> features.tsv, barcodes.tsv, matrix.mtx on disk, best of 2-3; the BAMs hold "
                    "the records of device-generated batches (xg_write_bam, htslib block layout, level 1)")
     return out, host_dec, dev_dec
 

@@ -30,7 +30,7 @@ for k in range(2):
     t = time.perf_counter()
     fc_wrapper(bam, bc_fn, ft_fn, os.path.join(td, "warm%d" % k), ncores=os.cpu_count() or 1)
     print("call %d: %.1f ms" % (k, 1e3 * (time.perf_counter() - t)), flush=True)
-for mode in ("0", "1", "0", "1"):              # Matrix-Market text on the host / on the device
+for mode in ("0", "1") * int(os.environ.get("PROF_AB_ROUNDS", "2")):              # Matrix-Market text on the host / on the device
     os.environ["XCLTK_B200_DEVICE_MTX"] = mode
     t = time.perf_counter()
     fc_wrapper(bam, bc_fn, ft_fn, os.path.join(td, "ab" + mode), ncores=os.cpu_count() or 1)
