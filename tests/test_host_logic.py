@@ -303,6 +303,45 @@ def test_write_mtx_rows_tiny_delta_entries_and_side_list(tmp_path):
     assert open(str(tmp_path / "e.mtx")).read().splitlines()[-1] == "3\t10\t0"
 
 
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 2 ** 32 - 1), st.integers(1, 60), st.sampled_from([7, 300, 5000, 70000, 1 << 20]),
+       st.sampled_from([3, 15, 16, 70000]))
+def test_tiny_layout_round_trip_property(seed, n_rows, n_cols, max_val):
+    """any matrix survives the 16-bit layout: encode as k_pack_rows_tiny does, decode with RowSegments, write with
+    xg_write_mtx_rows_tiny -- equal to the plain layout entry for entry and byte for byte"""
+    import tempfile
+    from xcltk_b200 import lib
+    rng = np.random.RandomState(seed)
+    cnt = rng.randint(0, min(n_cols, 50) + 1, size=n_rows).astype(np.int32)
+    order = rng.permutation(n_rows)
+    beg = np.zeros(n_rows, dtype=np.int64)
+    at = 0
+    for r in order:
+        beg[r] = at
+        at += int(cnt[r])
+    nnz = at
+    col = np.zeros(nnz, dtype=np.int32)
+    for r in range(n_rows):
+        col[beg[r]:beg[r] + cnt[r]] = np.sort(rng.choice(n_cols, cnt[r], replace=False))
+    val = rng.randint(1, max_val + 1, size=nnz).astype(np.int32)
+    first = np.zeros(nnz, dtype=bool)
+    first[beg[cnt > 0]] = True
+    d = col.astype(np.int64) - np.concatenate([[0], col[:-1]]) - 1
+    fits = ~first & (d >= 0) & (d <= 4094) & (val <= 15)
+    w = np.where(fits, (d << 4) | val, 0).astype(np.uint16)
+    idx = np.nonzero(~fits)[0].astype(np.int64)
+    perm = rng.permutation(len(idx))
+    tiny = lib.RowSegments(beg, cnt, None, None, (n_rows, n_cols), over=(idx[perm], val[idx][perm], col[idx][perm]), tiny=w)
+    plain = lib.RowSegments(beg, cnt, col, val, (n_rows, n_cols))
+    assert np.array_equal(tiny.col, col) and np.array_equal(tiny.val, val)
+    emitted = cnt > 0
+    out_row = np.where(emitted, np.cumsum(emitted), 0).astype(np.int32)
+    with tempfile.TemporaryDirectory() as td:
+        lib.write_mtx_rows(os.path.join(td, "a.mtx"), plain, out_row, int(emitted.sum()), 2)
+        lib.write_mtx_rows(os.path.join(td, "b.mtx"), tiny, out_row, int(emitted.sum()), 3)
+        assert open(os.path.join(td, "a.mtx"), "rb").read() == open(os.path.join(td, "b.mtx"), "rb").read()
+
+
 def test_genomic_chunks_partition_the_library():
     """bench.py --scaling strong: the chunks' features are a disjoint cover of the feature list, and every chunk's
     read range reaches from HALO_BP before its first feature to the end of its last one (reads are sorted)."""
